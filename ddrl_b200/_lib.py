@@ -1,0 +1,91 @@
+"""ctypes binding of libddrl_b200.so — the same stub INTEGRATION.md gives a reference maintainer.
+
+There is no CPU fallback: if the shared library is missing or a launch fails, every op raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libddrl_b200.so")
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+c_i64p = C.c_void_p
+c_f64p = C.c_void_p
+c_u8p = C.c_void_p
+c_stream = C.c_void_p
+
+
+class PPOHyper(C.Structure):
+    _fields_ = [("clip_param", C.c_float), ("vf_clip_param", C.c_float), ("vf_loss_coeff", C.c_float),
+                ("entropy_coeff", C.c_float), ("inv_global_mb", C.c_float)]
+
+
+# name -> (restype, argtypes); mirrors include/ddrl_b200.h one to one (tests check every symbol).
+PROTOTYPES = {
+    "ddrl_last_error": (C.c_char_p, []),
+    "ddrl_abi_version": (C.c_int, []),
+    "ddrl_launch_count": (C.c_int64, []),
+    "ddrl_fcnet_num_params": (C.c_int, [C.c_int, C.c_int]),
+    "ddrl_filter_ws_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
+    "ddrl_filter_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_i64p, c_f64p, c_f64p,
+                                     c_f64p, C.c_void_p, c_stream]),
+    "ddrl_filter_num_partials": (C.c_int, [C.c_int64]),
+    "ddrl_filter_partial": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, c_stream]),
+    "ddrl_filter_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, c_i64p, c_f64p, c_f64p, c_f64p,
+                                    c_stream]),
+    "ddrl_fcnet_forward": (C.c_int, [c_f32p, c_f32p, c_f64p, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                     c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ddrl_gae_ws_bytes": (C.c_int64, [C.c_int, C.c_int64]),
+    "ddrl_gae": (C.c_int, [c_f32p, c_f32p, c_u8p, c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
+                           C.c_float, c_f32p, c_f32p, c_f64p, C.c_void_p, c_stream]),
+    "ddrl_adv_standardize": (C.c_int, [c_f32p, c_f64p, C.c_int, C.c_int64, c_stream]),
+    "ddrl_gather_rows": (C.c_int, [c_f32p, c_i32p, C.c_int, C.c_int64, C.c_int, c_f32p, c_stream]),
+    "ddrl_ppo_train_step": (C.c_int, [c_f32p] * 10 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
+                                                     C.c_int64, c_i32p, c_f32p, C.POINTER(PPOHyper), C.c_int,
+                                                     c_f32p, c_f64p, c_stream]),
+    "ddrl_ppo_loss_grad": (C.c_int, [c_f32p] * 8 + [C.c_int, C.c_int64, C.c_int, c_f32p, C.POINTER(PPOHyper), C.c_int,
+                                                    c_f32p, c_f32p, c_f64p, c_stream]),
+    "ddrl_grad_reduce": (C.c_int, [c_f32p, c_f64p, C.c_int, C.c_int, C.c_int, c_f32p, c_f64p, c_i32p, c_stream]),
+    "ddrl_clip_adam": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_float, c_f32p, c_i32p, c_i32p, c_stream]),
+    "ddrl_graphnet_num_params": (C.c_int, [C.c_int]),
+    "ddrl_graphnet_forward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p,
+                                        c_stream]),
+    "ddrl_graphnet_backward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int,
+                                         C.c_int, c_f32p, c_stream]),
+    "ddrl_gcn_forward": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int, C.c_int, C.c_int, c_f32p,
+                                   c_stream]),
+    "ddrl_dg_sample": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p, c_stream]),
+    "ddrl_leg_coupling": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int, c_stream]),
+}
+
+_lib = None
+
+
+class DDRLError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the C-ABI library (once).  Raises if it has not been built — no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DDRLError(
+                f"{LIB_PATH} is missing: build it with `python -m ddrl_b200.build` (nvcc, sm_100a). "
+                "ddrl_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ddrl_last_error().decode("utf-8", "replace")
+        raise DDRLError(f"{what or 'ddrl'} failed (code {rc}): {msg}")

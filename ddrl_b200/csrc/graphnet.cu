@@ -1,0 +1,382 @@
+// GraphNet (models/graph_net.py:10-45): hyper-network leg encoder -> MPNN over the 4-leg graph ->
+// gather controlled node -> linear head; wrapper with separate actor and critic nets
+// (models/shared_graphnet_glorot_uniform_init.py:21-58).  Also the GCN layer (models/gcn.py:7-37).
+//
+// One CTA of 256 threads keeps ONE net's weights on chip for its whole life and walks over rows:
+//   thread (h = tid/4, fs = tid%4) owns the encoder columns j = f*64 + h for f = fs, fs+4, ... (<19):
+//     w_j = tanh(e . Wenc[:, j] + b_j)   (e = state[n][19:23]),  x[n][h] = tanh(sum_f state[n][f] w_j)
+//     -> the sum over f is 5 local terms + two shuffles, no block barrier;
+//   only the nodes the output depends on are encoded: the controlled node and its in-neighbours
+//     (adj[s][idx] != 0), i.e. 3 of 4 on the ring — identical result, 25 % less work;
+//   MPNN: y[h'] = tanh(sum_h x_i[h] Wupd[h][h'] + mean_s(x_s)[h] Wmsg[h][h']); thread (h' = tid/4,
+//     part = tid%4) owns h = 4i + part of both matrices in registers (mean before the transform is the
+//     same linear map as the reference's per-edge transform + segment mean);
+//   backward mirrors it with the transposed use of Wupd/Wmsg served from shared memory (stride 68 =>
+//     conflict free) and per-thread gradient accumulators in registers; per-CTA partials leave once.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ddrl {
+
+constexpr int GH = DDRL_HIDDEN;          // 64
+constexpr int GF = DDRL_GN_FEATS;        // 19
+constexpr int GE = DDRL_GN_ENC_IN;       // 4
+constexpr int GS = GF + GE;              // 23 floats per node
+constexpr int GN = DDRL_GN_NODES;        // 4
+constexpr int GT2 = 256;
+constexpr int GK = 5;                    // encoder columns per thread
+constexpr int GLD = 68;                  // smem stride of Wupd/Wmsg for the transposed use
+constexpr int GMAXO = 2 * DDRL_MAX_ACT;  // 16
+constexpr int GIN = GN * GS + GN * GN + 1 + GMAXO;  // staged floats per row: state, adj, idx, dout
+
+struct GnOffsets { int We, be, Wm, Wu, Wo, bo, NP; };
+__host__ __device__ inline GnOffsets gn_offsets(int O) {
+    GnOffsets o;
+    int p = 0;
+    o.We = p; p += GE * GF * GH;
+    o.be = p; p += GF * GH;
+    o.Wm = p; p += GH * GH;
+    o.Wu = p; p += GH * GH;
+    o.Wo = p; p += GH * O;
+    o.bo = p; p += O;
+    o.NP = p;
+    return o;
+}
+
+struct GnRow {      // per-row graph structure, identical in all threads; slot == node id (static indexing)
+    int idx, cnt;
+    bool need[GN];      // node must be encoded (controlled node or one of its in-neighbours)
+    bool is_snd[GN];    // node sends to idx
+};
+
+__device__ __forceinline__ GnRow gn_row(const float* sin) {
+    GnRow g;
+    g.idx = min(max(__float_as_int(sin[GN * GS + GN * GN]), 0), GN - 1);
+    g.cnt = 0;
+#pragma unroll
+    for (int n = 0; n < GN; ++n) {
+        const bool snd = sin[GN * GS + n * GN + g.idx] != 0.f;
+        g.is_snd[n] = snd;
+        g.need[n] = snd || n == g.idx;
+        g.cnt += snd ? 1 : 0;
+    }
+    return g;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(GT2, 1)
+graphnet_kernel(const float* __restrict__ theta, const int32_t* __restrict__ node_idx, const float* __restrict__ state,
+                const float* __restrict__ adj, const float* __restrict__ dlogits, const float* __restrict__ dvalue,
+                int64_t B, int A, float* __restrict__ logits, float* __restrict__ value, float* __restrict__ grad_part) {
+    __shared__ __align__(16) float sIn[2][GIN + 3];
+    __shared__ float sX[GN][GH];
+    __shared__ float sD[GH];
+    __shared__ float sOut[GT2 / 32][GMAXO];
+    __shared__ __align__(16) float sWuT[BWD ? GH * GLD : 1];
+    __shared__ __align__(16) float sWmT[BWD ? GH * GLD : 1];
+
+    const int net = blockIdx.y;                 // 0 actor, 1 critic
+    const int O = net == 0 ? 2 * A : 1;
+    const GnOffsets oa = gn_offsets(2 * A);
+    const GnOffsets o = gn_offsets(O);
+    const int net_base = net == 0 ? 0 : oa.NP;
+    const float* th = theta + net_base;
+    const int tid = threadIdx.x, h = tid >> 2, fs = tid & 3, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bx = blockIdx.x;
+
+    // ---- weights -> registers / shared --------------------------------------------------------------
+    float We[GK][GE], be[GK];
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+        const int f = fs + 4 * k;
+        const bool ok = f < GF;
+#pragma unroll
+        for (int q = 0; q < GE; ++q) We[k][q] = ok ? th[o.We + q * GF * GH + f * GH + h] : 0.f;
+        be[k] = ok ? th[o.be + f * GH + h] : 0.f;
+    }
+    float Wu[16], Wm[16];   // forward use: thread (h' = h, part = fs) owns input rows 4i + part
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        Wu[i] = th[o.Wu + (4 * i + fs) * GH + h];
+        Wm[i] = th[o.Wm + (4 * i + fs) * GH + h];
+    }
+    float Wo[GMAXO];
+#pragma unroll
+    for (int q = 0; q < GMAXO; ++q) Wo[q] = q < O ? th[o.Wo + h * O + q] : 0.f;
+    if (BWD) {
+        for (int i = tid; i < GH * GH; i += GT2) {
+            const int r = i >> 6, c = i & 63;
+            sWuT[r * GLD + c] = th[o.Wu + i];
+            sWmT[r * GLD + c] = th[o.Wm + i];
+        }
+    }
+    float gWe[GK][GE], gbe[GK], gWu[16], gWm[16], gWo[GMAXO], gbo = 0.f;
+    if (BWD) {
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            gbe[k] = 0.f;
+#pragma unroll
+            for (int q = 0; q < GE; ++q) gWe[k][q] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { gWu[i] = 0.f; gWm[i] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < GMAXO; ++q) gWo[q] = 0.f;
+    }
+
+    // ---- row staging: state[92] adj[16] idx[1] dout[O] ------------------------------------------------
+    auto fetch = [&](int64_t b) -> float {
+        if (b >= B) return 0.f;
+        if (tid < GN * GS) return state[b * GN * GS + tid];
+        if (tid < GN * GS + GN * GN) return adj[b * GN * GN + (tid - GN * GS)];
+        if (tid == GN * GS + GN * GN) return __int_as_float(node_idx[b]);
+        if (BWD) {
+            const int q = tid - (GN * GS + GN * GN + 1);
+            if (q < O) return net == 0 ? dlogits[b * O + q] : dvalue[b];
+        }
+        return 0.f;
+    };
+    int cur = 0;
+    if (tid < GIN) sIn[0][tid] = fetch(bx);
+    __syncthreads();
+
+    for (int64_t b = bx; b < B; b += G) {
+        const float* sin = sIn[cur];
+        const float pre_next = tid < GIN ? fetch(b + G) : 0.f;   // prefetch the next row (registers)
+        const GnRow g = gn_row(sin);
+
+        // ---- encoder for the needed nodes ---------------------------------------------------------
+        float wk[GN][GK], xk[GN];
+#pragma unroll
+        for (int i = 0; i < GN; ++i) {
+            xk[i] = 0.f;
+            if (g.need[i]) {
+                const float* st = sin + i * GS;
+                const float e0 = st[GF], e1 = st[GF + 1], e2 = st[GF + 2], e3 = st[GF + 3];
+                float part = 0.f;
+#pragma unroll
+                for (int k = 0; k < GK; ++k) {
+                    const int f = fs + 4 * k;
+                    float pre = be[k];
+                    pre = fmaf(e0, We[k][0], pre);
+                    pre = fmaf(e1, We[k][1], pre);
+                    pre = fmaf(e2, We[k][2], pre);
+                    pre = fmaf(e3, We[k][3], pre);
+                    const float w = tanhf(pre);
+                    wk[i][k] = w;
+                    if (f < GF) part = fmaf(st[f], w, part);
+                }
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                xk[i] = tanhf(part);
+                if (fs == 0) sX[i][h] = xk[i];
+            }
+        }
+        __syncthreads();   // S1: x of all needed nodes visible
+
+        // ---- MPNN for the controlled node: thread (h' = h, part = fs) ---------------------------------
+        const float inv_cnt = g.cnt > 0 ? 1.f / (float)g.cnt : 0.f;
+        float pre = 0.f;
+        float xi[16], xm[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int hh = 4 * i + fs;
+            xi[i] = sX[g.idx][hh];
+            float s = 0.f;
+#pragma unroll
+            for (int n = 0; n < GN; ++n)
+                if (g.is_snd[n]) s += sX[n][hh];
+            xm[i] = s * inv_cnt;
+            pre = fmaf(xi[i], Wu[i], pre);
+            pre = fmaf(xm[i], Wm[i], pre);
+        }
+        pre += __shfl_xor_sync(0xffffffffu, pre, 1);
+        pre += __shfl_xor_sync(0xffffffffu, pre, 2);
+        const float y = tanhf(pre);
+
+        if (!BWD) {
+            // head: out[q] = sum_h' y[h'] Wout[h'][q] + b[q]; warp shuffle over the 8 h' of the warp, then 8 warps
+#pragma unroll
+            for (int q = 0; q < GMAXO; ++q) {
+                if (q < O) {
+                    float v = fs == 0 ? y * Wo[q] : 0.f;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                    if (lane == 0) sOut[warp][q] = v;
+                }
+            }
+            if (tid < GIN) sIn[cur ^ 1][tid] = pre_next;
+            __syncthreads();   // S2
+            if (tid < O) {
+                float v = th[o.bo + tid];
+#pragma unroll
+                for (int w = 0; w < GT2 / 32; ++w) v += sOut[w][tid];
+                if (net == 0) logits[b * O + tid] = v; else value[b] = v;
+            }
+        } else {
+            const float* dout = sin + GN * GS + GN * GN + 1;
+            float dy = 0.f;
+#pragma unroll
+            for (int q = 0; q < GMAXO; ++q)
+                if (q < O) {
+                    dy = fmaf(dout[q], Wo[q], dy);
+                    gWo[q] = fmaf(y, dout[q], gWo[q]);
+                }
+            if (tid < O) gbo += dout[tid];
+            const float dpre = dy * (1.f - y * y);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                gWu[i] = fmaf(xi[i], dpre, gWu[i]);
+                gWm[i] = fmaf(xm[i], dpre, gWm[i]);
+            }
+            if (fs == 0) sD[h] = dpre;
+            if (tid < GIN) sIn[cur ^ 1][tid] = pre_next;
+            __syncthreads();   // S2: dpre visible
+            // dx_i[h], dxm[h]: thread (h, fs) sums over h' = 4i + fs with the transposed use from shared memory
+            float dxi = 0.f, dxm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float d = sD[4 * i + fs];
+                dxi = fmaf(sWuT[h * GLD + 4 * i + fs], d, dxi);
+                dxm = fmaf(sWmT[h * GLD + 4 * i + fs], d, dxm);
+            }
+            dxi += __shfl_xor_sync(0xffffffffu, dxi, 1);
+            dxi += __shfl_xor_sync(0xffffffffu, dxi, 2);
+            dxm += __shfl_xor_sync(0xffffffffu, dxm, 1);
+            dxm += __shfl_xor_sync(0xffffffffu, dxm, 2);
+            dxm *= inv_cnt;
+#pragma unroll
+            for (int i = 0; i < GN; ++i) {
+                if (g.need[i]) {
+                    const float dx = (i == g.idx ? dxi : 0.f) + (g.is_snd[i] ? dxm : 0.f);
+                    const float dpx = dx * (1.f - xk[i] * xk[i]);
+                    const float* st = sin + i * GS;
+                    const float e0 = st[GF], e1 = st[GF + 1], e2 = st[GF + 2], e3 = st[GF + 3];
+#pragma unroll
+                    for (int k = 0; k < GK; ++k) {
+                        const int f = fs + 4 * k;
+                        if (f < GF) {
+                            const float w = wk[i][k];
+                            const float dpw = dpx * st[f] * (1.f - w * w);
+                            gWe[k][0] = fmaf(e0, dpw, gWe[k][0]);
+                            gWe[k][1] = fmaf(e1, dpw, gWe[k][1]);
+                            gWe[k][2] = fmaf(e2, dpw, gWe[k][2]);
+                            gWe[k][3] = fmaf(e3, dpw, gWe[k][3]);
+                            gbe[k] += dpw;
+                        }
+                    }
+                }
+            }
+        }
+        cur ^= 1;
+    }
+
+    if (BWD) {
+        float* gp = grad_part + (int64_t)bx * (oa.NP + gn_offsets(1).NP) + net_base;
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const int f = fs + 4 * k;
+            if (f < GF) {
+#pragma unroll
+                for (int q = 0; q < GE; ++q) gp[o.We + q * GF * GH + f * GH + h] = gWe[k][q];
+                gp[o.be + f * GH + h] = gbe[k];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            gp[o.Wu + (4 * i + fs) * GH + h] = gWu[i];
+            gp[o.Wm + (4 * i + fs) * GH + h] = gWm[i];
+        }
+        if (fs == 0)
+#pragma unroll
+            for (int q = 0; q < GMAXO; ++q)
+                if (q < O) gp[o.Wo + h * O + q] = gWo[q];
+        if (tid < O) gp[o.bo + tid] = gbo;
+    }
+}
+
+// ---- GCN layer: y[b][n][u] = act(sum_f (sum_m An[n][m] x[b][m][f]) W[f][u] + bias[u]) ---------------------
+__global__ void gcn_forward_kernel(const float* __restrict__ x, const float* __restrict__ adj, const float* __restrict__ W,
+                                   const float* __restrict__ bias, int64_t B, int F, int U, int act,
+                                   float* __restrict__ y) {
+    extern __shared__ float sg[];   // ax[GN][F] per row handled by this CTA iteration
+    __shared__ float sAn[GN][GN];
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < GN * GN) {
+            const int n = threadIdx.x / GN;
+            float d = 0.f;
+            for (int m = 0; m < GN; ++m) d += adj[b * GN * GN + n * GN + m];
+            // graph_ops.adj_norm: rowsum ** -1 (inf for isolated nodes, as in the reference)
+            sAn[n][threadIdx.x % GN] = (1.f / d) * adj[b * GN * GN + threadIdx.x];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < GN * F; i += blockDim.x) {
+            const int n = i / F, f = i - n * F;
+            float s = 0.f;
+            for (int m = 0; m < GN; ++m) s = fmaf(sAn[n][m], x[(b * GN + m) * F + f], s);
+            sg[i] = s;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < GN * U; i += blockDim.x) {
+            const int n = i / U, u = i - n * U;
+            float s = 0.f;
+            for (int f = 0; f < F; ++f) s = fmaf(sg[n * F + f], W[f * U + u], s);
+            if (bias) s += bias[u];
+            y[(b * GN + n) * U + u] = act == 1 ? tanhf(s) : s;
+        }
+    }
+}
+
+}  // namespace ddrl
+
+using namespace ddrl;
+
+extern "C" int ddrl_graphnet_num_params(int num_outputs) {
+    if (num_outputs < 2 || num_outputs > GMAXO || (num_outputs & 1)) return DDRL_E_UNSUPPORTED_SHAPE;
+    return gn_offsets(num_outputs).NP + gn_offsets(1).NP;
+}
+
+static int gn_ctas(int64_t B) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(B, sms / 2));
+}
+
+extern "C" int ddrl_graphnet_forward(const float* theta, const int32_t* node_idx, const float* state, const float* adj,
+                                     int64_t B, int A, float* logits, float* value, void* stream) {
+    DDRL_REQUIRE(theta && node_idx && state && adj && logits && value && B >= 0, DDRL_E_BADARG,
+                 "graphnet_forward: null pointer or bad B");
+    DDRL_REQUIRE(A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE, "graphnet_forward: unsupported A=%d", A);
+    if (B == 0) return DDRL_OK;
+    graphnet_kernel<false><<<dim3(gn_ctas(B), 2), GT2, 0, (cudaStream_t)stream>>>(theta, node_idx, state, adj, nullptr,
+                                                                                 nullptr, B, A, logits, value, nullptr);
+    DDRL_CHECK_LAUNCH("graphnet_forward");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_graphnet_backward(const float* theta, const int32_t* node_idx, const float* state, const float* adj,
+                                      const float* dlogits, const float* dvalue, int64_t B, int A, int ctas,
+                                      float* grad_part, void* stream) {
+    DDRL_REQUIRE(theta && node_idx && state && adj && dlogits && dvalue && grad_part && B >= 1 && ctas >= 1,
+                 DDRL_E_BADARG, "graphnet_backward: null pointer or bad B/ctas");
+    DDRL_REQUIRE(A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE, "graphnet_backward: unsupported A=%d", A);
+    graphnet_kernel<true><<<dim3(ctas, 2), GT2, 0, (cudaStream_t)stream>>>(theta, node_idx, state, adj, dlogits, dvalue, B,
+                                                                          A, nullptr, nullptr, grad_part);
+    DDRL_CHECK_LAUNCH("graphnet_backward");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_gcn_forward(const float* x, const float* adj, const float* W, const float* b, int64_t B, int F,
+                                int U, int act, float* y, void* stream) {
+    DDRL_REQUIRE(x && adj && W && y && B >= 0 && F >= 1 && U >= 1, DDRL_E_BADARG, "gcn_forward: null pointer or bad shape");
+    DDRL_REQUIRE(F <= 2048 && (act == 0 || act == 1), DDRL_E_UNSUPPORTED_SHAPE, "gcn_forward: F=%d > 2048 or act=%d", F, act);
+    if (B == 0) return DDRL_OK;
+    const int nb = (int)std::min<int64_t>(B, 148 * 8);
+    gcn_forward_kernel<<<nb, 128, (size_t)GN * F * sizeof(float), (cudaStream_t)stream>>>(x, adj, W, b, B, F, U, act, y);
+    DDRL_CHECK_LAUNCH("gcn_forward");
+    return DDRL_OK;
+}

@@ -1,0 +1,494 @@
+// HBM-bound streaming kernels of the learner path: MeanStdFilter update, GAE reverse scan,
+// advantage standardisation, row shuffle, fixed-order gradient reduction, clip + TF1-Adam.
+// All reductions use a fixed order (no float atomics) => bit-reproducible.
+#include <algorithm>
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "ppo_loss.cuh"
+
+namespace ddrl {
+
+static thread_local char g_err[512] = "";
+static int64_t g_launches = 0;
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { __atomic_add_fetch(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+
+// =================================================================================================
+// K4: MeanStdFilter — per-CTA (n, mean, M2) over a contiguous row range, then a fixed-order Chan merge
+// =================================================================================================
+constexpr int FT = 256;        // threads
+constexpr int FROWS = 128;     // rows staged in shared memory per sub-chunk
+constexpr int FMAXBLK = 64;    // partials per policy
+constexpr int FMAXCOL = DDRL_MAX_OBS / 8;  // columns per warp
+
+struct Stat { double n, mean, m2; };
+__device__ __forceinline__ void chan_merge(Stat& a, const Stat& b) {
+    // RunningStat.update (ray.rllib.utils.filter): delta = M1 - M2; M = (n1 M1 + n2 M2)/n; S += S2 + delta^2 n1 n2 / n
+    const double n = a.n + b.n;
+    if (n == 0.0) return;
+    const double delta = a.mean - b.mean;
+    a.mean = (a.n * a.mean + b.n * b.mean) / n;
+    a.m2 = a.m2 + b.m2 + delta * delta * a.n * b.n / n;
+    a.n = n;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FT) filter_partial_kernel(const T* __restrict__ x, int64_t R, int D, int nblk,
+                                                            double* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char fsm_raw[];
+    T* xs = reinterpret_cast<T*>(fsm_raw);
+    const int p = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t per = ((R + nblk - 1) / nblk + FROWS - 1) / FROWS * FROWS;
+    const int64_t r0 = min((int64_t)b * per, R), r1 = min(r0 + per, R);
+    const T* xp = x + (int64_t)p * R * D;
+    Stat acc[FMAXCOL];
+#pragma unroll
+    for (int i = 0; i < FMAXCOL; ++i) acc[i] = Stat{0.0, 0.0, 0.0};
+    for (int64_t c0 = r0; c0 < r1; c0 += FROWS) {
+        const int nr = (int)min((int64_t)FROWS, r1 - c0);
+        __syncthreads();
+        for (int i = tid; i < nr * D; i += FT) xs[i] = xp[c0 * D + i];
+        __syncthreads();
+#pragma unroll
+        for (int ci = 0; ci < FMAXCOL; ++ci) {
+            const int d = warp + ci * 8;
+            if (d < D) {
+                double s = 0.0;
+                for (int r = lane; r < nr; r += 32) s += (double)xs[r * D + d];
+                s = warp_sum(s);
+                const double mean = s / nr;
+                double q = 0.0;
+                for (int r = lane; r < nr; r += 32) {
+                    const double e = (double)xs[r * D + d] - mean;
+                    q = fma(e, e, q);
+                }
+                q = warp_sum(q);
+                Stat c{(double)nr, mean, q};
+                chan_merge(acc[ci], c);
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int ci = 0; ci < FMAXCOL; ++ci) {
+            const int d = warp + ci * 8;
+            if (d < D) {
+                double* o = part + (((int64_t)p * nblk + b) * D + d) * 3;
+                o[0] = acc[ci].n; o[1] = acc[ci].mean; o[2] = acc[ci].m2;
+            }
+        }
+    }
+}
+
+__global__ void filter_merge_kernel(const double* __restrict__ part, int nblk, int D, int64_t R, int64_t* n_io,
+                                    double* M, double* S, double* norm) {
+    const int p = blockIdx.x, d = threadIdx.x;
+    const int64_t n_old = n_io[p];
+    const int64_t n_new = n_old + R;
+    __syncthreads();  // every thread has read the old count before thread 0 overwrites it
+    if (d == 0) n_io[p] = n_new;
+    if (d >= D) return;
+    Stat b{0.0, 0.0, 0.0};
+    for (int i = 0; i < nblk; ++i) {
+        const double* o = part + (((int64_t)p * nblk + i) * D + d) * 3;
+        chan_merge(b, Stat{o[0], o[1], o[2]});
+    }
+    Stat a{(double)n_old, M[p * D + d], S[p * D + d]};
+    chan_merge(a, b);
+    M[p * D + d] = a.mean;
+    S[p * D + d] = a.m2;
+    const double var = n_new > 1 ? a.m2 / (double)(n_new - 1) : a.mean * a.mean;
+    norm[(int64_t)p * 2 * D + d] = a.mean;
+    norm[(int64_t)p * 2 * D + D + d] = 1.0 / (sqrt(var) + 1e-8);
+}
+
+// =================================================================================================
+// K5: GAE reverse scan (float64 like the reference's scipy.signal.lfilter on float64 deltas)
+// =================================================================================================
+constexpr int GT = 256;
+__global__ void __launch_bounds__(GT) gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                                                 const uint8_t* __restrict__ dones, const float* __restrict__ v_boot,
+                                                 int T, int64_t C, int cpe, double gamma, double lambda,
+                                                 float* __restrict__ adv, float* __restrict__ vtarg,
+                                                 double* __restrict__ part) {
+    __shared__ double red[2][GT / 32];
+    const int p = blockIdx.y;
+    const int64_t c = (int64_t)blockIdx.x * GT + threadIdx.x;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        const int64_t base = (int64_t)p * T * C;
+        const int64_t ce = c / cpe, Ce = C / cpe;
+        double nv = (double)v_boot[(int64_t)p * C + c], na = 0.0;
+        for (int t = T - 1; t >= 0; --t) {
+            const double nd = dones[(int64_t)t * Ce + ce] ? 0.0 : 1.0;
+            const double v = (double)values[base + (int64_t)t * C + c];
+            const double delta = (double)rewards[base + (int64_t)t * C + c] + gamma * nd * nv - v;
+            na = delta + gamma * lambda * nd * na;
+            const float af = (float)na;
+            adv[base + (int64_t)t * C + c] = af;
+            vtarg[base + (int64_t)t * C + c] = (float)(na + v);
+            s += (double)af;
+            q = fma((double)af, (double)af, q);
+            nv = v;
+        }
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ss = 0.0, qq = 0.0;
+        for (int i = 0; i < GT / 32; ++i) { ss += red[0][i]; qq += red[1][i]; }
+        part[((int64_t)p * gridDim.x + blockIdx.x) * 2 + 0] = ss;
+        part[((int64_t)p * gridDim.x + blockIdx.x) * 2 + 1] = qq;
+    }
+}
+
+__global__ void gae_moments_kernel(const double* __restrict__ part, int nblk, double count, double* moments) {
+    const int p = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    // fixed assignment of partials to lanes, fixed tree afterwards
+    for (int i = threadIdx.x; i < nblk; i += 32) { s += part[((int64_t)p * nblk + i) * 2]; q += part[((int64_t)p * nblk + i) * 2 + 1]; }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (threadIdx.x == 0) { moments[p * 3 + 0] = count; moments[p * 3 + 1] = s; moments[p * 3 + 2] = q; }
+}
+
+__global__ void adv_standardize_kernel(float* __restrict__ adv, const double* __restrict__ moments, int64_t R) {
+    const int p = blockIdx.y;
+    const double n = moments[p * 3], mean = moments[p * 3 + 1] / n;
+    const double var = fmax(moments[p * 3 + 2] / n - mean * mean, 0.0);
+    const float mf = (float)mean, sf = fmaxf(1e-4f, (float)sqrt(var));
+    float* a = adv + (int64_t)p * R;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x)
+        a[i] = (a[i] - mf) / sf;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ perm, int64_t R, int W,
+                                   float* __restrict__ dst) {
+    const int p = blockIdx.y;
+    const float* s = src + (int64_t)p * R * W;
+    float* d = dst + (int64_t)p * R * W;
+    const int32_t* pm = perm + (int64_t)p * R;
+    const int64_t n = R * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / W;
+        const int c = (int)(i - r * W);
+        d[i] = s[(int64_t)pm[r] * W + c];
+    }
+}
+
+// =================================================================================================
+// gradient partial reduce (fixed order) and K7: clip_by_global_norm + TF1 Adam
+// =================================================================================================
+__global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double* __restrict__ spart, int G, int NP,
+                                   float* __restrict__ grad, double* __restrict__ step_stats,
+                                   const int32_t* __restrict__ step_ctr) {
+    const int p = blockIdx.y, P = gridDim.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < NP) {
+        const float* g = gpart + (int64_t)p * G * NP + j;
+        float s = 0.f;
+        for (int i = 0; i < G; ++i) s += g[(int64_t)i * NP];
+        grad[(int64_t)p * NP + j] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < DDRL_NSTAT && spart && step_stats) {
+        const int step = step_ctr ? *step_ctr : 0;
+        double s = 0.0;
+        for (int i = 0; i < G; ++i) s += spart[((int64_t)p * G + i) * DDRL_NSTAT + threadIdx.x];
+        step_stats[((int64_t)step * P + p) * DDRL_NSTAT + threadIdx.x] = s;
+    }
+}
+
+constexpr int AT = 256;
+__global__ void __launch_bounds__(AT) clip_adam_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                       float* __restrict__ v, float* beta_pow,
+                                                       const float* __restrict__ grad, int NP, float lr, float beta1,
+                                                       float beta2, float eps, float clip, float* gnorm_out,
+                                                       int32_t* step_ctr, int32_t* sync_ws) {
+    __shared__ float red[AT / 32];
+    __shared__ float s_scale;
+    const int p = blockIdx.y, P = gridDim.y, tid = threadIdx.x;
+    const float* g = grad + (int64_t)p * NP;
+    // every CTA of the policy recomputes the global norm in the same fixed order (identical bits everywhere)
+    float ss = 0.f;
+    for (int i = tid; i < NP; i += AT) ss = fmaf(g[i], g[i], ss);
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < AT / 32; ++i) t += red[i];
+        const float norm = sqrtf(t);
+        // tf.clip_by_global_norm: scale = clip * min(1/norm, 1/clip)
+        s_scale = clip > 0.f ? clip * fminf(1.f / norm, 1.f / clip) : 1.f;
+        if (gnorm_out && blockIdx.x == 0) gnorm_out[p] = norm;
+    }
+    __syncthreads();
+    const float scale = s_scale;
+    const float b1p = beta_pow[p * 2], b2p = beta_pow[p * 2 + 1];
+    // tensorflow/core/kernels/training_ops.cc ApplyAdam (non-nesterov)
+    const float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    const int j = blockIdx.x * AT + tid;
+    if (j < NP) {
+        const int64_t k = (int64_t)p * NP + j;
+        const float gj = g[j] * scale;
+        float mj = m[k], vj = v[k];
+        mj += (gj - mj) * (1.f - beta1);
+        vj += (gj * gj - vj) * (1.f - beta2);
+        m[k] = mj;
+        v[k] = vj;
+        theta[k] -= (mj * alpha) / (sqrtf(vj) + eps);
+    }
+    // arrival ticket: the last CTA advances the beta powers / step counter after everyone has read them
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int total = gridDim.x * gridDim.y;
+        const int t = atomicAdd(sync_ws, 1);
+        if (t == total - 1) {
+            for (int q = 0; q < P; ++q) {
+                beta_pow[q * 2] *= beta1;
+                beta_pow[q * 2 + 1] *= beta2;
+            }
+            if (step_ctr) *step_ctr += 1;
+            *sync_ws = 0;
+            __threadfence();
+        }
+    }
+}
+
+// K6 (stand-alone): PPO loss gradient w.r.t. model outputs, for models whose forward/backward are separate
+// kernels (GraphNet).  grid (G, P); per-CTA stat partials like the fused FCNet kernel.
+constexpr int LT = 256;
+__global__ void __launch_bounds__(LT) ppo_loss_grad_kernel(
+    const float* __restrict__ logits, const float* __restrict__ value, const float* __restrict__ actions,
+    const float* __restrict__ old_logits, const float* __restrict__ old_logp, const float* __restrict__ vf_preds,
+    const float* __restrict__ adv, const float* __restrict__ vtarg, int64_t R, int A, const float* __restrict__ kl_coeff,
+    const ddrl_ppo_hyper hp, float* __restrict__ dlogits, float* __restrict__ dvalue, double* __restrict__ stat_part) {
+    __shared__ double red[LT / 32][DDRL_NSTAT];
+    const int p = blockIdx.y, A2 = 2 * A;
+    const float klc = kl_coeff[p];
+    double st[DDRL_NSTAT];
+#pragma unroll
+    for (int i = 0; i < DDRL_NSTAT; ++i) st[i] = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * LT + threadIdx.x; r < R; r += (int64_t)gridDim.x * LT) {
+        const int64_t gr = (int64_t)p * R + r;
+        float out[2 * DDRL_MAX_ACT + 1], dl[2 * DDRL_MAX_ACT + 1];
+        double s[DDRL_NSTAT];
+#pragma unroll
+        for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
+            if (i < A2) out[i] = logits[gr * A2 + i];
+        out[A2] = value[gr];
+        ppo_row_loss(out, A, actions + gr * A, old_logits + gr * A2, old_logp[gr], vf_preds[gr], adv[gr], vtarg[gr],
+                     klc, hp, dl, s);
+#pragma unroll
+        for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
+            if (i < A2) dlogits[gr * A2 + i] = dl[i];
+        dvalue[gr] = dl[A2];
+#pragma unroll
+        for (int i = 0; i < DDRL_NSTAT; ++i) st[i] += s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DDRL_NSTAT; ++i) st[i] = warp_sum(st[i]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < DDRL_NSTAT; ++i) red[warp][i] = st[i];
+    __syncthreads();
+    if (threadIdx.x < DDRL_NSTAT) {
+        double t = 0.0;
+        for (int w = 0; w < LT / 32; ++w) t += red[w][threadIdx.x];
+        stat_part[((int64_t)p * gridDim.x + blockIdx.x) * DDRL_NSTAT + threadIdx.x] = t;
+    }
+}
+
+// DiagGaussian sample + logp (RLlib models/tf/tf_action_dist.py) for models without a fused epilogue.
+__global__ void dg_sample_kernel(const float* __restrict__ logits, const float* __restrict__ eps, int64_t R, int A,
+                                 float* __restrict__ action, float* __restrict__ logp) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+        float sz2 = 0.f, sls = 0.f;
+        for (int i = 0; i < A; ++i) {
+            const float mu = logits[r * 2 * A + i], ls = logits[r * 2 * A + A + i];
+            const float sd = expf(ls);
+            const float a = mu + sd * eps[r * A + i];
+            const float z = (a - mu) / sd;
+            sz2 = fmaf(z, z, sz2);
+            sls += ls;
+            action[r * A + i] = a;
+        }
+        logp[r] = -0.5f * sz2 - 0.5f * kLog2Pi * (float)A - sls;
+    }
+}
+
+__global__ void leg_coupling_kernel(float* __restrict__ logits, const int32_t* __restrict__ node_id,
+                                    const float* __restrict__ coupling, int64_t B, int W) {
+    const int64_t n = B * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / W;
+        const int j = (int)(i - b * W);
+        if (j < 2) logits[i] *= coupling[node_id[b] * 2 + j];
+    }
+}
+
+}  // namespace ddrl
+
+using namespace ddrl;
+
+extern "C" const char* ddrl_last_error(void) { return g_err; }
+extern "C" int ddrl_abi_version(void) { return 1; }
+extern "C" int64_t ddrl_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+static int filter_nblk(int64_t R) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(FMAXBLK, (R + FROWS - 1) / FROWS));
+}
+
+extern "C" int64_t ddrl_filter_ws_bytes(int P, int64_t R, int D) {
+    return (int64_t)P * filter_nblk(R) * D * 3 * (int64_t)sizeof(double);
+}
+
+extern "C" int ddrl_filter_num_partials(int64_t R) { return filter_nblk(R); }
+
+extern "C" int ddrl_filter_partial(const void* x, int x_is_f64, int P, int64_t R, int D, void* ws, void* stream) {
+    DDRL_REQUIRE(ws && P >= 1 && R >= 0, DDRL_E_BADARG, "filter_partial: null workspace or bad P/R");
+    DDRL_REQUIRE(R == 0 || x, DDRL_E_BADARG, "filter_partial: x is null");
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS, DDRL_E_UNSUPPORTED_SHAPE, "filter_partial: D=%d > %d", D, DDRL_MAX_OBS);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = filter_nblk(R);
+    if (R == 0) {
+        cudaMemsetAsync(ws, 0, (size_t)ddrl_filter_ws_bytes(P, R, D), st);
+        return DDRL_OK;
+    }
+    dim3 grid(nblk, P);
+    if (x_is_f64) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(filter_partial_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            attr = true;
+        }
+        filter_partial_kernel<double><<<grid, FT, (size_t)FROWS * D * sizeof(double), st>>>((const double*)x, R, D, nblk,
+                                                                                           (double*)ws);
+    } else {
+        filter_partial_kernel<float><<<grid, FT, (size_t)FROWS * D * sizeof(float), st>>>((const float*)x, R, D, nblk,
+                                                                                         (double*)ws);
+    }
+    DDRL_CHECK_LAUNCH("filter_partial");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_filter_merge(const void* parts, int nparts, int P, int D, int64_t R_total, int64_t* n, double* M,
+                                 double* S, double* norm, void* stream) {
+    DDRL_REQUIRE(parts && n && M && S && norm && P >= 1 && nparts >= 0 && R_total >= 0, DDRL_E_BADARG,
+                 "filter_merge: null pointer or bad shape");
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS, DDRL_E_UNSUPPORTED_SHAPE, "filter_merge: D=%d > %d", D, DDRL_MAX_OBS);
+    filter_merge_kernel<<<P, 64, 0, (cudaStream_t)stream>>>((const double*)parts, nparts, D, R_total, n, M, S, norm);
+    DDRL_CHECK_LAUNCH("filter_merge");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_filter_update(const void* x, int x_is_f64, int P, int64_t R, int D, int64_t* n, double* M,
+                                  double* S, double* norm, void* ws, void* stream) {
+    DDRL_REQUIRE(n && M && S && norm && ws, DDRL_E_BADARG, "filter_update: null pointer");
+    const int rc = ddrl_filter_partial(x, x_is_f64, P, R, D, ws, stream);
+    if (rc != DDRL_OK) return rc;
+    return ddrl_filter_merge(ws, filter_nblk(R), P, D, R, n, M, S, norm, stream);
+}
+
+extern "C" int64_t ddrl_gae_ws_bytes(int P, int64_t C) { return (int64_t)P * ((C + GT - 1) / GT) * 2 * (int64_t)sizeof(double); }
+
+extern "C" int ddrl_gae(const float* rewards, const float* values, const uint8_t* dones, const float* v_boot, int P,
+                        int T, int64_t C, int cols_per_env, float gamma, float lambda, float* adv, float* vtarg,
+                        double* moments, void* ws, void* stream) {
+    DDRL_REQUIRE(rewards && values && dones && v_boot && adv && vtarg && moments && ws, DDRL_E_BADARG, "gae: null pointer");
+    DDRL_REQUIRE(P >= 1 && T >= 1 && C >= 1 && cols_per_env >= 1 && C % cols_per_env == 0, DDRL_E_BADARG,
+                 "gae: bad P/T/C/cols_per_env (C must be a multiple of cols_per_env)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (int)((C + GT - 1) / GT);
+    gae_kernel<<<dim3(nblk, P), GT, 0, st>>>(rewards, values, dones, v_boot, T, C, cols_per_env, (double)gamma,
+                                             (double)lambda, adv, vtarg, (double*)ws);
+    DDRL_CHECK_LAUNCH("gae");
+    gae_moments_kernel<<<P, 32, 0, st>>>((const double*)ws, nblk, (double)T * (double)C, moments);
+    DDRL_CHECK_LAUNCH("gae_moments");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_adv_standardize(float* adv, const double* moments, int P, int64_t R, void* stream) {
+    DDRL_REQUIRE(adv && moments && P >= 1 && R >= 1, DDRL_E_BADARG, "adv_standardize: null pointer or bad P/R");
+    const int nb = (int)std::min<int64_t>(1024, (R + 255) / 256);
+    adv_standardize_kernel<<<dim3(nb, P), 256, 0, (cudaStream_t)stream>>>(adv, moments, R);
+    DDRL_CHECK_LAUNCH("adv_standardize");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_gather_rows(const float* src, const int32_t* perm, int P, int64_t R, int W, float* dst, void* stream) {
+    DDRL_REQUIRE(src && perm && dst && P >= 1 && R >= 1 && W >= 1, DDRL_E_BADARG, "gather_rows: null pointer or bad shape");
+    DDRL_REQUIRE(src != dst, DDRL_E_BADARG, "gather_rows: in-place gather is not supported");
+    const int nb = (int)std::min<int64_t>(2048, (R * W + 255) / 256);
+    gather_rows_kernel<<<dim3(nb, P), 256, 0, (cudaStream_t)stream>>>(src, perm, R, W, dst);
+    DDRL_CHECK_LAUNCH("gather_rows");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_grad_reduce(const float* grad_part, const double* stat_part, int P, int G, int NP, float* grad,
+                                double* step_stats, const int32_t* step_ctr, void* stream) {
+    DDRL_REQUIRE(grad_part && grad && P >= 1 && G >= 1 && NP >= 1, DDRL_E_BADARG, "grad_reduce: null pointer or bad shape");
+    grad_reduce_kernel<<<dim3((NP + 255) / 256, P), 256, 0, (cudaStream_t)stream>>>(grad_part, stat_part, G, NP, grad,
+                                                                                   step_stats, step_ctr);
+    DDRL_CHECK_LAUNCH("grad_reduce");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_clip_adam(float* theta, float* m, float* v, float* beta_pow, const float* grad, int P, int NP,
+                              float lr, float beta1, float beta2, float eps, float grad_clip, float* gnorm_out,
+                              int32_t* step_ctr, int32_t* sync_ws, void* stream) {
+    DDRL_REQUIRE(theta && m && v && beta_pow && grad && sync_ws && P >= 1 && NP >= 1, DDRL_E_BADARG,
+                 "clip_adam: null pointer or bad shape");
+    clip_adam_kernel<<<dim3((NP + AT - 1) / AT, P), AT, 0, (cudaStream_t)stream>>>(
+        theta, m, v, beta_pow, grad, NP, lr, beta1, beta2, eps, grad_clip, gnorm_out, step_ctr, sync_ws);
+    DDRL_CHECK_LAUNCH("clip_adam");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_ppo_loss_grad(const float* logits, const float* value, const float* actions, const float* old_logits,
+                                  const float* old_logp, const float* vf_preds, const float* adv, const float* vtarg,
+                                  int P, int64_t R, int A, const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas,
+                                  float* dlogits, float* dvalue, double* stat_part, void* stream) {
+    DDRL_REQUIRE(logits && value && actions && old_logits && old_logp && vf_preds && adv && vtarg && kl_coeff && hyper &&
+                     dlogits && dvalue && stat_part,
+                 DDRL_E_BADARG, "ppo_loss_grad: null pointer");
+    DDRL_REQUIRE(P >= 1 && R >= 1 && ctas >= 1, DDRL_E_BADARG, "ppo_loss_grad: bad P/R/ctas");
+    DDRL_REQUIRE(A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE, "ppo_loss_grad: unsupported A=%d", A);
+    ppo_loss_grad_kernel<<<dim3(ctas, P), LT, 0, (cudaStream_t)stream>>>(logits, value, actions, old_logits, old_logp,
+                                                                        vf_preds, adv, vtarg, R, A, kl_coeff, *hyper,
+                                                                        dlogits, dvalue, stat_part);
+    DDRL_CHECK_LAUNCH("ppo_loss_grad");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_dg_sample(const float* logits, const float* eps, int64_t R, int A, float* action, float* logp,
+                              void* stream) {
+    DDRL_REQUIRE(logits && eps && action && logp && R >= 0, DDRL_E_BADARG, "dg_sample: null pointer or bad R");
+    DDRL_REQUIRE(A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE, "dg_sample: unsupported A=%d", A);
+    if (R == 0) return DDRL_OK;
+    const int nb = (int)std::min<int64_t>(2048, (R + 255) / 256);
+    dg_sample_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(logits, eps, R, A, action, logp);
+    DDRL_CHECK_LAUNCH("dg_sample");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupling, int64_t B, int W,
+                                 void* stream) {
+    DDRL_REQUIRE(logits && node_id && coupling && B >= 0 && W >= 2, DDRL_E_BADARG, "leg_coupling: null pointer or bad shape");
+    if (B == 0) return DDRL_OK;
+    const int nb = (int)std::min<int64_t>(1024, (B * W + 255) / 256);
+    leg_coupling_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(logits, node_id, coupling, B, W);
+    DDRL_CHECK_LAUNCH("leg_coupling");
+    return DDRL_OK;
+}

@@ -1,0 +1,291 @@
+"""Thin torch-tensor wrappers over the C ABI (include/ddrl_b200.h).
+
+PyTorch is plumbing only: device memory, the current CUDA stream, ``torch.distributed``.  Every
+function validates device / dtype / contiguity, passes raw pointers to ``libddrl_b200.so`` and raises
+``DDRLError`` on any failure — there is no eager/PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DDRLError, PPOHyper
+
+HIDDEN = 64
+NSTAT = 8
+GN_NODES, GN_FEATS, GN_ENC_IN = 4, 19, 4
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise DDRLError(f"{name} must be a CUDA tensor (ddrl_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise DDRLError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise DDRLError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def fcnet_num_params(D: int, A: int) -> int:
+    n = _lib.load().ddrl_fcnet_num_params(D, A)
+    if n < 0:
+        raise DDRLError(f"unsupported FCNet shape D={D} A={A}")
+    return n
+
+
+def graphnet_num_params(num_outputs: int) -> int:
+    n = _lib.load().ddrl_graphnet_num_params(num_outputs)
+    if n < 0:
+        raise DDRLError(f"unsupported GraphNet num_outputs={num_outputs}")
+    return n
+
+
+def launch_count() -> int:
+    return int(_lib.load().ddrl_launch_count())
+
+
+# --------------------------------------------------------------------------------------------------
+def filter_update(x: torch.Tensor, n: torch.Tensor, M: torch.Tensor, S: torch.Tensor,
+                  norm: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [P,R,D] f32/f64; n [P] i64, M,S [P,D] f64 updated in place; returns norm [P,2,D] f64."""
+    lib = _lib.load()
+    P, R, D = x.shape
+    if norm is None:
+        norm = torch.empty(P, 2, D, dtype=torch.float64, device=x.device)
+    nbytes = lib.ddrl_filter_ws_bytes(P, R, D)
+    if ws is None or ws.numel() * ws.element_size() < nbytes:
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=x.device)
+    if x.dtype not in (torch.float32, torch.float64):
+        raise DDRLError("filter_update: x must be float32 or float64")
+    _lib.check(lib.ddrl_filter_update(_p(x, None, "x"), int(x.dtype == torch.float64), P, R, D,
+                                      _p(n, torch.int64, "n"), _p(M, torch.float64, "M"), _p(S, torch.float64, "S"),
+                                      _p(norm, torch.float64, "norm"), _p(ws, None, "ws"), _stream()),
+               "filter_update")
+    return norm
+
+
+def fcnet_forward(theta: torch.Tensor, obs: torch.Tensor, A: int, norm: Optional[torch.Tensor] = None,
+                  clip: float = 0.0, eps: Optional[torch.Tensor] = None, want_obs_out: bool = False,
+                  out: Optional[dict] = None) -> dict:
+    """theta [P,NP], obs [P,R,D] -> dict(logits [P,R,2A], value [P,R], [obs_out], [action, logp])."""
+    lib = _lib.load()
+    P, R, D = obs.shape
+    dev = obs.device
+    out = out or {}
+    f32 = torch.float32
+    logits = out.get("logits") if "logits" in out else torch.empty(P, R, 2 * A, dtype=f32, device=dev)
+    value = out.get("value") if "value" in out else torch.empty(P, R, dtype=f32, device=dev)
+    obs_out = out.get("obs_out") if "obs_out" in out else (torch.empty_like(obs) if want_obs_out else None)
+    action = logp = None
+    if eps is not None:
+        action = out.get("action") if "action" in out else torch.empty(P, R, A, dtype=f32, device=dev)
+        logp = out.get("logp") if "logp" in out else torch.empty(P, R, dtype=f32, device=dev)
+    if theta.shape != (P, fcnet_num_params(D, A)):
+        raise DDRLError(f"theta shape {tuple(theta.shape)} != ({P}, {fcnet_num_params(D, A)})")
+    _lib.check(lib.ddrl_fcnet_forward(_p(theta, f32, "theta"), _p(obs, f32, "obs"), _p(norm, torch.float64, "norm"),
+                                      float(clip), P, R, D, A, _p(obs_out, f32, "obs_out"), _p(logits, f32, "logits"),
+                                      _p(value, f32, "value"), _p(eps, f32, "eps"), _p(action, f32, "action"),
+                                      _p(logp, f32, "logp"), _stream()), "fcnet_forward")
+    res = {"logits": logits, "value": value}
+    if obs_out is not None:
+        res["obs_out"] = obs_out
+    if eps is not None:
+        res["action"], res["logp"] = action, logp
+    return res
+
+
+def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, v_boot: torch.Tensor,
+        cols_per_env: int, gamma: float, lam: float, adv: Optional[torch.Tensor] = None,
+        vtarg: Optional[torch.Tensor] = None, moments: Optional[torch.Tensor] = None,
+        ws: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """rewards, values [P,T,C] f32; dones [T,C/cols_per_env] u8; v_boot [P,C] -> adv, vtarg, moments [P,3] f64."""
+    lib = _lib.load()
+    P, T, Cc = rewards.shape
+    dev = rewards.device
+    adv = adv if adv is not None else torch.empty_like(rewards)
+    vtarg = vtarg if vtarg is not None else torch.empty_like(rewards)
+    moments = moments if moments is not None else torch.empty(P, 3, dtype=torch.float64, device=dev)
+    nbytes = lib.ddrl_gae_ws_bytes(P, Cc)
+    if ws is None or ws.numel() * ws.element_size() < nbytes:
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+    if tuple(dones.shape) != (T, Cc // cols_per_env):
+        raise DDRLError(f"dones shape {tuple(dones.shape)} != ({T}, {Cc // cols_per_env})")
+    _lib.check(lib.ddrl_gae(_p(rewards, torch.float32, "rewards"), _p(values, torch.float32, "values"),
+                            _p(dones, torch.uint8, "dones"), _p(v_boot, torch.float32, "v_boot"), P, T, Cc,
+                            cols_per_env, float(gamma), float(lam), _p(adv, torch.float32, "adv"),
+                            _p(vtarg, torch.float32, "vtarg"), _p(moments, torch.float64, "moments"),
+                            _p(ws, None, "ws"), _stream()), "gae")
+    return adv, vtarg, moments
+
+
+def adv_standardize(adv: torch.Tensor, moments: torch.Tensor) -> torch.Tensor:
+    P = adv.shape[0]
+    R = adv.numel() // P
+    _lib.check(_lib.load().ddrl_adv_standardize(_p(adv, torch.float32, "adv"), _p(moments, torch.float64, "moments"),
+                                                P, R, _stream()), "adv_standardize")
+    return adv
+
+
+def gather_rows(src: torch.Tensor, perm: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src [P,R,W] (or [P,R]) f32, perm [P,R] i32 -> dst[p,i] = src[p,perm[p,i]]."""
+    P, R = src.shape[:2]
+    W = src.numel() // (P * R)
+    dst = dst if dst is not None else torch.empty_like(src)
+    _lib.check(_lib.load().ddrl_gather_rows(_p(src, torch.float32, "src"), _p(perm, torch.int32, "perm"), P, R, W,
+                                            _p(dst, torch.float32, "dst"), _stream()), "gather_rows")
+    return dst
+
+
+def ppo_train_step(theta, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int,
+                   mb_perm, step_ctr, kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part,
+                   ext_dlogits=None, ext_dvalue=None):
+    lib = _lib.load()
+    P, R, D = obs.shape
+    f32 = torch.float32
+    perm_stride = mb_perm.shape[-1] if mb_perm is not None else 0
+    _lib.check(lib.ddrl_ppo_train_step(
+        _p(theta, f32, "theta"), _p(obs, f32, "obs"), _p(actions, f32, "actions"), _p(old_logits, f32, "old_logits"),
+        _p(old_logp, f32, "old_logp"), _p(vf_preds, f32, "vf_preds"), _p(adv, f32, "adv"), _p(vtarg, f32, "vtarg"),
+        _p(ext_dlogits, f32, "ext_dlogits"), _p(ext_dvalue, f32, "ext_dvalue"), P, R, D, A, MB,
+        _p(mb_perm, torch.int32, "mb_perm"), perm_stride, _p(step_ctr, torch.int32, "step_ctr"),
+        _p(kl_coeff, f32, "kl_coeff"), C.byref(hyper) if hyper is not None else None, ctas_per_policy,
+        _p(grad_part, f32, "grad_part"), _p(stat_part, torch.float64, "stat_part"), _stream()), "ppo_train_step")
+
+
+def grad_reduce(grad_part, stat_part, P: int, G: int, NP: int, grad, step_stats=None, step_ctr=None):
+    _lib.check(_lib.load().ddrl_grad_reduce(_p(grad_part, torch.float32, "grad_part"),
+                                            _p(stat_part, torch.float64, "stat_part"), P, G, NP,
+                                            _p(grad, torch.float32, "grad"), _p(step_stats, torch.float64, "step_stats"),
+                                            _p(step_ctr, torch.int32, "step_ctr"), _stream()), "grad_reduce")
+
+
+def clip_adam(theta, m, v, beta_pow, grad, lr: float, beta1: float, beta2: float, eps: float, grad_clip: float,
+              sync_ws, gnorm_out=None, step_ctr=None):
+    P, NP = theta.shape
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_clip_adam(_p(theta, f32, "theta"), _p(m, f32, "m"), _p(v, f32, "v"),
+                                          _p(beta_pow, f32, "beta_pow"), _p(grad, f32, "grad"), P, NP, float(lr),
+                                          float(beta1), float(beta2), float(eps), float(grad_clip),
+                                          _p(gnorm_out, f32, "gnorm_out"), _p(step_ctr, torch.int32, "step_ctr"),
+                                          _p(sync_ws, torch.int32, "sync_ws"), _stream()), "clip_adam")
+
+
+def fcnet_backward(theta, obs, dlogits, dvalue, A: int, ctas_per_policy: Optional[int] = None) -> torch.Tensor:
+    """External-gradient backward of the grouped FCNet: -> dtheta [P,NP] (torch.autograd boundary)."""
+    P, R, D = obs.shape
+    NP = theta.shape[1]
+    G = ctas_per_policy or max(1, min((R + 63) // 64, 148 // P))
+    gp = torch.empty(P, G, NP, dtype=torch.float32, device=obs.device)
+    grad = torch.empty(P, NP, dtype=torch.float32, device=obs.device)
+    ppo_train_step(theta, obs, None, None, None, None, None, None, A, R, None, None, None, None, G, gp, None,
+                   ext_dlogits=dlogits, ext_dvalue=dvalue)
+    grad_reduce(gp, None, P, G, NP, grad)
+    return grad
+
+
+# --------------------------------------------------------------------------------------------------
+def graphnet_forward(theta, node_idx, state, adj, A: int):
+    """theta [NP] (actor|critic), node_idx [B] i32, state [B,4,23], adj [B,4,4] -> logits [B,2A], value [B]."""
+    B = state.shape[0]
+    f32 = torch.float32
+    logits = torch.empty(B, 2 * A, dtype=f32, device=state.device)
+    value = torch.empty(B, dtype=f32, device=state.device)
+    if tuple(state.shape[1:]) != (GN_NODES, GN_FEATS + GN_ENC_IN) or tuple(adj.shape[1:]) != (GN_NODES, GN_NODES):
+        raise DDRLError(f"graphnet: state {tuple(state.shape)} / adj {tuple(adj.shape)} must be [B,4,23] / [B,4,4]")
+    if theta.numel() != graphnet_num_params(2 * A):
+        raise DDRLError(f"graphnet: theta has {theta.numel()} params, expected {graphnet_num_params(2 * A)}")
+    _lib.check(_lib.load().ddrl_graphnet_forward(_p(theta, f32, "theta"), _p(node_idx, torch.int32, "node_idx"),
+                                                 _p(state, f32, "state"), _p(adj, f32, "adj"), B, A,
+                                                 _p(logits, f32, "logits"), _p(value, f32, "value"), _stream()),
+               "graphnet_forward")
+    return logits, value
+
+
+def graphnet_backward(theta, node_idx, state, adj, dlogits, dvalue, A: int, ctas: Optional[int] = None):
+    B = state.shape[0]
+    f32 = torch.float32
+    NP = theta.numel()
+    G = ctas or max(1, min(B, 74))
+    gp = torch.zeros(G, NP, dtype=f32, device=state.device)
+    grad = torch.empty(1, NP, dtype=f32, device=state.device)
+    _lib.check(_lib.load().ddrl_graphnet_backward(_p(theta, f32, "theta"), _p(node_idx, torch.int32, "node_idx"),
+                                                  _p(state, f32, "state"), _p(adj, f32, "adj"),
+                                                  _p(dlogits, f32, "dlogits"), _p(dvalue, f32, "dvalue"), B, A, G,
+                                                  _p(gp, f32, "grad_part"), _stream()), "graphnet_backward")
+    grad_reduce(gp, None, 1, G, NP, grad)
+    return grad.reshape(-1)
+
+
+def gcn_forward(x, adj, W, b=None, act: str = "tanh"):
+    B, n, F = x.shape
+    U = W.shape[1]
+    y = torch.empty(B, n, U, dtype=torch.float32, device=x.device)
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_gcn_forward(_p(x, f32, "x"), _p(adj, f32, "adj"), _p(W, f32, "W"), _p(b, f32, "b"), B,
+                                            F, U, {"tanh": 1, None: 0, "linear": 0}[act], _p(y, f32, "y"), _stream()),
+               "gcn_forward")
+    return y
+
+
+def leg_coupling_(logits, node_id, coupling):
+    B, W = logits.shape
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_leg_coupling(_p(logits, f32, "logits"), _p(node_id, torch.int32, "node_id"),
+                                             _p(coupling, f32, "coupling"), B, W, _stream()), "leg_coupling")
+    return logits
+
+
+def filter_partial(x: torch.Tensor, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-rank half of the filter update: x [P,R,D] -> partials [P, nparts, D, 3] f64 {count, mean, M2}."""
+    lib = _lib.load()
+    P, R, D = x.shape
+    nparts = lib.ddrl_filter_num_partials(R)
+    if ws is None:
+        ws = torch.empty(P, nparts, D, 3, dtype=torch.float64, device=x.device)
+    _lib.check(lib.ddrl_filter_partial(_p(x, None, "x"), int(x.dtype == torch.float64), P, R, D,
+                                       _p(ws, torch.float64, "ws"), _stream()), "filter_partial")
+    return ws
+
+
+def filter_merge(parts: torch.Tensor, R_total: int, n, M, S, norm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fold parts [P, nparts, D, 3] (fixed order) into the running state; returns norm [P,2,D]."""
+    P, nparts, D, _ = parts.shape
+    if norm is None:
+        norm = torch.empty(P, 2, D, dtype=torch.float64, device=parts.device)
+    _lib.check(_lib.load().ddrl_filter_merge(_p(parts, torch.float64, "parts"), nparts, P, D, int(R_total),
+                                             _p(n, torch.int64, "n"), _p(M, torch.float64, "M"),
+                                             _p(S, torch.float64, "S"), _p(norm, torch.float64, "norm"), _stream()),
+               "filter_merge")
+    return norm
+
+
+def ppo_loss_grad(logits, value, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, kl_coeff,
+                  hyper: PPOHyper, ctas: int, dlogits, dvalue, stat_part):
+    """logits [P,R,2A], value [P,R] -> dlogits, dvalue (in the given buffers), stat_part [P,ctas,8] f64."""
+    P, R = value.shape
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_ppo_loss_grad(
+        _p(logits, f32, "logits"), _p(value, f32, "value"), _p(actions, f32, "actions"),
+        _p(old_logits, f32, "old_logits"), _p(old_logp, f32, "old_logp"), _p(vf_preds, f32, "vf_preds"),
+        _p(adv, f32, "adv"), _p(vtarg, f32, "vtarg"), P, R, A, _p(kl_coeff, f32, "kl_coeff"), C.byref(hyper), ctas,
+        _p(dlogits, f32, "dlogits"), _p(dvalue, f32, "dvalue"), _p(stat_part, torch.float64, "stat_part"), _stream()),
+        "ppo_loss_grad")
+
+
+def dg_sample(logits: torch.Tensor, eps: torch.Tensor):
+    """logits [R,2A], eps [R,A] -> action [R,A], logp [R]  (DiagGaussian sample, unclipped)."""
+    R, A = eps.shape
+    f32 = torch.float32
+    action = torch.empty(R, A, dtype=f32, device=logits.device)
+    logp = torch.empty(R, dtype=f32, device=logits.device)
+    _lib.check(_lib.load().ddrl_dg_sample(_p(logits, f32, "logits"), _p(eps, f32, "eps"), R, A, _p(action, f32, "action"),
+                                          _p(logp, f32, "logp"), _stream()), "dg_sample")
+    return action, logp

@@ -1,0 +1,352 @@
+"""Data-parallel PPO learner for the grouped per-leg controllers.
+
+One learner iteration on a rollout ``[T, C]`` per policy:
+  (i)   MeanStdFilter update + normalise, policy/value forward, DiagGaussian sample + logp   (K4, K1)
+  (ii)  bootstrap value, GAE, advantage standardisation                                       (K1, K5)
+  (iii) ``num_sgd_iter`` epochs of minibatch SGD: fused forward+PPO-loss+backward, fixed-order
+        gradient reduction, [NCCL all-reduce over ranks], global-norm clip + TF1 Adam        (K2/K6, K7)
+  (iv)  KL-coefficient update.
+It replaces what RLlib 1.0.1 executes around the reference's models for ``tune.run("PPO", ...)``
+(train_experiment_1_architecture_on_flat.py:201-211): sampler-side filter/forward, ``postprocess_ppo_gae``,
+``StandardizeFields``, ``TrainTFMultiGPU`` and ``UpdateKL``.  All policies of an architecture are
+processed by the same kernel launches ("grouped"); ranks shard the rollout by environment and exchange
+only the flat gradient (every optimizer step), the filter partials, the advantage moments and the
+learner-stat sums (once per iteration).
+
+All arithmetic runs in libddrl_b200.so; torch provides memory, streams, CUDA graphs and NCCL."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import DDRLError, PPOHyper
+from .config import PPOConfig
+
+STAT_NAMES = ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var")
+
+
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size(), dist.get_rank()
+    return None, 1, 0
+
+
+def finalize_stats(sums: np.ndarray, kl_coeff: np.ndarray, cfg: PPOConfig, rows: float) -> List[Dict[str, float]]:
+    """sums [steps, P, 8] float64 (per-minibatch stat sums over ``rows`` global rows) -> per-policy learner
+    stats averaged over the minibatches (float32 mean like RLlib's ``_averaged``)."""
+    steps, P, _ = sums.shape
+    n = float(rows)
+    out = []
+    for p in range(P):
+        s = sums[:, p, :]
+        pol, kl, vf, ent = s[:, 0] / n, s[:, 1] / n, s[:, 2] / n, s[:, 3] / n
+        total = pol + kl_coeff[p] * kl + cfg.vf_loss_coeff * vf - cfg.entropy_coeff * ent
+        yvar = s[:, 5] / n - (s[:, 4] / n) ** 2
+        dvar = s[:, 7] / n - (s[:, 6] / n) ** 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ev = np.maximum(-1.0, 1.0 - dvar / yvar)
+        m = lambda a: float(np.mean(a.astype(np.float32)))
+        out.append({"total_loss": m(total), "policy_loss": m(pol), "vf_loss": m(vf), "kl": m(kl), "entropy": m(ent),
+                    "vf_explained_var": m(ev), "cur_kl_coeff": float(kl_coeff[p]), "cur_lr": float(np.float32(cfg.lr)),
+                    "entropy_coeff": float(cfg.entropy_coeff)})
+    return out
+
+
+class _LearnerBase:
+    def __init__(self, P: int, NP: int, cfg: PPOConfig, device, theta: Optional[torch.Tensor]):
+        if not torch.cuda.is_available():
+            raise DDRLError("ddrl_b200 learners need a CUDA device (sm_100a); there is no CPU fallback")
+        self.P, self.NP, self.cfg = P, NP, cfg
+        self.device = torch.device(device)
+        f32 = torch.float32
+        self.theta = (theta.to(self.device, f32).contiguous().clone() if theta is not None
+                      else torch.zeros(P, NP, dtype=f32, device=self.device))
+        if tuple(self.theta.shape) != (P, NP):
+            raise DDRLError(f"theta shape {tuple(self.theta.shape)} != ({P}, {NP})")
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.beta_pow = torch.tensor([[cfg.beta1, cfg.beta2]] * P, dtype=f32, device=self.device)
+        self.kl_coeff_host = np.full(P, np.float32(cfg.kl_coeff), dtype=np.float64)
+        self.kl_coeff = torch.full((P,), cfg.kl_coeff, dtype=f32, device=self.device)
+        self.grad = torch.zeros(P, NP, dtype=f32, device=self.device)
+        self.gnorm = torch.zeros(P, dtype=f32, device=self.device)
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.sync_ws = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.dist, self.world, self.rank = _dist_world()
+
+    def _hyper(self, global_mb: int) -> PPOHyper:
+        c = self.cfg
+        return PPOHyper(c.clip_param, c.vf_clip_param, c.vf_loss_coeff, c.entropy_coeff, 1.0 / float(global_mb))
+
+    def _adam(self):
+        c = self.cfg
+        K.clip_adam(self.theta, self.m, self.v, self.beta_pow, self.grad, c.lr, c.beta1, c.beta2, c.adam_eps,
+                    c.grad_clip, self.sync_ws, self.gnorm, self.step_ctr)
+
+    def _update_kl(self, stats: List[Dict[str, float]]):
+        # KLCoeffMixin.update_kl (RLlib 1.0.1): x1.5 if kl > 2*target, x0.5 if kl < 0.5*target
+        for p, s in enumerate(stats):
+            if s["kl"] > 2.0 * self.cfg.kl_target:
+                self.kl_coeff_host[p] *= 1.5
+            elif s["kl"] < 0.5 * self.cfg.kl_target:
+                self.kl_coeff_host[p] *= 0.5
+        self.kl_coeff.copy_(torch.from_numpy(self.kl_coeff_host.astype(np.float32)), non_blocking=False)
+
+
+class FCNetLearner(_LearnerBase):
+    """P grouped FCNet policies (obs dim D, action dim A, hiddens [64,64], tanh, separate value net)."""
+
+    def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
+                 use_graph: bool = True, ctas_per_policy: Optional[int] = None):
+        super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
+        self.D, self.A = D, A
+        dev = self.device
+        self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
+        self.filt_M = torch.zeros(P, D, dtype=torch.float64, device=dev)
+        self.filt_S = torch.zeros(P, D, dtype=torch.float64, device=dev)
+        self.norm = torch.zeros(P, 2, D, dtype=torch.float64, device=dev)
+        self.use_graph = use_graph
+        self.ctas_per_policy = ctas_per_policy
+        self._bufs = None
+        self._graph = None
+        self._graph_key = None
+        self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    # ---- buffers ------------------------------------------------------------------------------------
+    def _alloc(self, T: int, Cc: int):
+        key = (T, Cc)
+        if self._bufs is not None and self._bufs["key"] == key:
+            return self._bufs
+        P, D, A, dev, f32 = self.P, self.D, self.A, self.device, torch.float32
+        R = T * Cc
+        b = {"key": key}
+        for name, w in (("obs", D), ("act", A), ("logits", 2 * A)):
+            b[name] = torch.empty(P, R, w, dtype=f32, device=dev)
+            b[name + "_s"] = torch.empty(P, R, w, dtype=f32, device=dev)
+        for name in ("logp", "value", "adv", "vtarg"):
+            b[name] = torch.empty(P, R, dtype=f32, device=dev)
+            b[name + "_s"] = torch.empty(P, R, dtype=f32, device=dev)
+        b["vboot"] = torch.empty(P, Cc, dtype=f32, device=dev)
+        b["moments"] = torch.empty(P, 3, dtype=torch.float64, device=dev)
+        b["gae_ws"] = torch.empty(max(8, P * ((Cc + 255) // 256) * 16), dtype=torch.uint8, device=dev)
+        b["filt_ws"] = None
+        self._bufs = b
+        self._graph = None
+        return b
+
+    def _sgd_setup(self, R: int):
+        cfg, P = self.cfg, self.P
+        MB = min(cfg.sgd_minibatch_size // self.world if self.world > 1 else cfg.sgd_minibatch_size, R)
+        if MB < 1:
+            raise DDRLError("sgd_minibatch_size smaller than the number of ranks")
+        nb = max(1, R // MB)
+        G = self.ctas_per_policy or max(1, min((MB + 15) // 16, self.sms // P))
+        return MB, nb, G
+
+    # ---- one optimizer step (3 kernels [+ NCCL]) -----------------------------------------------------------
+    def _sgd_step(self, b, MB, G, hyper, src):
+        K.ppo_train_step(self.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
+                         src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
+                         b["grad_part"], b["stat_part"])
+        K.grad_reduce(b["grad_part"], b["stat_part"], self.P, G, self.NP, self.grad, b["step_stats"], self.step_ctr)
+        if self.world > 1:
+            self.dist.all_reduce(self.grad)
+        self._adam()
+
+    # ---- the iteration --------------------------------------------------------------------------------------
+    def learn_on_rollout(self, raw_obs: torch.Tensor, boot_obs: torch.Tensor, rewards: torch.Tensor,
+                         dones: torch.Tensor, eps: torch.Tensor, perms: torch.Tensor,
+                         shuffle: Optional[torch.Tensor] = None, cols_per_env: int = 1,
+                         update_filter: bool = True) -> List[Dict[str, float]]:
+        """raw_obs [P,T,C,D] f32 (index-gathered per policy), boot_obs [P,C,D], rewards [P,T,C], dones [T,C/cpe] u8,
+        eps [P,T,C,A] (N(0,1) noise for action sampling), perms [P,E,nb] int32 (minibatch visiting order per epoch,
+        np.random.permutation(nb) in RLlib), shuffle [P,T*C] int32 row permutation or None.  All CUDA tensors.
+        Returns the per-policy learner stats of the LAST epoch and updates weights / Adam / filter / kl_coeff."""
+        P, T, Cc, D = raw_obs.shape
+        cfg, A = self.cfg, self.A
+        if D != self.D or P != self.P:
+            raise DDRLError(f"raw_obs shape {tuple(raw_obs.shape)} does not match learner (P={self.P}, D={self.D})")
+        R = T * Cc
+        b = self._alloc(T, Cc)
+        obs_flat = raw_obs.reshape(P, R, D)
+        # (i) filter + forward + sample ------------------------------------------------------------------
+        if update_filter:
+            if self.world > 1:
+                parts = K.filter_partial(obs_flat)
+                gathered = [torch.empty_like(parts) for _ in range(self.world)]
+                self.dist.all_gather(gathered, parts)
+                allp = torch.cat(gathered, dim=1).contiguous()          # [P, W*nparts, D, 3], rank order
+                K.filter_merge(allp, R * self.world, self.filt_n, self.filt_M, self.filt_S, self.norm)
+            else:
+                K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])
+        K.fcnet_forward(self.theta, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
+                        out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
+                             "logp": b["logp"]})
+        # (ii) bootstrap + GAE + standardise -----------------------------------------------------------
+        K.fcnet_forward(self.theta, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
+                        out={"logits": None, "value": b["vboot"], "obs_out": None})
+        K.gae(rewards, b["value"].view(P, T, Cc), dones, b["vboot"], cols_per_env, cfg.gamma, cfg.lambda_,
+              b["adv"].view(P, T, Cc), b["vtarg"].view(P, T, Cc), b["moments"], b["gae_ws"])
+        if self.world > 1:
+            self.dist.all_reduce(b["moments"])
+        K.adv_standardize(b["adv"], b["moments"])
+        # shuffle (SampleBatch.shuffle) -----------------------------------------------------------------
+        names = ("obs", "act", "logits", "logp", "value", "adv", "vtarg")
+        if shuffle is not None:
+            for nme in names:
+                K.gather_rows(b[nme], shuffle, b[nme + "_s"])
+            src = {n_: b[n_ + "_s"] for n_ in names}
+            src_key = "s"
+        else:
+            src = {n_: b[n_] for n_ in names}
+            src_key = "u"
+        # (iii) minibatch SGD ----------------------------------------------------------------------------
+        E = perms.shape[1]
+        MB, nb, G = self._sgd_setup(R)
+        if perms.shape[2] != nb:
+            raise DDRLError(f"perms has {perms.shape[2]} minibatches per epoch, expected {nb} (R={R}, MB={MB})")
+        steps = E * nb
+        if b.get("sgd_key") != (steps, G):
+            b["sgd_key"] = (steps, G)
+            b["mb_perm"] = torch.empty(P, steps, dtype=torch.int32, device=self.device)
+            b["grad_part"] = torch.empty(P, G, self.NP, dtype=torch.float32, device=self.device)
+            b["stat_part"] = torch.empty(P, G, K.NSTAT, dtype=torch.float64, device=self.device)
+            b["step_stats"] = torch.zeros(steps, P, K.NSTAT, dtype=torch.float64, device=self.device)
+            self._graph = None
+        b["mb_perm"].copy_(perms.reshape(P, steps))
+        self.step_ctr.zero_()
+        hyper = self._hyper(MB * self.world)
+        if self.use_graph and self.world == 1:
+            key = (T, Cc, steps, G, MB, src_key)
+            if self._graph is None or self._graph_key != key:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                # the capture itself executes nothing; kernels read step_ctr / mb_perm / kl_coeff from device memory
+                with torch.cuda.graph(g):
+                    for _ in range(nb):
+                        self._sgd_step(b, MB, G, hyper, src)
+                self._graph, self._graph_key, self._graph_hyper = g, key, hyper
+            for _ in range(E):
+                self._graph.replay()
+        else:
+            for _ in range(steps):
+                self._sgd_step(b, MB, G, hyper, src)
+        # (iv) stats + KL update ----------------------------------------------------------------------------
+        last = b["step_stats"][steps - nb:].clone()
+        if self.world > 1:
+            self.dist.all_reduce(last)
+        stats = finalize_stats(last.cpu().numpy(), self.kl_coeff_host, cfg, MB * self.world)
+        self._update_kl(stats)
+        self.last_launches_per_iter = None
+        return stats
+
+    # ---- plain inference (sampler side) ---------------------------------------------------------------------
+    def compute_actions(self, raw_obs: torch.Tensor, eps: Optional[torch.Tensor] = None, update_filter: bool = False):
+        """raw_obs [P,B,D] -> dict(logits, value[, action, logp]); optionally pushes the rows into the filter first
+        (RLlib sampler behaviour)."""
+        if update_filter:
+            K.filter_update(raw_obs, self.filt_n, self.filt_M, self.filt_S, self.norm)
+        use_norm = self.norm if int(self.filt_n.max().item()) > 0 else None
+        return K.fcnet_forward(self.theta, raw_obs, self.A, norm=use_norm, clip=self.cfg.filter_clip, eps=eps)
+
+
+class GraphNetLearner(_LearnerBase):
+    """One shared GraphNet policy (actor GraphNet(2A) + critic GraphNet(1)) over the 4-leg graph
+    (models/shared_graphnet_glorot_uniform_init.py:21-58; env QuantrupedMultiEnv_DecentralShared_Graph).
+    The observations reach the model already normalised (the env-side filter runs before the tuple is built,
+    quantruped_GraphDecentralizedController_environments.py:219-233), so there is no filter stage here."""
+
+    def __init__(self, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
+                 ctas: Optional[int] = None):
+        super().__init__(1, K.graphnet_num_params(2 * A), cfg, device, theta)
+        self.A = A
+        self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.ctas = ctas or max(1, self.sms // 2)
+
+    def forward(self, node_idx, state, adj):
+        return K.graphnet_forward(self.theta.reshape(-1), node_idx, state, adj, self.A)
+
+    def learn_on_rollout(self, node_idx, state, adj, boot_node_idx, boot_state, boot_adj, rewards, dones, eps, perms,
+                         shuffle=None, cols_per_env: int = 4) -> List[Dict[str, float]]:
+        """node_idx [T,C] i32, state [T,C,4,23], adj [T,C,4,4], boot_* the same without T, rewards [T,C],
+        dones [T,C/cpe] u8, eps [T,C,A], perms [E,nb] i32, shuffle [T*C] i32 or None."""
+        T, Cc = node_idx.shape
+        A, cfg, dev, f32 = self.A, self.cfg, self.device, torch.float32
+        R = T * Cc
+        th = self.theta.reshape(-1)
+        idx_f, st_f, adj_f = node_idx.reshape(R), state.reshape(R, 4, 23), adj.reshape(R, 4, 4)
+        logits, value = K.graphnet_forward(th, idx_f, st_f, adj_f, A)
+        act, logp = K.dg_sample(logits, eps.reshape(R, A).contiguous())
+        _, vboot = K.graphnet_forward(th, boot_node_idx.reshape(Cc), boot_state, boot_adj, A)
+        adv, vtarg, moments = K.gae(rewards.reshape(1, T, Cc), value.reshape(1, T, Cc), dones, vboot.reshape(1, Cc),
+                                    cols_per_env, cfg.gamma, cfg.lambda_)
+        if self.world > 1:
+            self.dist.all_reduce(moments)
+        K.adv_standardize(adv, moments)
+        cols = {"idx": idx_f, "st": st_f, "adj": adj_f, "act": act, "logits": logits, "logp": logp,
+                "value": value, "adv": adv.reshape(R), "vtarg": vtarg.reshape(R)}
+        if shuffle is not None:
+            sl = shuffle.long()
+            cols = {k: v[sl].contiguous() for k, v in cols.items()}
+        MB = min(cfg.sgd_minibatch_size // self.world if self.world > 1 else cfg.sgd_minibatch_size, R)
+        E, nb = perms.shape
+        if nb != max(1, R // MB):
+            raise DDRLError(f"perms has {nb} minibatches per epoch, expected {max(1, R // MB)}")
+        hyper = self._hyper(MB * self.world)
+        G = min(self.ctas, MB)
+        LG = max(1, min(64, (MB + 255) // 256))
+        dlogits = torch.empty(MB, 2 * A, dtype=f32, device=dev)
+        dvalue = torch.empty(MB, dtype=f32, device=dev)
+        gpart = torch.empty(G, self.NP, dtype=f32, device=dev)
+        spart = torch.empty(1, LG, K.NSTAT, dtype=torch.float64, device=dev)
+        step_stats = torch.zeros(E * nb, 1, K.NSTAT, dtype=torch.float64, device=dev)
+        order = perms.cpu().numpy()
+        self.step_ctr.zero_()
+        for e in range(E):
+            for i in range(nb):
+                r0 = int(order[e, i]) * MB
+                sl = slice(r0, r0 + MB)
+                lg, vl = K.graphnet_forward(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], A)
+                K.ppo_loss_grad(lg.reshape(1, MB, 2 * A), vl.reshape(1, MB), cols["act"][sl], cols["logits"][sl],
+                                cols["logp"][sl], cols["value"][sl], cols["adv"][sl], cols["vtarg"][sl], A,
+                                self.kl_coeff, hyper, LG, dlogits, dvalue, spart)
+                _lib_backward(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], dlogits, dvalue, MB, A, G, gpart)
+                # grad_part [G, NP] -> grad [1, NP]; loss-stat partials [1, LG, 8] -> step_stats[step]
+                K.grad_reduce(gpart, None, 1, G, self.NP, self.grad)
+                _reduce_stats(spart, step_stats, self.step_ctr)
+                if self.world > 1:
+                    self.dist.all_reduce(self.grad)
+                self._adam()
+        last = step_stats[E * nb - nb:].clone()
+        if self.world > 1:
+            self.dist.all_reduce(last)
+        stats = finalize_stats(last.cpu().numpy(), self.kl_coeff_host, cfg, MB * self.world)
+        self._update_kl(stats)
+        return stats
+
+
+def _lib_backward(th, idx, st, adj, dlogits, dvalue, B, A, G, gpart):
+    from . import _lib
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_graphnet_backward(K._p(th, f32, "theta"), K._p(idx, torch.int32, "node_idx"),
+                                                  K._p(st, f32, "state"), K._p(adj, f32, "adj"),
+                                                  K._p(dlogits, f32, "dlogits"), K._p(dvalue, f32, "dvalue"), B, A, G,
+                                                  K._p(gpart, f32, "grad_part"), K._stream()), "graphnet_backward")
+
+
+def _reduce_stats(spart: torch.Tensor, step_stats: torch.Tensor, step_ctr: torch.Tensor):
+    """stat partials [1, LG, 8] -> step_stats[*step_ctr] via the C-ABI reducer (its gradient half runs on a dummy)."""
+    from . import _lib
+    P, LG, _ = spart.shape
+    dummy = _reduce_stats.__dict__.setdefault("dummy", {})
+    key = (spart.device, LG)
+    if key not in dummy:
+        dummy[key] = (torch.zeros(P, LG, 1, dtype=torch.float32, device=spart.device),
+                      torch.zeros(P, 1, dtype=torch.float32, device=spart.device))
+    gp, g = dummy[key]
+    K.grad_reduce(gp, spart, P, LG, 1, g, step_stats, step_ctr)

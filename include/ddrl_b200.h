@@ -1,0 +1,214 @@
+/* ddrl_b200.h — C ABI of libddrl_b200.so (B200 / sm_100a learner hot path of DDRL).
+ *
+ * The reference (LucaHermes/ddrl) is pure Python on TF/RLlib and has NO FFI; this header is the
+ * boundary a maintainer binds with ctypes/cffi (INTEGRATION.md shows the stub).  Each entry point
+ * names the reference computation it replaces (paths relative to the reference repo root; "RLlib"
+ * = ray[rllib]==1.0.1, the version README.md:47 pins).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer to contiguous row-major memory unless it says "host";
+ *     model tensors are float32, filter state float64, counts int64, indices int32, dones uint8;
+ *   - shapes are explicit ints; the last argument is the cudaStream_t to launch on (as void*);
+ *   - no allocation, no host synchronisation, no ownership transfer: the caller owns every buffer,
+ *     including the workspaces whose sizes the *_bytes() helpers return;
+ *   - return 0 on success, <0 on error (DDRL_E_*); ddrl_last_error() gives the thread-local text;
+ *   - re-entrant and thread-safe per (device, stream);
+ *   - there is NO CPU fallback: without an sm_100 device every launch returns DDRL_E_CUDA.
+ */
+#ifndef DDRL_B200_H
+#define DDRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDRL_OK 0
+#define DDRL_E_BADARG (-1)
+#define DDRL_E_UNSUPPORTED_SHAPE (-2)
+#define DDRL_E_WORKSPACE (-3)
+#define DDRL_E_CUDA (-4)
+
+#define DDRL_HIDDEN 64      /* fcnet_hiddens = [64, 64] in every published params.json            */
+#define DDRL_MAX_OBS 64     /* D <= 64  (reference: 19..44)                                        */
+#define DDRL_MAX_ACT 8      /* A <= 8   (reference: 2, 4, 8)                                       */
+#define DDRL_NSTAT 8        /* per-minibatch stat sums, see ddrl_ppo_train_step                    */
+#define DDRL_GN_NODES 4     /* legs of the quantruped graph                                        */
+#define DDRL_GN_FEATS 19    /* per-leg features, hard-coded in models/graph_net.py:16,35           */
+#define DDRL_GN_ENC_IN 4    /* state[..., -4:]  models/graph_net.py:33                             */
+
+const char* ddrl_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int ddrl_abi_version(void);
+/* Number of kernels this library has launched in the calling process (monotonic; for bench.py's
+ * "gpu_launches" claim). */
+int64_t ddrl_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * FCNet parameter layout.  One flat float32 vector per policy in the Keras/checkpoint variable
+ * order of models/fcnet_glorot_uniform_init.py:48-113 with vf_share_layers=false:
+ *   fc_1/kernel[D,64] fc_1/bias[64] fc_value_1/kernel[D,64] fc_value_1/bias[64]
+ *   fc_2/kernel[64,64] fc_2/bias[64] fc_value_2/kernel[64,64] fc_value_2/bias[64]
+ *   fc_out/kernel[64,2A] fc_out/bias[2A] value_out/kernel[64,1] value_out/bias[1]
+ * = 128*D + 130*A + 8513 floats.  P policies are stored as theta[P][NP].
+ * ------------------------------------------------------------------------------------------- */
+int ddrl_fcnet_num_params(int D, int A);
+
+/* Replaces: ray.rllib.utils.filter.MeanStdFilter.__call__ (vectorised update), instantiated at
+ * simulation_envs/observation_filter.py:8-12 and by observation_filter="MeanStdFilter"
+ * (train_experiment_3_architecture_curriculum_targetvel.py:71).
+ * Pushes rows x[p][0..R) into the running statistics of policy p (Chan merge of fixed-order chunk
+ * partials; n is exact int64) and writes norm[p] = {mean[D], 1/(std+1e-8)[D]} (float64) computed
+ * from the UPDATED state, where std = sqrt(S/(n-1)) (n>1) or |M| (n<=1).
+ *   x        [P][R][D] float32 (x_is_f64=0) or float64 (x_is_f64=1)
+ *   n        [P] int64, M [P][D] float64, S [P][D] float64      (in/out)
+ *   norm     [P][2][D] float64                                    (out)
+ *   ws       workspace of ddrl_filter_ws_bytes(P, R, D) bytes
+ * R == 0 only refreshes norm. */
+int64_t ddrl_filter_ws_bytes(int P, int64_t R, int D);
+int ddrl_filter_update(const void* x, int x_is_f64, int P, int64_t R, int D, int64_t* n, double* M,
+                       double* S, double* norm, void* ws, void* stream);
+/* The two halves of ddrl_filter_update, for data-parallel learners (RLlib FilterManager.synchronize:
+ * worker filter buffers are merged into the driver copy): every rank runs ddrl_filter_partial on its
+ * own rows, the workspaces are all-gathered and concatenated per policy in rank order to
+ * parts [P][nparts][D][3] float64 = {count, mean, M2}, and ddrl_filter_merge folds them into the
+ * running state in that fixed order (R_total = rows summed over all parts; n stays exact).
+ * ddrl_filter_num_partials(R) = partials per policy that ddrl_filter_partial writes for R rows. */
+int ddrl_filter_num_partials(int64_t R);
+int ddrl_filter_partial(const void* x, int x_is_f64, int P, int64_t R, int D, void* ws, void* stream);
+int ddrl_filter_merge(const void* parts, int nparts, int P, int D, int64_t R_total, int64_t* n,
+                      double* M, double* S, double* norm, void* stream);
+
+/* Replaces: FullyConnectedNetwork_GlorotUniformInitializer.forward / value_function
+ * (models/fcnet_glorot_uniform_init.py:120-125) for P grouped policies, with optional fused
+ * prologue/epilogue:
+ *   obs      [P][R][D] float32 raw or already-normalised observations
+ *   norm     [P][2][D] float64 or NULL: if given, x = (float)((double)obs - mean) * inv)  (the
+ *            MeanStdFilter output, cast to float32 as RLlib does at the policy input)
+ *   clip     >0: clip normalised obs to [-clip, clip] (env-singleton filter path, clip=10); 0: none
+ *   obs_out  [P][R][D] float32 or NULL: the network input actually used (stored for the SGD epochs)
+ *   logits   [P][R][2A], value [P][R]                         (out; either may be NULL)
+ *   eps      [P][R][A] float32 or NULL: if given, DiagGaussian sample (RLlib
+ *            models/tf/tf_action_dist.py): action = mean + exp(log_std)*eps -> action [P][R][A]
+ *            (unclipped, as stored in the sample batch) and logp [P][R]. */
+int ddrl_fcnet_forward(const float* theta, const float* obs, const double* norm, float clip,
+                       int P, int64_t R, int D, int A, float* obs_out, float* logits, float* value,
+                       const float* eps, float* action, float* logp, void* stream);
+
+/* Replaces: compute_advantages + postprocess_ppo_gae (RLlib evaluation/postprocessing.py,
+ * agents/ppo/ppo_tf_policy.py), selected by use_gae/gamma/lambda at
+ * train_experiment_1_architecture_on_flat.py:119-120.  Reverse scan per column in float64:
+ *   delta_t = r_t + gamma*(1-done_t)*V_{t+1} - V_t ;  A_t = delta_t + gamma*lambda*(1-done_t)*A_{t+1}
+ *   rewards, values [P][T][C] float32; dones [T][C/cols_per_env] uint8 (shared by the policies and
+ *   by the cols_per_env agent columns of one env); v_boot [P][C] float32 (V of the obs after step T-1)
+ *   adv, vtarg [P][T][C] float32 (out);  moments [P][3] float64 (out): {count, sum(adv), sum(adv^2)}
+ *   ws: ddrl_gae_ws_bytes(P, C). */
+int64_t ddrl_gae_ws_bytes(int P, int64_t C);
+int ddrl_gae(const float* rewards, const float* values, const uint8_t* dones, const float* v_boot,
+             int P, int T, int64_t C, int cols_per_env, float gamma, float lambda, float* adv,
+             float* vtarg, double* moments, void* ws, void* stream);
+
+/* Replaces: StandardizeFields(["advantages"]) (RLlib execution/rollout_ops.py):
+ *   adv <- (adv - mean) / max(1e-4, std)  per policy, population std, from moments[P][3]
+ *   (moments may have been all-reduced across ranks first). In place. */
+int ddrl_adv_standardize(float* adv, const double* moments, int P, int64_t R, void* stream);
+
+/* Replaces: SampleBatch.shuffle() in TrainTFMultiGPU (RLlib execution/train_ops.py;
+ * shuffle_sequences=true).  dst[p][i][:] = src[p][perm[p][i]][:] for a [P][R][W] float32 array. */
+int ddrl_gather_rows(const float* src, const int32_t* perm, int P, int64_t R, int W, float* dst,
+                     void* stream);
+
+/* One minibatch of: model forward + PPOLoss + backward (no optimizer).
+ * Replaces: one session.run of loss+grads in TrainTFMultiGPU for all P policies at once
+ * (RLlib agents/ppo/ppo_tf_policy.py PPOLoss; DiagGaussian logp/kl/entropy).
+ * Batch arrays are [P][R][*] float32; the minibatch is rows [mb*MB, (mb+1)*MB) where
+ *   mb = mb_perm[p][*step_ctr]          (device ints; lets one CUDA graph serve every step)
+ *   kl_coeff [P] float32 (device),  hyper (host values): clip_param, vf_clip_param, vf_loss_coeff,
+ *   entropy_coeff, inv_global_mb = 1 / (MB summed over all ranks).
+ * Outputs (workspace, per CTA, reduced by ddrl_grad_reduce in fixed order -> deterministic):
+ *   grad_part [P][G][NP] float32, stat_part [P][G][DDRL_NSTAT] float64, G = ctas_per_policy
+ *   stat sums: 0 sum(-surr) 1 sum(kl) 2 sum(vf) 3 sum(entropy) 4 sum(R) 5 sum(R^2)
+ *              6 sum(R-v) 7 sum((R-v)^2)       (R = value_targets)
+ * If ext_dlogits != NULL the loss is skipped and the row gradients are read from
+ * ext_dlogits [P][R][2A] / ext_dvalue [P][R] (torch.autograd boundary of the ModelV2 classes). */
+typedef struct {
+    float clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff, inv_global_mb;
+} ddrl_ppo_hyper;
+
+int ddrl_ppo_train_step(const float* theta, const float* obs, const float* actions,
+                        const float* old_logits, const float* old_logp, const float* vf_preds,
+                        const float* adv, const float* vtarg, const float* ext_dlogits,
+                        const float* ext_dvalue, int P, int64_t R, int D, int A, int MB,
+                        const int32_t* mb_perm, int64_t perm_stride, const int32_t* step_ctr,
+                        const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas_per_policy,
+                        float* grad_part, double* stat_part, void* stream);
+
+/* Stand-alone PPOLoss gradient w.r.t. the model outputs (same arithmetic as the fused kernel), for
+ * models whose forward/backward are separate kernels (GraphNet):
+ *   logits [P][R][2A], value [P][R] + batch arrays -> dlogits [P][R][2A], dvalue [P][R],
+ *   stat_part [P][ctas][DDRL_NSTAT] float64 (reduce with ddrl_grad_reduce's stat path). */
+int ddrl_ppo_loss_grad(const float* logits, const float* value, const float* actions,
+                       const float* old_logits, const float* old_logp, const float* vf_preds,
+                       const float* adv, const float* vtarg, int P, int64_t R, int A,
+                       const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas, float* dlogits,
+                       float* dvalue, double* stat_part, void* stream);
+
+/* Fixed-order reduction of the per-CTA partials:
+ *   grad [P][NP] float32 = sum_g grad_part[p][g][:]
+ *   step_stats [*step_ctr][P][DDRL_NSTAT] float64 = sum_g stat_part[p][g][:]   (if step_stats) */
+int ddrl_grad_reduce(const float* grad_part, const double* stat_part, int P, int G, int NP,
+                     float* grad, double* step_stats, const int32_t* step_ctr, void* stream);
+
+/* Replaces: tf.clip_by_global_norm(grads, grad_clip) (RLlib ppo_tf_policy.clip_gradients) and
+ * tf.compat.v1.train.AdamOptimizer.apply_gradients, per policy:
+ *   scale = clip / max(||g||_2, clip);  lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+ *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  theta -= lr_t*m/(sqrt(v)+eps);  b1^t,b2^t *= b1,b2
+ *   grad [P][NP] (may have been NCCL-all-reduced), theta/m/v [P][NP],
+ *   beta_pow [P][2] (device) = {b1^t, b2^t} to be used by THIS step (TF convention: initialised to
+ *   {b1, b2}, multiplied after the update), gnorm_out [P] or NULL,
+ *   sync_ws: one zero-initialised int32 (device) used as an arrival ticket; the last CTA to finish
+ *   multiplies the beta powers, increments *step_ctr (if not NULL) and re-zeroes the ticket. */
+int ddrl_clip_adam(float* theta, float* m, float* v, float* beta_pow, const float* grad, int P,
+                   int NP, float lr, float beta1, float beta2, float eps, float grad_clip,
+                   float* gnorm_out, int32_t* step_ctr, int32_t* sync_ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GraphNet (models/graph_net.py:10-45) + actor/critic wrapper
+ * (models/shared_graphnet_glorot_uniform_init.py:21-58).  Parameter layout per GraphNet(O), Keras
+ * variable order: state_enc/kernel[4,19*64] state_enc/bias[19*64] msg_transform/kernel[64,64]
+ * node_update/kernel[64,64] linear_out/kernel[64,O] linear_out/bias[O]; the wrapper stores
+ * theta = [actor GraphNet(2A) | critic GraphNet(1)].
+ *   node_idx [B] int32, state [B][4][23] float32, adj [B][4][4] float32 (adj[s][r]!=0: edge s->r)
+ *   -> logits [B][2A], value [B].
+ * ------------------------------------------------------------------------------------------- */
+int ddrl_graphnet_num_params(int num_outputs);
+int ddrl_graphnet_forward(const float* theta, const int32_t* node_idx, const float* state,
+                          const float* adj, int64_t B, int A, float* logits, float* value,
+                          void* stream);
+/* Backward of the wrapper w.r.t. theta from dlogits [B][2A], dvalue [B]:
+ *   grad_part [G][NP] per-CTA partials (reduce with ddrl_grad_reduce(P=1)); G = ctas. */
+int ddrl_graphnet_backward(const float* theta, const int32_t* node_idx, const float* state,
+                           const float* adj, const float* dlogits, const float* dvalue, int64_t B,
+                           int A, int ctas, float* grad_part, void* stream);
+
+/* GCN layer (models/gcn.py:7-37, graph_ops.adj_norm models/graph_ops.py:13-21):
+ *   y = act((D^-1 A) X W + b), X [B][4][F], A [B][4][4], W [F][U], b [U] or NULL, act: 0 none 1 tanh */
+int ddrl_gcn_forward(const float* x, const float* adj, const float* W, const float* b, int64_t B,
+                     int F, int U, int act, float* y, void* stream);
+
+/* DiagGaussian sample + logp (RLlib models/tf/tf_action_dist.py DiagGaussian._build_sample_op / logp)
+ * for models without a fused epilogue: action = mean + exp(log_std)*eps, logp(action).
+ *   logits [R][2A], eps [R][A] -> action [R][A], logp [R]. */
+int ddrl_dg_sample(const float* logits, const float* eps, int64_t R, int A, float* action, float* logp,
+                   void* stream);
+
+/* LegCoupling (models/coupling_net_glorot_uniform_init.py:11-30,135):
+ *   logits[b][j] *= (j < 2 ? coupling[node_id[b]][j] : 1)      in place; coupling [4][2]. */
+int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupling, int64_t B,
+                      int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDRL_B200_H */

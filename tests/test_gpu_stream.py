@@ -1,0 +1,148 @@
+"""GPU parity of the streaming kernels: MeanStdFilter, GAE, standardisation, shuffle, DiagGaussian sample,
+LegCoupling — CUDA (C ABI) vs the oracle restating RLlib 1.0.1."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import ckpt_theta, scaled_err, synth_obs
+
+pytestmark = pytest.mark.gpu
+
+
+def _O():
+    import oracle.ddrl_oracle as O
+    return O
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype is not None else t).cuda()
+
+
+@pytest.mark.parametrize("R,dtype", [(1, np.float32), (2, np.float32), (127, np.float32), (128, np.float64),
+                                     (1000, np.float32), (20000, np.float32), (3001, np.float64)])
+def test_filter_update_matches_sequential_welford(R, dtype):
+    """count bit-exact; mean / M2 within 1e-12 rel of the reference's sequential push order; two successive
+    updates (state carried over) and the refreshed normalisation constants."""
+    from ddrl_b200 import kernels as K
+    O = _O()
+    _, filt, D, _ = ckpt_theta("FullyDecentral")
+    P = len(filt)
+    x1 = synth_obs(filt, R, 1).astype(dtype)
+    x2 = synth_obs(filt, R // 2 + 1, 2).astype(dtype)
+    n = torch.zeros(P, dtype=torch.int64, device="cuda")
+    M = torch.zeros(P, D, dtype=torch.float64, device="cuda")
+    S = torch.zeros(P, D, dtype=torch.float64, device="cuda")
+    refs = [O.MeanStdFilter((D,), clip=None) for _ in range(P)]
+    for x in (x1, x2):
+        norm = K.filter_update(_dev(x), n, M, S)
+        torch.cuda.synchronize()
+        for p in range(P):
+            refs[p](x[p])
+            rs = refs[p].rs
+            assert int(n[p]) == rs._n                                   # bit-exact count
+            np.testing.assert_allclose(M[p].cpu().numpy(), rs._M, rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(S[p].cpu().numpy(), rs._S, rtol=1e-11, atol=1e-18)
+            np.testing.assert_allclose(norm[p, 0].cpu().numpy(), rs.mean, rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(norm[p, 1].cpu().numpy(), 1.0 / (rs.std + 1e-8), rtol=1e-11)
+
+
+def test_filter_partial_merge_equals_single_update():
+    """Data-parallel path: per-rank partials concatenated in rank order == one update over all rows."""
+    from ddrl_b200 import kernels as K
+    _, filt, D, _ = ckpt_theta("Local")
+    P = len(filt)
+    x = synth_obs(filt, 3000, 3)
+    st = lambda: (torch.zeros(P, dtype=torch.int64, device="cuda"), torch.zeros(P, D, dtype=torch.float64, device="cuda"),
+                  torch.zeros(P, D, dtype=torch.float64, device="cuda"))
+    n1, M1, S1 = st()
+    K.filter_update(_dev(x), n1, M1, S1)
+    n2, M2, S2 = st()
+    parts = [K.filter_partial(_dev(x[:, i * 750:(i + 1) * 750])) for i in range(4)]
+    K.filter_merge(torch.cat(parts, dim=1).contiguous(), 3000, n2, M2, S2)
+    torch.cuda.synchronize()
+    assert torch.equal(n1, n2)
+    np.testing.assert_allclose(M2.cpu().numpy(), M1.cpu().numpy(), rtol=1e-13)
+    np.testing.assert_allclose(S2.cpu().numpy(), S1.cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("T,C,cpe,pdone", [(1, 1, 1, 0.0), (32, 300, 1, 0.03), (200, 8, 1, 0.005), (32, 64, 4, 0.1),
+                                           (7, 1000, 2, 1.0), (50, 33, 1, 0.0)])
+def test_gae_matches_reference_fragment_procedure(T, C, cpe, pdone):
+    """vs compute_advantages applied per fragment (scipy.signal.lfilter in float64, cast to float32)."""
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(T * 1000 + C)
+    P = 2
+    r = (0.3 + 0.5 * rng.standard_normal((P, T, C))).astype(np.float32)
+    v = (20 * rng.standard_normal((P, T, C))).astype(np.float32)
+    vb = (20 * rng.standard_normal((P, C))).astype(np.float32)
+    d_env = (rng.random((T, C // cpe)) < pdone).astype(np.uint8)
+    adv, vt, mom = K.gae(_dev(r), _dev(v), _dev(d_env), _dev(vb), cpe, 0.99, 0.95)
+    torch.cuda.synchronize()
+    d_col = np.repeat(d_env, cpe, axis=1)
+    for p in range(P):
+        a_ref, vt_ref = O.gae_columns(r[p], v[p], d_col, vb[p], 0.99, 0.95)
+        # float64 recursion on both sides, one rounding to float32: allow 1 ulp
+        np.testing.assert_allclose(adv[p].cpu().numpy(), a_ref, rtol=2e-7, atol=1e-6)
+        np.testing.assert_allclose(vt[p].cpu().numpy(), vt_ref, rtol=2e-7, atol=1e-6)
+        a64 = adv[p].cpu().numpy().astype(np.float64)
+        assert mom[p, 0].item() == T * C
+        np.testing.assert_allclose(mom[p, 1].item(), a64.sum(), rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(mom[p, 2].item(), (a64 ** 2).sum(), rtol=1e-12)
+
+
+def test_adv_standardize_matches_numpy():
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(5)
+    a = (3.0 + 7.0 * rng.standard_normal((3, 4096))).astype(np.float32)
+    a[2] = 1.25                                # zero variance -> max(1e-4, std) floor
+    mom = np.stack([[a.shape[1], a[p].astype(np.float64).sum(), (a[p].astype(np.float64) ** 2).sum()] for p in range(3)])
+    out = K.adv_standardize(_dev(a.copy()), _dev(mom))
+    torch.cuda.synchronize()
+    for p in range(3):
+        ref = O.standardized(a[p])
+        np.testing.assert_allclose(out[p].cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_gather_rows_is_exact():
+    from ddrl_b200 import kernels as K
+    rng = np.random.default_rng(6)
+    for W in (1, 2, 19, 44):
+        src = rng.standard_normal((3, 1000, W)).astype(np.float32)
+        perm = np.stack([rng.permutation(1000) for _ in range(3)]).astype(np.int32)
+        dst = K.gather_rows(_dev(src), _dev(perm))
+        torch.cuda.synchronize()
+        ref = np.stack([src[p][perm[p]] for p in range(3)])
+        assert np.array_equal(dst.cpu().numpy(), ref)
+
+
+def test_dg_sample_and_leg_coupling():
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(8)
+    for A in (2, 4, 8):
+        lg = rng.standard_normal((500, 2 * A)).astype(np.float32)
+        eps = rng.standard_normal((500, A)).astype(np.float32)
+        act, logp = K.dg_sample(_dev(lg), _dev(eps))
+        a_ref = O.dg_sample(torch.from_numpy(lg).double(), torch.from_numpy(eps).double())
+        assert scaled_err(act.cpu().numpy(), a_ref.numpy()) < 1e-6
+        assert scaled_err(logp.cpu().numpy(), O.dg_logp(torch.from_numpy(lg).double(), a_ref).numpy()) < 1e-5
+    lg = rng.standard_normal((333, 4)).astype(np.float32)
+    nid = rng.integers(0, 4, size=333).astype(np.int32)
+    coup = np.array(O.COUPLING_INIT, dtype=np.float32) * 0.7
+    out = K.leg_coupling_(_dev(lg.copy()), _dev(nid), _dev(coup))
+    ref = O.leg_coupling(torch.from_numpy(lg), torch.from_numpy(nid), torch.from_numpy(coup))
+    assert np.array_equal(out.cpu().numpy(), ref.numpy())
+
+
+def test_bad_arguments_fail_loudly():
+    from ddrl_b200 import kernels as K
+    from ddrl_b200._lib import DDRLError
+    with pytest.raises(DDRLError):
+        K.fcnet_forward(torch.zeros(1, 10, device="cuda"), torch.zeros(1, 4, 19, device="cuda"), 2)   # wrong NP
+    with pytest.raises(DDRLError):
+        K.fcnet_forward(torch.zeros(1, 11205), torch.zeros(1, 4, 19), 2)                               # CPU tensors
+    with pytest.raises(DDRLError):
+        K.fcnet_num_params(100, 2)                                                                     # D > 64
