@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the DDRL learner hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE learner iteration of the BASELINE.json configs[1] workload
+(FullyDecentral: 4 per-leg FCNet policies 19->2, 4096 parallel envs per GPU, fragment T=32, 10 SGD epochs):
+filter update+normalise -> forward/sample/logp/value -> bootstrap -> GAE -> standardise -> shuffle ->
+10 x 32 minibatch steps (fused fwd + PPO loss + bwd, gradient reduce, [NCCL all-reduce], clip + TF1 Adam)
+-> KL-coefficient update.  Metric: agent-steps/s = T * envs * agents / time, whole job over all ranks.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="FullyDecentral (BASELINE.json configs[1])", P=4, Ag=4, D=19, A=2, envs_per_gpu=4096, T=32,
+                epochs=10, minibatches_per_epoch=32)
+METRIC = "PPO learner agent-steps/sec (fwd+GAE+update)"
+UNIT = "agent-steps/s"
+
+
+def flops_per_agent_step(D, A, E):
+    """MACs = (1+3E)*F - 128*E*D, F = 128D + 128A + 8256; flops = 2x."""
+    F = 128 * D + 128 * A + 8256
+    return 2 * ((1 + 3 * E) * F - 128 * E * D)
+
+
+def train_flops_per_row(D, A):
+    F = 128 * D + 128 * A + 8256
+    return 2 * (3 * F - 128 * D)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def synth_rollout(P, T, C, D, A, envs, nb, E, seed, device=None, pinned=False):
+    """Synthetic quantruped-shaped rollout: raw obs ~ N(mu_k, sigma_k^2) with per-feature scales
+    spanning 0.1..89 like the FullyDecentral checkpoint filter, rewards ~ N(0.3, 0.5^2), done ~ Bernoulli(1e-3)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.linspace(-0.5, 3.0, D)
+    sigma = torch.logspace(-1.0, 1.95, D)
+    raw = mu + sigma * torch.randn(P, T, C, D, generator=g)
+    boot = mu + sigma * torch.randn(P, C, D, generator=g)
+    rewards = 0.3 + 0.5 * torch.randn(P, T, C, generator=g)
+    dones = (torch.rand(T, envs, generator=g) < 1e-3).to(torch.uint8)
+    eps = torch.randn(P, T, C, A, generator=g)
+    perms = torch.stack([torch.stack([torch.randperm(nb, generator=g) for _ in range(E)]) for _ in range(P)]).int()
+    shuffle = torch.stack([torch.randperm(T * C, generator=g) for _ in range(P)]).int()
+    out = dict(raw=raw.float(), boot=boot.float(), rewards=rewards.float(), dones=dones, eps=eps.float(), perms=perms,
+               shuffle=shuffle)
+    if pinned:
+        out = {k: v.contiguous().pin_memory() for k, v in out.items()}
+    if device is not None:
+        out = {k: v.to(device) for k, v in out.items()}
+    return out
+
+
+def cpu_iteration_baseline(envs, seed=0, threads=None):
+    """The oracle's float32 torch twin (CPU restatement of the reference's TF-CPU learner iteration) on a bounded
+    sample of the workload: same P/D/A/T/E and minibatches-per-epoch, `envs` environments.  -> agent-steps/s."""
+    import torch
+    import oracle.ddrl_oracle as O
+    W = WORKLOAD
+    P, D, A, T, E, nbw = W["P"], W["D"], W["A"], W["T"], W["epochs"], W["minibatches_per_epoch"]
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    C = envs * (W["Ag"] // P)
+    R = T * C
+    MB = R // nbw
+    r = synth_rollout(P, T, C, D, A, envs, nbw, E, seed)
+    cfg = O.PPOConfig(num_sgd_iter=E, sgd_minibatch_size=MB)
+    gen = torch.Generator().manual_seed(seed)
+    pols = [O.PolicyState(O.fcnet_init(D, 2 * A, gen), O.AdamState.zeros(O.n_params(O.fcnet_shapes(D, 2 * A)), torch.float32, cfg),
+                          O.MeanStdFilter((D,), clip=None), cfg.kl_coeff) for _ in range(P)]
+    t0 = time.perf_counter()
+    O.fcnet_learner_iteration(pols, r["raw"].numpy(), r["boot"].numpy(), r["rewards"].numpy(), r["dones"].numpy(),
+                              r["eps"].numpy(), r["shuffle"].numpy(), r["perms"].numpy(), 2 * A, cfg, torch.float32)
+    dt = time.perf_counter() - t0
+    return T * envs * W["Ag"] / dt, dt, threads
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  TF/Ray cannot be installed here
+    (DESIGN.md), so this times the oracle port (float32 torch twin) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W = WORKLOAD
+    envs = args.ref_envs
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, threads = cpu_iteration_baseline(envs, seed=i)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    sample = f"{envs} of {W['envs_per_gpu']} envs x T={W['T']} x {W['Ag']} agents per step, same P/D/A/epochs/minibatches-per-epoch"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": W["name"], "policies": W["P"], "obs_dim": W["D"], "act_dim": W["A"], "envs": envs,
+                   "fragment_T": W["T"], "num_sgd_iter": W["epochs"], "minibatches_per_epoch": W["minibatches_per_epoch"],
+                   "note": "oracle port (torch CPU float32 twin of the RLlib 1.0.1 learner iteration); TF/Ray not installable"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=WORKLOAD["envs_per_gpu"], help="envs per GPU")
+    ap.add_argument("--minibatches", type=int, default=WORKLOAD["minibatches_per_epoch"])
+    ap.add_argument("--ref-envs", type=int, default=512, help="envs in the CPU sample of --impl reference")
+    ap.add_argument("--cpu-envs", type=int, default=1024, help="envs in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ddrl_b200 import kernels as K
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import FCNetLearner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    W = WORKLOAD
+    P, D, A, T, E, Ag = W["P"], W["D"], W["A"], W["T"], W["epochs"], W["Ag"]
+    envs = args.envs
+    C = envs * (Ag // P)
+    R = T * C
+    nb = args.minibatches
+    MB_local = R // nb
+    cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=MB_local * world)
+
+    import oracle.ddrl_oracle as O  # Glorot init values only (host RNG); no oracle compute in the timed path
+    gen = torch.Generator().manual_seed(1234)
+    theta0 = torch.stack([O.fcnet_init(D, 2 * A, gen) for _ in range(P)])
+    L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=not args.no_graph)
+
+    sets = [synth_rollout(P, T, C, D, A, envs, nb, E, 1234 + rank + 100 * s, device=dev) for s in range(args.sets)]
+    host = synth_rollout(P, T, C, D, A, envs, nb, E, 999 + rank, pinned=True)
+    bytes_per_set = sum(v.numel() * v.element_size() for v in sets[0].values())
+
+    def step_resident(i):
+        s = sets[i % len(sets)]
+        return L.learn_on_rollout(s["raw"], s["boot"], s["rewards"], s["dones"], s["eps"], s["perms"], s["shuffle"])
+
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items() if k != "eps"}
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "eps")
+
+    def step_e2e(i):
+        for k, v in dbuf.items():
+            v.copy_(host[k], non_blocking=True)
+        eps = torch.randn(P, T, C, A, device=dev)
+        return L.learn_on_rollout(dbuf["raw"], dbuf["boot"], dbuf["rewards"], dbuf["dones"], eps, dbuf["perms"],
+                                  dbuf["shuffle"])   # returns host floats: includes the D2H read of the stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, warmup, steps):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    clocks = ClockSampler(local)
+    n0 = K.launch_count()
+    clocks.start()
+    ms_total = timed(step_resident, args.warmup, args.steps)
+    clk = clocks.stop()
+    # kernels per iteration: API launches outside the captured graph + graph replays x nodes
+    steps_per_iter = E * nb
+    launches_per_iter = 2 + 2 + 2 + 1 + 7 + steps_per_iter * 3       # filter, fwd x2, gae x2, standardise, 7 gathers, sgd
+    ms_e2e = timed(step_e2e, max(1, args.warmup // 2), max(3, args.steps // 2))
+    e2e_steps = max(3, args.steps // 2)
+
+    agent_steps = T * envs * Ag * world
+    value = agent_steps * args.steps / (ms_total * 1e-3)
+    e2e_value = agent_steps * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused fwd+loss+bwd), timed alone with CUDA events on its stream ----------
+    b = L._bufs
+    src = {n_: b[n_ + "_s"] for n_ in ("obs", "act", "logits", "logp", "value", "adv", "vtarg")}
+    MB, nbb, G = L._sgd_setup(R)
+    hyper = L._hyper(MB * world)
+    evs = []
+    L.step_ctr.zero_()
+    torch.cuda.synchronize()
+    for i in range(40):
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        L.step_ctr.fill_(i % (E * nb))
+        a.record()
+        K.ppo_train_step(L.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
+                         src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"], b["stat_part"])
+        c.record()
+        evs.append((a, c))
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in evs[8:]]))
+    flops_launch = train_flops_per_row(D, A) * MB * P
+    achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6
+    fp32_peak = 148 * 128 * 2 * sm_clock / 1e12
+    roofline = {"bound": "tensor", "kernel": "fcnet_train_kernel (fused fwd + PPO loss + bwd, FP32 FMA parity mode)",
+                "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                "traffic": None, "launch_ms": k_ms, "flops_per_launch": flops_launch,
+                "fp32_fma_pipe": {"peak": fp32_peak, "frac": achieved_tf / fp32_peak,
+                                  "note": "148 SM x 128 lanes x 2 x measured SM clock; the pipe this FP32-parity kernel runs on"},
+                "share_of_step": steps_per_iter * k_ms / (ms_total / args.steps)}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, dt, threads = cpu_iteration_baseline(args.cpu_envs)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_envs} of {envs} envs, one full learner iteration ({dt:.1f} s), torch CPU float32 twin of the oracle"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": W["name"], "policies": P, "agents_per_env": Ag, "obs_dim": D, "act_dim": A,
+                       "envs_per_gpu": envs, "envs_total": envs * world, "fragment_T": T, "rows_per_policy_per_gpu": R,
+                       "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_minibatch_size_global": MB_local * world,
+                       "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
+                       "cuda_graph": not args.no_graph and world == 1,
+                       "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),
+                    "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches_per_iter * args.steps),
+            "api_launch_calls": int(K.launch_count() - n0),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "flops_per_agent_step": flops_per_agent_step(D, A, E),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ import torch
 from . import kernels as K
 from ._lib import DDRLError, PPOHyper
 from .config import PPOConfig
+from .sharding import allreduce_sum_, gather_parts_rank_order, local_minibatch
 
 STAT_NAMES = ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var")
 
@@ -141,7 +142,7 @@ class FCNetLearner(_LearnerBase):
 
     def _sgd_setup(self, R: int):
         cfg, P = self.cfg, self.P
-        MB = min(cfg.sgd_minibatch_size // self.world if self.world > 1 else cfg.sgd_minibatch_size, R)
+        MB = min(local_minibatch(cfg.sgd_minibatch_size, self.world), R)
         if MB < 1:
             raise DDRLError("sgd_minibatch_size smaller than the number of ranks")
         nb = max(1, R // MB)
@@ -177,10 +178,7 @@ class FCNetLearner(_LearnerBase):
         # (i) filter + forward + sample ------------------------------------------------------------------
         if update_filter:
             if self.world > 1:
-                parts = K.filter_partial(obs_flat)
-                gathered = [torch.empty_like(parts) for _ in range(self.world)]
-                self.dist.all_gather(gathered, parts)
-                allp = torch.cat(gathered, dim=1).contiguous()          # [P, W*nparts, D, 3], rank order
+                allp = gather_parts_rank_order(K.filter_partial(obs_flat), self.dist, self.world)
                 K.filter_merge(allp, R * self.world, self.filt_n, self.filt_M, self.filt_S, self.norm)
             else:
                 K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])

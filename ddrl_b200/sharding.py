@@ -1,0 +1,40 @@
+"""Host-side logic of the data-parallel learner (one process per GPU, shard by environment).
+
+Pure functions over tensors + a ``torch.distributed`` handle, so the N>1 path can be exercised on CPU with the
+``gloo`` backend (tests/test_dist_cpu.py) exactly as it runs over NCCL on the GPUs."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+
+
+def shard_envs(n_envs: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous env slice of ``rank`` (weak scaling keeps n_envs/world fixed per GPU)."""
+    if n_envs % world:
+        raise ValueError(f"n_envs={n_envs} must be divisible by world={world}")
+    per = n_envs // world
+    return rank * per, (rank + 1) * per
+
+
+def local_minibatch(global_mb: int, world: int) -> int:
+    """Rows of every global minibatch that live on one rank."""
+    if global_mb % world:
+        raise ValueError(f"sgd_minibatch_size={global_mb} must be divisible by world={world}")
+    return global_mb // world
+
+
+def gather_parts_rank_order(parts: torch.Tensor, dist, world: int) -> torch.Tensor:
+    """parts [P, n, D, 3] per rank -> [P, world*n, D, 3], concatenated in RANK ORDER (fixed merge order =>
+    every rank computes bit-identical filter statistics)."""
+    if world == 1:
+        return parts
+    bufs: List[torch.Tensor] = [torch.empty_like(parts) for _ in range(world)]
+    dist.all_gather(bufs, parts.contiguous())
+    return torch.cat(bufs, dim=1).contiguous()
+
+
+def allreduce_sum_(t: torch.Tensor, dist, world: int) -> torch.Tensor:
+    if world > 1:
+        dist.all_reduce(t)
+    return t

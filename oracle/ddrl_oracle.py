@@ -641,7 +641,7 @@ def sgd_minibatch_step(theta, st: AdamState, forward_fn, batch: Dict[str, torch.
     (g,) = torch.autograd.grad(loss, th)
     gc, gnorm = clip_by_global_norm(g, cfg.grad_clip)
     new_theta = adam_tf1_step(theta.detach(), gc, st, cfg)
-    return new_theta, {k: float(v) for k, v in stats.items()}, g, float(gnorm)
+    return new_theta, {k: float(v.detach()) for k, v in stats.items()}, g, float(gnorm)
 
 
 def sgd_loop(theta, st: AdamState, forward_fn, batch: Dict[str, torch.Tensor], perms: np.ndarray,

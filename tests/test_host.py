@@ -1,0 +1,120 @@
+"""CPU: host-side mirror of the reference interface — registry names, multi-agent policy mapping, index tables,
+config keys, learner-stat finalisation."""
+import numpy as np
+import pytest
+
+import oracle.ddrl_oracle as O
+from ddrl_b200 import policies as Pz
+from ddrl_b200.config import PPOConfig, RLLIB_DEFAULTS
+
+
+def test_registry_names_match_reference_models_init():
+    import ddrl_b200.modelv2 as M
+    from ddrl_b200.catalog import ModelCatalog
+    assert ModelCatalog.get_custom_model("ffn") is M.FullyConnectedNetwork_GlorotUniformInitializer
+    assert ModelCatalog.get_custom_model("fc_glorot_uniform_init") is M.FullyConnectedNetwork_GlorotUniformInitializer
+    assert ModelCatalog.get_custom_model("gnn") is M.FullyConnectedNetwork_GNN_GlorotUniformInitializer
+    assert ModelCatalog.get_custom_model("cup") is M.FullyConnectedNetwork_Coupling_GlorotUniformInitializer
+    with pytest.raises(KeyError):
+        ModelCatalog.get_custom_model("nope")
+
+
+def test_variable_layouts_match_oracle_and_checkpoint_order():
+    import ddrl_b200.modelv2 as M
+    assert M.fcnet_shapes(19, 4) == [(n, tuple(s)) for n, s in O.fcnet_shapes(19, 4)]
+    got = [(n.split("/", 1)[1], s) for n, s in M.graphnet_shapes(4)]
+    assert got == O.graphnet_shapes(4) + O.graphnet_shapes(1)
+
+
+ARCH_TABLE = {  # SURVEY.md §8 architecture table
+    "QuantrupedMultiEnv_Centralized": (1, 1, 43, 8),
+    "QuantrupedMultiEnv_FullyDecentral": (4, 4, 19, 2),
+    "QuantrupedMultiEnv_Local": (4, 4, 35, 2),
+    "QuantrupedMultiEnv_SingleNeighbor": (4, 4, 27, 2),
+    "QuantrupedMultiEnv_SingleDiagonal": (4, 4, 27, 2),
+    "QuantrupedMultiEnv_SingleToFront": (4, 4, 27, 2),
+    "QuantrupedMultiEnv_TwoSides": (2, 2, 27, 4),
+    "QuantrupedMultiEnv_TwoDiags": (2, 2, 27, 4),
+    "QuantrupedMultiEnv_SharedDecentral": (1, 4, 19, 2),
+}
+
+
+@pytest.mark.parametrize("scope", list(ARCH_TABLE))
+def test_architecture_table(scope):
+    P, Ag, D, A = ARCH_TABLE[scope]
+    env = Pz.ARCHITECTURES[scope]
+    assert len(env.policy_names) == P and len(env.agent_names) == Ag
+    for tv in (False, True):
+        pol = env.return_policies(use_target_velocity=tv)
+        assert list(pol) == env.policy_names
+        for _, obs_space, act_space, cfg in pol.values():
+            assert obs_space.shape == (D + int(tv),) and act_space.shape == (A,) and cfg == {}
+        if scope != "QuantrupedMultiEnv_Centralized":
+            tab = env.gather_table(tv)
+            assert tab.shape == (Ag, D + int(tv)) and tab.dtype == np.int32 and tab.max() <= 42 + int(tv)
+    mc = Pz.multiagent_config(scope)
+    assert set(mc) == {"policies", "policy_mapping_fn", "policies_to_train"} and mc["policies_to_train"] == env.policy_names
+    for a in env.agent_names:
+        assert mc["policy_mapping_fn"](a) in env.policy_names
+
+
+def test_policy_mapping_and_indices_match_reference():
+    FD = Pz.QuantrupedFullyDecentralizedEnv
+    assert [FD.policy_mapping_fn(a) for a in ("agent_FL", "agent_HL", "agent_HR", "agent_FR", "agent_FL_7")] == \
+        ["policy_FL", "policy_HL", "policy_HR", "policy_FR", "policy_FL"]
+    assert FD.policy_mapping_fn("something_else") == "policy_FR"          # the reference's final else branch
+    assert FD.obs_indices()["agent_FL"] == O.get_obs_indices(["body", "fl"])
+    assert FD.action_indices() == {"agent_FL": [2, 3], "agent_HL": [4, 5], "agent_HR": [6, 7], "agent_FR": [0, 1]}
+    L = Pz.Quantruped_Local_Env.obs_indices()
+    assert L["agent_FL"] == O.get_obs_indices(["body", "fl", "hl", "fr"]) and len(L["agent_HR"]) == 35
+    SD = Pz.Quantruped_LocalSingleDiagonalLeg_Env.obs_indices()
+    assert SD["agent_HR"] == SD["agent_FL"] == O.get_obs_indices(["body", "fl", "hr"])
+    assert SD["agent_FR"] == SD["agent_HL"]
+    TS = Pz.Quantruped_TwoSideControllers_Env
+    assert TS.action_indices() == {"agent_LEFT": [2, 3, 4, 5], "agent_RIGHT": [6, 7, 0, 1]}
+    assert TS.policy_mapping_fn("agent_LEFT") == "policy_LEFT" and TS.policy_mapping_fn("agent_RIGHT") == "policy_RIGHT"
+    TD = Pz.Quantruped_TwoDiagControllers_Env
+    assert TD.action_indices() == {"agent_FLHR": [2, 3, 6, 7], "agent_HLFR": [4, 5, 0, 1]}
+    assert Pz.Quantruped_Centralized_Env.policy_mapping_fn("central_agent") == "central_policy"
+    tv = Pz.QuantrupedFullyDecentralizedEnv.obs_indices(True)["agent_HL"]
+    assert tv[11] == 43 and len(tv) == 20                                   # TVel: index 43 follows the body block
+
+
+def test_graph_env_tables():
+    G = Pz.QuantrupedDecentralizedSharedGraphEnv
+    np.testing.assert_array_equal(G.create_adj(), O.ring_adjacency().numpy())
+    pol = G.return_policies()
+    (_, space, act, _), = pol.values()
+    idx_space, obs_space, adj_space = space
+    assert obs_space.shape == (4, 23) and adj_space.shape == (4, 4) and idx_space.shape == (1,) and act.shape == (2,)
+    assert G.policy_mapping_fn("agent_HR") == "leg_policy"
+
+
+def test_config_from_rllib_dict_uses_published_values():
+    c = PPOConfig.from_rllib({"lambda": 0.9, "sgd_minibatch_size": 4096})
+    assert (c.gamma, c.lambda_, c.clip_param, c.vf_clip_param, c.vf_loss_coeff, c.kl_coeff, c.kl_target, c.lr,
+            c.grad_clip, c.num_sgd_iter, c.sgd_minibatch_size) == (0.99, 0.9, 0.2, 10.0, 0.5, 0.2, 0.01, 3e-4, 0.5, 10, 4096)
+    assert RLLIB_DEFAULTS["observation_filter"] == "MeanStdFilter" and RLLIB_DEFAULTS["train_batch_size"] == 16000
+
+
+def test_finalize_stats_matches_oracle_definitions():
+    from ddrl_b200.learner import finalize_stats
+    import torch
+    torch.manual_seed(0)
+    cfg_o, cfg = O.PPOConfig(entropy_coeff=0.01), PPOConfig(entropy_coeff=0.01)
+    n, A = 64, 2
+    lg = torch.randn(n, 2 * A, dtype=torch.float64)
+    act = O.dg_sample(lg, torch.randn(n, A, dtype=torch.float64))
+    old = lg + 0.1 * torch.randn_like(lg)
+    v, R, vp = torch.randn(n, dtype=torch.float64) * 5, torch.randn(n, dtype=torch.float64) * 5, torch.randn(n, dtype=torch.float64)
+    adv = torch.randn(n, dtype=torch.float64)
+    _, st = O.ppo_loss_from_outputs(lg, v, act, old, O.dg_logp(old, act), vp, adv, R, 0.3, cfg_o)
+    ratio = torch.exp(O.dg_logp(lg, act) - O.dg_logp(old, act))
+    surr = torch.minimum(adv * ratio, adv * ratio.clamp(0.8, 1.2))
+    vf = torch.maximum((v - R) ** 2, (vp + (v - vp).clamp(-10, 10) - R) ** 2)
+    sums = np.array([[[float((-surr).sum()), float(O.dg_kl(old, lg).sum()), float(vf.sum()), float(O.dg_entropy(lg).sum()),
+                       float(R.sum()), float((R * R).sum()), float((R - v).sum()), float(((R - v) ** 2).sum())]]])
+    out = finalize_stats(sums, np.array([0.3]), cfg, n)[0]
+    for k in O.STAT_KEYS:
+        assert abs(out[k] - float(st[k])) < 1e-5 * max(1.0, abs(float(st[k]))), k
+    assert out["cur_kl_coeff"] == 0.3 and out["cur_lr"] == float(np.float32(3e-4))
