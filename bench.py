@@ -255,7 +255,7 @@ def main():
     clk = clocks.stop()
     # kernels per iteration: API launches outside the captured graph + graph replays x nodes
     steps_per_iter = E * nb
-    launches_per_iter = 2 + 2 + 2 + 1 + 7 + steps_per_iter * 3       # filter, fwd x2, gae x2, standardise, 7 gathers, sgd
+    launches_per_iter = 1 + 2 + 2 + 2 + 1 + 7 + steps_per_iter * 3   # pack, filter x2, fwd x2, gae x2, standardise, 7 gathers, sgd
     ms_e2e = timed(step_e2e, max(1, args.warmup // 2), max(3, args.steps // 2))
     e2e_steps = max(3, args.steps // 2)
 
@@ -276,7 +276,8 @@ def main():
         L.step_ctr.fill_(i % (E * nb))
         a.record()
         K.ppo_train_step(L.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
-                         src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"], b["stat_part"])
+                         src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"], b["stat_part"],
+                         img=L.img)
         c.record()
         evs.append((a, c))
     torch.cuda.synchronize()

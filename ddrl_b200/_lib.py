@@ -28,6 +28,8 @@ PROTOTYPES = {
     "ddrl_abi_version": (C.c_int, []),
     "ddrl_launch_count": (C.c_int64, []),
     "ddrl_fcnet_num_params": (C.c_int, [C.c_int, C.c_int]),
+    "ddrl_fcnet_image_floats": (C.c_int, [C.c_int, C.c_int]),
+    "ddrl_fcnet_pack": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
     "ddrl_filter_ws_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "ddrl_filter_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_i64p, c_f64p, c_f64p,
                                      c_f64p, C.c_void_p, c_stream]),
@@ -35,21 +37,22 @@ PROTOTYPES = {
     "ddrl_filter_partial": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, c_stream]),
     "ddrl_filter_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, c_i64p, c_f64p, c_f64p, c_f64p,
                                     c_stream]),
-    "ddrl_fcnet_forward": (C.c_int, [c_f32p, c_f32p, c_f64p, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_int,
+    "ddrl_fcnet_forward": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f64p, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_int,
                                      c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "ddrl_gae_ws_bytes": (C.c_int64, [C.c_int, C.c_int64]),
-    "ddrl_gae": (C.c_int, [c_f32p, c_f32p, c_u8p, c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
-                           C.c_float, c_f32p, c_f32p, c_f64p, C.c_void_p, c_stream]),
+    "ddrl_gae": (C.c_int, [c_f32p, c_f32p, c_u8p, c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double,
+                           C.c_double, c_f32p, c_f32p, c_f64p, C.c_void_p, c_stream]),
     "ddrl_adv_standardize": (C.c_int, [c_f32p, c_f64p, C.c_int, C.c_int64, c_stream]),
     "ddrl_gather_rows": (C.c_int, [c_f32p, c_i32p, C.c_int, C.c_int64, C.c_int, c_f32p, c_stream]),
-    "ddrl_ppo_train_step": (C.c_int, [c_f32p] * 10 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
+    "ddrl_ppo_train_step": (C.c_int, [c_f32p] * 11 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
                                                      C.c_int64, c_i32p, c_f32p, C.POINTER(PPOHyper), C.c_int,
                                                      c_f32p, c_f64p, c_stream]),
     "ddrl_ppo_loss_grad": (C.c_int, [c_f32p] * 8 + [C.c_int, C.c_int64, C.c_int, c_f32p, C.POINTER(PPOHyper), C.c_int,
                                                     c_f32p, c_f32p, c_f64p, c_stream]),
     "ddrl_grad_reduce": (C.c_int, [c_f32p, c_f64p, C.c_int, C.c_int, C.c_int, c_f32p, c_f64p, c_i32p, c_stream]),
     "ddrl_clip_adam": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_float,
-                                 C.c_float, C.c_float, C.c_float, c_f32p, c_i32p, c_i32p, c_stream]),
+                                 C.c_float, C.c_float, C.c_float, c_f32p, c_i32p, c_i32p, c_f32p, C.c_int, C.c_int,
+                                 c_stream]),
     "ddrl_graphnet_num_params": (C.c_int, [C.c_int]),
     "ddrl_graphnet_forward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p,
                                         c_stream]),

@@ -5,96 +5,55 @@
 // Tiling (both kernels): a CTA of 256 threads owns the weights of ONE policy in shared memory and
 // walks over 64-row tiles.  The policy and value branches have identical shapes, so they are run as
 // one 128-wide network: layer 1 is x[64,D] * [W1|Wv1][D,128], layer 2 is block diagonal.  Every
-// thread owns a 4-row x 8-column register tile (ty = tid/16 -> rows, tx = tid%16 -> columns;
-// tx < 8 is the policy branch), operands come from shared memory as 128-bit loads
-// (32 FMA per 3 LDS.128).  Activations stay in shared memory (row-major, stride 132 floats) and are
-// overwritten in place by their gradients on the way back; weight gradients accumulate in registers
-// across all tiles of the CTA and leave as one per-CTA partial (reduced in fixed order by
-// ddrl_grad_reduce => deterministic).
+// thread owns a 4-row x 8-column register tile: ty = tid/16 -> rows 4ty..4ty+3; tx = tid%16 -> branch
+// tx/8 (0 policy, 1 value) and, inside the 64 columns of the branch, the two float4 groups
+// [4(tx%8), +4) and [32 + 4(tx%8), +4) — so the 8 lanes of a quarter warp read 128 contiguous bytes of
+// a weight row (conflict-free 128-bit shared loads; 32 FMA per 3 LDS.128).  Activations stay in shared
+// memory (row-major, stride 132 floats) and are overwritten in place by their gradients on the way
+// back; weight gradients accumulate in registers across all tiles of the CTA and leave as one per-CTA
+// partial (reduced in fixed order by ddrl_grad_reduce => deterministic).
+//
+// Weights reach shared memory either from the flat checkpoint-order vector (any caller) or from a
+// pre-packed "image" (exactly the shared-memory layout, maintained by ddrl_clip_adam / ddrl_fcnet_pack)
+// with one straight 128-bit copy — the SGD loop uses the image so the per-step weight (re)load costs a
+// coalesced 88 KB read from L2 instead of 11 K scattered loads + transposes.
 #include <math.h>
 
 #include <algorithm>
 
 #include "common.cuh"
+#include "fcnet_layout.cuh"
 #include "ppo_loss.cuh"
 
 namespace ddrl {
 
-constexpr int H = DDRL_HIDDEN;   // 64
-constexpr int HC = 2 * H;        // 128: policy | value concatenated
-constexpr int TM = 64;           // rows per tile
-constexpr int NT = 256;          // threads per CTA
-constexpr int LDH = HC + 4;      // activation row stride (pad keeps 128-bit row reads conflict free)
-constexpr int LDT = HC + 4;      // stride of the transposed layer-2 weights
-constexpr int LDD = 20;          // stride of the per-row head outputs / head gradients (2A+1 <= 17)
-constexpr int MAXHEAD = (H * (2 * DDRL_MAX_ACT + 1) + NT - 1) / NT;  // 5 head-gradient items / thread
-
-struct FcSmem {
-    int W1c, b1c, W2c, b2c, W2Tc, Wo, bo, Wvo, bvo, x, h1, h2, out, dl, red, norm, total;
-};
-
-__host__ __device__ inline FcSmem fc_smem(int D, int A, bool train, bool has_norm) {
-    const int Dp = (D + 3) & ~3;
-    FcSmem s;
-    int p = 0;
-    s.W1c = p;  p += Dp * HC;
-    s.b1c = p;  p += HC;
-    s.W2c = p;  p += H * HC;
-    s.b2c = p;  p += HC;
-    s.W2Tc = p; p += train ? H * LDT : 0;
-    s.Wo = p;   p += H * 2 * A;
-    s.bo = p;   p += ((2 * A + 3) & ~3);
-    s.Wvo = p;  p += H;
-    s.bvo = p;  p += 4;
-    s.x = p;    p += TM * Dp;
-    s.h1 = p;   p += TM * LDH;
-    s.h2 = p;   p += TM * LDH;
-    s.out = p;  p += TM * LDD;
-    s.dl = p;   p += TM * LDD;
-    p = (p + 1) & ~1;
-    s.red = p;  p += 2 * DDRL_NSTAT;                       // doubles
-    s.norm = p; p += has_norm ? 2 * 2 * ((D + 1) & ~1) : 0;  // doubles: mean[D], inv[D]
-    s.total = p;
-    return s;
+// ---- weights: global flat (checkpoint order) -> shared (concatenated / transposed) --------------
+__device__ void load_weights_flat(float* sm, const FcSmem& L, const float* __restrict__ th, int D, int A) {
+    const FcOffsets o = fc_offsets(D, A);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < L.x; i += NT) sm[i] = 0.f;   // pads (W1c rows D..Dp, WhT) must be zero
+    __syncthreads();
+    for (int j = tid; j < o.NP; j += NT) {
+        const float w = th[j];
+        int p0, p1;
+        fc_img_pos(L, o, D, A, j, p0, p1);
+        sm[p0] = w;
+        if (p1 >= 0) sm[p1] = w;
+    }
 }
 
-// ---- weights: global flat (checkpoint order) -> shared (concatenated / transposed) --------------
-__device__ void load_weights(float* sm, const FcSmem& L, const float* __restrict__ th, int D, int A, bool train) {
-    const FcOffsets o = fc_offsets(D, A);
-    const int Dp = (D + 3) & ~3;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < Dp * H; i += NT) {
-        const int k = i >> 6, c = i & 63;
-        const bool in = k < D;
-        sm[L.W1c + k * HC + c] = in ? th[o.W1 + i] : 0.f;
-        sm[L.W1c + k * HC + H + c] = in ? th[o.Wv1 + i] : 0.f;
-    }
-    for (int i = tid; i < H * H; i += NT) {
-        const int k = i >> 6, c = i & 63;
-        const float w = th[o.W2 + i], wv = th[o.Wv2 + i];
-        sm[L.W2c + k * HC + c] = w;
-        sm[L.W2c + k * HC + H + c] = wv;
-        if (train) {  // W2T[c][k]: row = output index, column = input index
-            sm[L.W2Tc + c * LDT + k] = w;
-            sm[L.W2Tc + c * LDT + H + k] = wv;
-        }
-    }
-    for (int i = tid; i < H; i += NT) {
-        sm[L.b1c + i] = th[o.b1 + i];
-        sm[L.b1c + H + i] = th[o.bv1 + i];
-        sm[L.b2c + i] = th[o.b2 + i];
-        sm[L.b2c + H + i] = th[o.bv2 + i];
-        sm[L.Wvo + i] = th[o.Wvo + i];
-    }
-    for (int i = tid; i < H * 2 * A; i += NT) sm[L.Wo + i] = th[o.Wo + i];
-    if (tid < 2 * A) sm[L.bo + tid] = th[o.bo + tid];
-    if (tid == 0) sm[L.bvo] = th[o.bvo];
+__device__ __forceinline__ void load_weights_img(float* sm, const FcSmem& L, const float* __restrict__ img) {
+    const float4* src = reinterpret_cast<const float4*>(img);
+    float4* dst = reinterpret_cast<float4*>(sm);
+    const int n4 = L.x >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += NT) dst[i] = src[i];
 }
 
 // ---- register-tile micro kernels -------------------------------------------------------------
-// acc[i][j] += sum_k A[i*lda + k] * B[k*ldb + j],  k in [0,K), K % 4 == 0.
-__device__ __forceinline__ void mm_nn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                      int K, float (&acc)[4][8]) {
+// acc[i][0..3] += sum_k A[i*lda + k] * B0[k*ldb + 0..3],  acc[i][4..7] likewise with B1;  K % 4 == 0.
+__device__ __forceinline__ void mm_nn(const float* __restrict__ A, int lda, const float* __restrict__ B0,
+                                      const float* __restrict__ B1, int ldb, int K, float (&acc)[4][8]) {
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
         float4 a[4];
@@ -102,8 +61,8 @@ __device__ __forceinline__ void mm_nn(const float* __restrict__ A, int lda, cons
         for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(A + i * lda + k);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const float4 b0 = *reinterpret_cast<const float4*>(B + (k + kk) * ldb);
-            const float4 b1 = *reinterpret_cast<const float4*>(B + (k + kk) * ldb + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(B0 + (k + kk) * ldb);
+            const float4 b1 = *reinterpret_cast<const float4*>(B1 + (k + kk) * ldb);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
@@ -120,14 +79,15 @@ __device__ __forceinline__ void mm_nn(const float* __restrict__ A, int lda, cons
     }
 }
 
-// acc[i][j] += sum_r A[r*lda + i] * B[r*ldb + j],  r = r0, r0+rs, ... < r1   (weight gradients).
-__device__ __forceinline__ void mm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                      int r0, int r1, int rs, float (&acc)[4][8]) {
+// acc[i][j] += sum_r A[r*lda + i] * B{0,1}[r*ldb + j],  r = r0, r0+rs, ... < r1   (weight gradients).
+__device__ __forceinline__ void mm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B0,
+                                      const float* __restrict__ B1, int ldb, int r0, int r1, int rs,
+                                      float (&acc)[4][8]) {
 #pragma unroll 4
     for (int r = r0; r < r1; r += rs) {
         const float4 a = *reinterpret_cast<const float4*>(A + r * lda);
-        const float4 b0 = *reinterpret_cast<const float4*>(B + r * ldb);
-        const float4 b1 = *reinterpret_cast<const float4*>(B + r * ldb + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(B0 + r * ldb);
+        const float4 b1 = *reinterpret_cast<const float4*>(B1 + r * ldb);
         const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -150,45 +110,41 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][8]) {
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 }
 
+// bias + tanh epilogue of a 4x8 tile, stored row-major into dst (stride LDH) at columns c0.. and c1..
+__device__ __forceinline__ void tanh_store(float* sm_dst, const float* bias, int row0, int c0, int c1,
+                                           const float (&acc)[4][8]) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + c1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 o0, o1;
+        o0.x = tanhf(acc[i][0] + b0.x); o0.y = tanhf(acc[i][1] + b0.y);
+        o0.z = tanhf(acc[i][2] + b0.z); o0.w = tanhf(acc[i][3] + b0.w);
+        o1.x = tanhf(acc[i][4] + b1.x); o1.y = tanhf(acc[i][5] + b1.y);
+        o1.z = tanhf(acc[i][6] + b1.z); o1.w = tanhf(acc[i][7] + b1.w);
+        float* dst = sm_dst + (row0 + i) * LDH;
+        *reinterpret_cast<float4*>(dst + c0) = o0;
+        *reinterpret_cast<float4*>(dst + c1) = o1;
+    }
+}
+
 // ---- forward of one tile: x (smem) -> h1, h2 (smem) -> out[r][0..2A] = logits, out[r][2A] = value --
 __device__ __forceinline__ void forward_tile(float* sm, const FcSmem& L, int D, int A, int nrows) {
     const int Dp = (D + 3) & ~3;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int br = (tx >> 3) * H, c0 = br + (tx & 7) * 4, c1 = c0 + 32;
     const bool live = ty * 4 < nrows;  // rows of this thread hold data (8-row granularity per warp)
     float acc[4][8];
     if (live) {
         zero_acc(acc);
-        mm_nn(sm + L.x + ty * 4 * Dp, Dp, sm + L.W1c + tx * 8, HC, Dp, acc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 o0, o1;
-            const float* b = sm + L.b1c + tx * 8;
-            o0.x = tanhf(acc[i][0] + b[0]); o0.y = tanhf(acc[i][1] + b[1]);
-            o0.z = tanhf(acc[i][2] + b[2]); o0.w = tanhf(acc[i][3] + b[3]);
-            o1.x = tanhf(acc[i][4] + b[4]); o1.y = tanhf(acc[i][5] + b[5]);
-            o1.z = tanhf(acc[i][6] + b[6]); o1.w = tanhf(acc[i][7] + b[7]);
-            float* dst = sm + L.h1 + (ty * 4 + i) * LDH + tx * 8;
-            *reinterpret_cast<float4*>(dst) = o0;
-            *reinterpret_cast<float4*>(dst + 4) = o1;
-        }
+        mm_nn(sm + L.x + ty * 4 * Dp, Dp, sm + L.W1c + c0, sm + L.W1c + c1, HC, Dp, acc);
+        tanh_store(sm + L.h1, sm + L.b1c, ty * 4, c0, c1, acc);
     }
     __syncthreads();
     if (live) {
         zero_acc(acc);
-        const int br = (tx >> 3) * H;  // branch column offset in h1
-        mm_nn(sm + L.h1 + ty * 4 * LDH + br, LDH, sm + L.W2c + tx * 8, HC, H, acc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 o0, o1;
-            const float* b = sm + L.b2c + tx * 8;
-            o0.x = tanhf(acc[i][0] + b[0]); o0.y = tanhf(acc[i][1] + b[1]);
-            o0.z = tanhf(acc[i][2] + b[2]); o0.w = tanhf(acc[i][3] + b[3]);
-            o1.x = tanhf(acc[i][4] + b[4]); o1.y = tanhf(acc[i][5] + b[5]);
-            o1.z = tanhf(acc[i][6] + b[6]); o1.w = tanhf(acc[i][7] + b[7]);
-            float* dst = sm + L.h2 + (ty * 4 + i) * LDH + tx * 8;
-            *reinterpret_cast<float4*>(dst) = o0;
-            *reinterpret_cast<float4*>(dst + 4) = o1;
-        }
+        mm_nn(sm + L.h1 + ty * 4 * LDH + br, LDH, sm + L.W2c + c0, sm + L.W2c + c1, HC, H, acc);
+        tanh_store(sm + L.h2, sm + L.b2c, ty * 4, c0, c1, acc);
     }
     __syncthreads();
     // heads: item = (row r, output o); o == 2A is the value head reading the value branch of h2.
@@ -237,18 +193,19 @@ __device__ __forceinline__ void load_x_tile(float* sm, const FcSmem& L, const fl
 // K1: grouped forward (+filter-normalise prologue, +DiagGaussian sample/logp epilogue)
 // =================================================================================================
 __global__ void __launch_bounds__(NT, 1)
-fcnet_forward_kernel(const float* __restrict__ theta, const float* __restrict__ obs, const double* __restrict__ norm,
-                     float clip, int64_t R, int D, int A, float* __restrict__ obs_out, float* __restrict__ logits,
-                     float* __restrict__ value, const float* __restrict__ eps, float* __restrict__ action,
-                     float* __restrict__ logp) {
+fcnet_forward_kernel(const float* __restrict__ theta, const float* __restrict__ img, const float* __restrict__ obs,
+                     const double* __restrict__ norm, float clip, int64_t R, int D, int A, float* __restrict__ obs_out,
+                     float* __restrict__ logits, float* __restrict__ value, const float* __restrict__ eps,
+                     float* __restrict__ action, float* __restrict__ logp) {
     extern __shared__ __align__(16) float sm[];
     const int p = blockIdx.y;
-    const FcSmem L = fc_smem(D, A, false, norm != nullptr);
+    const FcSmem L = fc_smem(D, A, norm != nullptr);
     const FcOffsets o = fc_offsets(D, A);
     const int tid = threadIdx.x;
     const int A2 = 2 * A;
+    if (img) load_weights_img(sm, L, img + (int64_t)p * L.x);
+    else load_weights_flat(sm, L, theta + (int64_t)p * o.NP, D, A);
     for (int i = tid; i < TM * ((D + 3) & ~3); i += NT) sm[L.x + i] = 0.f;
-    load_weights(sm, L, theta + (int64_t)p * o.NP, D, A, false);
     double* snorm = nullptr;
     if (norm) {
         snorm = reinterpret_cast<double*>(sm + L.norm);
@@ -304,7 +261,7 @@ fcnet_forward_kernel(const float* __restrict__ theta, const float* __restrict__ 
 // K2/K6: fused forward + PPO loss + backward for one minibatch (all policies), per-CTA partial grads
 // =================================================================================================
 struct TrainArgs {
-    const float *theta, *obs, *actions, *old_logits, *old_logp, *vf_preds, *adv, *vtarg, *ext_dlogits, *ext_dvalue;
+    const float *theta, *img, *obs, *actions, *old_logits, *old_logp, *vf_preds, *adv, *vtarg, *ext_dlogits, *ext_dvalue;
     int64_t R;
     int D, A, MB;
     const int32_t* mb_perm;
@@ -320,9 +277,10 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
     const int D = a.D, A = a.A, A2 = 2 * A, Dp = (D + 3) & ~3;
-    const FcSmem L = fc_smem(D, A, true, false);
+    const FcSmem L = fc_smem(D, A, false);
     const FcOffsets o = fc_offsets(D, A);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, lane = tid & 31, warp = tid >> 5;
+    const int br = (tx >> 3) * H, c0 = br + (tx & 7) * 4, c1 = c0 + 32;
     const bool ext = a.ext_dlogits != nullptr;
 
     // minibatch and this CTA's row range --------------------------------------------------------
@@ -333,8 +291,12 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
     const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
 
+    if (cr1 > cr0) {
+        if (a.img) load_weights_img(sm, L, a.img + (int64_t)p * L.x);
+        else load_weights_flat(sm, L, a.theta + (int64_t)p * o.NP, D, A);
+    }
     for (int i = tid; i < TM * Dp; i += NT) sm[L.x + i] = 0.f;
-    if (cr1 > cr0) load_weights(sm, L, a.theta + (int64_t)p * o.NP, D, A, true);
+    for (int i = tid; i < 2 * TM * LDD; i += NT) sm[L.out + i] = 0.f;   // out and dl (dl pad columns stay zero)
     __syncthreads();
 
     // gradient accumulators (registers, live across tiles) -----------------------------------
@@ -359,26 +321,46 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
 
     for (int64_t row0 = cr0; row0 < cr1; row0 += TM) {
         const int nrows = (int)min((int64_t)TM, cr1 - row0);
+        // prefetch the loss inputs of this tile's rows (threads 0..63, one row each): issued before the forward
+        // pass so their DRAM/L2 latency is hidden behind it
+        float pf_act[DDRL_MAX_ACT], pf_ol[2 * DDRL_MAX_ACT], pf_s[4];
+        const bool loss_thread = tid < TM && tid < nrows;
+        if (loss_thread) {
+            const int64_t gr = (int64_t)p * a.R + row0 + tid;
+            if (ext) {
+#pragma unroll
+                for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
+                    if (i < A2) pf_ol[i] = a.ext_dlogits[gr * A2 + i];
+                pf_s[0] = a.ext_dvalue[gr];
+            } else {
+#pragma unroll
+                for (int i = 0; i < DDRL_MAX_ACT; ++i)
+                    if (i < A) pf_act[i] = a.actions[gr * A + i];
+#pragma unroll
+                for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
+                    if (i < A2) pf_ol[i] = a.old_logits[gr * A2 + i];
+                pf_s[0] = a.old_logp[gr]; pf_s[1] = a.vf_preds[gr]; pf_s[2] = a.adv[gr]; pf_s[3] = a.vtarg[gr];
+            }
+        }
         load_x_tile(sm, L, obs_p, nullptr, nullptr, 0.f, row0, nrows, D);
         __syncthreads();
         forward_tile(sm, L, D, A, nrows);
 
         // ---- per-row loss gradient -> dl[r][0..2A) = dL/dlogits, dl[r][2A] = dL/dvalue ------------
         if (tid < TM) {
-            const int r = tid;
             double s[DDRL_NSTAT];
 #pragma unroll
             for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
-            if (r < nrows) {
-                const int64_t gr = (int64_t)p * a.R + row0 + r;
-                float* dl = sm + L.dl + r * LDD;
-                const float* out = sm + L.out + r * LDD;
+            if (loss_thread) {
+                float* dl = sm + L.dl + tid * LDD;
+                const float* out = sm + L.out + tid * LDD;
                 if (ext) {
-                    for (int i = 0; i < A2; ++i) dl[i] = a.ext_dlogits[gr * A2 + i];
-                    dl[A2] = a.ext_dvalue[gr];
+#pragma unroll
+                    for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
+                        if (i < A2) dl[i] = pf_ol[i];
+                    dl[A2] = pf_s[0];
                 } else {
-                    ppo_row_loss(out, A, a.actions + gr * A, a.old_logits + gr * A2, a.old_logp[gr], a.vf_preds[gr],
-                                 a.adv[gr], a.vtarg[gr], klc, a.hp, dl, s);
+                    ppo_row_loss(out, A, pf_act, pf_ol, pf_s[0], pf_s[1], pf_s[2], pf_s[3], klc, a.hp, dl, s);
                 }
             }
             if (!ext) {
@@ -409,6 +391,7 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
                 const float* hcol = sm + L.h2 + (oo == A2 ? H : 0) + k;
                 const float* dcol = sm + L.dl + oo;
                 float s = gHead[i];
+#pragma unroll 8
                 for (int r = 0; r < nrows; ++r) s = fmaf(hcol[r * LDH], dcol[r * LDD], s);
                 gHead[i] = s;
             }
@@ -420,81 +403,86 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
         }
         __syncthreads();
 
-        // ---- B2: dz2 = (dl . Wo^T) * (1 - h2^2), in place over h2 -------------------------------------
+        // ---- B2: dz2 = (dl . Wh^T) * (1 - h2^2), in place over h2 (dl columns beyond 2A are zero) ----------------
         if (ty * 4 < nrows) {
+            float dh[4][8];
+            zero_acc(dh);
+            mm_nn(sm + L.dl + ty * 4 * LDD, LDD, sm + L.WhT + c0, sm + L.WhT + c1, HC, (A2 + 4) & ~3, dh);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = ty * 4 + i;
-                const float* dl = sm + L.dl + r * LDD;
-                float* hrow = sm + L.h2 + r * LDH + tx * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = tx * 8 + j, k = c & 63;
-                    float s = 0.f;
-                    if (tx < 8) {
-                        const float* w = sm + L.Wo + k * A2;
-                        for (int q = 0; q < A2; ++q) s = fmaf(dl[q], w[q], s);
-                    } else {
-                        s = dl[A2] * sm[L.Wvo + k];
-                    }
-                    const float h = hrow[j];
-                    hrow[j] = s * (1.f - h * h);
-                }
+                float* hrow = sm + L.h2 + (ty * 4 + i) * LDH;
+                const float4 h0 = *reinterpret_cast<const float4*>(hrow + c0);
+                const float4 h1v = *reinterpret_cast<const float4*>(hrow + c1);
+                float4 o0, o1;
+                o0.x = dh[i][0] * (1.f - h0.x * h0.x); o0.y = dh[i][1] * (1.f - h0.y * h0.y);
+                o0.z = dh[i][2] * (1.f - h0.z * h0.z); o0.w = dh[i][3] * (1.f - h0.w * h0.w);
+                o1.x = dh[i][4] * (1.f - h1v.x * h1v.x); o1.y = dh[i][5] * (1.f - h1v.y * h1v.y);
+                o1.z = dh[i][6] * (1.f - h1v.z * h1v.z); o1.w = dh[i][7] * (1.f - h1v.w * h1v.w);
+                *reinterpret_cast<float4*>(hrow + c0) = o0;
+                *reinterpret_cast<float4*>(hrow + c1) = o1;
             }
         }
         __syncthreads();
 
         // ---- B3: gW2[k][c] += sum_r h1[r][br+k] dz2[r][c];  gb2[c] += sum_r dz2[r][c] -------------------
-        mm_tn(sm + L.h1 + (tx >> 3) * H + ty * 4, LDH, sm + L.h2 + tx * 8, LDH, 0, nrows, 1, gW2);
+        mm_tn(sm + L.h1 + br + ty * 4, LDH, sm + L.h2 + c0, sm + L.h2 + c1, LDH, 0, nrows, 1, gW2);
         if (tid < HC) {
-            float s = gb2;
-            for (int r = 0; r < nrows; ++r) s += sm[L.h2 + r * LDH + tid];
-            gb2 = s;
+            float s0 = 0.f, s1 = 0.f;
+            int r = 0;
+            for (; r + 1 < nrows; r += 2) { s0 += sm[L.h2 + r * LDH + tid]; s1 += sm[L.h2 + (r + 1) * LDH + tid]; }
+            if (r < nrows) s0 += sm[L.h2 + r * LDH + tid];
+            gb2 += s0 + s1;
         }
         // ---- B4: dz1 = (dz2 . W2^T) * (1 - h1^2)  (registers), then in place over h1 --------------------
         float dz1[4][8];
         const bool live = ty * 4 < nrows;
         if (live) {
             zero_acc(dz1);
-            mm_nn(sm + L.h2 + ty * 4 * LDH + (tx >> 3) * H, LDH, sm + L.W2Tc + tx * 8, LDT, H, dz1);
+            mm_nn(sm + L.h2 + ty * 4 * LDH + br, LDH, sm + L.W2Tc + c0, sm + L.W2Tc + c1, LDT, H, dz1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float* hrow = sm + L.h1 + (ty * 4 + i) * LDH + tx * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float h = hrow[j];
-                    dz1[i][j] *= (1.f - h * h);
-                }
+                const float* hrow = sm + L.h1 + (ty * 4 + i) * LDH;
+                const float4 h0 = *reinterpret_cast<const float4*>(hrow + c0);
+                const float4 h1v = *reinterpret_cast<const float4*>(hrow + c1);
+                dz1[i][0] *= (1.f - h0.x * h0.x); dz1[i][1] *= (1.f - h0.y * h0.y);
+                dz1[i][2] *= (1.f - h0.z * h0.z); dz1[i][3] *= (1.f - h0.w * h0.w);
+                dz1[i][4] *= (1.f - h1v.x * h1v.x); dz1[i][5] *= (1.f - h1v.y * h1v.y);
+                dz1[i][6] *= (1.f - h1v.z * h1v.z); dz1[i][7] *= (1.f - h1v.w * h1v.w);
             }
         }
         __syncthreads();
         if (live) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float* dst = sm + L.h1 + (ty * 4 + i) * LDH + tx * 8;
-                *reinterpret_cast<float4*>(dst) = make_float4(dz1[i][0], dz1[i][1], dz1[i][2], dz1[i][3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(dz1[i][4], dz1[i][5], dz1[i][6], dz1[i][7]);
+                float* dst = sm + L.h1 + (ty * 4 + i) * LDH;
+                *reinterpret_cast<float4*>(dst + c0) = make_float4(dz1[i][0], dz1[i][1], dz1[i][2], dz1[i][3]);
+                *reinterpret_cast<float4*>(dst + c1) = make_float4(dz1[i][4], dz1[i][5], dz1[i][6], dz1[i][7]);
             }
         }
         __syncthreads();
         // ---- B5: gW1[d][c] += sum_r x[r][d] dz1[r][c];  gb1[c] += sum_r dz1[r][c] ------------------------
-        if (w1_live) mm_tn(sm + L.x + dq * 4, Dp, sm + L.h1 + tx * 8, LDH, rsplit, nrows, nsplit, gW1);
+        if (w1_live) mm_tn(sm + L.x + dq * 4, Dp, sm + L.h1 + c0, sm + L.h1 + c1, LDH, rsplit, nrows, nsplit, gW1);
         if (tid < HC) {
-            float s = gb1;
-            for (int r = 0; r < nrows; ++r) s += sm[L.h1 + r * LDH + tid];
-            gb1 = s;
+            float s0 = 0.f, s1 = 0.f;
+            int r = 0;
+            for (; r + 1 < nrows; r += 2) { s0 += sm[L.h1 + r * LDH + tid]; s1 += sm[L.h1 + (r + 1) * LDH + tid]; }
+            if (r < nrows) s0 += sm[L.h1 + r * LDH + tid];
+            gb1 += s0 + s1;
         }
         __syncthreads();
     }
 
-    // ---- write the per-CTA partial gradient (flat checkpoint order) -------------------------------------
-    float* gp = a.grad_part + ((int64_t)p * G + bx) * o.NP;
-    {   // W2 / Wv2
-        const int base = (tx < 8 ? o.W2 : o.Wv2) + (tx & 7) * 8;
+    // ---- write the per-CTA partial gradient (flat checkpoint order, partial stride padded to 4 floats) -----------
+    const int NPs = (o.NP + 3) & ~3;
+    float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    {   // W2 / Wv2: rows k = 4ty+i, columns (tx%8)*4 + {0..3} and +32
+        float* base = gp + (tx < 8 ? o.W2 : o.Wv2);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            float* row = base + (ty * 4 + i) * H + (tx & 7) * 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gp[base + (ty * 4 + i) * H + j] = gW2[i][j];
+            for (int j = 0; j < 4; ++j) { row[j] = gW2[i][j]; row[32 + j] = gW2[i][4 + j]; }
+        }
     }
     if (tid < HC) {
         gp[(tid < H ? o.b1 : o.bv1) + (tid & 63)] = gb1;
@@ -514,9 +502,11 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     float* scratch = sm + L.h1;  // nsplit * Dp * HC <= 2 * TM * LDH floats
     if (w1_live) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) scratch[(rsplit * Dp + dq * 4 + i) * HC + tx * 8 + j] = gW1[i][j];
+        for (int i = 0; i < 4; ++i) {
+            float* row = scratch + (rsplit * Dp + dq * 4 + i) * HC;
+            *reinterpret_cast<float4*>(row + c0) = make_float4(gW1[i][0], gW1[i][1], gW1[i][2], gW1[i][3]);
+            *reinterpret_cast<float4*>(row + c1) = make_float4(gW1[i][4], gW1[i][5], gW1[i][6], gW1[i][7]);
+        }
     }
     __syncthreads();
     for (int i = tid; i < D * HC; i += NT) {
@@ -530,6 +520,21 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
 #pragma unroll
         for (int i = 0; i < DDRL_NSTAT; ++i) sp[i] = st[i];
     }
+}
+
+// flat theta -> packed shared-memory image (one thread per parameter)
+__global__ void fcnet_pack_kernel(const float* __restrict__ theta, int D, int A, float* __restrict__ img) {
+    const int p = blockIdx.y;
+    const FcSmem L = fc_smem(D, A, false);
+    const FcOffsets o = fc_offsets(D, A);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= o.NP) return;
+    int p0, p1;
+    fc_img_pos(L, o, D, A, j, p0, p1);
+    const float w = theta[(int64_t)p * o.NP + j];
+    float* im = img + (int64_t)p * L.x;
+    im[p0] = w;
+    if (p1 >= 0) im[p1] = w;
 }
 
 }  // namespace ddrl
@@ -551,44 +556,65 @@ extern "C" int ddrl_fcnet_num_params(int D, int A) {
     return fc_offsets(D, A).NP;
 }
 
-extern "C" int ddrl_fcnet_forward(const float* theta, const float* obs, const double* norm, float clip, int P,
-                                  int64_t R, int D, int A, float* obs_out, float* logits, float* value,
-                                  const float* eps, float* action, float* logp, void* stream) {
-    DDRL_REQUIRE(theta && obs && P >= 1 && R >= 0, DDRL_E_BADARG, "fcnet_forward: null theta/obs or bad P/R");
+extern "C" int ddrl_fcnet_image_floats(int D, int A) {
+    if (D < 1 || D > DDRL_MAX_OBS || A < 1 || A > DDRL_MAX_ACT) return DDRL_E_UNSUPPORTED_SHAPE;
+    return fc_smem(D, A, false).x;
+}
+
+extern "C" int ddrl_fcnet_pack(const float* theta, int P, int D, int A, float* img, void* stream) {
+    DDRL_REQUIRE(theta && img && P >= 1, DDRL_E_BADARG, "fcnet_pack: null pointer or bad P");
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
+                 "fcnet_pack: unsupported D=%d A=%d", D, A);
+    const int NP = fc_offsets(D, A).NP;
+    cudaMemsetAsync(img, 0, (size_t)P * fc_smem(D, A, false).x * sizeof(float), (cudaStream_t)stream);
+    fcnet_pack_kernel<<<dim3((NP + 255) / 256, P), 256, 0, (cudaStream_t)stream>>>(theta, D, A, img);
+    DDRL_CHECK_LAUNCH("fcnet_pack");
+    return DDRL_OK;
+}
+
+static int set_smem_attr(const void* fn, bool* done, const char* who) {
+    if (!*done) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            set_error("%s: cannot raise dynamic shared memory: %s", who, cudaGetErrorString(cudaGetLastError()));
+            return DDRL_E_CUDA;
+        }
+        *done = true;
+    }
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_fcnet_forward(const float* theta, const float* img, const float* obs, const double* norm,
+                                  float clip, int P, int64_t R, int D, int A, float* obs_out, float* logits,
+                                  float* value, const float* eps, float* action, float* logp, void* stream) {
+    DDRL_REQUIRE((theta || img) && obs && P >= 1 && R >= 0, DDRL_E_BADARG, "fcnet_forward: null theta/obs or bad P/R");
     DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
                  "fcnet_forward: unsupported D=%d A=%d (D<=%d, A<=%d, hiddens [64,64], tanh)", D, A, DDRL_MAX_OBS,
                  DDRL_MAX_ACT);
     DDRL_REQUIRE(!eps || (action && logp), DDRL_E_BADARG, "fcnet_forward: eps given without action/logp outputs");
     if (R == 0) return DDRL_OK;
-    const FcSmem L = fc_smem(D, A, false, norm != nullptr);
+    const FcSmem L = fc_smem(D, A, norm != nullptr);
     const size_t smem = (size_t)L.total * sizeof(float);
+    DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "fcnet_forward: shared memory %zu > 227 KB", smem);
     static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(fcnet_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess) {
-            set_error("fcnet_forward: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
-            return DDRL_E_CUDA;
-        }
-        attr_set = true;
-    }
+    if (int rc = set_smem_attr((const void*)fcnet_forward_kernel, &attr_set, "fcnet_forward")) return rc;
     const int64_t ntiles = (R + TM - 1) / TM;
     const int per_policy = (int)std::min<int64_t>(ntiles, std::max(1, num_sms() / P));
     dim3 grid(per_policy, P);
-    fcnet_forward_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(theta, obs, norm, clip, R, D, A, obs_out, logits,
-                                                                   value, eps, action, logp);
+    fcnet_forward_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(theta, img, obs, norm, clip, R, D, A, obs_out,
+                                                                   logits, value, eps, action, logp);
     DDRL_CHECK_LAUNCH("fcnet_forward");
     return DDRL_OK;
 }
 
-extern "C" int ddrl_ppo_train_step(const float* theta, const float* obs, const float* actions,
+extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const float* obs, const float* actions,
                                    const float* old_logits, const float* old_logp, const float* vf_preds,
                                    const float* adv, const float* vtarg, const float* ext_dlogits,
                                    const float* ext_dvalue, int P, int64_t R, int D, int A, int MB,
                                    const int32_t* mb_perm, int64_t perm_stride, const int32_t* step_ctr,
                                    const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas_per_policy,
                                    float* grad_part, double* stat_part, void* stream) {
-    DDRL_REQUIRE(theta && obs && grad_part && P >= 1 && R >= 1 && MB >= 1 && ctas_per_policy >= 1, DDRL_E_BADARG,
-                 "ppo_train_step: null pointer or bad P/R/MB/ctas");
+    DDRL_REQUIRE((theta || img) && obs && grad_part && P >= 1 && R >= 1 && MB >= 1 && ctas_per_policy >= 1,
+                 DDRL_E_BADARG, "ppo_train_step: null pointer or bad P/R/MB/ctas");
     DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
                  "ppo_train_step: unsupported D=%d A=%d", D, A);
     const bool ext = ext_dlogits != nullptr;
@@ -596,24 +622,17 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* obs, const f
                      : (actions && old_logits && old_logp && vf_preds && adv && vtarg && kl_coeff && hyper),
                  DDRL_E_BADARG, "ppo_train_step: missing batch arrays for the %s path", ext ? "external-gradient" : "PPO");
     TrainArgs a;
-    a.theta = theta; a.obs = obs; a.actions = actions; a.old_logits = old_logits; a.old_logp = old_logp;
+    a.theta = theta; a.img = img; a.obs = obs; a.actions = actions; a.old_logits = old_logits; a.old_logp = old_logp;
     a.vf_preds = vf_preds; a.adv = adv; a.vtarg = vtarg; a.ext_dlogits = ext_dlogits; a.ext_dvalue = ext_dvalue;
     a.R = R; a.D = D; a.A = A; a.MB = MB; a.mb_perm = mb_perm; a.perm_stride = perm_stride; a.step_ctr = step_ctr;
     a.kl_coeff = kl_coeff;
     if (hyper) a.hp = *hyper; else a.hp = ddrl_ppo_hyper{0.f, 0.f, 0.f, 0.f, 1.f};
     a.grad_part = grad_part; a.stat_part = stat_part;
-    const FcSmem L = fc_smem(D, A, true, false);
+    const FcSmem L = fc_smem(D, A, false);
     const size_t smem = (size_t)L.total * sizeof(float);
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step: shared memory %zu > 227 KB", smem);
     static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(fcnet_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess) {
-            set_error("ppo_train_step: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
-            return DDRL_E_CUDA;
-        }
-        attr_set = true;
-    }
+    if (int rc = set_smem_attr((const void*)fcnet_train_kernel, &attr_set, "ppo_train_step")) return rc;
     dim3 grid(ctas_per_policy, P);
     fcnet_train_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(a);
     DDRL_CHECK_LAUNCH("ppo_train_step");

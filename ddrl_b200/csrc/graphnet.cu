@@ -275,7 +275,7 @@ graphnet_kernel(const float* __restrict__ theta, const int32_t* __restrict__ nod
     }
 
     if (BWD) {
-        float* gp = grad_part + (int64_t)bx * (oa.NP + gn_offsets(1).NP) + net_base;
+        float* gp = grad_part + (int64_t)bx * ((oa.NP + gn_offsets(1).NP + 3) & ~3) + net_base;
 #pragma unroll
         for (int k = 0; k < GK; ++k) {
             const int f = fs + 4 * k;

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "fcnet_layout.cuh"
 #include "ppo_loss.cuh"
 
 namespace ddrl {
@@ -193,10 +194,12 @@ __global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double
                                    const int32_t* __restrict__ step_ctr) {
     const int p = blockIdx.y, P = gridDim.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int NPs = (NP + 3) & ~3;   // partial stride (ddrl_b200.h)
     if (j < NP) {
-        const float* g = gpart + (int64_t)p * G * NP + j;
+        const float* g = gpart + (int64_t)p * G * NPs + j;
         float s = 0.f;
-        for (int i = 0; i < G; ++i) s += g[(int64_t)i * NP];
+#pragma unroll 4
+        for (int i = 0; i < G; ++i) s += g[(int64_t)i * NPs];
         grad[(int64_t)p * NP + j] = s;
     }
     if (blockIdx.x == 0 && threadIdx.x < DDRL_NSTAT && spart && step_stats) {
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(AT) clip_adam_kernel(float* __restrict__ theta
                                                        float* __restrict__ v, float* beta_pow,
                                                        const float* __restrict__ grad, int NP, float lr, float beta1,
                                                        float beta2, float eps, float clip, float* gnorm_out,
-                                                       int32_t* step_ctr, int32_t* sync_ws) {
+                                                       int32_t* step_ctr, int32_t* sync_ws, float* __restrict__ img,
+                                                       int imgD, int imgA) {
     __shared__ float red[AT / 32];
     __shared__ float s_scale;
     const int p = blockIdx.y, P = gridDim.y, tid = threadIdx.x;
@@ -245,7 +249,17 @@ __global__ void __launch_bounds__(AT) clip_adam_kernel(float* __restrict__ theta
         vj += (gj * gj - vj) * (1.f - beta2);
         m[k] = mj;
         v[k] = vj;
-        theta[k] -= (mj * alpha) / (sqrtf(vj) + eps);
+        const float tnew = theta[k] - (mj * alpha) / (sqrtf(vj) + eps);
+        theta[k] = tnew;
+        if (img) {   // keep the packed shared-memory image of the FCNet weights in step with theta
+            const FcSmem L = fc_smem(imgD, imgA, false);
+            const FcOffsets o = fc_offsets(imgD, imgA);
+            int p0, p1;
+            fc_img_pos(L, o, imgD, imgA, j, p0, p1);
+            float* im = img + (int64_t)p * L.x;
+            im[p0] = tnew;
+            if (p1 >= 0) im[p1] = tnew;
+        }
     }
     // arrival ticket: the last CTA advances the beta powers / step counter after everyone has read them
     __syncthreads();
@@ -404,15 +418,15 @@ extern "C" int ddrl_filter_update(const void* x, int x_is_f64, int P, int64_t R,
 extern "C" int64_t ddrl_gae_ws_bytes(int P, int64_t C) { return (int64_t)P * ((C + GT - 1) / GT) * 2 * (int64_t)sizeof(double); }
 
 extern "C" int ddrl_gae(const float* rewards, const float* values, const uint8_t* dones, const float* v_boot, int P,
-                        int T, int64_t C, int cols_per_env, float gamma, float lambda, float* adv, float* vtarg,
+                        int T, int64_t C, int cols_per_env, double gamma, double lambda, float* adv, float* vtarg,
                         double* moments, void* ws, void* stream) {
     DDRL_REQUIRE(rewards && values && dones && v_boot && adv && vtarg && moments && ws, DDRL_E_BADARG, "gae: null pointer");
     DDRL_REQUIRE(P >= 1 && T >= 1 && C >= 1 && cols_per_env >= 1 && C % cols_per_env == 0, DDRL_E_BADARG,
                  "gae: bad P/T/C/cols_per_env (C must be a multiple of cols_per_env)");
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = (int)((C + GT - 1) / GT);
-    gae_kernel<<<dim3(nblk, P), GT, 0, st>>>(rewards, values, dones, v_boot, T, C, cols_per_env, (double)gamma,
-                                             (double)lambda, adv, vtarg, (double*)ws);
+    gae_kernel<<<dim3(nblk, P), GT, 0, st>>>(rewards, values, dones, v_boot, T, C, cols_per_env, gamma,
+                                             lambda, adv, vtarg, (double*)ws);
     DDRL_CHECK_LAUNCH("gae");
     gae_moments_kernel<<<P, 32, 0, st>>>((const double*)ws, nblk, (double)T * (double)C, moments);
     DDRL_CHECK_LAUNCH("gae_moments");
@@ -447,11 +461,16 @@ extern "C" int ddrl_grad_reduce(const float* grad_part, const double* stat_part,
 
 extern "C" int ddrl_clip_adam(float* theta, float* m, float* v, float* beta_pow, const float* grad, int P, int NP,
                               float lr, float beta1, float beta2, float eps, float grad_clip, float* gnorm_out,
-                              int32_t* step_ctr, int32_t* sync_ws, void* stream) {
+                              int32_t* step_ctr, int32_t* sync_ws, float* fcnet_img, int img_D, int img_A,
+                              void* stream) {
     DDRL_REQUIRE(theta && m && v && beta_pow && grad && sync_ws && P >= 1 && NP >= 1, DDRL_E_BADARG,
                  "clip_adam: null pointer or bad shape");
+    DDRL_REQUIRE(!fcnet_img || (img_D >= 1 && img_D <= DDRL_MAX_OBS && img_A >= 1 && img_A <= DDRL_MAX_ACT &&
+                                fc_offsets(img_D, img_A).NP == NP),
+                 DDRL_E_BADARG, "clip_adam: fcnet image given but (D=%d, A=%d) does not match NP=%d", img_D, img_A, NP);
     clip_adam_kernel<<<dim3((NP + AT - 1) / AT, P), AT, 0, (cudaStream_t)stream>>>(
-        theta, m, v, beta_pow, grad, NP, lr, beta1, beta2, eps, grad_clip, gnorm_out, step_ctr, sync_ws);
+        theta, m, v, beta_pow, grad, NP, lr, beta1, beta2, eps, grad_clip, gnorm_out, step_ctr, sync_ws, fcnet_img,
+        img_D, img_A);
     DDRL_CHECK_LAUNCH("clip_adam");
     return DDRL_OK;
 }

@@ -72,9 +72,23 @@ def filter_update(x: torch.Tensor, n: torch.Tensor, M: torch.Tensor, S: torch.Te
     return norm
 
 
+def fcnet_image_floats(D: int, A: int) -> int:
+    return int(_lib.load().ddrl_fcnet_image_floats(D, A))
+
+
+def fcnet_pack(theta: torch.Tensor, D: int, A: int, img: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """theta [P,NP] -> packed shared-memory image [P, image_floats] (see ddrl_b200.h)."""
+    P = theta.shape[0]
+    if img is None:
+        img = torch.empty(P, fcnet_image_floats(D, A), dtype=torch.float32, device=theta.device)
+    _lib.check(_lib.load().ddrl_fcnet_pack(_p(theta, torch.float32, "theta"), P, D, A, _p(img, torch.float32, "img"),
+                                           _stream()), "fcnet_pack")
+    return img
+
+
 def fcnet_forward(theta: torch.Tensor, obs: torch.Tensor, A: int, norm: Optional[torch.Tensor] = None,
                   clip: float = 0.0, eps: Optional[torch.Tensor] = None, want_obs_out: bool = False,
-                  out: Optional[dict] = None) -> dict:
+                  out: Optional[dict] = None, img: Optional[torch.Tensor] = None) -> dict:
     """theta [P,NP], obs [P,R,D] -> dict(logits [P,R,2A], value [P,R], [obs_out], [action, logp])."""
     lib = _lib.load()
     P, R, D = obs.shape
@@ -90,7 +104,8 @@ def fcnet_forward(theta: torch.Tensor, obs: torch.Tensor, A: int, norm: Optional
         logp = out.get("logp") if "logp" in out else torch.empty(P, R, dtype=f32, device=dev)
     if theta.shape != (P, fcnet_num_params(D, A)):
         raise DDRLError(f"theta shape {tuple(theta.shape)} != ({P}, {fcnet_num_params(D, A)})")
-    _lib.check(lib.ddrl_fcnet_forward(_p(theta, f32, "theta"), _p(obs, f32, "obs"), _p(norm, torch.float64, "norm"),
+    _lib.check(lib.ddrl_fcnet_forward(_p(theta, f32, "theta"), _p(img, f32, "img"), _p(obs, f32, "obs"),
+                                      _p(norm, torch.float64, "norm"),
                                       float(clip), P, R, D, A, _p(obs_out, f32, "obs_out"), _p(logits, f32, "logits"),
                                       _p(value, f32, "value"), _p(eps, f32, "eps"), _p(action, f32, "action"),
                                       _p(logp, f32, "logp"), _stream()), "fcnet_forward")
@@ -146,13 +161,14 @@ def gather_rows(src: torch.Tensor, perm: torch.Tensor, dst: Optional[torch.Tenso
 
 def ppo_train_step(theta, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int,
                    mb_perm, step_ctr, kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part,
-                   ext_dlogits=None, ext_dvalue=None):
+                   ext_dlogits=None, ext_dvalue=None, img=None):
     lib = _lib.load()
     P, R, D = obs.shape
     f32 = torch.float32
     perm_stride = mb_perm.shape[-1] if mb_perm is not None else 0
     _lib.check(lib.ddrl_ppo_train_step(
-        _p(theta, f32, "theta"), _p(obs, f32, "obs"), _p(actions, f32, "actions"), _p(old_logits, f32, "old_logits"),
+        _p(theta, f32, "theta"), _p(img, f32, "img"), _p(obs, f32, "obs"), _p(actions, f32, "actions"),
+        _p(old_logits, f32, "old_logits"),
         _p(old_logp, f32, "old_logp"), _p(vf_preds, f32, "vf_preds"), _p(adv, f32, "adv"), _p(vtarg, f32, "vtarg"),
         _p(ext_dlogits, f32, "ext_dlogits"), _p(ext_dvalue, f32, "ext_dvalue"), P, R, D, A, MB,
         _p(mb_perm, torch.int32, "mb_perm"), perm_stride, _p(step_ctr, torch.int32, "step_ctr"),
@@ -167,15 +183,21 @@ def grad_reduce(grad_part, stat_part, P: int, G: int, NP: int, grad, step_stats=
                                             _p(step_ctr, torch.int32, "step_ctr"), _stream()), "grad_reduce")
 
 
+def part_stride(NP: int) -> int:
+    """Row stride (floats) of the per-CTA gradient partials: NP rounded up to a multiple of 4."""
+    return (NP + 3) & ~3
+
+
 def clip_adam(theta, m, v, beta_pow, grad, lr: float, beta1: float, beta2: float, eps: float, grad_clip: float,
-              sync_ws, gnorm_out=None, step_ctr=None):
+              sync_ws, gnorm_out=None, step_ctr=None, img=None, img_D: int = 0, img_A: int = 0):
     P, NP = theta.shape
     f32 = torch.float32
     _lib.check(_lib.load().ddrl_clip_adam(_p(theta, f32, "theta"), _p(m, f32, "m"), _p(v, f32, "v"),
                                           _p(beta_pow, f32, "beta_pow"), _p(grad, f32, "grad"), P, NP, float(lr),
                                           float(beta1), float(beta2), float(eps), float(grad_clip),
                                           _p(gnorm_out, f32, "gnorm_out"), _p(step_ctr, torch.int32, "step_ctr"),
-                                          _p(sync_ws, torch.int32, "sync_ws"), _stream()), "clip_adam")
+                                          _p(sync_ws, torch.int32, "sync_ws"), _p(img, f32, "img"), int(img_D),
+                                          int(img_A), _stream()), "clip_adam")
 
 
 def fcnet_backward(theta, obs, dlogits, dvalue, A: int, ctas_per_policy: Optional[int] = None) -> torch.Tensor:
@@ -183,7 +205,7 @@ def fcnet_backward(theta, obs, dlogits, dvalue, A: int, ctas_per_policy: Optiona
     P, R, D = obs.shape
     NP = theta.shape[1]
     G = ctas_per_policy or max(1, min((R + 63) // 64, 148 // P))
-    gp = torch.empty(P, G, NP, dtype=torch.float32, device=obs.device)
+    gp = torch.empty(P, G, part_stride(NP), dtype=torch.float32, device=obs.device)
     grad = torch.empty(P, NP, dtype=torch.float32, device=obs.device)
     ppo_train_step(theta, obs, None, None, None, None, None, None, A, R, None, None, None, None, G, gp, None,
                    ext_dlogits=dlogits, ext_dvalue=dvalue)
@@ -214,7 +236,7 @@ def graphnet_backward(theta, node_idx, state, adj, dlogits, dvalue, A: int, ctas
     f32 = torch.float32
     NP = theta.numel()
     G = ctas or max(1, min(B, 74))
-    gp = torch.zeros(G, NP, dtype=f32, device=state.device)
+    gp = torch.zeros(G, part_stride(NP), dtype=f32, device=state.device)
     grad = torch.empty(1, NP, dtype=f32, device=state.device)
     _lib.check(_lib.load().ddrl_graphnet_backward(_p(theta, f32, "theta"), _p(node_idx, torch.int32, "node_idx"),
                                                   _p(state, f32, "state"), _p(adj, f32, "adj"),

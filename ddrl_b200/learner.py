@@ -53,7 +53,7 @@ def finalize_stats(sums: np.ndarray, kl_coeff: np.ndarray, cfg: PPOConfig, rows:
             ev = np.maximum(-1.0, 1.0 - dvar / yvar)
         m = lambda a: float(np.mean(a.astype(np.float32)))
         out.append({"total_loss": m(total), "policy_loss": m(pol), "vf_loss": m(vf), "kl": m(kl), "entropy": m(ent),
-                    "vf_explained_var": m(ev), "cur_kl_coeff": float(kl_coeff[p]), "cur_lr": float(np.float32(cfg.lr)),
+                    "vf_explained_var": m(ev), "cur_kl_coeff": float(np.float32(kl_coeff[p])), "cur_lr": float(np.float32(cfg.lr)),
                     "entropy_coeff": float(cfg.entropy_coeff)})
     return out
 
@@ -72,7 +72,7 @@ class _LearnerBase:
         self.m = torch.zeros_like(self.theta)
         self.v = torch.zeros_like(self.theta)
         self.beta_pow = torch.tensor([[cfg.beta1, cfg.beta2]] * P, dtype=f32, device=self.device)
-        self.kl_coeff_host = np.full(P, np.float32(cfg.kl_coeff), dtype=np.float64)
+        self.kl_coeff_host = np.full(P, cfg.kl_coeff, dtype=np.float64)   # python-float state, like KLCoeffMixin.kl_coeff_val
         self.kl_coeff = torch.full((P,), cfg.kl_coeff, dtype=f32, device=self.device)
         self.grad = torch.zeros(P, NP, dtype=f32, device=self.device)
         self.gnorm = torch.zeros(P, dtype=f32, device=self.device)
@@ -86,8 +86,10 @@ class _LearnerBase:
 
     def _adam(self):
         c = self.cfg
+        img = getattr(self, "img", None)
         K.clip_adam(self.theta, self.m, self.v, self.beta_pow, self.grad, c.lr, c.beta1, c.beta2, c.adam_eps,
-                    c.grad_clip, self.sync_ws, self.gnorm, self.step_ctr)
+                    c.grad_clip, self.sync_ws, self.gnorm, self.step_ctr, img, getattr(self, "D", 0) if img is not None else 0,
+                    self.A if img is not None else 0)
 
     def _update_kl(self, stats: List[Dict[str, float]]):
         # KLCoeffMixin.update_kl (RLlib 1.0.1): x1.5 if kl > 2*target, x0.5 if kl < 0.5*target
@@ -113,6 +115,9 @@ class FCNetLearner(_LearnerBase):
         self.norm = torch.zeros(P, 2, D, dtype=torch.float64, device=dev)
         self.use_graph = use_graph
         self.ctas_per_policy = ctas_per_policy
+        # packed shared-memory image of the weights (kept in step by clip_adam); rebuilt at every iteration start so
+        # external writes to self.theta (checkpoint import) are picked up
+        self.img = torch.zeros(P, K.fcnet_image_floats(D, A), dtype=torch.float32, device=dev)
         self._bufs = None
         self._graph = None
         self._graph_key = None
@@ -153,7 +158,7 @@ class FCNetLearner(_LearnerBase):
     def _sgd_step(self, b, MB, G, hyper, src):
         K.ppo_train_step(self.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
                          src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
-                         b["grad_part"], b["stat_part"])
+                         b["grad_part"], b["stat_part"], img=self.img)
         K.grad_reduce(b["grad_part"], b["stat_part"], self.P, G, self.NP, self.grad, b["step_stats"], self.step_ctr)
         if self.world > 1:
             self.dist.all_reduce(self.grad)
@@ -175,6 +180,7 @@ class FCNetLearner(_LearnerBase):
         R = T * Cc
         b = self._alloc(T, Cc)
         obs_flat = raw_obs.reshape(P, R, D)
+        K.fcnet_pack(self.theta, D, A, self.img)
         # (i) filter + forward + sample ------------------------------------------------------------------
         if update_filter:
             if self.world > 1:
@@ -184,10 +190,10 @@ class FCNetLearner(_LearnerBase):
                 K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])
         K.fcnet_forward(self.theta, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
                         out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
-                             "logp": b["logp"]})
+                             "logp": b["logp"]}, img=self.img)
         # (ii) bootstrap + GAE + standardise -----------------------------------------------------------
         K.fcnet_forward(self.theta, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
-                        out={"logits": None, "value": b["vboot"], "obs_out": None})
+                        out={"logits": None, "value": b["vboot"], "obs_out": None}, img=self.img)
         K.gae(rewards, b["value"].view(P, T, Cc), dones, b["vboot"], cols_per_env, cfg.gamma, cfg.lambda_,
               b["adv"].view(P, T, Cc), b["vtarg"].view(P, T, Cc), b["moments"], b["gae_ws"])
         if self.world > 1:
@@ -212,7 +218,7 @@ class FCNetLearner(_LearnerBase):
         if b.get("sgd_key") != (steps, G):
             b["sgd_key"] = (steps, G)
             b["mb_perm"] = torch.empty(P, steps, dtype=torch.int32, device=self.device)
-            b["grad_part"] = torch.empty(P, G, self.NP, dtype=torch.float32, device=self.device)
+            b["grad_part"] = torch.empty(P, G, K.part_stride(self.NP), dtype=torch.float32, device=self.device)
             b["stat_part"] = torch.empty(P, G, K.NSTAT, dtype=torch.float64, device=self.device)
             b["step_stats"] = torch.zeros(steps, P, K.NSTAT, dtype=torch.float64, device=self.device)
             self._graph = None
@@ -300,7 +306,7 @@ class GraphNetLearner(_LearnerBase):
         LG = max(1, min(64, (MB + 255) // 256))
         dlogits = torch.empty(MB, 2 * A, dtype=f32, device=dev)
         dvalue = torch.empty(MB, dtype=f32, device=dev)
-        gpart = torch.empty(G, self.NP, dtype=f32, device=dev)
+        gpart = torch.empty(G, K.part_stride(self.NP), dtype=f32, device=dev)
         spart = torch.empty(1, LG, K.NSTAT, dtype=torch.float64, device=dev)
         step_stats = torch.zeros(E * nb, 1, K.NSTAT, dtype=torch.float64, device=dev)
         order = perms.cpu().numpy()

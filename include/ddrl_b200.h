@@ -55,6 +55,14 @@ int64_t ddrl_launch_count(void);
  * ------------------------------------------------------------------------------------------- */
 int ddrl_fcnet_num_params(int D, int A);
 
+/* Packed weight image: the FCNet kernels keep one policy's weights in shared memory in a kernel-specific
+ * layout (branches concatenated, layer 2 also transposed, head matrix transposed).  An image is that layout in
+ * global memory, img[P][ddrl_fcnet_image_floats(D, A)], so the per-step weight load of the SGD loop is one
+ * coalesced 128-bit copy.  ddrl_fcnet_pack builds it from theta; ddrl_clip_adam keeps it in step when given.
+ * Every entry point that takes (theta, img) uses img when it is not NULL and theta otherwise. */
+int ddrl_fcnet_image_floats(int D, int A);
+int ddrl_fcnet_pack(const float* theta, int P, int D, int A, float* img, void* stream);
+
 /* Replaces: ray.rllib.utils.filter.MeanStdFilter.__call__ (vectorised update), instantiated at
  * simulation_envs/observation_filter.py:8-12 and by observation_filter="MeanStdFilter"
  * (train_experiment_3_architecture_curriculum_targetvel.py:71).
@@ -92,9 +100,9 @@ int ddrl_filter_merge(const void* parts, int nparts, int P, int D, int64_t R_tot
  *   eps      [P][R][A] float32 or NULL: if given, DiagGaussian sample (RLlib
  *            models/tf/tf_action_dist.py): action = mean + exp(log_std)*eps -> action [P][R][A]
  *            (unclipped, as stored in the sample batch) and logp [P][R]. */
-int ddrl_fcnet_forward(const float* theta, const float* obs, const double* norm, float clip,
-                       int P, int64_t R, int D, int A, float* obs_out, float* logits, float* value,
-                       const float* eps, float* action, float* logp, void* stream);
+int ddrl_fcnet_forward(const float* theta, const float* img, const float* obs, const double* norm,
+                       float clip, int P, int64_t R, int D, int A, float* obs_out, float* logits,
+                       float* value, const float* eps, float* action, float* logp, void* stream);
 
 /* Replaces: compute_advantages + postprocess_ppo_gae (RLlib evaluation/postprocessing.py,
  * agents/ppo/ppo_tf_policy.py), selected by use_gae/gamma/lambda at
@@ -106,7 +114,7 @@ int ddrl_fcnet_forward(const float* theta, const float* obs, const double* norm,
  *   ws: ddrl_gae_ws_bytes(P, C). */
 int64_t ddrl_gae_ws_bytes(int P, int64_t C);
 int ddrl_gae(const float* rewards, const float* values, const uint8_t* dones, const float* v_boot,
-             int P, int T, int64_t C, int cols_per_env, float gamma, float lambda, float* adv,
+             int P, int T, int64_t C, int cols_per_env, double gamma, double lambda, float* adv,
              float* vtarg, double* moments, void* ws, void* stream);
 
 /* Replaces: StandardizeFields(["advantages"]) (RLlib execution/rollout_ops.py):
@@ -127,7 +135,8 @@ int ddrl_gather_rows(const float* src, const int32_t* perm, int P, int64_t R, in
  *   kl_coeff [P] float32 (device),  hyper (host values): clip_param, vf_clip_param, vf_loss_coeff,
  *   entropy_coeff, inv_global_mb = 1 / (MB summed over all ranks).
  * Outputs (workspace, per CTA, reduced by ddrl_grad_reduce in fixed order -> deterministic):
- *   grad_part [P][G][NP] float32, stat_part [P][G][DDRL_NSTAT] float64, G = ctas_per_policy
+ *   grad_part [P][G][NPs] float32 (NPs = NP rounded up to a multiple of 4),
+ *   stat_part [P][G][DDRL_NSTAT] float64, G = ctas_per_policy
  *   stat sums: 0 sum(-surr) 1 sum(kl) 2 sum(vf) 3 sum(entropy) 4 sum(R) 5 sum(R^2)
  *              6 sum(R-v) 7 sum((R-v)^2)       (R = value_targets)
  * If ext_dlogits != NULL the loss is skipped and the row gradients are read from
@@ -136,7 +145,7 @@ typedef struct {
     float clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff, inv_global_mb;
 } ddrl_ppo_hyper;
 
-int ddrl_ppo_train_step(const float* theta, const float* obs, const float* actions,
+int ddrl_ppo_train_step(const float* theta, const float* img, const float* obs, const float* actions,
                         const float* old_logits, const float* old_logp, const float* vf_preds,
                         const float* adv, const float* vtarg, const float* ext_dlogits,
                         const float* ext_dvalue, int P, int64_t R, int D, int A, int MB,
@@ -155,7 +164,7 @@ int ddrl_ppo_loss_grad(const float* logits, const float* value, const float* act
                        float* dvalue, double* stat_part, void* stream);
 
 /* Fixed-order reduction of the per-CTA partials:
- *   grad [P][NP] float32 = sum_g grad_part[p][g][:]
+ *   grad [P][NP] float32 = sum_g grad_part[p][g][:NP]      (grad_part rows are NPs = (NP+3)&~3 floats apart)
  *   step_stats [*step_ctr][P][DDRL_NSTAT] float64 = sum_g stat_part[p][g][:]   (if step_stats) */
 int ddrl_grad_reduce(const float* grad_part, const double* stat_part, int P, int G, int NP,
                      float* grad, double* step_stats, const int32_t* step_ctr, void* stream);
@@ -168,10 +177,12 @@ int ddrl_grad_reduce(const float* grad_part, const double* stat_part, int P, int
  *   beta_pow [P][2] (device) = {b1^t, b2^t} to be used by THIS step (TF convention: initialised to
  *   {b1, b2}, multiplied after the update), gnorm_out [P] or NULL,
  *   sync_ws: one zero-initialised int32 (device) used as an arrival ticket; the last CTA to finish
- *   multiplies the beta powers, increments *step_ctr (if not NULL) and re-zeroes the ticket. */
+ *   multiplies the beta powers, increments *step_ctr (if not NULL) and re-zeroes the ticket.
+ *   fcnet_img (or NULL): packed FCNet weight image [P][ddrl_fcnet_image_floats(img_D, img_A)] to update in step. */
 int ddrl_clip_adam(float* theta, float* m, float* v, float* beta_pow, const float* grad, int P,
                    int NP, float lr, float beta1, float beta2, float eps, float grad_clip,
-                   float* gnorm_out, int32_t* step_ctr, int32_t* sync_ws, void* stream);
+                   float* gnorm_out, int32_t* step_ctr, int32_t* sync_ws, float* fcnet_img, int img_D,
+                   int img_A, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GraphNet (models/graph_net.py:10-45) + actor/critic wrapper
@@ -187,7 +198,7 @@ int ddrl_graphnet_forward(const float* theta, const int32_t* node_idx, const flo
                           const float* adj, int64_t B, int A, float* logits, float* value,
                           void* stream);
 /* Backward of the wrapper w.r.t. theta from dlogits [B][2A], dvalue [B]:
- *   grad_part [G][NP] per-CTA partials (reduce with ddrl_grad_reduce(P=1)); G = ctas. */
+ *   grad_part [G][NPs] per-CTA partials, NPs = (NP+3)&~3 (reduce with ddrl_grad_reduce(P=1)); G = ctas. */
 int ddrl_graphnet_backward(const float* theta, const int32_t* node_idx, const float* state,
                            const float* adj, const float* dlogits, const float* dvalue, int64_t B,
                            int A, int ctas, float* grad_part, void* stream);

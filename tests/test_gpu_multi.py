@@ -1,0 +1,108 @@
+"""GPU (needs >= 2 devices; run with `gpurun --gpus 2`): the 2-rank NCCL data-parallel learner reproduces the
+1-GPU result on the same global batch (shard by env, gradient all-reduce per optimizer step, rank-ordered filter
+merge, advantage-moment all-reduce)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import ckpt_theta, scaled_err, synth_obs
+
+pytestmark = pytest.mark.gpu
+
+T, C, E, NB = 16, 64, 2, 4
+ARCH = "FullyDecentral"
+
+
+def _problem():
+    theta, filt, D, A = ckpt_theta(ARCH)
+    P = theta.shape[0]
+    rng = np.random.default_rng(5)
+    raw = synth_obs(filt, T * C, 1).reshape(P, T, C, D)
+    boot = synth_obs(filt, C, 2)
+    rewards = (0.3 + 0.5 * rng.standard_normal((P, T, C))).astype(np.float32)
+    dones = (rng.random((T, C)) < 0.05).astype(np.uint8)
+    eps = rng.standard_normal((P, T, C, A)).astype(np.float32)
+    perms = np.stack([np.stack([rng.permutation(NB) for _ in range(E)]) for _ in range(P)]).astype(np.int32)
+    return dict(theta=theta, filt=filt, D=D, A=A, P=P, raw=raw, boot=boot, rewards=rewards, dones=dones, eps=eps, perms=perms)
+
+
+def _learner(pr, dev, mb):
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import FCNetLearner
+    cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=mb)
+    L = FCNetLearner(pr["P"], pr["D"], pr["A"], cfg, dev, theta=torch.from_numpy(pr["theta"]), use_graph=False)
+    filt = [(1000, M, S * (999.0 / (n - 1))) for n, M, S in pr["filt"]]
+    L.filt_n.copy_(torch.tensor([f[0] for f in filt]))
+    L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt])))
+    L.filt_S.copy_(torch.from_numpy(np.stack([f[2] for f in filt])))
+    return L
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pr = _problem()
+    Cl = C // world
+    sl = slice(rank * Cl, (rank + 1) * Cl)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    L = _learner(pr, dev, (T * C) // NB)
+    stats = L.learn_on_rollout(to(pr["raw"][:, :, sl]), to(pr["boot"][:, sl]), to(pr["rewards"][:, :, sl]),
+                               to(pr["dones"][:, sl]), to(pr["eps"][:, :, sl]), to(pr["perms"]))
+    torch.cuda.synchronize()
+    th = L.theta.cpu().numpy()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, th)
+    if rank == 0:
+        q.put((th, stats, L.filt_n.cpu().numpy(), L.filt_M.cpu().numpy(), [np.array_equal(g, th) for g in gathered]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_learner_equals_one_gpu_learner():
+    import torch.multiprocessing as mp
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    th2, stats2, n2, M2, same = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(same), "ranks diverged: replicated weights must stay bit-identical"
+
+    # 1-GPU run on the full batch, rows ordered so every minibatch is the union of the ranks' local minibatches
+    pr = _problem()
+    Cl, MBl = C // world, (T * C) // NB // world
+    order = []
+    for b in range(NB):
+        for r in range(world):
+            for j in range(MBl):
+                t, cl = divmod(b * MBl + j, Cl)
+                order.append(t * C + r * Cl + cl)
+    shuffle = np.tile(np.asarray(order, dtype=np.int32), (pr["P"], 1))
+    dev = torch.device("cuda", 0)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    L = _learner(pr, dev, (T * C) // NB)
+    stats1 = L.learn_on_rollout(to(pr["raw"]), to(pr["boot"]), to(pr["rewards"]), to(pr["dones"]), to(pr["eps"]),
+                                to(pr["perms"]), to(shuffle))
+    torch.cuda.synchronize()
+    assert np.array_equal(L.filt_n.cpu().numpy(), n2)
+    np.testing.assert_allclose(M2, L.filt_M.cpu().numpy(), rtol=1e-12, atol=1e-13)
+    th1 = L.theta.cpu().numpy()
+    for p in range(pr["P"]):
+        upd1 = th1[p].astype(np.float64) - pr["theta"][p]
+        upd2 = th2[p].astype(np.float64) - pr["theta"][p]
+        assert scaled_err(th2[p], th1[p]) < 1e-4
+        assert scaled_err(upd2, upd1) < 0.2          # FP32 reduction order differs; Adam amplifies
+        for k in ("total_loss", "policy_loss", "vf_loss", "kl", "entropy"):
+            assert abs(stats2[p][k] - stats1[p][k]) < 1e-4 * max(1.0, abs(stats1[p][k])), (k, stats2[p][k], stats1[p][k])

@@ -117,4 +117,4 @@ def test_finalize_stats_matches_oracle_definitions():
     out = finalize_stats(sums, np.array([0.3]), cfg, n)[0]
     for k in O.STAT_KEYS:
         assert abs(out[k] - float(st[k])) < 1e-5 * max(1.0, abs(float(st[k]))), k
-    assert out["cur_kl_coeff"] == 0.3 and out["cur_lr"] == float(np.float32(3e-4))
+    assert out["cur_kl_coeff"] == float(np.float32(0.3)) and out["cur_lr"] == float(np.float32(3e-4))
