@@ -42,12 +42,32 @@ __device__ void load_weights_flat(float* sm, const FcSmem& L, const float* __res
     }
 }
 
+// ---- cp.async (LDGSTS): global -> shared without staging registers; completion via commit/wait groups ----------
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ void load_weights_img(float* sm, const FcSmem& L, const float* __restrict__ img) {
-    const float4* src = reinterpret_cast<const float4*>(img);
-    float4* dst = reinterpret_cast<float4*>(sm);
     const int n4 = L.x >> 2;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n4; i += NT) dst[i] = src[i];
+    for (int i = threadIdx.x; i < n4; i += NT) cp_async16(sm + 4 * i, img + 4 * i);
+}
+
+// asynchronous x tile (no filter): rows row0.. -> xbuf[r*Dp + d]
+__device__ __forceinline__ void prefetch_x_tile(float* xbuf, const float* __restrict__ obs, int64_t row0, int nrows, int D) {
+    const int Dp = (D + 3) & ~3;
+    const int n = nrows * D;
+    const float* src = obs + row0 * D;
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const int r = i / D, d = i - r * D;
+        cp_async4(xbuf + r * Dp + d, src + i);
+    }
 }
 
 // ---- register-tile micro kernels -------------------------------------------------------------
@@ -156,16 +176,16 @@ __device__ __forceinline__ void forward_tile(float* sm, const FcSmem& L, int D, 
         const float* hrow = sm + L.h2 + r * LDH + (isv ? H : 0);
         const float* w = isv ? sm + L.Wvo : sm + L.Wo + o;
         const int ws = isv ? 1 : A2;
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
         for (int k = 0; k < H; k += 4) {
             const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
-            s = fmaf(hv.x, w[(k + 0) * ws], s);
-            s = fmaf(hv.y, w[(k + 1) * ws], s);
-            s = fmaf(hv.z, w[(k + 2) * ws], s);
-            s = fmaf(hv.w, w[(k + 3) * ws], s);
+            s0 = fmaf(hv.x, w[(k + 0) * ws], s0);
+            s1 = fmaf(hv.y, w[(k + 1) * ws], s1);
+            s2 = fmaf(hv.z, w[(k + 2) * ws], s2);
+            s3 = fmaf(hv.w, w[(k + 3) * ws], s3);
         }
-        sm[L.out + r * LDD + o] = s + (isv ? sm[L.bvo] : sm[L.bo + o]);
+        sm[L.out + r * LDD + o] = ((s0 + s1) + (s2 + s3)) + (isv ? sm[L.bvo] : sm[L.bo + o]);
     }
     __syncthreads();
 }
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
     const int D = a.D, A = a.A, A2 = 2 * A, Dp = (D + 3) & ~3;
-    const FcSmem L = fc_smem(D, A, false);
+    const FcSmem L = fc_smem(D, A, false, true);
     const FcOffsets o = fc_offsets(D, A);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, lane = tid & 31, warp = tid >> 5;
     const int br = (tx >> 3) * H, c0 = br + (tx & 7) * 4, c1 = c0 + 32;
@@ -291,13 +311,38 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
     const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
 
+    // ---- prologue: weights + first x tile + first loss inputs stream in asynchronously ----------------------
+    const float* obs_p = a.obs + (int64_t)p * a.R * D;
+    for (int i = tid; i < 2 * TM * Dp; i += NT) sm[L.x + i] = 0.f;       // both x buffers (pad columns stay zero)
+    for (int i = tid; i < 2 * TM * LDD; i += NT) sm[L.out + i] = 0.f;    // out and dl (dl pad columns stay zero)
+    __syncthreads();
+    auto prefetch_loss_inputs = [&](int64_t row0, int nrows) {
+        const int64_t g0 = (int64_t)p * a.R + row0;
+        float* pa = sm + L.pf;
+        float* po = pa + TM * A;
+        float* ps = po + TM * A2;
+        if (ext) {
+            for (int i = tid; i < nrows * A2; i += NT) cp_async4(po + i, a.ext_dlogits + g0 * A2 + i);
+            for (int i = tid; i < nrows; i += NT) cp_async4(ps + i, a.ext_dvalue + g0 + i);
+        } else {
+            for (int i = tid; i < nrows * A; i += NT) cp_async4(pa + i, a.actions + g0 * A + i);
+            for (int i = tid; i < nrows * A2; i += NT) cp_async4(po + i, a.old_logits + g0 * A2 + i);
+            for (int i = tid; i < nrows; i += NT) {
+                cp_async4(ps + i, a.old_logp + g0 + i);
+                cp_async4(ps + TM + i, a.vf_preds + g0 + i);
+                cp_async4(ps + 2 * TM + i, a.adv + g0 + i);
+                cp_async4(ps + 3 * TM + i, a.vtarg + g0 + i);
+            }
+        }
+    };
     if (cr1 > cr0) {
         if (a.img) load_weights_img(sm, L, a.img + (int64_t)p * L.x);
-        else load_weights_flat(sm, L, a.theta + (int64_t)p * o.NP, D, A);
+        const int n0 = (int)min((int64_t)TM, cr1 - cr0);
+        prefetch_x_tile(sm + L.x, obs_p, cr0, n0, D);
+        prefetch_loss_inputs(cr0, n0);
+        cp_async_commit();
+        if (!a.img) load_weights_flat(sm, L, a.theta + (int64_t)p * o.NP, D, A);
     }
-    for (int i = tid; i < TM * Dp; i += NT) sm[L.x + i] = 0.f;
-    for (int i = tid; i < 2 * TM * LDD; i += NT) sm[L.out + i] = 0.f;   // out and dl (dl pad columns stay zero)
-    __syncthreads();
 
     // gradient accumulators (registers, live across tiles) -----------------------------------
     float gW2[4][8], gW1[4][8], gHead[MAXHEAD];
@@ -317,50 +362,39 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     const bool w1_live = rsplit < nsplit;
 
     const float klc = ext ? 0.f : a.kl_coeff[p];
-    const float* obs_p = a.obs + (int64_t)p * a.R * D;
+    int xb = 0;   // x buffer holding the current tile
 
     for (int64_t row0 = cr0; row0 < cr1; row0 += TM) {
         const int nrows = (int)min((int64_t)TM, cr1 - row0);
-        // prefetch the loss inputs of this tile's rows (threads 0..63, one row each): issued before the forward
-        // pass so their DRAM/L2 latency is hidden behind it
-        float pf_act[DDRL_MAX_ACT], pf_ol[2 * DDRL_MAX_ACT], pf_s[4];
-        const bool loss_thread = tid < TM && tid < nrows;
-        if (loss_thread) {
-            const int64_t gr = (int64_t)p * a.R + row0 + tid;
-            if (ext) {
-#pragma unroll
-                for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
-                    if (i < A2) pf_ol[i] = a.ext_dlogits[gr * A2 + i];
-                pf_s[0] = a.ext_dvalue[gr];
-            } else {
-#pragma unroll
-                for (int i = 0; i < DDRL_MAX_ACT; ++i)
-                    if (i < A) pf_act[i] = a.actions[gr * A + i];
-#pragma unroll
-                for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
-                    if (i < A2) pf_ol[i] = a.old_logits[gr * A2 + i];
-                pf_s[0] = a.old_logp[gr]; pf_s[1] = a.vf_preds[gr]; pf_s[2] = a.adv[gr]; pf_s[3] = a.vtarg[gr];
-            }
+        const int xoff = xb ? L.x2 : L.x;
+        cp_async_wait_all();
+        __syncthreads();          // weights / x tile / loss inputs of this tile have landed for every thread
+        {   // prefetch the next x tile into the other buffer while this one is computed
+            const int64_t nxt = row0 + TM;
+            if (nxt < cr1) prefetch_x_tile(sm + (xb ? L.x : L.x2), obs_p, nxt, (int)min((int64_t)TM, cr1 - nxt), D);
+            cp_async_commit();
         }
-        load_x_tile(sm, L, obs_p, nullptr, nullptr, 0.f, row0, nrows, D);
-        __syncthreads();
-        forward_tile(sm, L, D, A, nrows);
+        FcSmem Lx = L;
+        Lx.x = xoff;
+        forward_tile(sm, Lx, D, A, nrows);
 
         // ---- per-row loss gradient -> dl[r][0..2A) = dL/dlogits, dl[r][2A] = dL/dvalue ------------
         if (tid < TM) {
             double s[DDRL_NSTAT];
 #pragma unroll
             for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
-            if (loss_thread) {
+            if (tid < nrows) {
                 float* dl = sm + L.dl + tid * LDD;
                 const float* out = sm + L.out + tid * LDD;
+                const float* pa = sm + L.pf;
+                const float* po = pa + TM * A;
+                const float* ps = po + TM * A2;
                 if (ext) {
-#pragma unroll
-                    for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i)
-                        if (i < A2) dl[i] = pf_ol[i];
-                    dl[A2] = pf_s[0];
+                    for (int i = 0; i < A2; ++i) dl[i] = po[tid * A2 + i];
+                    dl[A2] = ps[tid];
                 } else {
-                    ppo_row_loss(out, A, pf_act, pf_ol, pf_s[0], pf_s[1], pf_s[2], pf_s[3], klc, a.hp, dl, s);
+                    ppo_row_loss(out, A, pa + tid * A, po + tid * A2, ps[tid], ps[TM + tid], ps[2 * TM + tid],
+                                 ps[3 * TM + tid], klc, a.hp, dl, s);
                 }
             }
             if (!ext) {
@@ -381,6 +415,11 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
 #pragma unroll
             for (int i = 0; i < DDRL_NSTAT; ++i) st[i] += red[i];
         }
+        {   // the staged loss inputs are consumed: prefetch the next tile's (same cp.async group window as x)
+            const int64_t nxt = row0 + TM;
+            if (nxt < cr1) prefetch_loss_inputs(nxt, (int)min((int64_t)TM, cr1 - nxt));
+            cp_async_commit();
+        }
 
         // ---- B1: head weight gradients  gWo[k][o] += sum_r h2[r][k] dl[r][o] ---------------------------
 #pragma unroll
@@ -390,10 +429,16 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
                 const int k = item & 63, oo = item >> 6;
                 const float* hcol = sm + L.h2 + (oo == A2 ? H : 0) + k;
                 const float* dcol = sm + L.dl + oo;
-                float s = gHead[i];
-#pragma unroll 8
-                for (int r = 0; r < nrows; ++r) s = fmaf(hcol[r * LDH], dcol[r * LDD], s);
-                gHead[i] = s;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int r = 0;
+                for (; r + 3 < nrows; r += 4) {
+                    s0 = fmaf(hcol[r * LDH], dcol[r * LDD], s0);
+                    s1 = fmaf(hcol[(r + 1) * LDH], dcol[(r + 1) * LDD], s1);
+                    s2 = fmaf(hcol[(r + 2) * LDH], dcol[(r + 2) * LDD], s2);
+                    s3 = fmaf(hcol[(r + 3) * LDH], dcol[(r + 3) * LDD], s3);
+                }
+                for (; r < nrows; ++r) s0 = fmaf(hcol[r * LDH], dcol[r * LDD], s0);
+                gHead[i] += (s0 + s1) + (s2 + s3);
             }
         }
         if (tid <= A2) {
@@ -461,7 +506,7 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
         }
         __syncthreads();
         // ---- B5: gW1[d][c] += sum_r x[r][d] dz1[r][c];  gb1[c] += sum_r dz1[r][c] ------------------------
-        if (w1_live) mm_tn(sm + L.x + dq * 4, Dp, sm + L.h1 + c0, sm + L.h1 + c1, LDH, rsplit, nrows, nsplit, gW1);
+        if (w1_live) mm_tn(sm + xoff + dq * 4, Dp, sm + L.h1 + c0, sm + L.h1 + c1, LDH, rsplit, nrows, nsplit, gW1);
         if (tid < HC) {
             float s0 = 0.f, s1 = 0.f;
             int r = 0;
@@ -469,8 +514,9 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
             if (r < nrows) s0 += sm[L.h1 + r * LDH + tid];
             gb1 += s0 + s1;
         }
-        __syncthreads();
+        xb ^= 1;
     }
+    cp_async_wait_all();
 
     // ---- write the per-CTA partial gradient (flat checkpoint order, partial stride padded to 4 floats) -----------
     const int NPs = (o.NP + 3) & ~3;
@@ -628,7 +674,7 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const f
     a.kl_coeff = kl_coeff;
     if (hyper) a.hp = *hyper; else a.hp = ddrl_ppo_hyper{0.f, 0.f, 0.f, 0.f, 1.f};
     a.grad_part = grad_part; a.stat_part = stat_part;
-    const FcSmem L = fc_smem(D, A, false);
+    const FcSmem L = fc_smem(D, A, false, true);
     const size_t smem = (size_t)L.total * sizeof(float);
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step: shared memory %zu > 227 KB", smem);
     static bool attr_set = false;

@@ -20,10 +20,10 @@ constexpr int MAXHEAD = (H * (2 * DDRL_MAX_ACT + 1) + NT - 1) / NT;  // 5 head-g
 //   WhT [20][128]  : row q < 2A = [Wo[:, q] | 0], row 2A = [0 | Wvo], rest zero   (backward: dl . Wh^T)
 //   Wo [64][2A], bo, Wvo [64], bvo                                    (heads, forward)
 struct FcSmem {
-    int W1c, b1c, W2c, b2c, W2Tc, WhT, Wo, bo, Wvo, bvo, x, h1, h2, out, dl, red, norm, total;
+    int W1c, b1c, W2c, b2c, W2Tc, WhT, Wo, bo, Wvo, bvo, x, x2, pf, h1, h2, out, dl, red, norm, total;
 };
 
-__host__ __device__ inline FcSmem fc_smem(int D, int A, bool has_norm) {
+__host__ __device__ inline FcSmem fc_smem(int D, int A, bool has_norm, bool train = false) {
     const int Dp = (D + 3) & ~3;
     FcSmem s;
     int p = 0;
@@ -38,6 +38,8 @@ __host__ __device__ inline FcSmem fc_smem(int D, int A, bool has_norm) {
     s.Wvo = p;  p += H;
     s.bvo = p;  p += 4;
     s.x = p;    p += TM * Dp;
+    s.x2 = p;   p += train ? TM * Dp : 0;                 // second x buffer (cp.async double buffering)
+    s.pf = p;   p += train ? TM * (3 * A + 4) : 0;        // staged loss inputs: act[64][A] ol[64][2A] 4 x [64]
     s.h1 = p;   p += TM * LDH;
     s.h2 = p;   p += TM * LDH;
     s.out = p;  p += TM * LDD;
