@@ -315,7 +315,7 @@ def main():
                        "envs_per_gpu": envs, "envs_total": envs * world, "fragment_T": T, "rows_per_policy_per_gpu": R,
                        "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_minibatch_size_global": MB_local * world,
                        "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
-                       "cuda_graph": not args.no_graph and world == 1,
+                       "cuda_graph": bool(L.use_graph and L._graph is not None),
                        "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),

@@ -1,0 +1,111 @@
+// Minimal hand-written tcgen05 (UMMA) / TMEM / mbarrier layer for sm_100a — inline PTX only.
+//
+// Shared-memory operand convention used throughout this repo ("chunked", SWIZZLE_NONE canonical layout):
+// a 16-bit matrix X[rows][cols] is stored as 16-byte chunks of 8 consecutive cols, chunk-major:
+//     byte address(r, c) = ((c / 8) * rows + r) * 16 + (c % 8) * 2
+// so 8 consecutive rows of one chunk form one 128-byte UMMA core matrix.  The SAME buffer can be handed to the
+// tensor core in two ways (cute/atom/mma_traits_sm100.hpp, INTERLEAVE layouts):
+//   * K-major  (MN index = r, K index = c): LBO = rows*16 (next K chunk),  SBO = 128 (next 8 rows)
+//   * MN-major (MN index = c, K index = r): SBO = rows*16 (next MN chunk), LBO = 128 (next 8 K rows)
+// which is what lets the backward pass (dW = X^T dZ, reduction over rows) reuse the activations the forward pass
+// wrote, without a transposed copy.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace ddrl {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (64 bit) ------------------------------------------------------------
+// bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
+// [46,48) version = 1 (sm_100), [61,64) layout type (0 = no swizzle)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// chunked buffer with `rows` rows viewed K-major / MN-major (see header comment)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, int rows) { return smem_desc(saddr, rows * 16, 128); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, int rows) { return smem_desc(saddr, 128, rows * 16); }
+
+// ---- instruction descriptor (32 bit), kind::f16, fp16 inputs, fp32 accumulate ----------------------------------
+// [4,6) D format 1 = F32; [7,10) A format 0 = F16; [10,13) B format 0 = F16; bit 15 A major (1 = MN);
+// bit 16 B major; [17,23) N >> 3; [24,29) M >> 4
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- TMEM ---------------------------------------------------------------------------------------------------
+// one full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *smem_slot
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared stores -> visible to the async proxy (tensor core reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T : one thread issues
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+// ---- mbarrier -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// bounded wait: returns false if the phase did not complete within ~`spins` probes (never hangs the GPU)
+__device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity, uint32_t spins = 20000000u) {
+    const uint32_t a = smem_u32(mbar);
+    for (uint32_t i = 0; i < spins; ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// ---- TMEM -> registers: warp w reads lanes 32*(w%4).., 32 consecutive columns, one 32-bit value per lane/column ----
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- fp32 -> (hi, lo) fp16 split: x = hi + lo + O(2^-22 |x|) for |x| in the fp16 normal range ---------------------
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+}  // namespace umma
+}  // namespace ddrl

@@ -311,3 +311,14 @@ def dg_sample(logits: torch.Tensor, eps: torch.Tensor):
     _lib.check(_lib.load().ddrl_dg_sample(_p(logits, f32, "logits"), _p(eps, f32, "eps"), R, A, _p(action, f32, "action"),
                                           _p(logp, f32, "logp"), _stream()), "dg_sample")
     return action, logp
+
+
+def umma_selftest(A: torch.Tensor, B: torch.Tensor, N: int, Kdim: int, a_mn: bool, b_mn: bool, split: bool):
+    """Diagnostic tcgen05 GEMM (see ddrl_b200.h): returns (D [128,N] float32, status int)."""
+    D = torch.zeros(128, N, dtype=torch.float32, device=A.device)
+    status = torch.full((1,), -1, dtype=torch.int32, device=A.device)
+    _lib.check(_lib.load().ddrl_umma_selftest(_p(A, torch.float32, "A"), A.shape[0], A.shape[1], _p(B, torch.float32, "B"),
+                                              B.shape[0], B.shape[1], N, Kdim, int(a_mn), int(b_mn), int(split),
+                                              _p(D, torch.float32, "D"), _p(status, torch.int32, "status"), _stream()),
+               "umma_selftest")
+    return D, int(status.item())

@@ -225,19 +225,31 @@ class FCNetLearner(_LearnerBase):
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()
         hyper = self._hyper(MB * self.world)
-        if self.use_graph and self.world == 1:
+        ran = False
+        if self.use_graph:
             key = (T, Cc, steps, G, MB, src_key)
             if self._graph is None or self._graph_key != key:
                 torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                # the capture itself executes nothing; kernels read step_ctr / mb_perm / kl_coeff from device memory
-                with torch.cuda.graph(g):
-                    for _ in range(nb):
-                        self._sgd_step(b, MB, G, hyper, src)
-                self._graph, self._graph_key, self._graph_hyper = g, key, hyper
-            for _ in range(E):
-                self._graph.replay()
-        else:
+                if self.world > 1:
+                    self.dist.barrier()
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    # the capture executes nothing; kernels read step_ctr / mb_perm / kl_coeff from device memory, so
+                    # one captured epoch (nb steps incl. the NCCL all-reduce at N>1) serves every epoch and iteration
+                    with torch.cuda.graph(g):
+                        for _ in range(nb):
+                            self._sgd_step(b, MB, G, hyper, src)
+                    self._graph, self._graph_key = g, key
+                except Exception as exc:  # capture not possible (e.g. NCCL build without graph support): run eagerly
+                    self._graph, self.use_graph = None, False
+                    self.graph_error = repr(exc)
+                    torch.cuda.synchronize()
+                    self.step_ctr.zero_()
+            if self._graph is not None:
+                for _ in range(E):
+                    self._graph.replay()
+                ran = True
+        if not ran:
             for _ in range(steps):
                 self._sgd_step(b, MB, G, hyper, src)
         # (iv) stats + KL update ----------------------------------------------------------------------------

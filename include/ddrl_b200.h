@@ -219,6 +219,13 @@ int ddrl_dg_sample(const float* logits, const float* eps, int64_t R, int A, floa
 int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupling, int64_t B,
                       int W, void* stream);
 
+/* Diagnostic: one tcgen05 (UMMA) GEMM through TMEM with the chunked shared-memory operand layout the tensor-core
+ * training step uses (csrc/umma.cuh): D[128][N] = sum_k A(m,k) B(n,k), A(m,k) = A[m][k] (a_mn = 0, K-major) or
+ * A[k][m] (a_mn = 1, MN-major view); B alike; split != 0 -> fp16 (hi, lo) operand split with three products.
+ * A [ra][ca], B [rb][cb], D [128][N] float32 device arrays; *status (device int) = 0 ok, 1 = MMA completion timed out. */
+int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B, int rb, int cb, int N, int K, int a_mn,
+                       int b_mn, int split, float* D, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

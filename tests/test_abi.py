@@ -21,7 +21,8 @@ def test_header_declares_the_expected_surface():
     for must in ("ddrl_fcnet_forward", "ddrl_ppo_train_step", "ddrl_grad_reduce", "ddrl_clip_adam", "ddrl_filter_update",
                  "ddrl_filter_partial", "ddrl_filter_merge", "ddrl_gae", "ddrl_adv_standardize", "ddrl_gather_rows",
                  "ddrl_ppo_loss_grad", "ddrl_graphnet_forward", "ddrl_graphnet_backward", "ddrl_gcn_forward",
-                 "ddrl_leg_coupling", "ddrl_dg_sample", "ddrl_last_error", "ddrl_launch_count"):
+                 "ddrl_leg_coupling", "ddrl_dg_sample", "ddrl_last_error", "ddrl_launch_count", "ddrl_fcnet_pack",
+                 "ddrl_fcnet_image_floats", "ddrl_umma_selftest"):
         assert must in syms
 
 
@@ -64,10 +65,10 @@ def test_pure_host_entry_points():
 def test_bad_arguments_return_error_codes_without_touching_a_gpu():
     from ddrl_b200 import _lib
     lib = _lib.load()
-    assert lib.ddrl_fcnet_forward(None, None, None, 0.0, 1, 1, 19, 2, None, None, None, None, None, None, None) == -1
+    assert lib.ddrl_fcnet_forward(None, None, None, None, 0.0, 1, 1, 19, 2, None, None, None, None, None, None, None) == -1
     assert b"fcnet_forward" in lib.ddrl_last_error()
     assert lib.ddrl_gae(None, None, None, None, 1, 1, 1, 1, 0.99, 0.95, None, None, None, None, None) == -1
-    assert lib.ddrl_clip_adam(None, None, None, None, None, 1, 1, 0.0, 0.0, 0.0, 0.0, 0.0, None, None, None, None) == -1
+    assert lib.ddrl_clip_adam(None, None, None, None, None, 1, 1, 0.0, 0.0, 0.0, 0.0, 0.0, None, None, None, None, 0, 0, None) == -1
 
 
 def test_product_code_never_imports_the_oracle():
