@@ -11,7 +11,7 @@ namespace ddrl {
 // kind of buffer); B alike.  split != 0: every operand is split into fp16 (hi, lo) and three products
 // hi*hi + hi*lo + lo*hi are accumulated in FP32 (the precision scheme of the tensor-core training step).
 __global__ void __launch_bounds__(128, 1)
-umma_selftest_kernel(const float* __restrict__ A, int ra, int ca, const float* __restrict__ B, int rb, int cb, int N,
+umma_selftest_kernel(const float* __restrict__ A, int ra, int ca, const float* __restrict__ B, int rb, int cb, int M, int N,
                      int K, int a_mn, int b_mn, int split, float* __restrict__ D, int* __restrict__ status) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ uint32_t tmem_slot;
@@ -44,7 +44,7 @@ umma_selftest_kernel(const float* __restrict__ A, int ra, int ca, const float* _
     umma::fence_after_sync();
     const uint32_t taddr = tmem_slot;
     if (tid == 0) {
-        const uint32_t idesc = umma::idesc_f16(128, N, a_mn != 0, b_mn != 0);
+        const uint32_t idesc = umma::idesc_f16(M, N, a_mn != 0, b_mn != 0);
         const int nprod = split ? 3 : 1;
         bool acc = false;
         for (int pr = 0; pr < nprod; ++pr) {
@@ -85,13 +85,14 @@ umma_selftest_kernel(const float* __restrict__ A, int ra, int ca, const float* _
 
 using namespace ddrl;
 
-extern "C" int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B, int rb, int cb, int N, int K, int a_mn,
-                                  int b_mn, int split, float* D, int* status, void* stream) {
+extern "C" int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B, int rb, int cb, int M, int N, int K,
+                                  int a_mn, int b_mn, int split, float* D, int* status, void* stream) {
     DDRL_REQUIRE(A && B && D && status, DDRL_E_BADARG, "umma_selftest: null pointer");
     DDRL_REQUIRE(ra % 8 == 0 && rb % 8 == 0 && ca % 8 == 0 && cb % 8 == 0 && K % 16 == 0 && N % 16 == 0 && N >= 16 && N <= 256,
                  DDRL_E_UNSUPPORTED_SHAPE, "umma_selftest: shapes must be multiples of 8 (rows/cols), 16 (K, N)");
-    DDRL_REQUIRE((a_mn ? (ca == 128 && ra >= K) : (ra == 128 && ca >= K)) && (b_mn ? (cb >= N && rb >= K) : (rb >= N && cb >= K)),
-                 DDRL_E_UNSUPPORTED_SHAPE, "umma_selftest: buffer shapes do not cover M=128 x N x K");
+    DDRL_REQUIRE(M == 64 || M == 128, DDRL_E_UNSUPPORTED_SHAPE, "umma_selftest: M must be 64 or 128");
+    DDRL_REQUIRE((a_mn ? (ca >= M && ra >= K) : (ra >= M && ca >= K)) && (b_mn ? (cb >= N && rb >= K) : (rb >= N && cb >= K)),
+                 DDRL_E_UNSUPPORTED_SHAPE, "umma_selftest: buffer shapes do not cover M x N x K");
     const size_t smem = (size_t)(ra * ca + rb * cb) * 2 * sizeof(__half) + 128;
     DDRL_REQUIRE(smem <= 200 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "umma_selftest: %zu bytes of shared memory", smem);
     static bool attr = false;
@@ -102,7 +103,535 @@ extern "C" int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B
         }
         attr = true;
     }
-    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, ra, ca, B, rb, cb, N, K, a_mn, b_mn, split, D, status);
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, ra, ca, B, rb, cb, M, N, K, a_mn, b_mn, split, D, status);
     DDRL_CHECK_LAUNCH("umma_selftest");
+    return DDRL_OK;
+}
+
+// =================================================================================================================
+// Tensor-core FCNet training step: same contract as fcnet_train_kernel (csrc/fcnet.cu) — one minibatch of all
+// policies, fused forward + PPO loss + backward, per-CTA partial gradients in flat checkpoint order — with every
+// GEMM on tcgen05 (kind::f16, FP32 accumulation in TMEM).  FP32 operands are split into fp16 (hi, lo) pairs and
+// three products hi*hi + hi*lo + lo*hi are accumulated, which restores ~2^-21 relative accuracy (umma self test),
+// i.e. the 1e-5 parity bar still holds.
+//
+//   * tile = 128 rows (UMMA M); thread = (row, 32-column half) of a 64-wide branch tile, so the TMEM load
+//     (tcgen05.ld 32x32b.x32) hands each thread exactly its accumulators.
+//   * the value and policy branches are processed one after the other (the PPO loss separates into a policy part
+//     and a value part), which halves the activation footprint: H1, H2 are [128][64] fp16 hi/lo in the chunked layout.
+//   * the SAME activation buffers feed the forward chain (K-major view) and the weight-gradient GEMMs (MN-major
+//     view: M = feature, K = row), so the backward needs no transposed copies; weight gradients accumulate in TMEM
+//     (M = 64 accumulators) across all tiles of the CTA.
+//   * bias gradients ride along: X carries a constant-1 pad column, so dW1 gains a row = sum_r dz1 and a 16-wide
+//     MMA against that column gives sum_r dz2.
+//   * loss gradients are kept unscaled (no 1/minibatch) on chip so they stay inside the fp16 range; the scale is
+//     applied when the accumulators are written out.
+// =================================================================================================================
+#include "fcnet_tc_layout.cuh"
+#include "ppo_loss.cuh"
+
+namespace ddrl {
+
+struct TcTrainArgs {
+    const unsigned char* img;
+    const float *obs, *actions, *old_logits, *old_logp, *vf_preds, *adv, *vtarg;
+    int64_t R;
+    int D, A, MB;
+    const int32_t* mb_perm;
+    int64_t perm_stride;
+    const int32_t* step_ctr;
+    const float* kl_coeff;
+    ddrl_ppo_hyper hp;
+    float* grad_part;
+    double* stat_part;
+    int* status;
+};
+
+constexpr int TC_DACC = 0, TC_GW2 = 64, TC_GW1 = 192, TC_GB2 = 320, TC_GWH = 352, TC_TMEM_COLS = 512;
+// Power-of-two operand scales: the lo half of the split is ~2^-11 of the value, so unscaled activations / gradients
+// (|x| < 0.1) would put it into the fp16 subnormal range and lose the bits the split is there to keep.  Every buffer
+// is stored pre-multiplied by its scale (exact) and every accumulator read back is multiplied by the inverse product.
+// What matters is the ABSOLUTE error relative to the tensor's scale: entries too small for a normal lo half lose at
+// most 2^-25/scale, which is negligible next to the large entries that dominate every sum.  Overflow (|x*scale| >
+// 60000) is clamped and reported through *status = 2 so the caller can redo the step on the FP32 kernel.
+constexpr float TC_SX = 16.f;      // observations (|x| <= 3750)
+constexpr float TC_SH = 4096.f;    // tanh activations (|h| <= 1)
+constexpr float TC_SW = 256.f;     // weights (|w| <= 234)
+constexpr float TC_SL = 1.f;       // head gradients dl (typically 0.1 .. 30, ratio outliers to 1e4)
+constexpr float TC_SD = 8.f;       // hidden-layer gradients dz2, dz1 (|dz| <= 7500)
+
+__device__ __forceinline__ void tc_cp16(unsigned char* smem_dst, const unsigned char* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void tc_cp4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc));
+}
+
+// D[tmem] (+)= A * B^T with fp16 (hi, lo) operands: products (hi,hi) (hi,lo) (lo,hi); nprod == 2 -> (hi,hi) (lo,hi).
+// a_rows / b_rows = row count of the chunked buffers; *_mn selects the MN-major view.  One thread calls this.
+__device__ __forceinline__ void tc_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
+                                        uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate,
+                                        int nprod) {
+    const uint32_t idesc = umma::idesc_f16(M, N, a_mn, b_mn);
+    const uint32_t astep = a_mn ? 256u : (uint32_t)(2 * a_rows * 16);
+    const uint32_t bstep = b_mn ? 256u : (uint32_t)(2 * b_rows * 16);
+    bool acc = accumulate;
+    for (int pr = 0; pr < nprod; ++pr) {
+        const uint32_t pa = (pr == 2 || (nprod == 2 && pr == 1)) ? a_lo : a_hi;
+        const uint32_t pb = (nprod == 3 && pr == 1) ? b_lo : b_hi;
+        for (int ks = 0; ks < nk; ++ks) {
+            const uint64_t ad = a_mn ? umma::desc_mnmajor(pa + ks * astep, a_rows) : umma::desc_kmajor(pa + ks * astep, a_rows);
+            const uint64_t bd = b_mn ? umma::desc_mnmajor(pb + ks * bstep, b_rows) : umma::desc_kmajor(pb + ks * bstep, b_rows);
+            umma::mma_f16(d_tmem, ad, bd, idesc, acc);
+            acc = true;
+        }
+    }
+}
+
+__device__ __forceinline__ float tc_clamp_h(float x, bool& ovf) {
+    ovf = ovf || !(fabsf(x) <= 60000.f);
+    return fminf(fmaxf(x, -60000.f), 60000.f);
+}
+
+// split 8 floats (times a power-of-two scale) into fp16 hi / lo 16-byte chunks
+__device__ __forceinline__ void tc_split8(const float* v, float scale, uint4& hi, uint4& lo, bool& ovf) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x0 = tc_clamp_h(v[2 * i] * scale, ovf), x1 = tc_clamp_h(v[2 * i + 1] * scale, ovf);
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        h[i] = __halves2half2(h0, h1);
+        l[i] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+    }
+    hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                    *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+    lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                    *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+}
+
+// thread's 32 values (columns 32*hf .. +31 of row `row`) -> chunked [128][64] hi / lo buffers
+__device__ __forceinline__ void tc_store_rowhalf(unsigned char* bhi, unsigned char* blo, int row, int hf, const float (&v)[32],
+                                                 float scale, bool& ovf) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 hi, lo;
+        tc_split8(&v[8 * c], scale, hi, lo, ovf);
+        const int off = ((4 * hf + c) * TC_ROWS + row) * 16;
+        *reinterpret_cast<uint4*>(bhi + off) = hi;
+        *reinterpret_cast<uint4*>(blo + off) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainArgs a) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
+    const int D = a.D, A = a.A, A2 = 2 * A, KX = tc_kx(D), LDo = A2 + 1;
+    const TcImg I = tc_img(D, A);
+    const TcSmem S = tc_smem(D, A);
+    const FcOffsets o = fc_offsets(D, A);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S.bar);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + S.bar + 8);
+    const uint32_t sbase = umma::smem_u32(sm);
+
+    const int step = a.step_ctr ? *a.step_ctr : 0;
+    const int mb = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step] : step;
+    const int64_t mb0 = (int64_t)mb * a.MB;
+    const int64_t mb1 = min(mb0 + a.MB, a.R);
+    const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
+    const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
+    const int NPs = (o.NP + 3) & ~3;
+    float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    if (cr1 <= cr0) {   // no rows: zero partial, no tensor work
+        for (int i = tid; i < o.NP; i += TC_NT) gp[i] = 0.f;
+        if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
+        return;
+    }
+
+    const float* obs_p = a.obs + (int64_t)p * a.R * D;
+    float* xraw = reinterpret_cast<float*>(sm + S.xraw);
+    float* pf = reinterpret_cast<float*>(sm + S.pf);
+    float* hpart = reinterpret_cast<float*>(sm + S.hpart);
+    float* dlf = reinterpret_cast<float*>(sm + S.dlf);
+    const float* b1c = reinterpret_cast<const float*>(sm + I.b1c);
+    const float* b2c = reinterpret_cast<const float*>(sm + I.b2c);
+    const float* sWo = reinterpret_cast<const float*>(sm + I.Wo);
+    const float* sbo = reinterpret_cast<const float*>(sm + I.bo);
+    const float* sWvo = reinterpret_cast<const float*>(sm + I.Wvo);
+    const float* sbvo = reinterpret_cast<const float*>(sm + I.bvo);
+
+    auto prefetch_x = [&](int64_t r0, int n) {
+        for (int i = tid; i < n * D; i += TC_NT) tc_cp4(xraw + i, obs_p + r0 * D + i);
+    };
+    auto prefetch_loss = [&](int64_t r0, int n) {
+        const int64_t g0 = (int64_t)p * a.R + r0;
+        float* pa = pf;
+        float* po = pa + TC_ROWS * A;
+        float* ps = po + TC_ROWS * A2;
+        for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, a.actions + g0 * A + i);
+        for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+        for (int i = tid; i < n; i += TC_NT) {
+            tc_cp4(ps + i, a.old_logp + g0 + i);
+            tc_cp4(ps + TC_ROWS + i, a.vf_preds + g0 + i);
+            tc_cp4(ps + 2 * TC_ROWS + i, a.adv + g0 + i);
+            tc_cp4(ps + 3 * TC_ROWS + i, a.vtarg + g0 + i);
+        }
+    };
+
+    // ---- setup: TMEM, mbarrier, weights image, first tile's inputs ------------------------------------------------
+    if (warp == 0) umma::tmem_alloc(tslot, TC_TMEM_COLS);
+    if (tid == 0) { umma::mbar_init(mbar, 1); umma::fence_mbar_init(); }
+    {
+        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+        const int n0 = (int)min((int64_t)TC_ROWS, cr1 - cr0);
+        prefetch_x(cr0, n0);
+        prefetch_loss(cr0, n0);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    uint32_t phase = 0;
+    bool ok = true;
+    bool first = true;
+    bool ovf = false;
+    const float klc = a.kl_coeff[p];
+    double st[DDRL_NSTAT];
+#pragma unroll
+    for (int i = 0; i < DDRL_NSTAT; ++i) st[i] = 0.0;
+    float gbh[2 * DDRL_MAX_ACT + 1];   // head bias gradients (loss threads): sum_r dl[r][o]
+#pragma unroll
+    for (int i = 0; i < 2 * DDRL_MAX_ACT + 1; ++i) gbh[i] = 0.f;
+    const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
+
+    auto wait_mma = [&]() {
+        ok = umma::mbar_wait(mbar, phase) && ok;
+        phase ^= 1;
+        umma::fence_after_sync();
+    };
+    auto publish = [&]() {   // generic smem writes -> async proxy, TMEM reads retired, then CTA barrier
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
+
+    for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
+        const int nrows = (int)min((int64_t)TC_ROWS, cr1 - row0);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        // ---- x: fp32 staging -> fp16 hi/lo chunked [128][KX], constant 1 in column D, zero rows beyond nrows ----------
+        {
+            const int r = tid & (TC_ROWS - 1);
+            for (int c8 = tid >> 7; c8 < (KX >> 3); c8 += 2) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int d = c8 * 8 + e;
+                    v[e] = (r < nrows) ? (d < D ? xraw[r * D + d] : (d == D ? 1.f : 0.f)) : 0.f;
+                }
+                uint4 hi, lo;
+                tc_split8(v, TC_SX, hi, lo, ovf);
+                *reinterpret_cast<uint4*>(sm + S.X[0] + (c8 * TC_ROWS + r) * 16) = hi;
+                *reinterpret_cast<uint4*>(sm + S.X[1] + (c8 * TC_ROWS + r) * 16) = lo;
+            }
+        }
+        publish();
+        {   // staging buffer is free again: stream in the next tile's observations behind this tile's compute
+            const int64_t nxt = row0 + TC_ROWS;
+            if (nxt < cr1) prefetch_x(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+
+        for (int bi = 0; bi < 2; ++bi) {
+            const int b = 1 - bi;                      // value branch first, then policy
+            const int nout = b == 0 ? A2 : 1;
+            float h1[32], h2[32], v[32];
+            // ---- F1: Dacc = X * W1b^T ------------------------------------------------------------------------
+            if (tid == 0) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + TC_DACC, sbase + S.X[0], sbase + S.X[1], TC_ROWS, false, sbase + I.W1[b][0],
+                        sbase + I.W1[b][1], 64, false, 128, 64, KX >> 4, false, 3);
+                umma::mma_commit(mbar);
+            }
+            wait_mma();
+            umma::tmem_ld32(tmem + tlane + TC_DACC + 32 * hf, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h1[j] = tanhf(v[j] * (1.f / (TC_SX * TC_SW)) + b1c[b * 64 + 32 * hf + j]);
+            tc_store_rowhalf(sm + S.H1[0], sm + S.H1[1], row, hf, h1, TC_SH, ovf);
+            publish();
+            // ---- F2: Dacc = H1 * W2b ---------------------------------------------------------------------------
+            if (tid == 0) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + TC_DACC, sbase + S.H1[0], sbase + S.H1[1], TC_ROWS, false, sbase + I.W2[b][0],
+                        sbase + I.W2[b][1], 64, true, 128, 64, 4, false, 3);
+                umma::mma_commit(mbar);
+            }
+            wait_mma();
+            umma::tmem_ld32(tmem + tlane + TC_DACC + 32 * hf, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h2[j] = tanhf(v[j] * (1.f / (TC_SH * TC_SW)) + b2c[b * 64 + 32 * hf + j]);
+            tc_store_rowhalf(sm + S.H2[0], sm + S.H2[1], row, hf, h2, TC_SH, ovf);
+            // head partial sums over this thread's 32 hidden units
+            float part[2 * DDRL_MAX_ACT];
+#pragma unroll
+            for (int oo = 0; oo < 2 * DDRL_MAX_ACT; ++oo) {
+                part[oo] = 0.f;
+                if (oo < nout) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const int k = 32 * hf + j;
+                        s0 = fmaf(h2[j], b == 0 ? sWo[k * A2 + oo] : sWvo[k], s0);
+                        s1 = fmaf(h2[j + 1], b == 0 ? sWo[(k + 1) * A2 + oo] : sWvo[k + 1], s1);
+                    }
+                    part[oo] = s0 + s1;
+                    if (hf == 1) hpart[row * LDo + oo] = part[oo];
+                }
+            }
+            publish();
+            // ---- loss of this branch (one thread per row) -> dlf (fp32) and DL (fp16 hi/lo, chunked [128][16]) --------
+            if (hf == 0) {
+                float dl[2 * DDRL_MAX_ACT];
+                double s[DDRL_NSTAT];
+#pragma unroll
+                for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i) dl[i] = 0.f;
+                if (row < nrows) {
+                    const float* pa = pf;
+                    const float* po = pa + TC_ROWS * A;
+                    const float* ps = po + TC_ROWS * A2;
+                    if (b == 0) {
+                        float out[2 * DDRL_MAX_ACT];
+#pragma unroll
+                        for (int oo = 0; oo < 2 * DDRL_MAX_ACT; ++oo)
+                            if (oo < A2) out[oo] = part[oo] + hpart[row * LDo + oo] + sbo[oo];
+                        ppo_row_policy(out, A, pa + row * A, po + row * A2, ps[row], ps[2 * TC_ROWS + row], klc,
+                                       a.hp.clip_param, a.hp.entropy_coeff, 1.f, dl, s);
+                    } else {
+                        const float val = part[0] + hpart[row * LDo] + sbvo[0];
+                        dl[0] = ppo_row_value(val, ps[TC_ROWS + row], ps[3 * TC_ROWS + row], a.hp.vf_clip_param,
+                                              a.hp.vf_loss_coeff, 1.f, s);
+                    }
+                }
+                float dv16[16];
+#pragma unroll
+                for (int oo = 0; oo < 16; ++oo) {
+                    dv16[oo] = (oo < nout && oo < 2 * DDRL_MAX_ACT) ? dl[oo] : 0.f;
+                    if (oo < nout) {
+                        dlf[row * LDo + oo] = dv16[oo];
+                        gbh[b == 0 ? oo : A2] += dv16[oo];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint4 hi, lo;
+                    tc_split8(&dv16[8 * c], TC_SL, hi, lo, ovf);
+                    *reinterpret_cast<uint4*>(sm + S.DL[0] + (c * TC_ROWS + row) * 16) = hi;
+                    *reinterpret_cast<uint4*>(sm + S.DL[1] + (c * TC_ROWS + row) * 16) = lo;
+                }
+#pragma unroll
+                for (int i = 0; i < DDRL_NSTAT; ++i) st[i] += s[i];
+            }
+            publish();
+            // ---- B1 (async): gWh_b[k][o] (+)= H2^T * DL ------------------------------------------------------------
+            if (tid == 0) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + TC_GWH + 16 * b, sbase + S.H2[0], sbase + S.H2[1], TC_ROWS, true, sbase + S.DL[0],
+                        sbase + S.DL[1], TC_ROWS, true, 64, 16, 8, !first, 3);
+                umma::mma_commit(mbar);
+            }
+            // dz2 = (dl . Wh^T) * (1 - h2^2) in registers while B1 runs
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int k = 32 * hf + j;
+                float s = 0.f;
+                if (b == 0) {
+                    for (int oo = 0; oo < A2; ++oo) s = fmaf(dlf[row * LDo + oo], sWo[k * A2 + oo], s);
+                } else {
+                    s = dlf[row * LDo] * sWvo[k];
+                }
+                h2[j] = s * (1.f - h2[j] * h2[j]);
+            }
+            wait_mma();                                  // B1 has consumed H2: overwrite it with dz2
+            tc_store_rowhalf(sm + S.H2[0], sm + S.H2[1], row, hf, h2, TC_SD, ovf);
+            publish();
+            // ---- B3: gW2_b (+)= H1^T dZ2;  gb2_b (+)= dZ2^T 1;  B4: Dacc = dZ2 * W2b^T -------------------------------
+            if (tid == 0) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + TC_GW2 + 64 * b, sbase + S.H1[0], sbase + S.H1[1], TC_ROWS, true, sbase + S.H2[0],
+                        sbase + S.H2[1], TC_ROWS, true, 64, 64, 8, !first, 3);
+                tc_gemm(tmem + TC_GB2 + 16 * b, sbase + S.H2[0], sbase + S.H2[1], TC_ROWS, true,
+                        sbase + S.X[0] + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64, 16, 8, !first, 2);
+                tc_gemm(tmem + TC_DACC, sbase + S.H2[0], sbase + S.H2[1], TC_ROWS, false, sbase + I.W2[b][0],
+                        sbase + I.W2[b][1], 64, false, 128, 64, 4, false, 3);
+                umma::mma_commit(mbar);
+            }
+            wait_mma();
+            umma::tmem_ld32(tmem + tlane + TC_DACC + 32 * hf, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h1[j] = v[j] * (1.f / (TC_SD * TC_SW)) * (1.f - h1[j] * h1[j]);     // dz1
+            tc_store_rowhalf(sm + S.H1[0], sm + S.H1[1], row, hf, h1, TC_SD, ovf);
+            publish();
+            // ---- B5: gW1_b[c][d] (+)= dZ1^T X   (column D of X is the constant 1 -> bias gradient) ------------------
+            if (tid == 0) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + TC_GW1 + 64 * b, sbase + S.H1[0], sbase + S.H1[1], TC_ROWS, true, sbase + S.X[0],
+                        sbase + S.X[1], TC_ROWS, true, 64, KX, 8, !first, 3);
+                umma::mma_commit(mbar);
+            }
+            wait_mma();
+        }
+        {   // both branches consumed the staged loss inputs: fetch the next tile's
+            const int64_t nxt = row0 + TC_ROWS;
+            if (nxt < cr1) prefetch_loss(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+        first = false;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+    // ---- write-out: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
+    const float inv = a.hp.inv_global_mb;
+    const float inv_gw2 = inv / (TC_SH * TC_SD), inv_gw1 = inv / (TC_SD * TC_SX), inv_gwh = inv / (TC_SH * TC_SL);
+    const int m = 16 * q + lane;            // valid for lane < 16
+    const bool mine = lane < 16;
+    for (int b = 0; b < 2; ++b) {
+        float v[32];
+        umma::tmem_ld32(tmem + tlane + TC_GW2 + 64 * b + 32 * hf, v);
+        if (mine) {
+            float* dst = gp + (b ? o.Wv2 : o.W2) + m * 64 + 32 * hf;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j] = v[j] * inv_gw2;
+        }
+        if (32 * hf < KX) {
+            umma::tmem_ld32(tmem + tlane + TC_GW1 + 64 * b + 32 * hf, v);
+            if (mine) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int d = 32 * hf + j;
+                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = v[j] * inv_gw1;
+                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = v[j] * inv_gw1;
+                }
+            }
+        }
+        if (hf == 0) {
+            umma::tmem_ld32(tmem + tlane + TC_GB2 + 16 * b, v);
+            if (mine) gp[(b ? o.bv2 : o.b2) + m] = v[D - 8 * ch0] * inv_gw1;
+            umma::tmem_ld32(tmem + tlane + TC_GWH + 16 * b, v);
+            if (mine) {
+                if (b == 0) {
+#pragma unroll
+                    for (int oo = 0; oo < 2 * DDRL_MAX_ACT; ++oo)
+                        if (oo < A2) gp[o.Wo + m * A2 + oo] = v[oo] * inv_gwh;
+                } else {
+                    gp[o.Wvo + m] = v[0] * inv_gwh;
+                }
+            }
+        }
+    }
+    // head bias gradients and stats: reduce over the 128 loss threads (warps 0..3), fixed order
+    __syncthreads();
+    float* redf = reinterpret_cast<float*>(sm + S.hpart);          // [4 warps][17]
+    double* redd = reinterpret_cast<double*>(sm + S.red);          // [4 warps][8]
+    if (hf == 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * DDRL_MAX_ACT + 1; ++i) {
+            const float s = warp_sum(gbh[i]);
+            if (lane == 0) redf[warp * 17 + i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < DDRL_NSTAT; ++i) {
+            const double s = warp_sum(st[i]);
+            if (lane == 0) redd[warp * DDRL_NSTAT + i] = s;
+        }
+    }
+    __syncthreads();
+    if (tid <= A2) {
+        const float s = ((redf[tid] + redf[17 + tid]) + (redf[34 + tid] + redf[51 + tid])) * inv;
+        gp[tid == A2 ? o.bvo : o.bo + tid] = s;
+    }
+    if (tid < DDRL_NSTAT && a.stat_part)
+        a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] =
+            (redd[tid] + redd[DDRL_NSTAT + tid]) + (redd[2 * DDRL_NSTAT + tid] + redd[3 * DDRL_NSTAT + tid]);
+    if (a.status) {
+        if (tid == 0 && !ok) *a.status = 1;
+        else if (ovf) atomicMax(a.status, 2);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, TC_TMEM_COLS);
+}
+
+// flat theta -> tensor-core image (fp16 hi/lo weights + fp32 biases / heads)
+__global__ void fcnet_tc_pack_kernel(const float* __restrict__ theta, int D, int A, unsigned char* __restrict__ img) {
+    const int p = blockIdx.y;
+    const TcImg L = tc_img(D, A);
+    const FcOffsets o = fc_offsets(D, A);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= o.NP) return;
+    bool f16;
+    int p0, p1;
+    tc_img_pos(L, o, D, A, j, f16, p0, p1);
+    const float w = theta[(int64_t)p * o.NP + j];
+    unsigned char* im = img + (int64_t)p * L.bytes;
+    if (f16) {
+        __half hi, lo;
+        umma::split_f16(w * TC_SW, hi, lo);
+        *reinterpret_cast<__half*>(im + p0) = hi;
+        *reinterpret_cast<__half*>(im + p1) = lo;
+    } else {
+        *reinterpret_cast<float*>(im + p0) = w;
+    }
+}
+
+}  // namespace ddrl
+
+extern "C" int ddrl_fcnet_tc_image_bytes(int D, int A) {
+    if (D < 1 || D > DDRL_MAX_OBS - 1 || A < 1 || A > DDRL_MAX_ACT) return DDRL_E_UNSUPPORTED_SHAPE;
+    return tc_img(D, A).bytes;
+}
+
+extern "C" int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* img, void* stream) {
+    DDRL_REQUIRE(theta && img && P >= 1, DDRL_E_BADARG, "fcnet_tc_pack: null pointer or bad P");
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS - 1 && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
+                 "fcnet_tc_pack: unsupported D=%d A=%d", D, A);
+    const int NP = fc_offsets(D, A).NP;
+    cudaMemsetAsync(img, 0, (size_t)P * tc_img(D, A).bytes, (cudaStream_t)stream);
+    fcnet_tc_pack_kernel<<<dim3((NP + 255) / 256, P), 256, 0, (cudaStream_t)stream>>>(theta, D, A, (unsigned char*)img);
+    DDRL_CHECK_LAUNCH("fcnet_tc_pack");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, const float* actions, const float* old_logits,
+                                      const float* old_logp, const float* vf_preds, const float* adv, const float* vtarg,
+                                      int P, int64_t R, int D, int A, int MB, const int32_t* mb_perm, int64_t perm_stride,
+                                      const int32_t* step_ctr, const float* kl_coeff, const ddrl_ppo_hyper* hyper,
+                                      int ctas_per_policy, float* grad_part, double* stat_part, int* status, void* stream) {
+    DDRL_REQUIRE(tc_img_p && obs && actions && old_logits && old_logp && vf_preds && adv && vtarg && kl_coeff && hyper &&
+                     grad_part && P >= 1 && R >= 1 && MB >= 1 && ctas_per_policy >= 1,
+                 DDRL_E_BADARG, "ppo_train_step_tc: null pointer or bad P/R/MB/ctas");
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS - 1 && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
+                 "ppo_train_step_tc: unsupported D=%d A=%d", D, A);
+    TcTrainArgs a;
+    a.img = (const unsigned char*)tc_img_p; a.obs = obs; a.actions = actions; a.old_logits = old_logits;
+    a.old_logp = old_logp; a.vf_preds = vf_preds; a.adv = adv; a.vtarg = vtarg; a.R = R; a.D = D; a.A = A; a.MB = MB;
+    a.mb_perm = mb_perm; a.perm_stride = perm_stride; a.step_ctr = step_ctr; a.kl_coeff = kl_coeff; a.hp = *hyper;
+    a.grad_part = grad_part; a.stat_part = stat_part; a.status = status;
+    const size_t smem = (size_t)tc_smem(D, A).total;
+    DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(fcnet_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+            return DDRL_E_CUDA;
+        }
+        attr = true;
+    }
+    fcnet_train_tc_kernel<<<dim3(ctas_per_policy, P), TC_NT, smem, (cudaStream_t)stream>>>(a);
+    DDRL_CHECK_LAUNCH("ppo_train_step_tc");
     return DDRL_OK;
 }

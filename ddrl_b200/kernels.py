@@ -313,12 +313,40 @@ def dg_sample(logits: torch.Tensor, eps: torch.Tensor):
     return action, logp
 
 
-def umma_selftest(A: torch.Tensor, B: torch.Tensor, N: int, Kdim: int, a_mn: bool, b_mn: bool, split: bool):
-    """Diagnostic tcgen05 GEMM (see ddrl_b200.h): returns (D [128,N] float32, status int)."""
+def umma_selftest(A: torch.Tensor, B: torch.Tensor, N: int, Kdim: int, a_mn: bool, b_mn: bool, split: bool, M: int = 128):
+    """Diagnostic tcgen05 GEMM (see ddrl_b200.h): returns (D [128,N] float32 = raw TMEM lanes, status int)."""
     D = torch.zeros(128, N, dtype=torch.float32, device=A.device)
     status = torch.full((1,), -1, dtype=torch.int32, device=A.device)
     _lib.check(_lib.load().ddrl_umma_selftest(_p(A, torch.float32, "A"), A.shape[0], A.shape[1], _p(B, torch.float32, "B"),
-                                              B.shape[0], B.shape[1], N, Kdim, int(a_mn), int(b_mn), int(split),
+                                              B.shape[0], B.shape[1], M, N, Kdim, int(a_mn), int(b_mn), int(split),
                                               _p(D, torch.float32, "D"), _p(status, torch.int32, "status"), _stream()),
                "umma_selftest")
     return D, int(status.item())
+
+
+def fcnet_tc_pack(theta: torch.Tensor, D: int, A: int, img: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """theta [P,NP] -> tensor-core weight image [P, tc_image_bytes] uint8 (fp16 hi/lo weights + fp32 biases/heads)."""
+    lib = _lib.load()
+    P = theta.shape[0]
+    nbytes = lib.ddrl_fcnet_tc_image_bytes(D, A)
+    if nbytes < 0:
+        raise DDRLError(f"tensor-core path does not support D={D} A={A}")
+    if img is None:
+        img = torch.empty(P, nbytes, dtype=torch.uint8, device=theta.device)
+    _lib.check(lib.ddrl_fcnet_tc_pack(_p(theta, torch.float32, "theta"), P, D, A, _p(img, torch.uint8, "tc_img"), _stream()),
+               "fcnet_tc_pack")
+    return img
+
+
+def ppo_train_step_tc(tc_img, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int, mb_perm, step_ctr,
+                      kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part, status=None):
+    P, R, D = obs.shape
+    f32 = torch.float32
+    perm_stride = mb_perm.shape[-1] if mb_perm is not None else 0
+    _lib.check(_lib.load().ddrl_ppo_train_step_tc(
+        _p(tc_img, torch.uint8, "tc_img"), _p(obs, f32, "obs"), _p(actions, f32, "actions"),
+        _p(old_logits, f32, "old_logits"), _p(old_logp, f32, "old_logp"), _p(vf_preds, f32, "vf_preds"), _p(adv, f32, "adv"),
+        _p(vtarg, f32, "vtarg"), P, R, D, A, MB, _p(mb_perm, torch.int32, "mb_perm"), perm_stride,
+        _p(step_ctr, torch.int32, "step_ctr"), _p(kl_coeff, f32, "kl_coeff"), C.byref(hyper), ctas_per_policy,
+        _p(grad_part, f32, "grad_part"), _p(stat_part, torch.float64, "stat_part"), _p(status, torch.int32, "status"),
+        _stream()), "ppo_train_step_tc")

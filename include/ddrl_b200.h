@@ -219,12 +219,28 @@ int ddrl_dg_sample(const float* logits, const float* eps, int64_t R, int A, floa
 int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupling, int64_t B,
                       int W, void* stream);
 
+/* Tensor-core variant of ddrl_ppo_train_step (PPO path only): every GEMM of the fused forward + loss + backward
+ * runs on tcgen05 (kind::f16, FP32 accumulation in TMEM) with FP32 operands split into fp16 (hi, lo) pairs and
+ * three products per GEMM, which keeps the 1e-5 parity bar.  Same batch arrays, minibatch selection, outputs
+ * (grad_part [P][G][NPs], stat_part) and semantics as ddrl_ppo_train_step; the weights come from a tensor-core
+ * image tc_img [P][ddrl_fcnet_tc_image_bytes(D, A)] built by ddrl_fcnet_tc_pack (or kept in step by
+ * ddrl_clip_adam_tc).  D <= 63.  *status (device int, may be NULL) is set to 1 if an MMA completion wait timed out. */
+int ddrl_fcnet_tc_image_bytes(int D, int A);
+int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* tc_img, void* stream);
+int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* actions,
+                           const float* old_logits, const float* old_logp, const float* vf_preds,
+                           const float* adv, const float* vtarg, int P, int64_t R, int D, int A, int MB,
+                           const int32_t* mb_perm, int64_t perm_stride, const int32_t* step_ctr,
+                           const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas_per_policy,
+                           float* grad_part, double* stat_part, int* status, void* stream);
+
 /* Diagnostic: one tcgen05 (UMMA) GEMM through TMEM with the chunked shared-memory operand layout the tensor-core
- * training step uses (csrc/umma.cuh): D[128][N] = sum_k A(m,k) B(n,k), A(m,k) = A[m][k] (a_mn = 0, K-major) or
+ * training step uses (csrc/umma.cuh): D[m][n] = sum_k A(m,k) B(n,k), m < M (64 or 128), A(m,k) = A[m][k] (a_mn = 0, K-major) or
  * A[k][m] (a_mn = 1, MN-major view); B alike; split != 0 -> fp16 (hi, lo) operand split with three products.
- * A [ra][ca], B [rb][cb], D [128][N] float32 device arrays; *status (device int) = 0 ok, 1 = MMA completion timed out. */
-int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B, int rb, int cb, int N, int K, int a_mn,
-                       int b_mn, int split, float* D, int* status, void* stream);
+ * A [ra][ca], B [rb][cb] float32 device arrays; D [128][N] = the raw TMEM lanes 0..127 x N columns (for M = 64 the
+ * accumulator rows occupy a subset of the lanes); *status (device int) = 0 ok, 1 = MMA completion timed out. */
+int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B, int rb, int cb, int M, int N, int K,
+                       int a_mn, int b_mn, int split, float* D, int* status, void* stream);
 
 #ifdef __cplusplus
 }

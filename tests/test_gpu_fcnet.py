@@ -116,7 +116,7 @@ def _oracle_grads(b, rows, kl_coeff, cfg, dtype=torch.float64):
     return np.stack(grads), stats
 
 
-def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda"):
+def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda", tc=False):
     from ddrl_b200 import kernels as K
     from ddrl_b200._lib import PPOHyper
     P, A = b["P"], b["A"]
@@ -130,8 +130,15 @@ def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda"):
     ctr = torch.zeros(1, dtype=torch.int32, device=dev)
     klc = torch.tensor(kl_coeff, dtype=torch.float32, device=dev)
     hyper = PPOHyper(cfg.clip_param, cfg.vf_clip_param, cfg.vf_loss_coeff, cfg.entropy_coeff, 1.0 / MB)
-    K.ppo_train_step(t["theta"], t["obs"], t["actions"], t["old_logits"], t["old_logp"], t["vf_preds"], t["adv"],
-                     t["vtarg"], A, MB, perm, ctr, klc, hyper, G, gp, sp)
+    if tc:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        img = K.fcnet_tc_pack(t["theta"], b["D"], A)
+        K.ppo_train_step_tc(img, t["obs"], t["actions"], t["old_logits"], t["old_logp"], t["vf_preds"], t["adv"],
+                            t["vtarg"], A, MB, perm, ctr, klc, hyper, G, gp, sp, status)
+        assert int(status) == 0, "tcgen05 MMA completion timed out"
+    else:
+        K.ppo_train_step(t["theta"], t["obs"], t["actions"], t["old_logits"], t["old_logp"], t["vf_preds"], t["adv"],
+                         t["vtarg"], A, MB, perm, ctr, klc, hyper, G, gp, sp)
     K.grad_reduce(gp, sp, P, G, NP, grad, ss, ctr)
     torch.cuda.synchronize()
     return grad.cpu().numpy(), ss.cpu().numpy()[0]
@@ -141,17 +148,22 @@ def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda"):
                                     ("Local", 8), ("TwoSides", 3), ("SingleDiagonal", 16),
                                     ("Centralized_TVel", 7), ("FullyDecentral_TVel", 2), ("Local_TVel", 4),
                                     ("TwoSides_TVel", 9)])
-def test_train_step_gradients_match_float64_autograd(arch, G):
+@pytest.mark.parametrize("tc", [False, True], ids=["fp32", "tcgen05"])
+def test_train_step_gradients_match_float64_autograd(arch, G, tc):
     O = _oracle()
     cfg = O.PPOConfig(entropy_coeff=0.01)  # non-zero so the entropy term is exercised too
     R, MB = 1000, 500                       # minibatch 1 = rows [500, 1000): ragged tiles for most G
     b = _make_batch(arch, R, 3, "cuda")
     klc = [0.2 * 1.5 ** p for p in range(b["P"])]
-    grad, ssum = _cuda_train_step(b, MB, 1, G, klc, cfg)
+    grad, ssum = _cuda_train_step(b, MB, 1, G, klc, cfg, tc=tc)
     ref, stats = _oracle_grads(b, slice(MB, 2 * MB), klc, cfg)
     twin, _ = _oracle_grads(b, slice(MB, 2 * MB), klc, cfg, torch.float32)
+    # FP32 kernel: 1e-5.  tcgen05 kernel (fp16 hi/lo split, ~22-bit operands): STATED tolerance 5e-5 of the tensor's
+    # scale for gradients — the value branch amplifies forward round-off by |v| / |v - R| ~ 10 (the float32 torch twin
+    # itself sits at ~5e-6 there); forward outputs and loss statistics stay within 1e-5.
+    gtol = 5e-5 if tc else TOL
     for p in range(b["P"]):
-        assert scaled_err(grad[p], ref[p]) < TOL, (arch, p)
+        assert scaled_err(grad[p], ref[p]) < gtol, (arch, p)
         # per-variable check so a small tensor (biases, heads) cannot hide behind a large one.  A bias gradient is a
         # cancelling sum over rows (e.g. value_out/bias = sum_r dL/dv_r ~ 3e-4 from terms ~ 2e-2): perturbing v by
         # 3 ulp moves it by 1e-3 relative, so its own magnitude is not a usable scale for FP32 round-off.  Each
@@ -166,7 +178,7 @@ def test_train_step_gradients_match_float64_autograd(arch, G):
             e_twin = np.abs(twin[p][o:o + n].astype(np.float64) - ref[p][o:o + n]).max()
             # 1-D variables (biases) are pure cancelling sums over rows: floor at 5 % of the gradient's scale
             scale = max(np.abs(ref[p][o:o + n]).max(), (0.05 if shp[1] == 0 else 0.01) * gscale)
-            assert err < max(2e-5 * scale, 4.0 * e_twin), (arch, p, o, err, scale, e_twin)
+            assert err < max(2.0 * gtol * scale, 4.0 * e_twin), (arch, p, o, err, scale, e_twin)
             o += n
         s = ssum[p] / MB
         assert abs(s[0] - stats[p]["policy_loss"]) < TOL * max(1.0, abs(stats[p]["policy_loss"]))
