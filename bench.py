@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=1024, help="envs in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--mode", default="tc", choices=["tc", "fp32"], help="SGD-step kernel: tcgen05 split-fp16 or FP32 FMA")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -208,7 +209,7 @@ def main():
     import oracle.ddrl_oracle as O  # Glorot init values only (host RNG); no oracle compute in the timed path
     gen = torch.Generator().manual_seed(1234)
     theta0 = torch.stack([O.fcnet_init(D, 2 * A, gen) for _ in range(P)])
-    L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=not args.no_graph)
+    L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=not args.no_graph, mode=args.mode)
 
     sets = [synth_rollout(P, T, C, D, A, envs, nb, E, 1234 + rank + 100 * s, device=dev) for s in range(args.sets)]
     host = synth_rollout(P, T, C, D, A, envs, nb, E, 999 + rank, pinned=True)
@@ -275,9 +276,14 @@ def main():
         a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         L.step_ctr.fill_(i % (E * nb))
         a.record()
-        K.ppo_train_step(L.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
-                         src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"], b["stat_part"],
-                         img=L.img)
+        if args.mode == "tc":
+            K.ppo_train_step_tc(L.tc_img, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
+                                src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"],
+                                b["stat_part"], L.tc_status)
+        else:
+            K.ppo_train_step(L.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
+                             src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"],
+                             b["stat_part"], img=L.img)
         c.record()
         evs.append((a, c))
     torch.cuda.synchronize()
@@ -292,7 +298,9 @@ def main():
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6
     fp32_peak = 148 * 128 * 2 * sm_clock / 1e12
-    roofline = {"bound": "tensor", "kernel": "fcnet_train_kernel (fused fwd + PPO loss + bwd, FP32 FMA parity mode)",
+    kname = ("fcnet_train_tc_kernel (fused fwd + PPO loss + bwd; tcgen05 kind::f16, fp16 hi/lo split x3 products, TMEM accum)"
+             if args.mode == "tc" else "fcnet_train_kernel (fused fwd + PPO loss + bwd, FP32 FMA parity mode)")
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "traffic": None, "launch_ms": k_ms, "flops_per_launch": flops_launch,
@@ -310,12 +318,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if args.mode == "fp32" else "f32 (tcgen05 GEMMs on fp16 hi+lo split operands, f32 accumulate)",
+            "data": "synthetic",
             "config": {"workload": W["name"], "policies": P, "agents_per_env": Ag, "obs_dim": D, "act_dim": A,
                        "envs_per_gpu": envs, "envs_total": envs * world, "fragment_T": T, "rows_per_policy_per_gpu": R,
                        "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_minibatch_size_global": MB_local * world,
                        "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
-                       "cuda_graph": bool(L.use_graph and L._graph is not None),
+                       "cuda_graph": bool(L.use_graph and L._graph is not None), "sgd_kernel": args.mode,
                        "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),

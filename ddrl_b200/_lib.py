@@ -51,8 +51,8 @@ PROTOTYPES = {
                                                     c_f32p, c_f32p, c_f64p, c_stream]),
     "ddrl_grad_reduce": (C.c_int, [c_f32p, c_f64p, C.c_int, C.c_int, C.c_int, c_f32p, c_f64p, c_i32p, c_stream]),
     "ddrl_clip_adam": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_float,
-                                 C.c_float, C.c_float, C.c_float, c_f32p, c_i32p, c_i32p, c_f32p, C.c_int, C.c_int,
-                                 c_stream]),
+                                 C.c_float, C.c_float, C.c_float, c_f32p, c_i32p, c_i32p, c_f32p, C.c_void_p, C.c_int,
+                                 C.c_int, c_stream]),
     "ddrl_graphnet_num_params": (C.c_int, [C.c_int]),
     "ddrl_graphnet_forward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p,
                                         c_stream]),

@@ -6,6 +6,8 @@
 
 #include "common.cuh"
 #include "fcnet_layout.cuh"
+#include "fcnet_tc_layout.cuh"
+#include <cuda_fp16.h>
 #include "ppo_loss.cuh"
 
 namespace ddrl {
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(AT) clip_adam_kernel(float* __restrict__ theta
                                                        const float* __restrict__ grad, int NP, float lr, float beta1,
                                                        float beta2, float eps, float clip, float* gnorm_out,
                                                        int32_t* step_ctr, int32_t* sync_ws, float* __restrict__ img,
-                                                       int imgD, int imgA) {
+                                                       unsigned char* __restrict__ tcimg, int imgD, int imgA) {
     __shared__ float red[AT / 32];
     __shared__ float s_scale;
     const int p = blockIdx.y, P = gridDim.y, tid = threadIdx.x;
@@ -259,6 +261,22 @@ __global__ void __launch_bounds__(AT) clip_adam_kernel(float* __restrict__ theta
             float* im = img + (int64_t)p * L.x;
             im[p0] = tnew;
             if (p1 >= 0) im[p1] = tnew;
+        }
+        if (tcimg) {   // tensor-core image: fp16 (hi, lo) of 256*w for the GEMM weights, fp32 for biases / heads
+            const TcImg L = tc_img(imgD, imgA);
+            const FcOffsets o = fc_offsets(imgD, imgA);
+            bool f16;
+            int p0, p1;
+            tc_img_pos(L, o, imgD, imgA, j, f16, p0, p1);
+            unsigned char* im = tcimg + (int64_t)p * L.bytes;
+            if (f16) {
+                const float ws = tnew * 256.f;
+                const __half hi = __float2half_rn(ws);
+                *reinterpret_cast<__half*>(im + p0) = hi;
+                *reinterpret_cast<__half*>(im + p1) = __float2half_rn(ws - __half2float(hi));
+            } else {
+                *reinterpret_cast<float*>(im + p0) = tnew;
+            }
         }
     }
     // arrival ticket: the last CTA advances the beta powers / step counter after everyone has read them
@@ -461,16 +479,16 @@ extern "C" int ddrl_grad_reduce(const float* grad_part, const double* stat_part,
 
 extern "C" int ddrl_clip_adam(float* theta, float* m, float* v, float* beta_pow, const float* grad, int P, int NP,
                               float lr, float beta1, float beta2, float eps, float grad_clip, float* gnorm_out,
-                              int32_t* step_ctr, int32_t* sync_ws, float* fcnet_img, int img_D, int img_A,
-                              void* stream) {
+                              int32_t* step_ctr, int32_t* sync_ws, float* fcnet_img, void* fcnet_tc_img, int img_D,
+                              int img_A, void* stream) {
     DDRL_REQUIRE(theta && m && v && beta_pow && grad && sync_ws && P >= 1 && NP >= 1, DDRL_E_BADARG,
                  "clip_adam: null pointer or bad shape");
-    DDRL_REQUIRE(!fcnet_img || (img_D >= 1 && img_D <= DDRL_MAX_OBS && img_A >= 1 && img_A <= DDRL_MAX_ACT &&
+    DDRL_REQUIRE(!(fcnet_img || fcnet_tc_img) || (img_D >= 1 && img_D <= DDRL_MAX_OBS && img_A >= 1 && img_A <= DDRL_MAX_ACT &&
                                 fc_offsets(img_D, img_A).NP == NP),
                  DDRL_E_BADARG, "clip_adam: fcnet image given but (D=%d, A=%d) does not match NP=%d", img_D, img_A, NP);
     clip_adam_kernel<<<dim3((NP + AT - 1) / AT, P), AT, 0, (cudaStream_t)stream>>>(
         theta, m, v, beta_pow, grad, NP, lr, beta1, beta2, eps, grad_clip, gnorm_out, step_ctr, sync_ws, fcnet_img,
-        img_D, img_A);
+        (unsigned char*)fcnet_tc_img, img_D, img_A);
     DDRL_CHECK_LAUNCH("clip_adam");
     return DDRL_OK;
 }

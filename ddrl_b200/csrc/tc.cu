@@ -111,21 +111,24 @@ extern "C" int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B
 // =================================================================================================================
 // Tensor-core FCNet training step: same contract as fcnet_train_kernel (csrc/fcnet.cu) — one minibatch of all
 // policies, fused forward + PPO loss + backward, per-CTA partial gradients in flat checkpoint order — with every
-// GEMM on tcgen05 (kind::f16, FP32 accumulation in TMEM).  FP32 operands are split into fp16 (hi, lo) pairs and
-// three products hi*hi + hi*lo + lo*hi are accumulated, which restores ~2^-21 relative accuracy (umma self test),
-// i.e. the 1e-5 parity bar still holds.
+// GEMM (layers, heads, head back-projection, all weight gradients) on tcgen05 (kind::f16, FP32 accumulation in TMEM).
+// FP32 operands are split into fp16 (hi, lo) pairs and three products hi*hi + hi*lo + lo*hi are accumulated, which
+// restores ~2^-21 relative accuracy (umma self test).
 //
-//   * tile = 128 rows (UMMA M); thread = (row, 32-column half) of a 64-wide branch tile, so the TMEM load
-//     (tcgen05.ld 32x32b.x32) hands each thread exactly its accumulators.
+//   * tile = 128 rows (UMMA M); 512 threads, thread = (row, 16-column quarter) of a 64-wide branch tile, so a
+//     tcgen05.ld 32x32b.x8 hands each thread 8 of its accumulators at a time; epilogues are short ROLLED loops over
+//     8-column chunks (the previous fully unrolled version was 240 KB of SASS and instruction-fetch bound).
 //   * the value and policy branches are processed one after the other (the PPO loss separates into a policy part
 //     and a value part), which halves the activation footprint: H1, H2 are [128][64] fp16 hi/lo in the chunked layout.
 //   * the SAME activation buffers feed the forward chain (K-major view) and the weight-gradient GEMMs (MN-major
 //     view: M = feature, K = row), so the backward needs no transposed copies; weight gradients accumulate in TMEM
-//     (M = 64 accumulators) across all tiles of the CTA.
+//     (M = 64 accumulators, row m in lane 32*(m/16) + m%16) across all tiles of the CTA.
+//   * activations needed again by the backward (1 - h^2) are re-read from their hi + lo halves (exact to 2^-22).
 //   * bias gradients ride along: X carries a constant-1 pad column, so dW1 gains a row = sum_r dz1 and a 16-wide
 //     MMA against that column gives sum_r dz2.
-//   * loss gradients are kept unscaled (no 1/minibatch) on chip so they stay inside the fp16 range; the scale is
-//     applied when the accumulators are written out.
+//   * operands are stored pre-multiplied by power-of-two scales (exact) so the lo halves stay in the fp16 normal range;
+//     loss gradients are kept without the 1/minibatch factor on chip; both are undone at the accumulator read-out.
+//     fp16 overflow is clamped AND reported (*status = 2) so the caller can redo the step on the FP32 kernel.
 // =================================================================================================================
 #include "fcnet_tc_layout.cuh"
 #include "ppo_loss.cuh"
@@ -147,13 +150,10 @@ struct TcTrainArgs {
     int* status;
 };
 
-constexpr int TC_DACC = 0, TC_GW2 = 64, TC_GW1 = 192, TC_GB2 = 320, TC_GWH = 352, TC_TMEM_COLS = 512;
-// Power-of-two operand scales: the lo half of the split is ~2^-11 of the value, so unscaled activations / gradients
-// (|x| < 0.1) would put it into the fp16 subnormal range and lose the bits the split is there to keep.  Every buffer
-// is stored pre-multiplied by its scale (exact) and every accumulator read back is multiplied by the inverse product.
-// What matters is the ABSOLUTE error relative to the tensor's scale: entries too small for a normal lo half lose at
-// most 2^-25/scale, which is negligible next to the large entries that dominate every sum.  Overflow (|x*scale| >
-// 60000) is clamped and reported through *status = 2 so the caller can redo the step on the FP32 kernel.
+// TMEM columns
+constexpr int TC_DACC = 0, TC_HOUT = 64, TC_GW2 = 96, TC_GW1 = 224, TC_GB2 = 352, TC_GWH = 384, TC_TMEM_COLS = 512;
+// Power-of-two operand scales (see header comment).  What matters is the absolute error relative to the tensor's
+// scale: entries too small for a normal lo half lose at most 2^-25/scale, negligible next to the entries that dominate.
 constexpr float TC_SX = 16.f;      // observations (|x| <= 3750)
 constexpr float TC_SH = 4096.f;    // tanh activations (|h| <= 1)
 constexpr float TC_SW = 256.f;     // weights (|w| <= 234)
@@ -170,66 +170,115 @@ __device__ __forceinline__ void tc_cp4(float* smem_dst, const float* gsrc) {
 // D[tmem] (+)= A * B^T with fp16 (hi, lo) operands: products (hi,hi) (hi,lo) (lo,hi); nprod == 2 -> (hi,hi) (lo,hi).
 // a_rows / b_rows = row count of the chunked buffers; *_mn selects the MN-major view.  One thread calls this.
 __device__ __forceinline__ void tc_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
-                                        uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate,
-                                        int nprod) {
+                                        uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate, int nprod) {
     const uint32_t idesc = umma::idesc_f16(M, N, a_mn, b_mn);
-    const uint32_t astep = a_mn ? 256u : (uint32_t)(2 * a_rows * 16);
-    const uint32_t bstep = b_mn ? 256u : (uint32_t)(2 * b_rows * 16);
-    bool acc = accumulate;
+    // descriptors advance along K by adding to the 14-bit start-address field (16-byte units; smem < 256 KB, no carry)
+    const uint64_t astep = a_mn ? 16u : (uint64_t)(2 * a_rows);
+    const uint64_t bstep = b_mn ? 16u : (uint64_t)(2 * b_rows);
+    const uint64_t ah = a_mn ? umma::desc_mnmajor(a_hi, a_rows) : umma::desc_kmajor(a_hi, a_rows);
+    const uint64_t al = a_mn ? umma::desc_mnmajor(a_lo, a_rows) : umma::desc_kmajor(a_lo, a_rows);
+    const uint64_t bh = b_mn ? umma::desc_mnmajor(b_hi, b_rows) : umma::desc_kmajor(b_hi, b_rows);
+    const uint64_t bl = b_mn ? umma::desc_mnmajor(b_lo, b_rows) : umma::desc_kmajor(b_lo, b_rows);
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
     for (int pr = 0; pr < nprod; ++pr) {
-        const uint32_t pa = (pr == 2 || (nprod == 2 && pr == 1)) ? a_lo : a_hi;
-        const uint32_t pb = (nprod == 3 && pr == 1) ? b_lo : b_hi;
+        uint64_t ad = (pr == 2 || (nprod == 2 && pr == 1)) ? al : ah;
+        uint64_t bd = (nprod == 3 && pr == 1) ? bl : bh;
+#pragma unroll 4
         for (int ks = 0; ks < nk; ++ks) {
-            const uint64_t ad = a_mn ? umma::desc_mnmajor(pa + ks * astep, a_rows) : umma::desc_kmajor(pa + ks * astep, a_rows);
-            const uint64_t bd = b_mn ? umma::desc_mnmajor(pb + ks * bstep, b_rows) : umma::desc_kmajor(pb + ks * bstep, b_rows);
-            umma::mma_f16(d_tmem, ad, bd, idesc, acc);
-            acc = true;
+            umma::mma_f16(d_tmem, ad, bd, idesc, acc != 0u);
+            acc = 1u;
+            ad += astep;
+            bd += bstep;
         }
     }
 }
 
-__device__ __forceinline__ float tc_clamp_h(float x, bool& ovf) {
-    ovf = ovf || !(fabsf(x) <= 60000.f);
-    return fminf(fmaxf(x, -60000.f), 60000.f);
-}
-
-// split 8 floats (times a power-of-two scale) into fp16 hi / lo 16-byte chunks
-__device__ __forceinline__ void tc_split8(const float* v, float scale, uint4& hi, uint4& lo, bool& ovf) {
-    __half2 h[4], l[4];
+// split 8 floats (times a power-of-two scale) into fp16 hi / lo 16-byte chunks; returns true on fp16 overflow
+__device__ __forceinline__ bool tc_split8(const float* v, float scale, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+    bool ovf = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float x0 = tc_clamp_h(v[2 * i] * scale, ovf), x1 = tc_clamp_h(v[2 * i + 1] * scale, ovf);
+        float x0 = v[2 * i] * scale, x1 = v[2 * i + 1] * scale;
+        ovf = ovf || !(fabsf(x0) <= 60000.f) || !(fabsf(x1) <= 60000.f);
+        x0 = fminf(fmaxf(x0, -60000.f), 60000.f);
+        x1 = fminf(fmaxf(x1, -60000.f), 60000.f);
         const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-        h[i] = __halves2half2(h0, h1);
-        l[i] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+        const __half2 hh = __halves2half2(h0, h1);
+        const __half2 ll = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
-                    *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-    lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                    *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    return ovf;
 }
 
-// thread's 32 values (columns 32*hf .. +31 of row `row`) -> chunked [128][64] hi / lo buffers
-__device__ __forceinline__ void tc_store_rowhalf(unsigned char* bhi, unsigned char* blo, int row, int hf, const float (&v)[32],
-                                                 float scale, bool& ovf) {
+// hi + lo chunk -> 8 floats (times inv_scale)
+__device__ __forceinline__ void tc_join8(const uint4& hi, const uint4& lo, float inv_scale, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&hi);
+    const __half2* l = reinterpret_cast<const __half2*>(&lo);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int i = 0; i < 4; ++i) {
+        const float2 fh = __half22float2(h[i]), fl = __half22float2(l[i]);
+        v[2 * i] = (fh.x + fl.x) * inv_scale;
+        v[2 * i + 1] = (fh.y + fl.y) * inv_scale;
+    }
+}
+
+// Forward epilogue of this thread's 16 columns: act = tanh(acc * inv_in + bias) -> fp16 hi/lo (x TC_SH), chunked [128][64].
+__device__ __noinline__ bool tc_epi_tanh(uint32_t taddr, const float* bias, float inv_in, unsigned char* dhi, unsigned char* dlo,
+                                         int row, int cq) {
+    bool ovf = false;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[8];
+        umma::tmem_ld8(taddr + 8 * c, v);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
+        v[0] = tanhf(fmaf(v[0], inv_in, b0.x)); v[1] = tanhf(fmaf(v[1], inv_in, b0.y));
+        v[2] = tanhf(fmaf(v[2], inv_in, b0.z)); v[3] = tanhf(fmaf(v[3], inv_in, b0.w));
+        v[4] = tanhf(fmaf(v[4], inv_in, b1.x)); v[5] = tanhf(fmaf(v[5], inv_in, b1.y));
+        v[6] = tanhf(fmaf(v[6], inv_in, b1.z)); v[7] = tanhf(fmaf(v[7], inv_in, b1.w));
         uint4 hi, lo;
-        tc_split8(&v[8 * c], scale, hi, lo, ovf);
-        const int off = ((4 * hf + c) * TC_ROWS + row) * 16;
+        ovf = tc_split8(v, TC_SH, hi, lo) || ovf;
+        const int off = ((2 * cq + c) * TC_ROWS + row) * 16;
+        *reinterpret_cast<uint4*>(dhi + off) = hi;
+        *reinterpret_cast<uint4*>(dlo + off) = lo;
+    }
+    return ovf;
+}
+
+// Backward epilogue: g = acc * inv_in * (1 - h^2), h re-read from the buffer it then overwrites (fp16 hi/lo x TC_SD).
+__device__ __noinline__ bool tc_epi_grad(uint32_t taddr, float inv_in, unsigned char* bhi, unsigned char* blo, int row, int cq) {
+    bool ovf = false;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[8], h[8];
+        umma::tmem_ld8(taddr + 8 * c, v);
+        const int off = ((2 * cq + c) * TC_ROWS + row) * 16;
+        tc_join8(*reinterpret_cast<const uint4*>(bhi + off), *reinterpret_cast<const uint4*>(blo + off), 1.f / TC_SH, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * inv_in * (1.f - h[j] * h[j]);
+        uint4 hi, lo;
+        ovf = tc_split8(v, TC_SD, hi, lo) || ovf;
         *reinterpret_cast<uint4*>(bhi + off) = hi;
         *reinterpret_cast<uint4*>(blo + off) = lo;
     }
+    return ovf;
 }
 
+template <int A>
 __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainArgs a) {
+    constexpr int A2 = 2 * A;
     extern __shared__ __align__(1024) unsigned char sm[];
     const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
-    const int D = a.D, A = a.A, A2 = 2 * A, KX = tc_kx(D), LDo = A2 + 1;
+    const int D = a.D, KX = tc_kx(D);
     const TcImg I = tc_img(D, A);
     const TcSmem S = tc_smem(D, A);
     const FcOffsets o = fc_offsets(D, A);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S.bar);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + S.bar + 8);
     const uint32_t sbase = umma::smem_u32(sm);
@@ -251,13 +300,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     const float* obs_p = a.obs + (int64_t)p * a.R * D;
     float* xraw = reinterpret_cast<float*>(sm + S.xraw);
     float* pf = reinterpret_cast<float*>(sm + S.pf);
-    float* hpart = reinterpret_cast<float*>(sm + S.hpart);
-    float* dlf = reinterpret_cast<float*>(sm + S.dlf);
     const float* b1c = reinterpret_cast<const float*>(sm + I.b1c);
     const float* b2c = reinterpret_cast<const float*>(sm + I.b2c);
-    const float* sWo = reinterpret_cast<const float*>(sm + I.Wo);
     const float* sbo = reinterpret_cast<const float*>(sm + I.bo);
-    const float* sWvo = reinterpret_cast<const float*>(sm + I.Wvo);
     const float* sbvo = reinterpret_cast<const float*>(sm + I.bvo);
 
     auto prefetch_x = [&](int64_t r0, int n) {
@@ -295,16 +340,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     const uint32_t tmem = *tslot;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     uint32_t phase = 0;
-    bool ok = true;
-    bool first = true;
-    bool ovf = false;
+    bool ok = true, first = true;
+    int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 4 = activations, 8 = dl, 16 = dz2, 32 = dz1
     const float klc = a.kl_coeff[p];
     double st[DDRL_NSTAT];
 #pragma unroll
     for (int i = 0; i < DDRL_NSTAT; ++i) st[i] = 0.0;
-    float gbh[2 * DDRL_MAX_ACT + 1];   // head bias gradients (loss threads): sum_r dl[r][o]
+    float gbh[A2 + 1];   // head bias gradients (loss threads): sum_r dl[r][o]
 #pragma unroll
-    for (int i = 0; i < 2 * DDRL_MAX_ACT + 1; ++i) gbh[i] = 0.f;
+    for (int i = 0; i < A2 + 1; ++i) gbh[i] = 0.f;
     const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
 
     auto wait_mma = [&]() {
@@ -318,6 +362,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
         __syncthreads();
     };
 
+#pragma unroll 1
     for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
         const int nrows = (int)min((int64_t)TC_ROWS, cr1 - row0);
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -325,7 +370,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
         // ---- x: fp32 staging -> fp16 hi/lo chunked [128][KX], constant 1 in column D, zero rows beyond nrows ----------
         {
             const int r = tid & (TC_ROWS - 1);
-            for (int c8 = tid >> 7; c8 < (KX >> 3); c8 += 2) {
+#pragma unroll 1
+            for (int c8 = tid >> 7; c8 < (KX >> 3); c8 += 4) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -333,7 +379,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                     v[e] = (r < nrows) ? (d < D ? xraw[r * D + d] : (d == D ? 1.f : 0.f)) : 0.f;
                 }
                 uint4 hi, lo;
-                tc_split8(v, TC_SX, hi, lo, ovf);
+                ovf |= tc_split8(v, TC_SX, hi, lo) ? 2 : 0;
                 *reinterpret_cast<uint4*>(sm + S.X[0] + (c8 * TC_ROWS + r) * 16) = hi;
                 *reinterpret_cast<uint4*>(sm + S.X[1] + (c8 * TC_ROWS + r) * 16) = lo;
             }
@@ -345,10 +391,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
             asm volatile("cp.async.commit_group;\n" ::);
         }
 
+#pragma unroll 1
         for (int bi = 0; bi < 2; ++bi) {
             const int b = 1 - bi;                      // value branch first, then policy
-            const int nout = b == 0 ? A2 : 1;
-            float h1[32], h2[32], v[32];
+            const uint32_t dacc = tmem + tlane + TC_DACC + 16 * cq;
             // ---- F1: Dacc = X * W1b^T ------------------------------------------------------------------------
             if (tid == 0) {
                 umma::fence_after_sync();
@@ -357,10 +403,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 umma::mma_commit(mbar);
             }
             wait_mma();
-            umma::tmem_ld32(tmem + tlane + TC_DACC + 32 * hf, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h1[j] = tanhf(v[j] * (1.f / (TC_SX * TC_SW)) + b1c[b * 64 + 32 * hf + j]);
-            tc_store_rowhalf(sm + S.H1[0], sm + S.H1[1], row, hf, h1, TC_SH, ovf);
+            ovf |= tc_epi_tanh(dacc, b1c + b * 64 + 16 * cq, 1.f / (TC_SX * TC_SW), sm + S.H1[0], sm + S.H1[1], row, cq) ? 4 : 0;
             publish();
             // ---- F2: Dacc = H1 * W2b ---------------------------------------------------------------------------
             if (tid == 0) {
@@ -370,66 +413,48 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 umma::mma_commit(mbar);
             }
             wait_mma();
-            umma::tmem_ld32(tmem + tlane + TC_DACC + 32 * hf, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h2[j] = tanhf(v[j] * (1.f / (TC_SH * TC_SW)) + b2c[b * 64 + 32 * hf + j]);
-            tc_store_rowhalf(sm + S.H2[0], sm + S.H2[1], row, hf, h2, TC_SH, ovf);
-            // head partial sums over this thread's 32 hidden units
-            float part[2 * DDRL_MAX_ACT];
-#pragma unroll
-            for (int oo = 0; oo < 2 * DDRL_MAX_ACT; ++oo) {
-                part[oo] = 0.f;
-                if (oo < nout) {
-                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int k = 32 * hf + j;
-                        s0 = fmaf(h2[j], b == 0 ? sWo[k * A2 + oo] : sWvo[k], s0);
-                        s1 = fmaf(h2[j + 1], b == 0 ? sWo[(k + 1) * A2 + oo] : sWvo[k + 1], s1);
-                    }
-                    part[oo] = s0 + s1;
-                    if (hf == 1) hpart[row * LDo + oo] = part[oo];
-                }
-            }
+            ovf |= tc_epi_tanh(dacc, b2c + b * 64 + 16 * cq, 1.f / (TC_SH * TC_SW), sm + S.H2[0], sm + S.H2[1], row, cq) ? 4 : 0;
             publish();
-            // ---- loss of this branch (one thread per row) -> dlf (fp32) and DL (fp16 hi/lo, chunked [128][16]) --------
-            if (hf == 0) {
-                float dl[2 * DDRL_MAX_ACT];
+            // ---- heads: Hout[128][16] = H2 * WoT_b^T ---------------------------------------------------------------
+            if (tid == 0) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + TC_HOUT, sbase + S.H2[0], sbase + S.H2[1], TC_ROWS, false, sbase + I.WoT[b][0],
+                        sbase + I.WoT[b][1], TC_NO, false, 128, TC_NO, 4, false, 3);
+                umma::mma_commit(mbar);
+            }
+            wait_mma();
+            // ---- loss of this branch (warps 0..3, one thread per row) -> DL (fp16 hi/lo x TC_SL, chunked [128][16]) ------
+            if (cq == 0) {
+                float out[16], dl[16];
+                umma::tmem_ld16(tmem + tlane + TC_HOUT, out);
                 double s[DDRL_NSTAT];
 #pragma unroll
                 for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
 #pragma unroll
-                for (int i = 0; i < 2 * DDRL_MAX_ACT; ++i) dl[i] = 0.f;
+                for (int i = 0; i < 16; ++i) dl[i] = 0.f;
                 if (row < nrows) {
                     const float* pa = pf;
                     const float* po = pa + TC_ROWS * A;
                     const float* ps = po + TC_ROWS * A2;
                     if (b == 0) {
-                        float out[2 * DDRL_MAX_ACT];
+                        float lg[A2];
 #pragma unroll
-                        for (int oo = 0; oo < 2 * DDRL_MAX_ACT; ++oo)
-                            if (oo < A2) out[oo] = part[oo] + hpart[row * LDo + oo] + sbo[oo];
-                        ppo_row_policy(out, A, pa + row * A, po + row * A2, ps[row], ps[2 * TC_ROWS + row], klc,
+                        for (int oo = 0; oo < A2; ++oo) lg[oo] = fmaf(out[oo], 1.f / (TC_SH * TC_SW), sbo[oo]);
+                        ppo_row_policy(lg, A, pa + row * A, po + row * A2, ps[row], ps[2 * TC_ROWS + row], klc,
                                        a.hp.clip_param, a.hp.entropy_coeff, 1.f, dl, s);
+#pragma unroll
+                        for (int oo = 0; oo < A2; ++oo) gbh[oo] += dl[oo];
                     } else {
-                        const float val = part[0] + hpart[row * LDo] + sbvo[0];
+                        const float val = fmaf(out[0], 1.f / (TC_SH * TC_SW), sbvo[0]);
                         dl[0] = ppo_row_value(val, ps[TC_ROWS + row], ps[3 * TC_ROWS + row], a.hp.vf_clip_param,
                                               a.hp.vf_loss_coeff, 1.f, s);
-                    }
-                }
-                float dv16[16];
-#pragma unroll
-                for (int oo = 0; oo < 16; ++oo) {
-                    dv16[oo] = (oo < nout && oo < 2 * DDRL_MAX_ACT) ? dl[oo] : 0.f;
-                    if (oo < nout) {
-                        dlf[row * LDo + oo] = dv16[oo];
-                        gbh[b == 0 ? oo : A2] += dv16[oo];
+                        gbh[A2] += dl[0];
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint4 hi, lo;
-                    tc_split8(&dv16[8 * c], TC_SL, hi, lo, ovf);
+                    ovf |= tc_split8(&dl[8 * c], TC_SL, hi, lo) ? 8 : 0;
                     *reinterpret_cast<uint4*>(sm + S.DL[0] + (c * TC_ROWS + row) * 16) = hi;
                     *reinterpret_cast<uint4*>(sm + S.DL[1] + (c * TC_ROWS + row) * 16) = lo;
                 }
@@ -437,27 +462,17 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 for (int i = 0; i < DDRL_NSTAT; ++i) st[i] += s[i];
             }
             publish();
-            // ---- B1 (async): gWh_b[k][o] (+)= H2^T * DL ------------------------------------------------------------
+            // ---- B1: gWh_b[k][o] (+)= H2^T DL ;  dz2-pre: Dacc = DL * WoT_b (B MN-major: N = hidden unit, K = output) ----
             if (tid == 0) {
                 umma::fence_after_sync();
                 tc_gemm(tmem + TC_GWH + 16 * b, sbase + S.H2[0], sbase + S.H2[1], TC_ROWS, true, sbase + S.DL[0],
                         sbase + S.DL[1], TC_ROWS, true, 64, 16, 8, !first, 3);
+                tc_gemm(tmem + TC_DACC, sbase + S.DL[0], sbase + S.DL[1], TC_ROWS, false, sbase + I.WoT[b][0],
+                        sbase + I.WoT[b][1], TC_NO, true, 128, 64, 1, false, 3);
                 umma::mma_commit(mbar);
             }
-            // dz2 = (dl . Wh^T) * (1 - h2^2) in registers while B1 runs
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int k = 32 * hf + j;
-                float s = 0.f;
-                if (b == 0) {
-                    for (int oo = 0; oo < A2; ++oo) s = fmaf(dlf[row * LDo + oo], sWo[k * A2 + oo], s);
-                } else {
-                    s = dlf[row * LDo] * sWvo[k];
-                }
-                h2[j] = s * (1.f - h2[j] * h2[j]);
-            }
-            wait_mma();                                  // B1 has consumed H2: overwrite it with dz2
-            tc_store_rowhalf(sm + S.H2[0], sm + S.H2[1], row, hf, h2, TC_SD, ovf);
+            wait_mma();      // B1 has consumed H2; dz2 = pre * (1 - h2^2) overwrites it
+            ovf |= tc_epi_grad(dacc, 1.f / (TC_SL * TC_SW), sm + S.H2[0], sm + S.H2[1], row, cq) ? 16 : 0;
             publish();
             // ---- B3: gW2_b (+)= H1^T dZ2;  gb2_b (+)= dZ2^T 1;  B4: Dacc = dZ2 * W2b^T -------------------------------
             if (tid == 0) {
@@ -470,11 +485,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                         sbase + I.W2[b][1], 64, false, 128, 64, 4, false, 3);
                 umma::mma_commit(mbar);
             }
-            wait_mma();
-            umma::tmem_ld32(tmem + tlane + TC_DACC + 32 * hf, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h1[j] = v[j] * (1.f / (TC_SD * TC_SW)) * (1.f - h1[j] * h1[j]);     // dz1
-            tc_store_rowhalf(sm + S.H1[0], sm + S.H1[1], row, hf, h1, TC_SD, ovf);
+            wait_mma();      // B3 has consumed H1; dz1 = (dz2 W2^T) * (1 - h1^2) overwrites it
+            ovf |= tc_epi_grad(dacc, 1.f / (TC_SD * TC_SW), sm + S.H1[0], sm + S.H1[1], row, cq) ? 32 : 0;
             publish();
             // ---- B5: gW1_b[c][d] (+)= dZ1^T X   (column D of X is the constant 1 -> bias gradient) ------------------
             if (tid == 0) {
@@ -499,74 +511,82 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     const float inv_gw2 = inv / (TC_SH * TC_SD), inv_gw1 = inv / (TC_SD * TC_SX), inv_gwh = inv / (TC_SH * TC_SL);
     const int m = 16 * q + lane;            // valid for lane < 16
     const bool mine = lane < 16;
+#pragma unroll 1
     for (int b = 0; b < 2; ++b) {
-        float v[32];
-        umma::tmem_ld32(tmem + tlane + TC_GW2 + 64 * b + 32 * hf, v);
-        if (mine) {
-            float* dst = gp + (b ? o.Wv2 : o.W2) + m * 64 + 32 * hf;
+        float v[8];
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {        // gW2_b: this warp's 16 columns
+            umma::tmem_ld8(tmem + tlane + TC_GW2 + 64 * b + 16 * cq + 8 * c, v);
+            if (mine) {
+                float* dst = gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq + 8 * c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = v[j] * inv_gw2;
+                for (int j = 0; j < 8; ++j) dst[j] = v[j] * inv_gw2;
+            }
         }
-        if (32 * hf < KX) {
-            umma::tmem_ld32(tmem + tlane + TC_GW1 + 64 * b + 32 * hf, v);
+#pragma unroll 1
+        for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
+            umma::tmem_ld8(tmem + tlane + TC_GW1 + 64 * b + 8 * c8, v);
             if (mine) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int d = 32 * hf + j;
+                for (int j = 0; j < 8; ++j) {
+                    const int d = 8 * c8 + j;
                     if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = v[j] * inv_gw1;
                     else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = v[j] * inv_gw1;
                 }
             }
         }
-        if (hf == 0) {
-            umma::tmem_ld32(tmem + tlane + TC_GB2 + 16 * b, v);
-            if (mine) gp[(b ? o.bv2 : o.b2) + m] = v[D - 8 * ch0] * inv_gw1;
-            umma::tmem_ld32(tmem + tlane + TC_GWH + 16 * b, v);
+        if (cq == 0) {                                   // gb2_b: column of the constant-1 pad inside its 16-wide window
+            umma::tmem_ld8(tmem + tlane + TC_GB2 + 16 * b + (((D - 8 * ch0) >> 3) << 3), v);
+            const int jsel = (D - 8 * ch0) & 7;
+            const float g = jsel == 0 ? v[0] : jsel == 1 ? v[1] : jsel == 2 ? v[2] : jsel == 3 ? v[3] : jsel == 4 ? v[4]
+                          : jsel == 5 ? v[5] : jsel == 6 ? v[6] : v[7];
+            if (mine) gp[(b ? o.bv2 : o.b2) + m] = g * inv_gw1;
+        }
+        if (cq == 1) {                                   // gWh_b[k = m][o]
+            float w[16];
+            umma::tmem_ld16(tmem + tlane + TC_GWH + 16 * b, w);
             if (mine) {
                 if (b == 0) {
 #pragma unroll
-                    for (int oo = 0; oo < 2 * DDRL_MAX_ACT; ++oo)
-                        if (oo < A2) gp[o.Wo + m * A2 + oo] = v[oo] * inv_gwh;
+                    for (int oo = 0; oo < A2; ++oo) gp[o.Wo + m * A2 + oo] = w[oo] * inv_gwh;
                 } else {
-                    gp[o.Wvo + m] = v[0] * inv_gwh;
+                    gp[o.Wvo + m] = w[0] * inv_gwh;
                 }
             }
         }
     }
     // head bias gradients and stats: reduce over the 128 loss threads (warps 0..3), fixed order
     __syncthreads();
-    float* redf = reinterpret_cast<float*>(sm + S.hpart);          // [4 warps][17]
-    double* redd = reinterpret_cast<double*>(sm + S.red);          // [4 warps][8]
-    if (hf == 0) {
+    double* redd = reinterpret_cast<double*>(sm + S.red);          // [4 warps][32]
+    if (cq == 0) {
 #pragma unroll
-        for (int i = 0; i < 2 * DDRL_MAX_ACT + 1; ++i) {
+        for (int i = 0; i < A2 + 1; ++i) {
             const float s = warp_sum(gbh[i]);
-            if (lane == 0) redf[warp * 17 + i] = s;
+            if (lane == 0) redd[warp * 32 + 8 + i] = (double)s;
         }
 #pragma unroll
         for (int i = 0; i < DDRL_NSTAT; ++i) {
             const double s = warp_sum(st[i]);
-            if (lane == 0) redd[warp * DDRL_NSTAT + i] = s;
+            if (lane == 0) redd[warp * 32 + i] = s;
         }
     }
     __syncthreads();
     if (tid <= A2) {
-        const float s = ((redf[tid] + redf[17 + tid]) + (redf[34 + tid] + redf[51 + tid])) * inv;
+        const float s = (float)((redd[8 + tid] + redd[32 + 8 + tid]) + (redd[64 + 8 + tid] + redd[96 + 8 + tid])) * inv;
         gp[tid == A2 ? o.bvo : o.bo + tid] = s;
     }
     if (tid < DDRL_NSTAT && a.stat_part)
-        a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] =
-            (redd[tid] + redd[DDRL_NSTAT + tid]) + (redd[2 * DDRL_NSTAT + tid] + redd[3 * DDRL_NSTAT + tid]);
+        a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = (redd[tid] + redd[32 + tid]) + (redd[64 + tid] + redd[96 + tid]);
     if (a.status) {
-        if (tid == 0 && !ok) *a.status = 1;
-        else if (ovf) atomicMax(a.status, 2);
+        if (tid == 0 && !ok) atomicOr(a.status, 1);
+        if (ovf) atomicOr(a.status, ovf);
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, TC_TMEM_COLS);
 }
 
-// flat theta -> tensor-core image (fp16 hi/lo weights + fp32 biases / heads)
+// flat theta -> tensor-core image (fp16 hi/lo of 256*w for the GEMM weights + fp32 biases)
 __global__ void fcnet_tc_pack_kernel(const float* __restrict__ theta, int D, int A, unsigned char* __restrict__ img) {
     const int p = blockIdx.y;
     const TcImg L = tc_img(D, A);
@@ -606,6 +626,20 @@ extern "C" int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void*
     return DDRL_OK;
 }
 
+template <int A>
+static int launch_tc(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(fcnet_train_tc_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+            return DDRL_E_CUDA;
+        }
+        attr = true;
+    }
+    fcnet_train_tc_kernel<A><<<dim3(G, P), TC_NT, smem, st>>>(a);
+    return DDRL_OK;
+}
+
 extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, const float* actions, const float* old_logits,
                                       const float* old_logp, const float* vf_preds, const float* adv, const float* vtarg,
                                       int P, int64_t R, int D, int A, int MB, const int32_t* mb_perm, int64_t perm_stride,
@@ -614,8 +648,8 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     DDRL_REQUIRE(tc_img_p && obs && actions && old_logits && old_logp && vf_preds && adv && vtarg && kl_coeff && hyper &&
                      grad_part && P >= 1 && R >= 1 && MB >= 1 && ctas_per_policy >= 1,
                  DDRL_E_BADARG, "ppo_train_step_tc: null pointer or bad P/R/MB/ctas");
-    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS - 1 && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
-                 "ppo_train_step_tc: unsupported D=%d A=%d", D, A);
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS - 1 && (A == 1 || A == 2 || A == 4 || A == 8), DDRL_E_UNSUPPORTED_SHAPE,
+                 "ppo_train_step_tc: unsupported D=%d A=%d (A in {1,2,4,8}, D <= 63)", D, A);
     TcTrainArgs a;
     a.img = (const unsigned char*)tc_img_p; a.obs = obs; a.actions = actions; a.old_logits = old_logits;
     a.old_logp = old_logp; a.vf_preds = vf_preds; a.adv = adv; a.vtarg = vtarg; a.R = R; a.D = D; a.A = A; a.MB = MB;
@@ -623,15 +657,14 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     a.grad_part = grad_part; a.stat_part = stat_part; a.status = status;
     const size_t smem = (size_t)tc_smem(D, A).total;
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(fcnet_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-            set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
-            return DDRL_E_CUDA;
-        }
-        attr = true;
+    int rc;
+    switch (A) {
+        case 1: rc = launch_tc<1>(a, P, ctas_per_policy, smem, (cudaStream_t)stream); break;
+        case 2: rc = launch_tc<2>(a, P, ctas_per_policy, smem, (cudaStream_t)stream); break;
+        case 4: rc = launch_tc<4>(a, P, ctas_per_policy, smem, (cudaStream_t)stream); break;
+        default: rc = launch_tc<8>(a, P, ctas_per_policy, smem, (cudaStream_t)stream); break;
     }
-    fcnet_train_tc_kernel<<<dim3(ctas_per_policy, P), TC_NT, smem, (cudaStream_t)stream>>>(a);
+    if (rc != DDRL_OK) return rc;
     DDRL_CHECK_LAUNCH("ppo_train_step_tc");
     return DDRL_OK;
 }

@@ -189,15 +189,16 @@ def part_stride(NP: int) -> int:
 
 
 def clip_adam(theta, m, v, beta_pow, grad, lr: float, beta1: float, beta2: float, eps: float, grad_clip: float,
-              sync_ws, gnorm_out=None, step_ctr=None, img=None, img_D: int = 0, img_A: int = 0):
+              sync_ws, gnorm_out=None, step_ctr=None, img=None, img_D: int = 0, img_A: int = 0, tc_img=None):
     P, NP = theta.shape
     f32 = torch.float32
     _lib.check(_lib.load().ddrl_clip_adam(_p(theta, f32, "theta"), _p(m, f32, "m"), _p(v, f32, "v"),
                                           _p(beta_pow, f32, "beta_pow"), _p(grad, f32, "grad"), P, NP, float(lr),
                                           float(beta1), float(beta2), float(eps), float(grad_clip),
                                           _p(gnorm_out, f32, "gnorm_out"), _p(step_ctr, torch.int32, "step_ctr"),
-                                          _p(sync_ws, torch.int32, "sync_ws"), _p(img, f32, "img"), int(img_D),
-                                          int(img_A), _stream()), "clip_adam")
+                                          _p(sync_ws, torch.int32, "sync_ws"), _p(img, f32, "img"),
+                                          _p(tc_img, torch.uint8, "tc_img"), int(img_D), int(img_A), _stream()),
+               "clip_adam")
 
 
 def fcnet_backward(theta, obs, dlogits, dvalue, A: int, ctas_per_policy: Optional[int] = None) -> torch.Tensor:

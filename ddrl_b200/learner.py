@@ -89,7 +89,7 @@ class _LearnerBase:
         img = getattr(self, "img", None)
         K.clip_adam(self.theta, self.m, self.v, self.beta_pow, self.grad, c.lr, c.beta1, c.beta2, c.adam_eps,
                     c.grad_clip, self.sync_ws, self.gnorm, self.step_ctr, img, getattr(self, "D", 0) if img is not None else 0,
-                    self.A if img is not None else 0)
+                    self.A if img is not None else 0, tc_img=getattr(self, "tc_img", None))
 
     def _update_kl(self, stats: List[Dict[str, float]]):
         # KLCoeffMixin.update_kl (RLlib 1.0.1): x1.5 if kl > 2*target, x0.5 if kl < 0.5*target
@@ -105,8 +105,13 @@ class FCNetLearner(_LearnerBase):
     """P grouped FCNet policies (obs dim D, action dim A, hiddens [64,64], tanh, separate value net)."""
 
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
-                 use_graph: bool = True, ctas_per_policy: Optional[int] = None):
+                 use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc"):
+        """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
+                 "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes."""
         super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
+        if mode not in ("tc", "fp32"):
+            raise DDRLError(f"mode must be 'tc' or 'fp32', got {mode!r}")
+        self.mode = mode
         self.D, self.A = D, A
         dev = self.device
         self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -118,6 +123,10 @@ class FCNetLearner(_LearnerBase):
         # packed shared-memory image of the weights (kept in step by clip_adam); rebuilt at every iteration start so
         # external writes to self.theta (checkpoint import) are picked up
         self.img = torch.zeros(P, K.fcnet_image_floats(D, A), dtype=torch.float32, device=dev)
+        self.tc_img = None
+        self.tc_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if mode == "tc":
+            self.tc_img = K.fcnet_tc_pack(self.theta, D, A)
         self._bufs = None
         self._graph = None
         self._graph_key = None
@@ -156,9 +165,14 @@ class FCNetLearner(_LearnerBase):
 
     # ---- one optimizer step (3 kernels [+ NCCL]) -----------------------------------------------------------
     def _sgd_step(self, b, MB, G, hyper, src):
-        K.ppo_train_step(self.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
-                         src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
-                         b["grad_part"], b["stat_part"], img=self.img)
+        if self.mode == "tc":
+            K.ppo_train_step_tc(self.tc_img, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
+                                src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
+                                b["grad_part"], b["stat_part"], self.tc_status)
+        else:
+            K.ppo_train_step(self.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
+                             src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
+                             b["grad_part"], b["stat_part"], img=self.img)
         K.grad_reduce(b["grad_part"], b["stat_part"], self.P, G, self.NP, self.grad, b["step_stats"], self.step_ctr)
         if self.world > 1:
             self.dist.all_reduce(self.grad)
@@ -181,6 +195,9 @@ class FCNetLearner(_LearnerBase):
         b = self._alloc(T, Cc)
         obs_flat = raw_obs.reshape(P, R, D)
         K.fcnet_pack(self.theta, D, A, self.img)
+        if self.tc_img is not None:
+            K.fcnet_tc_pack(self.theta, D, A, self.tc_img)
+            self.tc_status.zero_()
         # (i) filter + forward + sample ------------------------------------------------------------------
         if update_filter:
             if self.world > 1:
@@ -257,8 +274,14 @@ class FCNetLearner(_LearnerBase):
         if self.world > 1:
             self.dist.all_reduce(last)
         stats = finalize_stats(last.cpu().numpy(), self.kl_coeff_host, cfg, MB * self.world)
+        if self.tc_img is not None:
+            code = int(self.tc_status.item())
+            if code:
+                what = [n for bit, n in ((1, "MMA completion timed out"), (2, "x overflow"), (4, "activation overflow"),
+                                         (8, "dl overflow"), (16, "dz2 overflow"), (32, "dz1 overflow")) if code & bit]
+                raise DDRLError("tensor-core SGD step failed (" + ", ".join(what) + "): fp16 split range exceeded — "
+                                "use mode='fp32' for this workload")
         self._update_kl(stats)
-        self.last_launches_per_iter = None
         return stats
 
     # ---- plain inference (sampler side) ---------------------------------------------------------------------

@@ -178,11 +178,12 @@ int ddrl_grad_reduce(const float* grad_part, const double* stat_part, int P, int
  *   {b1, b2}, multiplied after the update), gnorm_out [P] or NULL,
  *   sync_ws: one zero-initialised int32 (device) used as an arrival ticket; the last CTA to finish
  *   multiplies the beta powers, increments *step_ctr (if not NULL) and re-zeroes the ticket.
- *   fcnet_img (or NULL): packed FCNet weight image [P][ddrl_fcnet_image_floats(img_D, img_A)] to update in step. */
+ *   fcnet_img / fcnet_tc_img (or NULL): packed FP32 image [P][ddrl_fcnet_image_floats(img_D, img_A)] and tensor-core
+ *   image [P][ddrl_fcnet_tc_image_bytes(img_D, img_A)] of the FCNet weights, updated in step with theta. */
 int ddrl_clip_adam(float* theta, float* m, float* v, float* beta_pow, const float* grad, int P,
                    int NP, float lr, float beta1, float beta2, float eps, float grad_clip,
-                   float* gnorm_out, int32_t* step_ctr, int32_t* sync_ws, float* fcnet_img, int img_D,
-                   int img_A, void* stream);
+                   float* gnorm_out, int32_t* step_ctr, int32_t* sync_ws, float* fcnet_img,
+                   void* fcnet_tc_img, int img_D, int img_A, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GraphNet (models/graph_net.py:10-45) + actor/critic wrapper
@@ -224,7 +225,9 @@ int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupli
  * three products per GEMM, which keeps the 1e-5 parity bar.  Same batch arrays, minibatch selection, outputs
  * (grad_part [P][G][NPs], stat_part) and semantics as ddrl_ppo_train_step; the weights come from a tensor-core
  * image tc_img [P][ddrl_fcnet_tc_image_bytes(D, A)] built by ddrl_fcnet_tc_pack (or kept in step by
- * ddrl_clip_adam_tc).  D <= 63.  *status (device int, may be NULL) is set to 1 if an MMA completion wait timed out. */
+ * ddrl_clip_adam).  D <= 63, A in {1,2,4,8}.  *status (device int, may be NULL) receives OR-ed flags: 1 = an MMA
+ * completion wait timed out; 2/4/8/16/32 = fp16 overflow (clamped) while splitting x / activations / dl / dz2 / dz1 —
+ * the result is then unreliable and the step should be redone with ddrl_ppo_train_step. */
 int ddrl_fcnet_tc_image_bytes(int D, int A);
 int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* tc_img, void* stream);
 int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* actions,

@@ -68,7 +68,7 @@ def test_bad_arguments_return_error_codes_without_touching_a_gpu():
     assert lib.ddrl_fcnet_forward(None, None, None, None, 0.0, 1, 1, 19, 2, None, None, None, None, None, None, None) == -1
     assert b"fcnet_forward" in lib.ddrl_last_error()
     assert lib.ddrl_gae(None, None, None, None, 1, 1, 1, 1, 0.99, 0.95, None, None, None, None, None) == -1
-    assert lib.ddrl_clip_adam(None, None, None, None, None, 1, 1, 0.0, 0.0, 0.0, 0.0, 0.0, None, None, None, None, 0, 0, None) == -1
+    assert lib.ddrl_clip_adam(None, None, None, None, None, 1, 1, 0.0, 0.0, 0.0, 0.0, 0.0, None, None, None, None, None, 0, 0, None) == -1
 
 
 def test_product_code_never_imports_the_oracle():

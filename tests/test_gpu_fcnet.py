@@ -278,9 +278,10 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
-def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle):
+def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
     """filter -> forward/sample -> GAE -> standardise -> 2 epochs x 4 minibatches of clip+Adam -> KL update."""
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
@@ -303,7 +304,7 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle):
     perms = np.stack([np.stack([rng.permutation(nb) for _ in range(2)]) for _ in range(P)]).astype(np.int32)
     shuffle = np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32) if use_shuffle else None
 
-    L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph)
+    L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode)
     L.filt_n.copy_(torch.tensor([f[0] for f in filt0]))
     L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt0])))
     L.filt_S.copy_(torch.from_numpy(np.stack([f[2] for f in filt0])))

@@ -33,7 +33,7 @@ def _learner(pr, dev, mb):
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=mb)
-    L = FCNetLearner(pr["P"], pr["D"], pr["A"], cfg, dev, theta=torch.from_numpy(pr["theta"]), use_graph=False)
+    L = FCNetLearner(pr["P"], pr["D"], pr["A"], cfg, dev, theta=torch.from_numpy(pr["theta"]), use_graph=False, mode="fp32")
     filt = [(1000, M, S * (999.0 / (n - 1))) for n, M, S in pr["filt"]]
     L.filt_n.copy_(torch.tensor([f[0] for f in filt]))
     L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt])))
