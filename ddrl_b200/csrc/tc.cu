@@ -157,8 +157,10 @@ constexpr int TC_DACC = 0, TC_HOUT = 64, TC_GW2 = 96, TC_GW1 = 224, TC_GB2 = 352
 constexpr float TC_SX = 16.f;      // observations (|x| <= 3750)
 constexpr float TC_SH = 4096.f;    // tanh activations (|h| <= 1)
 constexpr float TC_SW = 256.f;     // weights (|w| <= 234)
-constexpr float TC_SL = 1.f;       // head gradients dl (typically 0.1 .. 30, ratio outliers to 1e4)
-constexpr float TC_SD = 8.f;       // hidden-layer gradients dz2, dz1 (|dz| <= 7500)
+// Loss gradients (dl and the dz2 / dz1 derived from it) have no a-priori scale (it follows |v - R| and the
+// advantages), so each branch picks ONE power-of-two scale per CTA from the first tile: max|dl| * scale ~ 256, which
+// leaves a factor 234 of headroom for |dz| to exceed |dl| before the fp16 range is hit (then: flagged, never silent).
+constexpr float TC_GTARGET = 256.f;
 
 __device__ __forceinline__ void tc_cp16(unsigned char* smem_dst, const unsigned char* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc));
@@ -250,8 +252,9 @@ __device__ __noinline__ bool tc_epi_tanh(uint32_t taddr, const float* bias, floa
     return ovf;
 }
 
-// Backward epilogue: g = acc * inv_in * (1 - h^2), h re-read from the buffer it then overwrites (fp16 hi/lo x TC_SD).
-__device__ __noinline__ bool tc_epi_grad(uint32_t taddr, float inv_in, unsigned char* bhi, unsigned char* blo, int row, int cq) {
+// Backward epilogue: g = acc * inv_in * (1 - h^2), h re-read from the buffer it then overwrites (fp16 hi/lo x out_scale).
+__device__ __noinline__ bool tc_epi_grad(uint32_t taddr, float inv_in, float out_scale, unsigned char* bhi, unsigned char* blo,
+                                         int row, int cq) {
     bool ovf = false;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
@@ -262,7 +265,7 @@ __device__ __noinline__ bool tc_epi_grad(uint32_t taddr, float inv_in, unsigned 
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = v[j] * inv_in * (1.f - h[j] * h[j]);
         uint4 hi, lo;
-        ovf = tc_split8(v, TC_SD, hi, lo) || ovf;
+        ovf = tc_split8(v, out_scale, hi, lo) || ovf;
         *reinterpret_cast<uint4*>(bhi + off) = hi;
         *reinterpret_cast<uint4*>(blo + off) = lo;
     }
@@ -451,10 +454,27 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                         gbh[A2] += dl[0];
                     }
                 }
+                if (first) {   // per-branch gradient scale of this CTA: power of two with max|dl| * scale ~ TC_GTARGET
+                    float mx = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fabsf(dl[i]));
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                    float* smx = reinterpret_cast<float*>(sm + S.red);
+                    if (lane == 0) smx[warp] = mx;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");     // the four loss warps only
+                    mx = fmaxf(fmaxf(smx[0], smx[1]), fmaxf(smx[2], smx[3]));
+                    int e = 0;
+                    if (mx > 0.f && mx < 3.0e38f) e = (int)floorf(log2f(TC_GTARGET / mx));
+                    e = max(-20, min(20, e));
+                    if (tid == 0) reinterpret_cast<float*>(sm + S.bar + 16)[b] = exp2f((float)e);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                const float sg_l = reinterpret_cast<const float*>(sm + S.bar + 16)[b];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint4 hi, lo;
-                    ovf |= tc_split8(&dl[8 * c], TC_SL, hi, lo) ? 8 : 0;
+                    ovf |= tc_split8(&dl[8 * c], sg_l, hi, lo) ? 8 : 0;
                     *reinterpret_cast<uint4*>(sm + S.DL[0] + (c * TC_ROWS + row) * 16) = hi;
                     *reinterpret_cast<uint4*>(sm + S.DL[1] + (c * TC_ROWS + row) * 16) = lo;
                 }
@@ -462,6 +482,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 for (int i = 0; i < DDRL_NSTAT; ++i) st[i] += s[i];
             }
             publish();
+            const float sg = reinterpret_cast<const float*>(sm + S.bar + 16)[b];   // this branch's gradient scale
             // ---- B1: gWh_b[k][o] (+)= H2^T DL ;  dz2-pre: Dacc = DL * WoT_b (B MN-major: N = hidden unit, K = output) ----
             if (tid == 0) {
                 umma::fence_after_sync();
@@ -472,7 +493,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 umma::mma_commit(mbar);
             }
             wait_mma();      // B1 has consumed H2; dz2 = pre * (1 - h2^2) overwrites it
-            ovf |= tc_epi_grad(dacc, 1.f / (TC_SL * TC_SW), sm + S.H2[0], sm + S.H2[1], row, cq) ? 16 : 0;
+            ovf |= tc_epi_grad(dacc, 1.f / (sg * TC_SW), sg, sm + S.H2[0], sm + S.H2[1], row, cq) ? 16 : 0;
             publish();
             // ---- B3: gW2_b (+)= H1^T dZ2;  gb2_b (+)= dZ2^T 1;  B4: Dacc = dZ2 * W2b^T -------------------------------
             if (tid == 0) {
@@ -486,7 +507,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 umma::mma_commit(mbar);
             }
             wait_mma();      // B3 has consumed H1; dz1 = (dz2 W2^T) * (1 - h1^2) overwrites it
-            ovf |= tc_epi_grad(dacc, 1.f / (TC_SD * TC_SW), sm + S.H1[0], sm + S.H1[1], row, cq) ? 32 : 0;
+            ovf |= tc_epi_grad(dacc, 1.f / (sg * TC_SW), sg, sm + S.H1[0], sm + S.H1[1], row, cq) ? 32 : 0;
             publish();
             // ---- B5: gW1_b[c][d] (+)= dZ1^T X   (column D of X is the constant 1 -> bias gradient) ------------------
             if (tid == 0) {
@@ -508,12 +529,14 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
 
     // ---- write-out: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
     const float inv = a.hp.inv_global_mb;
-    const float inv_gw2 = inv / (TC_SH * TC_SD), inv_gw1 = inv / (TC_SD * TC_SX), inv_gwh = inv / (TC_SH * TC_SL);
+    __syncthreads();
     const int m = 16 * q + lane;            // valid for lane < 16
     const bool mine = lane < 16;
 #pragma unroll 1
     for (int b = 0; b < 2; ++b) {
         float v[8];
+        const float sgb = reinterpret_cast<const float*>(sm + S.bar + 16)[b];
+        const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {        // gW2_b: this warp's 16 columns
             umma::tmem_ld8(tmem + tlane + TC_GW2 + 64 * b + 16 * cq + 8 * c, v);
