@@ -163,6 +163,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_graphnet(args):
+    """Supplementary line (not the headline): BASELINE.json configs[3] — shared GraphNet policy over the 4-leg graph,
+    4096 envs x 4 agents, T=32, one weight set; minibatch = rows/32; --steps learner iterations with E epochs."""
+    import torch
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import GraphNetLearner
+    import oracle.ddrl_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    A, T, N, E = 2, 32, args.envs, args.gn_epochs
+    C, R = N * 4, T * N * 4
+    nb = 32
+    cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=R // nb)
+    g = torch.Generator().manual_seed(7)
+    th = O.graphnet_wrapper_init(2 * A, g).reshape(1, -1)
+    L = GraphNetLearner(A, cfg, dev, theta=th)
+    state = torch.randn(T, C, 4, 23, generator=g).to(dev)
+    idx = torch.arange(4, dtype=torch.int32).repeat(T * N).reshape(T, C).to(dev)
+    adj = O.ring_adjacency().expand(T, C, 4, 4).contiguous().to(dev)
+    rewards = (0.3 + 0.5 * torch.randn(T, C, generator=g)).to(dev)
+    dones = (torch.rand(T, N, generator=g) < 1e-3).to(torch.uint8).to(dev)
+    eps = torch.randn(T, C, A, generator=g).to(dev)
+    perms = torch.stack([torch.randperm(nb, generator=g) for _ in range(E)]).int().to(dev)
+    shuffle = torch.randperm(R, generator=g).int().to(dev)
+
+    def step():
+        return L.learn_on_rollout(idx, state, adj, idx[0], state[0], adj[0], rewards, dones, eps, perms, shuffle)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"metric": METRIC, "value": T * N * 4 / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "Shared GraphNet policy over the 4-leg graph (BASELINE.json configs[3])",
+                                 "envs": N, "fragment_T": T, "rows": R, "num_sgd_iter": E, "minibatches_per_epoch": nb,
+                                 "note": "supplementary; FP32 kernels, eager launches"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,9 +221,13 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"], help="SGD-step kernel: tcgen05 split-fp16 or FP32 FMA")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
+    ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
+    ap.add_argument("--gn-epochs", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "graphnet":
+        return run_graphnet(args)
 
     import torch
     import torch.distributed as dist
@@ -256,7 +304,9 @@ def main():
     clk = clocks.stop()
     # kernels per iteration: API launches outside the captured graph + graph replays x nodes
     steps_per_iter = E * nb
-    launches_per_iter = 1 + 2 + 2 + 2 + 1 + 7 + steps_per_iter * 3   # pack, filter x2, fwd x2, gae x2, standardise, 7 gathers, sgd
+    fused = world == 1 and L.fuse_tail and L._sgd_setup(R)[2] * P <= L.sms     # train kernel carries reduce + clip + Adam
+    per_sgd = 1 if fused else 3
+    launches_per_iter = 1 + 2 + 2 + 2 + 1 + 7 + steps_per_iter * per_sgd   # pack, filter x2, fwd x2, gae x2, standardise, 7 gathers, sgd
     ms_e2e = timed(step_e2e, max(1, args.warmup // 2), max(3, args.steps // 2))
     e2e_steps = max(3, args.steps // 2)
 
@@ -325,6 +375,7 @@ def main():
                        "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_minibatch_size_global": MB_local * world,
                        "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
                        "cuda_graph": bool(L.use_graph and L._graph is not None), "sgd_kernel": args.mode,
+                       "kernels_per_sgd_step": per_sgd,
                        "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),

@@ -22,6 +22,13 @@ class PPOHyper(C.Structure):
                 ("entropy_coeff", C.c_float), ("inv_global_mb", C.c_float)]
 
 
+class SgdTail(C.Structure):
+    _fields_ = [("theta", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("beta_pow", C.c_void_p), ("grad", C.c_void_p),
+                ("gnorm_out", C.c_void_p), ("fcnet_img", C.c_void_p), ("fcnet_tc_img", C.c_void_p),
+                ("step_stats", C.c_void_p), ("step_ctr", C.c_void_p), ("barrier_ws", C.c_void_p), ("sq_ws", C.c_void_p),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_clip", C.c_float)]
+
+
 # name -> (restype, argtypes); mirrors include/ddrl_b200.h one to one (tests check every symbol).
 PROTOTYPES = {
     "ddrl_last_error": (C.c_char_p, []),
@@ -39,6 +46,7 @@ PROTOTYPES = {
                                     c_stream]),
     "ddrl_fcnet_forward": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f64p, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_int,
                                      c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "ddrl_obs_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
     "ddrl_gae_ws_bytes": (C.c_int64, [C.c_int, C.c_int64]),
     "ddrl_gae": (C.c_int, [c_f32p, c_f32p, c_u8p, c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double,
                            C.c_double, c_f32p, c_f32p, c_f64p, C.c_void_p, c_stream]),
@@ -46,7 +54,7 @@ PROTOTYPES = {
     "ddrl_gather_rows": (C.c_int, [c_f32p, c_i32p, C.c_int, C.c_int64, C.c_int, c_f32p, c_stream]),
     "ddrl_ppo_train_step": (C.c_int, [c_f32p] * 11 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
                                                      C.c_int64, c_i32p, c_f32p, C.POINTER(PPOHyper), C.c_int,
-                                                     c_f32p, c_f64p, c_stream]),
+                                                     c_f32p, c_f64p, C.POINTER(SgdTail), c_stream]),
     "ddrl_ppo_loss_grad": (C.c_int, [c_f32p] * 8 + [C.c_int, C.c_int64, C.c_int, c_f32p, C.POINTER(PPOHyper), C.c_int,
                                                     c_f32p, c_f32p, c_f64p, c_stream]),
     "ddrl_grad_reduce": (C.c_int, [c_f32p, c_f64p, C.c_int, C.c_int, C.c_int, c_f32p, c_f64p, c_i32p, c_stream]),
@@ -66,7 +74,7 @@ PROTOTYPES = {
     "ddrl_fcnet_tc_pack": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_stream]),
     "ddrl_ppo_train_step_tc": (C.c_int, [C.c_void_p] + [c_f32p] * 7 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
                                                                      C.c_int64, c_i32p, c_f32p, C.POINTER(PPOHyper), C.c_int,
-                                                                     c_f32p, c_f64p, c_i32p, c_stream]),
+                                                                     c_f32p, c_f64p, c_i32p, C.POINTER(SgdTail), c_stream]),
     "ddrl_umma_selftest": (C.c_int, [c_f32p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, c_f32p, c_i32p, c_stream]),
 }

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "fcnet_layout.cuh"
 #include "ppo_loss.cuh"
+#include "sgd_tail.cuh"
 
 namespace ddrl {
 
@@ -291,6 +292,7 @@ struct TrainArgs {
     ddrl_ppo_hyper hp;
     float* grad_part;
     double* stat_part;
+    SgdTail tail;
 };
 
 __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
@@ -566,6 +568,10 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
 #pragma unroll
         for (int i = 0; i < DDRL_NSTAT; ++i) sp[i] = st[i];
     }
+    if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
+        __threadfence();
+        sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A, sm + L.out);
+    }
 }
 
 // flat theta -> packed shared-memory image (one thread per parameter)
@@ -658,7 +664,7 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const f
                                    const float* ext_dvalue, int P, int64_t R, int D, int A, int MB,
                                    const int32_t* mb_perm, int64_t perm_stride, const int32_t* step_ctr,
                                    const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas_per_policy,
-                                   float* grad_part, double* stat_part, void* stream) {
+                                   float* grad_part, double* stat_part, const ddrl_sgd_tail* tail, void* stream) {
     DDRL_REQUIRE((theta || img) && obs && grad_part && P >= 1 && R >= 1 && MB >= 1 && ctas_per_policy >= 1,
                  DDRL_E_BADARG, "ppo_train_step: null pointer or bad P/R/MB/ctas");
     DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS && A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE,
@@ -674,6 +680,16 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const f
     a.kl_coeff = kl_coeff;
     if (hyper) a.hp = *hyper; else a.hp = ddrl_ppo_hyper{0.f, 0.f, 0.f, 0.f, 1.f};
     a.grad_part = grad_part; a.stat_part = stat_part;
+    a.tail = SgdTail{};
+    if (tail) {
+        DDRL_REQUIRE(tail->theta && tail->m && tail->v && tail->beta_pow && tail->grad && tail->barrier_ws && tail->sq_ws && !ext,
+                     DDRL_E_BADARG, "ppo_train_step: incomplete fused tail (or external-gradient mode)");
+        DDRL_REQUIRE(ctas_per_policy * P <= num_sms(), DDRL_E_BADARG,
+                     "ppo_train_step: fused tail needs all %d CTAs co-resident (%d SMs)", ctas_per_policy * P, num_sms());
+        a.tail = SgdTail{tail->theta, tail->m, tail->v, tail->beta_pow, tail->grad, tail->gnorm_out, tail->fcnet_img,
+                         (unsigned char*)tail->fcnet_tc_img, tail->step_stats, tail->step_ctr, tail->barrier_ws, tail->sq_ws,
+                         tail->lr, tail->beta1, tail->beta2, tail->eps, tail->grad_clip};
+    }
     const FcSmem L = fc_smem(D, A, false, true);
     const size_t smem = (size_t)L.total * sizeof(float);
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step: shared memory %zu > 227 KB", smem);

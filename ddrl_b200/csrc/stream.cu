@@ -342,6 +342,22 @@ __global__ void __launch_bounds__(LT) ppo_loss_grad_kernel(
     }
 }
 
+// a3: per-agent observation gather (quantruped_v3.get_obs_indices + distribute_observations): pure indexing
+template <typename T>
+__global__ void obs_gather_kernel(const T* __restrict__ full, int64_t S, int Dfull, const int32_t* __restrict__ table, int Ag,
+                                  int D, int P, float* __restrict__ out) {
+    const int k = Ag / P;
+    const int64_t n = S * Ag * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const int64_t t = i / D;
+        const int a = (int)(t % Ag);
+        const int64_t s = t / Ag;
+        const int p = a / k, j = a - p * k;
+        out[(((int64_t)p * S + s) * k + j) * D + d] = (float)full[s * Dfull + table[a * D + d]];
+    }
+}
+
 // DiagGaussian sample + logp (RLlib models/tf/tf_action_dist.py) for models without a fused epilogue.
 __global__ void dg_sample_kernel(const float* __restrict__ logits, const float* __restrict__ eps, int64_t R, int A,
                                  float* __restrict__ action, float* __restrict__ logp) {
@@ -506,6 +522,18 @@ extern "C" int ddrl_ppo_loss_grad(const float* logits, const float* value, const
                                                                         vf_preds, adv, vtarg, R, A, kl_coeff, *hyper,
                                                                         dlogits, dvalue, stat_part);
     DDRL_CHECK_LAUNCH("ppo_loss_grad");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_obs_gather(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag, int D,
+                               int P, float* out, void* stream) {
+    DDRL_REQUIRE(obs_full && table && out && S >= 0 && Dfull >= 1 && Ag >= 1 && D >= 1 && P >= 1 && Ag % P == 0, DDRL_E_BADARG,
+                 "obs_gather: null pointer or bad shape (agents must be a multiple of policies)");
+    if (S == 0) return DDRL_OK;
+    const int nb = (int)std::min<int64_t>(4096, (S * Ag * D + 255) / 256);
+    if (is_f64) obs_gather_kernel<double><<<nb, 256, 0, (cudaStream_t)stream>>>((const double*)obs_full, S, Dfull, table, Ag, D, P, out);
+    else obs_gather_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>((const float*)obs_full, S, Dfull, table, Ag, D, P, out);
+    DDRL_CHECK_LAUNCH("obs_gather");
     return DDRL_OK;
 }
 

@@ -132,6 +132,7 @@ extern "C" int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B
 // =================================================================================================================
 #include "fcnet_tc_layout.cuh"
 #include "ppo_loss.cuh"
+#include "sgd_tail.cuh"
 
 namespace ddrl {
 
@@ -148,6 +149,7 @@ struct TcTrainArgs {
     float* grad_part;
     double* stat_part;
     int* status;
+    SgdTail tail;
 };
 
 // TMEM columns
@@ -294,9 +296,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
     const int NPs = (o.NP + 3) & ~3;
     float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
-    if (cr1 <= cr0) {   // no rows: zero partial, no tensor work
+    if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
         for (int i = tid; i < o.NP; i += TC_NT) gp[i] = 0.f;
         if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
+        if (a.tail.theta) {
+            __threadfence();
+            const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+                                           reinterpret_cast<float*>(sm + S.red));
+            if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
+        }
         return;
     }
 
@@ -514,9 +522,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
                 umma::fence_after_sync();
                 tc_gemm(tmem + TC_GW1 + 64 * b, sbase + S.H1[0], sbase + S.H1[1], TC_ROWS, true, sbase + S.X[0],
                         sbase + S.X[1], TC_ROWS, true, 64, KX, 8, !first, 3);
-                umma::mma_commit(mbar);
+                if (bi == 1) umma::mma_commit(mbar);   // first branch: committed together with the next branch's F1
             }
-            wait_mma();
+            if (bi == 1) wait_mma();
         }
         {   // both branches consumed the staged loss inputs: fetch the next tile's
             const int64_t nxt = row0 + TC_ROWS;
@@ -607,6 +615,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, TC_TMEM_COLS);
+    if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
+        __threadfence();
+        const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+                                       reinterpret_cast<float*>(sm + S.red));
+        if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
+    }
 }
 
 // flat theta -> tensor-core image (fp16 hi/lo of 256*w for the GEMM weights + fp32 biases)
@@ -667,7 +681,8 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
                                       const float* old_logp, const float* vf_preds, const float* adv, const float* vtarg,
                                       int P, int64_t R, int D, int A, int MB, const int32_t* mb_perm, int64_t perm_stride,
                                       const int32_t* step_ctr, const float* kl_coeff, const ddrl_ppo_hyper* hyper,
-                                      int ctas_per_policy, float* grad_part, double* stat_part, int* status, void* stream) {
+                                      int ctas_per_policy, float* grad_part, double* stat_part, int* status,
+                                      const ddrl_sgd_tail* tail, void* stream) {
     DDRL_REQUIRE(tc_img_p && obs && actions && old_logits && old_logp && vf_preds && adv && vtarg && kl_coeff && hyper &&
                      grad_part && P >= 1 && R >= 1 && MB >= 1 && ctas_per_policy >= 1,
                  DDRL_E_BADARG, "ppo_train_step_tc: null pointer or bad P/R/MB/ctas");
@@ -678,6 +693,19 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     a.old_logp = old_logp; a.vf_preds = vf_preds; a.adv = adv; a.vtarg = vtarg; a.R = R; a.D = D; a.A = A; a.MB = MB;
     a.mb_perm = mb_perm; a.perm_stride = perm_stride; a.step_ctr = step_ctr; a.kl_coeff = kl_coeff; a.hp = *hyper;
     a.grad_part = grad_part; a.stat_part = stat_part; a.status = status;
+    a.tail = SgdTail{};
+    if (tail) {
+        DDRL_REQUIRE(tail->theta && tail->m && tail->v && tail->beta_pow && tail->grad && tail->barrier_ws && tail->sq_ws,
+                     DDRL_E_BADARG, "ppo_train_step_tc: incomplete fused tail");
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        DDRL_REQUIRE(ctas_per_policy * P <= sms, DDRL_E_BADARG,
+                     "ppo_train_step_tc: fused tail needs all %d CTAs co-resident (%d SMs)", ctas_per_policy * P, sms);
+        a.tail = SgdTail{tail->theta, tail->m, tail->v, tail->beta_pow, tail->grad, tail->gnorm_out, tail->fcnet_img,
+                         (unsigned char*)tail->fcnet_tc_img, tail->step_stats, tail->step_ctr, tail->barrier_ws, tail->sq_ws,
+                         tail->lr, tail->beta1, tail->beta2, tail->eps, tail->grad_clip};
+    }
     const size_t smem = (size_t)tc_smem(D, A).total;
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);
     int rc;

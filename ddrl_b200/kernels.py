@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import DDRLError, PPOHyper
+from ._lib import DDRLError, PPOHyper, SgdTail
 
 HIDDEN = 64
 NSTAT = 8
@@ -161,7 +161,7 @@ def gather_rows(src: torch.Tensor, perm: torch.Tensor, dst: Optional[torch.Tenso
 
 def ppo_train_step(theta, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int,
                    mb_perm, step_ctr, kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part,
-                   ext_dlogits=None, ext_dvalue=None, img=None):
+                   ext_dlogits=None, ext_dvalue=None, img=None, tail: Optional[SgdTail] = None):
     lib = _lib.load()
     P, R, D = obs.shape
     f32 = torch.float32
@@ -173,7 +173,8 @@ def ppo_train_step(theta, obs, actions, old_logits, old_logp, vf_preds, adv, vta
         _p(ext_dlogits, f32, "ext_dlogits"), _p(ext_dvalue, f32, "ext_dvalue"), P, R, D, A, MB,
         _p(mb_perm, torch.int32, "mb_perm"), perm_stride, _p(step_ctr, torch.int32, "step_ctr"),
         _p(kl_coeff, f32, "kl_coeff"), C.byref(hyper) if hyper is not None else None, ctas_per_policy,
-        _p(grad_part, f32, "grad_part"), _p(stat_part, torch.float64, "stat_part"), _stream()), "ppo_train_step")
+        _p(grad_part, f32, "grad_part"), _p(stat_part, torch.float64, "stat_part"),
+        C.byref(tail) if tail is not None else None, _stream()), "ppo_train_step")
 
 
 def grad_reduce(grad_part, stat_part, P: int, G: int, NP: int, grad, step_stats=None, step_ctr=None):
@@ -340,7 +341,8 @@ def fcnet_tc_pack(theta: torch.Tensor, D: int, A: int, img: Optional[torch.Tenso
 
 
 def ppo_train_step_tc(tc_img, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int, mb_perm, step_ctr,
-                      kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part, status=None):
+                      kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part, status=None,
+                      tail: Optional[SgdTail] = None):
     P, R, D = obs.shape
     f32 = torch.float32
     perm_stride = mb_perm.shape[-1] if mb_perm is not None else 0
@@ -350,4 +352,30 @@ def ppo_train_step_tc(tc_img, obs, actions, old_logits, old_logp, vf_preds, adv,
         _p(vtarg, f32, "vtarg"), P, R, D, A, MB, _p(mb_perm, torch.int32, "mb_perm"), perm_stride,
         _p(step_ctr, torch.int32, "step_ctr"), _p(kl_coeff, f32, "kl_coeff"), C.byref(hyper), ctas_per_policy,
         _p(grad_part, f32, "grad_part"), _p(stat_part, torch.float64, "stat_part"), _p(status, torch.int32, "status"),
-        _stream()), "ppo_train_step_tc")
+        C.byref(tail) if tail is not None else None, _stream()), "ppo_train_step_tc")
+
+
+def obs_gather(obs_full: torch.Tensor, table: torch.Tensor, P: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """obs_full [S, Dfull] f32/f64, table [Ag, D] i32 -> [P, S*(Ag/P), D] f32 (agent a -> policy a // (Ag/P))."""
+    S, Dfull = obs_full.shape
+    Ag, D = table.shape
+    if out is None:
+        out = torch.empty(P, S * (Ag // P), D, dtype=torch.float32, device=obs_full.device)
+    if obs_full.dtype not in (torch.float32, torch.float64):
+        raise DDRLError("obs_gather: obs_full must be float32 or float64")
+    _lib.check(_lib.load().ddrl_obs_gather(_p(obs_full, None, "obs_full"), int(obs_full.dtype == torch.float64), S, Dfull,
+                                           _p(table, torch.int32, "table"), Ag, D, P, _p(out, torch.float32, "out"), _stream()),
+               "obs_gather")
+    return out
+
+
+def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, beta2, eps, grad_clip, gnorm_out=None, img=None,
+                  tc_img=None, step_stats=None, step_ctr=None) -> SgdTail:
+    """Fused grad-reduce + clip + Adam tail of the single-GPU SGD step (see ddrl_sgd_tail in ddrl_b200.h).
+    The caller keeps the tensors alive; barrier_ws must be zero-initialised uint32/int32 [4*P + 4]."""
+    f32 = torch.float32
+    return SgdTail(_p(theta, f32, "theta"), _p(m, f32, "m"), _p(v, f32, "v"), _p(beta_pow, f32, "beta_pow"),
+                   _p(grad, f32, "grad"), _p(gnorm_out, f32, "gnorm_out"), _p(img, f32, "img"), _p(tc_img, torch.uint8, "tc_img"),
+                   _p(step_stats, torch.float64, "step_stats"), _p(step_ctr, torch.int32, "step_ctr"),
+                   _p(barrier_ws, torch.int32, "barrier_ws"), _p(sq_ws, f32, "sq_ws"), float(lr), float(beta1), float(beta2),
+                   float(eps), float(grad_clip))

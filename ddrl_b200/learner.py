@@ -105,13 +105,14 @@ class FCNetLearner(_LearnerBase):
     """P grouped FCNet policies (obs dim D, action dim A, hiddens [64,64], tanh, separate value net)."""
 
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
-                 use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc"):
+                 use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True):
         """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
                  "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes."""
         super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
         if mode not in ("tc", "fp32"):
             raise DDRLError(f"mode must be 'tc' or 'fp32', got {mode!r}")
         self.mode = mode
+        self.fuse_tail = fuse_tail
         self.D, self.A = D, A
         dev = self.device
         self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -165,14 +166,25 @@ class FCNetLearner(_LearnerBase):
 
     # ---- one optimizer step (3 kernels [+ NCCL]) -----------------------------------------------------------
     def _sgd_step(self, b, MB, G, hyper, src):
+        # single GPU: the train kernel also reduces the partials, clips and applies Adam (fused tail: 1 launch per step);
+        # data parallel: 3 kernels with the NCCL all-reduce of the flat gradient between reduce and Adam
+        tail = None
+        if self.world == 1 and self.fuse_tail and G * self.P <= self.sms:
+            c = self.cfg
+            tail = K.make_sgd_tail(self.theta, self.m, self.v, self.beta_pow, self.grad, b["tail_bar"], b["tail_sq"], c.lr,
+                                   c.beta1, c.beta2, c.adam_eps, c.grad_clip, self.gnorm,
+                                   img=self.img if self.mode == "fp32" else None, tc_img=self.tc_img,
+                                   step_stats=b["step_stats"], step_ctr=self.step_ctr)
         if self.mode == "tc":
             K.ppo_train_step_tc(self.tc_img, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
                                 src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
-                                b["grad_part"], b["stat_part"], self.tc_status)
+                                b["grad_part"], b["stat_part"], self.tc_status, tail=tail)
         else:
             K.ppo_train_step(self.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
                              src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
-                             b["grad_part"], b["stat_part"], img=self.img)
+                             b["grad_part"], b["stat_part"], img=self.img, tail=tail)
+        if tail is not None:
+            return
         K.grad_reduce(b["grad_part"], b["stat_part"], self.P, G, self.NP, self.grad, b["step_stats"], self.step_ctr)
         if self.world > 1:
             self.dist.all_reduce(self.grad)
@@ -238,6 +250,8 @@ class FCNetLearner(_LearnerBase):
             b["grad_part"] = torch.empty(P, G, K.part_stride(self.NP), dtype=torch.float32, device=self.device)
             b["stat_part"] = torch.empty(P, G, K.NSTAT, dtype=torch.float64, device=self.device)
             b["step_stats"] = torch.zeros(steps, P, K.NSTAT, dtype=torch.float64, device=self.device)
+            b["tail_bar"] = torch.zeros(4 * P + 4, dtype=torch.int32, device=self.device)
+            b["tail_sq"] = torch.zeros(P, G, dtype=torch.float32, device=self.device)
             self._graph = None
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()

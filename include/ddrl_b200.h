@@ -104,6 +104,13 @@ int ddrl_fcnet_forward(const float* theta, const float* img, const float* obs, c
                        float clip, int P, int64_t R, int D, int A, float* obs_out, float* logits,
                        float* value, const float* eps, float* action, float* logp, void* stream);
 
+/* Replaces: distribute_observations / get_obs_indices (simulation_envs/quantruped_adaptor_multi_environment.py:124-136,
+ * simulation_envs/quantruped_v3.py:282-300): per-agent index gather of the full observation, batched on the device.
+ *   obs_full [S][Dfull] float32/float64 (S = env-steps), table [Ag][D] int32 (agents in agent_names order; data, not
+ *   hard-coded), P policies with Ag/P agents each -> out [P][S*(Ag/P)][D] float32, row = s*(Ag/P) + j. Bit-exact. */
+int ddrl_obs_gather(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag,
+                    int D, int P, float* out, void* stream);
+
 /* Replaces: compute_advantages + postprocess_ppo_gae (RLlib evaluation/postprocessing.py,
  * agents/ppo/ppo_tf_policy.py), selected by use_gae/gamma/lambda at
  * train_experiment_1_architecture_on_flat.py:119-120.  Reverse scan per column in float64:
@@ -145,13 +152,31 @@ typedef struct {
     float clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff, inv_global_mb;
 } ddrl_ppo_hyper;
 
+/* Optional fused tail of a single-GPU SGD step (pass NULL to get the partials only): the train kernel itself then
+ * performs what ddrl_grad_reduce + ddrl_clip_adam would do — a barrier among the CTAs of each policy, the fixed-order
+ * partial reduction (each CTA owns a slice of the parameters), the global-norm clip, TF1 Adam, the packed weight
+ * images, the beta powers and *step_ctr — with bit-identical results and two kernel launches fewer per step.
+ * Requires ctas_per_policy * P <= number of SMs (all CTAs co-resident).  Device pointers:
+ *   theta, m, v [P][NP]; beta_pow [P][2]; grad [P][NP] (out: reduced gradient); gnorm_out [P] or NULL;
+ *   fcnet_img / fcnet_tc_img or NULL; step_stats [steps][P][DDRL_NSTAT] or NULL; step_ctr;
+ *   barrier_ws: 4*P + 4 zero-initialised uint32 (re-armed by the kernel); sq_ws: P * ctas_per_policy floats. */
+typedef struct {
+    float *theta, *m, *v, *beta_pow, *grad, *gnorm_out, *fcnet_img;
+    void* fcnet_tc_img;
+    double* step_stats;
+    int32_t* step_ctr;
+    uint32_t* barrier_ws;
+    float* sq_ws;
+    float lr, beta1, beta2, eps, grad_clip;
+} ddrl_sgd_tail;
+
 int ddrl_ppo_train_step(const float* theta, const float* img, const float* obs, const float* actions,
                         const float* old_logits, const float* old_logp, const float* vf_preds,
                         const float* adv, const float* vtarg, const float* ext_dlogits,
                         const float* ext_dvalue, int P, int64_t R, int D, int A, int MB,
                         const int32_t* mb_perm, int64_t perm_stride, const int32_t* step_ctr,
                         const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas_per_policy,
-                        float* grad_part, double* stat_part, void* stream);
+                        float* grad_part, double* stat_part, const ddrl_sgd_tail* tail, void* stream);
 
 /* Stand-alone PPOLoss gradient w.r.t. the model outputs (same arithmetic as the fused kernel), for
  * models whose forward/backward are separate kernels (GraphNet):
@@ -226,7 +251,7 @@ int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupli
  * (grad_part [P][G][NPs], stat_part) and semantics as ddrl_ppo_train_step; the weights come from a tensor-core
  * image tc_img [P][ddrl_fcnet_tc_image_bytes(D, A)] built by ddrl_fcnet_tc_pack (or kept in step by
  * ddrl_clip_adam).  D <= 63, A in {1,2,4,8}.  *status (device int, may be NULL) receives OR-ed flags: 1 = an MMA
- * completion wait timed out; 2/4/8/16/32 = fp16 overflow (clamped) while splitting x / activations / dl / dz2 / dz1 —
+ * completion wait timed out; 64 = a fused-tail barrier timed out; 2/4/8/16/32 = fp16 overflow (clamped) while splitting x / activations / dl / dz2 / dz1 —
  * the result is then unreliable and the step should be redone with ddrl_ppo_train_step. */
 int ddrl_fcnet_tc_image_bytes(int D, int A);
 int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* tc_img, void* stream);
@@ -235,7 +260,8 @@ int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* ac
                            const float* adv, const float* vtarg, int P, int64_t R, int D, int A, int MB,
                            const int32_t* mb_perm, int64_t perm_stride, const int32_t* step_ctr,
                            const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas_per_policy,
-                           float* grad_part, double* stat_part, int* status, void* stream);
+                           float* grad_part, double* stat_part, int* status, const ddrl_sgd_tail* tail,
+                           void* stream);
 
 /* Diagnostic: one tcgen05 (UMMA) GEMM through TMEM with the chunked shared-memory operand layout the tensor-core
  * training step uses (csrc/umma.cuh): D[m][n] = sum_k A(m,k) B(n,k), m < M (64 or 128), A(m,k) = A[m][k] (a_mn = 0, K-major) or
