@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"], help="SGD-step kernel: tcgen05 split-fp16 or FP32 FMA")
+    ap.add_argument("--tc-variant", type=int, default=0, choices=[0, 1, 2],
+                    help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
     ap.add_argument("--gn-epochs", type=int, default=2)
@@ -254,6 +256,8 @@ def main():
     MB_local = R // nb
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=MB_local * world)
 
+    if args.tc_variant:
+        K.tc_set_variant(args.tc_variant)
     import oracle.ddrl_oracle as O  # Glorot init values only (host RNG); no oracle compute in the timed path
     gen = torch.Generator().manual_seed(1234)
     theta0 = torch.stack([O.fcnet_init(D, 2 * A, gen) for _ in range(P)])
@@ -386,10 +390,19 @@ def main():
             "cpu_baseline": cpu,
             "flops_per_agent_step": flops_per_agent_step(D, A, E),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # release the captured graph (it holds NCCL work) before tearing the communicator down, and never let the
+        # teardown hang the job: the result line is already out
+        L._graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=15.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "ddrl_dg_sample": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p, c_stream]),
     "ddrl_leg_coupling": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int, c_stream]),
     "ddrl_fcnet_tc_image_bytes": (C.c_int, [C.c_int, C.c_int]),
+    "ddrl_tc_set_variant": (C.c_int, [C.c_int]),
     "ddrl_fcnet_tc_pack": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_stream]),
     "ddrl_ppo_train_step_tc": (C.c_int, [C.c_void_p] + [c_f32p] * 7 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
                                                                      C.c_int64, c_i32p, c_f32p, C.POINTER(PPOHyper), C.c_int,

@@ -59,6 +59,37 @@ __host__ __device__ inline TcSmem tc_smem(int D, int A) {
     return s;
 }
 
+
+// ---- "ping-pong" kernel (tc2.cu): both branches resident, so the tensor core works on one branch while the CTA runs
+// the other branch's epilogue.  Needs H1/H2 of BOTH branches (128 KB) -> only for KX <= 32 (D <= 30) and small heads.
+// The loss-gradient operand DL[b] reuses the fp32 staging area of the observations (dead once X has been split).
+struct Tc2Smem {
+    int X[2], H1[2][2], H2[2][2], DL[2][2], xraw, pf, red, bar, total;
+};
+__host__ __device__ inline Tc2Smem tc2_smem(int D, int A) {
+    const int KX = tc_kx(D);
+    Tc2Smem s;
+    int p = tc_img(D, A).bytes;
+    for (int h = 0; h < 2; ++h) { s.X[h] = p; p += TC_ROWS * KX * 2; }
+    for (int b = 0; b < 2; ++b)
+        for (int h = 0; h < 2; ++h) { s.H1[b][h] = p; p += TC_ROWS * 64 * 2; }
+    for (int b = 0; b < 2; ++b)
+        for (int h = 0; h < 2; ++h) { s.H2[b][h] = p; p += TC_ROWS * 64 * 2; }
+    const int dl_bytes = 4 * TC_ROWS * TC_NO * 2, x_bytes = ((TC_ROWS * D * 4) + 15) & ~15;
+    s.xraw = p;
+    for (int b = 0; b < 2; ++b)
+        for (int h = 0; h < 2; ++h) s.DL[b][h] = p + (2 * b + h) * TC_ROWS * TC_NO * 2;
+    p += dl_bytes > x_bytes ? dl_bytes : x_bytes;
+    s.pf = p;    p += ((TC_ROWS * (3 * A + 4) * 4) + 15) & ~15;
+    s.red = p;   p += 8 * 16 * 8;    // [8 loss warps][16] doubles
+    s.bar = p;   p += 64;            // 2 mbarriers, tmem slot, 2 gradient scales
+    s.total = p;
+    return s;
+}
+__host__ __device__ inline bool tc2_eligible(int D, int A) {
+    return tc_kx(D) <= 32 && tc2_smem(D, A).total <= 227 * 1024;
+}
+
 // Where flat parameter j lives in the image: fp16 pair (byte offsets of hi and lo, f16 = true) or one float.
 __host__ __device__ inline void tc_img_pos(const TcImg& L, const FcOffsets& o, int D, int A, int j, bool& f16, int& p0, int& p1) {
     const int A2 = 2 * A;

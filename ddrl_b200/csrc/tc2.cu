@@ -1,0 +1,487 @@
+// Tensor-core FCNet training step, "ping-pong" schedule (sm_100a, tcgen05 + TMEM).
+//
+// Same contract, operand layouts, scales and arithmetic as fcnet_train_tc_kernel (tc.cu) — one minibatch of all policies,
+// fused forward + PPO loss + backward, per-CTA partial gradients in flat checkpoint order — but BOTH branches of the
+// network (policy MLP and value MLP) are resident at once and software-pipelined against each other:
+//
+//     issue F1(pol), F1(val) | wait pol -> tanh epilogue(pol) -> issue F2(pol) | wait val -> tanh epilogue(val) -> issue F2(val) | ...
+//
+// While the 16 warps run one branch's epilogue (TMEM -> tanh / (1-h^2) -> fp16 hi/lo -> shared memory), the tensor core
+// executes the other branch's GEMMs, so the MMA latency that the branch-sequential kernel exposed 12 times per tile is
+// hidden; each branch has its own accumulator columns and its own mbarrier.  The two PPO-loss halves (policy part on
+// warps 0-3, value part on warps 4-7) run concurrently.  MMAs are issued by lane 0 of the LAST warp, which carries no
+// loss work.  Cost: H1/H2 of both branches live in shared memory (128 KB), so the kernel serves KX <= 32 (D <= 30) with
+// 2A+... small heads (tc2_eligible); larger observations keep the branch-sequential kernel.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace ddrl {
+
+// TMEM columns: per-branch forward/backward accumulator, head outputs, and the weight-gradient accumulators
+constexpr int T2_DACC = 0, T2_HOUT = 128, T2_GW2 = 160, T2_GW1 = 288, T2_GB2 = 352, T2_GWH = 384, T2_TMEM_COLS = 512;
+constexpr int T2_ISSUER = TC_NT - 32;   // lane 0 of warp 15
+
+__device__ __forceinline__ void t2_split2(float x0, float x1, uint32_t& h, uint32_t& l) {
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    h = *reinterpret_cast<const uint32_t*>(&hh);
+    l = *reinterpret_cast<const uint32_t*>(&ll);
+}
+// 8 floats (times a power-of-two scale) -> fp16 hi / lo chunks, no range check (caller knows |v * scale| < 65504)
+__device__ __forceinline__ void t2_split8(const float* v, float scale, uint4& hi, uint4& lo) {
+    t2_split2(v[0] * scale, v[1] * scale, hi.x, lo.x);
+    t2_split2(v[2] * scale, v[3] * scale, hi.y, lo.y);
+    t2_split2(v[4] * scale, v[5] * scale, hi.z, lo.z);
+    t2_split2(v[6] * scale, v[7] * scale, hi.w, lo.w);
+}
+
+// Forward epilogue of this thread's 16 columns: act = tanh(acc * inv_in + bias) -> fp16 hi/lo (x TC_SH), chunked [128][64].
+__device__ __noinline__ void t2_epi_tanh(uint32_t taddr, const float* bias, float inv_in, unsigned char* dhi, unsigned char* dlo,
+                                         int row, int cq) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[8];
+        umma::tmem_ld8(taddr + 8 * c, v);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
+        v[0] = tanhf(fmaf(v[0], inv_in, b0.x)); v[1] = tanhf(fmaf(v[1], inv_in, b0.y));
+        v[2] = tanhf(fmaf(v[2], inv_in, b0.z)); v[3] = tanhf(fmaf(v[3], inv_in, b0.w));
+        v[4] = tanhf(fmaf(v[4], inv_in, b1.x)); v[5] = tanhf(fmaf(v[5], inv_in, b1.y));
+        v[6] = tanhf(fmaf(v[6], inv_in, b1.z)); v[7] = tanhf(fmaf(v[7], inv_in, b1.w));
+        uint4 hi, lo;
+        t2_split8(v, TC_SH, hi, lo);          // |tanh| <= 1: always inside the fp16 range
+        const int off = ((2 * cq + c) * TC_ROWS + row) * 16;
+        *reinterpret_cast<uint4*>(dhi + off) = hi;
+        *reinterpret_cast<uint4*>(dlo + off) = lo;
+    }
+}
+
+// Backward epilogue: g = acc * inv_in * (1 - h^2), h re-read from the buffer it then overwrites (fp16 hi/lo x out_scale).
+// Returns true if |g * out_scale| left the fp16 range.
+__device__ __noinline__ bool t2_epi_grad(uint32_t taddr, float inv_in, float out_scale, unsigned char* bhi, unsigned char* blo,
+                                         int row, int cq) {
+    float mx = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[8], h[8];
+        umma::tmem_ld8(taddr + 8 * c, v);
+        const int off = ((2 * cq + c) * TC_ROWS + row) * 16;
+        tc_join8(*reinterpret_cast<const uint4*>(bhi + off), *reinterpret_cast<const uint4*>(blo + off), 1.f / TC_SH, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = v[j] * inv_in * (1.f - h[j] * h[j]);
+            mx = fmaxf(mx, fabsf(v[j]));
+        }
+        uint4 hi, lo;
+        t2_split8(v, out_scale, hi, lo);
+        *reinterpret_cast<uint4*>(bhi + off) = hi;
+        *reinterpret_cast<uint4*>(blo + off) = lo;
+    }
+    return !(mx * out_scale <= 60000.f);
+}
+
+template <int A>
+__global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrainArgs a) {
+    constexpr int A2 = 2 * A;
+    extern __shared__ __align__(1024) unsigned char sm[];
+    const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
+    const int D = a.D, KX = tc_kx(D);
+    const TcImg I = tc_img(D, A);
+    const Tc2Smem S = tc2_smem(D, A);
+    const FcOffsets o = fc_offsets(D, A);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S.bar);          // [2]: one per branch
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + S.bar + 16);
+    float* sgs = reinterpret_cast<float*>(sm + S.bar + 24);             // [2]: per-branch gradient scale
+    const uint32_t sbase = umma::smem_u32(sm);
+
+    const int step = a.step_ctr ? *a.step_ctr : 0;
+    const int mb = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step] : step;
+    const int64_t mb0 = (int64_t)mb * a.MB;
+    const int64_t mb1 = min(mb0 + a.MB, a.R);
+    const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
+    const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
+    const int NPs = (o.NP + 3) & ~3;
+    float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
+        for (int i = tid; i < o.NP; i += TC_NT) gp[i] = 0.f;
+        if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
+        if (a.tail.theta) {
+            __threadfence();
+            const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+                                           reinterpret_cast<float*>(sm + S.red));
+            if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
+        }
+        return;
+    }
+
+    const float* obs_p = a.obs + (int64_t)p * a.R * D;
+    float* xraw = reinterpret_cast<float*>(sm + S.xraw);
+    float* pf = reinterpret_cast<float*>(sm + S.pf);
+    const float* b1c = reinterpret_cast<const float*>(sm + I.b1c);
+    const float* b2c = reinterpret_cast<const float*>(sm + I.b2c);
+    const float* sbo = reinterpret_cast<const float*>(sm + I.bo);
+    const float* sbvo = reinterpret_cast<const float*>(sm + I.bvo);
+
+    auto prefetch_x = [&](int64_t r0, int n) {
+        for (int i = tid; i < n * D; i += TC_NT) tc_cp4(xraw + i, obs_p + r0 * D + i);
+    };
+    auto prefetch_loss = [&](int64_t r0, int n) {
+        const int64_t g0 = (int64_t)p * a.R + r0;
+        float* pa = pf;
+        float* po = pa + TC_ROWS * A;
+        float* ps = po + TC_ROWS * A2;
+        for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, a.actions + g0 * A + i);
+        for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+        for (int i = tid; i < n; i += TC_NT) {
+            tc_cp4(ps + i, a.old_logp + g0 + i);
+            tc_cp4(ps + TC_ROWS + i, a.vf_preds + g0 + i);
+            tc_cp4(ps + 2 * TC_ROWS + i, a.adv + g0 + i);
+            tc_cp4(ps + 3 * TC_ROWS + i, a.vtarg + g0 + i);
+        }
+    };
+
+    // ---- setup: TMEM, mbarriers, weights image, first tile's inputs ------------------------------------------------
+    if (warp == 0) umma::tmem_alloc(tslot, T2_TMEM_COLS);
+    if (tid == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(mbar + 1, 1); umma::fence_mbar_init(); }
+    {
+        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+        const int n0 = (int)min((int64_t)TC_ROWS, cr1 - cr0);
+        prefetch_x(cr0, n0);
+        prefetch_loss(cr0, n0);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    uint32_t ph0 = 0, ph1 = 0;
+    bool ok = true, first = true;
+    int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 8 = dl, 16 = dz2, 32 = dz1
+    const float klc = a.kl_coeff[p];
+    // loss warps: 0-3 policy part (s0 = -surr, s1 = KL, s2 = entropy), 4-7 value part (s0 = vf, s1..4 = R, R^2, R-v, (R-v)^2)
+    double st[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) st[i] = 0.0;
+    float gbh[A2];   // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0]
+#pragma unroll
+    for (int i = 0; i < A2; ++i) gbh[i] = 0.f;
+    const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
+
+    auto wait_b = [&](int b) {
+        if (b == 0) { ok = umma::mbar_wait(mbar, ph0) && ok; ph0 ^= 1; }
+        else        { ok = umma::mbar_wait(mbar + 1, ph1) && ok; ph1 ^= 1; }
+        umma::fence_after_sync();
+    };
+    auto publish = [&]() {   // generic smem writes -> async proxy, TMEM reads retired, then CTA barrier
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
+    const uint32_t Xh = sbase + S.X[0], Xl = sbase + S.X[1];
+
+#pragma unroll 1
+    for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
+        const int nrows = (int)min((int64_t)TC_ROWS, cr1 - row0);
+        if (!first) { wait_b(0); wait_b(1); }       // previous tile's B5 still reads X and dZ1
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        // ---- x: fp32 staging -> fp16 hi/lo chunked [128][KX], constant 1 in column D, zero rows beyond nrows ----------
+        {
+            const int r = tid & (TC_ROWS - 1);
+#pragma unroll 1
+            for (int c8 = tid >> 7; c8 < (KX >> 3); c8 += 4) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int d = c8 * 8 + e;
+                    v[e] = (r < nrows) ? (d < D ? xraw[r * D + d] : (d == D ? 1.f : 0.f)) : 0.f;
+                }
+                uint4 hi, lo;
+                ovf |= tc_split8(v, TC_SX, hi, lo) ? 2 : 0;
+                *reinterpret_cast<uint4*>(sm + S.X[0] + (c8 * TC_ROWS + r) * 16) = hi;
+                *reinterpret_cast<uint4*>(sm + S.X[1] + (c8 * TC_ROWS + r) * 16) = lo;
+            }
+        }
+        publish();
+        // ---- F1 (both branches): Dacc_b = X * W1b^T --------------------------------------------------------------
+        if (tid == T2_ISSUER) {
+            umma::fence_after_sync();
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                tc_gemm(tmem + T2_DACC + 64 * b, Xh, Xl, TC_ROWS, false, sbase + I.W1[b][0], sbase + I.W1[b][1], 64, false,
+                        128, 64, KX >> 4, false, 3);
+                umma::mma_commit(mbar + b);
+            }
+        }
+        // ---- tanh epilogue 1 -> F2: Dacc_b = H1_b * W2b -------------------------------------------------------------
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            wait_b(b);
+            t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b1c + b * 64 + 16 * cq, 1.f / (TC_SX * TC_SW),
+                        sm + S.H1[b][0], sm + S.H1[b][1], row, cq);
+            publish();
+            if (tid == T2_ISSUER) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + T2_DACC + 64 * b, sbase + S.H1[b][0], sbase + S.H1[b][1], TC_ROWS, false, sbase + I.W2[b][0],
+                        sbase + I.W2[b][1], 64, true, 128, 64, 4, false, 3);
+                umma::mma_commit(mbar + b);
+            }
+        }
+        // ---- tanh epilogue 2 -> heads: Hout_b[128][16] = H2_b * WoT_b^T ------------------------------------------------
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            wait_b(b);
+            t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b2c + b * 64 + 16 * cq, 1.f / (TC_SH * TC_SW),
+                        sm + S.H2[b][0], sm + S.H2[b][1], row, cq);
+            publish();
+            if (tid == T2_ISSUER) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + T2_HOUT + 16 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, false, sbase + I.WoT[b][0],
+                        sbase + I.WoT[b][1], TC_NO, false, 128, TC_NO, 4, false, 3);
+                umma::mma_commit(mbar + b);
+            }
+        }
+        // ---- PPO loss: warps 0-3 policy part, warps 4-7 value part -> DL_b (fp16 hi/lo x branch scale, chunked [128][16]) ----
+        wait_b(0);
+        wait_b(1);
+        if (cq < 2) {
+            const int b = cq;
+            float out[16], dl[16];
+            umma::tmem_ld16(tmem + tlane + T2_HOUT + 16 * b, out);
+            double s[DDRL_NSTAT];
+#pragma unroll
+            for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dl[i] = 0.f;
+            if (row < nrows) {
+                const float* pa = pf;
+                const float* po = pa + TC_ROWS * A;
+                const float* ps = po + TC_ROWS * A2;
+                if (b == 0) {
+                    float lg[A2];
+#pragma unroll
+                    for (int oo = 0; oo < A2; ++oo) lg[oo] = fmaf(out[oo], 1.f / (TC_SH * TC_SW), sbo[oo]);
+                    ppo_row_policy(lg, A, pa + row * A, po + row * A2, ps[row], ps[2 * TC_ROWS + row], klc,
+                                   a.hp.clip_param, a.hp.entropy_coeff, 1.f, dl, s);
+#pragma unroll
+                    for (int oo = 0; oo < A2; ++oo) gbh[oo] += dl[oo];
+                    st[0] += s[0]; st[1] += s[1]; st[2] += s[3];
+                } else {
+                    const float val = fmaf(out[0], 1.f / (TC_SH * TC_SW), sbvo[0]);
+                    dl[0] = ppo_row_value(val, ps[TC_ROWS + row], ps[3 * TC_ROWS + row], a.hp.vf_clip_param,
+                                          a.hp.vf_loss_coeff, 1.f, s);
+                    gbh[0] += dl[0];
+                    st[0] += s[2]; st[1] += s[4]; st[2] += s[5]; st[3] += s[6]; st[4] += s[7];
+                }
+            }
+            if (first) {   // per-branch gradient scale of this CTA: power of two with max|dl| * scale ~ TC_GTARGET
+                float mx = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fabsf(dl[i]));
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                float* smx = reinterpret_cast<float*>(sm + S.red);      // [8 warps]
+                if (lane == 0) smx[warp] = mx;
+                if (b == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four loss warps of this branch only
+                else        asm volatile("bar.sync 2, 128;" ::: "memory");
+                mx = fmaxf(fmaxf(smx[4 * b], smx[4 * b + 1]), fmaxf(smx[4 * b + 2], smx[4 * b + 3]));
+                int e = 0;
+                if (mx > 0.f && mx < 3.0e38f) e = (int)floorf(log2f(TC_GTARGET / mx));
+                e = max(-20, min(20, e));
+                if (q == 0 && lane == 0) sgs[b] = exp2f((float)e);
+                if (b == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else        asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
+            const float sg_l = sgs[b];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint4 hi, lo;
+                ovf |= tc_split8(&dl[8 * c], sg_l, hi, lo) ? 8 : 0;
+                *reinterpret_cast<uint4*>(sm + S.DL[b][0] + (c * TC_ROWS + row) * 16) = hi;
+                *reinterpret_cast<uint4*>(sm + S.DL[b][1] + (c * TC_ROWS + row) * 16) = lo;
+            }
+        }
+        publish();
+        {   // both branches consumed the staged loss inputs: fetch the next tile's
+            const int64_t nxt = row0 + TC_ROWS;
+            if (nxt < cr1) prefetch_loss(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
+        }
+        const float sg0 = sgs[0], sg1 = sgs[1];
+        // ---- B1: gWh_b[k][o] (+)= H2_b^T DL_b ;  dz2-pre: Dacc_b = DL_b * WoT_b (B MN-major) ---------------------------
+        if (tid == T2_ISSUER) {
+            umma::fence_after_sync();
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                tc_gemm(tmem + T2_GWH + 16 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, true, sbase + S.DL[b][0],
+                        sbase + S.DL[b][1], TC_ROWS, true, 64, 16, 8, !first, 3);
+                tc_gemm(tmem + T2_DACC + 64 * b, sbase + S.DL[b][0], sbase + S.DL[b][1], TC_ROWS, false, sbase + I.WoT[b][0],
+                        sbase + I.WoT[b][1], TC_NO, true, 128, 64, 1, false, 3);
+                umma::mma_commit(mbar + b);
+            }
+        }
+        // ---- dz2 epilogue -> B3: gW2_b (+)= H1_b^T dZ2_b; gb2_b (+)= dZ2_b^T 1;  B4: Dacc_b = dZ2_b * W2b^T -------------
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            const float sg = b ? sg1 : sg0;
+            wait_b(b);      // B1 has consumed H2_b; dz2 = pre * (1 - h2^2) overwrites it
+            ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H2[b][0],
+                               sm + S.H2[b][1], row, cq) ? 16 : 0;
+            publish();
+            if (tid == T2_ISSUER) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + T2_GW2 + 64 * b, sbase + S.H1[b][0], sbase + S.H1[b][1], TC_ROWS, true, sbase + S.H2[b][0],
+                        sbase + S.H2[b][1], TC_ROWS, true, 64, 64, 8, !first, 3);
+                tc_gemm(tmem + T2_GB2 + 16 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, true,
+                        Xh + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64, 16, 8, !first, 2);
+                tc_gemm(tmem + T2_DACC + 64 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, false, sbase + I.W2[b][0],
+                        sbase + I.W2[b][1], 64, false, 128, 64, 4, false, 3);
+                umma::mma_commit(mbar + b);
+            }
+        }
+        {   // both B1 are complete (DL dead): stream the next tile's observations into the shared staging area
+            const int64_t nxt = row0 + TC_ROWS;
+            if (nxt < cr1) prefetch_x(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+        // ---- dz1 epilogue -> B5: gW1_b[c][d] (+)= dZ1_b^T X   (column D of X is the constant 1 -> bias gradient) --------
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            const float sg = b ? sg1 : sg0;
+            wait_b(b);      // B3 has consumed H1_b; dz1 = (dz2 W2^T) * (1 - h1^2) overwrites it
+            ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H1[b][0],
+                               sm + S.H1[b][1], row, cq) ? 32 : 0;
+            publish();
+            if (tid == T2_ISSUER) {
+                umma::fence_after_sync();
+                tc_gemm(tmem + T2_GW1 + 32 * b, sbase + S.H1[b][0], sbase + S.H1[b][1], TC_ROWS, true, Xh, Xl, TC_ROWS, true,
+                        64, KX, 8, !first, 3);
+                umma::mma_commit(mbar + b);
+            }
+        }
+        first = false;
+    }
+    wait_b(0);
+    wait_b(1);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+    // ---- write-out: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
+    const float inv = a.hp.inv_global_mb;
+    __syncthreads();
+    const int m = 16 * q + lane;            // valid for lane < 16
+    const bool mine = lane < 16;
+#pragma unroll 1
+    for (int b = 0; b < 2; ++b) {
+        float v[8];
+        const float sgb = sgs[b];
+        const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {        // gW2_b: this warp's 16 columns
+            umma::tmem_ld8(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8 * c, v);
+            if (mine) {
+                float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq + 8 * c);
+                dst[0] = make_float4(v[0] * inv_gw2, v[1] * inv_gw2, v[2] * inv_gw2, v[3] * inv_gw2);
+                dst[1] = make_float4(v[4] * inv_gw2, v[5] * inv_gw2, v[6] * inv_gw2, v[7] * inv_gw2);
+            }
+        }
+#pragma unroll 1
+        for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
+            umma::tmem_ld8(tmem + tlane + T2_GW1 + 32 * b + 8 * c8, v);
+            if (mine) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int d = 8 * c8 + j;
+                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = v[j] * inv_gw1;
+                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = v[j] * inv_gw1;
+                }
+            }
+        }
+        if (cq == 2) {                                   // gb2_b: column of the constant-1 pad inside its 16-wide window
+            umma::tmem_ld8(tmem + tlane + T2_GB2 + 16 * b + (((D - 8 * ch0) >> 3) << 3), v);
+            const int jsel = (D - 8 * ch0) & 7;
+            const float g = jsel == 0 ? v[0] : jsel == 1 ? v[1] : jsel == 2 ? v[2] : jsel == 3 ? v[3] : jsel == 4 ? v[4]
+                          : jsel == 5 ? v[5] : jsel == 6 ? v[6] : v[7];
+            if (mine) gp[(b ? o.bv2 : o.b2) + m] = g * inv_gw1;
+        }
+        if (cq == 3) {                                   // gWh_b[k = m][o]
+            float w[16];
+            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * b, w);
+            if (mine) {
+                if (b == 0) {
+#pragma unroll
+                    for (int oo = 0; oo < A2; ++oo) gp[o.Wo + m * A2 + oo] = w[oo] * inv_gwh;
+                } else {
+                    gp[o.Wvo + m] = w[0] * inv_gwh;
+                }
+            }
+        }
+    }
+    // head bias gradients and stats: reduce over the loss threads (warps 0..3 policy, 4..7 value), fixed order
+    __syncthreads();
+    double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][16]
+    if (cq < 2) {
+#pragma unroll
+        for (int i = 0; i < A2; ++i) {
+            const float s = warp_sum(gbh[i]);
+            if (lane == 0 && 8 + i < 16) redd[warp * 16 + 8 + i] = (double)s;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double s = warp_sum(st[i]);
+            if (lane == 0) redd[warp * 16 + i] = s;
+        }
+    }
+    __syncthreads();
+    auto sum4 = [&](int w0, int i) { return (redd[w0 * 16 + i] + redd[(w0 + 1) * 16 + i]) + (redd[(w0 + 2) * 16 + i] + redd[(w0 + 3) * 16 + i]); };
+    if (tid < A2) gp[o.bo + tid] = (float)sum4(0, 8 + tid) * inv;
+    if (tid == A2) gp[o.bvo] = (float)sum4(4, 8) * inv;
+    if (tid < DDRL_NSTAT && a.stat_part) {
+        // stat slots (ddrl_b200.h): 0 -surr, 1 KL, 2 vf, 3 entropy, 4 R, 5 R^2, 6 R-v, 7 (R-v)^2
+        const int w0 = (tid == 0 || tid == 1 || tid == 3) ? 0 : 4;
+        const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
+        a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sum4(w0, idx);
+    }
+    if (a.status) {
+        if (tid == 0 && !ok) atomicOr(a.status, 1);
+        if (ovf) atomicOr(a.status, ovf);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, T2_TMEM_COLS);
+    if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
+        __threadfence();
+        const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+                                       reinterpret_cast<float*>(sm + S.red));
+        if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
+    }
+}
+
+template <int A>
+static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(fcnet_train_tc2_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+            return DDRL_E_CUDA;
+        }
+        attr = true;
+    }
+    fcnet_train_tc2_kernel<A><<<dim3(G, P), TC_NT, smem, st>>>(a);
+    return DDRL_OK;
+}
+
+int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
+    const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
+    switch (a.A) {
+        case 1: return launch_tc2_t<1>(a, P, G, smem, st);
+        case 2: return launch_tc2_t<2>(a, P, G, smem, st);
+        case 4: return launch_tc2_t<4>(a, P, G, smem, st);
+        default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4}"); return DDRL_E_UNSUPPORTED_SHAPE;
+    }
+}
+
+}  // namespace ddrl

@@ -1,0 +1,111 @@
+// Shared pieces of the tensor-core (tcgen05) FCNet training kernels: launch arguments, operand scales, the split-fp16
+// GEMM issue loop and the fp32 <-> (hi, lo) fp16 converters.  See the header comment of the kernel in tc.cu.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "fcnet_tc_layout.cuh"
+#include "ppo_loss.cuh"
+#include "sgd_tail.cuh"
+#include "umma.cuh"
+
+namespace ddrl {
+
+struct TcTrainArgs {
+    const unsigned char* img;
+    const float *obs, *actions, *old_logits, *old_logp, *vf_preds, *adv, *vtarg;
+    int64_t R;
+    int D, A, MB;
+    const int32_t* mb_perm;
+    int64_t perm_stride;
+    const int32_t* step_ctr;
+    const float* kl_coeff;
+    ddrl_ppo_hyper hp;
+    float* grad_part;
+    double* stat_part;
+    int* status;
+    SgdTail tail;
+};
+
+// ping-pong variant (tc2.cu); A in {1,2,4}, tc2_eligible(D, A)
+int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st);
+
+// Power-of-two operand scales (see header comment).  What matters is the absolute error relative to the tensor's
+// scale: entries too small for a normal lo half lose at most 2^-25/scale, negligible next to the entries that dominate.
+constexpr float TC_SX = 16.f;      // observations (|x| <= 3750)
+constexpr float TC_SH = 4096.f;    // tanh activations (|h| <= 1)
+constexpr float TC_SW = 256.f;     // weights (|w| <= 234)
+// Loss gradients (dl and the dz2 / dz1 derived from it) have no a-priori scale (it follows |v - R| and the
+// advantages), so each branch picks ONE power-of-two scale per CTA from the first tile: max|dl| * scale ~ 256, which
+// leaves a factor 234 of headroom for |dz| to exceed |dl| before the fp16 range is hit (then: flagged, never silent).
+constexpr float TC_GTARGET = 256.f;
+
+__device__ __forceinline__ void tc_cp16(unsigned char* smem_dst, const unsigned char* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void tc_cp4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc));
+}
+
+// D[tmem] (+)= A * B^T with fp16 (hi, lo) operands: products (hi,hi) (hi,lo) (lo,hi); nprod == 2 -> (hi,hi) (lo,hi).
+// a_rows / b_rows = row count of the chunked buffers; *_mn selects the MN-major view.  One thread calls this.
+__device__ __forceinline__ void tc_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
+                                        uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate, int nprod) {
+    const uint32_t idesc = umma::idesc_f16(M, N, a_mn, b_mn);
+    // descriptors advance along K by adding to the 14-bit start-address field (16-byte units; smem < 256 KB, no carry)
+    const uint64_t astep = a_mn ? 16u : (uint64_t)(2 * a_rows);
+    const uint64_t bstep = b_mn ? 16u : (uint64_t)(2 * b_rows);
+    const uint64_t ah = a_mn ? umma::desc_mnmajor(a_hi, a_rows) : umma::desc_kmajor(a_hi, a_rows);
+    const uint64_t al = a_mn ? umma::desc_mnmajor(a_lo, a_rows) : umma::desc_kmajor(a_lo, a_rows);
+    const uint64_t bh = b_mn ? umma::desc_mnmajor(b_hi, b_rows) : umma::desc_kmajor(b_hi, b_rows);
+    const uint64_t bl = b_mn ? umma::desc_mnmajor(b_lo, b_rows) : umma::desc_kmajor(b_lo, b_rows);
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
+    for (int pr = 0; pr < nprod; ++pr) {
+        uint64_t ad = (pr == 2 || (nprod == 2 && pr == 1)) ? al : ah;
+        uint64_t bd = (nprod == 3 && pr == 1) ? bl : bh;
+#pragma unroll 4
+        for (int ks = 0; ks < nk; ++ks) {
+            umma::mma_f16(d_tmem, ad, bd, idesc, acc != 0u);
+            acc = 1u;
+            ad += astep;
+            bd += bstep;
+        }
+    }
+}
+
+// split 8 floats (times a power-of-two scale) into fp16 hi / lo 16-byte chunks; returns true on fp16 overflow
+__device__ __forceinline__ bool tc_split8(const float* v, float scale, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+    bool ovf = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float x0 = v[2 * i] * scale, x1 = v[2 * i + 1] * scale;
+        ovf = ovf || !(fabsf(x0) <= 60000.f) || !(fabsf(x1) <= 60000.f);
+        x0 = fminf(fmaxf(x0, -60000.f), 60000.f);
+        x1 = fminf(fmaxf(x1, -60000.f), 60000.f);
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        const __half2 hh = __halves2half2(h0, h1);
+        const __half2 ll = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    return ovf;
+}
+
+// hi + lo chunk -> 8 floats (times inv_scale)
+__device__ __forceinline__ void tc_join8(const uint4& hi, const uint4& lo, float inv_scale, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&hi);
+    const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fh = __half22float2(h[i]), fl = __half22float2(l[i]);
+        v[2 * i] = (fh.x + fl.x) * inv_scale;
+        v[2 * i + 1] = (fh.y + fl.y) * inv_scale;
+    }
+}
+
+
+}  // namespace ddrl

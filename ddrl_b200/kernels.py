@@ -340,6 +340,11 @@ def fcnet_tc_pack(theta: torch.Tensor, D: int, A: int, img: Optional[torch.Tenso
     return img
 
 
+def tc_set_variant(variant: int) -> None:
+    """0 = automatic (ping-pong kernel when D <= 30 and A <= 4), 1 = branch-sequential kernel, 2 = ping-pong kernel."""
+    _lib.check(_lib.load().ddrl_tc_set_variant(int(variant)), "tc_set_variant")
+
+
 def ppo_train_step_tc(tc_img, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int, mb_perm, step_ctr,
                       kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part, status=None,
                       tail: Optional[SgdTail] = None):

@@ -254,6 +254,10 @@ int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupli
  * completion wait timed out; 64 = a fused-tail barrier timed out; 2/4/8/16/32 = fp16 overflow (clamped) while splitting x / activations / dl / dz2 / dz1 —
  * the result is then unreliable and the step should be redone with ddrl_ppo_train_step. */
 int ddrl_fcnet_tc_image_bytes(int D, int A);
+/* Two schedules of the same arithmetic exist: 1 = branch-sequential (any D <= 63), 2 = "ping-pong" (both branches
+ * resident, the tensor core runs one branch while the CTA runs the other's epilogue; D <= 30, A <= 4).
+ * 0 (default) picks ping-pong whenever the shape allows it.  Process-wide; meant for tests and A/B timing. */
+int ddrl_tc_set_variant(int variant);
 int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* tc_img, void* stream);
 int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* actions,
                            const float* old_logits, const float* old_logp, const float* vf_preds,

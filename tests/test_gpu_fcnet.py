@@ -133,9 +133,13 @@ def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda", tc=False):
     if tc:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         img = K.fcnet_tc_pack(t["theta"], b["D"], A)
-        K.ppo_train_step_tc(img, t["obs"], t["actions"], t["old_logits"], t["old_logp"], t["vf_preds"], t["adv"],
-                            t["vtarg"], A, MB, perm, ctr, klc, hyper, G, gp, sp, status)
-        assert int(status) == 0, "tcgen05 MMA completion timed out"
+        K.tc_set_variant(1 if tc == "seq" else 0)      # "seq": force the branch-sequential schedule
+        try:
+            K.ppo_train_step_tc(img, t["obs"], t["actions"], t["old_logits"], t["old_logp"], t["vf_preds"], t["adv"],
+                                t["vtarg"], A, MB, perm, ctr, klc, hyper, G, gp, sp, status)
+        finally:
+            K.tc_set_variant(0)
+        assert int(status) == 0, f"tcgen05 step reported status {int(status)}"
     else:
         K.ppo_train_step(t["theta"], t["obs"], t["actions"], t["old_logits"], t["old_logp"], t["vf_preds"], t["adv"],
                          t["vtarg"], A, MB, perm, ctr, klc, hyper, G, gp, sp)
@@ -148,7 +152,7 @@ def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda", tc=False):
                                     ("Local", 8), ("TwoSides", 3), ("SingleDiagonal", 16),
                                     ("Centralized_TVel", 7), ("FullyDecentral_TVel", 2), ("Local_TVel", 4),
                                     ("TwoSides_TVel", 9)])
-@pytest.mark.parametrize("tc", [False, True], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("tc", [False, True, "seq"], ids=["fp32", "tcgen05", "tcgen05-seq"])
 def test_train_step_gradients_match_float64_autograd(arch, G, tc):
     O = _oracle()
     cfg = O.PPOConfig(entropy_coeff=0.01)  # non-zero so the entropy term is exercised too
