@@ -22,11 +22,16 @@ class PPOHyper(C.Structure):
                 ("entropy_coeff", C.c_float), ("inv_global_mb", C.c_float)]
 
 
+MAX_RANKS = 8
+
+
 class SgdTail(C.Structure):
     _fields_ = [("theta", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("beta_pow", C.c_void_p), ("grad", C.c_void_p),
                 ("gnorm_out", C.c_void_p), ("fcnet_img", C.c_void_p), ("fcnet_tc_img", C.c_void_p),
                 ("step_stats", C.c_void_p), ("step_ctr", C.c_void_p), ("barrier_ws", C.c_void_p), ("sq_ws", C.c_void_p),
-                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_clip", C.c_float)]
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_clip", C.c_float),
+                ("status", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("seq", C.c_void_p),
+                ("peer_x", C.c_void_p * MAX_RANKS), ("peer_flag", C.c_void_p * MAX_RANKS)]
 
 
 # name -> (restype, argtypes); mirrors include/ddrl_b200.h one to one (tests check every symbol).
@@ -72,6 +77,11 @@ PROTOTYPES = {
     "ddrl_leg_coupling": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int, c_stream]),
     "ddrl_fcnet_tc_image_bytes": (C.c_int, [C.c_int, C.c_int]),
     "ddrl_tc_set_variant": (C.c_int, [C.c_int]),
+    "ddrl_sgd_exchange_floats": (C.c_int64, [C.c_int, C.c_int]),
+    "ddrl_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ddrl_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ddrl_peer_close": (C.c_int, [C.c_void_p]),
+    "ddrl_peer_free": (C.c_int, [C.c_void_p]),
     "ddrl_fcnet_tc_pack": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_stream]),
     "ddrl_ppo_train_step_tc": (C.c_int, [C.c_void_p] + [c_f32p] * 7 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p,
                                                                      C.c_int64, c_i32p, c_f32p, C.POINTER(PPOHyper), C.c_int,

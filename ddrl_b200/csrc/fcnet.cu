@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     }
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
         __threadfence();
-        sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A, sm + L.out);
+        sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A, sm + L.h1);
     }
 }
 
@@ -682,13 +682,10 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const f
     a.grad_part = grad_part; a.stat_part = stat_part;
     a.tail = SgdTail{};
     if (tail) {
-        DDRL_REQUIRE(tail->theta && tail->m && tail->v && tail->beta_pow && tail->grad && tail->barrier_ws && tail->sq_ws && !ext,
-                     DDRL_E_BADARG, "ppo_train_step: incomplete fused tail (or external-gradient mode)");
-        DDRL_REQUIRE(ctas_per_policy * P <= num_sms(), DDRL_E_BADARG,
-                     "ppo_train_step: fused tail needs all %d CTAs co-resident (%d SMs)", ctas_per_policy * P, num_sms());
-        a.tail = SgdTail{tail->theta, tail->m, tail->v, tail->beta_pow, tail->grad, tail->gnorm_out, tail->fcnet_img,
-                         (unsigned char*)tail->fcnet_tc_img, tail->step_stats, tail->step_ctr, tail->barrier_ws, tail->sq_ws,
-                         tail->lr, tail->beta1, tail->beta2, tail->eps, tail->grad_clip};
+        DDRL_REQUIRE(!ext, DDRL_E_BADARG, "ppo_train_step: the fused tail cannot be combined with external gradients");
+        const int rc = sgd_tail_check(tail, ctas_per_policy * P, "ppo_train_step");
+        if (rc != DDRL_OK) return rc;
+        a.tail = *tail;
     }
     const FcSmem L = fc_smem(D, A, false, true);
     const size_t smem = (size_t)L.total * sizeof(float);

@@ -1,11 +1,18 @@
 // Fused tail of one SGD step, executed by the SAME kernel that produced the per-CTA partial gradients:
-//   barrier (G CTAs of a policy) -> fixed-order reduction of the partials, each CTA owning a contiguous slice of the
-//   parameters (+ its share of ||g||^2) -> barrier -> tf.clip_by_global_norm + TF1 Adam on the slice, packed weight
-//   images kept in step -> the last CTA of the grid advances beta powers / step counter and re-arms the barriers.
-// It replaces the separate grad_reduce and clip_adam launches of the single-GPU path (two launch gaps per step and a
-// redundant full-gradient read per CTA).  All CTAs of the grid must be co-resident: the callers launch at most one
-// CTA per SM; every spin is bounded and reports through *status instead of hanging.
-// Arithmetic and summation order are identical to grad_reduce_kernel + clip_adam_kernel (bit-identical results).
+//
+//   barrier A (the G CTAs of a policy)                      partials visible
+//   slice reduce: CTA bx owns parameters [bx*S, bx*S+S) and sums them over the G partials — up to 8 thread groups load
+//                 different partials concurrently (one L2 round trip instead of G dependent ones), fixed summation order
+//   [world > 1]   in-kernel all-reduce over NVLink peer memory: the slice is PUSHED into every rank's exchange buffer
+//                 (plain peer stores), a system-scope release flag follows, the CTA polls its own flags for the peers'
+//                 slices and adds the `world` slices in rank order — every rank ends with bit-identical sums, one NVLink
+//                 one-way latency per step, no NCCL call, no extra launch
+//   barrier B     per-slice ||g||^2 visible -> global norm (same order everywhere), tf.clip_by_global_norm, TF1 Adam on
+//                 the slice, packed weight images kept in step
+//   ticket        the last CTA of the grid advances beta powers / step counter / exchange sequence and re-arms barriers
+//
+// It replaces grad_reduce + [ncclAllReduce] + clip_adam (two or three launches and their gaps per step).  All CTAs of the
+// grid must be co-resident (callers launch at most one CTA per SM); every spin is bounded and reports instead of hanging.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -15,90 +22,161 @@
 
 namespace ddrl {
 
-struct SgdTail {          // all device pointers; theta == nullptr disables the tail
-    float *theta, *m, *v, *beta_pow, *grad, *gnorm_out, *img;
-    unsigned char* tc_img;
-    double* step_stats;
-    int32_t* step_ctr;
-    unsigned int* bar;    // [4*P + 4] zero-initialised counters: per policy {A, B}, then the done ticket
-    float* sq;            // [P][G] partial sums of squares
-    float lr, beta1, beta2, eps, clip;
-};
+using SgdTail = ddrl_sgd_tail;   // include/ddrl_b200.h; theta == nullptr disables the tail
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // one thread: arrive and wait until `target` CTAs have arrived; false on timeout
 __device__ __forceinline__ bool grid_group_barrier(unsigned int* ctr, unsigned int target) {
     __threadfence();
     atomicAdd(ctr, 1u);
-    for (unsigned int i = 0; i < 40000000u; ++i) {
+    for (unsigned int i = 0; i < 4000000u; ++i) {
         if (ld_acquire_u32(ctr) >= target) return true;
-        __nanosleep(40);
+        __nanosleep(20);
     }
     return false;
 }
 
+__host__ __device__ inline int sgd_slice_len(int NP, int G) { return (((NP + G - 1) / G) + 3) & ~3; }
+
 // Called by every thread of every CTA after the partial gradient (and stat partial) of this CTA has been written.
-// smem_red: >= 40 floats of shared memory.  Returns false if a barrier timed out.
+// smem: 16 * blockDim.x + 256 bytes of (16-byte aligned) shared memory.  Returns false if a barrier or a peer wait timed out.
 __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __restrict__ grad_part,
                                               const double* __restrict__ stat_part, int p, int P, int bx, int G, int NP,
-                                              int step, int D, int A, float* smem_red) {
+                                              int step, int D, int A, float* smem) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int NPs = (NP + 3) & ~3;
+    float4* scr = reinterpret_cast<float4*>(smem);
+    float* red = smem + 4 * nt;                 // [64]: warp partials, flags
+    const int W = t.world > 1 ? t.world : 1;
     bool ok = true;
     __syncthreads();
-    if (tid == 0) smem_red[39] = grid_group_barrier(t.bar + 4 * p, (unsigned)G) ? 1.f : 0.f;
+    if (tid == 0) red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)G) ? 1.f : 0.f;
     __syncthreads();
-    ok = ok && smem_red[39] != 0.f;
-    // ---- reduce this CTA's slice of the parameters over the G partials (fixed order), partial ||g||^2 ----------------
-    const int S = (NP + G - 1) / G, j0 = bx * S, j1 = min(NP, j0 + S);
+    ok = ok && red[39] != 0.f;
+
+    // ---- slice reduce over the G partials --------------------------------------------------------------------------
+    const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S);
+    const int ncol4 = max(0, (j1 - j0) >> 2);
+    const int ngrp = ncol4 >= nt ? 1 : max(1, min(min(8, G), nt / max(ncol4, 1)));
+    const int cpp = nt / ngrp;                  // float4 columns per pass
+    const unsigned int seq = (W > 1) ? *t.seq : 0u;
+    const int par = (int)(seq & 1u);
+    const int64_t xstride = (int64_t)G * S;     // floats per (rank, policy) in the exchange buffer
+    float* slice_dst = (W > 1) ? t.peer_x[t.rank] + (((int64_t)par * W + t.rank) * P + p) * xstride + j0
+                               : t.grad + (int64_t)p * NP + j0;
+    for (int c0 = 0; c0 < ncol4; c0 += cpp) {
+        const int g = tid / cpp, c = c0 + (tid - g * cpp);
+        if (g < ngrp && c < ncol4) {
+            const float4* src = reinterpret_cast<const float4*>(grad_part + (int64_t)p * G * NPs + j0) + c;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int i = g; i < G; i += ngrp) {
+                const float4 v = __ldcg(src + (int64_t)i * (NPs >> 2));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            scr[g * cpp + (c - c0)] = acc;
+        }
+        __syncthreads();
+        const int nf = 4 * min(cpp, ncol4 - c0);
+        for (int f = tid; f < nf; f += nt) {
+            const int col = f >> 2, e = f & 3;
+            float s = 0.f;
+            for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * cpp + col])[e];
+            const int jj = 4 * c0 + f;           // offset inside the slice
+            if (j0 + jj < NP) {
+                if (W > 1) {
+                    for (int w = 0; w < W; ++w)   // push to every rank's exchange buffer (own copy included)
+                        t.peer_x[w][(((int64_t)par * W + t.rank) * P + p) * xstride + j0 + jj] = s;
+                } else {
+                    slice_dst[jj] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (bx == 0 && warp < DDRL_NSTAT && stat_part && t.step_stats) {   // warp w sums stat w (lanes stride over the partials)
+        double s = 0.0;
+        for (int i = lane; i < G; i += 32) s += __ldcg(stat_part + ((int64_t)p * G + i) * DDRL_NSTAT + warp);
+        s = warp_sum(s);
+        if (lane == 0) t.step_stats[((int64_t)step * P + p) * DDRL_NSTAT + warp] = s;
+    }
+    // ---- data parallel: flags out, flags in, sum the world's slices in rank order -----------------------------------
+    if (W > 1) {
+        __syncthreads();                           // all pushes of this CTA issued
+        if (tid < W) {
+            const unsigned int want = seq + 1u;
+            __threadfence_system();                // cumulative: orders the CTA's pushes (observed via bar.sync) before the flag
+            if (tid != t.rank) st_relaxed_sys_u32(t.peer_flag[tid] + ((int64_t)t.rank * P + p) * G + bx, want);
+            bool got = true;
+            if (tid != t.rank) {
+                got = false;
+                const unsigned int* fl = t.peer_flag[t.rank] + ((int64_t)tid * P + p) * G + bx;
+                for (unsigned int i = 0; i < 4000000u; ++i) {
+                    if ((int)(ld_acquire_sys_u32(fl) - want) >= 0) { got = true; break; }
+                    __nanosleep(20);
+                }
+            }
+            red[40 + tid] = got ? 1.f : 0.f;
+        }
+        __syncthreads();
+        for (int w = 0; w < W; ++w) ok = ok && red[40 + w] != 0.f;
+        const float* xl = t.peer_x[t.rank] + ((int64_t)par * W * P + p) * xstride + j0;   // + w * P * xstride per rank
+        for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
+            float s = 0.f;
+            for (int w = 0; w < W; ++w) s += __ldcg(xl + (int64_t)w * P * xstride + jj);
+            t.grad[(int64_t)p * NP + j0 + jj] = s;
+        }
+    }
+    __syncthreads();
+    // ---- ||g||^2 of the slice (fixed order) -> barrier B -> global norm ------------------------------------------------
     float ss = 0.f;
-    for (int j = j0 + tid; j < j1; j += nt) {
-        const float* g = grad_part + (int64_t)p * G * NPs + j;
-        float s = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < G; ++i) s += __ldcg(g + (int64_t)i * NPs);
-        t.grad[(int64_t)p * NP + j] = s;
+    for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
+        const float s = __ldcg(t.grad + (int64_t)p * NP + j0 + jj);
         ss = fmaf(s, s, ss);
     }
     ss = warp_sum(ss);
-    if (lane == 0) smem_red[warp] = ss;
-    if (bx == 0 && tid < DDRL_NSTAT && stat_part && t.step_stats) {
-        double s = 0.0;
-        for (int i = 0; i < G; ++i) s += __ldcg(stat_part + ((int64_t)p * G + i) * DDRL_NSTAT + tid);
-        t.step_stats[((int64_t)step * P + p) * DDRL_NSTAT + tid] = s;
-    }
+    if (lane == 0) red[warp] = ss;
     __syncthreads();
     if (tid == 0) {
         float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += smem_red[w];
-        t.sq[p * G + bx] = s;
-        smem_red[39] = grid_group_barrier(t.bar + 4 * p + 1, (unsigned)G) ? 1.f : 0.f;
+        for (int w = 0; w < nw; ++w) s += red[w];
+        t.sq_ws[p * G + bx] = s;
+        red[39] = grid_group_barrier(t.barrier_ws + 4 * p + 1, (unsigned)G) ? 1.f : 0.f;
     }
     __syncthreads();
-    ok = ok && smem_red[39] != 0.f;
-    // ---- global norm (every CTA, same fixed order), clip, TF1 Adam on the slice -------------------------------------
+    ok = ok && red[39] != 0.f;
     if (warp == 0) {
         float s = 0.f;
-        for (int i = lane; i < G; i += 32) s += __ldcg(t.sq + p * G + i);
+        for (int i = lane; i < G; i += 32) s += __ldcg(t.sq_ws + p * G + i);
         s = warp_sum(s);
         if (lane == 0) {
             const float norm = sqrtf(s);
-            smem_red[32] = t.clip > 0.f ? t.clip * fminf(1.f / norm, 1.f / t.clip) : 1.f;
+            red[32] = t.grad_clip > 0.f ? t.grad_clip * fminf(1.f / norm, 1.f / t.grad_clip) : 1.f;
             if (bx == 0 && t.gnorm_out) t.gnorm_out[p] = norm;
         }
     }
     __syncthreads();
-    const float scale = smem_red[32];
+    // ---- clip + TF1 Adam on the slice ---------------------------------------------------------------------------------
+    const float scale = red[32];
     const float b1p = __ldcg(t.beta_pow + p * 2), b2p = __ldcg(t.beta_pow + p * 2 + 1);
     const float alpha = t.lr * sqrtf(1.f - b2p) / (1.f - b1p);
-    for (int j = j0 + tid; j < j1; j += nt) {
+    for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
+        const int j = j0 + jj;
         const int64_t k = (int64_t)p * NP + j;
-        const float gj = t.grad[k] * scale;
+        const float gj = __ldcg(t.grad + k) * scale;
         float mj = t.m[k], vj = t.v[k];
         mj += (gj - mj) * (1.f - t.beta1);
         vj += (gj * gj - vj) * (1.f - t.beta2);
@@ -106,22 +184,22 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
         t.v[k] = vj;
         const float tnew = t.theta[k] - (mj * alpha) / (sqrtf(vj) + t.eps);
         t.theta[k] = tnew;
-        if (t.img) {
+        if (t.fcnet_img) {
             const FcSmem L = fc_smem(D, A, false);
             const FcOffsets o = fc_offsets(D, A);
             int p0, p1;
             fc_img_pos(L, o, D, A, j, p0, p1);
-            float* im = t.img + (int64_t)p * L.x;
+            float* im = t.fcnet_img + (int64_t)p * L.x;
             im[p0] = tnew;
             if (p1 >= 0) im[p1] = tnew;
         }
-        if (t.tc_img) {
+        if (t.fcnet_tc_img) {
             const TcImg L = tc_img(D, A);
             const FcOffsets o = fc_offsets(D, A);
             bool f16;
             int p0, p1;
             tc_img_pos(L, o, D, A, j, f16, p0, p1);
-            unsigned char* im = t.tc_img + (int64_t)p * L.bytes;
+            unsigned char* im = reinterpret_cast<unsigned char*>(t.fcnet_tc_img) + (int64_t)p * L.bytes;
             if (f16) {
                 const float ws = tnew * 256.f;
                 const __half hi = __float2half_rn(ws);
@@ -137,19 +215,38 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
     if (tid == 0) {
         __threadfence();
         const unsigned int total = gridDim.x * gridDim.y;
-        if (atomicAdd(t.bar + 4 * P, 1u) == total - 1) {
+        if (atomicAdd(t.barrier_ws + 4 * P, 1u) == total - 1) {
             for (int q = 0; q < P; ++q) {
                 t.beta_pow[q * 2] *= t.beta1;
                 t.beta_pow[q * 2 + 1] *= t.beta2;
-                t.bar[4 * q] = 0u;
-                t.bar[4 * q + 1] = 0u;
+                t.barrier_ws[4 * q] = 0u;
+                t.barrier_ws[4 * q + 1] = 0u;
             }
             if (t.step_ctr) *t.step_ctr += 1;
-            t.bar[4 * P] = 0u;
+            if (t.seq) *t.seq = seq + 1u;
+            t.barrier_ws[4 * P] = 0u;
             __threadfence();
         }
+        if (!ok && t.status) atomicOr(t.status, 64);
     }
     return ok;
+}
+
+// Host-side validation shared by the launchers.
+inline int sgd_tail_check(const ddrl_sgd_tail* tail, int ctas_total, const char* who) {
+    DDRL_REQUIRE(tail->theta && tail->m && tail->v && tail->beta_pow && tail->grad && tail->barrier_ws && tail->sq_ws,
+                 DDRL_E_BADARG, "%s: incomplete fused tail", who);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    DDRL_REQUIRE(ctas_total <= sms, DDRL_E_BADARG, "%s: fused tail needs all %d CTAs co-resident (%d SMs)", who, ctas_total, sms);
+    if (tail->world > 1) {
+        DDRL_REQUIRE(tail->world <= DDRL_MAX_RANKS && tail->rank >= 0 && tail->rank < tail->world && tail->seq, DDRL_E_BADARG,
+                     "%s: fused tail: bad world/rank/seq (world <= %d)", who, DDRL_MAX_RANKS);
+        for (int w = 0; w < tail->world; ++w)
+            DDRL_REQUIRE(tail->peer_x[w] && tail->peer_flag[w], DDRL_E_BADARG, "%s: fused tail: peer buffer %d missing", who, w);
+    }
+    return DDRL_OK;
 }
 
 }  // namespace ddrl

@@ -3,12 +3,14 @@
 // All reductions use a fixed order (no float atomics) => bit-reproducible.
 #include <algorithm>
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "fcnet_layout.cuh"
 #include "fcnet_tc_layout.cuh"
 #include <cuda_fp16.h>
 #include "ppo_loss.cuh"
+#include "sgd_tail.cuh"
 
 namespace ddrl {
 
@@ -555,5 +557,54 @@ extern "C" int ddrl_leg_coupling(float* logits, const int32_t* node_id, const fl
     const int nb = (int)std::min<int64_t>(1024, (B * W + 255) / 256);
     leg_coupling_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(logits, node_id, coupling, B, W);
     DDRL_CHECK_LAUNCH("leg_coupling");
+    return DDRL_OK;
+}
+
+extern "C" int64_t ddrl_sgd_exchange_floats(int NP, int ctas_per_policy) {
+    if (NP < 1 || ctas_per_policy < 1) return DDRL_E_BADARG;
+    return (int64_t)ctas_per_policy * sgd_slice_len(NP, ctas_per_policy);
+}
+
+// ---- peer-mapped memory (CUDA IPC) for the in-kernel gradient all-reduce ------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle64 is a cudaIpcMemHandle_t");
+
+extern "C" int ddrl_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+    DDRL_REQUIRE(bytes > 0 && ptr && handle64, DDRL_E_BADARG, "peer_alloc: bad arguments");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "peer_alloc: cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("peer_alloc: %s", cudaGetErrorString(e));
+        return DDRL_E_CUDA;
+    }
+    *ptr = p;
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_peer_open(const void* handle64, void** ptr) {
+    DDRL_REQUIRE(handle64 && ptr, DDRL_E_BADARG, "peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    *ptr = p;
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_peer_close(void* ptr) {
+    DDRL_REQUIRE(ptr, DDRL_E_BADARG, "peer_close: null pointer");
+    const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "peer_close: %s", cudaGetErrorString(e));
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_peer_free(void* ptr) {
+    DDRL_REQUIRE(ptr, DDRL_E_BADARG, "peer_free: null pointer");
+    const cudaError_t e = cudaFree(ptr);
+    DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "peer_free: %s", cudaGetErrorString(e));
     return DDRL_OK;
 }

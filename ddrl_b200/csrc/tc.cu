@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
         if (a.tail.theta) {
             __threadfence();
             const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                           reinterpret_cast<float*>(sm + S.red));
+                                           reinterpret_cast<float*>(sm + S.H1[0]));
             if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
         }
         return;
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
         __threadfence();
         const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                       reinterpret_cast<float*>(sm + S.red));
+                                       reinterpret_cast<float*>(sm + S.H1[0]));
         if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
     }
 }
@@ -609,16 +609,9 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     a.grad_part = grad_part; a.stat_part = stat_part; a.status = status;
     a.tail = SgdTail{};
     if (tail) {
-        DDRL_REQUIRE(tail->theta && tail->m && tail->v && tail->beta_pow && tail->grad && tail->barrier_ws && tail->sq_ws,
-                     DDRL_E_BADARG, "ppo_train_step_tc: incomplete fused tail");
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        DDRL_REQUIRE(ctas_per_policy * P <= sms, DDRL_E_BADARG,
-                     "ppo_train_step_tc: fused tail needs all %d CTAs co-resident (%d SMs)", ctas_per_policy * P, sms);
-        a.tail = SgdTail{tail->theta, tail->m, tail->v, tail->beta_pow, tail->grad, tail->gnorm_out, tail->fcnet_img,
-                         (unsigned char*)tail->fcnet_tc_img, tail->step_stats, tail->step_ctr, tail->barrier_ws, tail->sq_ws,
-                         tail->lr, tail->beta1, tail->beta2, tail->eps, tail->grad_clip};
+        const int rc = sgd_tail_check(tail, ctas_per_policy * P, "ppo_train_step_tc");
+        if (rc != DDRL_OK) return rc;
+        a.tail = *tail;
     }
     const size_t smem = (size_t)tc_smem(D, A).total;
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);

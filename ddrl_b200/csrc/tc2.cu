@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         if (a.tail.theta) {
             __threadfence();
             const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                           reinterpret_cast<float*>(sm + S.red));
+                                           reinterpret_cast<float*>(sm + S.H1[0][0]));
             if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
         }
         return;
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
         __threadfence();
         const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                       reinterpret_cast<float*>(sm + S.red));
+                                       reinterpret_cast<float*>(sm + S.H1[0][0]));
         if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
     }
 }

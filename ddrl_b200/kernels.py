@@ -375,12 +375,18 @@ def obs_gather(obs_full: torch.Tensor, table: torch.Tensor, P: int, out: Optiona
 
 
 def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, beta2, eps, grad_clip, gnorm_out=None, img=None,
-                  tc_img=None, step_stats=None, step_ctr=None) -> SgdTail:
-    """Fused grad-reduce + clip + Adam tail of the single-GPU SGD step (see ddrl_sgd_tail in ddrl_b200.h).
-    The caller keeps the tensors alive; barrier_ws must be zero-initialised uint32/int32 [4*P + 4]."""
+                  tc_img=None, step_stats=None, step_ctr=None, status=None) -> SgdTail:
+    """Fused grad-reduce + [peer all-reduce] + clip + Adam tail of the SGD step (see ddrl_sgd_tail in ddrl_b200.h).
+    The caller keeps the tensors alive; barrier_ws must be zero-initialised int32 [4*P + 4].  For world > 1 let
+    ``peer.PeerExchange.fill`` add the rank / peer-buffer fields."""
     f32 = torch.float32
-    return SgdTail(_p(theta, f32, "theta"), _p(m, f32, "m"), _p(v, f32, "v"), _p(beta_pow, f32, "beta_pow"),
-                   _p(grad, f32, "grad"), _p(gnorm_out, f32, "gnorm_out"), _p(img, f32, "img"), _p(tc_img, torch.uint8, "tc_img"),
-                   _p(step_stats, torch.float64, "step_stats"), _p(step_ctr, torch.int32, "step_ctr"),
-                   _p(barrier_ws, torch.int32, "barrier_ws"), _p(sq_ws, f32, "sq_ws"), float(lr), float(beta1), float(beta2),
-                   float(eps), float(grad_clip))
+    t = SgdTail()
+    t.theta, t.m, t.v = _p(theta, f32, "theta"), _p(m, f32, "m"), _p(v, f32, "v")
+    t.beta_pow, t.grad, t.gnorm_out = _p(beta_pow, f32, "beta_pow"), _p(grad, f32, "grad"), _p(gnorm_out, f32, "gnorm_out")
+    t.fcnet_img, t.fcnet_tc_img = _p(img, f32, "img"), _p(tc_img, torch.uint8, "tc_img")
+    t.step_stats, t.step_ctr = _p(step_stats, torch.float64, "step_stats"), _p(step_ctr, torch.int32, "step_ctr")
+    t.barrier_ws, t.sq_ws = _p(barrier_ws, torch.int32, "barrier_ws"), _p(sq_ws, f32, "sq_ws")
+    t.lr, t.beta1, t.beta2, t.eps, t.grad_clip = float(lr), float(beta1), float(beta2), float(eps), float(grad_clip)
+    t.status = _p(status, torch.int32, "status")
+    t.world, t.rank = 1, 0
+    return t

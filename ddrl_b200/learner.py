@@ -132,6 +132,7 @@ class FCNetLearner(_LearnerBase):
         self._graph = None
         self._graph_key = None
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self._peers = None
 
     # ---- buffers ------------------------------------------------------------------------------------
     def _alloc(self, T: int, Cc: int):
@@ -165,16 +166,29 @@ class FCNetLearner(_LearnerBase):
         return MB, nb, G
 
     # ---- one optimizer step (3 kernels [+ NCCL]) -----------------------------------------------------------
+    def _peer_exchange(self, G: int):
+        """Peer-mapped exchange buffers of the in-kernel gradient all-reduce (world > 1), created once per shape."""
+        key = (self.P, self.NP, G)
+        if self._peers is None or self._peers.key != key:
+            from .peer import PeerExchange
+            if self._peers is not None:
+                self._peers.close()
+            self._peers = PeerExchange(self.dist, self.world, self.rank, self.P, self.NP, G, self.device)
+        return self._peers
+
     def _sgd_step(self, b, MB, G, hyper, src):
-        # single GPU: the train kernel also reduces the partials, clips and applies Adam (fused tail: 1 launch per step);
-        # data parallel: 3 kernels with the NCCL all-reduce of the flat gradient between reduce and Adam
+        # ONE launch per optimizer step: the train kernel also reduces the partials, all-reduces the gradient slices
+        # over NVLink peer memory (world > 1), clips and applies Adam (csrc/sgd_tail.cuh).  fuse_tail=False keeps the
+        # 3-kernel path (train, grad_reduce, [NCCL all-reduce], clip_adam) for A/B tests.
         tail = None
-        if self.world == 1 and self.fuse_tail and G * self.P <= self.sms:
+        if self.fuse_tail and G * self.P <= self.sms:
             c = self.cfg
             tail = K.make_sgd_tail(self.theta, self.m, self.v, self.beta_pow, self.grad, b["tail_bar"], b["tail_sq"], c.lr,
                                    c.beta1, c.beta2, c.adam_eps, c.grad_clip, self.gnorm,
                                    img=self.img if self.mode == "fp32" else None, tc_img=self.tc_img,
-                                   step_stats=b["step_stats"], step_ctr=self.step_ctr)
+                                   step_stats=b["step_stats"], step_ctr=self.step_ctr, status=self.tc_status)
+            if self.world > 1:
+                self._peer_exchange(G).fill(tail)
         if self.mode == "tc":
             K.ppo_train_step_tc(self.tc_img, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
                                 src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
@@ -209,7 +223,6 @@ class FCNetLearner(_LearnerBase):
         K.fcnet_pack(self.theta, D, A, self.img)
         if self.tc_img is not None:
             K.fcnet_tc_pack(self.theta, D, A, self.tc_img)
-            self.tc_status.zero_()
         # (i) filter + forward + sample ------------------------------------------------------------------
         if update_filter:
             if self.world > 1:
@@ -255,7 +268,10 @@ class FCNetLearner(_LearnerBase):
             self._graph = None
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()
+        self.tc_status.zero_()
         hyper = self._hyper(MB * self.world)
+        if self.world > 1 and self.fuse_tail and G * P <= self.sms:
+            self._peer_exchange(G)      # allocate / map the peer buffers outside any graph capture
         ran = False
         if self.use_graph:
             key = (T, Cc, steps, G, MB, src_key)
@@ -271,6 +287,8 @@ class FCNetLearner(_LearnerBase):
                         for _ in range(nb):
                             self._sgd_step(b, MB, G, hyper, src)
                     self._graph, self._graph_key = g, key
+                    if self.world > 1:
+                        self.dist.barrier()     # replays spin on peer flags: start them together
                 except Exception as exc:  # capture not possible (e.g. NCCL build without graph support): run eagerly
                     self._graph, self.use_graph = None, False
                     self.graph_error = repr(exc)
@@ -288,13 +306,14 @@ class FCNetLearner(_LearnerBase):
         if self.world > 1:
             self.dist.all_reduce(last)
         stats = finalize_stats(last.cpu().numpy(), self.kl_coeff_host, cfg, MB * self.world)
-        if self.tc_img is not None:
-            code = int(self.tc_status.item())
-            if code:
-                what = [n for bit, n in ((1, "MMA completion timed out"), (2, "x overflow"), (4, "activation overflow"),
-                                         (8, "dl overflow"), (16, "dz2 overflow"), (32, "dz1 overflow")) if code & bit]
-                raise DDRLError("tensor-core SGD step failed (" + ", ".join(what) + "): fp16 split range exceeded — "
-                                "use mode='fp32' for this workload")
+        code = int(self.tc_status.item())
+        if code:
+            what = [n for bit, n in ((1, "MMA completion timed out"), (2, "x overflow"), (4, "activation overflow"),
+                                     (8, "dl overflow"), (16, "dz2 overflow"), (32, "dz1 overflow"),
+                                     (64, "fused-tail barrier / peer wait timed out")) if code & bit]
+            hint = (" — fp16 split range exceeded: use mode='fp32' for this workload" if code & 62 else
+                    " — a CTA barrier or a peer rank did not arrive in time")
+            raise DDRLError("SGD step failed (" + ", ".join(what) + ")" + hint)
         self._update_kl(stats)
         return stats
 

@@ -152,14 +152,23 @@ typedef struct {
     float clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff, inv_global_mb;
 } ddrl_ppo_hyper;
 
-/* Optional fused tail of a single-GPU SGD step (pass NULL to get the partials only): the train kernel itself then
- * performs what ddrl_grad_reduce + ddrl_clip_adam would do — a barrier among the CTAs of each policy, the fixed-order
- * partial reduction (each CTA owns a slice of the parameters), the global-norm clip, TF1 Adam, the packed weight
- * images, the beta powers and *step_ctr — with bit-identical results and two kernel launches fewer per step.
- * Requires ctas_per_policy * P <= number of SMs (all CTAs co-resident).  Device pointers:
+/* Optional fused tail of an SGD step (pass NULL to get the partials only): the train kernel itself then performs what
+ * ddrl_grad_reduce + [gradient all-reduce] + ddrl_clip_adam would do — a barrier among the CTAs of each policy, the
+ * fixed-order partial reduction (each CTA owns a slice of the parameters), at world > 1 an in-kernel all-reduce of the
+ * slices over NVLink peer memory, the global-norm clip, TF1 Adam, the packed weight images, the beta powers and
+ * *step_ctr — in ONE launch per step.  Requires ctas_per_policy * P <= number of SMs (all CTAs co-resident).
+ * Device pointers:
  *   theta, m, v [P][NP]; beta_pow [P][2]; grad [P][NP] (out: reduced gradient); gnorm_out [P] or NULL;
  *   fcnet_img / fcnet_tc_img or NULL; step_stats [steps][P][DDRL_NSTAT] or NULL; step_ctr;
- *   barrier_ws: 4*P + 4 zero-initialised uint32 (re-armed by the kernel); sq_ws: P * ctas_per_policy floats. */
+ *   barrier_ws: 4*P + 4 zero-initialised uint32 (re-armed by the kernel); sq_ws: P * ctas_per_policy floats;
+ *   status: device int or NULL, receives |= 64 when a bounded spin of the tail gave up (results then invalid).
+ * Data parallel (world > 1; one process per GPU, every rank launches the same step with the same shapes):
+ *   seq       device uint32, zero-initialised once, advanced by the kernel every step (flags carry seq + 1);
+ *   peer_x[w] exchange buffer of rank w (peer-mapped, ddrl_peer_alloc/open; [rank] = the local one):
+ *             2 * world * P * ddrl_sgd_exchange_floats(NP, ctas_per_policy) floats;
+ *   peer_flag[w] flag array of rank w: world * P * ctas_per_policy zero-initialised uint32.
+ * Every rank ends each step with bit-identical gradients (slices are summed in rank order) and weights. */
+#define DDRL_MAX_RANKS 8
 typedef struct {
     float *theta, *m, *v, *beta_pow, *grad, *gnorm_out, *fcnet_img;
     void* fcnet_tc_img;
@@ -168,7 +177,25 @@ typedef struct {
     uint32_t* barrier_ws;
     float* sq_ws;
     float lr, beta1, beta2, eps, grad_clip;
+    int32_t* status;          /* device int or NULL: OR-ed with 64 if a barrier / peer wait of the tail timed out */
+    int32_t world, rank;
+    uint32_t* seq;
+    float* peer_x[DDRL_MAX_RANKS];
+    uint32_t* peer_flag[DDRL_MAX_RANKS];
 } ddrl_sgd_tail;
+
+/* floats per (rank, policy) in the exchange buffer: ctas_per_policy slices of ((NP + G - 1) / G rounded up to 4) */
+int64_t ddrl_sgd_exchange_floats(int NP, int ctas_per_policy);
+
+/* Peer-mapped device memory for the in-kernel all-reduce (CUDA IPC; one process per GPU on one node).
+ *   ddrl_peer_alloc: cudaMalloc + zero-fill `bytes` on the current device; *ptr = device pointer, handle64 = 64-byte
+ *                    cudaIpcMemHandle_t to send to the other ranks (e.g. torch.distributed.all_gather_object);
+ *   ddrl_peer_open:  map another rank's allocation into this process (enables peer access), *ptr = local alias;
+ *   ddrl_peer_close / ddrl_peer_free: undo open / alloc. */
+int ddrl_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int ddrl_peer_open(const void* handle64, void** ptr);
+int ddrl_peer_close(void* ptr);
+int ddrl_peer_free(void* ptr);
 
 int ddrl_ppo_train_step(const float* theta, const float* img, const float* obs, const float* actions,
                         const float* old_logits, const float* old_logp, const float* vf_preds,

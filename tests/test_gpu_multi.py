@@ -29,11 +29,12 @@ def _problem():
     return dict(theta=theta, filt=filt, D=D, A=A, P=P, raw=raw, boot=boot, rewards=rewards, dones=dones, eps=eps, perms=perms)
 
 
-def _learner(pr, dev, mb):
+def _learner(pr, dev, mb, mode="fp32", fuse=True, graph=False):
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=mb)
-    L = FCNetLearner(pr["P"], pr["D"], pr["A"], cfg, dev, theta=torch.from_numpy(pr["theta"]), use_graph=False, mode="fp32")
+    L = FCNetLearner(pr["P"], pr["D"], pr["A"], cfg, dev, theta=torch.from_numpy(pr["theta"]), use_graph=graph, mode=mode,
+                     fuse_tail=fuse)
     filt = [(1000, M, S * (999.0 / (n - 1))) for n, M, S in pr["filt"]]
     L.filt_n.copy_(torch.tensor([f[0] for f in filt]))
     L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt])))
@@ -41,7 +42,16 @@ def _learner(pr, dev, mb):
     return L
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode, fuse, graph):
+    try:
+        _worker_body(rank, world, port, q, mode, fuse, graph)
+    except Exception as exc:  # surface the failure instead of leaving the parent waiting on the queue
+        import traceback
+        q.put(("error", rank, "".join(traceback.format_exception(exc))))
+        raise
+
+
+def _worker_body(rank, world, port, q, mode, fuse, graph):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -51,30 +61,43 @@ def _worker(rank, world, port, q):
     Cl = C // world
     sl = slice(rank * Cl, (rank + 1) * Cl)
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    L = _learner(pr, dev, (T * C) // NB)
+    L = _learner(pr, dev, (T * C) // NB, mode, fuse, graph)
     stats = L.learn_on_rollout(to(pr["raw"][:, :, sl]), to(pr["boot"][:, sl]), to(pr["rewards"][:, :, sl]),
                                to(pr["dones"][:, sl]), to(pr["eps"][:, :, sl]), to(pr["perms"]))
+    assert (L._peers is not None) == fuse, "fused tail must use the peer exchange, the 3-kernel path NCCL"
     torch.cuda.synchronize()
     th = L.theta.cpu().numpy()
     gathered = [None] * world
     dist.all_gather_object(gathered, th)
     if rank == 0:
         q.put((th, stats, L.filt_n.cpu().numpy(), L.filt_M.cpu().numpy(), [np.array_equal(g, th) for g in gathered]))
+    L._graph = None
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpu_learner_equals_one_gpu_learner():
+@pytest.mark.parametrize("mode,fuse,graph", [("fp32", True, False), ("fp32", False, False), ("tc", True, True)],
+                         ids=["fp32-peer", "fp32-nccl", "tc-peer-graph"])
+def test_two_gpu_learner_equals_one_gpu_learner(mode, fuse, graph):
+    """fuse=True: ONE kernel per step with the in-kernel NVLink all-reduce (csrc/sgd_tail.cuh); fuse=False: NCCL."""
     import torch.multiprocessing as mp
     world = 2
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, fuse, graph)) for r in range(world)]
     for p in procs:
         p.start()
-    th2, stats2, n2, M2, same = q.get(timeout=300)
+    res = q.get(timeout=300)
+    if res[0] == "error":
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+        pytest.fail(f"rank {res[1]} failed:\n{res[2]}")
+    th2, stats2, n2, M2, same = res
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -92,7 +115,7 @@ def test_two_gpu_learner_equals_one_gpu_learner():
     shuffle = np.tile(np.asarray(order, dtype=np.int32), (pr["P"], 1))
     dev = torch.device("cuda", 0)
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    L = _learner(pr, dev, (T * C) // NB)
+    L = _learner(pr, dev, (T * C) // NB, mode)
     stats1 = L.learn_on_rollout(to(pr["raw"]), to(pr["boot"]), to(pr["rewards"]), to(pr["dones"]), to(pr["eps"]),
                                 to(pr["perms"]), to(shuffle))
     torch.cuda.synchronize()
