@@ -3,10 +3,11 @@
 //   barrier A (the G CTAs of a policy)                      partials visible
 //   slice reduce: CTA bx owns parameters [bx*S, bx*S+S) and sums them over the G partials — up to 8 thread groups load
 //                 different partials concurrently (one L2 round trip instead of G dependent ones), fixed summation order
-//   [world > 1]   in-kernel all-reduce over NVLink peer memory: the slice is PUSHED into every rank's exchange buffer
-//                 (plain peer stores), a system-scope release flag follows, the CTA polls its own flags for the peers'
-//                 slices and adds the `world` slices in rank order — every rank ends with bit-identical sums, one NVLink
-//                 one-way latency per step, no NCCL call, no extra launch
+//   [world > 1]   in-kernel all-reduce over NVLink peer memory, low-latency ("LL") style: every reduced element is PUSHED
+//                 into every rank's exchange buffer as ONE 64-bit store {value, sequence flag} — no fence, no separate
+//                 flag round trip — and the owner thread polls its own buffer until the `world` words carry this step's
+//                 sequence number, then adds them in rank order.  Every rank ends with bit-identical sums after one
+//                 NVLink one-way latency; no NCCL call, no extra launch.  Buffers alternate by step parity.
 //   barrier B     per-slice ||g||^2 visible -> global norm (same order everywhere), tf.clip_by_global_norm, TF1 Adam on
 //                 the slice, packed weight images kept in step
 //   ticket        the last CTA of the grid advances beta powers / step counter / exchange sequence and re-arms barriers
@@ -29,13 +30,13 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed_sys_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // one thread: arrive and wait until `target` CTAs have arrived; false on timeout
@@ -63,7 +64,10 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
     const int W = t.world > 1 ? t.world : 1;
     bool ok = true;
     __syncthreads();
-    if (tid == 0) red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)G) ? 1.f : 0.f;
+    if (tid == 0) {
+        red[40] = 1.f;
+        red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)G) ? 1.f : 0.f;
+    }
     __syncthreads();
     ok = ok && red[39] != 0.f;
 
@@ -73,10 +77,11 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
     const int ngrp = ncol4 >= nt ? 1 : max(1, min(min(8, G), nt / max(ncol4, 1)));
     const int cpp = nt / ngrp;                  // float4 columns per pass
     const unsigned int seq = (W > 1) ? *t.seq : 0u;
+    const unsigned long long want = (unsigned long long)(seq + 1u) << 32;     // flag half of the LL words of this step
     const int par = (int)(seq & 1u);
-    const int64_t xstride = (int64_t)G * S;     // floats per (rank, policy) in the exchange buffer
-    float* slice_dst = (W > 1) ? t.peer_x[t.rank] + (((int64_t)par * W + t.rank) * P + p) * xstride + j0
-                               : t.grad + (int64_t)p * NP + j0;
+    const int64_t xstride = (int64_t)G * S;     // words per (rank, policy) in the exchange buffer
+    const int64_t xoff = (((int64_t)par * W + t.rank) * P + p) * xstride + j0;   // this rank's slot, same in every buffer
+    float* slice_dst = t.grad + (int64_t)p * NP + j0;
     for (int c0 = 0; c0 < ncol4; c0 += cpp) {
         const int g = tid / cpp, c = c0 + (tid - g * cpp);
         if (g < ngrp && c < ncol4) {
@@ -98,8 +103,9 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
             const int jj = 4 * c0 + f;           // offset inside the slice
             if (j0 + jj < NP) {
                 if (W > 1) {
+                    const unsigned long long word = want | (unsigned long long)__float_as_uint(s);
                     for (int w = 0; w < W; ++w)   // push to every rank's exchange buffer (own copy included)
-                        t.peer_x[w][(((int64_t)par * W + t.rank) * P + p) * xstride + j0 + jj] = s;
+                        st_relaxed_sys_u64(t.peer_x[w] + xoff + jj, word);
                 } else {
                     slice_dst[jj] = s;
                 }
@@ -113,32 +119,25 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
         s = warp_sum(s);
         if (lane == 0) t.step_stats[((int64_t)step * P + p) * DDRL_NSTAT + warp] = s;
     }
-    // ---- data parallel: flags out, flags in, sum the world's slices in rank order -----------------------------------
+    // ---- data parallel: wait for the world's words of this step, add them in rank order -------------------------------
     if (W > 1) {
-        __syncthreads();                           // all pushes of this CTA issued
-        if (tid < W) {
-            const unsigned int want = seq + 1u;
-            __threadfence_system();                // cumulative: orders the CTA's pushes (observed via bar.sync) before the flag
-            if (tid != t.rank) st_relaxed_sys_u32(t.peer_flag[tid] + ((int64_t)t.rank * P + p) * G + bx, want);
-            bool got = true;
-            if (tid != t.rank) {
-                got = false;
-                const unsigned int* fl = t.peer_flag[t.rank] + ((int64_t)tid * P + p) * G + bx;
-                for (unsigned int i = 0; i < 4000000u; ++i) {
-                    if ((int)(ld_acquire_sys_u32(fl) - want) >= 0) { got = true; break; }
-                    __nanosleep(20);
-                }
-            }
-            red[40 + tid] = got ? 1.f : 0.f;
-        }
-        __syncthreads();
-        for (int w = 0; w < W; ++w) ok = ok && red[40 + w] != 0.f;
-        const float* xl = t.peer_x[t.rank] + ((int64_t)par * W * P + p) * xstride + j0;   // + w * P * xstride per rank
+        const unsigned long long* xl = t.peer_x[t.rank] + ((int64_t)par * W * P + p) * xstride + j0;   // + w * P * xstride
+        bool got = true;
         for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
             float s = 0.f;
-            for (int w = 0; w < W; ++w) s += __ldcg(xl + (int64_t)w * P * xstride + jj);
-            t.grad[(int64_t)p * NP + j0 + jj] = s;
+            for (int w = 0; w < W; ++w) {
+                const unsigned long long* src = xl + (int64_t)w * P * xstride + jj;
+                unsigned long long word = ld_relaxed_sys_u64(src);
+                for (unsigned int i = 0; (word >> 32) != (want >> 32) && i < 2000000u; ++i) {
+                    __nanosleep(20);
+                    word = ld_relaxed_sys_u64(src);
+                }
+                got = got && (word >> 32) == (want >> 32);
+                s += __uint_as_float((unsigned int)word);
+            }
+            slice_dst[jj] = s;
         }
+        if (!got) red[40] = 0.f;      // benign race: every writer stores the same value
     }
     __syncthreads();
     // ---- ||g||^2 of the slice (fixed order) -> barrier B -> global norm ------------------------------------------------
@@ -150,6 +149,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
     ss = warp_sum(ss);
     if (lane == 0) red[warp] = ss;
     __syncthreads();
+    ok = ok && red[40] != 0.f;
     if (tid == 0) {
         float s = 0.f;
         for (int w = 0; w < nw; ++w) s += red[w];
@@ -244,7 +244,7 @@ inline int sgd_tail_check(const ddrl_sgd_tail* tail, int ctas_total, const char*
         DDRL_REQUIRE(tail->world <= DDRL_MAX_RANKS && tail->rank >= 0 && tail->rank < tail->world && tail->seq, DDRL_E_BADARG,
                      "%s: fused tail: bad world/rank/seq (world <= %d)", who, DDRL_MAX_RANKS);
         for (int w = 0; w < tail->world; ++w)
-            DDRL_REQUIRE(tail->peer_x[w] && tail->peer_flag[w], DDRL_E_BADARG, "%s: fused tail: peer buffer %d missing", who, w);
+            DDRL_REQUIRE(tail->peer_x[w], DDRL_E_BADARG, "%s: fused tail: peer buffer %d missing", who, w);
     }
     return DDRL_OK;
 }

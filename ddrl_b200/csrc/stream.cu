@@ -560,7 +560,7 @@ extern "C" int ddrl_leg_coupling(float* logits, const int32_t* node_id, const fl
     return DDRL_OK;
 }
 
-extern "C" int64_t ddrl_sgd_exchange_floats(int NP, int ctas_per_policy) {
+extern "C" int64_t ddrl_sgd_exchange_words(int NP, int ctas_per_policy) {
     if (NP < 1 || ctas_per_policy < 1) return DDRL_E_BADARG;
     return (int64_t)ctas_per_policy * sgd_slice_len(NP, ctas_per_policy);
 }

@@ -1,9 +1,9 @@
 """Peer-mapped exchange buffers for the in-kernel gradient all-reduce (one process per GPU, one node).
 
-Every rank allocates one exchange buffer and one flag array through the C ABI (``ddrl_peer_alloc``: cudaMalloc + CUDA
+Every rank allocates one exchange buffer through the C ABI (``ddrl_peer_alloc``: cudaMalloc + CUDA
 IPC handle), the 64-byte handles travel through ``torch.distributed.all_gather_object`` and every rank maps the other
 ranks' allocations (``ddrl_peer_open``).  The fused SGD tail (csrc/sgd_tail.cuh) then pushes its gradient slices straight
-into the peers' buffers over NVLink; no NCCL call is made on the per-step path."""
+into the peers' buffers over NVLink as 64-bit {value, sequence} words; no NCCL call is made on the per-step path."""
 from __future__ import annotations
 
 import ctypes as C
@@ -23,26 +23,18 @@ class PeerExchange:
             raise DDRLError(f"in-kernel all-reduce supports up to {MAX_RANKS} ranks, got {world}")
         lib = _lib.load()
         self.world, self.rank, self.key = world, rank, (P, NP, G)
-        xfloats = int(lib.ddrl_sgd_exchange_floats(NP, G))
-        if xfloats <= 0:
-            raise DDRLError("ddrl_sgd_exchange_floats failed")
-        self.x_bytes = 2 * world * P * xfloats * 4
-        self.flag_bytes = world * P * G * 4
+        words = int(lib.ddrl_sgd_exchange_words(NP, G))
+        if words <= 0:
+            raise DDRLError("ddrl_sgd_exchange_words failed")
+        self.x_bytes = 2 * world * P * words * 8          # two step parities x {value, sequence} words
         self._own: List[int] = []
         self._opened: List[int] = []
         with torch.cuda.device(device):
             hx, px = self._alloc(lib, self.x_bytes)
-            hf, pf = self._alloc(lib, self.flag_bytes)
             torch.cuda.synchronize()
             handles = [None] * world
-            dist.all_gather_object(handles, (hx, hf))
-            self.x_ptrs, self.flag_ptrs = [0] * world, [0] * world
-            for w in range(world):
-                if w == rank:
-                    self.x_ptrs[w], self.flag_ptrs[w] = px, pf
-                else:
-                    self.x_ptrs[w] = self._open(lib, handles[w][0])
-                    self.flag_ptrs[w] = self._open(lib, handles[w][1])
+            dist.all_gather_object(handles, hx)
+            self.x_ptrs = [px if w == rank else self._open(lib, handles[w]) for w in range(world)]
             dist.barrier()     # everybody has mapped everybody before the first step may push
         self.seq = torch.zeros(1, dtype=torch.int32, device=device)
 
@@ -66,7 +58,6 @@ class PeerExchange:
         tail.seq = self.seq.data_ptr()
         for w in range(self.world):
             tail.peer_x[w] = self.x_ptrs[w]
-            tail.peer_flag[w] = self.flag_ptrs[w]
 
     def close(self) -> None:
         lib = _lib.load()

@@ -163,10 +163,9 @@ typedef struct {
  *   barrier_ws: 4*P + 4 zero-initialised uint32 (re-armed by the kernel); sq_ws: P * ctas_per_policy floats;
  *   status: device int or NULL, receives |= 64 when a bounded spin of the tail gave up (results then invalid).
  * Data parallel (world > 1; one process per GPU, every rank launches the same step with the same shapes):
- *   seq       device uint32, zero-initialised once, advanced by the kernel every step (flags carry seq + 1);
- *   peer_x[w] exchange buffer of rank w (peer-mapped, ddrl_peer_alloc/open; [rank] = the local one):
- *             2 * world * P * ddrl_sgd_exchange_floats(NP, ctas_per_policy) floats;
- *   peer_flag[w] flag array of rank w: world * P * ctas_per_policy zero-initialised uint32.
+ *   seq       device uint32, zero-initialised once, advanced by the kernel every step;
+ *   peer_x[w] exchange buffer of rank w (peer-mapped, ddrl_peer_alloc/open; [rank] = the local one), zero-initialised:
+ *             2 * world * P * ddrl_sgd_exchange_words(NP, ctas_per_policy) 64-bit words {float value, uint32 seq + 1}.
  * Every rank ends each step with bit-identical gradients (slices are summed in rank order) and weights. */
 #define DDRL_MAX_RANKS 8
 typedef struct {
@@ -180,12 +179,11 @@ typedef struct {
     int32_t* status;          /* device int or NULL: OR-ed with 64 if a barrier / peer wait of the tail timed out */
     int32_t world, rank;
     uint32_t* seq;
-    float* peer_x[DDRL_MAX_RANKS];
-    uint32_t* peer_flag[DDRL_MAX_RANKS];
+    unsigned long long* peer_x[DDRL_MAX_RANKS];
 } ddrl_sgd_tail;
 
-/* floats per (rank, policy) in the exchange buffer: ctas_per_policy slices of ((NP + G - 1) / G rounded up to 4) */
-int64_t ddrl_sgd_exchange_floats(int NP, int ctas_per_policy);
+/* 64-bit words per (rank, policy) in the exchange buffer: ctas_per_policy slices of ((NP + G - 1) / G rounded up to 4) */
+int64_t ddrl_sgd_exchange_words(int NP, int ctas_per_policy);
 
 /* Peer-mapped device memory for the in-kernel all-reduce (CUDA IPC; one process per GPU on one node).
  *   ddrl_peer_alloc: cudaMalloc + zero-fill `bytes` on the current device; *ptr = device pointer, handle64 = 64-byte

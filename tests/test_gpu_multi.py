@@ -91,7 +91,7 @@ def test_two_gpu_learner_equals_one_gpu_learner(mode, fuse, graph):
     for p in procs:
         p.start()
     res = q.get(timeout=300)
-    if res[0] == "error":
+    if isinstance(res[0], str) and res[0] == "error":
         for p in procs:
             p.join(timeout=30)
             if p.is_alive():
