@@ -243,8 +243,11 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"   # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -309,9 +312,11 @@ def main():
     clk = clocks.stop()
     # kernels per iteration: API launches outside the captured graph + graph replays x nodes
     steps_per_iter = E * nb
-    fused = world == 1 and L.fuse_tail and L._sgd_setup(R)[2] * P <= L.sms     # train kernel carries reduce + clip + Adam
+    G_ = L._sgd_setup(R)[2]
+    fused = L.fuse_tail and G_ * P <= L.sms     # train kernel carries reduce + [peer all-reduce] + clip + Adam
     per_sgd = 1 if fused else 3
-    launches_per_iter = 1 + 2 + 2 + 2 + 1 + 7 + steps_per_iter * per_sgd   # pack, filter x2, fwd x2, gae x2, standardise, 7 gathers, sgd
+    sgd_launches = E if L._persistent_steps(G_) else steps_per_iter * per_sgd    # persistent: one launch per epoch
+    launches_per_iter = 1 + 2 + 2 + 2 + 1 + 7 + sgd_launches   # pack, filter x2, fwd x2, gae x2, standardise, 7 gathers, sgd
     ms_e2e = timed(step_e2e, max(1, args.warmup // 2), max(3, args.steps // 2))
     e2e_steps = max(3, args.steps // 2)
 
@@ -381,6 +386,7 @@ def main():
                        "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
                        "cuda_graph": bool(L.use_graph and L._graph is not None), "sgd_kernel": args.mode,
                        "kernels_per_sgd_step": per_sgd,
+                       "persistent_sgd_launch": bool(L._persistent_steps(G_)),
                        "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),
@@ -391,6 +397,8 @@ def main():
             "cpu_baseline": cpu,
             "flops_per_agent_step": flops_per_agent_step(D, A, E),
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         # release the captured graph (it holds NCCL work) before tearing the communicator down, and never let the

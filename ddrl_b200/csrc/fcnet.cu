@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
     }
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
         __threadfence();
-        sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A, sm + L.h1);
+        sgd_step_tail(a.tail, tail_single_step(a.tail, p), a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A, sm + L.h1);
     }
 }
 
@@ -685,6 +685,7 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const f
         DDRL_REQUIRE(!ext, DDRL_E_BADARG, "ppo_train_step: the fused tail cannot be combined with external gradients");
         const int rc = sgd_tail_check(tail, ctas_per_policy * P, "ppo_train_step");
         if (rc != DDRL_OK) return rc;
+        DDRL_REQUIRE(tail->nsteps <= 1, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step: nsteps > 1 is not supported by the FP32 kernel");
         a.tail = *tail;
     }
     const FcSmem L = fc_smem(D, A, false, true);

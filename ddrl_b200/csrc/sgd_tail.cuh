@@ -40,9 +40,10 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
 }
 
 // one thread: arrive and wait until `target` CTAs have arrived; false on timeout
-__device__ __forceinline__ bool grid_group_barrier(unsigned int* ctr, unsigned int target) {
+__device__ __noinline__ static bool grid_group_barrier(unsigned int* ctr, unsigned int target) {
     __threadfence();
     atomicAdd(ctr, 1u);
+#pragma unroll 1
     for (unsigned int i = 0; i < 4000000u; ++i) {
         if (ld_acquire_u32(ctr) >= target) return true;
         __nanosleep(20);
@@ -52,31 +53,73 @@ __device__ __forceinline__ bool grid_group_barrier(unsigned int* ctr, unsigned i
 
 __host__ __device__ inline int sgd_slice_len(int NP, int G) { return (((NP + G - 1) / G) + 3) & ~3; }
 
+// Inlined on purpose (an out-of-line call made the whole kernel 6 us slower: parameter struct copied to a local stack,
+// ABI register constraints); kernels keep ONE call site.
 // Called by every thread of every CTA after the partial gradient (and stat partial) of this CTA has been written.
 // smem: 16 * blockDim.x + 256 bytes of (16-byte aligned) shared memory.  Returns false if a barrier or a peer wait timed out.
-__device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __restrict__ grad_part,
+//
+// A launch may run several consecutive SGD steps ("persistent" kernels, ddrl_sgd_tail.nsteps > 1): TailStep carries the
+// per-step state the caller keeps in registers.  Barrier counters count up across the steps of a launch (target =
+// G * round) and are re-armed by the ticket of the LAST step; between steps the tail ends with an arrival on barrier C
+// (all of this policy's Adam slices written) which the caller awaits with sgd_wait_weights() before reloading weights.
+struct TailStep {
+    int round;           // 1-based step number inside this launch
+    bool last;           // last step of the launch: ticket (step counter, sequence, barrier re-arm) instead of barrier C
+    float b1p, b2p;      // beta1^t, beta2^t of THIS step (read from beta_pow at kernel entry, advanced by the caller)
+    unsigned int seq;    // exchange sequence number of this step (world > 1): *t.seq at kernel entry + round - 1
+    int nsteps;          // steps in this launch (the ticket advances the clocks by it)
+};
+__device__ __forceinline__ TailStep tail_single_step(const SgdTail& t, int p) {
+    TailStep ts;
+    ts.round = 1; ts.last = true; ts.nsteps = 1;
+    ts.b1p = __ldcg(t.beta_pow + p * 2); ts.b2p = __ldcg(t.beta_pow + p * 2 + 1);
+    ts.seq = (t.world > 1) ? *t.seq : 0u;
+    return ts;
+}
+// wait until every CTA of policy p has finished the Adam slice of step `round` (one thread per CTA calls this)
+__device__ __forceinline__ bool sgd_wait_weights(const SgdTail& t, int p, int G, int round) {
+#pragma unroll 1
+    for (unsigned int i = 0; i < 4000000u; ++i) {
+        if (ld_acquire_u32(t.barrier_ws + 4 * p + 2) >= (unsigned)(G * round)) return true;
+        __nanosleep(20);
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& ts, const float* __restrict__ grad_part,
                                               const double* __restrict__ stat_part, int p, int P, int bx, int G, int NP,
-                                              int step, int D, int A, float* smem) {
+                                              int step, int D, int A, float* smem, long long* dbg = nullptr) {
+#define TAIL_STAMP(i) do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[i] = clock64(); } while (0)
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int NPs = (NP + 3) & ~3;
     float4* scr = reinterpret_cast<float4*>(smem);
     float* red = smem + 4 * nt;                 // [64]: warp partials, flags
     const int W = t.world > 1 ? t.world : 1;
     bool ok = true;
+    // optimizer state of this thread's element: independent of everything below, so the loads fly behind barrier A
+    const int S_pf = sgd_slice_len(NP, G);
+    const bool pf = S_pf <= nt;
+    const int j_pf = bx * S_pf + tid;
+    float m_pf = 0.f, v_pf = 0.f, th_pf = 0.f;
+    if (pf && tid < S_pf && j_pf < NP) {
+        const int64_t k = (int64_t)p * NP + j_pf;
+        m_pf = __ldcg(t.m + k); v_pf = __ldcg(t.v + k); th_pf = __ldcg(t.theta + k);
+    }
     __syncthreads();
     if (tid == 0) {
         red[40] = 1.f;
-        red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)G) ? 1.f : 0.f;
+        red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)(G * ts.round)) ? 1.f : 0.f;
     }
     __syncthreads();
     ok = ok && red[39] != 0.f;
+    TAIL_STAMP(40);
 
     // ---- slice reduce over the G partials --------------------------------------------------------------------------
     const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S);
     const int ncol4 = max(0, (j1 - j0) >> 2);
     const int ngrp = ncol4 >= nt ? 1 : max(1, min(min(8, G), nt / max(ncol4, 1)));
     const int cpp = nt / ngrp;                  // float4 columns per pass
-    const unsigned int seq = (W > 1) ? *t.seq : 0u;
+    const unsigned int seq = ts.seq;
     const unsigned long long want = (unsigned long long)(seq + 1u) << 32;     // flag half of the LL words of this step
     const int par = (int)(seq & 1u);
     const int64_t xstride = (int64_t)G * S;     // words per (rank, policy) in the exchange buffer
@@ -87,10 +130,15 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
         if (g < ngrp && c < ncol4) {
             const float4* src = reinterpret_cast<const float4*>(grad_part + (int64_t)p * G * NPs + j0) + c;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-            for (int i = g; i < G; i += ngrp) {
-                const float4 v = __ldcg(src + (int64_t)i * (NPs >> 2));
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            const int64_t pstride = (int64_t)ngrp * (NPs >> 2);
+#pragma unroll 1
+            for (int i0 = g; i0 < G; i0 += 8 * ngrp) {     // 8 independent loads in flight, then the (fixed-order) adds
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    v[k] = (i0 + k * ngrp < G) ? __ldcg(src + (int64_t)i0 * (NPs >> 2) + k * pstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
             }
             scr[g * cpp + (c - c0)] = acc;
         }
@@ -104,6 +152,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
             if (j0 + jj < NP) {
                 if (W > 1) {
                     const unsigned long long word = want | (unsigned long long)__float_as_uint(s);
+#pragma unroll 1
                     for (int w = 0; w < W; ++w)   // push to every rank's exchange buffer (own copy included)
                         st_relaxed_sys_u64(t.peer_x[w] + xoff + jj, word);
                 } else {
@@ -125,9 +174,11 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
         bool got = true;
         for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
             float s = 0.f;
+#pragma unroll 1
             for (int w = 0; w < W; ++w) {
                 const unsigned long long* src = xl + (int64_t)w * P * xstride + jj;
                 unsigned long long word = ld_relaxed_sys_u64(src);
+#pragma unroll 1
                 for (unsigned int i = 0; (word >> 32) != (want >> 32) && i < 2000000u; ++i) {
                     __nanosleep(20);
                     word = ld_relaxed_sys_u64(src);
@@ -140,6 +191,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
         if (!got) red[40] = 0.f;      // benign race: every writer stores the same value
     }
     __syncthreads();
+    TAIL_STAMP(41);
     // ---- ||g||^2 of the slice (fixed order) -> barrier B -> global norm ------------------------------------------------
     float ss = 0.f;
     for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
@@ -154,10 +206,11 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
         float s = 0.f;
         for (int w = 0; w < nw; ++w) s += red[w];
         t.sq_ws[p * G + bx] = s;
-        red[39] = grid_group_barrier(t.barrier_ws + 4 * p + 1, (unsigned)G) ? 1.f : 0.f;
+        red[39] = grid_group_barrier(t.barrier_ws + 4 * p + 1, (unsigned)(G * ts.round)) ? 1.f : 0.f;
     }
     __syncthreads();
     ok = ok && red[39] != 0.f;
+    TAIL_STAMP(42);
     if (warp == 0) {
         float s = 0.f;
         for (int i = lane; i < G; i += 32) s += __ldcg(t.sq_ws + p * G + i);
@@ -171,18 +224,18 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
     __syncthreads();
     // ---- clip + TF1 Adam on the slice ---------------------------------------------------------------------------------
     const float scale = red[32];
-    const float b1p = __ldcg(t.beta_pow + p * 2), b2p = __ldcg(t.beta_pow + p * 2 + 1);
+    const float b1p = ts.b1p, b2p = ts.b2p;
     const float alpha = t.lr * sqrtf(1.f - b2p) / (1.f - b1p);
     for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
         const int j = j0 + jj;
         const int64_t k = (int64_t)p * NP + j;
         const float gj = __ldcg(t.grad + k) * scale;
-        float mj = t.m[k], vj = t.v[k];
+        float mj = pf ? m_pf : t.m[k], vj = pf ? v_pf : t.v[k];
         mj += (gj - mj) * (1.f - t.beta1);
         vj += (gj * gj - vj) * (1.f - t.beta2);
         t.m[k] = mj;
         t.v[k] = vj;
-        const float tnew = t.theta[k] - (mj * alpha) / (sqrtf(vj) + t.eps);
+        const float tnew = (pf ? th_pf : t.theta[k]) - (mj * alpha) / (sqrtf(vj) + t.eps);
         t.theta[k] = tnew;
         if (t.fcnet_img) {
             const FcSmem L = fc_smem(D, A, false);
@@ -210,26 +263,36 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const float* __r
             }
         }
     }
-    // ---- done ticket: the last CTA of the grid advances the optimizer clocks and re-arms the barriers ---------------
+    // ---- end of step: barrier-C arrival (more steps follow in this launch) or the done ticket (last step) -----------------
     __syncthreads();
+    TAIL_STAMP(43);
     if (tid == 0) {
         __threadfence();
-        const unsigned int total = gridDim.x * gridDim.y;
-        if (atomicAdd(t.barrier_ws + 4 * P, 1u) == total - 1) {
-            for (int q = 0; q < P; ++q) {
-                t.beta_pow[q * 2] *= t.beta1;
-                t.beta_pow[q * 2 + 1] *= t.beta2;
-                t.barrier_ws[4 * q] = 0u;
-                t.barrier_ws[4 * q + 1] = 0u;
+        if (!ts.last) {
+            atomicAdd(t.barrier_ws + 4 * p + 2, 1u);       // this CTA's Adam slice of step `round` is visible
+        } else {
+            if (bx == 0) {     // every CTA read beta_pow at kernel entry (before its first barrier-A arrival): safe to advance
+                t.beta_pow[p * 2] = ts.b1p * t.beta1;
+                t.beta_pow[p * 2 + 1] = ts.b2p * t.beta2;
             }
-            if (t.step_ctr) *t.step_ctr += 1;
-            if (t.seq) *t.seq = seq + 1u;
-            t.barrier_ws[4 * P] = 0u;
-            __threadfence();
+            const unsigned int total = gridDim.x * gridDim.y;
+            if (atomicAdd(t.barrier_ws + 4 * P, 1u) == total - 1) {   // last CTA of the grid: clocks, re-arm
+                for (int q = 0; q < P; ++q) {
+                    t.barrier_ws[4 * q] = 0u;
+                    t.barrier_ws[4 * q + 1] = 0u;
+                    t.barrier_ws[4 * q + 2] = 0u;
+                }
+                if (t.step_ctr) *t.step_ctr += ts.nsteps;
+                if (t.seq) *t.seq = ts.seq + 1u;
+                t.barrier_ws[4 * P] = 0u;
+                __threadfence();
+            }
         }
         if (!ok && t.status) atomicOr(t.status, 64);
     }
+    TAIL_STAMP(44);
     return ok;
+#undef TAIL_STAMP
 }
 
 // Host-side validation shared by the launchers.
@@ -240,6 +303,7 @@ inline int sgd_tail_check(const ddrl_sgd_tail* tail, int ctas_total, const char*
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     DDRL_REQUIRE(ctas_total <= sms, DDRL_E_BADARG, "%s: fused tail needs all %d CTAs co-resident (%d SMs)", who, ctas_total, sms);
+    DDRL_REQUIRE(tail->nsteps >= 0, DDRL_E_BADARG, "%s: fused tail: nsteps must be >= 0", who);
     if (tail->world > 1) {
         DDRL_REQUIRE(tail->world <= DDRL_MAX_RANKS && tail->rank >= 0 && tail->rank < tail->world && tail->seq, DDRL_E_BADARG,
                      "%s: fused tail: bad world/rank/seq (world <= %d)", who, DDRL_MAX_RANKS);

@@ -108,6 +108,81 @@ extern "C" int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B
     return DDRL_OK;
 }
 
+// Micro-benchmark: `reps` back-to-back tcgen05.mma (kind::f16, M x N x 16) issued by one thread on garbage operands of the
+// chunked layout; cycles[0] = issue loop only, cycles[1] = issue + commit + completion wait.  Sizes the MMA schedule.
+namespace ddrl {
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(int M, int N, int a_mn, int b_mn, int reps, int ksteps,
+                                                            long long* __restrict__ cycles, int* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smraw)[i] = 0x3c003c00u;   // 1.0h
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t taddr = tmem_slot;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    bool ok = true;
+    if (warp == 0) {
+        const uint32_t idesc = umma::idesc_f16(M, N, a_mn != 0, b_mn != 0);
+        const uint32_t sa = umma::smem_u32(smraw), sb = sa + 48 * 1024;
+        const uint64_t ad0 = a_mn ? umma::desc_mnmajor(sa, 128) : umma::desc_kmajor(sa, 128);
+        const uint64_t bd0 = b_mn ? umma::desc_mnmajor(sb, 128) : umma::desc_kmajor(sb, 128);
+        const uint64_t astep = a_mn ? 16u : 256u, bstep = b_mn ? 16u : 256u;
+        // mode (ksteps >> 8): 0 = `if (lane == 0)` branch; 1 = elect.sync-selected lane, warp-uniform control flow around it
+        const int mode = ksteps >> 8;
+        ksteps &= 255;
+        uint32_t elected = 0;
+        if (mode == 1) {
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+        } else {
+            elected = (tid == 0);
+        }
+        t0 = clock64();
+        if (elected) {
+            for (int r = 0; r < reps; ++r) {
+                uint64_t ad = ad0, bd = bd0;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    umma::mma_f16(taddr, ad, bd, idesc, true);
+                    ad += astep; bd += bstep;
+                }
+            }
+        }
+        __syncwarp();
+        t1 = clock64();
+        if (elected) umma::mma_commit(&mbar);
+        __syncwarp();
+        ok = umma::mbar_wait(&mbar, 0);
+        t2 = clock64();
+        if (tid == 0) {
+            cycles[0] = t1 - t0;
+            cycles[1] = t2 - t0;
+            *status = ok ? 0 : 1;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(taddr, 512);
+}
+}  // namespace ddrl
+
+extern "C" int ddrl_umma_bench(int M, int N, int a_mn, int b_mn, int reps, int ksteps, void* cycles2, int* status, void* stream) {
+    DDRL_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && reps >= 1 && (ksteps & 255) >= 1 && (ksteps & 255) <= 8 && cycles2 && status,
+                 DDRL_E_BADARG, "umma_bench: bad arguments");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(ddrl::umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+    }
+    ddrl::umma_bench_kernel<<<1, 128, 96 * 1024, (cudaStream_t)stream>>>(M, N, a_mn, b_mn, reps, ksteps, (long long*)cycles2, status);
+    DDRL_CHECK_LAUNCH("umma_bench");
+    return DDRL_OK;
+}
+
 // =================================================================================================================
 // Tensor-core FCNet training step: same contract as fcnet_train_kernel (csrc/fcnet.cu) — one minibatch of all
 // policies, fused forward + PPO loss + backward, per-CTA partial gradients in flat checkpoint order — with every
@@ -202,16 +277,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
     const int NPs = (o.NP + 3) & ~3;
     float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    do {   // single exit towards the fused tail (one inlined copy of it)
     if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
         for (int i = tid; i < o.NP; i += TC_NT) gp[i] = 0.f;
         if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
-        if (a.tail.theta) {
-            __threadfence();
-            const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                           reinterpret_cast<float*>(sm + S.H1[0]));
-            if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
-        }
-        return;
+        break;
     }
 
     const float* obs_p = a.obs + (int64_t)p * a.R * D;
@@ -521,9 +591,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, TC_TMEM_COLS);
+    } while (0);
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
         __threadfence();
-        const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+        const bool tok = sgd_step_tail(a.tail, tail_single_step(a.tail, p), a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
                                        reinterpret_cast<float*>(sm + S.H1[0]));
         if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
     }
@@ -570,6 +641,17 @@ extern "C" int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void*
 }
 
 static int g_tc_variant = 0;   // 0 = automatic, 1 = branch-sequential kernel, 2 = ping-pong kernel
+static long long* g_tc_dbg_clock = nullptr;
+
+extern "C" int ddrl_tc_pingpong_eligible(int D, int A) {
+    if (D < 1 || D > DDRL_MAX_OBS - 1 || !(A == 1 || A == 2 || A == 4 || A == 8)) return 0;
+    return (g_tc_variant != 1 && A <= 4 && tc2_eligible(D, A)) ? 1 : 0;
+}
+
+extern "C" int ddrl_tc_set_debug_clock(void* device_int64x64) {
+    g_tc_dbg_clock = reinterpret_cast<long long*>(device_int64x64);
+    return DDRL_OK;
+}
 
 extern "C" int ddrl_tc_set_variant(int variant) {
     DDRL_REQUIRE(variant >= 0 && variant <= 2, DDRL_E_BADARG, "tc_set_variant: variant must be 0, 1 or 2");
@@ -607,11 +689,15 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     a.old_logp = old_logp; a.vf_preds = vf_preds; a.adv = adv; a.vtarg = vtarg; a.R = R; a.D = D; a.A = A; a.MB = MB;
     a.mb_perm = mb_perm; a.perm_stride = perm_stride; a.step_ctr = step_ctr; a.kl_coeff = kl_coeff; a.hp = *hyper;
     a.grad_part = grad_part; a.stat_part = stat_part; a.status = status;
+    a.dbg_clock = g_tc_dbg_clock;
     a.tail = SgdTail{};
     if (tail) {
         const int rc = sgd_tail_check(tail, ctas_per_policy * P, "ppo_train_step_tc");
         if (rc != DDRL_OK) return rc;
         a.tail = *tail;
+        const bool pp = g_tc_variant == 2 || (g_tc_variant == 0 && tc2_eligible(D, A));
+        DDRL_REQUIRE(tail->nsteps <= 1 || pp, DDRL_E_UNSUPPORTED_SHAPE,
+                     "ppo_train_step_tc: nsteps > 1 needs the ping-pong kernel (D <= 30, A <= 4)");
     }
     const size_t smem = (size_t)tc_smem(D, A).total;
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);

@@ -19,8 +19,13 @@
 namespace ddrl {
 
 // TMEM columns: per-branch forward/backward accumulator, head outputs, and the weight-gradient accumulators
-constexpr int T2_DACC = 0, T2_HOUT = 128, T2_GW2 = 160, T2_GW1 = 288, T2_GB2 = 352, T2_GWH = 384, T2_TMEM_COLS = 512;
-constexpr int T2_ISSUER = TC_NT - 32;   // lane 0 of warp 15
+// GW1 and GWH exist twice per branch ([2b + s]: s = 0 takes the hi*hi product, s = 1 the two cross products) so that two
+// MMA warps can issue one weight-gradient GEMM concurrently; the halves are added at the write-out.
+constexpr int T2_DACC = 0, T2_HOUT = 128, T2_GW2 = 160, T2_GW1 = 288, T2_GB2 = 416, T2_GWH = 448, T2_TMEM_COLS = 512;
+constexpr int T2_NMMA = 4;                   // MMA-issue warps: one thread issues a tcgen05.mma every ~72 cycles whatever its
+                                             // shape (tests/umma_bench.py), so the ~270 MMAs of a tile are spread over 4 issuers
+constexpr int T2_NT = TC_NT + 32 * T2_NMMA;  // 16 epilogue warps + the MMA-issue warps
+constexpr int T2_MMA_WARP = TC_NT / 32;      // first MMA warp (16); these warps never touch an accumulator
 
 __device__ __forceinline__ void t2_split2(float x0, float x1, uint32_t& h, uint32_t& l) {
     const __half2 hh = __floats2half2_rn(x0, x1);
@@ -82,9 +87,15 @@ __device__ __noinline__ bool t2_epi_grad(uint32_t taddr, float inv_in, float out
     return !(mx * out_scale <= 60000.f);
 }
 
+#define T2_STAMP(i)                                                                        \
+    do {                                                                                   \
+        if (a.dbg_clock && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg_clock[i] = clock64(); \
+    } while (0)
+
 template <int A>
-__global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrainArgs a) {
+__global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrainArgs a) {
     constexpr int A2 = 2 * A;
+    T2_STAMP(0);
     extern __shared__ __align__(1024) unsigned char sm[];
     const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
     const int D = a.D, KX = tc_kx(D);
@@ -97,24 +108,66 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     float* sgs = reinterpret_cast<float*>(sm + S.bar + 24);             // [2]: per-branch gradient scale
     const uint32_t sbase = umma::smem_u32(sm);
 
-    const int step = a.step_ctr ? *a.step_ctr : 0;
+    // ---- once per launch: TMEM, mbarriers, launch-wide state -------------------------------------------------------------
+    if (warp == 0) umma::tmem_alloc(tslot, T2_TMEM_COLS);
+    if (tid == 0) { umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::fence_mbar_init(); }   // every MMA warp commits
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    uint32_t ph0 = 0, ph1 = 0;
+    bool ok = true;
+    int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 8 = dl, 16 = dz2, 32 = dz1
+    const float klc = a.kl_coeff[p];
+    const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
+    const int NPs = (o.NP + 3) & ~3;
+    float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    const bool has_tail = a.tail.theta != nullptr;
+    const int nsteps = (has_tail && a.tail.nsteps > 1) ? a.tail.nsteps : 1;   // consecutive SGD steps of this launch
+    const int step0 = a.step_ctr ? *a.step_ctr : 0;
+    TailStep ts;
+    ts.round = 0; ts.last = false; ts.nsteps = nsteps; ts.b1p = 0.f; ts.b2p = 0.f; ts.seq = 0u;
+    if (has_tail) {
+        ts.b1p = __ldcg(a.tail.beta_pow + p * 2);
+        ts.b2p = __ldcg(a.tail.beta_pow + p * 2 + 1);
+        ts.seq = (a.tail.world > 1) ? *a.tail.seq : 0u;
+    }
+
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+    if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
+        if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
+        __syncthreads();
+    }
+    if (warp < T2_MMA_WARP) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
+        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+#pragma unroll 2
+        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    T2_STAMP(35);
+    const int step = step0 + s;
     const int mb = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step] : step;
     const int64_t mb0 = (int64_t)mb * a.MB;
+    if (mb0 >= 0) T2_STAMP(36);
+    bool first = true;
+    // loss warps: 0-3 policy part (s0 = -surr, s1 = KL, s2 = entropy), 4-7 value part (s0 = vf, s1..4 = R, R^2, R-v, (R-v)^2)
+    double st[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) st[i] = 0.0;
+    float gbh[A2];   // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0]
+#pragma unroll
+    for (int i = 0; i < A2; ++i) gbh[i] = 0.f;
     const int64_t mb1 = min(mb0 + a.MB, a.R);
     const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
     const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
-    const int NPs = (o.NP + 3) & ~3;
-    float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    do {   // single exit towards the fused tail (one inlined copy of it)
     if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
-        for (int i = tid; i < o.NP; i += TC_NT) gp[i] = 0.f;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        for (int i = tid; i < o.NP; i += T2_NT) gp[i] = 0.f;
         if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
-        if (a.tail.theta) {
-            __threadfence();
-            const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                           reinterpret_cast<float*>(sm + S.H1[0][0]));
-            if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
-        }
-        return;
+        break;
     }
 
     const float* obs_p = a.obs + (int64_t)p * a.R * D;
@@ -126,6 +179,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     const float* sbvo = reinterpret_cast<const float*>(sm + I.bvo);
 
     auto prefetch_x = [&](int64_t r0, int n) {
+#pragma unroll 1
         for (int i = tid; i < n * D; i += TC_NT) tc_cp4(xraw + i, obs_p + r0 * D + i);
     };
     auto prefetch_loss = [&](int64_t r0, int n) {
@@ -133,8 +187,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         float* pa = pf;
         float* po = pa + TC_ROWS * A;
         float* ps = po + TC_ROWS * A2;
+#pragma unroll 1
         for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, a.actions + g0 * A + i);
+#pragma unroll 1
         for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+#pragma unroll 1
         for (int i = tid; i < n; i += TC_NT) {
             tc_cp4(ps + i, a.old_logp + g0 + i);
             tc_cp4(ps + TC_ROWS + i, a.vf_preds + g0 + i);
@@ -143,53 +200,132 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
     };
 
-    // ---- setup: TMEM, mbarriers, weights image, first tile's inputs ------------------------------------------------
-    if (warp == 0) umma::tmem_alloc(tslot, T2_TMEM_COLS);
-    if (tid == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(mbar + 1, 1); umma::fence_mbar_init(); }
-    {
-        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
-        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+    // ---- this step's first tile: inputs ---------------------------------------------------------------------------------
+    if (warp < T2_MMA_WARP) {
         const int n0 = (int)min((int64_t)TC_ROWS, cr1 - cr0);
         prefetch_x(cr0, n0);
         prefetch_loss(cr0, n0);
         asm volatile("cp.async.commit_group;\n" ::);
     }
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem = *tslot;
-    const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    uint32_t ph0 = 0, ph1 = 0;
-    bool ok = true, first = true;
-    int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 8 = dl, 16 = dz2, 32 = dz1
-    const float klc = a.kl_coeff[p];
-    // loss warps: 0-3 policy part (s0 = -surr, s1 = KL, s2 = entropy), 4-7 value part (s0 = vf, s1..4 = R, R^2, R-v, (R-v)^2)
-    double st[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) st[i] = 0.0;
-    float gbh[A2];   // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0]
-#pragma unroll
-    for (int i = 0; i < A2; ++i) gbh[i] = 0.f;
-    const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
+    T2_STAMP(1);
 
     auto wait_b = [&](int b) {
         if (b == 0) { ok = umma::mbar_wait(mbar, ph0) && ok; ph0 ^= 1; }
         else        { ok = umma::mbar_wait(mbar + 1, ph1) && ok; ph1 ^= 1; }
         umma::fence_after_sync();
     };
-    auto publish = [&]() {   // generic smem writes -> async proxy, TMEM reads retired, then CTA barrier
+    // epilogue warps -> MMA warp hand-off: generic smem writes -> async proxy, TMEM reads retired, then a barrier that the
+    // MMA warp joins (it issues right behind it).  The MMA warp is a warp of its own ON PURPOSE: when the issuing lane
+    // shared a warp with lanes spinning in mbarrier.try_wait, the suspended warp delayed every issue by 0.5-2 us.
+    auto publish = [&]() {
         umma::fence_async_smem();
         umma::fence_before_sync();
-        __syncthreads();
+        asm volatile("bar.sync 3, %0;" ::"n"(T2_NT) : "memory");
     };
+    auto mma_turn = [&]() {    // MMA warp: wait for the epilogue warps' hand-off
+        asm volatile("bar.sync 3, %0;" ::"n"(T2_NT) : "memory");
+        umma::fence_after_sync();
+    };
+    auto epi_sync = [&]() { asm volatile("bar.sync 4, %0;" ::"n"(TC_NT) : "memory"); };   // the 16 epilogue warps only
     const uint32_t Xh = sbase + S.X[0], Xl = sbase + S.X[1];
 
+    if (warp >= T2_MMA_WARP) {
+        // ================= MMA-issue warps: one hand-off barrier per batch; lane 0 of each warp issues ITS share of the batch
+        // (shares never split an accumulator) and commits to the branch's mbarrier (expected arrivals = T2_NMMA) ==========
+        const int mw = warp - T2_MMA_WARP;
+        const uint32_t H1h[2] = {sbase + S.H1[0][0], sbase + S.H1[1][0]}, H1l[2] = {sbase + S.H1[0][1], sbase + S.H1[1][1]};
+        const uint32_t H2h[2] = {sbase + S.H2[0][0], sbase + S.H2[1][0]}, H2l[2] = {sbase + S.H2[0][1], sbase + S.H2[1][1]};
+        const uint32_t DLh[2] = {sbase + S.DL[0][0], sbase + S.DL[1][0]}, DLl[2] = {sbase + S.DL[0][1], sbase + S.DL[1][1]};
+#pragma unroll 1
+        for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
+            const bool acc = !first;
+            mma_turn();      // X split done.  F1: Dacc_b = X * W1b^T   (warp b)
+            if (lane == 0) {
+                if (mw < 2)
+                    tc_gemm(tmem + T2_DACC + 64 * mw, Xh, Xl, TC_ROWS, false, sbase + I.W1[mw][0], sbase + I.W1[mw][1], 64, false,
+                            128, 64, KX >> 4, false, 3);
+                umma::mma_commit(mbar);
+                umma::mma_commit(mbar + 1);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {   // F2: Dacc_b = H1_b * W2b   (warp b)
+                mma_turn();
+                if (lane == 0) {
+                    if (mw == b)
+                        tc_gemm(tmem + T2_DACC + 64 * b, H1h[b], H1l[b], TC_ROWS, false, sbase + I.W2[b][0], sbase + I.W2[b][1], 64,
+                                true, 128, 64, 4, false, 3);
+                    umma::mma_commit(mbar + b);
+                }
+                __syncwarp();
+            }
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {   // heads: Hout_b[128][16] = H2_b * WoT_b^T   (warp b)
+                mma_turn();
+                if (lane == 0) {
+                    if (mw == b)
+                        tc_gemm(tmem + T2_HOUT + 16 * b, H2h[b], H2l[b], TC_ROWS, false, sbase + I.WoT[b][0], sbase + I.WoT[b][1],
+                                TC_NO, false, 128, TC_NO, 4, false, 3);
+                    umma::mma_commit(mbar + b);
+                }
+                __syncwarp();
+            }
+            mma_turn();      // loss done.  dz2-pre: Dacc_b = DL_b * WoT_b (warp b, first);  gWh_b (+)= H2_b^T DL_b by product
+            if (lane == 0) {
+                const int b = mw & 1;
+                if (mw < 2) {
+                    tc_gemm(tmem + T2_DACC + 64 * b, DLh[b], DLl[b], TC_ROWS, false, sbase + I.WoT[b][0], sbase + I.WoT[b][1], TC_NO,
+                            true, 128, 64, 1, false, 3);
+                    tc_gemm_mask(tmem + T2_GWH + 16 * (2 * b), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64, 16, 8,
+                                 acc, 1);
+                } else {
+                    tc_gemm_mask(tmem + T2_GWH + 16 * (2 * b + 1), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64,
+                                 16, 8, acc, 6);
+                }
+                umma::mma_commit(mbar);
+                umma::mma_commit(mbar + 1);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {   // B4: Dacc_b = dZ2_b * W2b^T (warp 0);  gW2_b (+)= H1_b^T dZ2_b (warp 1 / 3);  gb2_b (warp 2)
+                mma_turn();
+                if (lane == 0) {
+                    if (mw == 0)
+                        tc_gemm(tmem + T2_DACC + 64 * b, H2h[b], H2l[b], TC_ROWS, false, sbase + I.W2[b][0], sbase + I.W2[b][1], 64,
+                                false, 128, 64, 4, false, 3);
+                    else if (mw == (b ? 3 : 1))
+                        tc_gemm(tmem + T2_GW2 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, H2h[b], H2l[b], TC_ROWS, true, 64, 64, 8, acc, 3);
+                    else if (mw == 2)
+                        tc_gemm(tmem + T2_GB2 + 16 * b, H2h[b], H2l[b], TC_ROWS, true, Xh + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
+                                16, 8, acc, 2);
+                    umma::mma_commit(mbar + b);
+                }
+                __syncwarp();
+            }
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {   // B5: gW1_b[c][d] (+)= dZ1_b^T X by product (column D of X = constant 1 -> bias gradient)
+                mma_turn();
+                if (lane == 0) {
+                    if (mw == 0)
+                        tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8, acc, 1);
+                    if (mw == 1)
+                        tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b + 1), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8,
+                                     acc, 6);
+                    umma::mma_commit(mbar + b);
+                }
+                __syncwarp();
+            }
+            first = false;
+        }
+    } else {
+    // ================= epilogue warps ==========================================================================================
 #pragma unroll 1
     for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
         const int nrows = (int)min((int64_t)TC_ROWS, cr1 - row0);
         if (!first) { wait_b(0); wait_b(1); }       // previous tile's B5 still reads X and dZ1
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncthreads();
+        epi_sync();
+        T2_STAMP(2);
         // ---- x: fp32 staging -> fp16 hi/lo chunked [128][KX], constant 1 in column D, zero rows beyond nrows ----------
         {
             const int r = tid & (TC_ROWS - 1);
@@ -208,47 +344,34 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             }
         }
         publish();
+        T2_STAMP(3);
         // ---- F1 (both branches): Dacc_b = X * W1b^T --------------------------------------------------------------
-        if (tid == T2_ISSUER) {
-            umma::fence_after_sync();
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                tc_gemm(tmem + T2_DACC + 64 * b, Xh, Xl, TC_ROWS, false, sbase + I.W1[b][0], sbase + I.W1[b][1], 64, false,
-                        128, 64, KX >> 4, false, 3);
-                umma::mma_commit(mbar + b);
-            }
-        }
         // ---- tanh epilogue 1 -> F2: Dacc_b = H1_b * W2b -------------------------------------------------------------
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
             wait_b(b);
+            T2_STAMP(4 + 3 * b);
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b1c + b * 64 + 16 * cq, 1.f / (TC_SX * TC_SW),
                         sm + S.H1[b][0], sm + S.H1[b][1], row, cq);
+            T2_STAMP(5 + 3 * b);
             publish();
-            if (tid == T2_ISSUER) {
-                umma::fence_after_sync();
-                tc_gemm(tmem + T2_DACC + 64 * b, sbase + S.H1[b][0], sbase + S.H1[b][1], TC_ROWS, false, sbase + I.W2[b][0],
-                        sbase + I.W2[b][1], 64, true, 128, 64, 4, false, 3);
-                umma::mma_commit(mbar + b);
-            }
+            T2_STAMP(6 + 3 * b);
         }
         // ---- tanh epilogue 2 -> heads: Hout_b[128][16] = H2_b * WoT_b^T ------------------------------------------------
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
             wait_b(b);
+            T2_STAMP(10 + 3 * b);
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b2c + b * 64 + 16 * cq, 1.f / (TC_SH * TC_SW),
                         sm + S.H2[b][0], sm + S.H2[b][1], row, cq);
+            T2_STAMP(11 + 3 * b);
             publish();
-            if (tid == T2_ISSUER) {
-                umma::fence_after_sync();
-                tc_gemm(tmem + T2_HOUT + 16 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, false, sbase + I.WoT[b][0],
-                        sbase + I.WoT[b][1], TC_NO, false, 128, TC_NO, 4, false, 3);
-                umma::mma_commit(mbar + b);
-            }
+            T2_STAMP(12 + 3 * b);
         }
         // ---- PPO loss: warps 0-3 policy part, warps 4-7 value part -> DL_b (fp16 hi/lo x branch scale, chunked [128][16]) ----
         wait_b(0);
         wait_b(1);
+        T2_STAMP(16);
         if (cq < 2) {
             const int b = cq;
             float out[16], dl[16];
@@ -306,42 +429,26 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
                 *reinterpret_cast<uint4*>(sm + S.DL[b][1] + (c * TC_ROWS + row) * 16) = lo;
             }
         }
+        T2_STAMP(17);
         publish();
+        T2_STAMP(18);
         {   // both branches consumed the staged loss inputs: fetch the next tile's
             const int64_t nxt = row0 + TC_ROWS;
             if (nxt < cr1) prefetch_loss(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
         }
         const float sg0 = sgs[0], sg1 = sgs[1];
         // ---- B1: gWh_b[k][o] (+)= H2_b^T DL_b ;  dz2-pre: Dacc_b = DL_b * WoT_b (B MN-major) ---------------------------
-        if (tid == T2_ISSUER) {
-            umma::fence_after_sync();
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                tc_gemm(tmem + T2_GWH + 16 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, true, sbase + S.DL[b][0],
-                        sbase + S.DL[b][1], TC_ROWS, true, 64, 16, 8, !first, 3);
-                tc_gemm(tmem + T2_DACC + 64 * b, sbase + S.DL[b][0], sbase + S.DL[b][1], TC_ROWS, false, sbase + I.WoT[b][0],
-                        sbase + I.WoT[b][1], TC_NO, true, 128, 64, 1, false, 3);
-                umma::mma_commit(mbar + b);
-            }
-        }
         // ---- dz2 epilogue -> B3: gW2_b (+)= H1_b^T dZ2_b; gb2_b (+)= dZ2_b^T 1;  B4: Dacc_b = dZ2_b * W2b^T -------------
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
             const float sg = b ? sg1 : sg0;
             wait_b(b);      // B1 has consumed H2_b; dz2 = pre * (1 - h2^2) overwrites it
+            T2_STAMP(19 + 3 * b);
             ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H2[b][0],
                                sm + S.H2[b][1], row, cq) ? 16 : 0;
+            T2_STAMP(20 + 3 * b);
             publish();
-            if (tid == T2_ISSUER) {
-                umma::fence_after_sync();
-                tc_gemm(tmem + T2_GW2 + 64 * b, sbase + S.H1[b][0], sbase + S.H1[b][1], TC_ROWS, true, sbase + S.H2[b][0],
-                        sbase + S.H2[b][1], TC_ROWS, true, 64, 64, 8, !first, 3);
-                tc_gemm(tmem + T2_GB2 + 16 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, true,
-                        Xh + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64, 16, 8, !first, 2);
-                tc_gemm(tmem + T2_DACC + 64 * b, sbase + S.H2[b][0], sbase + S.H2[b][1], TC_ROWS, false, sbase + I.W2[b][0],
-                        sbase + I.W2[b][1], 64, false, 128, 64, 4, false, 3);
-                umma::mma_commit(mbar + b);
-            }
+            T2_STAMP(21 + 3 * b);
         }
         {   // both B1 are complete (DL dead): stream the next tile's observations into the shared staging area
             const int64_t nxt = row0 + TC_ROWS;
@@ -353,50 +460,58 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         for (int b = 0; b < 2; ++b) {
             const float sg = b ? sg1 : sg0;
             wait_b(b);      // B3 has consumed H1_b; dz1 = (dz2 W2^T) * (1 - h1^2) overwrites it
+            T2_STAMP(25 + 3 * b);
             ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H1[b][0],
                                sm + S.H1[b][1], row, cq) ? 32 : 0;
+            T2_STAMP(26 + 3 * b);
             publish();
-            if (tid == T2_ISSUER) {
-                umma::fence_after_sync();
-                tc_gemm(tmem + T2_GW1 + 32 * b, sbase + S.H1[b][0], sbase + S.H1[b][1], TC_ROWS, true, Xh, Xl, TC_ROWS, true,
-                        64, KX, 8, !first, 3);
-                umma::mma_commit(mbar + b);
-            }
+            T2_STAMP(27 + 3 * b);
         }
         first = false;
     }
     wait_b(0);
     wait_b(1);
+    T2_STAMP(31);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }   // epilogue warps
 
     // ---- write-out: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
     const float inv = a.hp.inv_global_mb;
     __syncthreads();
     const int m = 16 * q + lane;            // valid for lane < 16
     const bool mine = lane < 16;
+    if (warp < T2_MMA_WARP) {
 #pragma unroll 1
     for (int b = 0; b < 2; ++b) {
         float v[8];
         const float sgb = sgs[b];
         const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {        // gW2_b: this warp's 16 columns
-            umma::tmem_ld8(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8 * c, v);
+        {   // gW2_b (this warp's 16 columns) and gW1_b (8 input features, two product halves): 4 TMEM loads in flight, one wait
+            uint32_t r0[8], r1[8], r2[8], r3[8];
+            const bool has_w1 = cq < (KX >> 3);       // KX <= 32: at most one 8-feature group per column quarter
+            umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq, r0);
+            umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8, r1);
+            umma::tmem_ld8_nowait(tmem + tlane + T2_GW1 + 32 * (2 * b) + (has_w1 ? 8 * cq : 0), r2);
+            umma::tmem_ld8_nowait(tmem + tlane + T2_GW1 + 32 * (2 * b + 1) + (has_w1 ? 8 * cq : 0), r3);
+            umma::tmem_ld_wait();
             if (mine) {
-                float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq + 8 * c);
-                dst[0] = make_float4(v[0] * inv_gw2, v[1] * inv_gw2, v[2] * inv_gw2, v[3] * inv_gw2);
-                dst[1] = make_float4(v[4] * inv_gw2, v[5] * inv_gw2, v[6] * inv_gw2, v[7] * inv_gw2);
-            }
-        }
-#pragma unroll 1
-        for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
-            umma::tmem_ld8(tmem + tlane + T2_GW1 + 32 * b + 8 * c8, v);
-            if (mine) {
+                float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq);
+                dst[0] = make_float4(__uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
+                                     __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
+                dst[1] = make_float4(__uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
+                                     __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
+                dst[2] = make_float4(__uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
+                                     __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
+                dst[3] = make_float4(__uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
+                                     __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
+                if (has_w1) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int d = 8 * c8 + j;
-                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = v[j] * inv_gw1;
-                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = v[j] * inv_gw1;
+                    for (int j = 0; j < 8; ++j) {
+                        const int d = 8 * cq + j;
+                        const float g = (__uint_as_float(r2[j]) + __uint_as_float(r3[j])) * inv_gw1;
+                        if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = g;
+                        else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = g;
+                    }
                 }
             }
         }
@@ -408,8 +523,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             if (mine) gp[(b ? o.bv2 : o.b2) + m] = g * inv_gw1;
         }
         if (cq == 3) {                                   // gWh_b[k = m][o]
-            float w[16];
-            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * b, w);
+            float w[16], w2[16];
+            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * (2 * b), w);
+            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * (2 * b + 1), w2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] += w2[j];
             if (mine) {
                 if (b == 0) {
 #pragma unroll
@@ -420,7 +538,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             }
         }
     }
+    }   // write-out (epilogue warps)
     // head bias gradients and stats: reduce over the loss threads (warps 0..3 policy, 4..7 value), fixed order
+    T2_STAMP(32);
     __syncthreads();
     double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][16]
     if (cq < 2) {
@@ -445,6 +565,21 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
         a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sum4(w0, idx);
     }
+    } while (0);
+    T2_STAMP(33);
+    if (has_tail) {   // fused grad-reduce + [peer all-reduce] + clip + Adam
+        ts.round = s + 1;
+        ts.last = s == nsteps - 1;
+        __threadfence();
+        const bool tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+                                       reinterpret_cast<float*>(sm + S.H1[0][0]), a.dbg_clock);
+        ok = ok && tok;
+        ts.b1p *= a.tail.beta1;
+        ts.b2p *= a.tail.beta2;
+        ts.seq += 1u;
+    }
+    T2_STAMP(34);
+    }   // steps of this launch
     if (a.status) {
         if (tid == 0 && !ok) atomicOr(a.status, 1);
         if (ovf) atomicOr(a.status, ovf);
@@ -452,12 +587,6 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, T2_TMEM_COLS);
-    if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
-        __threadfence();
-        const bool tok = sgd_step_tail(a.tail, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                       reinterpret_cast<float*>(sm + S.H1[0][0]));
-        if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);
-    }
 }
 
 template <int A>
@@ -470,7 +599,7 @@ static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStr
         }
         attr = true;
     }
-    fcnet_train_tc2_kernel<A><<<dim3(G, P), TC_NT, smem, st>>>(a);
+    fcnet_train_tc2_kernel<A><<<dim3(G, P), T2_NT, smem, st>>>(a);
     return DDRL_OK;
 }
 

@@ -24,6 +24,7 @@ struct TcTrainArgs {
     float* grad_part;
     double* stat_part;
     int* status;
+    long long* dbg_clock;   // optional: CTA (0, 0) thread 0 stores clock64() at phase boundaries (ddrl_tc_set_debug_clock)
     SgdTail tail;
 };
 
@@ -64,6 +65,33 @@ __device__ __forceinline__ void tc_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t
     for (int pr = 0; pr < nprod; ++pr) {
         uint64_t ad = (pr == 2 || (nprod == 2 && pr == 1)) ? al : ah;
         uint64_t bd = (nprod == 3 && pr == 1) ? bl : bh;
+#pragma unroll 4
+        for (int ks = 0; ks < nk; ++ks) {
+            umma::mma_f16(d_tmem, ad, bd, idesc, acc != 0u);
+            acc = 1u;
+            ad += astep;
+            bd += bstep;
+        }
+    }
+}
+
+// Same with an explicit product mask (bit 0: hi*hi, bit 1: hi*lo, bit 2: lo*hi): lets several issuing warps share one
+// GEMM by product, each into its own accumulator (the accumulators are added at read-out).
+__device__ __forceinline__ void tc_gemm_mask(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
+                                             uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate, int pmask) {
+    const uint32_t idesc = umma::idesc_f16(M, N, a_mn, b_mn);
+    const uint64_t astep = a_mn ? 16u : (uint64_t)(2 * a_rows);
+    const uint64_t bstep = b_mn ? 16u : (uint64_t)(2 * b_rows);
+    const uint64_t ah = a_mn ? umma::desc_mnmajor(a_hi, a_rows) : umma::desc_kmajor(a_hi, a_rows);
+    const uint64_t al = a_mn ? umma::desc_mnmajor(a_lo, a_rows) : umma::desc_kmajor(a_lo, a_rows);
+    const uint64_t bh = b_mn ? umma::desc_mnmajor(b_hi, b_rows) : umma::desc_kmajor(b_hi, b_rows);
+    const uint64_t bl = b_mn ? umma::desc_mnmajor(b_lo, b_rows) : umma::desc_kmajor(b_lo, b_rows);
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
+    for (int pr = 0; pr < 3; ++pr) {
+        if (!((pmask >> pr) & 1)) continue;
+        uint64_t ad = pr == 2 ? al : ah;
+        uint64_t bd = pr == 1 ? bl : bh;
 #pragma unroll 4
         for (int ks = 0; ks < nk; ++ks) {
             umma::mma_f16(d_tmem, ad, bd, idesc, acc != 0u);

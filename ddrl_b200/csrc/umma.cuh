@@ -72,6 +72,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bounded wait: returns false if the phase did not complete within ~`spins` probes (never hangs the GPU)
 __device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity, uint32_t spins = 20000000u) {
     const uint32_t a = smem_u32(mbar);
+#pragma unroll 1
     for (uint32_t i = 0; i < spins; ++i) {
         uint32_t ok;
         asm volatile(
@@ -110,6 +111,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue only: pair with tmem_ld_wait() once several loads are in flight (the results must not be read before it)
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(

@@ -345,6 +345,10 @@ def tc_set_variant(variant: int) -> None:
     _lib.check(_lib.load().ddrl_tc_set_variant(int(variant)), "tc_set_variant")
 
 
+def tc_pingpong_eligible(D: int, A: int) -> bool:
+    return bool(_lib.load().ddrl_tc_pingpong_eligible(int(D), int(A)))
+
+
 def ppo_train_step_tc(tc_img, obs, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int, mb_perm, step_ctr,
                       kl_coeff, hyper: PPOHyper, ctas_per_policy: int, grad_part, stat_part, status=None,
                       tail: Optional[SgdTail] = None):
@@ -388,5 +392,5 @@ def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, bet
     t.barrier_ws, t.sq_ws = _p(barrier_ws, torch.int32, "barrier_ws"), _p(sq_ws, f32, "sq_ws")
     t.lr, t.beta1, t.beta2, t.eps, t.grad_clip = float(lr), float(beta1), float(beta2), float(eps), float(grad_clip)
     t.status = _p(status, torch.int32, "status")
-    t.world, t.rank = 1, 0
+    t.world, t.rank, t.nsteps = 1, 0, 1
     return t

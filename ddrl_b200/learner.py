@@ -105,7 +105,8 @@ class FCNetLearner(_LearnerBase):
     """P grouped FCNet policies (obs dim D, action dim A, hiddens [64,64], tanh, separate value net)."""
 
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
-                 use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True):
+                 use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True,
+                 persistent: bool = True):
         """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
                  "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes."""
         super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
@@ -113,6 +114,7 @@ class FCNetLearner(_LearnerBase):
             raise DDRLError(f"mode must be 'tc' or 'fp32', got {mode!r}")
         self.mode = mode
         self.fuse_tail = fuse_tail
+        self.persistent = persistent      # one persistent launch per epoch where the kernel supports it
         self.D, self.A = D, A
         dev = self.device
         self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -176,10 +178,11 @@ class FCNetLearner(_LearnerBase):
             self._peers = PeerExchange(self.dist, self.world, self.rank, self.P, self.NP, G, self.device)
         return self._peers
 
-    def _sgd_step(self, b, MB, G, hyper, src):
+    def _sgd_step(self, b, MB, G, hyper, src, nsteps: int = 1):
         # ONE launch per optimizer step: the train kernel also reduces the partials, all-reduces the gradient slices
-        # over NVLink peer memory (world > 1), clips and applies Adam (csrc/sgd_tail.cuh).  fuse_tail=False keeps the
-        # 3-kernel path (train, grad_reduce, [NCCL all-reduce], clip_adam) for A/B tests.
+        # over NVLink peer memory (world > 1), clips and applies Adam (csrc/sgd_tail.cuh).  With nsteps > 1 (ping-pong
+        # tcgen05 kernel) ONE persistent launch runs that many consecutive steps.  fuse_tail=False keeps the 3-kernel
+        # path (train, grad_reduce, [NCCL all-reduce], clip_adam) for A/B tests.
         tail = None
         if self.fuse_tail and G * self.P <= self.sms:
             c = self.cfg
@@ -187,8 +190,11 @@ class FCNetLearner(_LearnerBase):
                                    c.beta1, c.beta2, c.adam_eps, c.grad_clip, self.gnorm,
                                    img=self.img if self.mode == "fp32" else None, tc_img=self.tc_img,
                                    step_stats=b["step_stats"], step_ctr=self.step_ctr, status=self.tc_status)
+            tail.nsteps = nsteps
             if self.world > 1:
                 self._peer_exchange(G).fill(tail)
+        elif nsteps != 1:
+            raise DDRLError("multi-step launches need the fused tail")
         if self.mode == "tc":
             K.ppo_train_step_tc(self.tc_img, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
                                 src["vtarg"], self.A, MB, b["mb_perm"], self.step_ctr, self.kl_coeff, hyper, G,
@@ -203,6 +209,11 @@ class FCNetLearner(_LearnerBase):
         if self.world > 1:
             self.dist.all_reduce(self.grad)
         self._adam()
+
+    def _persistent_steps(self, G: int) -> bool:
+        """True if one launch can run a whole epoch of SGD steps (ping-pong tcgen05 kernel + fused tail)."""
+        return (self.persistent and self.mode == "tc" and self.fuse_tail and G * self.P <= self.sms
+                and K.tc_pingpong_eligible(self.D, self.A))
 
     # ---- the iteration --------------------------------------------------------------------------------------
     def learn_on_rollout(self, raw_obs: torch.Tensor, boot_obs: torch.Tensor, rewards: torch.Tensor,
@@ -273,7 +284,12 @@ class FCNetLearner(_LearnerBase):
         if self.world > 1 and self.fuse_tail and G * P <= self.sms:
             self._peer_exchange(G)      # allocate / map the peer buffers outside any graph capture
         ran = False
-        if self.use_graph:
+        if self._persistent_steps(G):
+            # one persistent launch per epoch: nb consecutive optimizer steps inside the kernel (no graph needed)
+            for _ in range(E):
+                self._sgd_step(b, MB, G, hyper, src, nsteps=nb)
+            ran = True
+        elif self.use_graph:
             key = (T, Cc, steps, G, MB, src_key)
             if self._graph is None or self._graph_key != key:
                 torch.cuda.synchronize()

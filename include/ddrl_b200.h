@@ -161,7 +161,10 @@ typedef struct {
  *   theta, m, v [P][NP]; beta_pow [P][2]; grad [P][NP] (out: reduced gradient); gnorm_out [P] or NULL;
  *   fcnet_img / fcnet_tc_img or NULL; step_stats [steps][P][DDRL_NSTAT] or NULL; step_ctr;
  *   barrier_ws: 4*P + 4 zero-initialised uint32 (re-armed by the kernel); sq_ws: P * ctas_per_policy floats;
- *   status: device int or NULL, receives |= 64 when a bounded spin of the tail gave up (results then invalid).
+ *   status: device int or NULL, receives |= 64 when a bounded spin of the tail gave up (results then invalid);
+ *   nsteps > 1: the launch runs that many consecutive optimizer steps (*step_ctr .. *step_ctr + nsteps - 1) as ONE
+ *   persistent kernel — TMEM, barriers and the instruction stream stay warm, the launch gap disappears; the CTAs of a
+ *   policy meet at a third barrier before they reload the updated weights.
  * Data parallel (world > 1; one process per GPU, every rank launches the same step with the same shapes):
  *   seq       device uint32, zero-initialised once, advanced by the kernel every step;
  *   peer_x[w] exchange buffer of rank w (peer-mapped, ddrl_peer_alloc/open; [rank] = the local one), zero-initialised:
@@ -180,6 +183,7 @@ typedef struct {
     int32_t world, rank;
     uint32_t* seq;
     unsigned long long* peer_x[DDRL_MAX_RANKS];
+    int32_t nsteps;           /* consecutive SGD steps per launch (0 or 1 = one); > 1 only ddrl_ppo_train_step_tc (ping-pong) */
 } ddrl_sgd_tail;
 
 /* 64-bit words per (rank, policy) in the exchange buffer: ctas_per_policy slices of ((NP + G - 1) / G rounded up to 4) */
@@ -283,6 +287,12 @@ int ddrl_fcnet_tc_image_bytes(int D, int A);
  * resident, the tensor core runs one branch while the CTA runs the other's epilogue; D <= 30, A <= 4).
  * 0 (default) picks ping-pong whenever the shape allows it.  Process-wide; meant for tests and A/B timing. */
 int ddrl_tc_set_variant(int variant);
+/* 1 if ddrl_ppo_train_step_tc will use the ping-pong kernel for (D, A) under the current variant setting (the kernel that
+ * accepts ddrl_sgd_tail.nsteps > 1), else 0. */
+int ddrl_tc_pingpong_eligible(int D, int A);
+/* Diagnostic: when non-NULL (device int64[64]), thread 0 of CTA (0, 0) of the ping-pong kernel stores clock64() at its
+ * phase boundaries (index = phase number) — in-kernel phase timing without a profiler.  NULL switches it off. */
+int ddrl_tc_set_debug_clock(void* device_int64x64);
 int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* tc_img, void* stream);
 int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* actions,
                            const float* old_logits, const float* old_logp, const float* vf_preds,
@@ -299,6 +309,10 @@ int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* ac
  * accumulator rows occupy a subset of the lanes); *status (device int) = 0 ok, 1 = MMA completion timed out. */
 int ddrl_umma_selftest(const float* A, int ra, int ca, const float* B, int rb, int cb, int M, int N, int K,
                        int a_mn, int b_mn, int split, float* D, int* status, void* stream);
+
+/* Diagnostic micro-benchmark: `reps` x `ksteps` back-to-back tcgen05.mma kind::f16 (M x N x 16, operands in the chunked
+ * layout, a_mn / b_mn = MN-major views) issued by one thread; cycles2 (device int64[2]) = {issue loop, issue + completion}. */
+int ddrl_umma_bench(int M, int N, int a_mn, int b_mn, int reps, int ksteps, void* cycles2, int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -282,13 +282,15 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
 def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
     """filter -> forward/sample -> GAE -> standardise -> 2 epochs x 4 minibatches of clip+Adam -> KL update.
-    "-3k" = the three-kernel SGD step (train, grad_reduce, clip_adam) instead of the fused tail."""
+    "-3k" = the three-kernel SGD step (train, grad_reduce, clip_adam) instead of the fused tail; "-1step" = one launch
+    per optimizer step instead of one persistent launch per epoch."""
     fuse = not mode.endswith("-3k")
+    persistent = not mode.endswith("-1step")      # "tc": one persistent launch per epoch where the kernel allows it
     mode = mode.split("-")[0]
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
@@ -311,7 +313,8 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     perms = np.stack([np.stack([rng.permutation(nb) for _ in range(2)]) for _ in range(P)]).astype(np.int32)
     shuffle = np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32) if use_shuffle else None
 
-    L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse)
+    L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse,
+                     persistent=persistent)
     L.filt_n.copy_(torch.tensor([f[0] for f in filt0]))
     L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt0])))
     L.filt_S.copy_(torch.from_numpy(np.stack([f[2] for f in filt0])))
