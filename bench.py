@@ -324,31 +324,28 @@ def main():
     value = agent_steps * args.steps / (ms_total * 1e-3)
     e2e_value = agent_steps * e2e_steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (fused fwd+loss+bwd), timed alone with CUDA events on its stream ----------
+    # ---- roofline of the dominant kernel: the SGD-step kernel exactly as the product path launches it (fused forward +
+    # PPO loss + backward + gradient reduce + [peer all-reduce] + clip + Adam; persistent: one launch = one epoch of
+    # `nb` steps), each launch bracketed by CUDA events on the launching (= torch current) stream -------------------------
     b = L._bufs
     src = {n_: b[n_ + "_s"] for n_ in ("obs", "act", "logits", "logp", "value", "adv", "vtarg")}
     MB, nbb, G = L._sgd_setup(R)
     hyper = L._hyper(MB * world)
+    persistent = L._persistent_steps(G)
+    steps_per_launch = nb if persistent else 1
+    n_launch = E if persistent else 40
     evs = []
     L.step_ctr.zero_()
-    torch.cuda.synchronize()
-    for i in range(40):
+    barrier()
+    for i in range(n_launch):
         a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        L.step_ctr.fill_(i % (E * nb))
         a.record()
-        if args.mode == "tc":
-            K.ppo_train_step_tc(L.tc_img, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
-                                src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"],
-                                b["stat_part"], L.tc_status)
-        else:
-            K.ppo_train_step(L.theta, src["obs"], src["act"], src["logits"], src["logp"], src["value"], src["adv"],
-                             src["vtarg"], A, MB, b["mb_perm"], L.step_ctr, L.kl_coeff, hyper, G, b["grad_part"],
-                             b["stat_part"], img=L.img)
+        L._sgd_step(b, MB, G, hyper, src, nsteps=steps_per_launch)
         c.record()
         evs.append((a, c))
     torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(c) for a, c in evs[8:]]))
-    flops_launch = train_flops_per_row(D, A) * MB * P
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in evs[2:]]))
+    flops_launch = train_flops_per_row(D, A) * MB * P * steps_per_launch
     achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12
     peaks = {}
     try:
@@ -358,15 +355,20 @@ def main():
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6
     fp32_peak = 148 * 128 * 2 * sm_clock / 1e12
-    kname = ("fcnet_train_tc_kernel (fused fwd + PPO loss + bwd; tcgen05 kind::f16, fp16 hi/lo split x3 products, TMEM accum)"
-             if args.mode == "tc" else "fcnet_train_kernel (fused fwd + PPO loss + bwd, FP32 FMA parity mode)")
+    kname = (("fcnet_train_tc2_kernel" if K.tc_pingpong_eligible(D, A) else "fcnet_train_tc_kernel") +
+             " (fused fwd + PPO loss + bwd + grad reduce + clip + Adam; tcgen05 kind::f16, fp16 hi/lo split x3 products, TMEM accum)"
+             if args.mode == "tc" else "fcnet_train_kernel (fused fwd + PPO loss + bwd + grad reduce + clip + Adam, FP32 FMA parity mode)")
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-                "traffic": None, "launch_ms": k_ms, "flops_per_launch": flops_launch,
+                "traffic": (68.98e6 if (persistent and args.mode == "tc" and envs == 4096 and nb == 32) else None),
+                "traffic_note": "dram__bytes_read+write per launch (32 steps), ncu --set full, profiles/r01_ncu_train_tc2_persistent_summary.txt",
+                "launch_ms": k_ms, "flops_per_launch": flops_launch, "sgd_steps_per_launch": steps_per_launch,
+                "us_per_sgd_step": 1e3 * k_ms / steps_per_launch,
+                "note": "latency/issue-bound: 4096 rows x 4 policies per step = one 128-row tile per SM (DESIGN.md §4)",
                 "fp32_fma_pipe": {"peak": fp32_peak, "frac": achieved_tf / fp32_peak,
                                   "note": "148 SM x 128 lanes x 2 x measured SM clock; the pipe this FP32-parity kernel runs on"},
-                "share_of_step": steps_per_iter * k_ms / (ms_total / args.steps)}
+                "share_of_step": (steps_per_iter / steps_per_launch) * k_ms / (ms_total / args.steps)}
 
     line = None
     if rank == 0:
