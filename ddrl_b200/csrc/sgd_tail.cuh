@@ -89,7 +89,15 @@ __device__ __forceinline__ bool sgd_wait_weights(const SgdTail& t, int p, int G,
 __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& ts, const float* __restrict__ grad_part,
                                               const double* __restrict__ stat_part, int p, int P, int bx, int G, int NP,
                                               int step, int D, int A, float* smem, long long* dbg = nullptr) {
-#define TAIL_STAMP(i) do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[i] = clock64(); } while (0)
+#define TAIL_STAMP(i)                                                                                              \
+    do {                                                                                                           \
+        if (dbg && threadIdx.x == 0) {                                                                             \
+            if (blockIdx.x == 0 && blockIdx.y == 0) dbg[i] = clock64();                                            \
+            long long gt_;                                                                                         \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                \
+            dbg[64 + 8 * (blockIdx.y * gridDim.x + blockIdx.x) + ((i) - 37)] = gt_;   /* 40..43 -> slots 3..6 */     \
+        }                                                                                                          \
+    } while (0)
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int NPs = (NP + 3) & ~3;
     float4* scr = reinterpret_cast<float4*>(smem);
@@ -290,7 +298,6 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
         }
         if (!ok && t.status) atomicOr(t.status, 64);
     }
-    TAIL_STAMP(44);
     return ok;
 #undef TAIL_STAMP
 }

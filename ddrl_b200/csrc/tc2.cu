@@ -108,6 +108,17 @@ __device__ __noinline__ bool t2_epi_grad(uint32_t taddr, float inv_in, float out
         if (a.dbg_clock && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg_clock[i] = clock64(); \
     } while (0)
 
+// every CTA: globaltimer stamps (comparable across SMs) at a few points of the step -> dbg_clock[64 + 8 * cta + k]
+__device__ __forceinline__ long long t2_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define T2_GSTAMP(k)                                                                                     \
+    do {                                                                                                 \
+        if (a.dbg_clock && threadIdx.x == 0) a.dbg_clock[64 + 8 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = t2_gtime(); \
+    } while (0)
+
 template <int A>
 __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrainArgs a) {
     constexpr int A2 = 2 * A;
@@ -150,42 +161,6 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         ts.seq = (a.tail.world > 1) ? *a.tail.seq : 0u;
     }
 
-#pragma unroll 1
-    for (int s = 0; s < nsteps; ++s) {
-    if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
-        if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
-        __syncthreads();
-    }
-    if (warp < T2_MMA_WARP) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
-        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
-#pragma unroll 2
-        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
-        asm volatile("cp.async.commit_group;\n" ::);
-    }
-    T2_STAMP(35);
-    const int step = step0 + s;
-    const int mb = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step] : step;
-    const int64_t mb0 = (int64_t)mb * a.MB;
-    if (mb0 >= 0) T2_STAMP(36);
-    bool first = true;
-    // loss warps: 0-3 policy part (s0 = -surr, s1 = KL, s2 = entropy), 4-7 value part (s0 = vf, s1..4 = R, R^2, R-v, (R-v)^2)
-    double st[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) st[i] = 0.0;
-    float gbh[A2];   // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0]
-#pragma unroll
-    for (int i = 0; i < A2; ++i) gbh[i] = 0.f;
-    const int64_t mb1 = min(mb0 + a.MB, a.R);
-    const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
-    const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
-    do {   // single exit towards the fused tail (one inlined copy of it)
-    if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        for (int i = tid; i < o.NP; i += T2_NT) gp[i] = 0.f;
-        if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
-        break;
-    }
-
     const float* obs_p = a.obs + (int64_t)p * a.R * D;
     float* xraw = reinterpret_cast<float*>(sm + S.xraw);
     float* pf = reinterpret_cast<float*>(sm + S.pf);
@@ -216,8 +191,47 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
     };
 
+    bool prefetched = false;   // the first tile's inputs of this step were already requested behind the previous step's tail
+
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+    if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
+        if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
+        __syncthreads();
+    }
+    if (warp < T2_MMA_WARP) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
+        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+#pragma unroll 2
+        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    T2_STAMP(35);
+    T2_GSTAMP(0);
+    const int step = step0 + s;
+    const int mb = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step] : step;
+    const int64_t mb0 = (int64_t)mb * a.MB;
+    if (mb0 >= 0) T2_STAMP(36);
+    bool first = true;
+    // loss warps: 0-3 policy part (s0 = -surr, s1 = KL, s2 = entropy), 4-7 value part (s0 = vf, s1..4 = R, R^2, R-v, (R-v)^2)
+    double st[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) st[i] = 0.0;
+    float gbh[A2];   // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0]
+#pragma unroll
+    for (int i = 0; i < A2; ++i) gbh[i] = 0.f;
+    const int64_t mb1 = min(mb0 + a.MB, a.R);
+    const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
+    const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
+    do {   // single exit towards the fused tail (one inlined copy of it)
+    if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        for (int i = tid; i < o.NP; i += T2_NT) gp[i] = 0.f;
+        if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
+        break;
+    }
+
     // ---- this step's first tile: inputs ---------------------------------------------------------------------------------
-    if (warp < T2_MMA_WARP) {
+    if (warp < T2_MMA_WARP && !prefetched) {
         const int n0 = (int)min((int64_t)TC_ROWS, cr1 - cr0);
         prefetch_x(cr0, n0);
         prefetch_loss(cr0, n0);
@@ -488,7 +502,21 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     wait_b(0);
     wait_b(1);
     T2_STAMP(31);
+    T2_GSTAMP(1);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (cq < 2) {   // loss warps: head-bias gradients and loss statistics -> per-warp sums (read after the write-out barrier)
+        double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][16]
+#pragma unroll
+        for (int i = 0; i < A2; ++i) {
+            const float sx = warp_sum(gbh[i]);
+            if (lane == 0 && 8 + i < 16) redd[warp * 16 + 8 + i] = (double)sx;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double sx = warp_sum(st[i]);
+            if (lane == 0) redd[warp * 16 + i] = sx;
+        }
+    }
     }   // epilogue warps
 
     // ---- write-out: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
@@ -555,23 +583,9 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
     }
     }   // write-out (epilogue warps)
-    // head bias gradients and stats: reduce over the loss threads (warps 0..3 policy, 4..7 value), fixed order
+    // head bias gradients and stats: add the four per-warp sums of each loss half (written before the write-out barrier)
     T2_STAMP(32);
-    __syncthreads();
-    double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][16]
-    if (cq < 2) {
-#pragma unroll
-        for (int i = 0; i < A2; ++i) {
-            const float s = warp_sum(gbh[i]);
-            if (lane == 0 && 8 + i < 16) redd[warp * 16 + 8 + i] = (double)s;
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const double s = warp_sum(st[i]);
-            if (lane == 0) redd[warp * 16 + i] = s;
-        }
-    }
-    __syncthreads();
+    const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][16]
     auto sum4 = [&](int w0, int i) { return (redd[w0 * 16 + i] + redd[(w0 + 1) * 16 + i]) + (redd[(w0 + 2) * 16 + i] + redd[(w0 + 3) * 16 + i]); };
     if (tid < A2) gp[o.bo + tid] = (float)sum4(0, 8 + tid) * inv;
     if (tid == A2) gp[o.bvo] = (float)sum4(4, 8) * inv;
@@ -583,6 +597,20 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     }
     } while (0);
     T2_STAMP(33);
+    T2_GSTAMP(2);
+    prefetched = false;
+    if (s + 1 < nsteps && warp < T2_MMA_WARP) {   // the next step's inputs do not depend on the weights: request them now,
+        const int mbn = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step + 1] : step + 1;   // they land behind the tail
+        const int64_t n0 = (int64_t)mbn * a.MB, n1 = min(n0 + a.MB, a.R);
+        const int64_t c0n = min(n0 + (int64_t)bx * rpc, n1), c1n = min(c0n + rpc, n1);
+        if (c1n > c0n) {
+            const int nn = (int)min((int64_t)TC_ROWS, c1n - c0n);
+            prefetch_x(c0n, nn);
+            prefetch_loss(c0n, nn);
+            asm volatile("cp.async.commit_group;\n" ::);
+            prefetched = true;
+        }
+    }
     if (has_tail) {   // fused grad-reduce + [peer all-reduce] + clip + Adam
         ts.round = s + 1;
         ts.last = s == nsteps - 1;
@@ -595,6 +623,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         ts.seq += 1u;
     }
     T2_STAMP(34);
+    T2_GSTAMP(7);
     }   // steps of this launch
     if (a.status) {
         if (tid == 0 && !ok) atomicOr(a.status, 1);

@@ -290,8 +290,9 @@ int ddrl_tc_set_variant(int variant);
 /* 1 if ddrl_ppo_train_step_tc will use the ping-pong kernel for (D, A) under the current variant setting (the kernel that
  * accepts ddrl_sgd_tail.nsteps > 1), else 0. */
 int ddrl_tc_pingpong_eligible(int D, int A);
-/* Diagnostic: when non-NULL (device int64[64]), thread 0 of CTA (0, 0) of the ping-pong kernel stores clock64() at its
- * phase boundaries (index = phase number) — in-kernel phase timing without a profiler.  NULL switches it off. */
+/* Diagnostic: when non-NULL (device int64[64 + 8 * #CTAs]), thread 0 of CTA (0, 0) of the ping-pong kernel stores clock64()
+ * at its phase boundaries (index = phase number) and thread 0 of EVERY CTA stores %globaltimer at 8 points of the step
+ * ([64 + 8 * cta + k]) — in-kernel timing without a profiler.  NULL switches it off. */
 int ddrl_tc_set_debug_clock(void* device_int64x64);
 int ddrl_fcnet_tc_pack(const float* theta, int P, int D, int A, void* tc_img, void* stream);
 int ddrl_ppo_train_step_tc(const void* tc_img, const float* obs, const float* actions,

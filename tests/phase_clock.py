@@ -32,7 +32,7 @@ def main():
     theta0 = torch.stack([O.fcnet_init(D, 2 * A, gen) for _ in range(P)])
     L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=False)
     s = bench.synth_rollout(P, T, C, D, A, envs, nb, E, 3, device=dev)
-    clk = torch.zeros(64, dtype=torch.int64, device=dev)
+    clk = torch.zeros(64 + 8 * 160, dtype=torch.int64, device=dev)
     L.learn_on_rollout(s["raw"], s["boot"], s["rewards"], s["dones"], s["eps"], s["perms"], s["shuffle"])
     torch.cuda.synchronize()
     _lib.load().ddrl_tc_set_debug_clock(clk.data_ptr())
@@ -50,6 +50,21 @@ def main():
             continue
         print(f"{i:2d} {NAMES[i]:18s} +{(c[i] - prev) / 1.965e3:7.2f} us   @{(c[i] - t0) / 1.965e3:7.2f} us")
         prev = c[i]
+
+
+    # all CTAs, globaltimer (ns): 0 step start, 1 main loop done, 2 write-out + stats done, 3 barrier A passed, 4 slice
+    # reduce done, 5 barrier B passed, 6 Adam done, 7 step end
+    g = c[64:64 + 8 * 148].reshape(148, 8).astype(np.float64)
+    base = g[:, 0].min()
+    names = ["start", "main done", "write-out", "barrier A", "slice red", "barrier B", "adam", "end"]
+    print("per-CTA globaltimer (us after the earliest step start): min / median / max over 148 CTAs")
+    for k in range(8):
+        col = (g[:, k] - base) / 1e3
+        print(f"  {names[k]:10s} {col.min():7.2f} {np.median(col):7.2f} {col.max():7.2f}   argmax CTA {int(col.argmax())}")
+    d = (g[:, 1] - g[:, 0]) / 1e3
+    print("main loop duration per CTA: min %.2f med %.2f max %.2f; slowest CTAs %s" % (d.min(), np.median(d), d.max(), np.argsort(-d)[:8].tolist()))
+    d2 = (g[:, 2] - g[:, 1]) / 1e3
+    print("write-out duration per CTA: min %.2f med %.2f max %.2f" % (d2.min(), np.median(d2), d2.max()))
 
 
 if __name__ == "__main__":
