@@ -388,7 +388,8 @@ def main():
                        "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
                        "cuda_graph": bool(L.use_graph and L._graph is not None), "sgd_kernel": args.mode,
                        "kernels_per_sgd_step": per_sgd,
-                       "persistent_sgd_launch": bool(L._persistent_steps(G_)),
+                       "persistent_sgd_launch": bool(L._persistent_steps(G_)), "ctas_per_policy": G_,
+                       "cluster_size": K.tc_last_cluster() if args.mode == "tc" else 0,
                        "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),

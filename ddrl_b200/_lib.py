@@ -78,6 +78,8 @@ PROTOTYPES = {
     "ddrl_fcnet_tc_image_bytes": (C.c_int, [C.c_int, C.c_int]),
     "ddrl_tc_set_variant": (C.c_int, [C.c_int]),
     "ddrl_tc_pingpong_eligible": (C.c_int, [C.c_int, C.c_int]),
+    "ddrl_tc_set_cluster": (C.c_int, [C.c_int]),
+    "ddrl_tc_last_cluster": (C.c_int, []),
     "ddrl_tc_set_debug_clock": (C.c_int, [C.c_void_p]),
     "ddrl_umma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_i32p, c_stream]),
     "ddrl_sgd_exchange_words": (C.c_int64, [C.c_int, C.c_int]),

@@ -569,7 +569,6 @@ __global__ void __launch_bounds__(NT, 1) fcnet_train_kernel(const TrainArgs a) {
         for (int i = 0; i < DDRL_NSTAT; ++i) sp[i] = st[i];
     }
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
-        __threadfence();
         sgd_step_tail(a.tail, tail_single_step(a.tail, p), a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A, sm + L.h1);
     }
 }

@@ -39,14 +39,14 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// one thread: arrive and wait until `target` CTAs have arrived; false on timeout
+// one thread, after a __syncthreads(): arrive (gpu-scope RELEASE: cumulative over the CTA's writes ordered before it by
+// the barrier — no separate __threadfence) and spin (tight acquire loads, no sleep) until `target` CTAs have arrived;
+// false on timeout
 __device__ __noinline__ static bool grid_group_barrier(unsigned int* ctr, unsigned int target) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 #pragma unroll 1
-    for (unsigned int i = 0; i < 4000000u; ++i) {
+    for (unsigned int i = 0; i < 8000000u; ++i) {
         if (ld_acquire_u32(ctr) >= target) return true;
-        __nanosleep(20);
     }
     return false;
 }
@@ -81,14 +81,16 @@ __device__ __forceinline__ bool sgd_wait_weights(const SgdTail& t, int p, int G,
 #pragma unroll 1
     for (unsigned int i = 0; i < 4000000u; ++i) {
         if (ld_acquire_u32(t.barrier_ws + 4 * p + 2) >= (unsigned)(G * round)) return true;
-        __nanosleep(20);
     }
     return false;
 }
 
 __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& ts, const float* __restrict__ grad_part,
                                               const double* __restrict__ stat_part, int p, int P, int bx, int G, int NP,
-                                              int step, int D, int A, float* smem, long long* dbg = nullptr) {
+                                              int step, int D, int A, float* smem, long long* dbg = nullptr, int npart = 0) {
+    // npart: number of gradient partials per policy at grad_part[p][0..npart) (default: one per CTA = G; a kernel that
+    // pre-reduces inside thread-block clusters passes the number of clusters)
+    if (npart <= 0) npart = G;
 #define TAIL_STAMP(i)                                                                                              \
     do {                                                                                                           \
         if (dbg && threadIdx.x == 0) {                                                                             \
@@ -125,7 +127,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     // ---- slice reduce over the G partials --------------------------------------------------------------------------
     const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S);
     const int ncol4 = max(0, (j1 - j0) >> 2);
-    const int ngrp = ncol4 >= nt ? 1 : max(1, min(min(8, G), nt / max(ncol4, 1)));
+    const int ngrp = ncol4 >= nt ? 1 : max(1, min(min(8, npart), nt / max(ncol4, 1)));
     const int cpp = nt / ngrp;                  // float4 columns per pass
     const unsigned int seq = ts.seq;
     const unsigned long long want = (unsigned long long)(seq + 1u) << 32;     // flag half of the LL words of this step
@@ -140,11 +142,11 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             const int64_t pstride = (int64_t)ngrp * (NPs >> 2);
 #pragma unroll 1
-            for (int i0 = g; i0 < G; i0 += 8 * ngrp) {     // 8 independent loads in flight, then the (fixed-order) adds
+            for (int i0 = g; i0 < npart; i0 += 8 * ngrp) {     // 8 independent loads in flight, then the (fixed-order) adds
                 float4 v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    v[k] = (i0 + k * ngrp < G) ? __ldcg(src + (int64_t)i0 * (NPs >> 2) + k * pstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[k] = (i0 + k * ngrp < npart) ? __ldcg(src + (int64_t)i0 * (NPs >> 2) + k * pstride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
             }
@@ -275,10 +277,10 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     __syncthreads();
     TAIL_STAMP(43);
     if (tid == 0) {
-        __threadfence();
         if (!ts.last) {
-            atomicAdd(t.barrier_ws + 4 * p + 2, 1u);       // this CTA's Adam slice of step `round` is visible
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(t.barrier_ws + 4 * p + 2) : "memory");   // Adam slice visible
         } else {
+            __threadfence();
             if (bx == 0) {     // every CTA read beta_pow at kernel entry (before its first barrier-A arrival): safe to advance
                 t.beta_pow[p * 2] = ts.b1p * t.beta1;
                 t.beta_pow[p * 2 + 1] = ts.b2p * t.beta2;

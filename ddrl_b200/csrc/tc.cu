@@ -593,7 +593,6 @@ __global__ void __launch_bounds__(TC_NT, 1) fcnet_train_tc_kernel(const TcTrainA
     if (warp == 0) umma::tmem_dealloc(tmem, TC_TMEM_COLS);
     } while (0);
     if (a.tail.theta) {   // fused grad-reduce + clip + Adam (single-GPU SGD loop)
-        __threadfence();
         const bool tok = sgd_step_tail(a.tail, tail_single_step(a.tail, p), a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
                                        reinterpret_cast<float*>(sm + S.H1[0]));
         if (!tok && tid == 0 && a.status) atomicOr(a.status, 64);

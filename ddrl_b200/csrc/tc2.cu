@@ -149,7 +149,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     const float klc = a.kl_coeff[p];
     const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
     const int NPs = (o.NP + 3) & ~3;
-    float* gp = a.grad_part + ((int64_t)p * G + bx) * NPs;
+    // Thread-block clusters (launch attribute; cluster = cs consecutive CTAs of one policy): the per-CTA partial gradient
+    // goes to shared memory, the cluster adds its cs partials over distributed shared memory (CTA r owns 1/cs of the
+    // vector) and only ONE partial per cluster reaches L2 — the 148 x 45 KB write / drain / re-read per step was ~9 us.
+    const int cs = (int)umma::cluster_nctarank(), crank = (int)umma::cluster_ctarank();
+    const int ncl = G / cs, cid = bx / cs;                 // clusters per policy, this CTA's cluster
+    float* stg = reinterpret_cast<float*>(sm + S.H2[0][0]);   // [NPs] staging of the partial (H2 is free after the main loop)
+    float* gp = cs > 1 ? stg : a.grad_part + ((int64_t)p * G + bx) * NPs;
     const bool has_tail = a.tail.theta != nullptr;
     const int nsteps = (has_tail && a.tail.nsteps > 1) ? a.tail.nsteps : 1;   // consecutive SGD steps of this launch
     const int step0 = a.step_ctr ? *a.step_ctr : 0;
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     do {   // single exit towards the fused tail (one inlined copy of it)
     if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        for (int i = tid; i < o.NP; i += T2_NT) gp[i] = 0.f;
+        for (int i = tid; i < NPs; i += T2_NT) gp[i] = 0.f;
         if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
         break;
     }
@@ -589,6 +595,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     auto sum4 = [&](int w0, int i) { return (redd[w0 * 16 + i] + redd[(w0 + 1) * 16 + i]) + (redd[(w0 + 2) * 16 + i] + redd[(w0 + 3) * 16 + i]); };
     if (tid < A2) gp[o.bo + tid] = (float)sum4(0, 8 + tid) * inv;
     if (tid == A2) gp[o.bvo] = (float)sum4(4, 8) * inv;
+    if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) gp[o.NP + (tid - A2 - 1)] = 0.f;   // padding floats of the partial
     if (tid < DDRL_NSTAT && a.stat_part) {
         // stat slots (ddrl_b200.h): 0 -surr, 1 KL, 2 vf, 3 entropy, 4 R, 5 R^2, 6 R-v, 7 (R-v)^2
         const int w0 = (tid == 0 || tid == 1 || tid == 3) ? 0 : 4;
@@ -596,6 +603,28 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sum4(w0, idx);
     }
     } while (0);
+    if (cs > 1) {   // in-cluster reduction over distributed shared memory: CTA `crank` adds part `crank` of the cs staged partials
+        __syncthreads();
+        umma::cluster_sync_all();
+        const int n4 = NPs >> 2, pl4 = (n4 + cs - 1) / cs;          // float4s in the vector / per part
+        float4* dstp = reinterpret_cast<float4*>(a.grad_part + ((int64_t)p * G + cid) * NPs);
+        const uint32_t stg_s = umma::smem_u32(stg);
+#pragma unroll 1
+        for (int i = crank * pl4 + tid; i < min(n4, (crank + 1) * pl4); i += T2_NT) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int r0 = 0; r0 < cs; r0 += 8) {     // up to 8 remote loads in flight, rank order
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    v[k] = (r0 + k < cs) ? umma::ld_dsmem_f4(umma::dsmem_addr(stg_s + 16u * (uint32_t)i, (uint32_t)(r0 + k)))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+            }
+            dstp[i] = acc;
+        }
+    }
     T2_STAMP(33);
     T2_GSTAMP(2);
     prefetched = false;
@@ -614,9 +643,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     if (has_tail) {   // fused grad-reduce + [peer all-reduce] + clip + Adam
         ts.round = s + 1;
         ts.last = s == nsteps - 1;
-        __threadfence();
         const bool tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                       reinterpret_cast<float*>(sm + S.H1[0][0]), a.dbg_clock);
+                                       reinterpret_cast<float*>(sm + S.H1[0][0]), a.dbg_clock, ncl);
         ok = ok && tok;
         ts.b1p *= a.tail.beta1;
         ts.b2p *= a.tail.beta2;
@@ -634,28 +662,79 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     if (warp == 0) umma::tmem_dealloc(tmem, T2_TMEM_COLS);
 }
 
+static int g_tc2_cluster = 0;    // 0 = off (default: measured slower), -1 = automatic (largest of 16, 8, 4, 2 that
+                                 // divides G and is co-resident), else the forced size
+
 template <int A>
-static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st) {
+static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st, int* used_cluster) {
     static bool attr = false;
+    auto kern = fcnet_train_tc2_kernel<A>;
     if (!attr) {
-        if (cudaFuncSetAttribute(fcnet_train_tc2_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
             return DDRL_E_CUDA;
         }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // clusters of 16 (opt-in size)
+        cudaGetLastError();
         attr = true;
     }
-    fcnet_train_tc2_kernel<A><<<dim3(G, P), T2_NT, smem, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G, P);
+    cfg.blockDim = dim3(T2_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    // cluster size: cached per (P, G); the persistent / fused-tail kernel needs ALL clusters co-resident
+    static int cache_P = -1, cache_G = -1, cache_cs = 1, cache_req = -2;
+    if (cache_P != P || cache_G != G || cache_req != g_tc2_cluster) {
+        int best = 1;
+        const int cand[4] = {16, 8, 4, 2};
+        for (int c = 0; c < 4; ++c) {
+            const int csz = cand[c];
+            if (g_tc2_cluster >= 0 && csz != g_tc2_cluster) continue;
+            if (G % csz) continue;
+            at[0].val.clusterDim.x = csz;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (ncl * csz >= G * P) { best = csz; break; }
+        }
+        cache_P = P; cache_G = G; cache_cs = best; cache_req = g_tc2_cluster;
+    }
+    // without the fused tail the caller reduces G per-CTA partials itself (ddrl_grad_reduce): no cluster pre-reduction
+    const int cs_use = a.tail.theta ? cache_cs : 1;
+    at[0].val.clusterDim.x = cs_use;
+    if (used_cluster) *used_cluster = cs_use;
+    if (cudaLaunchKernelEx(&cfg, kern, a) != cudaSuccess) {
+        set_error("ppo_train_step_tc: cluster launch (size %d) failed: %s", cs_use, cudaGetErrorString(cudaGetLastError()));
+        return DDRL_E_CUDA;
+    }
     return DDRL_OK;
 }
+
+static int g_tc2_last_cluster = 0;
 
 int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
     const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
     switch (a.A) {
-        case 1: return launch_tc2_t<1>(a, P, G, smem, st);
-        case 2: return launch_tc2_t<2>(a, P, G, smem, st);
-        case 4: return launch_tc2_t<4>(a, P, G, smem, st);
+        case 1: return launch_tc2_t<1>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 2: return launch_tc2_t<2>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 4: return launch_tc2_t<4>(a, P, G, smem, st, &g_tc2_last_cluster);
         default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4}"); return DDRL_E_UNSUPPORTED_SHAPE;
     }
 }
 
 }  // namespace ddrl
+
+extern "C" int ddrl_tc_set_cluster(int cluster_size) {
+    DDRL_REQUIRE(cluster_size == -1 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 ||
+                     cluster_size == 16, DDRL_E_BADARG, "tc_set_cluster: size must be -1 (auto), 1, 2, 4, 8 or 16");
+    ddrl::g_tc2_cluster = cluster_size == 1 ? 0 : cluster_size;
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_tc_last_cluster(void) { return ddrl::g_tc2_last_cluster; }

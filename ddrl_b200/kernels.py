@@ -345,6 +345,15 @@ def tc_set_variant(variant: int) -> None:
     _lib.check(_lib.load().ddrl_tc_set_variant(int(variant)), "tc_set_variant")
 
 
+def tc_set_cluster(size: int) -> None:
+    """-1 = automatic, 1 = off, 2/4/8/16 = forced thread-block cluster size of the ping-pong kernel."""
+    _lib.check(_lib.load().ddrl_tc_set_cluster(int(size)), "tc_set_cluster")
+
+
+def tc_last_cluster() -> int:
+    return int(_lib.load().ddrl_tc_last_cluster())
+
+
 def tc_pingpong_eligible(D: int, A: int) -> bool:
     return bool(_lib.load().ddrl_tc_pingpong_eligible(int(D), int(A)))
 

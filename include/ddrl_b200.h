@@ -290,6 +290,13 @@ int ddrl_tc_set_variant(int variant);
 /* 1 if ddrl_ppo_train_step_tc will use the ping-pong kernel for (D, A) under the current variant setting (the kernel that
  * accepts ddrl_sgd_tail.nsteps > 1), else 0. */
 int ddrl_tc_pingpong_eligible(int D, int A);
+/* Thread-block clusters of the ping-pong kernel: the CTAs of a cluster add their partial gradients over distributed
+ * shared memory, so one partial per CLUSTER (not per CTA) goes through L2.  1 (default) = no clusters — on the bench
+ * workload the per-step time is set by the three CTA-group barriers, not by the partial traffic, and clusters of 4 measured
+ * 5 % slower; -1 = the largest of 16, 8, 4, 2 that divides ctas_per_policy and keeps every cluster co-resident; 2/4/8/16 =
+ * that size.  ddrl_tc_last_cluster() returns the size the most recent launch used. */
+int ddrl_tc_set_cluster(int cluster_size);
+int ddrl_tc_last_cluster(void);
 /* Diagnostic: when non-NULL (device int64[64 + 8 * #CTAs]), thread 0 of CTA (0, 0) of the ping-pong kernel stores clock64()
  * at its phase boundaries (index = phase number) and thread 0 of EVERY CTA stores %globaltimer at 8 points of the step
  * ([64 + 8 * cta + k]) — in-kernel timing without a profiler.  NULL switches it off. */

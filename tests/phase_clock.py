@@ -54,10 +54,12 @@ def main():
 
     # all CTAs, globaltimer (ns): 0 step start, 1 main loop done, 2 write-out + stats done, 3 barrier A passed, 4 slice
     # reduce done, 5 barrier B passed, 6 Adam done, 7 step end
-    g = c[64:64 + 8 * 148].reshape(148, 8).astype(np.float64)
+    nc = L.P * L._sgd_setup(R)[2]
+    print('CTAs', nc, 'cluster size', K.tc_last_cluster())
+    g = c[64:64 + 8 * nc].reshape(nc, 8).astype(np.float64)
     base = g[:, 0].min()
     names = ["start", "main done", "write-out", "barrier A", "slice red", "barrier B", "adam", "end"]
-    print("per-CTA globaltimer (us after the earliest step start): min / median / max over 148 CTAs")
+    print("per-CTA globaltimer (us after the earliest step start): min / median / max over all CTAs")
     for k in range(8):
         col = (g[:, k] - base) / 1e3
         print(f"  {names[k]:10s} {col.min():7.2f} {np.median(col):7.2f} {col.max():7.2f}   argmax CTA {int(col.argmax())}")

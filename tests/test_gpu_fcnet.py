@@ -282,7 +282,7 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
 def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
@@ -291,6 +291,7 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     per optimizer step instead of one persistent launch per epoch."""
     fuse = not mode.endswith("-3k")
     persistent = not mode.endswith("-1step")      # "tc": one persistent launch per epoch where the kernel allows it
+    cluster = mode.endswith("-cluster")           # thread-block clusters pre-reduce the partial gradients over DSMEM
     mode = mode.split("-")[0]
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
@@ -314,7 +315,10 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     shuffle = np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32) if use_shuffle else None
 
     L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse,
-                     persistent=persistent)
+                     persistent=persistent, ctas_per_policy=8 if cluster else None)
+    if cluster:
+        from ddrl_b200 import kernels as K
+        K.tc_set_cluster(-1)
     L.filt_n.copy_(torch.tensor([f[0] for f in filt0]))
     L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt0])))
     L.filt_S.copy_(torch.from_numpy(np.stack([f[2] for f in filt0])))
@@ -323,6 +327,11 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
                                _dev(dones, dev), _dev(b["eps"].reshape(P, T, C, A), dev), _dev(perms, dev),
                                _dev(shuffle, dev) if use_shuffle else None)
     torch.cuda.synchronize()
+    if cluster:
+        used = K.tc_last_cluster()
+        K.tc_set_cluster(1)
+        if K.tc_pingpong_eligible(D, A):
+            assert used in (2, 4, 8), f"cluster launch expected, got cluster size {used}"
 
     pols, out = _oracle_iteration(b, theta0, cfg_o, O, torch.float64, perms, shuffle, T, C, dones, boot_raw, rewards, filt0)
     twin, _ = _oracle_iteration(b, theta0, cfg_o, O, torch.float32, perms, shuffle, T, C, dones, boot_raw, rewards, filt0)
