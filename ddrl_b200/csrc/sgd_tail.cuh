@@ -135,6 +135,9 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     const int64_t xstride = (int64_t)G * S;     // words per (rank, policy) in the exchange buffer
     const int64_t xoff = (((int64_t)par * W + t.rank) * P + p) * xstride + j0;   // this rank's slot, same in every buffer
     float* slice_dst = t.grad + (int64_t)p * NP + j0;
+    // common case (slice fits one pass of the CTA, `pf`): thread tid owns element j0 + tid and keeps its reduced gradient
+    // in a register from here to the Adam update — no global write -> read round trips inside the tail
+    float gval = 0.f;
     for (int c0 = 0; c0 < ncol4; c0 += cpp) {
         const int g = tid / cpp, c = c0 + (tid - g * cpp);
         if (g < ngrp && c < ncol4) {
@@ -167,10 +170,11 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
                         st_relaxed_sys_u64(t.peer_x[w] + xoff + jj, word);
                 } else {
                     slice_dst[jj] = s;
+                    gval = s;
                 }
             }
         }
-        __syncthreads();
+        if (!pf) __syncthreads();
     }
     if (bx == 0 && warp < DDRL_NSTAT && stat_part && t.step_stats) {   // warp w sums stat w (lanes stride over the partials)
         double s = 0.0;
@@ -197,16 +201,21 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
                 s += __uint_as_float((unsigned int)word);
             }
             slice_dst[jj] = s;
+            gval = s;
         }
         if (!got) red[40] = 0.f;      // benign race: every writer stores the same value
     }
-    __syncthreads();
+    if (!pf) __syncthreads();
     TAIL_STAMP(41);
     // ---- ||g||^2 of the slice (fixed order) -> barrier B -> global norm ------------------------------------------------
     float ss = 0.f;
-    for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
-        const float s = __ldcg(t.grad + (int64_t)p * NP + j0 + jj);
-        ss = fmaf(s, s, ss);
+    if (pf) {
+        ss = gval * gval;        // gval == 0 for threads without an element
+    } else {
+        for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
+            const float s = __ldcg(t.grad + (int64_t)p * NP + j0 + jj);
+            ss = fmaf(s, s, ss);
+        }
     }
     ss = warp_sum(ss);
     if (lane == 0) red[warp] = ss;
@@ -239,7 +248,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
         const int j = j0 + jj;
         const int64_t k = (int64_t)p * NP + j;
-        const float gj = __ldcg(t.grad + k) * scale;
+        const float gj = (pf ? gval : __ldcg(t.grad + k)) * scale;
         float mj = pf ? m_pf : t.m[k], vj = pf ? v_pf : t.v[k];
         mj += (gj - mj) * (1.f - t.beta1);
         vj += (gj * gj - vj) * (1.f - t.beta2);
