@@ -333,6 +333,12 @@ class FCNetLearner(_LearnerBase):
         self._update_kl(stats)
         return stats
 
+    def refresh_filter_norm(self):
+        """Recompute the normalisation table (mean, 1/(std+1e-8)) from filt_n / filt_M / filt_S — after the state was
+        written from outside (checkpoint import)."""
+        zero = torch.zeros(self.P, 1, self.D, 3, dtype=torch.float64, device=self.device)
+        K.filter_merge(zero, 0, self.filt_n, self.filt_M, self.filt_S, self.norm)
+
     # ---- plain inference (sampler side) ---------------------------------------------------------------------
     def compute_actions(self, raw_obs: torch.Tensor, eps: Optional[torch.Tensor] = None, update_filter: bool = False):
         """raw_obs [P,B,D] -> dict(logits, value[, action, logp]); optionally pushes the rows into the filter first
