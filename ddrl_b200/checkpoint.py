@@ -256,7 +256,9 @@ def from_learner(learner, policy_ids: List[str], stats: Optional[List[Dict[str, 
     pols: "OrderedDict[str, PolicyCheckpoint]" = OrderedDict()
     for p, pid in enumerate(policy_ids):
         st = dict(stats[p]) if stats else {}
-        st.setdefault("cur_kl_coeff", float(learner.kl_coeff_host[p]))
+        # the coefficient the NEXT iteration will use (RLlib's own stat is the pre-update value and its checkpoints do not
+        # carry the kl_coeff variable at all — a restored RLlib trainer restarts from config["kl_coeff"])
+        st["cur_kl_coeff"] = float(learner.kl_coeff_host[p])
         st.setdefault("cur_lr", float(np.float32(learner.cfg.lr)))
         pols[pid] = PolicyCheckpoint(
             theta=learner.theta[p].detach().cpu().numpy().copy(), shapes=shapes,

@@ -65,4 +65,4 @@ def test_checkpoint_drives_the_learner(arch, tmp_path):
     for name in ("theta", "m", "v", "beta_pow", "filt_n", "filt_M", "filt_S", "norm", "kl_coeff"):
         assert torch.equal(getattr(L, name), getattr(L2, name)), name
     assert ck3.counters["num_steps_trained"] == 123
-    assert ck3.policies[pids[0]].learner_stats["cur_kl_coeff"] == pytest.approx(stats[0]["cur_kl_coeff"])
+    assert ck3.policies[pids[0]].learner_stats["cur_kl_coeff"] == pytest.approx(float(L.kl_coeff_host[0]))
