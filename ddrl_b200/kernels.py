@@ -259,6 +259,59 @@ def gcn_forward(x, adj, W, b=None, act: str = "tanh"):
     return y
 
 
+_ACT = {"tanh": 1, None: 0, "linear": 0}
+
+
+def mpnn2_forward(x, adj, W_msg, W_upd, b=None, act: str = "tanh"):
+    """MPNN2 (models/gcn.py:96-150): x [B,4,F], adj [B,4,4], W_msg [2F,U], W_upd [F+U,U] -> [B,4,U]."""
+    B, n, F = x.shape
+    U = W_upd.shape[1]
+    if n != 4 or tuple(W_msg.shape) != (2 * F, U) or tuple(W_upd.shape) != (F + U, U):
+        raise DDRLError(f"mpnn2_forward: bad shapes x {tuple(x.shape)} W_msg {tuple(W_msg.shape)} W_upd {tuple(W_upd.shape)}")
+    y = torch.empty(B, n, U, dtype=torch.float32, device=x.device)
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_mpnn2_forward(_p(x, f32, "x"), _p(adj, f32, "adj"), _p(W_msg, f32, "W_msg"), _p(W_upd, f32, "W_upd"),
+                                              _p(b, f32, "b"), B, F, U, _ACT[act], _p(y, f32, "y"), _stream()), "mpnn2_forward")
+    return y
+
+
+def gat1_forward(x, adj, W_pre, w_att, b=None, act: str = "tanh"):
+    """GAT1 (models/gcn.py:153-206): x [B,4,F], adj [B,4,4], W_pre [F,U], w_att [2U] (or [2U,1]) -> [B,4,U]."""
+    B, n, F = x.shape
+    U = W_pre.shape[1]
+    w_att = w_att.reshape(-1)
+    if n != 4 or W_pre.shape[0] != F or w_att.numel() != 2 * U:
+        raise DDRLError(f"gat1_forward: bad shapes x {tuple(x.shape)} W_pre {tuple(W_pre.shape)} w_att {tuple(w_att.shape)}")
+    y = torch.empty(B, n, U, dtype=torch.float32, device=x.device)
+    f32 = torch.float32
+    _lib.check(_lib.load().ddrl_gat1_forward(_p(x, f32, "x"), _p(adj, f32, "adj"), _p(W_pre, f32, "W_pre"), _p(w_att, f32, "w_att"),
+                                             _p(b, f32, "b"), B, F, U, _ACT[act], _p(y, f32, "y"), _stream()), "gat1_forward")
+    return y
+
+
+def symm_norm(adj):
+    """graph_ops.symm_norm (models/graph_ops.py:3-11): D^-1/2 A D^-1/2, adj [B,N,N]."""
+    B, N, _ = adj.shape
+    out = torch.empty_like(adj)
+    _lib.check(_lib.load().ddrl_symm_norm(_p(adj, torch.float32, "adj"), B, N, _p(out, torch.float32, "out"), _stream()), "symm_norm")
+    return out
+
+
+def segment_softmax(data, segment_ids, num_segments: int):
+    """graph_ops.segment_softmax (models/graph_ops.py:23-26): data [E] or [E,C], segment_ids [E] int32."""
+    d2 = data.reshape(data.shape[0], -1).contiguous()
+    E, Cc = d2.shape
+    sums = torch.empty(num_segments, Cc, dtype=torch.float32, device=data.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=data.device)
+    out = torch.empty_like(d2)
+    _lib.check(_lib.load().ddrl_segment_softmax(_p(d2, torch.float32, "data"), _p(segment_ids, torch.int32, "segment_ids"), E, Cc,
+                                                int(num_segments), _p(sums, torch.float32, "sums"), _p(bad, torch.int32, "bad"),
+                                                _p(out, torch.float32, "out"), _stream()), "segment_softmax")
+    if int(bad.item()):
+        raise DDRLError("segment_softmax: a segment id is outside [0, num_segments)")
+    return out.reshape(data.shape)
+
+
 def leg_coupling_(logits, node_id, coupling):
     B, W = logits.shape
     f32 = torch.float32

@@ -263,6 +263,24 @@ int ddrl_graphnet_backward(const float* theta, const int32_t* node_idx, const fl
 int ddrl_gcn_forward(const float* x, const float* adj, const float* W, const float* b, int64_t B,
                      int F, int U, int act, float* y, void* stream);
 
+/* Graph-layer variants the reference carries but does not wire into a model, forward only,
+ * 4-node graphs: X [B][4][F], A [B][4][4] (adj[s][r] != 0 => edge s -> r), F, U <= 64, act: 0 none, 1 tanh.
+ *   MPNN2 (models/gcn.py:96-150):  e = [x_s, x_r] W_msg (W_msg [2F][U]);  m_r = mean of incoming e (0 if none);
+ *                                   y = act([x, m] W_upd + b)  (W_upd [F+U][U], b [U] or NULL)
+ *   GAT1  (models/gcn.py:153-206): self loops added; x' = x W_pre (W_pre [F][U]); a = leaky_relu_0.2(w_att . [x'_s, x'_r])
+ *                                   (w_att [2U]); softmax of a over the edges of each receiver; y_s = act(sum_r Att[s][r] x'_r + b)
+ *   symm_norm (models/graph_ops.py:3-11): D^-1/2 A D^-1/2 for A [B][N][N], N <= 64 (zero degree -> NaN like the reference)
+ *   segment_softmax (models/graph_ops.py:23-26): out = exp(data) / segment_sum(exp(data)); data [E][C], segment_ids [E]
+ *       int32 in [0, num_segments); sums_ws [num_segments][C] floats and bad_id (device int: 1 if an id was out of
+ *       range) are scratch; sums use float atomics (order-dependent in the last bits). */
+int ddrl_mpnn2_forward(const float* x, const float* adj, const float* W_msg, const float* W_upd, const float* b,
+                       int64_t B, int F, int U, int act, float* y, void* stream);
+int ddrl_gat1_forward(const float* x, const float* adj, const float* W_pre, const float* w_att, const float* b,
+                      int64_t B, int F, int U, int act, float* y, void* stream);
+int ddrl_symm_norm(const float* adj, int64_t B, int N, float* out, void* stream);
+int ddrl_segment_softmax(const float* data, const int32_t* segment_ids, int64_t E, int C, int64_t num_segments,
+                         float* sums_ws, int* bad_id, float* out, void* stream);
+
 /* DiagGaussian sample + logp (RLlib models/tf/tf_action_dist.py DiagGaussian._build_sample_op / logp)
  * for models without a fused epilogue: action = mean + exp(log_std)*eps, logp(action).
  *   logits [R][2A], eps [R][A] -> action [R][A], logp [R]. */

@@ -155,3 +155,72 @@ def test_graphnet_ppo_iteration_runs_and_first_step_matches_oracle():
     assert scaled_err(L.theta.cpu().numpy().reshape(-1), new_t.numpy()) < TOL
     for k in ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var"):
         assert abs(stats[0][k] - s_ref[k]) < 1e-4 * max(1.0, abs(s_ref[k])), (k, stats[0][k], s_ref[k])
+
+
+# ---- the graph-layer variants the reference carries but does not wire into a model ---------------------
+def _rand_adj(rng, B, selfloops=False):
+    adj = (rng.random((B, 4, 4)) < 0.5).astype(np.float32)
+    ring = _O().ring_adjacency().numpy()
+    adj[: B // 2] = ring                      # half the batch: the quantruped ring
+    if not selfloops:
+        adj[:, np.arange(4), np.arange(4)] = 0.0
+    return adj
+
+
+@pytest.mark.parametrize("F,U,bias,act", [(23, 64, False, "tanh"), (64, 64, True, "tanh"), (19, 32, True, None)])
+def test_mpnn2_layer(F, U, bias, act):
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(F + U)
+    B = 257
+    x = rng.standard_normal((B, 4, F)).astype(np.float32)
+    adj = _rand_adj(rng, B)
+    Wm = (rng.standard_normal((2 * F, U)) * 0.2).astype(np.float32)
+    Wu = (rng.standard_normal((F + U, U)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(U).astype(np.float32)
+    y = K.mpnn2_forward(_dev(x), _dev(adj), _dev(Wm), _dev(Wu), _dev(b) if bias else None, act)
+    d = lambda a: torch.from_numpy(a).double()
+    ref = O.mpnn2_layer(d(x), d(adj), d(Wm), d(Wu), d(b) if bias else None, act)
+    assert scaled_err(y.cpu().numpy(), ref.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("F,U,bias,act", [(23, 64, False, "tanh"), (64, 48, True, None)])
+def test_gat1_layer(F, U, bias, act):
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(F * U)
+    B = 130
+    x = rng.standard_normal((B, 4, F)).astype(np.float32)
+    adj = _rand_adj(rng, B, selfloops=True)
+    Wp = (rng.standard_normal((F, U)) * 0.2).astype(np.float32)
+    wa = (rng.standard_normal((2 * U, 1)) * 0.3).astype(np.float32)
+    b = rng.standard_normal(U).astype(np.float32)
+    y = K.gat1_forward(_dev(x), _dev(adj), _dev(Wp), _dev(wa), _dev(b) if bias else None, act)
+    d = lambda a: torch.from_numpy(a).double()
+    ref = O.gat1_layer(d(x), d(adj), d(Wp), d(wa), d(b) if bias else None, act)
+    assert scaled_err(y.cpu().numpy(), ref.numpy()) < 1e-5
+
+
+def test_symm_norm_and_segment_softmax():
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(3)
+    adj = (rng.random((64, 4, 4)) < 0.6).astype(np.float32)
+    adj[:, :, 0] = 1.0                         # every row has a neighbour (zero degree is NaN in the reference too)
+    out = K.symm_norm(_dev(adj)).cpu().numpy()
+    ref = O.symm_norm(torch.from_numpy(adj).double()).numpy()
+    assert scaled_err(out, ref) < 1e-6
+    z = np.zeros((1, 4, 4), np.float32)        # zero-degree rows: NaN, like tf (0 ** -0.5 = inf, inf * 0 = nan)
+    assert np.isnan(K.symm_norm(_dev(z)).cpu().numpy()).all()
+    E, S = 1000, 37
+    data = rng.standard_normal((E, 1)).astype(np.float32)
+    seg = rng.integers(0, S, size=E).astype(np.int32)
+    sm = K.segment_softmax(_dev(data), _dev(seg), S).cpu().numpy()
+    ref = O.segment_softmax(torch.from_numpy(data).double(), torch.from_numpy(seg).long(), S).numpy()
+    assert scaled_err(sm, ref) < 1e-6
+    sums = np.zeros(S)
+    np.add.at(sums, seg, sm[:, 0])
+    assert np.allclose(sums[np.bincount(seg, minlength=S) > 0], 1.0, atol=1e-5)      # every non-empty segment sums to 1
+    from ddrl_b200._lib import DDRLError
+    with pytest.raises(DDRLError):
+        K.segment_softmax(_dev(data), _dev(seg), S - 5)
