@@ -360,6 +360,61 @@ __global__ void obs_gather_kernel(const T* __restrict__ full, int64_t S, int Dfu
     }
 }
 
+// N2: per-agent reward / cost split of the multi-agent adaptor, batched over env-steps (float64 arithmetic like numpy):
+//   contact_a = sum_body Wc[a][body] * contact_w * sum_j clip(cfrc[body][j], -1, 1)^2      (distribute_contact_cost)
+//   mode 0  fw / Ag - ctrl_w * |act_a|^2 - contact_a                                        (distribute_per_leg_reward)
+//   mode 1  fw - Ag * (ctrl_w * |act_a|^2 + contact_a)                                      (… with norm_reward)
+//   mode 2  (fw - ctrl_w * sum_a |act_a|^2 - contact_w * sum_all clip(cfrc)^2) / Ag         (distribute_global_reward)
+//   mode 3  fw / Ag - ctrl_w * 0.25 * sum_a |act_a|^2 - contact_a                           (GlobalCosts env)
+__global__ void reward_split_kernel(const float* __restrict__ fw, const float* __restrict__ act, const double* __restrict__ cfrc,
+                                    const double* __restrict__ Wc, int64_t S, int Ag, int A, int NB, double ctrl_w,
+                                    double contact_w, int mode, float* __restrict__ rew) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double body[16];
+    double all_contact = 0.0;
+    for (int b = 0; b < NB; ++b) {
+        double q = 0.0;
+        for (int j = 0; j < 6; ++j) {
+            const double f = fmin(fmax(cfrc[(s * NB + b) * 6 + j], -1.0), 1.0);
+            q += contact_w * (f * f);
+        }
+        body[b] = q;
+        all_contact += q;
+    }
+    double ctrl[8], ctrl_sum = 0.0;
+    for (int a = 0; a < Ag; ++a) {
+        double q = 0.0;
+        for (int j = 0; j < A; ++j) {
+            const double v = (double)act[(s * Ag + a) * A + j];
+            q += v * v;
+        }
+        ctrl[a] = q;
+        ctrl_sum += q;
+    }
+    const double f = (double)fw[s];
+    for (int a = 0; a < Ag; ++a) {
+        double c = 0.0;
+        for (int b = 0; b < NB; ++b) c += body[b] * Wc[a * NB + b];
+        double r;
+        if (mode == 0) r = f / Ag - ctrl_w * ctrl[a] - c;
+        else if (mode == 1) r = f - Ag * (ctrl_w * ctrl[a] + c);
+        else if (mode == 2) r = (f - ctrl_w * ctrl_sum - all_contact) / Ag;
+        else r = f / Ag - ctrl_w * 0.25 * ctrl_sum - c;
+        rew[s * Ag + a] = (float)r;
+    }
+}
+
+// N2: concatenate_actions (adaptor :205-212) with RLlib's clip_actions: env_action[table[a][j]] = clip(act[a][j], lo, hi)
+__global__ void concat_actions_kernel(const float* __restrict__ act, const int32_t* __restrict__ table, int64_t S, int Ag, int A,
+                                      int Afull, float lo, float hi, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * Ag * A) return;
+    const int64_t s = i / (Ag * A);
+    const int k = (int)(i % (Ag * A));
+    out[s * Afull + table[k]] = fminf(fmaxf(act[i], lo), hi);
+}
+
 // DiagGaussian sample + logp (RLlib models/tf/tf_action_dist.py) for models without a fused epilogue.
 __global__ void dg_sample_kernel(const float* __restrict__ logits, const float* __restrict__ eps, int64_t R, int A,
                                  float* __restrict__ action, float* __restrict__ logp) {
@@ -606,5 +661,31 @@ extern "C" int ddrl_peer_free(void* ptr) {
     DDRL_REQUIRE(ptr, DDRL_E_BADARG, "peer_free: null pointer");
     const cudaError_t e = cudaFree(ptr);
     DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "peer_free: %s", cudaGetErrorString(e));
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_reward_split(const float* fw_reward, const float* actions, const double* cfrc_ext, const double* contact_table,
+                                 int64_t S, int Ag, int A, int NB, double ctrl_cost_weight, double contact_cost_weight, int mode,
+                                 float* rewards, void* stream) {
+    DDRL_REQUIRE(fw_reward && actions && cfrc_ext && contact_table && rewards && S >= 0, DDRL_E_BADARG, "reward_split: null pointer or bad S");
+    DDRL_REQUIRE(Ag >= 1 && Ag <= 8 && A >= 1 && NB >= 1 && NB <= 16 && mode >= 0 && mode <= 3, DDRL_E_UNSUPPORTED_SHAPE,
+                 "reward_split: unsupported Ag=%d NB=%d mode=%d (Ag <= 8, NB <= 16, mode 0..3)", Ag, NB, mode);
+    if (S == 0) return DDRL_OK;
+    reward_split_kernel<<<(unsigned)((S + 127) / 128), 128, 0, (cudaStream_t)stream>>>(fw_reward, actions, cfrc_ext, contact_table, S, Ag,
+                                                                                      A, NB, ctrl_cost_weight, contact_cost_weight,
+                                                                                      mode, rewards);
+    DDRL_CHECK_LAUNCH("reward_split");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_concat_actions(const float* actions, const int32_t* action_table, int64_t S, int Ag, int A, int A_full,
+                                   float clip_lo, float clip_hi, float* env_actions, void* stream) {
+    DDRL_REQUIRE(actions && action_table && env_actions && S >= 0 && Ag >= 1 && A >= 1 && A_full >= Ag * A, DDRL_E_BADARG,
+                 "concat_actions: null pointer or bad shape (A_full >= Ag * A)");
+    if (S == 0) return DDRL_OK;
+    const int64_t n = S * Ag * A;
+    concat_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(actions, action_table, S, Ag, A, A_full,
+                                                                                        clip_lo, clip_hi, env_actions);
+    DDRL_CHECK_LAUNCH("concat_actions");
     return DDRL_OK;
 }

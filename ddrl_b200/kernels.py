@@ -456,3 +456,30 @@ def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, bet
     t.status = _p(status, torch.int32, "status")
     t.world, t.rank, t.nsteps = 1, 0, 1
     return t
+
+
+REWARD_MODES = {"per_leg": 0, "per_leg_norm": 1, "global": 2, "global_costs": 3}
+
+
+def reward_split(fw_reward, actions, cfrc_ext, contact_table, ctrl_cost_weight: float, contact_cost_weight: float,
+                 mode: str = "per_leg"):
+    """Per-agent rewards of the multi-agent adaptor, batched: fw_reward [S] f32, actions [S,Ag,A] f32, cfrc_ext [S,NB,6] f64,
+    contact_table [Ag,NB] f64 -> [S,Ag] f32 (see ddrl_reward_split)."""
+    S, Ag, A = actions.shape
+    NB = cfrc_ext.shape[1]
+    out = torch.empty(S, Ag, dtype=torch.float32, device=actions.device)
+    _lib.check(_lib.load().ddrl_reward_split(_p(fw_reward, torch.float32, "fw_reward"), _p(actions, torch.float32, "actions"),
+                                             _p(cfrc_ext, torch.float64, "cfrc_ext"), _p(contact_table, torch.float64, "contact_table"),
+                                             S, Ag, A, NB, float(ctrl_cost_weight), float(contact_cost_weight), REWARD_MODES[mode],
+                                             _p(out, torch.float32, "rewards"), _stream()), "reward_split")
+    return out
+
+
+def concat_actions(actions, action_table, A_full: int = 8, clip=(-1.0, 1.0)):
+    """actions [S,Ag,A] f32 + action_table [Ag,A] i32 -> env actions [S,A_full] f32, clipped like RLlib's clip_actions."""
+    S, Ag, A = actions.shape
+    out = torch.zeros(S, A_full, dtype=torch.float32, device=actions.device)
+    _lib.check(_lib.load().ddrl_concat_actions(_p(actions, torch.float32, "actions"), _p(action_table, torch.int32, "action_table"),
+                                               S, Ag, A, A_full, float(clip[0]), float(clip[1]), _p(out, torch.float32, "out"),
+                                               _stream()), "concat_actions")
+    return out

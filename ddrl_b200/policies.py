@@ -26,6 +26,9 @@ OBS_FIELDS = [
     "hl_hip_hist_ctrl", "hl_knee_vel_hist_ctrl", "hr_hip_hist_ctrl", "hr_knee_vel_hist_ctrl",
 ]
 ACTION_FIELDS = ["fr_hip", "fr_knee", "fl_hip", "fl_knee", "hl_hip", "hl_knee", "hr_hip", "hr_knee"]
+# simulation_envs/quantruped_v3.py:105-112 — rows of sim.data.cfrc_ext ([14 bodies][6])
+CONTACT_FORCE_FIELDS = ["body_floor", "body", "fl_hip", "fl_leg", "fl_foot", "hl_hip", "hl_leg", "hl_foot",
+                        "hr_hip", "hr_leg", "hr_foot", "fr_hip", "fr_leg", "fr_foot"]
 TVEL_FIELD = "body_target_x_vel"   # appended as index 43 by QuAntrupedTVelEnv.set_target_velocity (quantruped_v3.py:394-400)
 
 
@@ -46,6 +49,22 @@ def get_action_indices(prefixes: Sequence[str] = None) -> List[int]:
     for p in prefixes:
         out.extend(i for i, f in enumerate(ACTION_FIELDS) if f.startswith(p))
     return out
+
+
+def get_contact_force_indices(prefixes: Sequence[str] = None, weights: Sequence[float] = None):
+    """quantruped_v3.py:319-341: (indices, weights [k][1]) of the cfrc_ext rows whose field name starts with a prefix."""
+    if prefixes is None:
+        n = len(CONTACT_FORCE_FIELDS)
+        return list(range(n)), [[1.0]] * n
+    if weights is None:
+        weights = [1.0] * len(prefixes)
+    idx: List[int] = []
+    w: List[List[float]] = []
+    for pfx, wt in zip(prefixes, weights):
+        hit = [i for i, f in enumerate(CONTACT_FORCE_FIELDS) if f.startswith(pfx)]
+        idx.extend(hit)
+        w.extend([[wt]] * len(hit))
+    return idx, w
 
 
 class _Arch:
@@ -90,6 +109,37 @@ class _Arch:
     @classmethod
     def agents_per_policy(cls) -> int:
         return len(cls.agent_names) // len(cls.policy_names)
+
+    @classmethod
+    def contact_force_indices(cls):
+        """Per agent (indices, weights) like the env constructors build them: the torso rows ('body' matches body_floor
+        and body) weighted by 1 / #agents-sharing-them, the agent's own legs by 1
+        (e.g. quantruped_fourDecentralizedController_environments.py:31-36, …twoDecentralized…:66-69); the centralized
+        controller takes every row with weight 1 (quantruped_centralizedController_environment.py:54-56)."""
+        out = {}
+        for a in cls.agent_names:
+            legs = cls._act_prefixes[a]
+            if legs is None:
+                out[a] = get_contact_force_indices()
+            else:
+                out[a] = get_contact_force_indices(["body", *legs], [len(legs) / 4.0] + [1.0] * len(legs))
+        return out
+
+    @classmethod
+    def contact_table(cls) -> np.ndarray:
+        """float64 [n_agents, 14] dense weights of the cfrc_ext rows (0 = row not used by the agent)."""
+        t = np.zeros((len(cls.agent_names), len(CONTACT_FORCE_FIELDS)), dtype=np.float64)
+        for i, a in enumerate(cls.agent_names):
+            idx, w = cls.contact_force_indices()[a]
+            for j, wt in zip(idx, w):
+                t[i, j] += wt[0]
+        return t
+
+    @classmethod
+    def action_table(cls) -> np.ndarray:
+        """int32 [n_agents, A]: position of each agent action in the 8-dim env action (concatenate_actions)."""
+        ai = cls.action_indices()
+        return np.asarray([ai[a] for a in cls.agent_names], dtype=np.int32)
 
     @classmethod
     def gather_table(cls, use_target_velocity: bool = False) -> np.ndarray:

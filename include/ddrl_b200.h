@@ -111,6 +111,21 @@ int ddrl_fcnet_forward(const float* theta, const float* img, const float* obs, c
 int ddrl_obs_gather(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag,
                     int D, int P, float* out, void* stream);
 
+/* Replaces (batched over S env-steps): distribute_per_leg_reward / distribute_global_reward / distribute_contact_cost
+ * (simulation_envs/quantruped_adaptor_multi_environment.py:160-203) and the GlobalCosts variant
+ * (quantruped_fourDecentralizedController_GlobalCosts_environments.py:69-83), float64 arithmetic like numpy:
+ *   fw_reward [S] (info['reward_forward']), actions [S][Ag][A] (unclipped policy outputs), cfrc_ext [S][NB][6] float64,
+ *   contact_table [Ag][NB] float64 (weights of get_contact_force_indices, 0 = unused) -> rewards [S][Ag] float32.
+ *   mode 0 per-leg, 1 per-leg with norm_reward, 2 global reward, 3 GlobalCosts.  Ag <= 8, NB <= 16. */
+int ddrl_reward_split(const float* fw_reward, const float* actions, const double* cfrc_ext,
+                      const double* contact_table, int64_t S, int Ag, int A, int NB, double ctrl_cost_weight,
+                      double contact_cost_weight, int mode, float* rewards, void* stream);
+
+/* Replaces: concatenate_actions (quantruped_adaptor_multi_environment.py:205-212) + RLlib clip_actions:
+ *   env_actions [S][A_full][action_table[a][j]] = clip(actions [S][Ag][A], clip_lo, clip_hi); action_table [Ag][A] int32. */
+int ddrl_concat_actions(const float* actions, const int32_t* action_table, int64_t S, int Ag, int A, int A_full,
+                        float clip_lo, float clip_hi, float* env_actions, void* stream);
+
 /* Replaces: compute_advantages + postprocess_ppo_gae (RLlib evaluation/postprocessing.py,
  * agents/ppo/ppo_tf_policy.py), selected by use_gae/gamma/lambda at
  * train_experiment_1_architecture_on_flat.py:119-120.  Reverse scan per column in float64:

@@ -343,6 +343,64 @@ def get_action_indices(prefixes):
     return out
 
 
+def get_contact_force_indices(prefixes=None, weights=None):
+    """simulation_envs/quantruped_v3.py:319-341."""
+    fields = ['body_floor', 'body', 'fl_hip', 'fl_leg', 'fl_foot', 'hl_hip', 'hl_leg', 'hl_foot',
+              'hr_hip', 'hr_leg', 'hr_foot', 'fr_hip', 'fr_leg', 'fr_foot']      # quantruped_v3.py:105-112
+    if prefixes is None:
+        return np.arange(len(fields)), np.ones([len(fields), 1])
+    if weights is None:
+        weights = np.ones(len(prefixes))
+    idx, w = [], []
+    for prefix, weight in zip(prefixes, weights):
+        hit = list(np.where([f.startswith(prefix) for f in fields])[0])
+        idx.extend(hit)
+        w.extend([[weight]] * len(hit))
+    return idx, w
+
+
+def distribute_rewards(fw_reward, action_dict, cfrc_ext, contact_force_indices, agent_names, ctrl_cost_weight,
+                       contact_cost_weight, mode="per_leg"):
+    """One env step of the adaptor's reward split, line by line (quantruped_adaptor_multi_environment.py:151-203;
+    mode 'global_costs': quantruped_fourDecentralizedController_GlobalCosts_environments.py:69-83)  -> {agent: reward}."""
+    contact_forces = np.clip(cfrc_ext, -1., 1.)
+    contact_costs = contact_cost_weight * np.square(contact_forces)
+    contact_cost = {}
+    for a in agent_names:
+        idx, weights = contact_force_indices[a]
+        contact_cost[a] = np.sum(np.multiply(contact_costs[idx], weights))
+    rew = {}
+    n = len(agent_names)
+    if mode == "global":
+        contact_costs_sum = contact_cost_weight * np.sum(np.square(contact_forces))
+        ctrl_costs_sum = 0.
+        for a in agent_names:
+            ctrl_costs_sum += np.sum(np.square(action_dict[a]))
+        for a in agent_names:
+            rew[a] = (fw_reward - ctrl_cost_weight * ctrl_costs_sum - contact_costs_sum) / n
+    elif mode == "global_costs":
+        s = 0
+        for a in agent_names:
+            s += np.sum(np.square(action_dict[a]))
+        for a in agent_names:
+            rew[a] = (fw_reward / n) - (ctrl_cost_weight * 0.25 * s) - contact_cost[a]
+    else:
+        for a in agent_names:
+            if mode == "per_leg_norm":
+                rew[a] = fw_reward - n * (ctrl_cost_weight * np.sum(np.square(action_dict[a])) + contact_cost[a])
+            else:
+                rew[a] = fw_reward / n - ctrl_cost_weight * np.sum(np.square(action_dict[a])) - contact_cost[a]
+    return rew
+
+
+def concatenate_actions(action_dict, action_indices):
+    """quantruped_adaptor_multi_environment.py:205-212."""
+    actions = np.empty(8,)
+    for k in action_dict:
+        actions[action_indices[k]] = action_dict[k]
+    return actions
+
+
 # --------------------------------------------------------------------------------------------
 # a4  MeanStdFilter / RunningStat        ray.rllib.utils.filter (1.0.1), used at
 #     simulation_envs/observation_filter.py:8-12 and via observation_filter="MeanStdFilter"

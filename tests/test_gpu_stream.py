@@ -168,3 +168,35 @@ def test_obs_gather_is_bit_exact(scope, tvel):
         ref = np.stack([np.stack([full[s][table[p * k + j]] for s in range(37) for j in range(k)]) for p in range(P)])
         assert out.shape == (P, 37 * k, D)
         assert np.array_equal(out, ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("scope", ["QuantrupedMultiEnv_FullyDecentral", "QuantrupedMultiEnv_TwoSides", "QuantrupedMultiEnv_Centralized"])
+@pytest.mark.parametrize("mode", ["per_leg", "per_leg_norm", "global", "global_costs"])
+def test_reward_split_and_action_concat_match_the_adaptor(scope, mode):
+    """N2: batched per-agent reward / cost split and action concatenation == the adaptor's per-step dict loops."""
+    import oracle.ddrl_oracle as O
+    from ddrl_b200 import kernels as K
+    from ddrl_b200.policies import ARCHITECTURES
+    env = ARCHITECTURES[scope]
+    Ag, A = len(env.agent_names), env.act_dim()
+    rng = np.random.default_rng(Ag * 10 + A)
+    S = 97
+    fw = rng.standard_normal(S).astype(np.float32)
+    act = (1.5 * rng.standard_normal((S, Ag, A))).astype(np.float32)           # some beyond [-1, 1]
+    cfrc = 2.0 * rng.standard_normal((S, 14, 6))                               # clipped to [-1, 1] inside
+    cfrc[rng.random((S, 14, 6)) < 0.5] = 0.0
+    ctrl_w, con_w = 0.25, 0.025                                                # experiment-3 env_config (SURVEY.md §5)
+    cfi = env.contact_force_indices()
+    rew = K.reward_split(_dev(fw), _dev(act), _dev(cfrc), _dev(env.contact_table()), ctrl_w, con_w, mode).cpu().numpy()
+    ref = np.zeros((S, Ag))
+    for s in range(S):
+        r = O.distribute_rewards(float(fw[s]), {a: act[s, i] for i, a in enumerate(env.agent_names)}, cfrc[s], cfi,
+                                 env.agent_names, ctrl_w, con_w, mode)
+        ref[s] = [r[a] for a in env.agent_names]
+    assert np.abs(rew - ref).max() < 1e-6 * max(1.0, np.abs(ref).max())
+    table = env.action_table()
+    full = K.concat_actions(_dev(act), _dev(table)).cpu().numpy()
+    ai = env.action_indices()
+    for s in range(0, S, 7):
+        refa = O.concatenate_actions({a: np.clip(act[s, i], -1.0, 1.0) for i, a in enumerate(env.agent_names)}, ai)
+        assert np.array_equal(full[s], refa.astype(np.float32))

@@ -118,3 +118,33 @@ def test_finalize_stats_matches_oracle_definitions():
     for k in O.STAT_KEYS:
         assert abs(out[k] - float(st[k])) < 1e-5 * max(1.0, abs(float(st[k]))), k
     assert out["cur_kl_coeff"] == float(np.float32(0.3)) and out["cur_lr"] == float(np.float32(3e-4))
+
+
+def test_contact_force_tables_match_the_reference_env_constructors():
+    """get_contact_force_indices(['body', leg], [1/4, 1]) etc. — the literal calls of the env constructors
+    (quantruped_fourDecentralizedController_environments.py:31-36, …twoDecentralized…:66-69, …centralized…:54-56)."""
+    import oracle.ddrl_oracle as O
+    from ddrl_b200.policies import ARCHITECTURES
+    lit = {
+        "QuantrupedMultiEnv_FullyDecentral": {f"agent_{L}": (["body", L.lower()], [1. / 4., 1.]) for L in ("FL", "HL", "HR", "FR")},
+        "QuantrupedMultiEnv_Local": {f"agent_{L}": (["body", L.lower()], [1. / 4., 1.]) for L in ("FL", "HL", "HR", "FR")},
+        "QuantrupedMultiEnv_TwoSides": {"agent_LEFT": (["body", "fl", "hl"], [1. / 2., 1., 1.]),
+                                        "agent_RIGHT": (["body", "hr", "fr"], [1. / 2., 1., 1.])},
+        "QuantrupedMultiEnv_TwoDiags": {"agent_FLHR": (["body", "fl", "hr"], [1. / 2., 1., 1.]),
+                                        "agent_HLFR": (["body", "hl", "fr"], [1. / 2., 1., 1.])},
+        "QuantrupedMultiEnv_Centralized": {"central_agent": (None, None)},
+    }
+    for scope, agents in lit.items():
+        env = ARCHITECTURES[scope]
+        mine = env.contact_force_indices()
+        table = env.contact_table()
+        assert table.shape == (len(env.agent_names), 14)
+        for i, a in enumerate(env.agent_names):
+            idx, w = O.get_contact_force_indices(*agents[a])
+            assert list(mine[a][0]) == list(idx)
+            assert np.allclose(np.asarray(mine[a][1], dtype=np.float64), np.asarray(w, dtype=np.float64))
+            dense = np.zeros(14)
+            for j, wt in zip(idx, w):
+                dense[j] += np.asarray(wt).reshape(-1)[0]
+            assert np.array_equal(table[i], dense)
+    assert ARCHITECTURES["QuantrupedMultiEnv_FullyDecentral"].action_table().tolist() == [[2, 3], [4, 5], [6, 7], [0, 1]]
