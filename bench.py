@@ -224,8 +224,20 @@ def main():
                     help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
+    ap.add_argument("--arch", default="FullyDecentral",
+                    help="supplementary: any published architecture (Centralized, FullyDecentral, Local, SingleNeighbor, "
+                         "SingleDiagonal, SingleToFront, TwoSides, TwoDiags; append _TVel for the target-velocity obs); "
+                         "the headline line is the default FullyDecentral = BASELINE.json configs[1]")
     ap.add_argument("--gn-epochs", type=int, default=2)
     args = ap.parse_args()
+    if args.arch != "FullyDecentral":      # supplementary architectures: same harness, the architecture's P / D / A
+        from ddrl_b200.policies import ARCHITECTURES
+        tvel = args.arch.endswith("_TVel")
+        env = ARCHITECTURES["QuantrupedMultiEnv_" + args.arch.replace("_TVel", "")]
+        if len(env.agent_names) != len(env.policy_names):
+            raise SystemExit("--arch: only the published one-agent-per-policy architectures")
+        WORKLOAD.update(name=f"{args.arch} (supplementary architecture, same harness as configs[1])", P=len(env.policy_names),
+                        Ag=len(env.agent_names), D=env.obs_dim(tvel), A=env.act_dim())
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "graphnet":

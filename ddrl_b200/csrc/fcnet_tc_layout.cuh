@@ -61,25 +61,32 @@ __host__ __device__ inline TcSmem tc_smem(int D, int A) {
 
 
 // ---- "ping-pong" kernel (tc2.cu): both branches resident, so the tensor core works on one branch while the CTA runs
-// the other branch's epilogue.  Needs H1/H2 of BOTH branches (128 KB) -> only for KX <= 32 (D <= 30) and small heads.
-// The loss-gradient operand DL[b] reuses the fp32 staging area of the observations (dead once X has been split).
+// the other branch's epilogue.  H1/H2 of BOTH branches take 128 KB, so two buffers live in space that is dead at the time:
+//   * the loss-gradient operand DL[b] sits in the W1 part of the weight image (W1 is only read by F1; a CTA with another
+//     tile to go reloads it from L2 behind the backward, and every step reloads the whole image anyway);
+//   * the fp32 staging of the observations (xraw) sits in H2[1] (free from B3(1) of one tile to tanh2(1) of the next).
+// That fits KX <= 48 (D <= 46) with A <= 4: every published architecture except the centralized one (A = 8).
 struct Tc2Smem {
     int X[2], H1[2][2], H2[2][2], DL[2][2], xraw, pf, red, bar, total;
+    bool dl_in_w1;
 };
 __host__ __device__ inline Tc2Smem tc2_smem(int D, int A) {
     const int KX = tc_kx(D);
+    const TcImg I = tc_img(D, A);
     Tc2Smem s;
-    int p = tc_img(D, A).bytes;
+    int p = I.bytes;
     for (int h = 0; h < 2; ++h) { s.X[h] = p; p += TC_ROWS * KX * 2; }
     for (int b = 0; b < 2; ++b)
         for (int h = 0; h < 2; ++h) { s.H1[b][h] = p; p += TC_ROWS * 64 * 2; }
     for (int b = 0; b < 2; ++b)
         for (int h = 0; h < 2; ++h) { s.H2[b][h] = p; p += TC_ROWS * 64 * 2; }
-    const int dl_bytes = 4 * TC_ROWS * TC_NO * 2, x_bytes = ((TC_ROWS * D * 4) + 15) & ~15;
-    s.xraw = p;
+    const int dl_bytes = 4 * TC_ROWS * TC_NO * 2, w1_bytes = 4 * 64 * KX * 2;
+    s.dl_in_w1 = w1_bytes >= dl_bytes;              // KX >= 32
+    const int dl0 = s.dl_in_w1 ? I.W1[0][0] : p;
+    if (!s.dl_in_w1) p += dl_bytes;
     for (int b = 0; b < 2; ++b)
-        for (int h = 0; h < 2; ++h) s.DL[b][h] = p + (2 * b + h) * TC_ROWS * TC_NO * 2;
-    p += dl_bytes > x_bytes ? dl_bytes : x_bytes;
+        for (int h = 0; h < 2; ++h) s.DL[b][h] = dl0 + (2 * b + h) * TC_ROWS * TC_NO * 2;
+    s.xraw = s.H2[1][0];                            // 32 KB >= 128 rows x 63 floats
     s.pf = p;    p += ((TC_ROWS * (3 * A + 4) * 4) + 15) & ~15;
     s.red = p;   p += 8 * 16 * 8;    // [8 loss warps][16] doubles
     s.bar = p;   p += 64;            // 2 mbarriers, tmem slot, 2 gradient scales
@@ -87,7 +94,7 @@ __host__ __device__ inline Tc2Smem tc2_smem(int D, int A) {
     return s;
 }
 __host__ __device__ inline bool tc2_eligible(int D, int A) {
-    return tc_kx(D) <= 32 && tc2_smem(D, A).total <= 227 * 1024;
+    return tc_kx(D) <= 48 && tc2_smem(D, A).total <= 227 * 1024;
 }
 
 // Where flat parameter j lives in the image: fp16 pair (byte offsets of hi and lo, f16 = true) or one float.

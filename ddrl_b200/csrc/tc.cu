@@ -696,7 +696,7 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
         a.tail = *tail;
         const bool pp = g_tc_variant == 2 || (g_tc_variant == 0 && tc2_eligible(D, A));
         DDRL_REQUIRE(tail->nsteps <= 1 || pp, DDRL_E_UNSUPPORTED_SHAPE,
-                     "ppo_train_step_tc: nsteps > 1 needs the ping-pong kernel (D <= 30, A <= 4)");
+                     "ppo_train_step_tc: nsteps > 1 needs the ping-pong kernel (D <= 46, A <= 4)");
     }
     const size_t smem = (size_t)tc_smem(D, A).total;
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);
@@ -704,7 +704,7 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     const bool pingpong = g_tc_variant == 2 || (g_tc_variant == 0 && tc2_eligible(D, A));
     if (pingpong) {
         DDRL_REQUIRE(tc2_eligible(D, A) && A <= 4, DDRL_E_UNSUPPORTED_SHAPE,
-                     "ppo_train_step_tc: ping-pong variant needs D <= 30 and A <= 4 (D=%d, A=%d)", D, A);
+                     "ppo_train_step_tc: ping-pong variant needs D <= 46 and A <= 4 (D=%d, A=%d)", D, A);
         rc = launch_tc2(a, P, ctas_per_policy, (cudaStream_t)stream);
         if (rc != DDRL_OK) return rc;
         DDRL_CHECK_LAUNCH("ppo_train_step_tc");

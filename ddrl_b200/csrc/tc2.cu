@@ -10,8 +10,9 @@
 // executes the other branch's GEMMs, so the MMA latency that the branch-sequential kernel exposed 12 times per tile is
 // hidden; each branch has its own accumulator columns and its own mbarrier.  The two PPO-loss halves (policy part on
 // warps 0-3, value part on warps 4-7) run concurrently.  MMAs are issued by lane 0 of the LAST warp, which carries no
-// loss work.  Cost: H1/H2 of both branches live in shared memory (128 KB), so the kernel serves KX <= 32 (D <= 30) with
-// 2A+... small heads (tc2_eligible); larger observations keep the branch-sequential kernel.
+// loss work.  Cost: H1/H2 of both branches live in shared memory (128 KB); DL and the observation staging reuse space that
+// is dead at the time (fcnet_tc_layout.cuh), which fits D <= 46 with A <= 4 (tc2_eligible); the centralized controller
+// (A = 8) keeps the branch-sequential kernel.
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -148,13 +149,14 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 8 = dl, 16 = dz2, 32 = dz1
     const float klc = a.kl_coeff[p];
     const int ch0 = (D >> 3) & ~1;     // 16-column window of X that contains the constant-1 pad column D
+    const bool gw1_split = KX <= 32;   // two product-split accumulators of KX columns per branch fit TMEM only then
     const int NPs = (o.NP + 3) & ~3;
     // Thread-block clusters (launch attribute; cluster = cs consecutive CTAs of one policy): the per-CTA partial gradient
     // goes to shared memory, the cluster adds its cs partials over distributed shared memory (CTA r owns 1/cs of the
     // vector) and only ONE partial per cluster reaches L2 — the 148 x 45 KB write / drain / re-read per step was ~9 us.
     const int cs = (int)umma::cluster_nctarank(), crank = (int)umma::cluster_ctarank();
     const int ncl = G / cs, cid = bx / cs;                 // clusters per policy, this CTA's cluster
-    float* stg = reinterpret_cast<float*>(sm + S.H2[0][0]);   // [NPs] staging of the partial (H2 is free after the main loop)
+    float* stg = reinterpret_cast<float*>(sm + S.H1[0][0]);   // [NPs] staging of the partial (H1 is free after the main loop)
     float* gp = cs > 1 ? stg : a.grad_part + ((int64_t)p * G + bx) * NPs;
     const bool has_tail = a.tail.theta != nullptr;
     const int nsteps = (has_tail && a.tail.nsteps > 1) ? a.tail.nsteps : 1;   // consecutive SGD steps of this launch
@@ -342,11 +344,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             for (int b = 0; b < 2; ++b) {   // B5: gW1_b[c][d] (+)= dZ1_b^T X by product (column D of X = constant 1 -> bias gradient)
                 mma_turn();
                 if (lane == 0) {
-                    if (mw == 0)
-                        tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8, acc, 1);
-                    if (mw == 1)
-                        tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b + 1), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8,
-                                     acc, 6);
+                    if (gw1_split) {
+                        if (mw == 0)
+                            tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8,
+                                         acc, 1);
+                        if (mw == 1)
+                            tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b + 1), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX,
+                                         8, acc, 6);
+                    } else if (mw == b) {
+                        tc_gemm(tmem + T2_GW1 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8, acc, 3);
+                    }
                     umma::mma_commit(mbar + b);
                 }
                 __syncwarp();
@@ -486,16 +493,21 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             publish();
             T2_STAMP(21 + 3 * b);
         }
-        {   // both B1 are complete (DL dead): stream the next tile's observations into the shared staging area
-            const int64_t nxt = row0 + TC_ROWS;
-            if (nxt < cr1) prefetch_x(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
-            asm volatile("cp.async.commit_group;\n" ::);
+        if (S.dl_in_w1 && row0 + TC_ROWS < cr1) {   // both B1 are complete (DL dead) and another tile follows: restore W1
+            const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+#pragma unroll 1
+            for (int i = I.W1[0][0] / 16 + tid; i < I.W2[0][0] / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
         }
         // ---- dz1 epilogue -> B5: gW1_b[c][d] (+)= dZ1_b^T X   (column D of X is the constant 1 -> bias gradient) --------
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
             const float sg = b ? sg1 : sg0;
             wait_b(b);      // B3 has consumed H1_b; dz1 = (dz2 W2^T) * (1 - h1^2) overwrites it
+            if (b == 1) {   // B3(1) done: dZ2_1 (in H2[1]) is dead -> stream the next tile's observations into that space
+                const int64_t nxt = row0 + TC_ROWS;
+                if (nxt < cr1) prefetch_x(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
+                asm volatile("cp.async.commit_group;\n" ::);
+            }
             T2_STAMP(25 + 3 * b);
             ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H1[b][0],
                                sm + S.H1[b][1], row, cq) ? 32 : 0;
@@ -536,13 +548,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         float v[8];
         const float sgb = sgs[b];
         const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
-        {   // gW2_b (this warp's 16 columns) and gW1_b (8 input features, two product halves): 4 TMEM loads in flight, one wait
-            uint32_t r0[8], r1[8], r2[8], r3[8];
-            const bool has_w1 = cq < (KX >> 3);       // KX <= 32: at most one 8-feature group per column quarter
+        {   // gW2_b: this warp's 16 columns
+            uint32_t r0[8], r1[8];
             umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq, r0);
             umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8, r1);
-            umma::tmem_ld8_nowait(tmem + tlane + T2_GW1 + 32 * (2 * b) + (has_w1 ? 8 * cq : 0), r2);
-            umma::tmem_ld8_nowait(tmem + tlane + T2_GW1 + 32 * (2 * b + 1) + (has_w1 ? 8 * cq : 0), r3);
             umma::tmem_ld_wait();
             if (mine) {
                 float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq);
@@ -554,14 +563,22 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
                                      __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
                 dst[3] = make_float4(__uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
                                      __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
-                if (has_w1) {
+            }
+        }
+#pragma unroll 1
+        for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
+            uint32_t r2[8], r3[8];
+            const uint32_t base0 = tmem + tlane + T2_GW1 + (gw1_split ? 32 * (2 * b) : 64 * b) + 8 * c8;
+            umma::tmem_ld8_nowait(base0, r2);
+            umma::tmem_ld8_nowait(gw1_split ? base0 + 32 : base0, r3);      // second product half (split) or the same again
+            umma::tmem_ld_wait();
+            if (mine) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int d = 8 * cq + j;
-                        const float g = (__uint_as_float(r2[j]) + __uint_as_float(r3[j])) * inv_gw1;
-                        if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = g;
-                        else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = g;
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const int d = 8 * c8 + j;
+                    const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
+                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = g;
+                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = g;
                 }
             }
         }
@@ -644,7 +661,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         ts.round = s + 1;
         ts.last = s == nsteps - 1;
         const bool tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                       reinterpret_cast<float*>(sm + S.H1[0][0]), a.dbg_clock, ncl);
+                                       reinterpret_cast<float*>(sm + S.H2[0][0]), a.dbg_clock, ncl);
         ok = ok && tok;
         ts.b1p *= a.tail.beta1;
         ts.b2p *= a.tail.beta2;

@@ -317,7 +317,7 @@ int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupli
  * the result is then unreliable and the step should be redone with ddrl_ppo_train_step. */
 int ddrl_fcnet_tc_image_bytes(int D, int A);
 /* Two schedules of the same arithmetic exist: 1 = branch-sequential (any D <= 63), 2 = "ping-pong" (both branches
- * resident, the tensor core runs one branch while the CTA runs the other's epilogue; D <= 30, A <= 4).
+ * resident, the tensor core runs one branch while the CTA runs the other's epilogue; D <= 46, A <= 4).
  * 0 (default) picks ping-pong whenever the shape allows it.  Process-wide; meant for tests and A/B timing. */
 int ddrl_tc_set_variant(int variant);
 /* 1 if ddrl_ppo_train_step_tc will use the ping-pong kernel for (D, A) under the current variant setting (the kernel that

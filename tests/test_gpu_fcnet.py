@@ -149,7 +149,7 @@ def _cuda_train_step(b, MB, mb_index, G, kl_coeff, cfg, dev="cuda", tc=False):
 
 
 @pytest.mark.parametrize("arch,G", [("FullyDecentral", 1), ("FullyDecentral", 37), ("Centralized", 5),
-                                    ("Local", 8), ("TwoSides", 3), ("SingleDiagonal", 16),
+                                    ("Local", 8), ("Local", 2), ("TwoSides", 3), ("SingleDiagonal", 16),
                                     ("Centralized_TVel", 7), ("FullyDecentral_TVel", 2), ("Local_TVel", 4),
                                     ("TwoSides_TVel", 9)])
 @pytest.mark.parametrize("tc", [False, True, "seq"], ids=["fp32", "tcgen05", "tcgen05-seq"])
