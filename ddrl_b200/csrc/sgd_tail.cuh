@@ -186,20 +186,26 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     if (W > 1) {
         const unsigned long long* xl = t.peer_x[t.rank] + ((int64_t)par * W * P + p) * xstride + j0;   // + w * P * xstride
         bool got = true;
+        const unsigned int want32 = (unsigned int)(want >> 32);
         for (int jj = tid; jj < S && j0 + jj < NP; jj += nt) {
-            float s = 0.f;
+            // all ranks' words are requested together (one L2 round trip when they have already landed — the common case);
+            // only the missing ones are polled again
+            unsigned long long wd[DDRL_MAX_RANKS];
+            unsigned int pending = (1u << W) - 1u;
 #pragma unroll 1
-            for (int w = 0; w < W; ++w) {
-                const unsigned long long* src = xl + (int64_t)w * P * xstride + jj;
-                unsigned long long word = ld_relaxed_sys_u64(src);
-#pragma unroll 1
-                for (unsigned int i = 0; (word >> 32) != (want >> 32) && i < 2000000u; ++i) {
-                    __nanosleep(20);
-                    word = ld_relaxed_sys_u64(src);
-                }
-                got = got && (word >> 32) == (want >> 32);
-                s += __uint_as_float((unsigned int)word);
+            for (unsigned int it = 0; pending != 0u && it < 2000000u; ++it) {
+#pragma unroll
+                for (int w = 0; w < DDRL_MAX_RANKS; ++w)
+                    if ((pending >> w) & 1u) wd[w] = ld_relaxed_sys_u64(xl + (int64_t)w * P * xstride + jj);
+#pragma unroll
+                for (int w = 0; w < DDRL_MAX_RANKS; ++w)
+                    if (((pending >> w) & 1u) && (unsigned int)(wd[w] >> 32) == want32) pending &= ~(1u << w);
             }
+            got = got && pending == 0u;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < DDRL_MAX_RANKS; ++w)
+                if (w < W) s += __uint_as_float((unsigned int)wd[w]);      // rank order: identical bits on every rank
             slice_dst[jj] = s;
             gval = s;
         }
