@@ -68,12 +68,14 @@ struct TailStep {
     float b1p, b2p;      // beta1^t, beta2^t of THIS step (read from beta_pow at kernel entry, advanced by the caller)
     unsigned int seq;    // exchange sequence number of this step (world > 1): *t.seq at kernel entry + round - 1
     int nsteps;          // steps in this launch (the ticket advances the clocks by it)
+    unsigned int epoch;  // barrier_ws[4P+1] at kernel entry: steps executed by earlier launches (tags of the sq words)
 };
 __device__ __forceinline__ TailStep tail_single_step(const SgdTail& t, int p) {
     TailStep ts;
     ts.round = 1; ts.last = true; ts.nsteps = 1;
     ts.b1p = __ldcg(t.beta_pow + p * 2); ts.b2p = __ldcg(t.beta_pow + p * 2 + 1);
     ts.seq = (t.world > 1) ? *t.seq : 0u;
+    ts.epoch = __ldcg(t.barrier_ws + 4 * gridDim.y + 1);
     return ts;
 }
 // wait until every CTA of policy p has finished the Adam slice of step `round` (one thread per CTA calls this)
@@ -227,25 +229,44 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     if (lane == 0) red[warp] = ss;
     __syncthreads();
     ok = ok && red[40] != 0.f;
+    // "barrier B" without a counter: every CTA publishes {||g_slice||^2, epoch tag} as ONE 64-bit word and polls the G words
+    // of its policy until they carry this step's tag — no release drain of unrelated stores, no second read of the sums
+    // one word per 128-byte line: the pollers of a policy spread over G lines / L2 slices instead of hammering three
+    constexpr int SQ_STRIDE = 16;
+    unsigned long long* sq64 = reinterpret_cast<unsigned long long*>(t.sq_ws) + (int64_t)p * G * SQ_STRIDE;
+    const unsigned int btag = ts.epoch + (unsigned int)ts.round;
     if (tid == 0) {
         float s = 0.f;
         for (int w = 0; w < nw; ++w) s += red[w];
-        t.sq_ws[p * G + bx] = s;
-        red[39] = grid_group_barrier(t.barrier_ws + 4 * p + 1, (unsigned)(G * ts.round)) ? 1.f : 0.f;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(sq64 + (int64_t)bx * SQ_STRIDE),
+                     "l"(((unsigned long long)btag << 32) | (unsigned long long)__float_as_uint(s)) : "memory");
+    }
+    if (warp == 0) {
+        float s = 0.f;
+        bool got = true;
+        for (int i = lane; i < G; i += 32) {
+            unsigned long long w64 = 0ull;
+            bool hit = false;
+#pragma unroll 1
+            for (unsigned int it = 0; it < 8000000u; ++it) {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w64) : "l"(sq64 + (int64_t)i * SQ_STRIDE) : "memory");
+                if ((unsigned int)(w64 >> 32) == btag) { hit = true; break; }
+            }
+            got = got && hit;
+            s += __uint_as_float((unsigned int)w64);
+        }
+        s = warp_sum(s);
+        got = __all_sync(0xffffffffu, got);
+        if (lane == 0) {
+            const float norm = sqrtf(s);
+            red[32] = t.grad_clip > 0.f ? t.grad_clip * fminf(1.f / norm, 1.f / t.grad_clip) : 1.f;
+            red[39] = got ? 1.f : 0.f;
+            if (bx == 0 && t.gnorm_out) t.gnorm_out[p] = norm;
+        }
     }
     __syncthreads();
     ok = ok && red[39] != 0.f;
     TAIL_STAMP(42);
-    if (warp == 0) {
-        float s = 0.f;
-        for (int i = lane; i < G; i += 32) s += __ldcg(t.sq_ws + p * G + i);
-        s = warp_sum(s);
-        if (lane == 0) {
-            const float norm = sqrtf(s);
-            red[32] = t.grad_clip > 0.f ? t.grad_clip * fminf(1.f / norm, 1.f / t.grad_clip) : 1.f;
-            if (bx == 0 && t.gnorm_out) t.gnorm_out[p] = norm;
-        }
-    }
     __syncthreads();
     // ---- clip + TF1 Adam on the slice ---------------------------------------------------------------------------------
     const float scale = red[32];
@@ -307,6 +328,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
                     t.barrier_ws[4 * q + 1] = 0u;
                     t.barrier_ws[4 * q + 2] = 0u;
                 }
+                t.barrier_ws[4 * P + 1] = ts.epoch + (unsigned int)ts.nsteps;   // every CTA read it at kernel entry
                 if (t.step_ctr) *t.step_ctr += ts.nsteps;
                 if (t.seq) *t.seq = ts.seq + 1u;
                 t.barrier_ws[4 * P] = 0u;

@@ -275,7 +275,7 @@ class FCNetLearner(_LearnerBase):
             b["stat_part"] = torch.empty(P, G, K.NSTAT, dtype=torch.float64, device=self.device)
             b["step_stats"] = torch.zeros(steps, P, K.NSTAT, dtype=torch.float64, device=self.device)
             b["tail_bar"] = torch.zeros(4 * P + 4, dtype=torch.int32, device=self.device)
-            b["tail_sq"] = torch.zeros(P, G, dtype=torch.float32, device=self.device)
+            b["tail_sq"] = torch.zeros(P, G, 32, dtype=torch.float32, device=self.device)   # one 128-byte line per {sum, tag} word
             self._graph = None
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()

@@ -175,7 +175,8 @@ typedef struct {
  * Device pointers:
  *   theta, m, v [P][NP]; beta_pow [P][2]; grad [P][NP] (out: reduced gradient); gnorm_out [P] or NULL;
  *   fcnet_img / fcnet_tc_img or NULL; step_stats [steps][P][DDRL_NSTAT] or NULL; step_ctr;
- *   barrier_ws: 4*P + 4 zero-initialised uint32 (re-armed by the kernel); sq_ws: P * ctas_per_policy floats;
+ *   barrier_ws: 4*P + 4 zero-initialised uint32 (counters re-armed by the kernel; [4P+1] = steps executed so far);
+ *   sq_ws: P * ctas_per_policy zero-initialised 128-byte lines, first 64-bit word = {float ||g_slice||^2, uint32 step tag};
  *   status: device int or NULL, receives |= 64 when a bounded spin of the tail gave up (results then invalid);
  *   nsteps > 1: the launch runs that many consecutive optimizer steps (*step_ctr .. *step_ctr + nsteps - 1) as ONE
  *   persistent kernel — TMEM, barriers and the instruction stream stay warm, the launch gap disappears; the CTAs of a

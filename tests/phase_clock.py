@@ -15,8 +15,8 @@ NAMES = {0: "entry", 1: "setup done", 2: "inputs landed", 3: "x split+publish", 
          21: "publish", 22: "B1(1) ready", 23: "dz2(1)", 24: "publish", 25: "B3(0) ready", 26: "dz1(0)", 27: "publish",
          28: "B3(1) ready", 29: "dz1(1)", 30: "publish", 31: "B5 done", 32: "write-out", 33: "stats+dealloc", 34: "tail end", 35: "image issued", 36: "step/perm read", 37: "prefetch fn setup",
          38: "tmem alloc", 39: "inputs issued", 40: "tail: barrier A", 41: "tail: slice reduce", 42: "tail: sq + barrier B",
-         43: "tail: norm + Adam", 44: "tail: ticket"}
-ORDER = [0, 35, 36, 37, 38, 39] + list(range(1, 34)) + [40, 41, 42, 43, 44, 34]
+         43: "tail: norm + Adam", 44: "tail: ticket", 45: "write-out entry barrier"}
+ORDER = [0, 35, 36, 37, 38, 39] + list(range(1, 32)) + [45, 32, 33, 40, 41, 42, 43, 44, 34]
 
 
 def main():
