@@ -262,6 +262,78 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     auto epi_sync = [&]() { asm volatile("bar.sync 4, %0;" ::"n"(TC_NT) : "memory"); };   // the 16 epilogue warps only
     const uint32_t Xh = sbase + S.X[0], Xl = sbase + S.X[1];
 
+    // ---- write-out pieces: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
+    const float inv = a.hp.inv_global_mb;
+    const int m = 16 * q + lane;            // valid for lane < 16
+    const bool mine = lane < 16;
+    // gW2_b, gb2_b, gWh_b are final once B3(b) / B1 have completed, i.e. BEFORE the last B5: they are written while B5 runs.
+    // (Not with clusters: the staging buffer of the partial lives in H1, which B5 still reads.)
+    const bool early_out = cs == 1;
+    auto write_w2_heads = [&](int b) {
+        const float sgb = sgs[b];
+        const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
+        {   // gW2_b: this warp's 16 columns
+            uint32_t r0[8], r1[8];
+            umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq, r0);
+            umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8, r1);
+            umma::tmem_ld_wait();
+            if (mine) {
+                float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq);
+                dst[0] = make_float4(__uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
+                                     __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
+                dst[1] = make_float4(__uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
+                                     __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
+                dst[2] = make_float4(__uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
+                                     __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
+                dst[3] = make_float4(__uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
+                                     __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
+            }
+        }
+        if (cq == 2) {                                   // gb2_b: column of the constant-1 pad inside its 16-wide window
+            float v[8];
+            umma::tmem_ld8(tmem + tlane + T2_GB2 + 16 * b + (((D - 8 * ch0) >> 3) << 3), v);
+            const int jsel = (D - 8 * ch0) & 7;
+            const float g = jsel == 0 ? v[0] : jsel == 1 ? v[1] : jsel == 2 ? v[2] : jsel == 3 ? v[3] : jsel == 4 ? v[4]
+                          : jsel == 5 ? v[5] : jsel == 6 ? v[6] : v[7];
+            if (mine) gp[(b ? o.bv2 : o.b2) + m] = g * inv_gw1;
+        }
+        if (cq == 3) {                                   // gWh_b[k = m][o]
+            float w[16], w2[16];
+            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * (2 * b), w);
+            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * (2 * b + 1), w2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] += w2[j];
+            if (mine) {
+                if (b == 0) {
+#pragma unroll
+                    for (int oo = 0; oo < A2; ++oo) gp[o.Wo + m * A2 + oo] = w[oo] * inv_gwh;
+                } else {
+                    gp[o.Wvo + m] = w[0] * inv_gwh;
+                }
+            }
+        }
+    };
+    auto write_w1 = [&](int b) {
+        const float inv_gw1 = inv / (sgs[b] * TC_SX);
+#pragma unroll 1
+        for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
+            uint32_t r2[8], r3[8];
+            const uint32_t base0 = tmem + tlane + T2_GW1 + (gw1_split ? 32 * (2 * b) : 64 * b) + 8 * c8;
+            umma::tmem_ld8_nowait(base0, r2);
+            umma::tmem_ld8_nowait(gw1_split ? base0 + 32 : base0, r3);      // second product half (split) or the same again
+            umma::tmem_ld_wait();
+            if (mine) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int d = 8 * c8 + j;
+                    const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
+                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = g;
+                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = g;
+                }
+            }
+        }
+    };
+
     if (warp >= T2_MMA_WARP) {
         // ================= MMA-issue warps: one hand-off barrier per batch; lane 0 of each warp issues ITS share of the batch
         // (shares never split an accumulator) and commits to the branch's mbarrier (expected arrivals = T2_NMMA) ==========
@@ -512,6 +584,11 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
         first = false;
     }
+    if (early_out) {   // B5 of the last tile is in flight: gW2 / gb2 / gWh (complete since B3 / B1) leave meanwhile
+        umma::fence_after_sync();
+        write_w2_heads(0);
+        write_w2_heads(1);
+    }
     wait_b(0);
     wait_b(1);
     T2_STAMP(31);
@@ -532,76 +609,14 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     }
     }   // epilogue warps
 
-    // ---- write-out: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
-    const float inv = a.hp.inv_global_mb;
+    // ---- late write-out: what B5 produced (gW1, b1); everything else left while B5 was running (or leaves now: clusters) ----
     __syncthreads();
-    const int m = 16 * q + lane;            // valid for lane < 16
-    const bool mine = lane < 16;
     T2_STAMP(45);
     if (warp < T2_MMA_WARP) {
-#pragma unroll 1
-    for (int b = 0; b < 2; ++b) {
-        float v[8];
-        const float sgb = sgs[b];
-        const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
-        {   // gW2_b: this warp's 16 columns
-            uint32_t r0[8], r1[8];
-            umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq, r0);
-            umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8, r1);
-            umma::tmem_ld_wait();
-            if (mine) {
-                float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq);
-                dst[0] = make_float4(__uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
-                                     __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
-                dst[1] = make_float4(__uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
-                                     __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
-                dst[2] = make_float4(__uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
-                                     __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
-                dst[3] = make_float4(__uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
-                                     __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
-            }
-        }
-#pragma unroll 1
-        for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
-            uint32_t r2[8], r3[8];
-            const uint32_t base0 = tmem + tlane + T2_GW1 + (gw1_split ? 32 * (2 * b) : 64 * b) + 8 * c8;
-            umma::tmem_ld8_nowait(base0, r2);
-            umma::tmem_ld8_nowait(gw1_split ? base0 + 32 : base0, r3);      // second product half (split) or the same again
-            umma::tmem_ld_wait();
-            if (mine) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int d = 8 * c8 + j;
-                    const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
-                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = g;
-                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = g;
-                }
-            }
-        }
-        if (cq == 2) {                                   // gb2_b: column of the constant-1 pad inside its 16-wide window
-            umma::tmem_ld8(tmem + tlane + T2_GB2 + 16 * b + (((D - 8 * ch0) >> 3) << 3), v);
-            const int jsel = (D - 8 * ch0) & 7;
-            const float g = jsel == 0 ? v[0] : jsel == 1 ? v[1] : jsel == 2 ? v[2] : jsel == 3 ? v[3] : jsel == 4 ? v[4]
-                          : jsel == 5 ? v[5] : jsel == 6 ? v[6] : v[7];
-            if (mine) gp[(b ? o.bv2 : o.b2) + m] = g * inv_gw1;
-        }
-        if (cq == 3) {                                   // gWh_b[k = m][o]
-            float w[16], w2[16];
-            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * (2 * b), w);
-            umma::tmem_ld16(tmem + tlane + T2_GWH + 16 * (2 * b + 1), w2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] += w2[j];
-            if (mine) {
-                if (b == 0) {
-#pragma unroll
-                    for (int oo = 0; oo < A2; ++oo) gp[o.Wo + m * A2 + oo] = w[oo] * inv_gwh;
-                } else {
-                    gp[o.Wvo + m] = w[0] * inv_gwh;
-                }
-            }
-        }
+        if (!early_out) { write_w2_heads(0); write_w2_heads(1); }
+        write_w1(0);
+        write_w1(1);
     }
-    }   // write-out (epilogue warps)
     // head bias gradients and stats: add the four per-warp sums of each loss half (written before the write-out barrier)
     T2_STAMP(32);
     const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][16]
