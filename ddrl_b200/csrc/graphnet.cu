@@ -21,6 +21,15 @@
 
 namespace ddrl {
 
+// tanh = sign(x) * (1 - 2 / (exp(2|x|) + 1)) on the MUFU pipe (ex2 + rcp): absolute error <= 2.4e-7 over the whole range
+// (tanhf: 1.2e-7) at a third of the instructions — the hyper-network evaluates 1216 tanh per node.
+__device__ __forceinline__ float gn_tanh(float x) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.f));
+    return copysignf(fmaf(-2.f, r, 1.f), x);
+}
+
 constexpr int GH = DDRL_HIDDEN;          // 64
 constexpr int GF = DDRL_GN_FEATS;        // 19
 constexpr int GE = DDRL_GN_ENC_IN;       // 4
@@ -165,13 +174,13 @@ graphnet_kernel(const float* __restrict__ theta, const int32_t* __restrict__ nod
                     pre = fmaf(e1, We[k][1], pre);
                     pre = fmaf(e2, We[k][2], pre);
                     pre = fmaf(e3, We[k][3], pre);
-                    const float w = tanhf(pre);
+                    const float w = gn_tanh(pre);
                     wk[i][k] = w;
                     if (f < GF) part = fmaf(st[f], w, part);
                 }
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
-                xk[i] = tanhf(part);
+                xk[i] = gn_tanh(part);
                 if (fs == 0) sX[i][h] = xk[i];
             }
         }
@@ -195,7 +204,7 @@ graphnet_kernel(const float* __restrict__ theta, const int32_t* __restrict__ nod
         }
         pre += __shfl_xor_sync(0xffffffffu, pre, 1);
         pre += __shfl_xor_sync(0xffffffffu, pre, 2);
-        const float y = tanhf(pre);
+        const float y = gn_tanh(pre);
 
         if (!BWD) {
             // head: out[q] = sum_h' y[h'] Wout[h'][q] + b[q]; warp shuffle over the 8 h' of the warp, then 8 warps
