@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"], help="SGD-step kernel: tcgen05 split-fp16 or FP32 FMA")
     ap.add_argument("--tc-variant", type=int, default=0, choices=[0, 1, 2],
                     help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
+    ap.add_argument("--ctas", type=int, default=0, help="CTAs per policy of the SGD-step kernel (0 = the learner's choice)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
     ap.add_argument("--arch", default="FullyDecentral",
@@ -277,7 +278,8 @@ def main():
     import oracle.ddrl_oracle as O  # Glorot init values only (host RNG); no oracle compute in the timed path
     gen = torch.Generator().manual_seed(1234)
     theta0 = torch.stack([O.fcnet_init(D, 2 * A, gen) for _ in range(P)])
-    L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=not args.no_graph, mode=args.mode)
+    L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=not args.no_graph, mode=args.mode,
+                     ctas_per_policy=args.ctas or None)
 
     sets = [synth_rollout(P, T, C, D, A, envs, nb, E, 1234 + rank + 100 * s, device=dev) for s in range(args.sets)]
     host = synth_rollout(P, T, C, D, A, envs, nb, E, 999 + rank, pinned=True)

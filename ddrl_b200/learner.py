@@ -165,6 +165,13 @@ class FCNetLearner(_LearnerBase):
             raise DDRLError("sgd_minibatch_size smaller than the number of ranks")
         nb = max(1, R // MB)
         G = self.ctas_per_policy or max(1, min((MB + 15) // 16, self.sms // P))
+        if not self.ctas_per_policy and self.mode == "tc" and self.fuse_tail and self.sms // P >= 32:
+            # measured (profiles/README.md, CTA sweep): the fused tail (three barriers among the G CTAs of a policy, one
+            # parameter slice per CTA) is fastest around G = 32 whatever the minibatch size, as long as no CTA needs an
+            # extra 128-row tile for it; CTAs without rows still own a slice
+            tiles = lambda g: -(-((-(-MB // g) + 7) // 8 * 8) // 128)
+            if tiles(32) <= tiles(self.sms // P):
+                G = 32
         return MB, nb, G
 
     # ---- one optimizer step (3 kernels [+ NCCL]) -----------------------------------------------------------
