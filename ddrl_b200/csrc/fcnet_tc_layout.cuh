@@ -65,10 +65,11 @@ __host__ __device__ inline TcSmem tc_smem(int D, int A) {
 //   * the loss-gradient operand DL[b] sits in the W1 part of the weight image (W1 is only read by F1; a CTA with another
 //     tile to go reloads it from L2 behind the backward, and every step reloads the whole image anyway);
 //   * the fp32 staging of the observations (xraw) sits in H2[1] (free from B3(1) of one tile to tanh2(1) of the next).
-// That fits KX <= 48 (D <= 46) with A <= 4: every published architecture except the centralized one (A = 8).
+// That fits KX <= 48 (D <= 46) for A <= 4, and A = 8 for 31 <= D <= 46 (the centralized controller): every published
+// architecture.
 struct Tc2Smem {
-    int X[2], H1[2][2], H2[2][2], DL[2][2], xraw, pf, red, bar, total;
-    bool dl_in_w1;
+    int X[2], H1[2][2], H2[2][2], DL[2][2], xraw, pf, po, red, bar, total;
+    bool dl_in_w1, po_in_w1;
 };
 __host__ __device__ inline Tc2Smem tc2_smem(int D, int A) {
     const int KX = tc_kx(D);
@@ -87,8 +88,13 @@ __host__ __device__ inline Tc2Smem tc2_smem(int D, int A) {
     for (int b = 0; b < 2; ++b)
         for (int h = 0; h < 2; ++h) s.DL[b][h] = dl0 + (2 * b + h) * TC_ROWS * TC_NO * 2;
     s.xraw = s.H2[1][0];                            // 32 KB >= 128 rows x 63 floats
-    s.pf = p;    p += ((TC_ROWS * (3 * A + 4) * 4) + 15) & ~15;
-    s.red = p;   p += 8 * 16 * 8;    // [8 loss warps][16] doubles
+    // staged loss inputs: actions [128][A], old_logits [128][2A], 4 x [128] scalars.  For A = 8 the old logits (8 KB) move
+    // into the part of the W1 region that DL leaves free (KX >= 48) and are fetched after F1 has consumed W1.
+    s.po_in_w1 = A > 4 && s.dl_in_w1 && w1_bytes >= dl_bytes + TC_ROWS * 2 * A * 4;
+    s.pf = p;
+    if (s.po_in_w1) { s.po = I.W1[0][0] + dl_bytes; p += ((TC_ROWS * (A + 4) * 4) + 15) & ~15; }
+    else            { s.po = p + TC_ROWS * A * 4;   p += ((TC_ROWS * (3 * A + 4) * 4) + 15) & ~15; }
+    s.red = p;   p += 8 * 24 * 8;    // [8 loss warps][24] doubles: 5 stat sums, 16 head-bias gradient sums
     s.bar = p;   p += 64;            // 2 mbarriers, tmem slot, 2 gradient scales
     s.total = p;
     return s;

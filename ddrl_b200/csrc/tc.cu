@@ -644,7 +644,7 @@ static long long* g_tc_dbg_clock = nullptr;
 
 extern "C" int ddrl_tc_pingpong_eligible(int D, int A) {
     if (D < 1 || D > DDRL_MAX_OBS - 1 || !(A == 1 || A == 2 || A == 4 || A == 8)) return 0;
-    return (g_tc_variant != 1 && A <= 4 && tc2_eligible(D, A)) ? 1 : 0;
+    return (g_tc_variant != 1 && tc2_eligible(D, A)) ? 1 : 0;
 }
 
 extern "C" int ddrl_tc_set_debug_clock(void* device_int64x64) {
@@ -696,15 +696,15 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
         a.tail = *tail;
         const bool pp = g_tc_variant == 2 || (g_tc_variant == 0 && tc2_eligible(D, A));
         DDRL_REQUIRE(tail->nsteps <= 1 || pp, DDRL_E_UNSUPPORTED_SHAPE,
-                     "ppo_train_step_tc: nsteps > 1 needs the ping-pong kernel (D <= 46, A <= 4)");
+                     "ppo_train_step_tc: nsteps > 1 needs the ping-pong kernel (D <= 46; A = 8: D >= 31)");
     }
     const size_t smem = (size_t)tc_smem(D, A).total;
     DDRL_REQUIRE(smem <= 227 * 1024, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step_tc: shared memory %zu > 227 KB", smem);
     int rc;
     const bool pingpong = g_tc_variant == 2 || (g_tc_variant == 0 && tc2_eligible(D, A));
     if (pingpong) {
-        DDRL_REQUIRE(tc2_eligible(D, A) && A <= 4, DDRL_E_UNSUPPORTED_SHAPE,
-                     "ppo_train_step_tc: ping-pong variant needs D <= 46 and A <= 4 (D=%d, A=%d)", D, A);
+        DDRL_REQUIRE(tc2_eligible(D, A), DDRL_E_UNSUPPORTED_SHAPE,
+                     "ppo_train_step_tc: ping-pong variant needs D <= 46 (A = 8: 31 <= D <= 46) (D=%d, A=%d)", D, A);
         rc = launch_tc2(a, P, ctas_per_policy, (cudaStream_t)stream);
         if (rc != DDRL_OK) return rc;
         DDRL_CHECK_LAUNCH("ppo_train_step_tc");

@@ -11,8 +11,8 @@
 // hidden; each branch has its own accumulator columns and its own mbarrier.  The two PPO-loss halves (policy part on
 // warps 0-3, value part on warps 4-7) run concurrently.  MMAs are issued by lane 0 of the LAST warp, which carries no
 // loss work.  Cost: H1/H2 of both branches live in shared memory (128 KB); DL and the observation staging reuse space that
-// is dead at the time (fcnet_tc_layout.cuh), which fits D <= 46 with A <= 4 (tc2_eligible); the centralized controller
-// (A = 8) keeps the branch-sequential kernel.
+// is dead at the time (fcnet_tc_layout.cuh), which fits D <= 46 (tc2_eligible; A = 8 needs D >= 31, i.e. the centralized
+// controller); other shapes keep the branch-sequential kernel.
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -179,12 +179,14 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     auto prefetch_loss = [&](int64_t r0, int n) {
         const int64_t g0 = (int64_t)p * a.R + r0;
         float* pa = pf;
-        float* po = pa + TC_ROWS * A;
-        float* ps = po + TC_ROWS * A2;
+        float* po = reinterpret_cast<float*>(sm + S.po);
+        float* ps = pa + TC_ROWS * A + (S.po_in_w1 ? 0 : TC_ROWS * A2);
 #pragma unroll 1
         for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, a.actions + g0 * A + i);
+        if (!S.po_in_w1) {
 #pragma unroll 1
-        for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+            for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+        }
 #pragma unroll 1
         for (int i = tid; i < n; i += TC_NT) {
             tc_cp4(ps + i, a.old_logp + g0 + i);
@@ -194,6 +196,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
     };
 
+    auto prefetch_po = [&](int64_t r0, int n) {   // old logits into the W1 region: only once F1 has consumed W1 (po_in_w1)
+        const int64_t g0 = (int64_t)p * a.R + r0;
+        float* po = reinterpret_cast<float*>(sm + S.po);
+#pragma unroll 1
+        for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
     bool prefetched = false;   // the first tile's inputs of this step were already requested behind the previous step's tail
 
 #pragma unroll 1
@@ -467,6 +476,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             publish();
             T2_STAMP(6 + 3 * b);
         }
+        if (S.po_in_w1) prefetch_po(row0, nrows);     // both F1 are complete: W1 is dead, its spare part takes the old logits
         // ---- tanh epilogue 2 -> heads: Hout_b[128][16] = H2_b * WoT_b^T ------------------------------------------------
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
@@ -475,6 +485,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b2c + b * 64 + 16 * cq, 1.f / (TC_SH * TC_SW),
                         sm + S.H2[b][0], sm + S.H2[b][1], row, cq);
             T2_STAMP(11 + 3 * b);
+            if (S.po_in_w1 && b == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // old logits landed (barrier follows)
             publish();
             T2_STAMP(12 + 3 * b);
         }
@@ -493,8 +504,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             for (int i = 0; i < 16; ++i) dl[i] = 0.f;
             if (row < nrows) {
                 const float* pa = pf;
-                const float* po = pa + TC_ROWS * A;
-                const float* ps = po + TC_ROWS * A2;
+                const float* po = reinterpret_cast<const float*>(sm + S.po);
+                const float* ps = pa + TC_ROWS * A + (S.po_in_w1 ? 0 : TC_ROWS * A2);
                 if (b == 0) {
                     float lg[A2];
 #pragma unroll
@@ -595,16 +606,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     T2_GSTAMP(1);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     if (cq < 2) {   // loss warps: head-bias gradients and loss statistics -> per-warp sums (read after the write-out barrier)
-        double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][16]
+        double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][24]
 #pragma unroll
         for (int i = 0; i < A2; ++i) {
             const float sx = warp_sum(gbh[i]);
-            if (lane == 0 && 8 + i < 16) redd[warp * 16 + 8 + i] = (double)sx;
+            if (lane == 0) redd[warp * 24 + 8 + i] = (double)sx;
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const double sx = warp_sum(st[i]);
-            if (lane == 0) redd[warp * 16 + i] = sx;
+            if (lane == 0) redd[warp * 24 + i] = sx;
         }
     }
     }   // epilogue warps
@@ -619,8 +630,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     }
     // head bias gradients and stats: add the four per-warp sums of each loss half (written before the write-out barrier)
     T2_STAMP(32);
-    const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][16]
-    auto sum4 = [&](int w0, int i) { return (redd[w0 * 16 + i] + redd[(w0 + 1) * 16 + i]) + (redd[(w0 + 2) * 16 + i] + redd[(w0 + 3) * 16 + i]); };
+    const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][24]
+    auto sum4 = [&](int w0, int i) { return (redd[w0 * 24 + i] + redd[(w0 + 1) * 24 + i]) + (redd[(w0 + 2) * 24 + i] + redd[(w0 + 3) * 24 + i]); };
     if (tid < A2) gp[o.bo + tid] = (float)sum4(0, 8 + tid) * inv;
     if (tid == A2) gp[o.bvo] = (float)sum4(4, 8) * inv;
     if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) gp[o.NP + (tid - A2 - 1)] = 0.f;   // padding floats of the partial
@@ -752,7 +763,8 @@ int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
         case 1: return launch_tc2_t<1>(a, P, G, smem, st, &g_tc2_last_cluster);
         case 2: return launch_tc2_t<2>(a, P, G, smem, st, &g_tc2_last_cluster);
         case 4: return launch_tc2_t<4>(a, P, G, smem, st, &g_tc2_last_cluster);
-        default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4}"); return DDRL_E_UNSUPPORTED_SHAPE;
+        case 8: return launch_tc2_t<8>(a, P, G, smem, st, &g_tc2_last_cluster);
+        default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4,8}"); return DDRL_E_UNSUPPORTED_SHAPE;
     }
 }
 
