@@ -689,6 +689,7 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     a.mb_perm = mb_perm; a.perm_stride = perm_stride; a.step_ctr = step_ctr; a.kl_coeff = kl_coeff; a.hp = *hyper;
     a.grad_part = grad_part; a.stat_part = stat_part; a.status = status;
     a.dbg_clock = g_tc_dbg_clock;
+    a.norm = nullptr; a.clip = 0.f; a.obs_out = a.logits_out = a.value_out = a.action_out = a.logp_out = nullptr; a.eps = nullptr;
     a.tail = SgdTail{};
     if (tail) {
         const int rc = sgd_tail_check(tail, ctas_per_policy * P, "ppo_train_step_tc");
@@ -720,3 +721,29 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     DDRL_CHECK_LAUNCH("ppo_train_step_tc");
     return DDRL_OK;
 }
+
+extern "C" int ddrl_fcnet_forward_tc(const void* tc_img_p, const float* obs, const double* norm, float clip, int P, int64_t R,
+                                     int D, int A, float* obs_out, float* logits, float* value, const float* eps, float* action,
+                                     float* logp, int* status, void* stream) {
+    DDRL_REQUIRE(tc_img_p && obs && P >= 1 && R >= 0, DDRL_E_BADARG, "fcnet_forward_tc: null pointer or bad P/R");
+    DDRL_REQUIRE(!eps || (action && logp), DDRL_E_BADARG, "fcnet_forward_tc: eps given without action / logp outputs");
+    DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS - 1 && (A == 1 || A == 2 || A == 4 || A == 8) && tc2_eligible(D, A),
+                 DDRL_E_UNSUPPORTED_SHAPE, "fcnet_forward_tc: unsupported D=%d A=%d (D <= 46; A = 8: D >= 31)", D, A);
+    DDRL_REQUIRE(R <= 0x7fffffff, DDRL_E_UNSUPPORTED_SHAPE, "fcnet_forward_tc: R must fit 31 bits");
+    if (R == 0) return DDRL_OK;
+    TcTrainArgs a = {};
+    a.img = (const unsigned char*)tc_img_p; a.obs = obs; a.R = R; a.D = D; a.A = A; a.MB = (int)R;
+    a.hp = ddrl_ppo_hyper{0.f, 0.f, 0.f, 0.f, 1.f};
+    a.status = status; a.dbg_clock = nullptr; a.tail = SgdTail{};
+    a.norm = norm; a.clip = clip; a.obs_out = obs_out; a.logits_out = logits; a.value_out = value; a.eps = eps;
+    a.action_out = action; a.logp_out = logp;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>((R + TC_ROWS - 1) / TC_ROWS, std::max(1, sms / P)));
+    const int rc = launch_tc2_forward(a, P, G, (cudaStream_t)stream);
+    if (rc != DDRL_OK) return rc;
+    DDRL_CHECK_LAUNCH("fcnet_forward_tc");
+    return DDRL_OK;
+}
+

@@ -114,7 +114,9 @@ __device__ __forceinline__ long long t2_gtime() {
         if (a.dbg_clock && threadIdx.x == 0) a.dbg_clock[64 + 8 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = t2_gtime(); \
     } while (0)
 
-template <int A>
+// FWD = true: forward-only (inference) mode — the same F1 / tanh / F2 / tanh / heads pipeline over ALL rows of each policy
+// (a.MB = a.R), filter normalisation in the X split, DiagGaussian sample + logp in place of the loss, nothing after it.
+template <int A, bool FWD>
 __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrainArgs a) {
     constexpr int A2 = 2 * A;
     T2_STAMP(0);
@@ -181,8 +183,12 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         float* pa = pf;
         float* po = reinterpret_cast<float*>(sm + S.po);
         float* ps = pa + TC_ROWS * A + (S.po_in_w1 ? 0 : TC_ROWS * A2);
+        const float* first_in = FWD ? a.eps : a.actions;      // inference: the only per-row input besides x is the noise
+        if (first_in) {
 #pragma unroll 1
-        for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, a.actions + g0 * A + i);
+            for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, first_in + g0 * A + i);
+        }
+        if (FWD) return;
         if (!S.po_in_w1) {
 #pragma unroll 1
             for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
@@ -384,6 +390,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
                 }
                 __syncwarp();
             }
+            if (FWD) continue;      // inference: nothing after the heads
             mma_turn();      // loss done.  dz2-pre: Dacc_b = DL_b * WoT_b (warp b, first);  gWh_b (+)= H2_b^T DL_b by product
             if (lane == 0) {
                 const int b = mw & 1;
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 #pragma unroll 1
     for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
         const int nrows = (int)min((int64_t)TC_ROWS, cr1 - row0);
-        if (!first) { wait_b(0); wait_b(1); }       // previous tile's B5 still reads X and dZ1
+        if (!FWD && !first) { wait_b(0); wait_b(1); }       // previous tile's B5 still reads X and dZ1
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         epi_sync();
         T2_STAMP(2);
@@ -454,7 +461,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int d = c8 * 8 + e;
-                    v[e] = (r < nrows) ? (d < D ? xraw[r * D + d] : (d == D ? 1.f : 0.f)) : 0.f;
+                    float x = (r < nrows && d < D) ? xraw[r * D + d] : 0.f;
+                    if (FWD && r < nrows && d < D) {      // MeanStdFilter normalise (float64 like the FP32 kernel), clip, obs_out
+                        if (a.norm) {
+                            const double* nm = a.norm + (int64_t)p * 2 * D;
+                            x = (float)(((double)x - __ldg(nm + d)) * __ldg(nm + D + d));
+                            if (a.clip > 0.f) x = fminf(fmaxf(x, -a.clip), a.clip);
+                        }
+                        if (a.obs_out) a.obs_out[((int64_t)p * a.R + row0 + r) * D + d] = x;
+                    }
+                    v[e] = (r < nrows) ? (d < D ? x : (d == D ? 1.f : 0.f)) : 0.f;
                 }
                 uint4 hi, lo;
                 ovf |= tc_split8(v, TC_SX, hi, lo) ? 2 : 0;
@@ -476,7 +492,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             publish();
             T2_STAMP(6 + 3 * b);
         }
-        if (S.po_in_w1) prefetch_po(row0, nrows);     // both F1 are complete: W1 is dead, its spare part takes the old logits
+        if (!FWD && S.po_in_w1) prefetch_po(row0, nrows);     // both F1 are complete: W1 is dead, its spare part takes the old logits
         // ---- tanh epilogue 2 -> heads: Hout_b[128][16] = H2_b * WoT_b^T ------------------------------------------------
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b2c + b * 64 + 16 * cq, 1.f / (TC_SH * TC_SW),
                         sm + S.H2[b][0], sm + S.H2[b][1], row, cq);
             T2_STAMP(11 + 3 * b);
-            if (S.po_in_w1 && b == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // old logits landed (barrier follows)
+            if (!FWD && S.po_in_w1 && b == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // old logits landed (barrier follows)
             publish();
             T2_STAMP(12 + 3 * b);
         }
@@ -493,6 +509,47 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         wait_b(0);
         wait_b(1);
         T2_STAMP(16);
+        if (FWD) {      // inference epilogue: logits, value, DiagGaussian sample + logp (RLlib tf_action_dist.DiagGaussian)
+            float out[16];
+            if (cq < 2) umma::tmem_ld16(tmem + tlane + T2_HOUT + 16 * cq, out);    // .sync.aligned: whole warps
+            if (cq < 2 && row < nrows) {
+                const int64_t gr = (int64_t)p * a.R + row0 + row;
+                if (cq == 0) {
+                    float lg[A2];
+#pragma unroll
+                    for (int oo = 0; oo < A2; ++oo) lg[oo] = fmaf(out[oo], 1.f / (TC_SH * TC_SW), sbo[oo]);
+                    if (a.logits_out) {
+#pragma unroll
+                        for (int oo = 0; oo < A2; ++oo) a.logits_out[gr * A2 + oo] = lg[oo];
+                    }
+                    if (a.eps) {
+                        float sz2 = 0.f, sls = 0.f;
+#pragma unroll
+                        for (int i = 0; i < A; ++i) {
+                            const float mu = lg[i], ls = lg[A + i];
+                            const float sd = expf(ls);
+                            const float act = mu + sd * pf[row * A + i];
+                            const float z = (act - mu) / sd;
+                            sz2 = fmaf(z, z, sz2);
+                            sls += ls;
+                            a.action_out[gr * A + i] = act;
+                        }
+                        a.logp_out[gr] = -0.5f * sz2 - 0.5f * kLog2Pi * (float)A - sls;
+                    }
+                } else if (a.value_out) {
+                    a.value_out[gr] = fmaf(out[0], 1.f / (TC_SH * TC_SW), sbvo[0]);
+                }
+            }
+            epi_sync();      // every reader of this tile's staged noise is done; H2[1] (heads consumed) takes the next x
+            const int64_t nxt = row0 + TC_ROWS;
+            if (nxt < cr1) {
+                const int nn = (int)min((int64_t)TC_ROWS, cr1 - nxt);
+                prefetch_x(nxt, nn);
+                prefetch_loss(nxt, nn);
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+            continue;
+        }
         if (cq < 2) {
             const int b = cq;
             float out[16], dl[16];
@@ -595,6 +652,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
         first = false;
     }
+    if (!FWD) {
     if (early_out) {   // B5 of the last tile is in flight: gW2 / gb2 / gWh (complete since B3 / B1) leave meanwhile
         umma::fence_after_sync();
         write_w2_heads(0);
@@ -618,7 +676,9 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             if (lane == 0) redd[warp * 24 + i] = sx;
         }
     }
+    }   // training only
     }   // epilogue warps
+    if (FWD) break;      // inference: no partial gradient, no statistics, no tail
 
     // ---- late write-out: what B5 produced (gW1, b1); everything else left while B5 was running (or leaves now: clusters) ----
     __syncthreads();
@@ -704,10 +764,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 static int g_tc2_cluster = 0;    // 0 = off (default: measured slower), -1 = automatic (largest of 16, 8, 4, 2 that
                                  // divides G and is co-resident), else the forced size
 
-template <int A>
+template <int A, bool FWD>
 static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st, int* used_cluster) {
     static bool attr = false;
-    auto kern = fcnet_train_tc2_kernel<A>;
+    auto kern = fcnet_train_tc2_kernel<A, FWD>;
     if (!attr) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
@@ -760,11 +820,23 @@ static int g_tc2_last_cluster = 0;
 int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
     const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
     switch (a.A) {
-        case 1: return launch_tc2_t<1>(a, P, G, smem, st, &g_tc2_last_cluster);
-        case 2: return launch_tc2_t<2>(a, P, G, smem, st, &g_tc2_last_cluster);
-        case 4: return launch_tc2_t<4>(a, P, G, smem, st, &g_tc2_last_cluster);
-        case 8: return launch_tc2_t<8>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 1: return launch_tc2_t<1, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 2: return launch_tc2_t<2, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 4: return launch_tc2_t<4, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 8: return launch_tc2_t<8, false>(a, P, G, smem, st, &g_tc2_last_cluster);
         default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4,8}"); return DDRL_E_UNSUPPORTED_SHAPE;
+    }
+}
+
+int launch_tc2_forward(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
+    const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
+    int dummy = 0;
+    switch (a.A) {
+        case 1: return launch_tc2_t<1, true>(a, P, G, smem, st, &dummy);
+        case 2: return launch_tc2_t<2, true>(a, P, G, smem, st, &dummy);
+        case 4: return launch_tc2_t<4, true>(a, P, G, smem, st, &dummy);
+        case 8: return launch_tc2_t<8, true>(a, P, G, smem, st, &dummy);
+        default: set_error("fcnet_forward_tc: A must be 1, 2, 4 or 8"); return DDRL_E_UNSUPPORTED_SHAPE;
     }
 }
 

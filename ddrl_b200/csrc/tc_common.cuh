@@ -26,10 +26,16 @@ struct TcTrainArgs {
     int* status;
     long long* dbg_clock;   // optional: CTA (0, 0) thread 0 stores clock64() at phase boundaries (ddrl_tc_set_debug_clock)
     SgdTail tail;
+    // forward-only mode of the ping-pong kernel (inference: ddrl_fcnet_forward_tc): filter table, outputs, sampling noise
+    const double* norm;     // [P][2][D] mean, 1/(std + 1e-8) or nullptr
+    float clip;
+    float *obs_out, *logits_out, *value_out, *action_out, *logp_out;
+    const float* eps;
 };
 
 // ping-pong variant (tc2.cu); A in {1,2,4}, tc2_eligible(D, A)
 int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st);
+int launch_tc2_forward(const TcTrainArgs& a, int P, int G, cudaStream_t st);
 
 // Power-of-two operand scales (see header comment).  What matters is the absolute error relative to the tensor's
 // scale: entries too small for a normal lo half lose at most 2^-25/scale, negligible next to the entries that dominate.

@@ -393,6 +393,32 @@ def fcnet_tc_pack(theta: torch.Tensor, D: int, A: int, img: Optional[torch.Tenso
     return img
 
 
+def fcnet_forward_tc(tc_img, obs, A: int, norm=None, clip: float = 0.0, eps=None, out: Optional[dict] = None,
+                     status: Optional[torch.Tensor] = None) -> dict:
+    """Inference on the tensor cores (ddrl_fcnet_forward_tc): obs [P,R,D] f32 + tensor-core weight image -> dict(logits,
+    value[, obs_out][, action, logp]).  ``out`` may carry preallocated tensors; a None entry skips that output."""
+    P, R, D = obs.shape
+    f32 = torch.float32
+    dev = obs.device
+    o = dict(out) if out is not None else {}
+    if out is None:
+        o["logits"] = torch.empty(P, R, 2 * A, dtype=f32, device=dev)
+        o["value"] = torch.empty(P, R, dtype=f32, device=dev)
+        o["obs_out"] = torch.empty(P, R, D, dtype=f32, device=dev) if norm is not None else None
+    if eps is not None:
+        o.setdefault("action", torch.empty(P, R, A, dtype=f32, device=dev))
+        o.setdefault("logp", torch.empty(P, R, dtype=f32, device=dev))
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().ddrl_fcnet_forward_tc(
+        _p(tc_img, torch.uint8, "tc_img"), _p(obs, f32, "obs"), _p(norm, torch.float64, "norm"), float(clip or 0.0), P, R, D, A,
+        _p(o.get("obs_out"), f32, "obs_out"), _p(o.get("logits"), f32, "logits"), _p(o.get("value"), f32, "value"),
+        _p(eps, f32, "eps"), _p(o.get("action"), f32, "action"), _p(o.get("logp"), f32, "logp"),
+        _p(status, torch.int32, "status"), _stream()), "fcnet_forward_tc")
+    o["status"] = status
+    return o
+
+
 def tc_set_variant(variant: int) -> None:
     """0 = automatic (ping-pong kernel when D <= 30 and A <= 4), 1 = branch-sequential kernel, 2 = ping-pong kernel."""
     _lib.check(_lib.load().ddrl_tc_set_variant(int(variant)), "tc_set_variant")

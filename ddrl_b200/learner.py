@@ -106,7 +106,7 @@ class FCNetLearner(_LearnerBase):
 
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
                  use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True,
-                 persistent: bool = True):
+                 persistent: bool = True, tc_forward: bool = True):
         """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
                  "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes."""
         super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
@@ -115,6 +115,7 @@ class FCNetLearner(_LearnerBase):
         self.mode = mode
         self.fuse_tail = fuse_tail
         self.persistent = persistent      # one persistent launch per epoch where the kernel supports it
+        self.tc_forward = tc_forward and mode == "tc"   # inference forward on the tensor cores as well
         self.D, self.A = D, A
         dev = self.device
         self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -238,6 +239,7 @@ class FCNetLearner(_LearnerBase):
         R = T * Cc
         b = self._alloc(T, Cc)
         obs_flat = raw_obs.reshape(P, R, D)
+        self.tc_status.zero_()
         K.fcnet_pack(self.theta, D, A, self.img)
         if self.tc_img is not None:
             K.fcnet_tc_pack(self.theta, D, A, self.tc_img)
@@ -248,12 +250,20 @@ class FCNetLearner(_LearnerBase):
                 K.filter_merge(allp, R * self.world, self.filt_n, self.filt_M, self.filt_S, self.norm)
             else:
                 K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])
-        K.fcnet_forward(self.theta, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
-                        out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
-                             "logp": b["logp"]}, img=self.img)
-        # (ii) bootstrap + GAE + standardise -----------------------------------------------------------
-        K.fcnet_forward(self.theta, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
-                        out={"logits": None, "value": b["vboot"], "obs_out": None}, img=self.img)
+        if self.tc_forward and self.tc_img is not None and K.tc_pingpong_eligible(D, A):
+            # inference on the tensor cores (same pipeline as the training forward, ~3e-6 relative)
+            K.fcnet_forward_tc(self.tc_img, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
+                               out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
+                                    "logp": b["logp"]}, status=self.tc_status)
+            K.fcnet_forward_tc(self.tc_img, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
+                               out={"logits": None, "value": b["vboot"], "obs_out": None}, status=self.tc_status)
+        else:
+            K.fcnet_forward(self.theta, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
+                            out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
+                                 "logp": b["logp"]}, img=self.img)
+            # (ii) bootstrap + GAE + standardise -----------------------------------------------------------
+            K.fcnet_forward(self.theta, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
+                            out={"logits": None, "value": b["vboot"], "obs_out": None}, img=self.img)
         K.gae(rewards, b["value"].view(P, T, Cc), dones, b["vboot"], cols_per_env, cfg.gamma, cfg.lambda_,
               b["adv"].view(P, T, Cc), b["vtarg"].view(P, T, Cc), b["moments"], b["gae_ws"])
         if self.world > 1:
@@ -286,7 +296,6 @@ class FCNetLearner(_LearnerBase):
             self._graph = None
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()
-        self.tc_status.zero_()
         hyper = self._hyper(MB * self.world)
         if self.world > 1 and self.fuse_tail and G * P <= self.sms:
             self._peer_exchange(G)      # allocate / map the peer buffers outside any graph capture

@@ -317,6 +317,13 @@ int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupli
  * completion wait timed out; 64 = a fused-tail barrier timed out; 2/4/8/16/32 = fp16 overflow (clamped) while splitting x / activations / dl / dz2 / dz1 —
  * the result is then unreliable and the step should be redone with ddrl_ppo_train_step. */
 int ddrl_fcnet_tc_image_bytes(int D, int A);
+/* Inference on the tensor cores: same contract as ddrl_fcnet_forward (filter normalise prologue, logits / value,
+ * DiagGaussian sample + logp epilogue) with the GEMMs on tcgen05 (fp16 hi/lo split, ~3e-6 relative); weights from the
+ * tensor-core image.  Shapes the ping-pong kernel covers (D <= 46; A = 8: D >= 31).  Any of obs_out / logits / value /
+ * eps (+ action, logp) may be NULL. */
+int ddrl_fcnet_forward_tc(const void* tc_img, const float* obs, const double* norm, float clip, int P, int64_t R,
+                          int D, int A, float* obs_out, float* logits, float* value, const float* eps,
+                          float* action, float* logp, int* status, void* stream);
 /* Two schedules of the same arithmetic exist: 1 = branch-sequential (any D <= 63), 2 = "ping-pong" (both branches
  * resident, the tensor core runs one branch while the CTA runs the other's epilogue; D <= 46, A <= 4).
  * 0 (default) picks ping-pong whenever the shape allows it.  Process-wide; meant for tests and A/B timing. */

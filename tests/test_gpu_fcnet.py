@@ -384,3 +384,38 @@ def test_packed_weight_image_path_equals_flat_path():
         sync = torch.zeros(1, dtype=torch.int32, device="cuda")
         K.clip_adam(th, m, v, bp, g, cfg.lr, cfg.beta1, cfg.beta2, cfg.adam_eps, cfg.grad_clip, sync, img=img, img_D=D, img_A=A)
         assert torch.equal(img, K.fcnet_pack(th, D, A))
+
+
+@pytest.mark.parametrize("arch", ["FullyDecentral", "Local", "TwoSides", "Centralized", "SingleDiagonal", "FullyDecentral_TVel"])
+@pytest.mark.parametrize("R", [1, 100, 128, 700])
+def test_tensor_core_inference_forward_matches_oracle(arch, R):
+    """ddrl_fcnet_forward_tc: filter normalise -> logits / value -> DiagGaussian sample + logp, on checkpoint weights with
+    the checkpoint's filter; 1e-5 of the tensor's scale vs the float64 oracle; obs_out identical to the FP32 kernel's."""
+    from ddrl_b200 import kernels as K
+    O = _oracle()
+    theta, filt, D, A = ckpt_theta(arch)
+    P = theta.shape[0]
+    rng = np.random.default_rng(R)
+    raw = synth_obs(filt, R, 7)
+    eps = rng.standard_normal((P, R, A)).astype(np.float32)
+    norm = np.stack([np.stack([M, 1.0 / (np.sqrt(S / (n - 1)) + 1e-8)]) for n, M, S in filt])
+    th = _dev(theta, "cuda")
+    img = K.fcnet_tc_pack(th, D, A)
+    out = K.fcnet_forward_tc(img, _dev(raw, "cuda"), A, norm=_dev(norm, "cuda"), eps=_dev(eps, "cuda"))
+    ref32 = K.fcnet_forward(th, _dev(raw, "cuda"), A, norm=_dev(norm, "cuda"), eps=_dev(eps, "cuda"), want_obs_out=True)
+    torch.cuda.synchronize()
+    assert int(out["status"]) == 0
+    assert torch.equal(out["obs_out"], ref32["obs_out"])
+    for p in range(P):
+        x = ((raw[p].astype(np.float64) - norm[p, 0]) * norm[p, 1]).astype(np.float32)
+        lg, v = O.fcnet_forward(t64(theta[p]), t64(x), 2 * A)
+        act = O.dg_sample(lg, t64(eps[p]))
+        lp = O.dg_logp(lg, act)
+        assert scaled_err(out["logits"][p].cpu().numpy(), lg.numpy()) < TOL
+        assert scaled_err(out["value"][p].cpu().numpy(), v.numpy()) < TOL
+        assert scaled_err(out["action"][p].cpu().numpy(), act.numpy()) < TOL
+        assert scaled_err(out["logp"][p].cpu().numpy(), lp.numpy()) < TOL
+    # value-only call (bootstrap): no eps, no logits
+    vb = torch.empty(P, R, dtype=torch.float32, device="cuda")
+    K.fcnet_forward_tc(img, _dev(raw, "cuda"), A, norm=_dev(norm, "cuda"), out={"logits": None, "value": vb, "obs_out": None})
+    assert torch.equal(vb, out["value"])
