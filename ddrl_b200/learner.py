@@ -136,6 +136,8 @@ class FCNetLearner(_LearnerBase):
         self._graph_key = None
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self._peers = None
+        self._prep_graphs = {}
+        self._prep_warm = False
 
     # ---- buffers ------------------------------------------------------------------------------------
     def _alloc(self, T: int, Cc: int):
@@ -223,6 +225,76 @@ class FCNetLearner(_LearnerBase):
         return (self.persistent and self.mode == "tc" and self.fuse_tail and G * self.P <= self.sms
                 and K.tc_pingpong_eligible(self.D, self.A))
 
+    # ---- everything before the SGD epochs: filter, inference forward, bootstrap, GAE, standardise, shuffle ----------------
+    def _prepare(self, b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc):
+        P, R, D = obs_flat.shape
+        cfg, A = self.cfg, self.A
+        self.tc_status.zero_()
+        K.fcnet_pack(self.theta, D, A, self.img)
+        if self.tc_img is not None:
+            K.fcnet_tc_pack(self.theta, D, A, self.tc_img)
+        # (i) filter + forward + sample ------------------------------------------------------------------
+        if update_filter:
+            if self.world > 1:
+                allp = gather_parts_rank_order(K.filter_partial(obs_flat), self.dist, self.world)
+                K.filter_merge(allp, R * self.world, self.filt_n, self.filt_M, self.filt_S, self.norm)
+            else:
+                K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])
+        if self.tc_forward and self.tc_img is not None and K.tc_pingpong_eligible(D, A):
+            # inference on the tensor cores (same pipeline as the training forward, ~3e-6 relative)
+            K.fcnet_forward_tc(self.tc_img, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps_flat,
+                               out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
+                                    "logp": b["logp"]}, status=self.tc_status)
+            K.fcnet_forward_tc(self.tc_img, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
+                               out={"logits": None, "value": b["vboot"], "obs_out": None}, status=self.tc_status)
+        else:
+            K.fcnet_forward(self.theta, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps_flat,
+                            out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
+                                 "logp": b["logp"]}, img=self.img)
+            K.fcnet_forward(self.theta, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
+                            out={"logits": None, "value": b["vboot"], "obs_out": None}, img=self.img)
+        # (ii) bootstrap + GAE + standardise -----------------------------------------------------------
+        K.gae(rewards, b["value"].view(P, T, Cc), dones, b["vboot"], cols_per_env, cfg.gamma, cfg.lambda_,
+              b["adv"].view(P, T, Cc), b["vtarg"].view(P, T, Cc), b["moments"], b["gae_ws"])
+        if self.world > 1:
+            self.dist.all_reduce(b["moments"])
+        K.adv_standardize(b["adv"], b["moments"])
+        # shuffle (SampleBatch.shuffle) -----------------------------------------------------------------
+        if shuffle is not None:
+            for nme in ("obs", "act", "logits", "logp", "value", "adv", "vtarg"):
+                K.gather_rows(b[nme], shuffle, b[nme + "_s"])
+
+    def _prepare_cached(self, b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc):
+        """Single GPU: the ~20 short launches of the preparation phase are captured once per set of input buffers and
+        replayed (the kernels only see pointers; graphs are keyed by the input addresses, at most 8 are kept)."""
+        args = (b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc)
+        if not self.use_graph or self.world > 1 or self._prep_graphs is None or not self._prep_warm:
+            self._prep_warm = True           # first call runs eagerly (one-time function attributes, lazy allocations)
+            return self._prepare(*args)
+        if b.get("filt_ws") is None:
+            from . import _lib
+            nbytes = int(_lib.load().ddrl_filter_ws_bytes(obs_flat.shape[0], obs_flat.shape[1], obs_flat.shape[2]))
+            b["filt_ws"] = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
+        key = (obs_flat.data_ptr(), boot_obs.data_ptr(), rewards.data_ptr(), dones.data_ptr(), eps_flat.data_ptr(),
+               shuffle.data_ptr() if shuffle is not None else 0, tuple(obs_flat.shape), cols_per_env, bool(update_filter), id(b))
+        g = self._prep_graphs.get(key)
+        if g is None:
+            if len(self._prep_graphs) >= 8:      # inputs keep moving (fresh tensors every call): stop capturing
+                self._prep_graphs = None
+                return self._prepare(*args)
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._prepare(*args)
+                self._prep_graphs[key] = g
+            except Exception as exc:
+                self._prep_graphs = None
+                self.graph_error = repr(exc)
+                torch.cuda.synchronize()
+                return self._prepare(*args)
+        g.replay()
+
     # ---- the iteration --------------------------------------------------------------------------------------
     def learn_on_rollout(self, raw_obs: torch.Tensor, boot_obs: torch.Tensor, rewards: torch.Tensor,
                          dones: torch.Tensor, eps: torch.Tensor, perms: torch.Tensor,
@@ -239,46 +311,11 @@ class FCNetLearner(_LearnerBase):
         R = T * Cc
         b = self._alloc(T, Cc)
         obs_flat = raw_obs.reshape(P, R, D)
-        self.tc_status.zero_()
-        K.fcnet_pack(self.theta, D, A, self.img)
-        if self.tc_img is not None:
-            K.fcnet_tc_pack(self.theta, D, A, self.tc_img)
-        # (i) filter + forward + sample ------------------------------------------------------------------
-        if update_filter:
-            if self.world > 1:
-                allp = gather_parts_rank_order(K.filter_partial(obs_flat), self.dist, self.world)
-                K.filter_merge(allp, R * self.world, self.filt_n, self.filt_M, self.filt_S, self.norm)
-            else:
-                K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])
-        if self.tc_forward and self.tc_img is not None and K.tc_pingpong_eligible(D, A):
-            # inference on the tensor cores (same pipeline as the training forward, ~3e-6 relative)
-            K.fcnet_forward_tc(self.tc_img, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
-                               out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
-                                    "logp": b["logp"]}, status=self.tc_status)
-            K.fcnet_forward_tc(self.tc_img, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
-                               out={"logits": None, "value": b["vboot"], "obs_out": None}, status=self.tc_status)
-        else:
-            K.fcnet_forward(self.theta, obs_flat, A, norm=self.norm, clip=cfg.filter_clip, eps=eps.reshape(P, R, A),
-                            out={"logits": b["logits"], "value": b["value"], "obs_out": b["obs"], "action": b["act"],
-                                 "logp": b["logp"]}, img=self.img)
-            # (ii) bootstrap + GAE + standardise -----------------------------------------------------------
-            K.fcnet_forward(self.theta, boot_obs, A, norm=self.norm, clip=cfg.filter_clip,
-                            out={"logits": None, "value": b["vboot"], "obs_out": None}, img=self.img)
-        K.gae(rewards, b["value"].view(P, T, Cc), dones, b["vboot"], cols_per_env, cfg.gamma, cfg.lambda_,
-              b["adv"].view(P, T, Cc), b["vtarg"].view(P, T, Cc), b["moments"], b["gae_ws"])
-        if self.world > 1:
-            self.dist.all_reduce(b["moments"])
-        K.adv_standardize(b["adv"], b["moments"])
-        # shuffle (SampleBatch.shuffle) -----------------------------------------------------------------
+        eps_flat = eps.reshape(P, R, A)
         names = ("obs", "act", "logits", "logp", "value", "adv", "vtarg")
-        if shuffle is not None:
-            for nme in names:
-                K.gather_rows(b[nme], shuffle, b[nme + "_s"])
-            src = {n_: b[n_ + "_s"] for n_ in names}
-            src_key = "s"
-        else:
-            src = {n_: b[n_] for n_ in names}
-            src_key = "u"
+        src_key = "s" if shuffle is not None else "u"
+        src = {n_: b[n_ + ("_s" if shuffle is not None else "")] for n_ in names}
+        self._prepare_cached(b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc)
         # (iii) minibatch SGD ----------------------------------------------------------------------------
         E = perms.shape[1]
         MB, nb, G = self._sgd_setup(R)

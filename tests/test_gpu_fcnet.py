@@ -419,3 +419,35 @@ def test_tensor_core_inference_forward_matches_oracle(arch, R):
     vb = torch.empty(P, R, dtype=torch.float32, device="cuda")
     K.fcnet_forward_tc(img, _dev(raw, "cuda"), A, norm=_dev(norm, "cuda"), out={"logits": None, "value": vb, "obs_out": None})
     assert torch.equal(vb, out["value"])
+
+
+def test_graph_replayed_iterations_are_bit_identical_to_eager_ones():
+    """use_graph=True replays the preparation phase (filter, inference, GAE, shuffle) from a CUDA graph keyed by the input
+    buffers; three consecutive iterations must leave exactly the state the eager learner reaches."""
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import FCNetLearner
+    arch, T, C = "FullyDecentral", 16, 32
+    R = T * C
+    b = _make_batch(arch, R, 9, "cuda")
+    P, D, A = b["P"], b["D"], b["A"]
+    theta0, filt0, _, _ = ckpt_theta(arch)
+    rng = np.random.default_rng(3)
+    rewards = _dev((0.3 + 0.5 * rng.standard_normal((P, T, C))).astype(np.float32), "cuda")
+    dones = _dev((rng.random((T, C)) < 0.05).astype(np.uint8), "cuda")
+    boot = _dev(synth_obs(filt0, C, 5), "cuda")
+    raw = _dev(b["raw"].reshape(P, T, C, D), "cuda")
+    eps = _dev(b["eps"].reshape(P, T, C, A), "cuda")
+    perms = _dev(np.stack([np.stack([rng.permutation(R // 128) for _ in range(2)]) for _ in range(P)]).astype(np.int32), "cuda")
+    shuffle = _dev(np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32), "cuda")
+    out = []
+    for graph in (True, False):
+        L = FCNetLearner(P, D, A, PPOConfig(num_sgd_iter=2, sgd_minibatch_size=128), "cuda", theta=torch.from_numpy(theta0),
+                         use_graph=graph)
+        stats = [L.learn_on_rollout(raw, boot, rewards, dones, eps, perms, shuffle) for _ in range(3)]
+        torch.cuda.synchronize()
+        if graph:
+            assert L._prep_graphs is not None and len(L._prep_graphs) == 1, getattr(L, "graph_error", None)
+        out.append((L.theta.clone(), L.m.clone(), L.v.clone(), L.filt_M.clone(), L.filt_n.clone(), stats))
+    for x, y in zip(out[0][:5], out[1][:5]):
+        assert torch.equal(x, y)
+    assert out[0][5] == out[1][5]
