@@ -420,7 +420,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-                "traffic": (69.92e6 if (persistent and args.mode == "tc" and envs == 4096 and nb == 32 and args.arch == "FullyDecentral") else None),
+                "traffic": (69.41e6 if (persistent and args.mode == "tc" and envs == 4096 and nb == 32 and args.arch == "FullyDecentral") else None),
                 "traffic_note": "dram__bytes_read+write per launch (32 steps), ncu --set full, profiles/r01_ncu_train_tc2_persistent_summary.txt",
                 "launch_ms": k_ms, "flops_per_launch": flops_launch, "sgd_steps_per_launch": steps_per_launch,
                 "us_per_sgd_step": 1e3 * k_ms / steps_per_launch,
