@@ -282,7 +282,7 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
 def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
@@ -292,13 +292,15 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     fuse = not mode.endswith("-3k")
     persistent = not mode.endswith("-1step")      # "tc": one persistent launch per epoch where the kernel allows it
     cluster = mode.endswith("-cluster")           # thread-block clusters pre-reduce the partial gradients over DSMEM
+    multitile = mode.endswith("-multitile")       # 2 CTAs per policy x 256 rows: two 128-row tiles per CTA, persistent launch
     mode = mode.split("-")[0]
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
     O = _oracle()
-    T, C = 16, 32
+    T, C = (16, 128) if multitile else (16, 32)
     R = T * C
-    cfgd = dict(num_sgd_iter=2, sgd_minibatch_size=128)
+    MBS = 512 if multitile else 128
+    cfgd = dict(num_sgd_iter=2, sgd_minibatch_size=MBS)
     cfg_o = O.PPOConfig(**cfgd)
     cfg = PPOConfig(**cfgd)
     b = _make_batch(arch, R, 6, "cuda")
@@ -310,12 +312,12 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     rewards = (0.3 + 0.5 * rng.standard_normal((P, T, C))).astype(np.float32)
     dones = (rng.random((T, C)) < 0.05).astype(np.uint8)
     boot_raw = synth_obs(ckpt_theta(arch)[1], C, 99)
-    nb = R // 128
+    nb = R // MBS
     perms = np.stack([np.stack([rng.permutation(nb) for _ in range(2)]) for _ in range(P)]).astype(np.int32)
     shuffle = np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32) if use_shuffle else None
 
     L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse,
-                     persistent=persistent, ctas_per_policy=8 if cluster else None)
+                     persistent=persistent, ctas_per_policy=8 if cluster else 2 if multitile else None)
     if cluster:
         from ddrl_b200 import kernels as K
         K.tc_set_cluster(-1)
@@ -387,7 +389,7 @@ def test_packed_weight_image_path_equals_flat_path():
 
 
 @pytest.mark.parametrize("arch", ["FullyDecentral", "Local", "TwoSides", "Centralized", "SingleDiagonal", "FullyDecentral_TVel"])
-@pytest.mark.parametrize("R", [1, 100, 128, 700])
+@pytest.mark.parametrize("R", [1, 100, 128, 700, 20011])      # 20011: several 128-row tiles per CTA, ragged last tile
 def test_tensor_core_inference_forward_matches_oracle(arch, R):
     """ddrl_fcnet_forward_tc: filter normalise -> logits / value -> DiagGaussian sample + logp, on checkpoint weights with
     the checkpoint's filter; 1e-5 of the tensor's scale vs the float64 oracle; obs_out identical to the FP32 kernel's."""
