@@ -169,7 +169,8 @@ def run_graphnet(args):
     import torch
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import GraphNetLearner
-    import oracle.ddrl_oracle as O
+    from ddrl_b200.modelv2 import _FlatParams, graphnet_shapes
+    from ddrl_b200.policies import QuantrupedDecentralizedSharedGraphEnv
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     A, T, N, E = 2, 32, args.envs, args.gn_epochs
@@ -177,11 +178,11 @@ def run_graphnet(args):
     nb = 32
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=R // nb)
     g = torch.Generator().manual_seed(7)
-    th = O.graphnet_wrapper_init(2 * A, g).reshape(1, -1)
+    th = _FlatParams(graphnet_shapes(2 * A)).init_host(g, small=("actor/linear_out", "critic/linear_out")).reshape(1, -1)
     L = GraphNetLearner(A, cfg, dev, theta=th)
     state = torch.randn(T, C, 4, 23, generator=g).to(dev)
     idx = torch.arange(4, dtype=torch.int32).repeat(T * N).reshape(T, C).to(dev)
-    adj = O.ring_adjacency().expand(T, C, 4, 4).contiguous().to(dev)
+    adj = torch.from_numpy(QuantrupedDecentralizedSharedGraphEnv.create_adj()).float().expand(T, C, 4, 4).contiguous().to(dev)
     rewards = (0.3 + 0.5 * torch.randn(T, C, generator=g)).to(dev)
     dones = (torch.rand(T, N, generator=g) < 1e-3).to(torch.uint8).to(dev)
     eps = torch.randn(T, C, A, generator=g).to(dev)
@@ -275,14 +276,15 @@ def main():
 
     if args.tc_variant:
         K.tc_set_variant(args.tc_variant)
-    import oracle.ddrl_oracle as O  # Glorot init values only (host RNG); no oracle compute in the timed path
+    from ddrl_b200.modelv2 import fcnet_init_flat      # the product's own GlorotUniformScaled initialiser
     gen = torch.Generator().manual_seed(1234)
-    theta0 = torch.stack([O.fcnet_init(D, 2 * A, gen) for _ in range(P)])
+    theta0 = torch.stack([fcnet_init_flat(D, 2 * A, gen) for _ in range(P)])
     L = FCNetLearner(P, D, A, cfg, dev, theta=theta0, use_graph=not args.no_graph, mode=args.mode,
                      ctas_per_policy=args.ctas or None)
 
     sets = [synth_rollout(P, T, C, D, A, envs, nb, E, 1234 + rank + 100 * s, device=dev) for s in range(args.sets)]
-    host = synth_rollout(P, T, C, D, A, envs, nb, E, 999 + rank, pinned=True)
+    host = {k: v.contiguous().pin_memory() for k, v in synth_rollout(P, T, C, D, A, envs, nb, E, 999 + rank).items()
+            if k in ("rewards", "dones", "perms", "shuffle")}   # pinned e2e inputs besides the observations (below)
     bytes_per_set = sum(v.numel() * v.element_size() for v in sets[0].values())
 
     def step_resident(i):
@@ -301,7 +303,7 @@ def main():
     mu_f, sg_f = torch.linspace(-0.5, 3.0, Dfull), torch.logspace(-1.0, 1.95, Dfull)
     host_full = (mu_f + sg_f * torch.randn(T * envs, Dfull, generator=gfull)).float().contiguous().pin_memory()
     host_boot = (mu_f + sg_f * torch.randn(envs, Dfull, generator=gfull)).float().contiguous().pin_memory()
-    host_small = {k: v for k, v in host.items() if k not in ("eps", "raw", "boot")}
+    host_small = host
     draw = torch.empty(P, T * C, D, dtype=torch.float32, device=dev)
     dbootg = torch.empty(P, C, D, dtype=torch.float32, device=dev)
     h2d = sum(v.numel() * v.element_size() for v in list(host_small.values()) + [host_full, host_boot])

@@ -3,8 +3,11 @@
 One learner iteration on a rollout ``[T, C]`` per policy:
   (i)   MeanStdFilter update + normalise, policy/value forward, DiagGaussian sample + logp   (K4, K1)
   (ii)  bootstrap value, GAE, advantage standardisation                                       (K1, K5)
-  (iii) ``num_sgd_iter`` epochs of minibatch SGD: fused forward+PPO-loss+backward, fixed-order
-        gradient reduction, [NCCL all-reduce over ranks], global-norm clip + TF1 Adam        (K2/K6, K7)
+  (iii) ``num_sgd_iter`` epochs of minibatch SGD.  Default (``mode="tc"``): ONE persistent tcgen05 launch per epoch
+        that runs every optimizer step inside the kernel — forward + PPO loss + backward, fixed-order gradient
+        reduction, in-kernel NVLink all-reduce over ranks, global-norm clip, TF1 Adam (csrc/tc2.cu, csrc/sgd_tail.cuh).
+        ``mode="fp32"`` / ``fuse_tail=False`` keep the FP32-FMA kernel and the three-kernel step with an NCCL
+        all-reduce between gradient reduce and Adam                                            (K2/K6, K7)
   (iv)  KL-coefficient update.
 It replaces what RLlib 1.0.1 executes around the reference's models for ``tune.run("PPO", ...)``
 (train_experiment_1_architecture_on_flat.py:201-211): sampler-side filter/forward, ``postprocess_ppo_gae``,
@@ -13,7 +16,8 @@ processed by the same kernel launches ("grouped"); ranks shard the rollout by en
 only the flat gradient (every optimizer step), the filter partials, the advantage moments and the
 learner-stat sums (once per iteration).
 
-All arithmetic runs in libddrl_b200.so; torch provides memory, streams, CUDA graphs and NCCL."""
+All arithmetic runs in libddrl_b200.so; torch provides memory, streams, CUDA graphs and the once-per-iteration NCCL
+collectives (filter partials, advantage moments, stat sums)."""
 from __future__ import annotations
 
 import math

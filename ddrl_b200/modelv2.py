@@ -100,6 +100,12 @@ def fcnet_shapes(D: int, num_outputs: int):
             ("value_out/kernel", (H, 1)), ("value_out/bias", (1,))]
 
 
+def fcnet_init_flat(D: int, num_outputs: int, gen: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Flat float32 parameter vector of one FCNet policy initialised like the reference (GlorotUniformScaled: scale 1.0
+    for the hidden layers, 0.01 for fc_out / value_out, zero biases; models/fcnet_glorot_uniform_init.py:48-113)."""
+    return _FlatParams(fcnet_shapes(D, num_outputs)).init_host(gen, small=("fc_out", "value_out"))
+
+
 def graphnet_shapes(num_outputs: int):
     H, F, E = K.HIDDEN, K.GN_FEATS, K.GN_ENC_IN
     one = lambda O, pre: [(pre + "state_enc/kernel", (E, F * H)), (pre + "state_enc/bias", (F * H,)),
