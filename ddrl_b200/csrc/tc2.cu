@@ -1,18 +1,26 @@
-// Tensor-core FCNet training step, "ping-pong" schedule (sm_100a, tcgen05 + TMEM).
+// Tensor-core FCNet step, "ping-pong" schedule (sm_100a, tcgen05 + TMEM): the PPO training step of all policies as ONE
+// persistent kernel, and (template flag FWD) the inference forward.
 //
-// Same contract, operand layouts, scales and arithmetic as fcnet_train_tc_kernel (tc.cu) — one minibatch of all policies,
-// fused forward + PPO loss + backward, per-CTA partial gradients in flat checkpoint order — but BOTH branches of the
-// network (policy MLP and value MLP) are resident at once and software-pipelined against each other:
+// Same operand layouts, scales and arithmetic as fcnet_train_tc_kernel (tc.cu) — fused forward + PPO loss + backward,
+// per-CTA partial gradients in flat checkpoint order — but BOTH branches of the network (policy MLP and value MLP) are
+// resident at once and software-pipelined against each other:
 //
 //     issue F1(pol), F1(val) | wait pol -> tanh epilogue(pol) -> issue F2(pol) | wait val -> tanh epilogue(val) -> issue F2(val) | ...
 //
-// While the 16 warps run one branch's epilogue (TMEM -> tanh / (1-h^2) -> fp16 hi/lo -> shared memory), the tensor core
-// executes the other branch's GEMMs, so the MMA latency that the branch-sequential kernel exposed 12 times per tile is
-// hidden; each branch has its own accumulator columns and its own mbarrier.  The two PPO-loss halves (policy part on
-// warps 0-3, value part on warps 4-7) run concurrently.  MMAs are issued by lane 0 of the LAST warp, which carries no
-// loss work.  Cost: H1/H2 of both branches live in shared memory (128 KB); DL and the observation staging reuse space that
-// is dead at the time (fcnet_tc_layout.cuh), which fits D <= 46 (tc2_eligible; A = 8 needs D >= 31, i.e. the centralized
-// controller); other shapes keep the branch-sequential kernel.
+//   * 16 epilogue warps (TMEM -> tanh / (1-h^2) -> fp16 hi/lo -> shared memory) + 4 MMA-issue warps.  While the epilogue
+//     warps work on one branch the tensor core executes the other branch's GEMMs; each branch has its own accumulator
+//     columns and its own mbarrier (expected arrivals = the 4 issuers).  The issuers are warps of their own because a lane
+//     that shares a warp with lanes spinning in mbarrier.try_wait gets its issue delayed by 0.5-2 us, and there are four of
+//     them because one thread issues a tcgen05.mma only every ~72 cycles whatever its shape (tests/umma_bench.py).
+//   * the two PPO-loss halves (policy part on warps 0-3, value part on warps 4-7) run concurrently.
+//   * H1/H2 of both branches live in shared memory (128 KB); DL, the observation staging and (A = 8) the old logits reuse
+//     space that is dead at the time (fcnet_tc_layout.cuh): D <= 46, every published architecture (tc2_eligible).
+//   * the launch runs a.tail.nsteps consecutive optimizer steps: per step the fused tail (sgd_tail.cuh) reduces the
+//     partial gradients over the CTAs of a policy, all-reduces them over NVLink peer memory (world > 1), clips and applies
+//     Adam; the CTAs of a policy meet at a barrier before they reload the updated weight image.  The next step's inputs are
+//     requested behind the tail; gW2 / gb2 / gWh leave for the partial while the last B5 is still running.
+//   * FWD = true: forward-only over all rows of each policy (filter normalise in the X split, DiagGaussian sample + logp in
+//     place of the loss) — ddrl_fcnet_forward_tc.
 #include <algorithm>
 
 #include "tc_common.cuh"
