@@ -4,8 +4,8 @@
 //   slice reduce: CTA bx owns parameters [bx*S, bx*S+S) and sums them over the G partials — up to 8 thread groups load
 //                 different partials concurrently (one L2 round trip instead of G dependent ones), fixed summation order
 //   [world > 1]   in-kernel all-reduce over NVLink peer memory, low-latency ("LL") style: every reduced element is PUSHED
-//                 into every rank's exchange buffer as ONE 64-bit store {value, sequence flag} — no fence, no separate
-//                 flag round trip — and the owner thread polls its own buffer until the `world` words carry this step's
+//                 into every rank's exchange buffer as a 64-bit word {value, sequence flag} (two words per 16-byte store)
+//                 — no fence, no separate flag round trip — and the owner thread polls its own buffer until the `world` words carry this step's
 //                 sequence number, then adds them in rank order.  Every rank ends with bit-identical sums after one
 //                 NVLink one-way latency; no NCCL call, no extra launch.  Buffers alternate by step parity.
 //   barrier B     per-slice ||g||^2 visible -> global norm (same order everywhere), tf.clip_by_global_norm, TF1 Adam on
@@ -164,16 +164,27 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
             float s = 0.f;
             for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * cpp + col])[e];
             const int jj = 4 * c0 + f;           // offset inside the slice
-            if (j0 + jj < NP) {
-                if (W > 1) {
-                    const unsigned long long word = want | (unsigned long long)__float_as_uint(s);
+            if (W > 1) {
+                // push to every rank's exchange buffer (own copy included).  Two neighbouring elements travel as ONE 16-byte
+                // store {value, flag, value, flag} issued by the even lane (NCCL-LL line: each 8-byte half is self-validating,
+                // so the store need not be atomic as a whole) — half the NVLink packets of one store per element.
+                const float s_nb = __shfl_down_sync(__activemask(), s, 1);      // nf is a multiple of 4: lane pairs stay together
+                if (j0 + jj < NP && (f & 1) == 0) {
+                    const unsigned long long w0 = want | (unsigned long long)__float_as_uint(s);
+                    if (j0 + jj + 1 < NP) {
+                        const unsigned long long w1 = want | (unsigned long long)__float_as_uint(s_nb);
 #pragma unroll 1
-                    for (int w = 0; w < W; ++w)   // push to every rank's exchange buffer (own copy included)
-                        st_relaxed_sys_u64(t.peer_x[w] + xoff + jj, word);
-                } else {
-                    slice_dst[jj] = s;
-                    gval = s;
+                        for (int w = 0; w < W; ++w)
+                            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(t.peer_x[w] + xoff + jj), "l"(w0), "l"(w1)
+                                         : "memory");
+                    } else {
+#pragma unroll 1
+                        for (int w = 0; w < W; ++w) st_relaxed_sys_u64(t.peer_x[w] + xoff + jj, w0);
+                    }
                 }
+            } else if (j0 + jj < NP) {
+                slice_dst[jj] = s;
+                gval = s;
             }
         }
         if (!pf) __syncthreads();
