@@ -52,6 +52,8 @@ PROTOTYPES = {
     "ddrl_fcnet_forward": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f64p, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_int,
                                      c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "ddrl_obs_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
+    "ddrl_graph_obs_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_f64p, c_f64p, C.c_double,
+                                       c_f64p, C.c_int, c_f32p, c_i32p, c_stream]),
     "ddrl_reward_split": (C.c_int, [c_f32p, c_f32p, c_f64p, c_f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_int, c_f32p, c_stream]),
     "ddrl_concat_actions": (C.c_int, [c_f32p, c_i32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, c_f32p, c_stream]),

@@ -360,6 +360,53 @@ __global__ void obs_gather_kernel(const T* __restrict__ full, int64_t S, int Dfu
     }
 }
 
+// N2: node features of the shared-graph env, batched over env-steps (all arithmetic in float64 with explicit _rn
+// operations so that no FMA contraction changes a bit against numpy):
+//   state[s][a][d <  Dn] = clip((full[s][table[a][d]] - mean[..]) / (std[..] + 1e-8), -clip, clip)   (env filter, frozen stats)
+//   state[s][a][Dn + 0..3] = full[s][1:5] (x) [0, 0, zw[a][0], zw[a][1]]                                  (leg_encoding_ego)
+// With rep != 0 every env-step emits Ag sample rows (row = s*Ag + j carries the whole [Ag][Dn+4] matrix and node_idx = j),
+// which is the batch layout RLlib builds from the per-agent observation tuples.
+template <typename T>
+__global__ void graph_obs_build_kernel(const T* __restrict__ full, int64_t S, int Dfull, const int32_t* __restrict__ table,
+                                       int Ag, int Dn, const double* __restrict__ mean, const double* __restrict__ stdv,
+                                       double clip, const double* __restrict__ zw, int rep, float* __restrict__ state,
+                                       int32_t* __restrict__ node_idx) {
+    const int F = Dn + 4;
+    const int64_t n = S * Ag * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % F);
+        const int64_t t = i / F;
+        const int a = (int)(t % Ag);
+        const int64_t s = t / Ag;
+        const T* o = full + s * Dfull;
+        double y;
+        if (d < Dn) {
+            const int c = table[a * Dn + d];
+            y = (double)o[c];
+            if (mean) y = __dsub_rn(y, mean[c]);
+            if (stdv) y = __ddiv_rn(y, __dadd_rn(stdv[c], 1e-8));
+            if (clip > 0.0) y = fmin(fmax(y, -clip), clip);
+        } else {
+            const double x1 = (double)o[1], y1 = (double)o[2], z1 = (double)o[3], w1 = (double)o[4];
+            const double qz = zw[2 * a], qw = zw[2 * a + 1];
+            // quat2 = (0, 0, qz, qw); the zero products are kept out: x + (+-0) == x for every x numpy can produce here
+            switch (d - Dn) {
+                case 0: y = __dadd_rn(__dmul_rn(x1, qw), __dmul_rn(y1, qz)); break;                      //  x1*w2 + y1*z2
+                case 1: y = __dadd_rn(__dmul_rn(-x1, qz), __dmul_rn(y1, qw)); break;                     // -x1*z2 + y1*w2
+                case 2: y = __dadd_rn(__dmul_rn(z1, qw), __dmul_rn(w1, qz)); break;                      //  z1*w2 + w1*z2
+                default: y = __dadd_rn(__dmul_rn(-z1, qz), __dmul_rn(w1, qw)); break;                    // -z1*z2 + w1*w2
+            }
+        }
+        const float v = (float)y;
+        if (rep) {
+            for (int j = 0; j < Ag; ++j) state[((s * Ag + j) * Ag + a) * F + d] = v;
+            if (d == 0 && node_idx) node_idx[s * Ag + a] = a;
+        } else {
+            state[i] = v;
+        }
+    }
+}
+
 // N2: per-agent reward / cost split of the multi-agent adaptor, batched over env-steps (float64 arithmetic like numpy):
 //   contact_a = sum_body Wc[a][body] * contact_w * sum_j clip(cfrc[body][j], -1, 1)^2      (distribute_contact_cost)
 //   mode 0  fw / Ag - ctrl_w * |act_a|^2 - contact_a                                        (distribute_per_leg_reward)
@@ -591,6 +638,22 @@ extern "C" int ddrl_obs_gather(const void* obs_full, int is_f64, int64_t S, int 
     if (is_f64) obs_gather_kernel<double><<<nb, 256, 0, (cudaStream_t)stream>>>((const double*)obs_full, S, Dfull, table, Ag, D, P, out);
     else obs_gather_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>((const float*)obs_full, S, Dfull, table, Ag, D, P, out);
     DDRL_CHECK_LAUNCH("obs_gather");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_graph_obs_build(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag,
+                                    int Dn, const double* mean, const double* stdv, double clip, const double* leg_zw,
+                                    int replicate, float* state, int32_t* node_idx, void* stream) {
+    DDRL_REQUIRE(obs_full && table && leg_zw && state && S >= 0 && Dfull >= 5 && Ag >= 1 && Dn >= 0, DDRL_E_BADARG,
+                 "graph_obs_build: null pointer or bad shape (the observation must hold the body quaternion in columns 1..4)");
+    if (S == 0) return DDRL_OK;
+    const int nb = (int)std::min<int64_t>(4096, (S * Ag * (Dn + 4) + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_f64) graph_obs_build_kernel<double><<<nb, 256, 0, st>>>((const double*)obs_full, S, Dfull, table, Ag, Dn, mean, stdv,
+                                                                   clip, leg_zw, replicate, state, node_idx);
+    else graph_obs_build_kernel<float><<<nb, 256, 0, st>>>((const float*)obs_full, S, Dfull, table, Ag, Dn, mean, stdv, clip,
+                                                           leg_zw, replicate, state, node_idx);
+    DDRL_CHECK_LAUNCH("graph_obs_build");
     return DDRL_OK;
 }
 

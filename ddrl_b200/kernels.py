@@ -466,6 +466,26 @@ def obs_gather(obs_full: torch.Tensor, table: torch.Tensor, P: int, out: Optiona
     return out
 
 
+def graph_obs_build(obs_full: torch.Tensor, table: torch.Tensor, leg_zw: torch.Tensor, mean: Optional[torch.Tensor] = None,
+                    std: Optional[torch.Tensor] = None, clip: float = 10.0, replicate: bool = False):
+    """Node features of the shared-graph env: obs_full [S, Dfull] f32/f64 RAW, table [Ag, Dn] i32, leg_zw [Ag, 2] f64
+    ({sin, cos} of half the leg angle), mean / std [Dfull] f64 frozen filter statistics (None = no normalisation)
+    -> state [S, Ag, Dn+4] f32, or with ``replicate`` (state [S*Ag, Ag, Dn+4], node_idx [S*Ag] i32)."""
+    S, Dfull = obs_full.shape
+    Ag, Dn = table.shape
+    if obs_full.dtype not in (torch.float32, torch.float64):
+        raise DDRLError("graph_obs_build: obs_full must be float32 or float64")
+    dev = obs_full.device
+    state = torch.empty((S * Ag, Ag, Dn + 4) if replicate else (S, Ag, Dn + 4), dtype=torch.float32, device=dev)
+    node_idx = torch.empty(S * Ag, dtype=torch.int32, device=dev) if replicate else None
+    _lib.check(_lib.load().ddrl_graph_obs_build(_p(obs_full, None, "obs_full"), int(obs_full.dtype == torch.float64), S, Dfull,
+                                                _p(table, torch.int32, "table"), Ag, Dn, _p(mean, torch.float64, "mean"),
+                                                _p(std, torch.float64, "std"), float(clip), _p(leg_zw, torch.float64, "leg_zw"),
+                                                int(replicate), _p(state, torch.float32, "state"),
+                                                _p(node_idx, torch.int32, "node_idx"), _stream()), "graph_obs_build")
+    return (state, node_idx) if replicate else state
+
+
 def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, beta2, eps, grad_clip, gnorm_out=None, img=None,
                   tc_img=None, step_stats=None, step_ctr=None, status=None) -> SgdTail:
     """Fused grad-reduce + [peer all-reduce] + clip + Adam tail of the SGD step (see ddrl_sgd_tail in ddrl_b200.h).

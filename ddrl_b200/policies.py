@@ -236,6 +236,13 @@ class QuantrupedDecentralizedSharedGraphEnv(_Arch):
         return [[n[s], n[r]] for s, r in ring] + [[n[r], n[s]] for s, r in ring]
 
     @classmethod
+    def leg_quat_table(cls) -> np.ndarray:
+        """float64 [4, 2] = {sin, cos} of HALF the leg's mounting angle: the (z, w) components of the yaw quaternion
+        `leg_encoding_ego` multiplies the body orientation with (…GraphDecentralized…:145-161)."""
+        half = np.deg2rad(np.asarray([cls.leg_angles[a] for a in cls.agent_names]) / 2.0)
+        return np.stack((np.sin(half), np.cos(half)), axis=1)
+
+    @classmethod
     def create_adj(cls) -> np.ndarray:
         adj = np.zeros([4, 4], dtype=np.float64)
         adj[(*np.transpose(cls.create_edge_index()),)] = 1.0

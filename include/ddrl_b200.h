@@ -111,6 +111,19 @@ int ddrl_fcnet_forward(const float* theta, const float* img, const float* obs, c
 int ddrl_obs_gather(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag,
                     int D, int P, float* out, void* stream);
 
+/* Replaces (batched over S env-steps): QuantrupedDecentralizedSharedGraphEnv.distribute_observations with its
+ * leg_encoding_ego / quaternion_multiply (simulation_envs/quantruped_GraphDecentralizedController_environments.py:145-161,
+ * 215-245): the node-feature matrix of the shared-graph policy.
+ *   obs_full [S][Dfull] float32/float64 RAW observations; table [Ag][Dn] int32 (obs_indices, agent order);
+ *   mean / stdv [Dfull] float64 or NULL: frozen statistics of the env-side MeanStdFilter (y = (x-mean)/(std+1e-8));
+ *   clip > 0: clamp to [-clip, clip] (RLlib default 10); leg_zw [Ag][2] float64 = {sin, cos} of HALF the leg angle
+ *   -> state float32: replicate == 0: [S][Ag][Dn+4];  replicate != 0: [S*Ag][Ag][Dn+4] (sample row s*Ag+j = agent j's
+ *      observation tuple, all Ag rows of an env-step carry the same matrix) and node_idx [S*Ag] int32 = j (may be NULL).
+ *   float64 arithmetic, rounded once to float32: bit-exact against numpy. */
+int ddrl_graph_obs_build(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag,
+                         int Dn, const double* mean, const double* stdv, double clip, const double* leg_zw,
+                         int replicate, float* state, int32_t* node_idx, void* stream);
+
 /* Replaces (batched over S env-steps): distribute_per_leg_reward / distribute_global_reward / distribute_contact_cost
  * (simulation_envs/quantruped_adaptor_multi_environment.py:160-203) and the GlobalCosts variant
  * (quantruped_fourDecentralizedController_GlobalCosts_environments.py:69-83), float64 arithmetic like numpy:

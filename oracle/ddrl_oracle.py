@@ -401,6 +401,43 @@ def concatenate_actions(action_dict, action_indices):
     return actions
 
 
+LEG_ANGLES = {"agent_FL": 45., "agent_HL": 135., "agent_HR": -135., "agent_FR": -45.}   # …GraphDecentralized…:138-143
+
+
+def leg_encoding(angle):
+    """quantruped_GraphDecentralizedController_environments.py:145-147  -> [sin, cos] of the angle in degrees."""
+    rad = np.deg2rad(angle)
+    return np.stack((np.sin(rad), np.cos(rad)))
+
+
+def quaternion_multiply(quat1, quat2):
+    """quantruped_GraphDecentralizedController_environments.py:149-156 (component order as written there)."""
+    x1, y1, z1, w1 = quat1
+    x2, y2, z2, w2 = quat2
+    return np.array([x1 * w2 + y1 * z2 - z1 * y2 + w1 * x2,
+                     -x1 * z2 + y1 * w2 + z1 * x2 + w1 * y2,
+                     x1 * y2 - y1 * x2 + z1 * w2 + w1 * z2,
+                     -x1 * x2 - y1 * y2 - z1 * z2 + w1 * w2])
+
+
+def leg_encoding_ego(angle, full_obs):
+    """:158-161 — body orientation obs[1:5] times the leg's yaw quaternion (half angle)."""
+    quat_z, quat_w = leg_encoding(angle / 2.)
+    return quaternion_multiply(full_obs[1:5], [0., 0., quat_z, quat_w])
+
+
+def graph_distribute_observations(obs_full, normalize, obs_indices, leg_angles=None):
+    """Node-feature matrix of the shared-graph env for ONE env step
+    (quantruped_GraphDecentralizedController_environments.py:215-245): per agent, the normalised 43-dim observation
+    gathered by the agent's index list, followed by the 4 ego leg-encoding numbers computed from the RAW observation.
+    `normalize` is the env-side filter call (`_normalize_observation`, quantruped_adaptor_multi_environment.py:83-85).
+    Returns [n_agents, len(idx) + 4] in obs_full's dtype; every agent receives (its index, this matrix, adj)."""
+    leg_angles = LEG_ANGLES if leg_angles is None else leg_angles
+    normed = normalize(obs_full)
+    rows = [np.concatenate((normed[obs_indices[a]], leg_encoding_ego(leg_angles[a], obs_full))) for a in obs_indices]
+    return np.stack(rows).astype(obs_full.dtype)
+
+
 # --------------------------------------------------------------------------------------------
 # a4  MeanStdFilter / RunningStat        ray.rllib.utils.filter (1.0.1), used at
 #     simulation_envs/observation_filter.py:8-12 and via observation_filter="MeanStdFilter"

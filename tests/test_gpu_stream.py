@@ -200,3 +200,53 @@ def test_reward_split_and_action_concat_match_the_adaptor(scope, mode):
     for s in range(0, S, 7):
         refa = O.concatenate_actions({a: np.clip(act[s, i], -1.0, 1.0) for i, a in enumerate(env.agent_names)}, ai)
         assert np.array_equal(full[s], refa.astype(np.float32))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_graph_obs_build_equals_the_reference_env(dtype):
+    """N2: node features of the shared-graph env (filter-normalised index gather + ego leg quaternion) against vectors made
+    by the reference's own code (tests/golden/make_graph_obs_golden.py).  float64 input: bit-exact."""
+    import os
+    from ddrl_b200 import kernels as K
+    from ddrl_b200.policies import ARCHITECTURES
+    from tests.util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "graph_obs.npz"))
+    env = ARCHITECTURES["QuantrupedMultiEnv_DecentralShared_Graph"]
+    obs = g["obs_full"].astype(dtype)
+    table, zw = _dev(env.gather_table()), _dev(env.leg_quat_table())
+    state = K.graph_obs_build(_dev(obs), table, zw, _dev(g["mean"]), _dev(g["std"]), clip=10.0).cpu().numpy()
+    want = g["frozen"].astype(np.float32)
+    if dtype is np.float64:
+        assert np.array_equal(state, want)
+    else:
+        assert np.abs(state - want).max() < 2e-6 * np.abs(want).max()
+    rep, node_idx = K.graph_obs_build(_dev(obs), table, zw, _dev(g["mean"]), _dev(g["std"]), clip=10.0, replicate=True)
+    rep, node_idx = rep.cpu().numpy(), node_idx.cpu().numpy()
+    assert np.array_equal(node_idx, np.tile(np.arange(4, dtype=np.int32), len(obs)))
+    assert np.array_equal(rep.reshape(len(obs), 4, 4, 23), np.repeat(state[:, None], 4, axis=1))
+    raw = K.graph_obs_build(_dev(obs), table, zw, None, None, clip=0.0).cpu().numpy()           # no filter: plain gather
+    assert np.array_equal(raw[:, :, :19], obs[:, env.gather_table()].astype(np.float32))
+    assert np.array_equal(raw[:, :, 19:], state[:, :, 19:])
+    empty = K.graph_obs_build(_dev(obs[:0]), table, zw, _dev(g["mean"]), _dev(g["std"]))
+    assert tuple(empty.shape) == (0, 4, 23)
+
+
+@pytest.mark.parametrize("tag,scope", [("four", "QuantrupedMultiEnv_FullyDecentral"), ("two", "QuantrupedMultiEnv_TwoSides"),
+                                       ("one", "QuantrupedMultiEnv_Centralized")])
+def test_reward_split_and_action_concat_equal_reference_vectors(tag, scope):
+    """N2 against vectors produced by the reference's own adaptor methods (tests/golden/make_env_glue_golden.py; its
+    fw / action inputs are float32-representable).  Rewards: float64 on both sides, summed in a different order, rounded to
+    float32 by the device -> 1e-6; the action scatter is bit-exact."""
+    import os
+    from ddrl_b200 import kernels as K
+    from ddrl_b200.policies import ARCHITECTURES
+    from tests.util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "env_glue.npz"))
+    env = ARCHITECTURES[scope]
+    fw, act, cfrc = g[f"{tag}/fw"].astype(np.float32), g[f"{tag}/act"].astype(np.float32), g[f"{tag}/cfrc"]
+    for mode in ("per_leg", "per_leg_norm", "global", "global_costs"):
+        rew = K.reward_split(_dev(fw), _dev(act), _dev(cfrc), _dev(env.contact_table()), 0.25, 0.025, mode).cpu().numpy()
+        want = g[f"{tag}/{mode}"]
+        assert np.abs(rew - want).max() < 1e-6 * max(1.0, np.abs(want).max()), mode
+    full = K.concat_actions(_dev(act), _dev(env.action_table())).cpu().numpy()
+    assert np.array_equal(full, g[f"{tag}/actions"].astype(np.float32))
