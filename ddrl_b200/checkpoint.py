@@ -158,6 +158,24 @@ def _unflatten(pid: str, flat: np.ndarray, shapes, suffix: str = "", prefix_pid:
     return out
 
 
+def fcnet_variable_shapes(D: int, A: int) -> List[tuple]:
+    """Shapes of the 12 FCNet variables in checkpoint order (hiddens [64, 64], separate value branch)."""
+    return [(D, 64), (64,), (D, 64), (64,), (64, 64), (64,), (64, 64), (64,), (64, 2 * A), (2 * A,), (64, 1), (1,)]
+
+
+def theta_to_variables(pid: str, theta: np.ndarray, D: int, A: int) -> "OrderedDict[str, np.ndarray]":
+    """Flat parameter vector -> {"<pid>/fc_1/kernel": ..., ...}: what `Policy.get_weights()` returns in the reference."""
+    return _unflatten(pid, np.asarray(theta, dtype=np.float32).reshape(-1), fcnet_variable_shapes(D, A))
+
+
+def variables_to_theta(pid: str, variables, D: int, A: int) -> np.ndarray:
+    """Inverse of `theta_to_variables` (`Policy.set_weights`); shapes are checked against the (D, A) architecture."""
+    theta, shapes = _flatten(pid, variables)
+    if [tuple(s) for s in shapes] != fcnet_variable_shapes(D, A):
+        raise ValueError(f"{pid}: variable shapes {shapes} do not match FCNet(D={D}, A={A})")
+    return theta
+
+
 def save_rllib_checkpoint(path: str, ckpt: Checkpoint) -> None:
     """Write ``ckpt`` in the reference's file format (see module docstring).  The filter classes are pickled under
     ``ray.rllib.utils.filter`` so that the reference's ``agent.restore`` resolves them to the real RLlib classes."""

@@ -320,7 +320,11 @@ class FCNetLearner(_LearnerBase):
         src_key = "s" if shuffle is not None else "u"
         src = {n_: b[n_ + ("_s" if shuffle is not None else "")] for n_ in names}
         self._prepare_cached(b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc)
-        # (iii) minibatch SGD ----------------------------------------------------------------------------
+        return self._sgd_phase(b, src, src_key, perms, R, T, Cc)
+
+    def _sgd_phase(self, b, src, src_key, perms, R: int, T: int, Cc: int) -> List[Dict[str, float]]:
+        """(iii) minibatch SGD over the prepared columns `src` + (iv) stats and KL-coefficient update."""
+        P, cfg = self.P, self.cfg
         E = perms.shape[1]
         MB, nb, G = self._sgd_setup(R)
         if perms.shape[2] != nb:
@@ -389,6 +393,56 @@ class FCNetLearner(_LearnerBase):
             raise DDRLError("SGD step failed (" + ", ".join(what) + ")" + hint)
         self._update_kl(stats)
         return stats
+
+    def learn_on_batch(self, obs: torch.Tensor, actions: torch.Tensor, action_dist_inputs: torch.Tensor,
+                       action_logp: torch.Tensor, vf_preds: torch.Tensor, advantages: torch.Tensor,
+                       value_targets: torch.Tensor, perms: torch.Tensor, shuffle: Optional[torch.Tensor] = None,
+                       standardize: bool = True) -> List[Dict[str, float]]:
+        """The learner half only, on POSTPROCESSED sample-batch columns as RLlib's `Policy.learn_on_batch` receives them
+        (rollout workers have already filtered the observations, sampled the actions and run `postprocess_ppo_gae`):
+        obs [P,R,D] (filtered), actions [P,R,A], action_dist_inputs [P,R,2A], action_logp / vf_preds / advantages /
+        value_targets [P,R] — float32 CUDA tensors, one row block per policy.  `standardize` applies
+        StandardizeFields(["advantages"]) per policy; `shuffle` [P,R] int32 and `perms` [P,E,nb] as in learn_on_rollout.
+        Runs StandardizeFields -> shuffle -> E x nb minibatch steps -> KL update and returns the learner stats."""
+        P, R, D = obs.shape
+        A = self.A
+        if D != self.D or P != self.P:
+            raise DDRLError(f"obs shape {tuple(obs.shape)} does not match learner (P={self.P}, D={self.D})")
+        cols = {"obs": (obs, (P, R, D)), "act": (actions, (P, R, A)), "logits": (action_dist_inputs, (P, R, 2 * A)),
+                "logp": (action_logp, (P, R)), "value": (vf_preds, (P, R)), "adv": (advantages, (P, R)),
+                "vtarg": (value_targets, (P, R))}
+        for name, (t, shape) in cols.items():
+            if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_cuda:
+                raise DDRLError(f"learn_on_batch: column {name!r} must be a float32 CUDA tensor of shape {shape}, "
+                                f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        b = self._alloc(R, 1)
+        self.tc_status.zero_()
+        K.fcnet_pack(self.theta, D, A, self.img)
+        if self.tc_img is not None:
+            K.fcnet_tc_pack(self.theta, D, A, self.tc_img)
+        for name, (t, _) in cols.items():
+            b[name].copy_(t)
+        if standardize:
+            self.standardize_advantages(b["adv"])
+        names = ("obs", "act", "logits", "logp", "value", "adv", "vtarg")
+        if shuffle is not None:
+            for nme in names:
+                K.gather_rows(b[nme], shuffle, b[nme + "_s"])
+        src = {n_: b[n_ + ("_s" if shuffle is not None else "")] for n_ in names}
+        return self._sgd_phase(b, src, "s" if shuffle is not None else "u", perms, R, R, 1)
+
+    def standardize_advantages(self, adv: torch.Tensor) -> torch.Tensor:
+        """StandardizeFields(["advantages"]) in place on adv [P,R] (float32, CUDA): per policy (adv - mean) / max(1e-4, std)
+        over ALL rows of the train batch (all ranks' rows at world > 1).  The three moments are float64 torch reductions
+        (plumbing); the rescale is `ddrl_adv_standardize`."""
+        P = adv.shape[0]
+        a64 = adv.reshape(P, -1).double()
+        moments = torch.stack([torch.full((P,), float(a64.shape[1]), dtype=torch.float64, device=adv.device),
+                               a64.sum(dim=1), (a64 * a64).sum(dim=1)], dim=1).contiguous()
+        if self.world > 1:
+            self.dist.all_reduce(moments)
+        K.adv_standardize(adv, moments)
+        return adv
 
     def refresh_filter_norm(self):
         """Recompute the normalisation table (mean, 1/(std+1e-8)) from filt_n / filt_M / filt_S — after the state was
