@@ -644,9 +644,10 @@ extern "C" int ddrl_obs_gather(const void* obs_full, int is_f64, int64_t S, int 
 extern "C" int ddrl_graph_obs_build(const void* obs_full, int is_f64, int64_t S, int Dfull, const int32_t* table, int Ag,
                                     int Dn, const double* mean, const double* stdv, double clip, const double* leg_zw,
                                     int replicate, float* state, int32_t* node_idx, void* stream) {
-    DDRL_REQUIRE(obs_full && table && leg_zw && state && S >= 0 && Dfull >= 5 && Ag >= 1 && Dn >= 0, DDRL_E_BADARG,
-                 "graph_obs_build: null pointer or bad shape (the observation must hold the body quaternion in columns 1..4)");
-    if (S == 0) return DDRL_OK;
+    DDRL_REQUIRE(S >= 0 && Dfull >= 5 && Ag >= 1 && Dn >= 0, DDRL_E_BADARG,
+                 "graph_obs_build: bad shape (the observation must hold the body quaternion in columns 1..4)");
+    if (S == 0) return DDRL_OK;      // an empty batch has no buffers to check
+    DDRL_REQUIRE(obs_full && table && leg_zw && state, DDRL_E_BADARG, "graph_obs_build: null pointer");
     const int nb = (int)std::min<int64_t>(4096, (S * Ag * (Dn + 4) + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (is_f64) graph_obs_build_kernel<double><<<nb, 256, 0, st>>>((const double*)obs_full, S, Dfull, table, Ag, Dn, mean, stdv,
