@@ -72,6 +72,7 @@ PROTOTYPES = {
                                  C.c_float, C.c_float, C.c_float, c_f32p, c_i32p, c_i32p, c_f32p, C.c_void_p, C.c_int,
                                  C.c_int, c_stream]),
     "ddrl_graphnet_num_params": (C.c_int, [C.c_int]),
+    "ddrl_graphnet_set_variant": (C.c_int, [C.c_int]),
     "ddrl_graphnet_forward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p,
                                         c_stream]),
     "ddrl_graphnet_backward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int,

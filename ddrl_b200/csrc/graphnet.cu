@@ -14,6 +14,7 @@
 //   backward mirrors it with the transposed use of Wupd/Wmsg served from shared memory (stride 68 =>
 //     conflict free) and per-thread gradient accumulators in registers; per-CTA partials leave once.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -307,6 +308,131 @@ graphnet_kernel(const float* __restrict__ theta, const int32_t* __restrict__ nod
     }
 }
 
+// ---- forward only, ONE WARP PER ROW ------------------------------------------------------------------------------------
+// The row-per-CTA kernel above pays two block barriers and a cross-warp reduction per row (~1.9 us per row: 426 us for a
+// 16 384-row minibatch, profiles/r01_launches_graphnet_summary.csv).  Inference and the SGD-step forward need no gradient
+// accumulators, so here one net's weights live in SHARED memory (73 KB, 3 CTAs per SM) and every warp walks over its own
+// rows without any block barrier: lane l owns the hidden units l and l + 32,
+//   encoder  x[n][h] = tanh(sum_f state[n][f] * tanh(b[f][h] + e . We[:, f, h]))     (conflict-free rows of We / be)
+//   MPNN     y[h']   = tanh(sum_h x_idx[h] Wu[h][h'] + mean_s x_s[h] Wm[h][h'])       (x through 1 KB of per-warp smem)
+//   head     out[q]  = sum_h' y[h'] Wo[h'][q] + bo[q]                                 (warp shuffle reduction)
+// Same arithmetic as graphnet_kernel<false> up to the FP32 summation order.
+constexpr int GWF_NT = 256;                   // 8 warps
+constexpr int GWF_WARPS = GWF_NT / 32;
+constexpr int GWF_ROW = 128;                  // staged floats per row (92 state + 16 adj + idx, padded)
+constexpr int GWF_WO = GMAXO + 1;             // stride of the head matrix: lanes hit distinct banks
+constexpr int GWF_SMEM_FLOATS = GE * GF * GH + GF * GH + 2 * GH * GH + GH * GWF_WO + GMAXO + GWF_WARPS * GWF_ROW +
+                                GWF_WARPS * GN * GH;
+
+__global__ void __launch_bounds__(GWF_NT, 3)
+graphnet_fwd_warp_kernel(const float* __restrict__ theta, const int32_t* __restrict__ node_idx,
+                         const float* __restrict__ state, const float* __restrict__ adj, int64_t B, int A,
+                         float* __restrict__ logits, float* __restrict__ value) {
+    extern __shared__ __align__(16) float gsm[];
+    float* sWe = gsm;                           // [GE][GF*GH]
+    float* sbe = sWe + GE * GF * GH;            // [GF*GH]
+    float* sWu = sbe + GF * GH;                 // [GH][GH]  (input h, output h')
+    float* sWm = sWu + GH * GH;
+    float* sWo = sWm + GH * GH;                 // [GH][GWF_WO]
+    float* sbo = sWo + GH * GWF_WO;             // [GMAXO]
+    float* sRowAll = sbo + GMAXO;               // [warps][GWF_ROW]
+    float* sXAll = sRowAll + GWF_WARPS * GWF_ROW;   // [warps][GN][GH]
+
+    const int net = blockIdx.y;                 // 0 actor, 1 critic
+    const int O = net == 0 ? 2 * A : 1;
+    const GnOffsets o = gn_offsets(O);
+    const float* th = theta + (net == 0 ? 0 : gn_offsets(2 * A).NP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < GE * GF * GH; i += GWF_NT) sWe[i] = th[o.We + i];
+    for (int i = tid; i < GF * GH; i += GWF_NT) sbe[i] = th[o.be + i];
+    for (int i = tid; i < GH * GH; i += GWF_NT) {
+        sWu[i] = th[o.Wu + i];
+        sWm[i] = th[o.Wm + i];
+    }
+    for (int i = tid; i < GH * GMAXO; i += GWF_NT) {
+        const int hh = i / GMAXO, q = i - hh * GMAXO;
+        sWo[hh * GWF_WO + q] = q < O ? th[o.Wo + hh * O + q] : 0.f;
+    }
+    if (tid < GMAXO) sbo[tid] = tid < O ? th[o.bo + tid] : 0.f;
+    __syncthreads();
+
+    float* sRow = sRowAll + warp * GWF_ROW;
+    float* sX = sXAll + warp * GN * GH;
+    const int64_t stride = (int64_t)gridDim.x * GWF_WARPS;
+    for (int64_t b = (int64_t)blockIdx.x * GWF_WARPS + warp; b < B; b += stride) {
+        for (int i = lane; i < GN * GS; i += 32) sRow[i] = state[b * GN * GS + i];
+        if (lane < GN * GN) sRow[GN * GS + lane] = adj[b * GN * GN + lane];
+        if (lane == GN * GN) sRow[GN * GS + GN * GN] = __int_as_float(node_idx[b]);
+        __syncwarp();
+        const GnRow g = gn_row(sRow);
+
+        // ---- encoder of the needed nodes (controlled node + its in-neighbours) --------------------------------------
+#pragma unroll
+        for (int n = 0; n < GN; ++n) {
+            if (g.need[n]) {                    // warp-uniform
+                const float* st = sRow + n * GS;
+                const float e0 = st[GF], e1 = st[GF + 1], e2 = st[GF + 2], e3 = st[GF + 3];
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int f = 0; f < GF; ++f) {
+                    const int j = f * GH + lane;
+                    float p0 = sbe[j], p1 = sbe[j + 32];
+                    p0 = fmaf(e0, sWe[j], p0);
+                    p1 = fmaf(e0, sWe[j + 32], p1);
+                    p0 = fmaf(e1, sWe[GF * GH + j], p0);
+                    p1 = fmaf(e1, sWe[GF * GH + j + 32], p1);
+                    p0 = fmaf(e2, sWe[2 * GF * GH + j], p0);
+                    p1 = fmaf(e2, sWe[2 * GF * GH + j + 32], p1);
+                    p0 = fmaf(e3, sWe[3 * GF * GH + j], p0);
+                    p1 = fmaf(e3, sWe[3 * GF * GH + j + 32], p1);
+                    const float sf = st[f];
+                    a0 = fmaf(sf, gn_tanh(p0), a0);
+                    a1 = fmaf(sf, gn_tanh(p1), a1);
+                }
+                sX[n * GH + lane] = gn_tanh(a0);
+                sX[n * GH + lane + 32] = gn_tanh(a1);
+            }
+        }
+        __syncwarp();
+
+        // ---- MPNN for the controlled node -----------------------------------------------------------------------------
+        const float inv_cnt = g.cnt > 0 ? 1.f / (float)g.cnt : 0.f;
+        const float* xs = sX + g.idx * GH;
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll 8
+        for (int hh = 0; hh < GH; ++hh) {
+            const float xi = xs[hh];
+            float sm = 0.f;
+#pragma unroll
+            for (int n = 0; n < GN; ++n)
+                if (g.is_snd[n]) sm += sX[n * GH + hh];
+            const float xm = sm * inv_cnt;
+            y0 = fmaf(xi, sWu[hh * GH + lane], y0);
+            y1 = fmaf(xi, sWu[hh * GH + lane + 32], y1);
+            y0 = fmaf(xm, sWm[hh * GH + lane], y0);
+            y1 = fmaf(xm, sWm[hh * GH + lane + 32], y1);
+        }
+        y0 = gn_tanh(y0);
+        y1 = gn_tanh(y1);
+
+        // ---- head ---------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < GMAXO; ++q) {
+            if (q < O) {
+                float v = fmaf(y0, sWo[lane * GWF_WO + q], y1 * sWo[(lane + 32) * GWF_WO + q]);
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+                if (lane == q) {
+                    v += sbo[q];
+                    if (net == 0) logits[b * O + q] = v; else value[b] = v;
+                }
+            }
+        }
+        __syncwarp();      // every lane is done with sRow / sX before the next row overwrites them
+    }
+}
+
 // ---- GCN layer: y[b][n][u] = act(sum_f (sum_m An[n][m] x[b][m][f]) W[f][u] + bias[u]) ---------------------
 __global__ void gcn_forward_kernel(const float* __restrict__ x, const float* __restrict__ adj, const float* __restrict__ W,
                                    const float* __restrict__ bias, int64_t B, int F, int U, int act,
@@ -349,6 +475,19 @@ extern "C" int ddrl_graphnet_num_params(int num_outputs) {
     return gn_offsets(num_outputs).NP + gn_offsets(1).NP;
 }
 
+// forward schedule: 0 = one row per CTA (graphnet_kernel<false>), 1 = one row per warp (graphnet_fwd_warp_kernel);
+// -1 = default, which the environment variable DDRL_GN_FWD_VARIANT may override (A/B timing without a rebuild)
+static int g_gn_fwd_variant = -1;
+constexpr int GN_FWD_DEFAULT = 1;   // measured: configs[3] iteration 75.5 -> 51.9 ms (profiles/README.md)
+static int gn_fwd_variant() {
+    if (g_gn_fwd_variant >= 0) return g_gn_fwd_variant;
+    static int from_env = [] {
+        const char* e = getenv("DDRL_GN_FWD_VARIANT");
+        return (e && (e[0] == '0' || e[0] == '1') && e[1] == 0) ? e[0] - '0' : GN_FWD_DEFAULT;
+    }();
+    return from_env;
+}
+
 static int gn_ctas(int64_t B) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -361,9 +500,32 @@ extern "C" int ddrl_graphnet_forward(const float* theta, const int32_t* node_idx
                  "graphnet_forward: null pointer or bad B");
     DDRL_REQUIRE(A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE, "graphnet_forward: unsupported A=%d", A);
     if (B == 0) return DDRL_OK;
+    if (gn_fwd_variant() == 1) {
+        static bool attr_set = false;       // per process; the attribute is sticky for the function
+        const size_t smem = (size_t)GWF_SMEM_FLOATS * sizeof(float);
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(graphnet_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "graphnet_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            attr_set = true;
+        }
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        // 3 CTAs per SM, the two nets side by side: (3 * sms / 2) CTAs per net, never more than one warp per row
+        const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((B + GWF_WARPS - 1) / GWF_WARPS, 3 * sms / 2));
+        graphnet_fwd_warp_kernel<<<dim3(gx, 2), GWF_NT, smem, (cudaStream_t)stream>>>(theta, node_idx, state, adj, B, A, logits,
+                                                                                      value);
+        DDRL_CHECK_LAUNCH("graphnet_forward");
+        return DDRL_OK;
+    }
     graphnet_kernel<false><<<dim3(gn_ctas(B), 2), GT2, 0, (cudaStream_t)stream>>>(theta, node_idx, state, adj, nullptr,
                                                                                  nullptr, B, A, logits, value, nullptr);
     DDRL_CHECK_LAUNCH("graphnet_forward");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_graphnet_set_variant(int variant) {
+    DDRL_REQUIRE(variant >= -1 && variant <= 1, DDRL_E_BADARG, "graphnet_set_variant: variant must be -1 (default), 0 or 1");
+    g_gn_fwd_variant = variant;
     return DDRL_OK;
 }
 

@@ -216,12 +216,23 @@ def fcnet_backward(theta, obs, dlogits, dvalue, A: int, ctas_per_policy: Optiona
 
 
 # --------------------------------------------------------------------------------------------------
-def graphnet_forward(theta, node_idx, state, adj, A: int):
-    """theta [NP] (actor|critic), node_idx [B] i32, state [B,4,23], adj [B,4,4] -> logits [B,2A], value [B]."""
+def graphnet_set_variant(variant: int) -> None:
+    """Forward schedule of the GraphNet kernels: 0 row-per-CTA, 1 row-per-warp, -1 library default."""
+    _lib.check(_lib.load().ddrl_graphnet_set_variant(int(variant)), "graphnet_set_variant")
+
+
+def graphnet_forward(theta, node_idx, state, adj, A: int, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """theta [NP] (actor|critic), node_idx [B] i32, state [B,4,23], adj [B,4,4] -> logits [B,2A], value [B]
+    (written into ``out`` = (logits, value) when given)."""
     B = state.shape[0]
     f32 = torch.float32
-    logits = torch.empty(B, 2 * A, dtype=f32, device=state.device)
-    value = torch.empty(B, dtype=f32, device=state.device)
+    if out is not None:
+        logits, value = out
+        if tuple(logits.shape) != (B, 2 * A) or tuple(value.shape) != (B,):
+            raise DDRLError(f"graphnet: out shapes {tuple(logits.shape)} / {tuple(value.shape)} != ({B}, {2 * A}) / ({B},)")
+    else:
+        logits = torch.empty(B, 2 * A, dtype=f32, device=state.device)
+        value = torch.empty(B, dtype=f32, device=state.device)
     if tuple(state.shape[1:]) != (GN_NODES, GN_FEATS + GN_ENC_IN) or tuple(adj.shape[1:]) != (GN_NODES, GN_NODES):
         raise DDRLError(f"graphnet: state {tuple(state.shape)} / adj {tuple(adj.shape)} must be [B,4,23] / [B,4,4]")
     if theta.numel() != graphnet_num_params(2 * A):

@@ -281,6 +281,10 @@ int ddrl_graphnet_num_params(int num_outputs);
 int ddrl_graphnet_forward(const float* theta, const int32_t* node_idx, const float* state,
                           const float* adj, int64_t B, int A, float* logits, float* value,
                           void* stream);
+/* Forward schedule (A/B timing and tests): 0 = one row per CTA, 1 = one row per warp with the weights in shared memory,
+ * -1 = library default (overridable by the environment variable DDRL_GN_FWD_VARIANT=0|1).  Same results up to the FP32
+ * summation order. */
+int ddrl_graphnet_set_variant(int variant);
 /* Backward of the wrapper w.r.t. theta from dlogits [B][2A], dvalue [B]:
  *   grad_part [G][NPs] per-CTA partials, NPs = (NP+3)&~3 (reduce with ddrl_grad_reduce(P=1)); G = ctas. */
 int ddrl_graphnet_backward(const float* theta, const int32_t* node_idx, const float* state,

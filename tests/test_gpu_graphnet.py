@@ -43,15 +43,22 @@ def _theta(A, seed, big=False):
     return th
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["row-per-cta", "row-per-warp"])
 @pytest.mark.parametrize("B,A,adj_kind", [(1, 2, "ring"), (257, 2, "ring"), (300, 2, "random"), (64, 4, "random"),
-                                          (40, 8, "ring")])
-def test_graphnet_forward(B, A, adj_kind):
+                                          (40, 8, "ring"), (7, 2, "random"), (9, 8, "random"), (20011, 2, "ring")])
+def test_graphnet_forward(B, A, adj_kind, variant):
     from ddrl_b200 import kernels as K
     O = _O()
     idx, state, adj = _inputs(B, B + A, adj_kind)
     th = _theta(A, 1, big=True)
-    lg, v = K.graphnet_forward(_dev(th.numpy(), torch.float32), _dev(idx), _dev(state), _dev(adj), A)
-    torch.cuda.synchronize()
+    nan = lambda *shape: torch.full(shape, float("nan"), device="cuda")
+    K.graphnet_set_variant(variant)
+    try:
+        lg, v = K.graphnet_forward(_dev(th.numpy(), torch.float32), _dev(idx), _dev(state), _dev(adj), A,
+                                   out=(nan(B, 2 * A), nan(B)))
+        torch.cuda.synchronize()
+    finally:
+        K.graphnet_set_variant(-1)
     th32 = th.float().double()   # the device sees float32 weights
     lg_ref, v_ref = O.graphnet_forward(th32, torch.from_numpy(idx), torch.from_numpy(state).double(),
                                        torch.from_numpy(adj).double(), 2 * A)
