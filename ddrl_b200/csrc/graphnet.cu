@@ -367,47 +367,71 @@ graphnet_fwd_warp_kernel(const float* __restrict__ theta, const int32_t* __restr
         __syncwarp();
         const GnRow g = gn_row(sRow);
 
-        // ---- encoder of the needed nodes (controlled node + its in-neighbours) --------------------------------------
+        // ---- encoder of the needed nodes (controlled node + its in-neighbours): every encoder weight is read from shared
+        //      memory ONCE per row and used for all of the row's nodes -----------------------------------------------------
+        float e[GN][GE], a0[GN], a1[GN];
 #pragma unroll
         for (int n = 0; n < GN; ++n) {
-            if (g.need[n]) {                    // warp-uniform
-                const float* st = sRow + n * GS;
-                const float e0 = st[GF], e1 = st[GF + 1], e2 = st[GF + 2], e3 = st[GF + 3];
-                float a0 = 0.f, a1 = 0.f;
+            a0[n] = 0.f;
+            a1[n] = 0.f;
 #pragma unroll
-                for (int f = 0; f < GF; ++f) {
-                    const int j = f * GH + lane;
-                    float p0 = sbe[j], p1 = sbe[j + 32];
-                    p0 = fmaf(e0, sWe[j], p0);
-                    p1 = fmaf(e0, sWe[j + 32], p1);
-                    p0 = fmaf(e1, sWe[GF * GH + j], p0);
-                    p1 = fmaf(e1, sWe[GF * GH + j + 32], p1);
-                    p0 = fmaf(e2, sWe[2 * GF * GH + j], p0);
-                    p1 = fmaf(e2, sWe[2 * GF * GH + j + 32], p1);
-                    p0 = fmaf(e3, sWe[3 * GF * GH + j], p0);
-                    p1 = fmaf(e3, sWe[3 * GF * GH + j + 32], p1);
-                    const float sf = st[f];
-                    a0 = fmaf(sf, gn_tanh(p0), a0);
-                    a1 = fmaf(sf, gn_tanh(p1), a1);
+            for (int q = 0; q < GE; ++q) e[n][q] = sRow[n * GS + GF + q];
+        }
+#pragma unroll
+        for (int f = 0; f < GF; ++f) {
+            const int j = f * GH + lane;
+            const float b0 = sbe[j], b1 = sbe[j + 32];
+            const float w00 = sWe[j], w01 = sWe[j + 32];
+            const float w10 = sWe[GF * GH + j], w11 = sWe[GF * GH + j + 32];
+            const float w20 = sWe[2 * GF * GH + j], w21 = sWe[2 * GF * GH + j + 32];
+            const float w30 = sWe[3 * GF * GH + j], w31 = sWe[3 * GF * GH + j + 32];
+#pragma unroll
+            for (int n = 0; n < GN; ++n) {
+                if (g.need[n]) {                // warp-uniform
+                    float p0 = b0, p1 = b1;
+                    p0 = fmaf(e[n][0], w00, p0);
+                    p1 = fmaf(e[n][0], w01, p1);
+                    p0 = fmaf(e[n][1], w10, p0);
+                    p1 = fmaf(e[n][1], w11, p1);
+                    p0 = fmaf(e[n][2], w20, p0);
+                    p1 = fmaf(e[n][2], w21, p1);
+                    p0 = fmaf(e[n][3], w30, p0);
+                    p1 = fmaf(e[n][3], w31, p1);
+                    const float sf = sRow[n * GS + f];
+                    a0[n] = fmaf(sf, gn_tanh(p0), a0[n]);
+                    a1[n] = fmaf(sf, gn_tanh(p1), a1[n]);
                 }
-                sX[n * GH + lane] = gn_tanh(a0);
-                sX[n * GH + lane + 32] = gn_tanh(a1);
             }
         }
-        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < GN; ++n) {
+            if (g.need[n]) {
+                sX[n * GH + lane] = gn_tanh(a0[n]);
+                sX[n * GH + lane + 32] = gn_tanh(a1[n]);
+            }
+        }
+        __syncwarp();      // x of all needed nodes visible; the staged state is no longer needed
 
-        // ---- MPNN for the controlled node -----------------------------------------------------------------------------
+        // ---- MPNN for the controlled node: mean of the senders once per row (into the free staging buffer) ----------------
         const float inv_cnt = g.cnt > 0 ? 1.f / (float)g.cnt : 0.f;
+        {
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < GN; ++n)
+                if (g.is_snd[n]) {
+                    m0 += sX[n * GH + lane];
+                    m1 += sX[n * GH + lane + 32];
+                }
+            sRow[lane] = m0 * inv_cnt;
+            sRow[lane + 32] = m1 * inv_cnt;
+        }
+        __syncwarp();
         const float* xs = sX + g.idx * GH;
         float y0 = 0.f, y1 = 0.f;
 #pragma unroll 8
         for (int hh = 0; hh < GH; ++hh) {
             const float xi = xs[hh];
-            float sm = 0.f;
-#pragma unroll
-            for (int n = 0; n < GN; ++n)
-                if (g.is_snd[n]) sm += sX[n * GH + hh];
-            const float xm = sm * inv_cnt;
+            const float xm = sRow[hh];
             y0 = fmaf(xi, sWu[hh * GH + lane], y0);
             y1 = fmaf(xi, sWu[hh * GH + lane + 32], y1);
             y0 = fmaf(xm, sWm[hh * GH + lane], y0);
@@ -478,7 +502,7 @@ extern "C" int ddrl_graphnet_num_params(int num_outputs) {
 // forward schedule: 0 = one row per CTA (graphnet_kernel<false>), 1 = one row per warp (graphnet_fwd_warp_kernel);
 // -1 = default, which the environment variable DDRL_GN_FWD_VARIANT may override (A/B timing without a rebuild)
 static int g_gn_fwd_variant = -1;
-constexpr int GN_FWD_DEFAULT = 1;   // measured: configs[3] iteration 75.5 -> 51.9 ms (profiles/README.md)
+constexpr int GN_FWD_DEFAULT = 1;   // measured: configs[3] iteration 75.5 -> 47.5 ms (profiles/README.md)
 static int gn_fwd_variant() {
     if (g_gn_fwd_variant >= 0) return g_gn_fwd_variant;
     static int from_env = [] {
