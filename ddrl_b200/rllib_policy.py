@@ -16,8 +16,9 @@ RLlib's execution plan (`ray/rllib/agents/ppo/ppo.py` `execution_plan`, driven b
 `{policy_id: {column: array}}` in, `{policy_id: {"learner_stats": {...}}}` out — the shape `RolloutWorker.learn_on_batch`
 returns), `get_weights` / `set_weights` with the TF variable names of the reference checkpoints, and
 `update_environment_after_epoch` for the `on_train_result` curriculum callback
-(train_experiment_1_architecture_on_flat.py:171-178).  With ray installed a `Policy` subclass forwards these five methods
-one to one; ray is absent in this image, so that subclass is not shipped.
+(train_experiment_1_architecture_on_flat.py:171-178).  With ray installed the train op of a custom execution plan calls
+`learn_on_batch` on the concatenated MultiAgentBatch; ray is absent in this image, so that glue is shown in
+INTEGRATION.md §4.1, not shipped.
 
 Everything that computes runs on the GPU through `learner.FCNetLearner` / the C ABI; this module only validates and
 stacks host arrays, draws the permutations RLlib would draw (numpy RandomState) and copies to / from the device."""
