@@ -71,3 +71,15 @@ def test_curriculum_schedule_equals_the_reference_callback():
     got = [RP.curriculum_smoothness(t, lo, hi, g["range_last_timestep"], rng.rand()) for t in g["timesteps_total"]]
     assert got == g["smoothness"]                      # float64 on both sides, same operation order: bit equal
     assert all(hi <= s <= lo for s in got)
+
+
+def test_rllib_surface_orchestration_with_oracle_mocked_kernels():
+    """tests/host_dryrun.py: the GPU tests of the RLlib surface executed on CPU with every kernel replaced by the oracle —
+    host orchestration only (own process: it monkeypatches torch)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_dryrun.py")], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert out.stdout.split() == ["test1", "fp32", "ok", "test2", "fp32", "ok", "test1", "tc", "ok", "test2", "tc", "ok"]
