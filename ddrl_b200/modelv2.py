@@ -100,6 +100,54 @@ def fcnet_shapes(D: int, num_outputs: int):
             ("value_out/kernel", (H, 1)), ("value_out/bias", (1,))]
 
 
+def fcnet_variant_shapes(D: int, num_outputs: int, vf_share_layers: bool = False, free_log_std: bool = False):
+    """Variables of the FCNet in the order the reference creates them for its two optional layouts
+    (models/fcnet_glorot_uniform_init.py): `free_log_std` registers a state-independent `log_std[A]` FIRST and halves the
+    width of fc_out (:30-36, 85-93); `vf_share_layers` drops the fc_value_* layers — value_out then reads the policy
+    branch's last hidden layer (:95-113)."""
+    H = K.HIDDEN
+    n_out = num_outputs // 2 if free_log_std else num_outputs
+    out = [("log_std", (n_out,))] if free_log_std else []
+    for i, fan_in in ((1, D), (2, H)):
+        out += [(f"fc_{i}/kernel", (fan_in, H)), (f"fc_{i}/bias", (H,))]
+        if not vf_share_layers:
+            out += [(f"fc_value_{i}/kernel", (fan_in, H)), (f"fc_value_{i}/bias", (H,))]
+    out += [("fc_out/kernel", (H, n_out)), ("fc_out/bias", (n_out,)), ("value_out/kernel", (H, 1)), ("value_out/bias", (1,))]
+    return out
+
+
+def fcnet_layout_map(D: int, num_outputs: int, vf_share_layers: bool = False, free_log_std: bool = False) -> torch.Tensor:
+    """int64 [NP_kernel]: for every element of the kernels' parameter layout (`fcnet_shapes`, two separate 64-64 branches,
+    fc_out of width 2A) the index of the model variable that supplies it, or n_model for a constant zero.
+
+    The kernels always evaluate two branches and a state-dependent log-std; the optional layouts are the same arithmetic
+    on tied / constant weights:
+      vf_share_layers: fc_value_i := fc_i, so the "value branch" recomputes the policy branch's hidden layers and
+                       value_out reads h2 — exactly the shared-layer network; gradients of the two copies add up;
+      free_log_std:    fc_out/kernel = [W | 0], fc_out/bias = [b | log_std]: logits = [h2 W + b, log_std] for every row.
+    `theta_kernel = cat(theta_model, [0])[map]`, so autograd's index-select backward performs the gradient tying."""
+    model = fcnet_variant_shapes(D, num_outputs, vf_share_layers, free_log_std)
+    off, o = {}, 0
+    for name, shp in model:
+        off[name] = o
+        o += int(np.prod(shp))
+    n_model = o
+    H, n_out = K.HIDDEN, (num_outputs // 2 if free_log_std else num_outputs)
+    parts = []
+    for name, shp in fcnet_shapes(D, num_outputs):
+        n = int(np.prod(shp))
+        src = name.replace("fc_value_", "fc_") if vf_share_layers else name
+        if free_log_std and name == "fc_out/kernel":
+            idx = torch.full((H, num_outputs), n_model, dtype=torch.int64)
+            idx[:, :n_out] = off[src] + torch.arange(H * n_out).reshape(H, n_out)
+            parts.append(idx.reshape(-1))
+        elif free_log_std and name == "fc_out/bias":
+            parts.append(torch.cat([off[src] + torch.arange(n_out), off["log_std"] + torch.arange(n_out)]))
+        else:
+            parts.append(off[src] + torch.arange(n))
+    return torch.cat(parts)
+
+
 def fcnet_init_flat(D: int, num_outputs: int, gen: Optional[torch.Generator] = None) -> torch.Tensor:
     """Flat float32 parameter vector of one FCNet policy initialised like the reference (GlorotUniformScaled: scale 1.0
     for the hidden layers, 0.01 for fc_out / value_out, zero biases; models/fcnet_glorot_uniform_init.py:48-113)."""
@@ -115,8 +163,9 @@ def graphnet_shapes(num_outputs: int):
 
 
 def _check_fcnet_config(model_config: dict, who: str):
-    """The kernels implement the configuration of every published run (Results/**/params.json): hiddens [64, 64],
-    tanh, separate value network, state-dependent log-std, final linear layer.  Anything else fails loudly."""
+    """The kernels implement hiddens [64, 64], tanh and a final linear layer (every published run,
+    Results/**/params.json); `vf_share_layers` and `free_log_std` are served through `fcnet_layout_map`.  Anything else
+    fails loudly."""
     hid = list(model_config.get("fcnet_hiddens", [64, 64]))
     act = model_config.get("fcnet_activation", "tanh")
     bad = []
@@ -126,10 +175,6 @@ def _check_fcnet_config(model_config: dict, who: str):
         bad.append(f"fcnet_activation={act!r} (supported: 'tanh')")
     if model_config.get("no_final_linear"):
         bad.append("no_final_linear=True")
-    if model_config.get("free_log_std"):
-        bad.append("free_log_std=True")
-    if model_config.get("vf_share_layers") and not model_config.get("_ddrl_allow_vf_share_key", True):
-        bad.append("vf_share_layers=True")
     if bad:
         raise DDRLError(f"{who}: unsupported model_config for the sm_100a kernels: " + "; ".join(bad))
 
@@ -222,18 +267,29 @@ class FullyConnectedNetwork_GlorotUniformInitializer(_DDRLModel):
         if num_outputs % 2:
             raise DDRLError("num_outputs must be 2 * action_dim (DiagGaussian)")
         self.A = num_outputs // 2
-        self._params = _FlatParams(fcnet_shapes(self.D, num_outputs))
-        if self._params.numel != K.fcnet_num_params(self.D, self.A):
+        self.vf_share_layers = bool(model_config.get("vf_share_layers"))
+        self.free_log_std = bool(model_config.get("free_log_std"))
+        self._params = _FlatParams(fcnet_variant_shapes(self.D, num_outputs, self.vf_share_layers, self.free_log_std))
+        self._map = None                  # optional layouts: model variables -> the kernels' two-branch layout
+        if self.vf_share_layers or self.free_log_std:
+            self._map = fcnet_layout_map(self.D, num_outputs, self.vf_share_layers, self.free_log_std).cuda()
+        if (self._map.numel() if self._map is not None else self._params.numel) != K.fcnet_num_params(self.D, self.A):
             raise DDRLError("parameter layout mismatch with libddrl_b200.so")
         gen = model_config.get("_ddrl_generator")
         flat = self._params.init_host(gen, small=("fc_out", "value_out"))
         self.theta = torch.nn.Parameter(flat.cuda()) if _HAVE_RAY else flat.cuda().requires_grad_(True)
         self.register_variables(self._params.views(self.theta.detach(), prefix=f"{name}/" if name else ""))
 
+    def kernel_parameters(self) -> torch.Tensor:
+        """The flat vector in the kernels' layout (= `theta` for the default layout), differentiable w.r.t. `theta`."""
+        if self._map is None:
+            return self.theta
+        return torch.cat([self.theta, self.theta.new_zeros(1)])[self._map]
+
     def forward(self, input_dict, state, seq_lens):
         obs = input_dict["obs_flat"]
         obs = torch.as_tensor(obs, dtype=torch.float32, device=self.theta.device).contiguous()
-        model_out, self._value_out = _FCNetFn.apply(self.theta, obs, self.A)
+        model_out, self._value_out = _FCNetFn.apply(self.kernel_parameters(), obs, self.A)
         return model_out, state
 
 
@@ -297,7 +353,7 @@ class FullyConnectedNetwork_Coupling_GlorotUniformInitializer(FullyConnectedNetw
         dev = self.theta.device
         obs = torch.as_tensor(obs, dtype=torch.float32, device=dev).contiguous()
         node_idx = torch.as_tensor(node_idx, device=dev).reshape(-1).to(torch.int32).contiguous()
-        logits, self._value_out = _FCNetFn.apply(self.theta, obs, self.A)
+        logits, self._value_out = _FCNetFn.apply(self.kernel_parameters(), obs, self.A)
         if logits.requires_grad:
             # keep autograd intact: the multiply by a per-row constant is expressed on the graph
             coeff = torch.cat([self.leg_coupling.coupling, torch.ones(4, self.A, device=dev)], dim=1)[node_idx.long()]

@@ -148,3 +148,32 @@ def test_contact_force_tables_match_the_reference_env_constructors():
                 dense[j] += np.asarray(wt).reshape(-1)[0]
             assert np.array_equal(table[i], dense)
     assert ARCHITECTURES["QuantrupedMultiEnv_FullyDecentral"].action_table().tolist() == [[2, 3], [4, 5], [6, 7], [0, 1]]
+
+
+@pytest.mark.parametrize("D,A", [(19, 2), (43, 8)])
+@pytest.mark.parametrize("vf_share,free_std", [(True, False), (False, True), (True, True), (False, False)])
+def test_fcnet_optional_layouts_map_onto_the_two_branch_kernel_layout(D, A, vf_share, free_std):
+    """`vf_share_layers` / `free_log_std` (models/fcnet_glorot_uniform_init.py:30-36,85-113) are served by the kernels'
+    fixed two-branch layout through `fcnet_layout_map`: the oracle's variant forward on the model's own variables equals its
+    standard forward on the mapped vector, and autograd through the index-select ties the gradients."""
+    import torch
+    import oracle.ddrl_oracle as O
+    from ddrl_b200.modelv2 import fcnet_layout_map, fcnet_variant_shapes
+    shapes = fcnet_variant_shapes(D, 2 * A, vf_share, free_std)
+    assert shapes == O.fcnet_shapes(D, 2 * A, (64, 64), vf_share, free_std)          # the reference's variable order
+    g = torch.Generator().manual_seed(D + A)
+    theta = O.fcnet_init(D, 2 * A, g, vf_share_layers=vf_share, free_log_std=free_std, dtype=torch.float64)
+    theta = (theta + 0.05 * torch.randn(theta.shape, generator=g, dtype=torch.float64)).requires_grad_(True)
+    m = fcnet_layout_map(D, 2 * A, vf_share, free_std)
+    assert m.numel() == O.n_params(O.fcnet_shapes(D, 2 * A)) and int(m.max()) <= theta.numel() and int(m.min()) >= 0
+    if not (vf_share or free_std):
+        assert torch.equal(m, torch.arange(theta.numel()))
+    full = torch.cat([theta, theta.new_zeros(1)])[m]
+    x = torch.randn(50, D, generator=g, dtype=torch.float64)
+    lg_v, v_v = O.fcnet_forward(theta, x, 2 * A, vf_share_layers=vf_share, free_log_std=free_std)
+    lg_f, v_f = O.fcnet_forward(full, x, 2 * A)
+    assert torch.equal(lg_v, lg_f) and torch.equal(v_v, v_f)
+    wl, wv = torch.randn(50, 2 * A, generator=g, dtype=torch.float64), torch.randn(50, generator=g, dtype=torch.float64)
+    (g_v,) = torch.autograd.grad((lg_v * wl).sum() + (v_v * wv).sum(), theta, retain_graph=True)
+    (g_f,) = torch.autograd.grad((lg_f * wl).sum() + (v_f * wv).sum(), theta)
+    assert float((g_v - g_f).abs().max()) <= 1e-12 * float(g_v.abs().max())
