@@ -73,6 +73,11 @@ PROTOTYPES = {
                                  C.c_int, c_stream]),
     "ddrl_graphnet_num_params": (C.c_int, [C.c_int]),
     "ddrl_graphnet_set_variant": (C.c_int, [C.c_int]),
+    "ddrl_graphnet_train_ws_bytes": (C.c_int64, [C.c_int64]),
+    "ddrl_graphnet_train_stat_parts": (C.c_int, [C.c_int64]),
+    "ddrl_graphnet_train_step": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+                                           C.c_int64, C.c_int, c_f32p, C.POINTER(PPOHyper), C.c_int, C.c_void_p, c_f32p, c_f64p,
+                                           c_stream]),
     "ddrl_graphnet_forward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p,
                                         c_stream]),
     "ddrl_graphnet_backward": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int,

@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ppo_loss.cuh"
 
 namespace ddrl {
 
@@ -457,6 +458,336 @@ graphnet_fwd_warp_kernel(const float* __restrict__ theta, const int32_t* __restr
     }
 }
 
+// ---- SGD step in two launches (opt-in, ddrl_graphnet_train_step) ----------------------------------------------------------
+// The three-kernel step (forward 125 us, loss, row-per-CTA backward 520 us per 16 384 rows) recomputes the forward inside
+// the backward with two block barriers per row.  Split by what parallelises how:
+//   K1 graphnet_train_fwd_kernel   one WARP per row (the forward kernel above) + the row's PPO loss gradient + the backward
+//                                  down to the layer inputs; leaves per (net, row) a record {x_idx, mean of senders, dpre, y,
+//                                  dpx[node], dout} in a workspace (2.1 KB; L2 / HBM streamed once) and per-CTA loss statistics;
+//   K2 graphnet_train_acc_kernel   the weight gradients are rank-1 updates summed over rows: thread (h, fs) owns fixed
+//                                  register accumulators (the layout of graphnet_kernel<true>) and streams the records with
+//                                  no barrier in the row loop; it re-evaluates only ITS 5 hyper-network columns per node.
+// Arithmetic per element is that of graphnet_kernel<true> + ppo_loss_grad_kernel.
+constexpr int GTR_XI = 0, GTR_XM = GH, GTR_DPRE = 2 * GH, GTR_Y = 3 * GH, GTR_DPX = 4 * GH, GTR_DOUT = 8 * GH;
+constexpr int GTR_REC = 8 * GH + GMAXO;       // 528 floats per (net, row)
+constexpr int GWS = GH + 1;                   // padded stride of Wu / Wm: conflict-free by row AND by column
+constexpr int GTF_SMEM_FLOATS = GE * GF * GH + GF * GH + 2 * GH * GWS + GH * GWF_WO + GMAXO +
+                                GWF_WARPS * (GWF_ROW + GN * GH + 2 * GMAXO);
+
+__global__ void __launch_bounds__(GWF_NT, 2)
+graphnet_train_fwd_kernel(const float* __restrict__ theta, const int32_t* __restrict__ node_idx,
+                          const float* __restrict__ state, const float* __restrict__ adj,
+                          const float* __restrict__ actions, const float* __restrict__ old_logits,
+                          const float* __restrict__ old_logp, const float* __restrict__ vf_preds,
+                          const float* __restrict__ adv, const float* __restrict__ vtarg, int64_t B, int A,
+                          const float* __restrict__ kl_coeff, const ddrl_ppo_hyper hp, float* __restrict__ rec,
+                          double* __restrict__ stat_part) {
+    extern __shared__ __align__(16) float gsm[];
+    __shared__ double sStat[GWF_WARPS][DDRL_NSTAT];
+    float* sWe = gsm;
+    float* sbe = sWe + GE * GF * GH;
+    float* sWu = sbe + GF * GH;                 // [GH][GWS]
+    float* sWm = sWu + GH * GWS;
+    float* sWo = sWm + GH * GWS;                // [GH][GWF_WO]
+    float* sbo = sWo + GH * GWF_WO;
+    float* sRowAll = sbo + GMAXO;               // [warps][GWF_ROW]
+    float* sXAll = sRowAll + GWF_WARPS * GWF_ROW;   // [warps][GN][GH]
+    float* sOAll = sXAll + GWF_WARPS * GN * GH;     // [warps][2][GMAXO]: model outputs, their loss gradient
+
+    const int net = blockIdx.y;
+    const int O = net == 0 ? 2 * A : 1;
+    const GnOffsets o = gn_offsets(O);
+    const float* th = theta + (net == 0 ? 0 : gn_offsets(2 * A).NP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < GE * GF * GH; i += GWF_NT) sWe[i] = th[o.We + i];
+    for (int i = tid; i < GF * GH; i += GWF_NT) sbe[i] = th[o.be + i];
+    for (int i = tid; i < GH * GH; i += GWF_NT) {
+        const int r = i >> 6, c = i & 63;
+        sWu[r * GWS + c] = th[o.Wu + i];
+        sWm[r * GWS + c] = th[o.Wm + i];
+    }
+    for (int i = tid; i < GH * GMAXO; i += GWF_NT) {
+        const int hh = i / GMAXO, q = i - hh * GMAXO;
+        sWo[hh * GWF_WO + q] = q < O ? th[o.Wo + hh * O + q] : 0.f;
+    }
+    if (tid < GMAXO) sbo[tid] = tid < O ? th[o.bo + tid] : 0.f;
+    __syncthreads();
+
+    float* sRow = sRowAll + warp * GWF_ROW;
+    float* sX = sXAll + warp * GN * GH;
+    float* sO = sOAll + warp * 2 * GMAXO;
+    float* sDo = sO + GMAXO;
+    float* recn = rec + (int64_t)net * B * GTR_REC;
+    const float klc = kl_coeff[0];
+    double acc[DDRL_NSTAT];
+#pragma unroll
+    for (int i = 0; i < DDRL_NSTAT; ++i) acc[i] = 0.0;
+
+    const int64_t stride = (int64_t)gridDim.x * GWF_WARPS;
+    for (int64_t b = (int64_t)blockIdx.x * GWF_WARPS + warp; b < B; b += stride) {
+        for (int i = lane; i < GN * GS; i += 32) sRow[i] = state[b * GN * GS + i];
+        if (lane < GN * GN) sRow[GN * GS + lane] = adj[b * GN * GN + lane];
+        if (lane == GN * GN) sRow[GN * GS + GN * GN] = __int_as_float(node_idx[b]);
+        __syncwarp();
+        const GnRow g = gn_row(sRow);
+
+        // ---- forward: identical to graphnet_fwd_warp_kernel -------------------------------------------------------------
+        float e[GN][GE], a0[GN], a1[GN];
+#pragma unroll
+        for (int n = 0; n < GN; ++n) {
+            a0[n] = 0.f;
+            a1[n] = 0.f;
+#pragma unroll
+            for (int q = 0; q < GE; ++q) e[n][q] = sRow[n * GS + GF + q];
+        }
+#pragma unroll
+        for (int f = 0; f < GF; ++f) {
+            const int j = f * GH + lane;
+            const float b0 = sbe[j], b1 = sbe[j + 32];
+            const float w00 = sWe[j], w01 = sWe[j + 32];
+            const float w10 = sWe[GF * GH + j], w11 = sWe[GF * GH + j + 32];
+            const float w20 = sWe[2 * GF * GH + j], w21 = sWe[2 * GF * GH + j + 32];
+            const float w30 = sWe[3 * GF * GH + j], w31 = sWe[3 * GF * GH + j + 32];
+#pragma unroll
+            for (int n = 0; n < GN; ++n) {
+                if (g.need[n]) {
+                    float p0 = b0, p1 = b1;
+                    p0 = fmaf(e[n][0], w00, p0);
+                    p1 = fmaf(e[n][0], w01, p1);
+                    p0 = fmaf(e[n][1], w10, p0);
+                    p1 = fmaf(e[n][1], w11, p1);
+                    p0 = fmaf(e[n][2], w20, p0);
+                    p1 = fmaf(e[n][2], w21, p1);
+                    p0 = fmaf(e[n][3], w30, p0);
+                    p1 = fmaf(e[n][3], w31, p1);
+                    const float sf = sRow[n * GS + f];
+                    a0[n] = fmaf(sf, gn_tanh(p0), a0[n]);
+                    a1[n] = fmaf(sf, gn_tanh(p1), a1[n]);
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < GN; ++n) {
+            if (g.need[n]) {
+                sX[n * GH + lane] = gn_tanh(a0[n]);
+                sX[n * GH + lane + 32] = gn_tanh(a1[n]);
+            }
+        }
+        __syncwarp();
+        const float inv_cnt = g.cnt > 0 ? 1.f / (float)g.cnt : 0.f;
+        {
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < GN; ++n)
+                if (g.is_snd[n]) {
+                    m0 += sX[n * GH + lane];
+                    m1 += sX[n * GH + lane + 32];
+                }
+            sRow[lane] = m0 * inv_cnt;              // xm in sRow[0..64); sRow[64..128) will take dpre
+            sRow[lane + 32] = m1 * inv_cnt;
+        }
+        __syncwarp();
+        const float* xs = sX + g.idx * GH;
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll 8
+        for (int hh = 0; hh < GH; ++hh) {
+            const float xi = xs[hh];
+            const float xm = sRow[hh];
+            y0 = fmaf(xi, sWu[hh * GWS + lane], y0);
+            y1 = fmaf(xi, sWu[hh * GWS + lane + 32], y1);
+            y0 = fmaf(xm, sWm[hh * GWS + lane], y0);
+            y1 = fmaf(xm, sWm[hh * GWS + lane + 32], y1);
+        }
+        y0 = gn_tanh(y0);
+        y1 = gn_tanh(y1);
+#pragma unroll
+        for (int q = 0; q < GMAXO; ++q) {
+            if (q < O) {
+                float v = fmaf(y0, sWo[lane * GWF_WO + q], y1 * sWo[(lane + 32) * GWF_WO + q]);
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+                if (lane == q) sO[q] = v + sbo[q];
+            }
+        }
+        __syncwarp();
+
+        // ---- PPO loss gradient of this row w.r.t. this net's outputs (policy part: actor CTAs, value part: critic CTAs) --
+        if (lane == 0) {
+            double s[DDRL_NSTAT];
+#pragma unroll
+            for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
+            if (net == 0)
+                ppo_row_policy(sO, A, actions + b * A, old_logits + b * 2 * A, old_logp[b], adv[b], klc, hp.clip_param,
+                               hp.entropy_coeff, hp.inv_global_mb, sDo, s);
+            else
+                sDo[0] = ppo_row_value(sO[0], vf_preds[b], vtarg[b], hp.vf_clip_param, hp.vf_loss_coeff, hp.inv_global_mb, s);
+#pragma unroll
+            for (int i = 0; i < DDRL_NSTAT; ++i) acc[i] += s[i];
+        }
+        __syncwarp();
+
+        // ---- backward to the layer inputs ---------------------------------------------------------------------------------
+        float dy0 = 0.f, dy1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < GMAXO; ++q) {
+            if (q < O) {
+                const float d = sDo[q];
+                dy0 = fmaf(d, sWo[lane * GWF_WO + q], dy0);
+                dy1 = fmaf(d, sWo[(lane + 32) * GWF_WO + q], dy1);
+            }
+        }
+        const float dp0 = dy0 * (1.f - y0 * y0), dp1 = dy1 * (1.f - y1 * y1);
+        float* rr = recn + b * GTR_REC;
+        rr[GTR_XI + lane] = xs[lane];
+        rr[GTR_XI + lane + 32] = xs[lane + 32];
+        rr[GTR_XM + lane] = sRow[lane];
+        rr[GTR_XM + lane + 32] = sRow[lane + 32];
+        rr[GTR_DPRE + lane] = dp0;
+        rr[GTR_DPRE + lane + 32] = dp1;
+        rr[GTR_Y + lane] = y0;
+        rr[GTR_Y + lane + 32] = y1;
+        if (lane < GMAXO) rr[GTR_DOUT + lane] = lane < O ? sDo[lane] : 0.f;
+        sRow[64 + lane] = dp0;
+        sRow[96 + lane] = dp1;
+        __syncwarp();
+        float dxi0 = 0.f, dxi1 = 0.f, dxm0 = 0.f, dxm1 = 0.f;
+#pragma unroll 8
+        for (int hh = 0; hh < GH; ++hh) {
+            const float d = sRow[64 + hh];
+            dxi0 = fmaf(sWu[lane * GWS + hh], d, dxi0);
+            dxi1 = fmaf(sWu[(lane + 32) * GWS + hh], d, dxi1);
+            dxm0 = fmaf(sWm[lane * GWS + hh], d, dxm0);
+            dxm1 = fmaf(sWm[(lane + 32) * GWS + hh], d, dxm1);
+        }
+        dxm0 *= inv_cnt;
+        dxm1 *= inv_cnt;
+#pragma unroll
+        for (int n = 0; n < GN; ++n) {
+            float q0 = 0.f, q1 = 0.f;
+            if (g.need[n]) {
+                const float dx0 = (n == g.idx ? dxi0 : 0.f) + (g.is_snd[n] ? dxm0 : 0.f);
+                const float dx1 = (n == g.idx ? dxi1 : 0.f) + (g.is_snd[n] ? dxm1 : 0.f);
+                const float x0 = sX[n * GH + lane], x1 = sX[n * GH + lane + 32];
+                q0 = dx0 * (1.f - x0 * x0);
+                q1 = dx1 * (1.f - x1 * x1);
+            }
+            rr[GTR_DPX + n * GH + lane] = q0;
+            rr[GTR_DPX + n * GH + lane + 32] = q1;
+        }
+        __syncwarp();      // every lane is done with sRow / sX / sO before the next row overwrites them
+    }
+
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < DDRL_NSTAT; ++i) sStat[warp][i] = acc[i];
+    __syncthreads();
+    if (tid < DDRL_NSTAT) {
+        double t = 0.0;
+        for (int w = 0; w < GWF_WARPS; ++w) t += sStat[w][tid];
+        stat_part[((int64_t)net * gridDim.x + blockIdx.x) * DDRL_NSTAT + tid] = t;
+    }
+}
+
+__global__ void __launch_bounds__(GT2, 1)
+graphnet_train_acc_kernel(const float* __restrict__ theta, const int32_t* __restrict__ node_idx,
+                          const float* __restrict__ state, const float* __restrict__ adj, const float* __restrict__ rec,
+                          int64_t B, int A, float* __restrict__ grad_part) {
+    const int net = blockIdx.y;
+    const int O = net == 0 ? 2 * A : 1;
+    const GnOffsets oa = gn_offsets(2 * A);
+    const GnOffsets o = gn_offsets(O);
+    const int net_base = net == 0 ? 0 : oa.NP;
+    const float* th = theta + net_base;
+    const int tid = threadIdx.x, h = tid & (GH - 1), fs = tid >> 6;   // a warp = 32 consecutive hidden units, one fs
+    const int G = gridDim.x, bx = blockIdx.x;
+
+    float We[GK][GE], be[GK];
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+        const int f = fs + 4 * k;
+        const bool ok = f < GF;
+#pragma unroll
+        for (int q = 0; q < GE; ++q) We[k][q] = ok ? th[o.We + q * GF * GH + f * GH + h] : 0.f;
+        be[k] = ok ? th[o.be + f * GH + h] : 0.f;
+    }
+    float gWe[GK][GE], gbe[GK], gWu[16], gWm[16], gWo[GMAXO], gbo = 0.f;
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+        gbe[k] = 0.f;
+#pragma unroll
+        for (int q = 0; q < GE; ++q) gWe[k][q] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { gWu[i] = 0.f; gWm[i] = 0.f; }
+#pragma unroll
+    for (int q = 0; q < GMAXO; ++q) gWo[q] = 0.f;
+
+    const float* recn = rec + (int64_t)net * B * GTR_REC;
+    for (int64_t b = bx; b < B; b += G) {
+        const float* rr = recn + b * GTR_REC;
+        const int idx = min(max(node_idx[b], 0), GN - 1);
+        const float dpre = rr[GTR_DPRE + h], y = rr[GTR_Y + h];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            gWu[i] = fmaf(rr[GTR_XI + 4 * i + fs], dpre, gWu[i]);
+            gWm[i] = fmaf(rr[GTR_XM + 4 * i + fs], dpre, gWm[i]);
+        }
+#pragma unroll
+        for (int q = 0; q < GMAXO; ++q)
+            if (q < O) gWo[q] = fmaf(y, rr[GTR_DOUT + q], gWo[q]);
+        if (tid < O) gbo += rr[GTR_DOUT + tid];
+#pragma unroll
+        for (int n = 0; n < GN; ++n) {
+            const bool need = n == idx || adj[b * GN * GN + n * GN + idx] != 0.f;      // block-uniform
+            if (need) {
+                const float dpx = rr[GTR_DPX + n * GH + h];
+                const float* st = state + b * GN * GS + n * GS;
+                const float e0 = st[GF], e1 = st[GF + 1], e2 = st[GF + 2], e3 = st[GF + 3];
+#pragma unroll
+                for (int k = 0; k < GK; ++k) {
+                    const int f = fs + 4 * k;
+                    if (f < GF) {
+                        float pre = be[k];
+                        pre = fmaf(e0, We[k][0], pre);
+                        pre = fmaf(e1, We[k][1], pre);
+                        pre = fmaf(e2, We[k][2], pre);
+                        pre = fmaf(e3, We[k][3], pre);
+                        const float w = gn_tanh(pre);
+                        const float dpw = dpx * st[f] * (1.f - w * w);
+                        gWe[k][0] = fmaf(e0, dpw, gWe[k][0]);
+                        gWe[k][1] = fmaf(e1, dpw, gWe[k][1]);
+                        gWe[k][2] = fmaf(e2, dpw, gWe[k][2]);
+                        gWe[k][3] = fmaf(e3, dpw, gWe[k][3]);
+                        gbe[k] += dpw;
+                    }
+                }
+            }
+        }
+    }
+
+    float* gp = grad_part + (int64_t)bx * ((oa.NP + gn_offsets(1).NP + 3) & ~3) + net_base;
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+        const int f = fs + 4 * k;
+        if (f < GF) {
+#pragma unroll
+            for (int q = 0; q < GE; ++q) gp[o.We + q * GF * GH + f * GH + h] = gWe[k][q];
+            gp[o.be + f * GH + h] = gbe[k];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        gp[o.Wu + (4 * i + fs) * GH + h] = gWu[i];
+        gp[o.Wm + (4 * i + fs) * GH + h] = gWm[i];
+    }
+    if (fs == 0)
+#pragma unroll
+        for (int q = 0; q < GMAXO; ++q)
+            if (q < O) gp[o.Wo + h * O + q] = gWo[q];
+    if (tid < O) gp[o.bo + tid] = gbo;
+}
+
 // ---- GCN layer: y[b][n][u] = act(sum_f (sum_m An[n][m] x[b][m][f]) W[f][u] + bias[u]) ---------------------
 __global__ void gcn_forward_kernel(const float* __restrict__ x, const float* __restrict__ adj, const float* __restrict__ W,
                                    const float* __restrict__ bias, int64_t B, int F, int U, int act,
@@ -562,6 +893,48 @@ extern "C" int ddrl_graphnet_backward(const float* theta, const int32_t* node_id
     graphnet_kernel<true><<<dim3(ctas, 2), GT2, 0, (cudaStream_t)stream>>>(theta, node_idx, state, adj, dlogits, dvalue, B,
                                                                           A, nullptr, nullptr, grad_part);
     DDRL_CHECK_LAUNCH("graphnet_backward");
+    return DDRL_OK;
+}
+
+static int gn_train_fwd_ctas(int64_t B) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<int64_t>(1, std::min<int64_t>((B + GWF_WARPS - 1) / GWF_WARPS, sms));   // 2 CTAs per SM over the two nets
+}
+
+extern "C" int64_t ddrl_graphnet_train_ws_bytes(int64_t B) {
+    return B < 0 ? DDRL_E_BADARG : 2 * B * (int64_t)GTR_REC * (int64_t)sizeof(float);
+}
+
+extern "C" int ddrl_graphnet_train_stat_parts(int64_t B) {
+    return B < 1 ? DDRL_E_BADARG : 2 * gn_train_fwd_ctas(B);
+}
+
+extern "C" int ddrl_graphnet_train_step(const float* theta, const int32_t* node_idx, const float* state, const float* adj,
+                                        const float* actions, const float* old_logits, const float* old_logp,
+                                        const float* vf_preds, const float* adv, const float* vtarg, int64_t B, int A,
+                                        const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas, void* ws,
+                                        float* grad_part, double* stat_part, void* stream) {
+    DDRL_REQUIRE(theta && node_idx && state && adj && actions && old_logits && old_logp && vf_preds && adv && vtarg &&
+                     kl_coeff && hyper && ws && grad_part && stat_part,
+                 DDRL_E_BADARG, "graphnet_train_step: null pointer");
+    DDRL_REQUIRE(B >= 1 && ctas >= 1, DDRL_E_BADARG, "graphnet_train_step: bad B/ctas");
+    DDRL_REQUIRE(A >= 1 && A <= DDRL_MAX_ACT, DDRL_E_UNSUPPORTED_SHAPE, "graphnet_train_step: unsupported A=%d", A);
+    static bool attr_set = false;
+    const size_t smem = (size_t)GTF_SMEM_FLOATS * sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(graphnet_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DDRL_REQUIRE(e == cudaSuccess, DDRL_E_CUDA, "graphnet_train_step: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    graphnet_train_fwd_kernel<<<dim3(gn_train_fwd_ctas(B), 2), GWF_NT, smem, st>>>(
+        theta, node_idx, state, adj, actions, old_logits, old_logp, vf_preds, adv, vtarg, B, A, kl_coeff, *hyper,
+        static_cast<float*>(ws), stat_part);
+    DDRL_CHECK_LAUNCH("graphnet_train_step (forward + loss)");
+    graphnet_train_acc_kernel<<<dim3(ctas, 2), GT2, 0, st>>>(theta, node_idx, state, adj, static_cast<const float*>(ws), B, A,
+                                                            grad_part);
+    DDRL_CHECK_LAUNCH("graphnet_train_step (weight gradients)");
     return DDRL_OK;
 }
 

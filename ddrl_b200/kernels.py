@@ -368,6 +368,42 @@ def ppo_loss_grad(logits, value, actions, old_logits, old_logp, vf_preds, adv, v
         "ppo_loss_grad")
 
 
+def graphnet_train_stat_parts(B: int) -> int:
+    n = _lib.load().ddrl_graphnet_train_stat_parts(int(B))
+    if n < 0:
+        raise DDRLError(f"graphnet_train_stat_parts: bad B={B}")
+    return n
+
+
+def graphnet_train_step(theta, node_idx, state, adj, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, kl_coeff,
+                        hyper: PPOHyper, ctas: int, grad_part, stat_part, ws: Optional[torch.Tensor] = None):
+    """One GraphNet SGD step in two launches (forward + PPO loss + backward to the layer inputs per row, then the weight
+    gradients): theta [NP], node_idx [B] i32, state [B,4,23], adj [B,4,4], actions [B,A], old_logits [B,2A],
+    old_logp / vf_preds / adv / vtarg [B] -> grad_part [ctas, NPs] f32, stat_part [graphnet_train_stat_parts(B), 8] f64.
+    ``ws``: uint8 workspace of ddrl_graphnet_train_ws_bytes(B) bytes (allocated when None).  Returns ws for reuse."""
+    lib = _lib.load()
+    B = state.shape[0]
+    f32 = torch.float32
+    if tuple(state.shape[1:]) != (GN_NODES, GN_FEATS + GN_ENC_IN) or tuple(adj.shape[1:]) != (GN_NODES, GN_NODES):
+        raise DDRLError(f"graphnet: state {tuple(state.shape)} / adj {tuple(adj.shape)} must be [B,4,23] / [B,4,4]")
+    if theta.numel() != graphnet_num_params(2 * A):
+        raise DDRLError(f"graphnet: theta has {theta.numel()} params, expected {graphnet_num_params(2 * A)}")
+    nbytes = int(lib.ddrl_graphnet_train_ws_bytes(B))
+    if ws is None or ws.numel() * ws.element_size() < nbytes:
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=state.device)
+    parts = graphnet_train_stat_parts(B)
+    if stat_part.numel() != parts * NSTAT or tuple(grad_part.shape) != (ctas, part_stride(theta.numel())):
+        raise DDRLError(f"graphnet_train_step: stat_part needs {parts} x {NSTAT} float64, grad_part [{ctas}, "
+                        f"{part_stride(theta.numel())}] float32")
+    _lib.check(lib.ddrl_graphnet_train_step(
+        _p(theta, f32, "theta"), _p(node_idx, torch.int32, "node_idx"), _p(state, f32, "state"), _p(adj, f32, "adj"),
+        _p(actions, f32, "actions"), _p(old_logits, f32, "old_logits"), _p(old_logp, f32, "old_logp"),
+        _p(vf_preds, f32, "vf_preds"), _p(adv, f32, "adv"), _p(vtarg, f32, "vtarg"), B, A, _p(kl_coeff, f32, "kl_coeff"),
+        C.byref(hyper), int(ctas), _p(ws, None, "ws"), _p(grad_part, f32, "grad_part"),
+        _p(stat_part, torch.float64, "stat_part"), _stream()), "graphnet_train_step")
+    return ws
+
+
 def dg_sample(logits: torch.Tensor, eps: torch.Tensor):
     """logits [R,2A], eps [R,A] -> action [R,A], logp [R]  (DiagGaussian sample, unclipped)."""
     R, A = eps.shape

@@ -467,9 +467,13 @@ class GraphNetLearner(_LearnerBase):
     quantruped_GraphDecentralizedController_environments.py:219-233), so there is no filter stage here."""
 
     def __init__(self, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
-                 ctas: Optional[int] = None):
+                 ctas: Optional[int] = None, two_launch_step: bool = False):
+        """two_launch_step: run every SGD step as `ddrl_graphnet_train_step` (warp-per-row forward + loss + backward to
+        the layer inputs, then the weight gradients) instead of forward + ppo_loss_grad + row-per-CTA backward.  Opt-in:
+        written after round 1's GPU budget was spent, not yet timed or parity-run on a GPU."""
         super().__init__(1, K.graphnet_num_params(2 * A), cfg, device, theta)
         self.A = A
+        self.two_launch_step = two_launch_step
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.ctas = ctas or max(1, self.sms // 2)
 
@@ -510,17 +514,25 @@ class GraphNetLearner(_LearnerBase):
         gpart = torch.empty(G, K.part_stride(self.NP), dtype=f32, device=dev)
         spart = torch.empty(1, LG, K.NSTAT, dtype=torch.float64, device=dev)
         step_stats = torch.zeros(E * nb, 1, K.NSTAT, dtype=torch.float64, device=dev)
+        ws = None
+        if self.two_launch_step:
+            spart = torch.empty(1, K.graphnet_train_stat_parts(MB), K.NSTAT, dtype=torch.float64, device=dev)
         order = perms.cpu().numpy()
         self.step_ctr.zero_()
         for e in range(E):
             for i in range(nb):
                 r0 = int(order[e, i]) * MB
                 sl = slice(r0, r0 + MB)
-                lg, vl = K.graphnet_forward(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], A)
-                K.ppo_loss_grad(lg.reshape(1, MB, 2 * A), vl.reshape(1, MB), cols["act"][sl], cols["logits"][sl],
-                                cols["logp"][sl], cols["value"][sl], cols["adv"][sl], cols["vtarg"][sl], A,
-                                self.kl_coeff, hyper, LG, dlogits, dvalue, spart)
-                _lib_backward(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], dlogits, dvalue, MB, A, G, gpart)
+                if self.two_launch_step:
+                    ws = K.graphnet_train_step(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], cols["act"][sl],
+                                               cols["logits"][sl], cols["logp"][sl], cols["value"][sl], cols["adv"][sl],
+                                               cols["vtarg"][sl], A, self.kl_coeff, hyper, G, gpart, spart, ws)
+                else:
+                    lg, vl = K.graphnet_forward(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], A)
+                    K.ppo_loss_grad(lg.reshape(1, MB, 2 * A), vl.reshape(1, MB), cols["act"][sl], cols["logits"][sl],
+                                    cols["logp"][sl], cols["value"][sl], cols["adv"][sl], cols["vtarg"][sl], A,
+                                    self.kl_coeff, hyper, LG, dlogits, dvalue, spart)
+                    _lib_backward(th, cols["idx"][sl], cols["st"][sl], cols["adj"][sl], dlogits, dvalue, MB, A, G, gpart)
                 # grad_part [G, NP] -> grad [1, NP]; loss-stat partials [1, LG, 8] -> step_stats[step]
                 K.grad_reduce(gpart, None, 1, G, self.NP, self.grad)
                 _reduce_stats(spart, step_stats, self.step_ctr)
@@ -551,7 +563,8 @@ def _reduce_stats(spart: torch.Tensor, step_stats: torch.Tensor, step_ctr: torch
     dummy = _reduce_stats.__dict__.setdefault("dummy", {})
     key = (spart.device, LG)
     if key not in dummy:
-        dummy[key] = (torch.zeros(P, LG, 1, dtype=torch.float32, device=spart.device),
+        # NP = 1 -> the reducer strides the partial rows by part_stride(1) = 4 floats
+        dummy[key] = (torch.zeros(P, LG, K.part_stride(1), dtype=torch.float32, device=spart.device),
                       torch.zeros(P, 1, dtype=torch.float32, device=spart.device))
     gp, g = dummy[key]
     K.grad_reduce(gp, spart, P, LG, 1, g, step_stats, step_ctr)

@@ -291,6 +291,24 @@ int ddrl_graphnet_backward(const float* theta, const int32_t* node_idx, const fl
                            const float* adj, const float* dlogits, const float* dvalue, int64_t B,
                            int A, int ctas, float* grad_part, void* stream);
 
+/* One SGD step of the GraphNet wrapper in two launches (opt-in alternative to ddrl_graphnet_forward + ddrl_ppo_loss_grad +
+ * ddrl_graphnet_backward; same arithmetic): (1) one warp per row: forward, the row's PPOLoss gradient w.r.t. this net's
+ * outputs (policy part for the actor, value part for the critic; RLlib ppo_tf_policy.PPOLoss) and the backward down to the
+ * layer inputs, leaving a 2.1 KB record per (net, row) in `ws`; (2) thread-owned register accumulation of the weight
+ * gradients over the rows of each CTA.
+ *   theta, node_idx [B], state [B][4][23], adj [B][4][4] as in ddrl_graphnet_forward; actions [B][A], old_logits [B][2A],
+ *   old_logp / vf_preds / adv / vtarg [B]; kl_coeff: device float; ws: ddrl_graphnet_train_ws_bytes(B) bytes;
+ *   grad_part [ctas][NPs] per-CTA partials like ddrl_graphnet_backward (reduce with ddrl_grad_reduce(P=1));
+ *   stat_part [ddrl_graphnet_train_stat_parts(B)][DDRL_NSTAT] float64 partial sums (actor CTAs fill the policy entries,
+ *   critic CTAs the value entries; sum them all). */
+int64_t ddrl_graphnet_train_ws_bytes(int64_t B);
+int ddrl_graphnet_train_stat_parts(int64_t B);
+int ddrl_graphnet_train_step(const float* theta, const int32_t* node_idx, const float* state, const float* adj,
+                             const float* actions, const float* old_logits, const float* old_logp,
+                             const float* vf_preds, const float* adv, const float* vtarg, int64_t B, int A,
+                             const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas, void* ws,
+                             float* grad_part, double* stat_part, void* stream);
+
 /* GCN layer (models/gcn.py:7-37, graph_ops.adj_norm models/graph_ops.py:13-21):
  *   y = act((D^-1 A) X W + b), X [B][4][F], A [B][4][4], W [F][U], b [U] or NULL, act: 0 none 1 tanh */
 int ddrl_gcn_forward(const float* x, const float* adj, const float* W, const float* b, int64_t B,
