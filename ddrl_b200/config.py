@@ -2,7 +2,7 @@
 resolved values of every published run: Results/**/params.json)."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict
 
 DEFAULT_MODEL_CONFIG: Dict[str, Any] = {

@@ -20,7 +20,6 @@ All arithmetic runs in libddrl_b200.so; torch provides memory, streams, CUDA gra
 collectives (filter partials, advantage moments, stat sums)."""
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -29,7 +28,7 @@ import torch
 from . import kernels as K
 from ._lib import DDRLError, PPOHyper
 from .config import PPOConfig
-from .sharding import allreduce_sum_, gather_parts_rank_order, local_minibatch
+from .sharding import gather_parts_rank_order, local_minibatch
 
 STAT_NAMES = ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var")
 
@@ -558,7 +557,6 @@ def _lib_backward(th, idx, st, adj, dlogits, dvalue, B, A, G, gpart):
 
 def _reduce_stats(spart: torch.Tensor, step_stats: torch.Tensor, step_ctr: torch.Tensor):
     """stat partials [1, LG, 8] -> step_stats[*step_ctr] via the C-ABI reducer (its gradient half runs on a dummy)."""
-    from . import _lib
     P, LG, _ = spart.shape
     dummy = _reduce_stats.__dict__.setdefault("dummy", {})
     key = (spart.device, LG)
