@@ -179,7 +179,7 @@ def run_graphnet(args):
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=R // nb)
     g = torch.Generator().manual_seed(7)
     th = _FlatParams(graphnet_shapes(2 * A)).init_host(g, small=("actor/linear_out", "critic/linear_out")).reshape(1, -1)
-    L = GraphNetLearner(A, cfg, dev, theta=th)
+    L = GraphNetLearner(A, cfg, dev, theta=th, two_launch_step=args.gn_two_launch)
     state = torch.randn(T, C, 4, 23, generator=g).to(dev)
     idx = torch.arange(4, dtype=torch.int32).repeat(T * N).reshape(T, C).to(dev)
     adj = torch.from_numpy(QuantrupedDecentralizedSharedGraphEnv.create_adj()).float().expand(T, C, 4, 4).contiguous().to(dev)
@@ -205,6 +205,7 @@ def run_graphnet(args):
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "Shared GraphNet policy over the 4-leg graph (BASELINE.json configs[3])",
                                  "envs": N, "fragment_T": T, "rows": R, "num_sgd_iter": E, "minibatches_per_epoch": nb,
+                                 "sgd_step": "two-launch (opt-in)" if args.gn_two_launch else "forward + loss + backward",
                                  "note": "supplementary; FP32 kernels, eager launches"}}))
 
 
@@ -225,6 +226,7 @@ def main():
                     help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per policy of the SGD-step kernel (0 = the learner's choice)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
+    ap.add_argument("--gn-two-launch", action="store_true", help="graphnet workload: ddrl_graphnet_train_step (opt-in, see DESIGN.md §7)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
     ap.add_argument("--arch", default="FullyDecentral",
                     help="supplementary: any published architecture (Centralized, FullyDecentral, Local, SingleNeighbor, "
