@@ -15,6 +15,11 @@ Parity status
   ``Results/`` — variable names/shapes/order, TF1-Adam slot layout, MeanStdFilter state schema,
   the loss-composition identity on all 360 policies (3e-7 rel), ``cur_kl_coeff`` in 0.2*1.5^k,
   vf_loss >> vf_clip_param (PPO2-style value clipping), parameter-count CSV.
+* Pinned by the reference's OWN numpy code executed here (tests/test_env_glue_golden.py; the pure-numpy
+  methods are lifted from the reference files' ASTs by tests/golden/make_{env_glue,graph_obs,curriculum}_golden.py
+  and run unmodified on stub objects): get_obs_indices / get_action_indices / get_contact_force_indices,
+  the reward / cost split in its four variants, concatenate_actions, the shared-graph env's
+  distribute_observations / leg_encoding_ego / quaternion_multiply — bit for bit.
 * Everything else (GAE recursion, standardisation eps 1e-4, filter eps 1e-8, Adam eps placement,
   minibatch slicing, GraphNet/MPNN/GCN/Coupling) is a restatement with no reference-run vector
   behind it:  **parity unpinned** for those functions (DESIGN.md says the same).
