@@ -256,6 +256,59 @@ class QuantrupedDecentralizedSharedGraphEnv(_Arch):
         return {"leg_policy": (None, graph_space, spaces.Box(-1.0, 1.0, (2,)), {})}
 
 
+class QuantrupedFullyDecentralizedGlobalCostEnv(QuantrupedFullyDecentralizedEnv):
+    """Per-leg controllers trained on local costs but a shared control-cost term
+    (quantruped_fourDecentralizedController_GlobalCosts_environments.py:6-112): same observation / action routing and
+    policy mapping as FullyDecentral; the reward split is mode "global_costs" of `ddrl_reward_split`."""
+    reward_mode = "global_costs"
+
+
+class QuantrupedDecentralizedGraphEnv(_Arch):
+    """Four per-leg policies over Tuple(node_idx[1], obs[4, 19], adj[4, 4])
+    (quantruped_GraphDecentralizedController_environments.py:37-120).  The node width 19 has no leg-encoding columns, so
+    it does not fit GraphNet's `state[..., -4:]` split (models/graph_net.py:33) — the table is mirrored, the model is not."""
+    policy_names = [f"policy_{l}" for l in _LEGS]
+    agent_names = [f"agent_{l}" for l in _LEGS]
+    _obs_prefixes = {f"agent_{l}": ["body", _leg[l]] for l in _LEGS}
+    _act_prefixes = {f"agent_{l}": [_leg[l]] for l in _LEGS}
+    _agent_policy = {f"agent_{l}": f"policy_{l}" for l in _LEGS}
+    model = "gnn"
+    create_edge_index = staticmethod(QuantrupedDecentralizedSharedGraphEnv.create_edge_index)
+    create_adj = classmethod(lambda cls: QuantrupedDecentralizedSharedGraphEnv.create_adj())
+
+    @classmethod
+    def return_policies(cls, use_target_velocity: bool = False):
+        n_dims = 19 + int(use_target_velocity)
+        graph_space = spaces.Tuple([spaces.MultiDiscrete([4]), spaces.Box(-np.inf, np.inf, (4, n_dims), np.float64),
+                                    spaces.MultiDiscrete(np.ones([4, 4]) * 2)])
+        return {p: (None, graph_space, spaces.Box(-1.0, 1.0, (2,)), {}) for p in cls.policy_names}
+
+
+class QuantrupedSingleDecentralizedLegIDEnv(QuantrupedSingleDecentralizedEnv):
+    """Shared per-leg policy that also receives the leg index: obs = Tuple(node_idx[1], obs[19]) — the input of the
+    LegCoupling model "cup" (quantruped_singleDecentralizedController_environments.py:66-115)."""
+    model = "cup"
+
+    @classmethod
+    def return_policies(cls, use_target_velocity: bool = False):
+        obs_space = spaces.Tuple([spaces.MultiDiscrete([4]),
+                                  spaces.Box(-np.inf, np.inf, (19 + int(use_target_velocity),), np.float64)])
+        return {"policy_legs": (None, obs_space, spaces.Box(-1.0, 1.0, (2,)), {})}
+
+
+class QuantrupedSingleDecentralizedLegTransforms(QuantrupedSingleDecentralizedEnv):
+    """Shared per-leg policy whose knee actions of the right-hand legs are mirrored before they reach the simulator
+    (quantruped_singleDecentralizedController_environments.py:117-148): `concatenate_actions(...) * action_scale`."""
+
+    @classmethod
+    def action_scale(cls) -> np.ndarray:
+        """float32 [8] in the env's action order (ACTION_FIELDS): -1 for fr_knee and hr_knee, 1 elsewhere."""
+        scale = np.ones(len(ACTION_FIELDS), dtype=np.float32)
+        for pfx in ("fr_knee", "hr_knee"):
+            scale[get_action_indices([pfx])] = -1.0
+        return scale
+
+
 ARCHITECTURES = {
     "QuantrupedMultiEnv_Centralized": Quantruped_Centralized_Env,
     "QuantrupedMultiEnv_FullyDecentral": QuantrupedFullyDecentralizedEnv,
@@ -267,6 +320,10 @@ ARCHITECTURES = {
     "QuantrupedMultiEnv_TwoDiags": Quantruped_TwoDiagControllers_Env,
     "QuantrupedMultiEnv_SharedDecentral": QuantrupedSingleDecentralizedEnv,
     "QuantrupedMultiEnv_DecentralShared_Graph": QuantrupedDecentralizedSharedGraphEnv,
+    "QuantrupedMultiEnv_Decentral_Graph": QuantrupedDecentralizedGraphEnv,
+    "QuantrupedMultiEnv_FullyDecentralGlobalCost": QuantrupedFullyDecentralizedGlobalCostEnv,
+    "QuantrupedMultiEnv_SharedDecentralLegID": QuantrupedSingleDecentralizedLegIDEnv,
+    "QuantrupedMultiEnv_SharedDecentralLegTransforms": QuantrupedSingleDecentralizedLegTransforms,
 }
 
 

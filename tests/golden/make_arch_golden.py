@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Golden table of the multi-agent architectures from the reference's own classes.
+
+    python tests/golden/make_arch_golden.py        (HERE only: needs /root/reference)
+
+The env modules import gym / ray / MuJoCo, so only their STATIC interface is lifted from the ASTs and executed unmodified:
+class-level constants (`policy_names`, `agent_names`, `leg_angles`) and the `@staticmethod`s `policy_mapping_fn` /
+`return_policies`, with the class hierarchy kept (the root `MultiAgentEnv` becomes `object`) and `gym.spaces` replaced by
+`ddrl_b200.spaces` (same constructor signatures).  The `--policy_scope` -> class table is read from the if-chain of
+train_experiment_1_architecture_on_flat.py:63-90.  Writes tests/golden/architectures.json:
+    {scope: {"class": name, "policy_names": [...], "agent_names": [...], "mapping": {agent_id: policy_id},
+             "policies": {"flat" | "tvel": {policy_id: {"obs": <space>, "act": <space>}}}}}
+with <space> = ["Box", shape, dtype] | ["MultiDiscrete", nvec] | ["Tuple", [<space>, ...]]."""
+import ast
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from ddrl_b200 import spaces  # noqa: E402
+
+REF = "/root/reference"
+PROBE_IDS = ["agent_FL", "agent_HL", "agent_HR", "agent_FR", "agent_LEFT", "agent_RIGHT", "agent_FLHR", "agent_HLFR",
+             "central_agent", "agent_FL_1", "agent_HR7", "somebody_else"]
+
+
+def static_part(cls: ast.ClassDef) -> ast.ClassDef:
+    keep = []
+    for n in cls.body:
+        if isinstance(n, ast.Assign) and all(isinstance(t, ast.Name) for t in n.targets):
+            keep.append(n)
+        elif isinstance(n, ast.FunctionDef) and any(getattr(d, "id", "") == "staticmethod" for d in n.decorator_list):
+            keep.append(n)
+    bases = [b if getattr(b, "id", "") != "MultiAgentEnv" else ast.Name(id="object", ctx=ast.Load()) for b in cls.bases]
+    return ast.ClassDef(name=cls.name, bases=bases, keywords=[], body=keep or [ast.Pass()], decorator_list=[])
+
+
+def lift_module(name: str):
+    """Static interface of simulation_envs/<name>.py in its own namespace (two modules define a class of the same name)."""
+    ns = {"np": np, "spaces": spaces}
+    files = [f"{REF}/simulation_envs/quantruped_adaptor_multi_environment.py"]
+    if name != "quantruped_adaptor_multi_environment":
+        files.append(f"{REF}/simulation_envs/{name}.py")
+    for f in files:
+        tree = ast.parse(open(f).read())
+        body = [static_part(n) for n in tree.body if isinstance(n, ast.ClassDef)]
+        exec(compile(ast.fix_missing_locations(ast.Module(body=body, type_ignores=[])), f, "exec"), ns)
+    return ns
+
+
+def scope_table():
+    """{policy_scope: (module, class name)} from the import if-chain of the training script."""
+    tree = ast.parse(open(f"{REF}/train_experiment_1_architecture_on_flat.py").read())
+    out = {}
+
+    def walk(node):
+        if isinstance(node, ast.If) and isinstance(node.test, ast.Compare) and getattr(node.test.left, "id", "") == "policy_scope":
+            scope = node.test.comparators[0].value
+            imp = next(n for n in node.body if isinstance(n, ast.ImportFrom))
+            out[scope] = (imp.module.split(".")[-1], imp.names[0].name)
+            for n in node.orelse:
+                if isinstance(n, ast.If):
+                    walk(n)
+                elif isinstance(n, ast.ImportFrom):
+                    out["QuantrupedMultiEnv_Centralized"] = (n.module.split(".")[-1], n.names[0].name)   # else branch (:61, :89-90)
+    for n in tree.body:
+        walk(n)
+    return out
+
+
+def describe(sp):
+    if isinstance(sp, spaces.Tuple):
+        return ["Tuple", [describe(s) for s in sp]]
+    if isinstance(sp, spaces.MultiDiscrete):
+        return ["MultiDiscrete", np.asarray(sp.nvec).astype(int).tolist()]
+    return ["Box", list(sp.shape), str(np.dtype(sp.dtype))]
+
+
+def main():
+    table, out = scope_table(), {}
+    for scope, (mod, cname) in sorted(table.items()):
+        cls = lift_module(mod)[cname]
+        pol = {}
+        for tag, tv in (("flat", False), ("tvel", True)):
+            pol[tag] = {pid: {"obs": describe(spec[1]), "act": describe(spec[2])}
+                        for pid, spec in cls.return_policies(use_target_velocity=tv).items()}
+        out[scope] = {"class": cname, "policy_names": list(cls.policy_names), "agent_names": list(getattr(cls, "agent_names", [])),
+                      "mapping": {a: cls.policy_mapping_fn(a) for a in PROBE_IDS}, "policies": pol}
+    json.dump(out, open(os.path.join(HERE, "architectures.json"), "w"), indent=1, sort_keys=True)
+    print("wrote architectures.json:", len(out), "scopes")
+
+
+if __name__ == "__main__":
+    main()

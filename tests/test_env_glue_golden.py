@@ -69,3 +69,48 @@ def test_oracle_graph_node_features_with_frozen_filter():
         assert np.array_equal(O.graph_distribute_observations(obs[t], norm, idx), want[t]), t
     q = want[:, :, 19:]                                   # unit body quaternion times a unit yaw quaternion stays unit
     assert np.allclose(np.linalg.norm(q, axis=-1), 1.0, atol=1e-12)
+
+
+# ---- a13: the architecture table against the reference's own static env interface ------------------------------------------
+import json  # noqa: E402
+
+ARCH = json.load(open(os.path.join(GOLDEN, "architectures.json")))
+
+
+def _describe(sp):
+    from ddrl_b200 import spaces
+    if isinstance(sp, spaces.Tuple):
+        return ["Tuple", [_describe(s) for s in sp]]
+    if isinstance(sp, spaces.MultiDiscrete):
+        return ["MultiDiscrete", np.asarray(sp.nvec).astype(int).tolist()]
+    return ["Box", list(sp.shape), str(np.dtype(sp.dtype))]
+
+
+def test_every_policy_scope_of_the_training_script_is_mirrored():
+    assert set(ARCH) == set(P.ARCHITECTURES)
+
+
+@pytest.mark.parametrize("scope", sorted(ARCH))
+def test_architecture_table_equals_the_reference_classes(scope):
+    """policy / agent names, `policy_mapping_fn` on known and unknown agent ids, and the spaces of `return_policies`
+    (flat and target-velocity variants) — from tests/golden/make_arch_golden.py, which executes the reference's static
+    class members.  One documented deviation: the fork keys the centralized policy "centr_A_policy" in return_policies
+    while its policy_mapping_fn and every published checkpoint say "central_policy"; the published name is kept."""
+    ref, env = ARCH[scope], P.ARCHITECTURES[scope]
+    assert env.__name__ == ref["class"]
+    assert list(env.policy_names) == ref["policy_names"] and list(env.agent_names) == ref["agent_names"]
+    for agent_id, pid in ref["mapping"].items():
+        assert env.policy_mapping_fn(agent_id) == pid, agent_id
+    for tag, tv in (("flat", False), ("tvel", True)):
+        got = {pid: {"obs": _describe(spec[1]), "act": _describe(spec[2])}
+               for pid, spec in env.return_policies(use_target_velocity=tv).items()}
+        want = ref["policies"][tag]
+        if scope == "QuantrupedMultiEnv_Centralized":
+            want = {"central_policy": want["centr_A_policy"]}
+        assert got == want, tag
+    assert P.multiagent_config(scope)["policies_to_train"] == ref["policy_names"]
+
+
+def test_leg_transform_action_scale():
+    s = P.ARCHITECTURES["QuantrupedMultiEnv_SharedDecentralLegTransforms"].action_scale()
+    assert s.tolist() == [1.0, -1.0, 1.0, 1.0, 1.0, 1.0, 1.0, -1.0]       # fr_knee, hr_knee (ACTION_FIELDS order)
