@@ -20,9 +20,14 @@ Parity status
   and run unmodified on stub objects): get_obs_indices / get_action_indices / get_contact_force_indices,
   the reward / cost split in its four variants, concatenate_actions, the shared-graph env's
   distribute_observations / leg_encoding_ego / quaternion_multiply — bit for bit.
-* Everything else (GAE recursion, standardisation eps 1e-4, filter eps 1e-8, Adam eps placement,
-  minibatch slicing, GraphNet/MPNN/GCN/Coupling) is a restatement with no reference-run vector
-  behind it:  **parity unpinned** for those functions (DESIGN.md says the same).
+* Pinned by the reference's own MODEL code executed on a numpy stand-in for TensorFlow
+  (tests/test_models_golden.py; tests/golden/make_models_golden.py + tf_shim.py import /root/reference/models
+  unmodified): graph_ops, GCN / MPNN / MPNN2 / GAT1, GraphNet and its actor / critic wrapper, the FCNet in
+  all four layouts, LegCoupling — to 1e-12.  (Pins the reference's composition of ops, not TF's kernels.)
+* Everything that lives inside RLlib / TF rather than in the reference repo (GAE recursion,
+  standardisation eps 1e-4, filter eps 1e-8, Adam eps placement, minibatch slicing) is a restatement with
+  no reference-run vector behind it beyond the checkpoint pins:  **parity unpinned** for those functions
+  (DESIGN.md says the same).
 
 Every function cites the reference file:line it follows (paths relative to /root/reference) or the
 RLlib 1.0.1 module it restates.  dtype is a parameter: float64 is the ground truth the CUDA FP32
