@@ -123,6 +123,15 @@ def main():
     assert st == [] and len(wrap.variables()) == 12
     OUT["wrap/logits"], OUT["wrap/value"] = logits, wrap.value_function()
 
+    # the `_GlobalCritic` wrapper cannot be constructed as shipped (shared_graphnet_glorot_uniform_init.py:69: super() names a
+    # class it does not derive from) — the reason DESIGN.md lists it as "no behaviour to be identical to"
+    from models.shared_graphnet_glorot_uniform_init import FullyConnectedNetwork_GNN_GlorotUniformInitializer_GlobalCritic as GC
+    try:
+        GC(graph_space, spaces.Box(-1, 1, (2,)), 4, CFG, "x")
+        raise AssertionError("the reference's GlobalCritic wrapper became constructible: mirror it")
+    except TypeError as exc:
+        assert "super(type, obj)" in str(exc)
+
     # ---- FCNet: default layout and the two optional ones ------------------------------------------------------------------------------
     D, A, B = 19, 2, 13
     xf = rnd(B, D)
