@@ -177,3 +177,30 @@ def test_fcnet_optional_layouts_map_onto_the_two_branch_kernel_layout(D, A, vf_s
     (g_v,) = torch.autograd.grad((lg_v * wl).sum() + (v_v * wv).sum(), theta, retain_graph=True)
     (g_f,) = torch.autograd.grad((lg_f * wl).sum() + (v_f * wv).sum(), theta)
     assert float((g_v - g_f).abs().max()) <= 1e-12 * float(g_v.abs().max())
+
+
+def test_config_defaults_equal_every_published_run():
+    """`RLLIB_DEFAULTS`, `PPOConfig.from_rllib` and `DEFAULT_MODEL_CONFIG` against the 120 published params.json files
+    (tests/golden/make_params_golden.py): every learner-path hyper-parameter has ONE value across all runs."""
+    import json
+    import os
+    from ddrl_b200.config import DEFAULT_MODEL_CONFIG, RLLIB_DEFAULTS, PPOConfig
+    from tests.util import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "published_params.json")))
+    assert g["n_runs"] == 120
+    for k, v in RLLIB_DEFAULTS.items():
+        assert g["top"][k] == [v], k
+    c = PPOConfig.from_rllib({})
+    for field_, key in (("gamma", "gamma"), ("lambda_", "lambda"), ("clip_param", "clip_param"), ("vf_clip_param", "vf_clip_param"),
+                        ("vf_loss_coeff", "vf_loss_coeff"), ("entropy_coeff", "entropy_coeff"), ("kl_coeff", "kl_coeff"),
+                        ("kl_target", "kl_target"), ("lr", "lr"), ("grad_clip", "grad_clip"), ("num_sgd_iter", "num_sgd_iter"),
+                        ("sgd_minibatch_size", "sgd_minibatch_size")):
+        assert [getattr(c, field_)] == g["top"][key], field_
+    for k in ("custom_model", "fcnet_hiddens", "fcnet_activation", "free_log_std", "no_final_linear"):
+        assert g["model"][k] == [DEFAULT_MODEL_CONFIG[k]], k
+    # params.json is dumped before PPO's setup_config copies the TOP-LEVEL vf_share_layers (False in all runs) into the model
+    # config; the checkpoints' fc_value_* variables confirm the separate value network
+    assert g["model"]["vf_share_layers"] == [True] and g["top"]["vf_share_layers"] == [False]
+    assert DEFAULT_MODEL_CONFIG["vf_share_layers"] is False
+    assert g["top"]["lr_schedule"] == [None] and g["top"]["entropy_coeff_schedule"] == [None]       # constant lr / entropy coeff
+    assert g["env_config"]["ctrl_cost_weight"] == [0.25, 0.5] and g["env_config"]["contact_cost_weight"] == [0.025, 0.05]
