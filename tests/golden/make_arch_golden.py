@@ -9,8 +9,12 @@ class-level constants (`policy_names`, `agent_names`, `leg_angles`) and the `@st
 `ddrl_b200.spaces` (same constructor signatures).  The `--policy_scope` -> class table is read from the if-chain of
 train_experiment_1_architecture_on_flat.py:63-90.  Writes tests/golden/architectures.json:
     {scope: {"class": name, "policy_names": [...], "agent_names": [...], "mapping": {agent_id: policy_id},
-             "policies": {"flat" | "tvel": {policy_id: {"obs": <space>, "act": <space>}}}}}
-with <space> = ["Box", shape, dtype] | ["MultiDiscrete", nvec] | ["Tuple", [<space>, ...]]."""
+             "policies": {"flat" | "tvel": {policy_id: {"obs": <space>, "act": <space>}}},
+             "tables": {"obs": {agent: [index...]}, "act": {agent: [index...]}, "contact": {agent: [[row...], [weight...]]}}}}
+with <space> = ["Box", shape, dtype] | ["MultiDiscrete", nvec] | ["Tuple", [<space>, ...]].
+"tables" are what each class's CONSTRUCTOR builds (flat terrain observation, 43 fields): the constructors are executed too, on
+a root class whose `__init__` only provides `self.env` = the index helpers of `QuAntrupedEnv` (quantruped_v3.py:68-112,282-341,
+lifted the same way) instead of creating the MuJoCo simulation."""
 import ast
 import json
 import os
@@ -28,19 +32,33 @@ PROBE_IDS = ["agent_FL", "agent_HL", "agent_HR", "agent_FR", "agent_LEFT", "agen
 
 
 def static_part(cls: ast.ClassDef) -> ast.ClassDef:
-    keep = []
-    for n in cls.body:
-        if isinstance(n, ast.Assign) and all(isinstance(t, ast.Name) for t in n.targets):
-            keep.append(n)
-        elif isinstance(n, ast.FunctionDef) and any(getattr(d, "id", "") == "staticmethod" for d in n.decorator_list):
-            keep.append(n)
+    """Class-level constants and all methods (only the static ones and the constructors are ever called)."""
+    keep = [n for n in cls.body if isinstance(n, ast.FunctionDef)
+            or (isinstance(n, ast.Assign) and all(isinstance(t, ast.Name) for t in n.targets))]
     bases = [b if getattr(b, "id", "") != "MultiAgentEnv" else ast.Name(id="object", ctx=ast.Load()) for b in cls.bases]
     return ast.ClassDef(name=cls.name, bases=bases, keywords=[], body=keep or [ast.Pass()], decorator_list=[])
 
 
+def sim_helpers():
+    """`QuAntrupedEnv` reduced to its field lists and index helpers."""
+    tree = ast.parse(open(f"{REF}/simulation_envs/quantruped_v3.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "QuAntrupedEnv")
+    want = {"get_obs_indices", "get_action_indices", "get_contact_force_indices"}
+    body = [n for n in cls.body if (isinstance(n, ast.FunctionDef) and n.name in want)
+            or (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "").endswith("_FIELDS"))]
+    ns = {"np": np}
+    mod = ast.Module(body=[ast.ClassDef(name="Sim", bases=[], keywords=[], body=body, decorator_list=[])], type_ignores=[])
+    exec(compile(ast.fix_missing_locations(mod), "quantruped_v3.py", "exec"), ns)
+    return ns["Sim"]()
+
+
 def lift_module(name: str):
-    """Static interface of simulation_envs/<name>.py in its own namespace (two modules define a class of the same name)."""
-    ns = {"np": np, "spaces": spaces}
+    """Static interface + constructors of simulation_envs/<name>.py in its own namespace (two modules define a class of the
+    same name)."""
+    class MeanStdFilter:                      # the graph env builds one in its constructor; never called here
+        def __init__(self, shape):
+            self.shape = shape
+    ns = {"np": np, "spaces": spaces, "MeanStdFilter": MeanStdFilter}
     files = [f"{REF}/simulation_envs/quantruped_adaptor_multi_environment.py"]
     if name != "quantruped_adaptor_multi_environment":
         files.append(f"{REF}/simulation_envs/{name}.py")
@@ -48,7 +66,25 @@ def lift_module(name: str):
         tree = ast.parse(open(f).read())
         body = [static_part(n) for n in tree.body if isinstance(n, ast.ClassDef)]
         exec(compile(ast.fix_missing_locations(ast.Module(body=body, type_ignores=[])), f, "exec"), ns)
+
+    def root_init(self, config):              # instead of QuantrupedMultiPoliciesEnv.__init__ (creates the simulation)
+        self.env = sim_helpers()
+    ns["QuantrupedMultiPoliciesEnv"].__init__ = root_init
     return ns
+
+
+def tables(env):
+    def cfi(v):
+        idx, w = v
+        return [np.asarray(idx).astype(int).tolist(), np.asarray(w, dtype=float).reshape(-1).tolist()]
+    out = {}
+    if hasattr(env, "obs_indices"):
+        out["obs"] = {a: np.asarray(v).astype(int).tolist() for a, v in env.obs_indices.items()}
+    if hasattr(env, "action_indices"):
+        out["act"] = {a: np.asarray(v).astype(int).tolist() for a, v in env.action_indices.items()}
+    if hasattr(env, "contact_force_indices"):
+        out["contact"] = {a: cfi(v) for a, v in env.contact_force_indices.items()}
+    return out
 
 
 def scope_table():
@@ -88,7 +124,7 @@ def main():
             pol[tag] = {pid: {"obs": describe(spec[1]), "act": describe(spec[2])}
                         for pid, spec in cls.return_policies(use_target_velocity=tv).items()}
         out[scope] = {"class": cname, "policy_names": list(cls.policy_names), "agent_names": list(getattr(cls, "agent_names", [])),
-                      "mapping": {a: cls.policy_mapping_fn(a) for a in PROBE_IDS}, "policies": pol}
+                      "mapping": {a: cls.policy_mapping_fn(a) for a in PROBE_IDS}, "policies": pol, "tables": tables(cls({}))}
     json.dump(out, open(os.path.join(HERE, "architectures.json"), "w"), indent=1, sort_keys=True)
     print("wrote architectures.json:", len(out), "scopes")
 

@@ -114,3 +114,20 @@ def test_architecture_table_equals_the_reference_classes(scope):
 def test_leg_transform_action_scale():
     s = P.ARCHITECTURES["QuantrupedMultiEnv_SharedDecentralLegTransforms"].action_scale()
     assert s.tolist() == [1.0, -1.0, 1.0, 1.0, 1.0, 1.0, 1.0, -1.0]       # fr_knee, hr_knee (ACTION_FIELDS order)
+
+
+@pytest.mark.parametrize("scope", sorted(ARCH))
+def test_index_tables_equal_what_the_reference_constructors_build(scope):
+    """obs / action / contact-force index tables of every agent of every scope, from the reference CONSTRUCTORS executed on a
+    simulation-free root class (tests/golden/make_arch_golden.py) — includes the SingleDiagonal quirk (HR and FR reuse the
+    FL / HL lists) and the prefix-major ordering."""
+    ref, env = ARCH[scope]["tables"], P.ARCHITECTURES[scope]
+    assert {a: list(map(int, v)) for a, v in env.obs_indices().items()} == ref["obs"]
+    assert {a: list(map(int, v)) for a, v in env.action_indices().items()} == ref["act"]
+    got = env.contact_force_indices()
+    assert set(got) == set(ref["contact"])
+    for a, (idx, w) in got.items():
+        assert [int(i) for i in idx] == ref["contact"][a][0], a
+        assert [float(np.asarray(x).reshape(-1)[0]) for x in w] == ref["contact"][a][1], a
+    if ref["obs"] and scope not in ("QuantrupedMultiEnv_Centralized",):
+        assert env.gather_table().tolist() == [ref["obs"][a] for a in env.agent_names]
