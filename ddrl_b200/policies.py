@@ -8,7 +8,7 @@ simulation_envs/quantruped_v3.py:282-317).  ``ARCHITECTURES`` is keyed by the ``
 (train_experiment_1_architecture_on_flat.py:63-90)."""
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -257,10 +257,12 @@ class QuantrupedDecentralizedSharedGraphEnv(_Arch):
 
 
 class QuantrupedFullyDecentralizedGlobalCostEnv(QuantrupedFullyDecentralizedEnv):
-    """Per-leg controllers trained on local costs but a shared control-cost term
+    """Per-leg controllers meant to share the control-cost term
     (quantruped_fourDecentralizedController_GlobalCosts_environments.py:6-112): same observation / action routing and
-    policy mapping as FullyDecentral; the reward split is mode "global_costs" of `ddrl_reward_split`."""
-    reward_mode = "global_costs"
+    policy mapping as FullyDecentral.  Its `distribute_reward` override (mode "global_costs" of `ddrl_reward_split`) is
+    SHADOWED as shipped: the root constructor binds `self.distribute_reward` as an instance attribute
+    (quantruped_adaptor_multi_environment.py:52-60), so this scope pays the per-leg reward like every other one
+    (`reward_mode`; tests/golden/make_env_step_golden.py runs the reference's step() to show it)."""
 
 
 class QuantrupedDecentralizedGraphEnv(_Arch):
@@ -325,6 +327,16 @@ ARCHITECTURES = {
     "QuantrupedMultiEnv_SharedDecentralLegID": QuantrupedSingleDecentralizedLegIDEnv,
     "QuantrupedMultiEnv_SharedDecentralLegTransforms": QuantrupedSingleDecentralizedLegTransforms,
 }
+
+
+def reward_mode(env_config: Optional[dict] = None) -> str:
+    """Mode of `ddrl_reward_split` the reference's adaptor is wired to for an env_config — the same for every scope
+    (quantruped_adaptor_multi_environment.py:52-62,173-203): 'global' with `global_reward`, else the per-leg split,
+    normalised ('per_leg_norm') with `norm_reward`."""
+    cfg = env_config or {}
+    if cfg.get("global_reward", False):
+        return "global"
+    return "per_leg_norm" if cfg.get("norm_reward", False) else "per_leg"
 
 
 def multiagent_config(policy_scope: str, use_target_velocity: bool = False) -> dict:

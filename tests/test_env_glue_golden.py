@@ -131,3 +131,44 @@ def test_index_tables_equal_what_the_reference_constructors_build(scope):
         assert [float(np.asarray(x).reshape(-1)[0]) for x in w] == ref["contact"][a][1], a
     if ref["obs"] and scope not in ("QuantrupedMultiEnv_Centralized",):
         assert env.gather_table().tolist() == [ref["obs"][a] for a in env.agent_names]
+
+
+# ---- one whole env step as the reference wires it (constructors + step() executed, simulation stubbed) ----------------------
+STEP = np.load(os.path.join(GOLDEN, "env_step.npz"))
+MODES = {("distribute_per_leg_reward", False): "per_leg", ("distribute_per_leg_reward", True): "per_leg_norm",
+         ("distribute_global_reward", False): "global", ("distribute_global_reward", True): "global"}
+CFGS = {"per_leg": {}, "norm": {"norm_reward": True}, "global": {"global_reward": True}}
+
+
+@pytest.mark.parametrize("scope", sorted(ARCH))
+@pytest.mark.parametrize("cfg", sorted(CFGS))
+def test_env_step_rewards_actions_and_observations(scope, cfg):
+    env = P.ARCHITECTURES[scope]
+    agents = list(env.agent_names)
+    wired = MODES[(str(STEP[f"{scope}/{cfg}/reward_fn"]), bool(STEP[f"{scope}/{cfg}/normalize_rewards"]))]
+    assert P.reward_mode(CFGS[cfg]) == wired          # also for the GlobalCost scope: its override is shadowed as shipped
+    acts, fw, cfrc, obs_full = STEP[f"actions/{scope}"], STEP["fw"], STEP["cfrc"], STEP["obs_full"]
+    cfi, ai = env.contact_force_indices(), env.action_indices()
+    filt = O.MeanStdFilter((43,))                      # the env-side singleton: one update per step, before the gather
+    node_filt = O.MeanStdFilter((4, 19))               # Decentral_Graph normalises the gathered node matrix instead
+    for t in range(len(fw)):
+        ad = {a: acts[t, i] for i, a in enumerate(agents)}
+        want_act = O.concatenate_actions(ad, {a: (ai[a] if env._act_prefixes[a] is not None else list(range(8))) for a in agents})
+        if scope.endswith("LegTransforms"):
+            want_act = want_act * env.action_scale()
+        assert np.array_equal(STEP[f"{scope}/{cfg}/sim_action"][t], want_act), t
+        r = O.distribute_rewards(fw[t], ad, cfrc[t], cfi, agents, 0.25, 0.025, wired)
+        assert np.array_equal(STEP[f"{scope}/{cfg}/rew"][t], np.asarray([r[a] for a in agents])), t
+        got = STEP[f"{scope}/{cfg}/obs"][t]
+        oi = env.obs_indices()
+        if scope == "QuantrupedMultiEnv_DecentralShared_Graph":
+            want = O.graph_distribute_observations(obs_full[t], filt, oi)
+            assert all(np.array_equal(got[i], want) for i in range(len(agents))), t
+        elif scope == "QuantrupedMultiEnv_Decentral_Graph":
+            want = node_filt(np.stack([obs_full[t][oi[a]] for a in agents]))
+            assert all(np.array_equal(got[i], want) for i in range(len(agents))), t
+        else:
+            normed = filt(obs_full[t])
+            for i, a in enumerate(agents):
+                idx = oi[a] if env._obs_prefixes[a] is not None else list(range(43))
+                assert np.array_equal(got[i], normed[idx]), (t, a)

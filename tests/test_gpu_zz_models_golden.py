@@ -58,3 +58,32 @@ def test_gcn_norms_and_coupling_kernels_equal_reference():
     assert scaled_err(sm.cpu().numpy(), G["ops/segment_softmax"]) < TOL
     out = K.leg_coupling_(dev("cup/logits_in"), dev("cup/node_id", np.int32).reshape(-1), dev("cup/coupling"))
     assert np.array_equal(out.cpu().numpy(), G["cup/layer_out"].astype(np.float32))
+
+
+S = np.load(os.path.join(GOLDEN, "env_step.npz"))
+WIRED = {("distribute_per_leg_reward", False): "per_leg", ("distribute_per_leg_reward", True): "per_leg_norm",
+         ("distribute_global_reward", False): "global", ("distribute_global_reward", True): "global"}
+
+
+@pytest.mark.parametrize("scope", ["QuantrupedMultiEnv_FullyDecentral", "QuantrupedMultiEnv_TwoDiags", "QuantrupedMultiEnv_Centralized",
+                                   "QuantrupedMultiEnv_Local", "QuantrupedMultiEnv_SharedDecentralLegTransforms",
+                                   "QuantrupedMultiEnv_FullyDecentralGlobalCost"])
+def test_env_step_kernels_equal_the_reference_step(scope):
+    """ddrl_reward_split / ddrl_concat_actions on the inputs of the reference's own env step() (run with a stubbed simulator,
+    tests/golden/make_env_step_golden.py), for the three env_configs the training script can select."""
+    from ddrl_b200 import kernels as K
+    from ddrl_b200 import policies as P
+    env = P.ARCHITECTURES[scope]
+    to = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(dt))).cuda()      # noqa: E731
+    act = S[f"actions/{scope}"]
+    for cfg, env_config in (("per_leg", {}), ("norm", {"norm_reward": True}), ("global", {"global_reward": True})):
+        mode = WIRED[(str(S[f"{scope}/{cfg}/reward_fn"]), bool(S[f"{scope}/{cfg}/normalize_rewards"]))]
+        assert P.reward_mode(env_config) == mode
+        rew = K.reward_split(to(S["fw"]), to(act), to(S["cfrc"], np.float64), to(env.contact_table(), np.float64), 0.25, 0.025,
+                             mode).cpu().numpy()
+        want = S[f"{scope}/{cfg}/rew"]
+        assert np.abs(rew - want).max() < 2e-6 * max(1.0, np.abs(want).max()), cfg
+    full = K.concat_actions(to(act), to(env.action_table(), np.int32))
+    if scope.endswith("LegTransforms"):
+        full = full * to(env.action_scale())
+    assert np.array_equal(full.cpu().numpy(), S[f"{scope}/per_leg/sim_action"].astype(np.float32))
