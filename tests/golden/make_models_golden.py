@@ -132,6 +132,16 @@ def main():
     except TypeError as exc:
         assert "super(type, obj)" in str(exc)
 
+    # the Decentral_Graph scope hands GraphNet node matrices [4, 19]: the encoder splits off the last 4 columns and multiplies
+    # the remaining 15 with a [19, 64] matrix (graph_net.py:33-37) — the reference model cannot even be built on that space
+    narrow = spaces.Tuple([spaces.MultiDiscrete([4]), spaces.Box(-np.inf, np.inf, (4, 19), np.float64),
+                           spaces.MultiDiscrete(np.ones([4, 4]) * 2)])
+    try:
+        models.FullyConnectedNetwork_GNN_GlorotUniformInitializer(narrow, spaces.Box(-1, 1, (2,)), 4, CFG, "x")
+        raise AssertionError("GraphNet accepted [4, 19] node matrices")
+    except ValueError as exc:
+        assert "19" in str(exc) and "15" in str(exc)
+
     # ---- FCNet: default layout and the two optional ones ------------------------------------------------------------------------------
     D, A, B = 19, 2, 13
     xf = rnd(B, D)
