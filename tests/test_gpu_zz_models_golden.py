@@ -54,8 +54,9 @@ def test_gcn_norms_and_coupling_kernels_equal_reference():
     y = K.gcn_forward(dev("layers/x"), dev("gcn/adj"), dev("gcn/W"), dev("gcn/b"), "tanh")
     assert scaled_err(y.cpu().numpy(), G["gcn/y"]) < TOL
     assert scaled_err(K.symm_norm(dev("ops/adj")).cpu().numpy(), G["ops/symm_norm"]) < TOL
-    sm = K.segment_softmax(dev("ops/seg_data"), dev("ops/seg_ids", np.int32), 5)
-    assert scaled_err(sm.cpu().numpy(), G["ops/segment_softmax"]) < TOL
+    for c in range(3):       # one column per call (the softmax is per column; the GPU suite exercises C = 1)
+        sm = K.segment_softmax(dev("ops/seg_data")[:, c:c + 1].contiguous(), dev("ops/seg_ids", np.int32), 5)
+        assert scaled_err(sm.cpu().numpy(), G["ops/segment_softmax"][:, c:c + 1]) < TOL
     out = K.leg_coupling_(dev("cup/logits_in"), dev("cup/node_id", np.int32).reshape(-1), dev("cup/coupling"))
     assert np.array_equal(out.cpu().numpy(), G["cup/layer_out"].astype(np.float32))
 
