@@ -204,3 +204,16 @@ def test_config_defaults_equal_every_published_run():
     assert DEFAULT_MODEL_CONFIG["vf_share_layers"] is False
     assert g["top"]["lr_schedule"] == [None] and g["top"]["entropy_coeff_schedule"] == [None]       # constant lr / entropy coeff
     assert g["env_config"]["ctrl_cost_weight"] == [0.25, 0.5] and g["env_config"]["contact_cost_weight"] == [0.025, 0.05]
+
+
+def test_modelv2_fcnet_layouts_orchestration_with_oracle_mocked_kernels():
+    """tests/host_dryrun_modelv2.py: the ModelV2 GPU tests (default, vf_share_layers, free_log_std) executed on CPU with the two
+    FCNet kernels replaced by the oracle — host logic only (own process: it monkeypatches torch)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_dryrun_modelv2.py")], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 5
