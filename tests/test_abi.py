@@ -94,3 +94,26 @@ def test_ops_refuse_cpu_tensors():
     from ddrl_b200._lib import DDRLError
     with pytest.raises(DDRLError, match="CUDA"):
         K.gather_rows(torch.zeros(1, 4, 2), torch.zeros(1, 4, dtype=torch.int32))
+
+
+def test_plain_c_program_links_and_calls_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 program including only include/ddrl_b200.h links against libddrl_b200.so and
+    calls it (sizes, parameter counts, argument validation with ddrl_last_error) — no Python, torch or CUDA headers."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "ddrl_b200")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(lib_dir, "libddrl_b200.so")):
+        pytest.skip("gcc or the built library is missing")
+    exe = str(tmp_path / "c_abi_smoke")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                         os.path.join(root, "tests", "c_abi_smoke.c"), "-L", lib_dir, "-lddrl_b200", "-o", exe],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=lib_dir))
+    assert run.returncode == 0, run.stderr
+    lines = run.stdout.splitlines()
+    assert lines[1] == "fcnet 11205 15057 -2"            # 128 D + 130 A + 8513; D = 65 > DDRL_MAX_OBS -> DDRL_E_UNSUPPORTED_SHAPE
+    assert lines[2] == "graphnet 28869"                  # actor 14 532 + critic 14 337 (SURVEY.md §8)
+    assert lines[5].startswith("badarg -1 fcnet_forward:")
+    assert lines[6] == "sizes 20 8"
