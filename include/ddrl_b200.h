@@ -12,7 +12,8 @@
  *   - no allocation, no host synchronisation, no ownership transfer: the caller owns every buffer,
  *     including the workspaces whose sizes the *_bytes() helpers return;
  *   - return 0 on success, <0 on error (DDRL_E_*); ddrl_last_error() gives the thread-local text;
- *   - re-entrant and thread-safe per (device, stream);
+ *   - re-entrant and thread-safe per stream; ONE DEVICE PER PROCESS (the one-process-per-GPU model): kernels that need more
+ *     than 48 KB of dynamic shared memory opt in once per process, on the device that is current at their first launch;
  *   - there is NO CPU fallback: without an sm_100 device every launch returns DDRL_E_CUDA.
  */
 #ifndef DDRL_B200_H
