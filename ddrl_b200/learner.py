@@ -498,6 +498,36 @@ class GraphNetLearner(_LearnerBase):
         K.adv_standardize(adv, moments)
         cols = {"idx": idx_f, "st": st_f, "adj": adj_f, "act": act, "logits": logits, "logp": logp,
                 "value": value, "adv": adv.reshape(R), "vtarg": vtarg.reshape(R)}
+        return self._sgd_phase(cols, perms, shuffle, R)
+
+    def learn_on_batch(self, node_idx, state, adj, actions, action_dist_inputs, action_logp, vf_preds, advantages,
+                       value_targets, perms, shuffle=None, standardize: bool = True) -> List[Dict[str, float]]:
+        """The learner half only, on POSTPROCESSED sample-batch columns (what RLlib's `Policy.learn_on_batch` receives for the
+        shared graph policy): node_idx [R] i32, state [R,4,23], adj [R,4,4] (the observation tuple), actions [R,A],
+        action_dist_inputs [R,2A], action_logp / vf_preds / advantages / value_targets [R] — float32 CUDA tensors.
+        StandardizeFields -> shuffle -> E x nb minibatch steps -> KL update, as in `learn_on_rollout`."""
+        R = state.shape[0]
+        adv = advantages.reshape(1, R).clone()
+        if standardize:
+            a64 = adv.double()
+            moments = torch.stack([torch.full((1,), float(R), dtype=torch.float64, device=adv.device), a64.sum(dim=1),
+                                   (a64 * a64).sum(dim=1)], dim=1).contiguous()
+            if self.world > 1:
+                self.dist.all_reduce(moments)
+            K.adv_standardize(adv, moments)
+        cols = {"idx": node_idx.reshape(R), "st": state, "adj": adj, "act": actions, "logits": action_dist_inputs,
+                "logp": action_logp, "value": vf_preds, "adv": adv.reshape(R), "vtarg": value_targets}
+        for name, t in cols.items():
+            want = torch.int32 if name == "idx" else torch.float32
+            if t.shape[0] != R or t.dtype != want or not t.is_cuda:
+                raise DDRLError(f"learn_on_batch: column {name!r} must be a {want} CUDA tensor with {R} rows, got {t.dtype} "
+                                f"{tuple(t.shape)} on {t.device}")
+        return self._sgd_phase(cols, perms, shuffle, R)
+
+    def _sgd_phase(self, cols, perms, shuffle, R: int) -> List[Dict[str, float]]:
+        """shuffle + E x nb minibatch steps over the prepared columns + stats + KL-coefficient update."""
+        A, cfg, dev, f32 = self.A, self.cfg, self.device, torch.float32
+        th = self.theta.reshape(-1)
         if shuffle is not None:
             sl = shuffle.long()
             cols = {k: v[sl].contiguous() for k, v in cols.items()}

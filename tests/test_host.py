@@ -217,3 +217,16 @@ def test_modelv2_fcnet_layouts_orchestration_with_oracle_mocked_kernels():
                          timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 5
+
+
+def test_graphnet_learner_orchestration_with_oracle_mocked_kernels():
+    """tests/host_dryrun_graphnet.py: one GraphNetLearner iteration against the oracle and learn_on_batch == the SGD phase of
+    learn_on_rollout, executed on CPU with every kernel replaced by the oracle — host logic only (own process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_dryrun_graphnet.py")], capture_output=True, text=True,
+                         timeout=900, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert out.stdout.split() == ["iteration", "ok", "learn_on_batch", "ok"]
