@@ -10,9 +10,10 @@ class-level constants (`policy_names`, `agent_names`, `leg_angles`) and the `@st
 train_experiment_1_architecture_on_flat.py:63-90.  Writes tests/golden/architectures.json:
     {scope: {"class": name, "policy_names": [...], "agent_names": [...], "mapping": {agent_id: policy_id},
              "policies": {"flat" | "tvel": {policy_id: {"obs": <space>, "act": <space>}}},
-             "tables": {"obs": {agent: [index...]}, "act": {agent: [index...]}, "contact": {agent: [[row...], [weight...]]}}}}
+             "tables" | "tables_tvel": {"obs": {agent: [index...]}, "act": {agent: [index...]},
+                                        "contact": {agent: [[row...], [weight...]]}}}}
 with <space> = ["Box", shape, dtype] | ["MultiDiscrete", nvec] | ["Tuple", [<space>, ...]].
-"tables" are what each class's CONSTRUCTOR builds (flat terrain observation, 43 fields): the constructors are executed too, on
+"tables" / "tables_tvel" are what each class's CONSTRUCTOR builds (43 fields / the 44 fields of the target-velocity env): the constructors are executed too, on
 a root class whose `__init__` only provides `self.env` = the index helpers of `QuAntrupedEnv` (quantruped_v3.py:68-112,282-341,
 lifted the same way) instead of creating the MuJoCo simulation."""
 import ast
@@ -39,13 +40,19 @@ def static_part(cls: ast.ClassDef) -> ast.ClassDef:
     return ast.ClassDef(name=cls.name, bases=bases, keywords=[], body=keep or [ast.Pass()], decorator_list=[])
 
 
-def sim_helpers():
-    """`QuAntrupedEnv` reduced to its field lists and index helpers."""
+def sim_helpers(tvel: bool = False):
+    """`QuAntrupedEnv` reduced to its field lists and index helpers; `tvel`: with the 44-entry OBS_FIELDS of
+    `QuAntrupedTVelEnv` as the class declares it (quantruped_v3.py:354-383).  (At run time `set_target_velocity` appends the
+    target-velocity field a SECOND time (:394-400), which contradicts `return_policies` (D + 1) and the published TVel
+    checkpoints (D + 1); the declared list is the one both agree with.)"""
     tree = ast.parse(open(f"{REF}/simulation_envs/quantruped_v3.py").read())
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "QuAntrupedEnv")
     want = {"get_obs_indices", "get_action_indices", "get_contact_force_indices"}
     body = [n for n in cls.body if (isinstance(n, ast.FunctionDef) and n.name in want)
             or (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "").endswith("_FIELDS"))]
+    if tvel:
+        tv = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "QuAntrupedTVelEnv")
+        body += [n for n in tv.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "OBS_FIELDS"]   # overrides
     ns = {"np": np}
     mod = ast.Module(body=[ast.ClassDef(name="Sim", bases=[], keywords=[], body=body, decorator_list=[])], type_ignores=[])
     exec(compile(ast.fix_missing_locations(mod), "quantruped_v3.py", "exec"), ns)
@@ -68,7 +75,7 @@ def lift_module(name: str):
         exec(compile(ast.fix_missing_locations(ast.Module(body=body, type_ignores=[])), f, "exec"), ns)
 
     def root_init(self, config):              # instead of QuantrupedMultiPoliciesEnv.__init__ (creates the simulation)
-        self.env = sim_helpers()
+        self.env = sim_helpers(tvel=bool(config.get("target_velocity")))
     ns["QuantrupedMultiPoliciesEnv"].__init__ = root_init
     return ns
 
@@ -124,7 +131,8 @@ def main():
             pol[tag] = {pid: {"obs": describe(spec[1]), "act": describe(spec[2])}
                         for pid, spec in cls.return_policies(use_target_velocity=tv).items()}
         out[scope] = {"class": cname, "policy_names": list(cls.policy_names), "agent_names": list(getattr(cls, "agent_names", [])),
-                      "mapping": {a: cls.policy_mapping_fn(a) for a in PROBE_IDS}, "policies": pol, "tables": tables(cls({}))}
+                      "mapping": {a: cls.policy_mapping_fn(a) for a in PROBE_IDS}, "policies": pol, "tables": tables(cls({})),
+                      "tables_tvel": tables(cls({"target_velocity": [1.0]}))}
     json.dump(out, open(os.path.join(HERE, "architectures.json"), "w"), indent=1, sort_keys=True)
     print("wrote architectures.json:", len(out), "scopes")
 

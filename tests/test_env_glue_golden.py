@@ -131,6 +131,10 @@ def test_index_tables_equal_what_the_reference_constructors_build(scope):
         assert [float(np.asarray(x).reshape(-1)[0]) for x in w] == ref["contact"][a][1], a
     if ref["obs"] and scope not in ("QuantrupedMultiEnv_Centralized",):
         assert env.gather_table().tolist() == [ref["obs"][a] for a in env.agent_names]
+    # target-velocity variant: the 44-field list QuAntrupedTVelEnv declares (index 43 joins the body block)
+    tv = ARCH[scope]["tables_tvel"]["obs"]
+    assert {a: list(map(int, v)) for a, v in env.obs_indices(use_target_velocity=True).items()} == tv
+    assert all(len(v) == len(ref["obs"][a]) + 1 and 43 in v for a, v in tv.items())
 
 
 # ---- one whole env step as the reference wires it (constructors + step() executed, simulation stubbed) ----------------------
