@@ -3,7 +3,7 @@
 Every kernel wrapper the learner touches (GraphNet forward / backward, DiagGaussian sample, GAE, StandardizeFields, PPO loss
 gradient, partial reduction, clip + TF1 Adam) is replaced by the ORACLE's float64 restatement, "cuda" is mapped to "cpu", and
 two GPU tests are executed unchanged: one learner iteration against the oracle (tests/test_gpu_graphnet.py) and
-`learn_on_batch` == the SGD phase of `learn_on_rollout` (tests/test_gpu_zz_graphnet_batch.py).  It checks the orchestration —
+`learn_on_batch` == the SGD phase of `learn_on_rollout` (tests/test_gpu_graphnet_batch.py).  It checks the orchestration —
 row order, slicing, shuffle, which statistics go where, KL update — and no kernel.  Test infrastructure only."""
 import os
 import sys
@@ -13,7 +13,6 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["DDRL_RUN_UNVALIDATED"] = "1"
 import oracle.ddrl_oracle as O  # noqa: E402
 
 _dev = torch.device
@@ -121,7 +120,7 @@ K.ppo_loss_grad, K.grad_reduce, K.clip_adam = ppo_loss_grad, grad_reduce, clip_a
 L._lib_backward = lib_backward
 
 import tests.test_gpu_graphnet as T  # noqa: E402
-import tests.test_gpu_zz_graphnet_batch as Z  # noqa: E402
+import tests.test_gpu_graphnet_batch as Z  # noqa: E402
 
 T.test_graphnet_ppo_iteration_runs_and_first_step_matches_oracle()
 print("iteration ok")

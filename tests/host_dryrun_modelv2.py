@@ -10,7 +10,6 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["DDRL_RUN_UNVALIDATED"] = "1"
 import oracle.ddrl_oracle as O  # noqa: E402
 
 torch.cuda.is_available = lambda: True
@@ -34,7 +33,7 @@ def bwd(theta, obs, dl, dv, A):
 
 K.fcnet_forward, K.fcnet_backward = fwd, bwd
 import tests.test_gpu_modelv2 as T  # noqa: E402
-import tests.test_gpu_zz_modelv2_layouts as Z  # noqa: E402
+import tests.test_gpu_modelv2_layouts as Z  # noqa: E402
 
 for flags in [(True, False), (False, True), (True, True)]:
     Z.test_fcnet_modelv2_optional_layouts(*flags)

@@ -1,8 +1,5 @@
-"""GPU (gated): `GraphNetLearner.learn_on_batch` on postprocessed sample-batch columns reproduces the SGD phase of
-`learn_on_rollout` (SURVEY.md §8-f N4 for the shared graph policy).
-
-Written after round 1's GPU budget was spent: executed on CPU with oracle-mocked kernels (tests/host_dryrun_graphnet.py), never on
-a GPU — gated behind DDRL_RUN_UNVALIDATED=1 until its first GPU run."""
+"""GPU: `GraphNetLearner.learn_on_batch` on postprocessed sample-batch columns reproduces the SGD phase of
+`learn_on_rollout` (SURVEY.md §8-f N4 for the shared graph policy)."""
 import os
 
 import numpy as np
@@ -11,9 +8,7 @@ import torch
 
 from tests.test_gpu_graphnet import _dev, _inputs, _theta
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DDRL_RUN_UNVALIDATED") != "1",
-                                 reason="GraphNetLearner.learn_on_batch: never run on a GPU; set DDRL_RUN_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 def test_graphnet_learn_on_batch_is_the_sgd_phase_of_learn_on_rollout():

@@ -1,10 +1,6 @@
-"""GPU (opt-in): the two-launch GraphNet SGD step (`ddrl_graphnet_train_step`: warp-per-row forward + PPO loss + backward to
+"""GPU: the two-launch GraphNet SGD step (`ddrl_graphnet_train_step`: warp-per-row forward + PPO loss + backward to
 the layer inputs, then thread-owned weight-gradient accumulation) against the validated three-kernel step
-(`ddrl_graphnet_forward` + `ddrl_ppo_loss_grad` + `ddrl_graphnet_backward`) and the oracle.
-
-NOT RUN BY DEFAULT: the kernels were written after round 1's GPU budget was spent — they compile for sm_100a but have never
-executed.  `DDRL_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_zz_graphnet_train.py -m gpu` is the first thing to do with
-them on a GPU; the learner uses them only with `GraphNetLearner(two_launch_step=True)`."""
+(`ddrl_graphnet_forward` + `ddrl_ppo_loss_grad` + `ddrl_graphnet_backward`) and the oracle."""
 import os
 
 import numpy as np
@@ -14,9 +10,7 @@ import torch
 from tests.test_gpu_graphnet import _O, _dev, _inputs, _theta
 from tests.util import scaled_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DDRL_RUN_UNVALIDATED") != "1",
-                                 reason="two-launch GraphNet SGD step has not run on a GPU yet; set DDRL_RUN_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _batch(B, A, seed):

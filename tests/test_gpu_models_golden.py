@@ -1,8 +1,6 @@
 """GPU: the CUDA model kernels directly against vectors produced by the reference's own model code
 (tests/golden/make_models_golden.py: `/root/reference/models/*.py` executed on a numpy stand-in for TensorFlow) — the same
-kernels the other GPU tests compare with the oracle, here on the golden inputs and weights (rounded to float32).
-
-Added after round 1's GPU budget was spent: gated behind DDRL_RUN_UNVALIDATED=1 until its first GPU run."""
+kernels the other GPU tests compare with the oracle, here on the golden inputs and weights (rounded to float32)."""
 import os
 
 import numpy as np
@@ -11,10 +9,7 @@ import torch
 
 from tests.util import GOLDEN, scaled_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DDRL_RUN_UNVALIDATED") != "1",
-                                 reason="kernels vs reference-model golden vectors: written after round 1's GPU budget was spent, never run on a GPU; "
-                                        "set DDRL_RUN_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 TOL = 1e-5
 G = np.load(os.path.join(GOLDEN, "models.npz"))
 

@@ -1,7 +1,4 @@
-"""GPU: the optional FCNet layouts of the ModelV2 class (`vf_share_layers`, `free_log_std`) on the two-branch kernels.
-
-Kept in its own, alphabetically LAST GPU test file: it was written after round 1's GPU budget was spent (checked on CPU
-with oracle-mocked kernels only), and is therefore gated behind DDRL_RUN_UNVALIDATED=1 until its first GPU run."""
+"""GPU: the optional FCNet layouts of the ModelV2 class (`vf_share_layers`, `free_log_std`) on the two-branch kernels."""
 import os
 
 import numpy as np
@@ -11,10 +8,7 @@ import torch
 from tests.test_gpu_modelv2 import MODEL_CONFIG, TOL, _O
 from tests.util import scaled_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DDRL_RUN_UNVALIDATED") != "1",
-                                 reason="optional FCNet layouts of the ModelV2 class: written after round 1's GPU budget was spent, never run on a GPU; "
-                                        "set DDRL_RUN_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("vf_share,free_std", [(True, False), (False, True), (True, True)])

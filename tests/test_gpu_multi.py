@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 T, C, E, NB = 16, 64, 2, 4
 ARCH = "FullyDecentral"
+UPD_TOL = 0.2
 
 
 def _problem():
@@ -77,13 +78,15 @@ def _worker_body(rank, world, port, q, mode, fuse, graph):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("mode,fuse,graph", [("fp32", True, False), ("fp32", False, False), ("tc", True, True)],
-                         ids=["fp32-peer", "fp32-nccl", "tc-peer-graph"])
-def test_two_gpu_learner_equals_one_gpu_learner(mode, fuse, graph):
-    """fuse=True: ONE kernel per step with the in-kernel NVLink all-reduce (csrc/sgd_tail.cuh); fuse=False: NCCL."""
+                         ids=["fp32-peer", "fp32-nccl", "tc-peer-persistent"])
+def test_multi_gpu_learner_equals_one_gpu_learner(mode, fuse, graph, world):
+    """the G-GPU run equals the 1-GPU run on the same global batch.
+    fuse=True: ONE kernel per step with the in-kernel NVLink all-reduce (csrc/sgd_tail.cuh); fuse=False: NCCL."""
     import torch.multiprocessing as mp
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -125,7 +128,11 @@ def test_two_gpu_learner_equals_one_gpu_learner(mode, fuse, graph):
     for p in range(pr["P"]):
         upd1 = th1[p].astype(np.float64) - pr["theta"][p]
         upd2 = th2[p].astype(np.float64) - pr["theta"][p]
-        assert scaled_err(th2[p], th1[p]) < 1e-4
-        assert scaled_err(upd2, upd1) < 0.2          # FP32 reduction order differs; Adam amplifies
+        e_th, e_upd = scaled_err(th2[p], th1[p]), scaled_err(upd2, upd1)
+        if os.environ.get("DDRL_ERRLOG"):
+            with open(os.environ["DDRL_ERRLOG"], "a") as f:
+                f.write(f"multi world={world} mode={mode} fuse={fuse} p={p} theta_err={e_th:.3e} update_err={e_upd:.3e}\n")
+        assert e_th < 1e-4
+        assert e_upd < UPD_TOL          # FP32 reduction order differs; Adam amplifies
         for k in ("total_loss", "policy_loss", "vf_loss", "kl", "entropy"):
             assert abs(stats2[p][k] - stats1[p][k]) < 1e-4 * max(1.0, abs(stats1[p][k])), (k, stats2[p][k], stats1[p][k])
