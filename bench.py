@@ -33,6 +33,18 @@ METRIC = "PPO learner agent-steps/sec (fwd+GAE+update)"
 UNIT = "agent-steps/s"
 
 
+def workload_config(envs, world, nb, sets):
+    """The workload description both arms print as `config` (identical dicts at the same --gpus / --envs / --minibatches)."""
+    W = WORKLOAD
+    C = envs * (W["Ag"] // W["P"])
+    R = W["T"] * C
+    return {"workload": W["name"], "policies": W["P"], "agents_per_env": W["Ag"], "obs_dim": W["D"], "act_dim": W["A"],
+            "envs_per_gpu": envs, "envs_total": envs * world, "fragment_T": W["T"], "rows_per_policy_per_gpu": R,
+            "num_sgd_iter": W["epochs"], "minibatches_per_epoch": nb, "sgd_minibatch_size_global": (R // nb) * world,
+            "inputs": f"{sets} rotating synthetic rollout sets per GPU (seeds 1234 + rank + 100 * set), visited round robin: "
+                      "the sets exceed the 126 MB L2 in aggregate, no explicit flush"}
+
+
 def flops_per_agent_step(D, A, E):
     """MACs = (1+3E)*F - 128*E*D, F = 128D + 128A + 8256; flops = 2x."""
     F = 128 * D + 128 * A + 8256
@@ -108,78 +120,116 @@ def synth_rollout(P, T, C, D, A, envs, nb, E, seed, device=None, pinned=False):
     return out
 
 
+class CpuLearner:
+    """The oracle's float32 torch twin (CPU restatement of the reference's TF-CPU learner iteration: RLlib 1.0.1 around the
+    reference's models) with persistent policy state, on `envs` environments of the workload (same P/D/A/T/E and
+    minibatches per epoch).  The P policies are independent, so they run on P host threads, each with cores/P intra-op
+    threads (measured faster than one policy at a time with all cores: the matrices are small)."""
+
+    def __init__(self, envs, nb=None, threads=None):
+        import torch
+        import oracle.ddrl_oracle as O
+        self.O, self.torch = O, torch
+        W = WORKLOAD
+        self.P, self.D, self.A, self.T, self.E = W["P"], W["D"], W["A"], W["T"], W["epochs"]
+        self.nb = nb or W["minibatches_per_epoch"]
+        self.envs, self.Ag = envs, W["Ag"]
+        self.C = envs * (W["Ag"] // self.P)
+        self.threads = threads or os.cpu_count() or 1
+        self.par = self.P if self.threads >= 2 * self.P else 1
+        torch.set_num_threads(max(1, self.threads // self.par))
+        self.cfg = O.PPOConfig(num_sgd_iter=self.E, sgd_minibatch_size=(self.T * self.C) // self.nb)
+        gen = torch.Generator().manual_seed(1234)
+        self.pols = [O.PolicyState(O.fcnet_init(self.D, 2 * self.A, gen),
+                                   O.AdamState.zeros(O.n_params(O.fcnet_shapes(self.D, 2 * self.A)), torch.float32, self.cfg),
+                                   O.MeanStdFilter((self.D,), clip=None), self.cfg.kl_coeff) for _ in range(self.P)]
+
+    def rollout(self, seed):
+        r = synth_rollout(self.P, self.T, self.C, self.D, self.A, self.envs, self.nb, self.E, seed)
+        return {k: v.numpy() for k, v in r.items()}
+
+    def iteration(self, r):
+        """One learner iteration on rollout set r -> seconds."""
+        O, A, cfg = self.O, self.A, self.cfg
+
+        def one(p):
+            sl = slice(p, p + 1)
+            return O.fcnet_learner_iteration(self.pols[sl], r["raw"][sl], r["boot"][sl], r["rewards"][sl], r["dones"], r["eps"][sl],
+                                             r["shuffle"][sl], r["perms"][sl], 2 * A, cfg, self.torch.float32)
+        t0 = time.perf_counter()
+        if self.par > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(self.par) as ex:
+                list(ex.map(one, range(self.P)))
+        else:
+            for p in range(self.P):
+                one(p)
+        return time.perf_counter() - t0
+
+    def agent_steps(self):
+        return self.T * self.envs * self.Ag
+
+
 def cpu_iteration_baseline(envs, seed=0, threads=None):
-    """The oracle's float32 torch twin (CPU restatement of the reference's TF-CPU learner iteration) on a bounded
-    sample of the workload: same P/D/A/T/E and minibatches-per-epoch, `envs` environments.  -> agent-steps/s."""
-    import torch
-    import oracle.ddrl_oracle as O
-    W = WORKLOAD
-    P, D, A, T, E, nbw = W["P"], W["D"], W["A"], W["T"], W["epochs"], W["minibatches_per_epoch"]
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    C = envs * (W["Ag"] // P)
-    R = T * C
-    MB = R // nbw
-    r = synth_rollout(P, T, C, D, A, envs, nbw, E, seed)
-    cfg = O.PPOConfig(num_sgd_iter=E, sgd_minibatch_size=MB)
-    gen = torch.Generator().manual_seed(seed)
-    pols = [O.PolicyState(O.fcnet_init(D, 2 * A, gen), O.AdamState.zeros(O.n_params(O.fcnet_shapes(D, 2 * A)), torch.float32, cfg),
-                          O.MeanStdFilter((D,), clip=None), cfg.kl_coeff) for _ in range(P)]
-    t0 = time.perf_counter()
-    O.fcnet_learner_iteration(pols, r["raw"].numpy(), r["boot"].numpy(), r["rewards"].numpy(), r["dones"].numpy(),
-                              r["eps"].numpy(), r["shuffle"].numpy(), r["perms"].numpy(), 2 * A, cfg, torch.float32)
-    dt = time.perf_counter() - t0
-    return T * envs * W["Ag"] / dt, dt, threads
+    """One CPU learner iteration on a bounded sample (`envs` environments) -> (agent-steps/s, seconds, threads)."""
+    L = CpuLearner(envs, threads=threads)
+    dt = L.iteration(L.rollout(seed))
+    return L.agent_steps() / dt, dt, L.threads
 
 
 # ------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  TF/Ray cannot be installed here
-    (DESIGN.md), so this times the oracle port (float32 torch twin) with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path, on OUR arm's config (same envs per GPU, T,
+    epochs, minibatches; the same rotating synthetic rollout sets).  TF/Ray cannot be installed here, so
+    this times the oracle port (float32 torch twin of the RLlib 1.0.1 learner iteration) with all host threads.  Under
+    torchrun rank 0 alone runs it (one GPU's share of the workload: the metric is per-job agent-steps/s of the CPU path)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)      # torchrun pins it to 1: the CPU arm may use every host core
     W = WORKLOAD
-    envs = args.ref_envs
-    vals = []
+    envs, nb = args.envs, args.minibatches
+    L = CpuLearner(envs, nb=nb, threads=os.cpu_count() or 1)
+    sets = [L.rollout(1234 + 100 * s_) for s_ in range(args.sets)]
+    times = []
     for i in range(args.warmup + args.steps):
-        v, dt, threads = cpu_iteration_baseline(envs, seed=i)
+        dt = L.iteration(sets[i % len(sets)])
         if i >= args.warmup:
-            vals.append((v, dt))
-    value = float(np.mean([v for v, _ in vals]))
-    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
-    sample = f"{envs} of {W['envs_per_gpu']} envs x T={W['T']} x {W['Ag']} agents per step, same P/D/A/epochs/minibatches-per-epoch"
+            times.append(dt)
+    ms = float(np.mean(times) * 1e3)
+    value = L.agent_steps() / (ms * 1e-3)
+    sample = (f"all {envs} envs x T={W['T']} x {W['Ag']} agents per step (the full per-GPU workload of the GPU arm), "
+              f"{L.par} policy threads x {max(1, L.threads // L.par)} intra-op threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": W["name"], "policies": W["P"], "obs_dim": W["D"], "act_dim": W["A"], "envs": envs,
-                   "fragment_T": W["T"], "num_sgd_iter": W["epochs"], "minibatches_per_epoch": W["minibatches_per_epoch"],
-                   "note": "oracle port (torch CPU float32 twin of the RLlib 1.0.1 learner iteration); TF/Ray not installable"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(envs, 1, nb, args.sets),
+        "note": "oracle port (torch CPU float32 twin of the RLlib 1.0.1 learner iteration); TF/Ray are not installable offline; "
+                "one GPU's share of the workload on the host cores whatever --gpus says",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": L.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def run_graphnet(args):
-    """Supplementary line (not the headline): BASELINE.json configs[3] — shared GraphNet policy over the 4-leg graph,
-    4096 envs x 4 agents, T=32, one weight set; minibatch = rows/32; --steps learner iterations with E epochs."""
+def time_graphnet(envs, epochs, steps, warmup, two_launch=True):
+    """BASELINE.json configs[3] — shared GraphNet policy over the 4-leg graph, `envs` envs x 4 agents, T=32, one weight set,
+    minibatch = rows/32; -> (ms per learner iteration, config dict)."""
     import torch
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import GraphNetLearner
     from ddrl_b200.modelv2 import _FlatParams, graphnet_shapes
     from ddrl_b200.policies import QuantrupedDecentralizedSharedGraphEnv
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    A, T, N, E = 2, 32, args.envs, args.gn_epochs
+    dev = torch.device("cuda", torch.cuda.current_device())
+    A, T, N, E = 2, 32, envs, epochs
     C, R = N * 4, T * N * 4
     nb = 32
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=R // nb)
     g = torch.Generator().manual_seed(7)
     th = _FlatParams(graphnet_shapes(2 * A)).init_host(g, small=("actor/linear_out", "critic/linear_out")).reshape(1, -1)
-    L = GraphNetLearner(A, cfg, dev, theta=th, two_launch_step=args.gn_two_launch)
+    L = GraphNetLearner(A, cfg, dev, theta=th, two_launch_step=two_launch)
     state = torch.randn(T, C, 4, 23, generator=g).to(dev)
     idx = torch.arange(4, dtype=torch.int32).repeat(T * N).reshape(T, C).to(dev)
     adj = torch.from_numpy(QuantrupedDecentralizedSharedGraphEnv.create_adj()).float().expand(T, C, 4, 4).contiguous().to(dev)
@@ -191,22 +241,108 @@ def run_graphnet(args):
 
     def step():
         return L.learn_on_rollout(idx, state, adj, idx[0], state[0], adj[0], rewards, dones, eps, perms, shuffle)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"metric": METRIC, "value": T * N * 4 / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+    ms = e0.elapsed_time(e1) / steps
+    return ms, {"workload": "Shared GraphNet policy over the 4-leg graph (BASELINE.json configs[3])", "envs": N, "fragment_T": T,
+                "rows": R, "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_step": getattr(L, "step_kind", "two-launch" if two_launch else "three-kernel")}
+
+
+def run_graphnet(args):
+    """Supplementary line (not the headline): BASELINE.json configs[3]."""
+    import torch
+    torch.cuda.set_device(0)
+    ms, cfgd = time_graphnet(args.envs, args.gn_epochs, args.steps, args.warmup, not args.gn_three_kernel)
+    print(json.dumps({"metric": METRIC, "value": cfgd["rows"] / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "Shared GraphNet policy over the 4-leg graph (BASELINE.json configs[3])",
-                                 "envs": N, "fragment_T": T, "rows": R, "num_sgd_iter": E, "minibatches_per_epoch": nb,
-                                 "sgd_step": "two-launch (opt-in)" if args.gn_two_launch else "forward + loss + backward",
-                                 "note": "supplementary; FP32 kernels, eager launches"}}))
+                      "config": dict(cfgd, note="supplementary")}))
+
+
+def time_fcnet(arch, envs, nb, mode, steps, warmup, sets=2):
+    """A short resident-input timing of one architecture / shape on the current device (same harness as the headline, fewer
+    steps) -> dict(agent-steps/s, ms per iteration, us per optimizer step)."""
+    import torch
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import FCNetLearner
+    from ddrl_b200.modelv2 import fcnet_init_flat
+    from ddrl_b200.policies import ARCHITECTURES
+    tvel = arch.endswith("_TVel")
+    env = ARCHITECTURES["QuantrupedMultiEnv_" + arch.replace("_TVel", "")]
+    P, Ag, D, A = len(env.policy_names), len(env.agent_names), env.obs_dim(tvel), env.act_dim()
+    T, E = WORKLOAD["T"], WORKLOAD["epochs"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    C = envs * (Ag // P)
+    R = T * C
+    cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=R // nb)
+    gen = torch.Generator().manual_seed(1234)
+    L = FCNetLearner(P, D, A, cfg, dev, theta=torch.stack([fcnet_init_flat(D, 2 * A, gen) for _ in range(P)]), mode=mode)
+    rs = [synth_rollout(P, T, C, D, A, envs, nb, E, 77 + s_, device=dev) for s_ in range(sets)]
+
+    def step(i):
+        r = rs[i % sets]
+        return L.learn_on_rollout(r["raw"], r["boot"], r["rewards"], r["dones"], r["eps"], r["perms"], r["shuffle"])
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # the SGD phase alone: E launches (persistent) or E * nb steps
+    b = L._bufs
+    src = {n_: b[n_ + "_s"] for n_ in ("obs", "act", "logits", "logp", "value", "adv", "vtarg")}
+    MB, _, G = L._sgd_setup(R)
+    hyper = L._hyper(MB)
+    pers = L._persistent_steps(G)
+    L.step_ctr.zero_()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nl = E if pers else min(E * nb, 64)
+    e0.record()
+    for _ in range(nl):
+        L._sgd_step(b, MB, G, hyper, src, nsteps=nb if pers else 1)
+    e1.record()
+    torch.cuda.synchronize()
+    us_step = 1e3 * e0.elapsed_time(e1) / (nl * (nb if pers else 1))
+    del L, rs
+    return {"arch": arch, "policies": P, "agents_per_env": Ag, "obs_dim": D, "act_dim": A, "envs": envs, "rows_per_policy": R,
+            "minibatches_per_epoch": nb, "sgd_minibatch_size": R // nb, "mode": mode, "value": T * envs * Ag / (ms * 1e-3),
+            "unit": UNIT, "ms_per_step": ms, "us_per_sgd_step": us_step, "steps": steps, "warmup": warmup}
+
+
+def run_supplementary(args):
+    """Short resident-input runs of the other BASELINE.json configs (3 timed iterations each after 2 warm-ups; the headline
+    stays configs[1]): C1 the reference's own latency-bound minibatch shape, Local, Centralized, the FP32-parity SGD kernel
+    and the shared GraphNet policy at the configured 10 epochs."""
+    import torch
+    out = {}
+    jobs = [("C1_reference_minibatch_shape_FullyDecentral_16000rows_MB128", ("FullyDecentral", 500, 125, "tc")),
+            ("C1_Centralized_16000rows_MB128", ("Centralized", 500, 125, "tc")),
+            ("C3_Local", ("Local", args.envs, args.minibatches, "tc")),
+            ("Centralized", ("Centralized", args.envs, args.minibatches, "tc")),
+            ("FullyDecentral_fp32_parity_kernel", ("FullyDecentral", args.envs, args.minibatches, "fp32"))]
+    for name, (arch, envs, nb, mode) in jobs:
+        try:
+            out[name] = time_fcnet(arch, envs, nb, mode, 3, 2)
+        except Exception as exc:      # supplementary only: never lose the headline line
+            out[name] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+    try:
+        ms, cfgd = time_graphnet(args.envs, WORKLOAD["epochs"], 2, 1)
+        out["C4_shared_GraphNet"] = dict(cfgd, value=cfgd["rows"] / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=2, warmup=1)
+    except Exception as exc:
+        out["C4_shared_GraphNet"] = {"error": repr(exc)}
+    return out
 
 
 def main():
@@ -217,22 +353,22 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=WORKLOAD["envs_per_gpu"], help="envs per GPU")
     ap.add_argument("--minibatches", type=int, default=WORKLOAD["minibatches_per_epoch"])
-    ap.add_argument("--ref-envs", type=int, default=512, help="envs in the CPU sample of --impl reference")
     ap.add_argument("--cpu-envs", type=int, default=1024, help="envs in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-supplementary", action="store_true", help="skip the short supplementary runs of the other BASELINE configs")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--mode", default="tc", choices=["tc", "fp32"], help="SGD-step kernel: tcgen05 split-fp16 or FP32 FMA")
     ap.add_argument("--tc-variant", type=int, default=0, choices=[0, 1, 2],
                     help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per policy of the SGD-step kernel (0 = the learner's choice)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
-    ap.add_argument("--gn-two-launch", action="store_true", help="graphnet workload: ddrl_graphnet_train_step (opt-in, see DESIGN.md §7)")
+    ap.add_argument("--gn-three-kernel", action="store_true", help="graphnet workload: forward + loss + row-per-CTA backward (A/B)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
     ap.add_argument("--arch", default="FullyDecentral",
                     help="supplementary: any published architecture (Centralized, FullyDecentral, Local, SingleNeighbor, "
                          "SingleDiagonal, SingleToFront, TwoSides, TwoDiags; append _TVel for the target-velocity obs); "
                          "the headline line is the default FullyDecentral = BASELINE.json configs[1]")
-    ap.add_argument("--gn-epochs", type=int, default=2)
+    ap.add_argument("--gn-epochs", type=int, default=WORKLOAD["epochs"])
     args = ap.parse_args()
     if args.arch != "FullyDecentral":      # supplementary architectures: same harness, the architecture's P / D / A
         from ddrl_b200.policies import ARCHITECTURES
@@ -416,27 +552,47 @@ def main():
     except Exception:
         pass
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6
-    fp32_peak = 148 * 128 * 2 * sm_clock / 1e12
+    # DRAM traffic of that kernel: read from the committed ncu artefact of the same launch shape (never a constant here)
+    traffic, traffic_note = None, "no ncu --set full capture of this launch shape under profiles/"
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        for ent in tr["captures"]:
+            c = ent["shape"]
+            if (c["arch"] == args.arch and c["envs_per_gpu"] == envs and c["minibatches_per_epoch"] == nb and c["mode"] == args.mode
+                    and c["sgd_steps_per_launch"] == steps_per_launch and c["world"] == world):
+                traffic = float(ent["dram_bytes_read"]) + float(ent["dram_bytes_write"])
+                traffic_note = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full: profiles/{ent['source']}"
+    except Exception:
+        pass
     kname = (("fcnet_train_tc2_kernel" if K.tc_pingpong_eligible(D, A) else "fcnet_train_tc_kernel") +
              " (fused fwd + PPO loss + bwd + grad reduce + clip + Adam; tcgen05 kind::f16, fp16 hi/lo split x3 products, TMEM accum)"
              if args.mode == "tc" else "fcnet_train_kernel (fused fwd + PPO loss + bwd + grad reduce + clip + Adam, FP32 FMA parity mode)")
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-                "traffic": (69.41e6 if (persistent and args.mode == "tc" and envs == 4096 and nb == 32 and args.arch == "FullyDecentral") else None),
-                "traffic_note": "dram__bytes_read+write per launch (32 steps), ncu --set full, profiles/r01_ncu_train_tc2_persistent_summary.txt",
+                "traffic": traffic, "traffic_note": traffic_note,
                 "launch_ms": k_ms, "flops_per_launch": flops_launch, "sgd_steps_per_launch": steps_per_launch,
                 "us_per_sgd_step": 1e3 * k_ms / steps_per_launch,
                 "note": "latency/issue-bound: 4096 rows x 4 policies per step = one 128-row tile per SM (DESIGN.md §4)",
-                "fp32_fma_pipe": {"peak": fp32_peak, "frac": achieved_tf / fp32_peak,
-                                  "note": "148 SM x 128 lanes x 2 x measured SM clock; the pipe this FP32-parity kernel runs on"},
                 "share_of_step": (steps_per_iter / steps_per_launch) * k_ms / (ms_total / args.steps)}
+
+    # replicated state must be bit-identical on every rank: 64-bit checksum of the weights and Adam slots
+    def checksum(t):
+        return t.contiguous().view(torch.int32).to(torch.int64).sum()
+    cks = torch.stack([checksum(L.theta), checksum(L.m), checksum(L.v)])
+    ranks_identical = True
+    if world > 1:
+        allc = [torch.empty_like(cks) for _ in range(world)]
+        dist.all_gather(allc, cks)
+        ranks_identical = all(bool(torch.equal(a_, allc[0])) for a_ in allc)
+    supplementary = None
+    if rank == 0 and world == 1 and not args.no_supplementary and args.arch == "FullyDecentral" and args.mode == "tc":
+        supplementary = run_supplementary(args)
 
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (at N > 1 the other ranks would idle on metered GPUs)
             v, dt, threads = cpu_iteration_baseline(args.cpu_envs)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_envs} of {envs} envs, one full learner iteration ({dt:.1f} s), torch CPU float32 twin of the oracle"}
@@ -445,15 +601,16 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.mode == "fp32" else "f32 (tcgen05 GEMMs on fp16 hi+lo split operands, f32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": W["name"], "policies": P, "agents_per_env": Ag, "obs_dim": D, "act_dim": A,
-                       "envs_per_gpu": envs, "envs_total": envs * world, "fragment_T": T, "rows_per_policy_per_gpu": R,
-                       "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_minibatch_size_global": MB_local * world,
-                       "parallelism": f"dp{world} (shard by env, NCCL grad all-reduce per optimizer step)" if world > 1 else "single GPU",
-                       "cuda_graph": bool(L.use_graph and L._graph is not None), "sgd_kernel": args.mode,
-                       "kernels_per_sgd_step": per_sgd,
-                       "persistent_sgd_launch": bool(L._persistent_steps(G_)), "ctas_per_policy": G_,
-                       "cluster_size": K.tc_last_cluster() if args.mode == "tc" else 0,
-                       "l2": f"{args.sets} rotating rollout sets x {bytes_per_set / 1e6:.0f} MB (> 126 MB L2 in aggregate)"},
+            "config": dict(workload_config(envs, world, nb, args.sets),
+                           parallelism=(f"dp{world}: rollout sharded by env, one process per GPU; the gradient all-reduce of every optimizer "
+                                        "step runs INSIDE the SGD-step kernel over NVLink peer memory (no NCCL call on the per-step "
+                                        "path); NCCL only for the per-iteration filter / advantage-moment / stat exchanges")
+                           if world > 1 else "single GPU"),
+            "impl_detail": {"cuda_graph_prepare_phase": bool(L.use_graph and L._prep_graphs), "sgd_kernel": args.mode,
+                            "kernels_per_sgd_step": per_sgd, "persistent_sgd_launch": bool(L._persistent_steps(G_)),
+                            "ctas_per_policy": G_, "cluster_size": K.tc_last_cluster() if args.mode == "tc" else 0,
+                            "bytes_per_rollout_set": int(bytes_per_set)},
+            "ranks_identical": ranks_identical,
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nb * P * 8 * 8),
                     "inputs": "pinned host: full 43-dim observations per env step (+ boot obs, rewards, dones, perms, shuffle); "
@@ -465,6 +622,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "flops_per_agent_step": flops_per_agent_step(D, A, E),
+            "supplementary": supplementary,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 T, C, E, NB = 16, 64, 2, 4
 ARCH = "FullyDecentral"
-UPD_TOL = 0.2
+UPD_TOL = 2e-3     # measured on hardware: 5e-5 (world 2); was 0.2 before the test had ever run
 
 
 def _problem():
