@@ -214,7 +214,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def time_graphnet(envs, epochs, steps, warmup, two_launch=True):
+def time_graphnet(envs, epochs, steps, warmup, two_launch=False):
     """BASELINE.json configs[3] — shared GraphNet policy over the 4-leg graph, `envs` envs x 4 agents, T=32, one weight set,
     minibatch = rows/32; -> (ms per learner iteration, config dict)."""
     import torch
@@ -259,7 +259,7 @@ def run_graphnet(args):
     """Supplementary line (not the headline): BASELINE.json configs[3]."""
     import torch
     torch.cuda.set_device(0)
-    ms, cfgd = time_graphnet(args.envs, args.gn_epochs, args.steps, args.warmup, not args.gn_three_kernel)
+    ms, cfgd = time_graphnet(args.envs, args.gn_epochs, args.steps, args.warmup, args.gn_two_launch)
     print(json.dumps({"metric": METRIC, "value": cfgd["rows"] / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                       "config": dict(cfgd, note="supplementary")}))
@@ -362,7 +362,7 @@ def main():
                     help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per policy of the SGD-step kernel (0 = the learner's choice)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
-    ap.add_argument("--gn-three-kernel", action="store_true", help="graphnet workload: forward + loss + row-per-CTA backward (A/B)")
+    ap.add_argument("--gn-two-launch", action="store_true", help="graphnet workload: ddrl_graphnet_train_step (A/B; measured slower than the three-kernel step)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
     ap.add_argument("--arch", default="FullyDecentral",
                     help="supplementary: any published architecture (Centralized, FullyDecentral, Local, SingleNeighbor, "

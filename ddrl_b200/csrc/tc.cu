@@ -37,7 +37,6 @@ umma_selftest_kernel(const float* __restrict__ A, int ra, int ca, const float* _
     }
     const uint32_t ncols = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     if (warp == 0) umma::tmem_alloc(&tmem_slot, ncols);
-    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); }
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
@@ -119,7 +118,6 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int M, int N, int a_
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smraw)[i] = 0x3c003c00u;   // 1.0h
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
-    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); }
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
@@ -127,33 +125,54 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int M, int N, int a_
     const uint32_t taddr = tmem_slot;
     long long t0 = 0, t1 = 0, t2 = 0;
     bool ok = true;
-    if (warp == 0) {
+    // ksteps encodes the experiment: bits [0,8) k-steps per rep; bit 8: elect.sync instead of `lane == 0`;
+    // bits [9,12): accumulators - 1 the issuing thread cycles through (independent MMA chains, N columns apart);
+    // bits [12,14): log2(issuing warps) — warp w issues the same stream into its own accumulator set (128 columns apart)
+    // bit 14: warp-uniform issue (umma::mma_f16_elect, operands made provably uniform with __shfl_sync)
+    const int mode = (ksteps >> 8) & 1, nacc = ((ksteps >> 9) & 7) + 1, nwarps = 1 << ((ksteps >> 12) & 3);
+    const bool uniform = (ksteps >> 14) & 1;
+    ksteps &= 255;
+    if (tid == 0) { umma::mbar_init(&mbar, nwarps); umma::fence_mbar_init(); }
+    __syncthreads();
+    if (warp < nwarps) {
         const uint32_t idesc = umma::idesc_f16(M, N, a_mn != 0, b_mn != 0);
         const uint32_t sa = umma::smem_u32(smraw), sb = sa + 48 * 1024;
         const uint64_t ad0 = a_mn ? umma::desc_mnmajor(sa, 128) : umma::desc_kmajor(sa, 128);
         const uint64_t bd0 = b_mn ? umma::desc_mnmajor(sb, 128) : umma::desc_kmajor(sb, 128);
         const uint64_t astep = a_mn ? 16u : 256u, bstep = b_mn ? 16u : 256u;
-        // mode (ksteps >> 8): 0 = `if (lane == 0)` branch; 1 = elect.sync-selected lane, warp-uniform control flow around it
-        const int mode = ksteps >> 8;
-        ksteps &= 255;
         uint32_t elected = 0;
         if (mode == 1) {
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
         } else {
-            elected = (tid == 0);
+            elected = ((tid & 31) == 0);
         }
+        const uint32_t tbase = taddr + (nwarps > 1 ? 128 * warp : 0);
         t0 = clock64();
-        if (elected) {
+        if (uniform) {
+            const uint32_t tb_u = __shfl_sync(0xffffffffu, tbase, 0);
+            for (int r = 0; r < reps; ++r) {
+                uint64_t ad = ad0, bd = bd0;
+#pragma unroll 4
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    for (int ac = 0; ac < nacc; ++ac) umma::mma_f16_elect(tb_u + (uint32_t)(ac * N), ad, bd, idesc, 1u);
+                    ad += astep; bd += bstep;
+                }
+            }
+            __syncwarp();
+            t1 = clock64();
+            umma::mma_commit_elect(&mbar);
+            elected = 0;
+        } else if (elected) {
             for (int r = 0; r < reps; ++r) {
                 uint64_t ad = ad0, bd = bd0;
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    umma::mma_f16(taddr, ad, bd, idesc, true);
+                    for (int ac = 0; ac < nacc; ++ac) umma::mma_f16(tbase + (uint32_t)(ac * N), ad, bd, idesc, true);
                     ad += astep; bd += bstep;
                 }
             }
         }
         __syncwarp();
-        t1 = clock64();
+        if (!uniform) t1 = clock64();
         if (elected) umma::mma_commit(&mbar);
         __syncwarp();
         ok = umma::mbar_wait(&mbar, 0);

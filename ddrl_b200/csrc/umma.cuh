@@ -59,6 +59,23 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// Warp-uniform issue: EVERY lane of the warp executes this with identical (warp-uniform) operands, one elected lane issues.
+// With operands the compiler can prove uniform (kernel parameters, constants, __shfl_sync(.., 0) results) ptxas keeps the
+// descriptors and the TMEM address in uniform registers and emits a bare UTCHMMA; inside an `if (lane == 0)` branch it
+// wraps every MMA into an ELECT / R2UR / BRA.U.ANY "waterfall" loop (~80-150 cycles per instruction, measured).
+__device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* mbar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(mbar))
+        : "memory");
+}
 // all MMAs issued so far by this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
