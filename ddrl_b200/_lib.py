@@ -31,7 +31,7 @@ class SgdTail(C.Structure):
                 ("step_stats", C.c_void_p), ("step_ctr", C.c_void_p), ("barrier_ws", C.c_void_p), ("sq_ws", C.c_void_p),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_clip", C.c_float),
                 ("status", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("seq", C.c_void_p),
-                ("peer_x", C.c_void_p * MAX_RANKS), ("nsteps", C.c_int32)]
+                ("peer_x", C.c_void_p * MAX_RANKS), ("nsteps", C.c_int32), ("ll_ws", C.c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/ddrl_b200.h one to one (tests check every symbol).
@@ -86,6 +86,7 @@ PROTOTYPES = {
                                    c_stream]),
     "ddrl_dg_sample": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_f32p, c_stream]),
     "ddrl_leg_coupling": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int, c_stream]),
+    "ddrl_leg_coupling_backward": (C.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int, c_f32p, c_stream]),
     "ddrl_fcnet_tc_image_bytes": (C.c_int, [C.c_int, C.c_int]),
     "ddrl_fcnet_forward_tc": (C.c_int, [C.c_void_p, c_f32p, c_f64p, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_int,
                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_stream]),
@@ -100,6 +101,7 @@ PROTOTYPES = {
     "ddrl_tc_set_debug_clock": (C.c_int, [C.c_void_p]),
     "ddrl_umma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_i32p, c_stream]),
     "ddrl_sgd_exchange_words": (C.c_int64, [C.c_int, C.c_int]),
+    "ddrl_sgd_ll_words": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ddrl_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "ddrl_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ddrl_peer_close": (C.c_int, [C.c_void_p]),

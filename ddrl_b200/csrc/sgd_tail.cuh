@@ -352,6 +352,380 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
 #undef TAIL_STAMP
 }
 
+// =====================================================================================================================
+// "LL" tail (ping-pong tcgen05 kernel, ddrl_sgd_tail.ll_ws != NULL): the same arithmetic as sgd_step_tail, but every
+// cross-CTA hand-off inside a step travels as self-validating 64-bit words {payload, step tag} (NCCL-"LL" style) instead
+// of plain data behind a release / acquire barrier:
+//
+//   write-out   each CTA stores its partial gradient (and its 8 float64 loss statistics as 16 half words) as LL words
+//   reduce      the owner of slice bx reads the G partial slices — polling only words whose tag is not this step's yet —
+//               and adds them in a fixed order (no barrier A, no store drain before an arrival)
+//   [world > 1] peer exchange, unchanged (it already was an LL exchange)
+//   norm        tagged ||g_slice||^2 words, unchanged ("barrier B")
+//   Adam        on the slice; the new weights are PUBLISHED as LL words in tensor-core image order
+//               {fp16 hi | fp16 lo << 16, tag} (biases: {fp32, tag}), index = image byte offset / 2
+//   next step   every CTA rebuilds its shared-memory weight image from those words (ll_load_image: no barrier C, no
+//               second pass over a global image behind it)
+//
+// Buffers are single (not double-buffered): a CTA writes the partial of step s+1 only after it has read every owner's
+// weights of step s, and an owner publishes those only after it has read every partial of step s.  Tags are the global
+// step count (ts.epoch + round >= 1); the workspace starts zeroed.  All sums keep a fixed order: bit-reproducible.
+__host__ __device__ inline int ll_part_words(int NP) { return ((NP + 3) & ~3) + 2 * DDRL_NSTAT; }
+__host__ __device__ inline int64_t ll_img_words(int D, int A) { return tc_img(D, A).bytes / 2; }
+__host__ __device__ inline int64_t ll_total_words(int P, int G, int NP, int D, int A) {
+    return (int64_t)P * G * ll_part_words(NP) + (int64_t)P * ll_img_words(D, A);
+}
+
+__device__ __forceinline__ void ll_st1(unsigned long long* p, unsigned int payload, unsigned int tag) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | payload) : "memory");
+}
+__device__ __forceinline__ void ll_st2(unsigned long long* p, unsigned int a, unsigned int b, unsigned int tag) {
+    const unsigned long long t = (unsigned long long)tag << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(t | a), "l"(t | b) : "memory");
+}
+__device__ __forceinline__ void ll_ld2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long* p) {
+    unsigned long long a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+constexpr unsigned int LL_SPINS = 4000000u;
+
+// One matrix of the image: nel fp16 elements at byte offsets hi_off / lo_off (chunked layout, element offset e).
+// kind 0: W1 [64][KX] chunked along d (element real iff d < D); 1: W2 (all real); 2: WoT (real iff row o < nreal).
+// Real elements are taken from the LL words (waiting for this step's tag), padding is written as zero.
+__device__ __forceinline__ bool ll_load_matrix(const unsigned long long* __restrict__ img, unsigned char* sm, int hi_off, int lo_off,
+                                               int nel, int kind, int lim, unsigned int tag, int tid, int nt) {
+    bool ok = true;
+    const int npair = nel >> 1;
+    const unsigned long long* src = img + (hi_off >> 1);
+#pragma unroll 1
+    for (int b0 = tid; b0 < npair; b0 += 4 * nt) {
+        unsigned long long w0[4], w1[4];
+        unsigned int need = 0u;      // bit 2k: first element of pair k is real, bit 2k+1: second
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pr = b0 + k * nt, e = 2 * pr;
+            w0[k] = 0ull; w1[k] = 0ull;
+            if (pr < npair) {
+                bool r0, r1;
+                if (kind == 0)      { const int d = ((e >> 9) << 3) + (e & 7); r0 = d < lim; r1 = d + 1 < lim; }
+                else if (kind == 1) { r0 = r1 = true; }
+                else                { r0 = r1 = ((e >> 3) & (TC_NO - 1)) < lim; }
+                need |= (r0 ? 1u : 0u) << (2 * k) | (r1 ? 1u : 0u) << (2 * k + 1);
+            }
+        }
+        unsigned int pending = need;
+#pragma unroll 1
+        for (unsigned int it = 0; pending != 0u && it < LL_SPINS; ++it) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((pending >> (2 * k)) & 3u) ll_ld2(src + 2 * (b0 + k * nt), w0[k], w1[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (((pending >> (2 * k)) & 1u) && (unsigned int)(w0[k] >> 32) == tag) pending &= ~(1u << (2 * k));
+                if (((pending >> (2 * k + 1)) & 1u) && (unsigned int)(w1[k] >> 32) == tag) pending &= ~(1u << (2 * k + 1));
+            }
+        }
+        ok = ok && pending == 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pr = b0 + k * nt;
+            if (pr < npair) {
+                const unsigned int a = ((need >> (2 * k)) & 1u) ? (unsigned int)w0[k] : 0u;
+                const unsigned int b = ((need >> (2 * k + 1)) & 1u) ? (unsigned int)w1[k] : 0u;
+                *reinterpret_cast<unsigned int*>(sm + hi_off + 4 * pr) = (a & 0xffffu) | (b << 16);
+                *reinterpret_cast<unsigned int*>(sm + lo_off + 4 * pr) = (a >> 16) | (b & 0xffff0000u);
+            }
+        }
+    }
+    return ok;
+}
+
+// Rebuild the shared-memory weight image of policy p from the LL words of step `tag` (all nt calling threads take part;
+// the caller publishes the writes to the async proxy).  w1_only: just the W1 matrices (multi-tile CTAs restore them
+// after the loss-gradient operand has used their space).
+__device__ __forceinline__ bool ll_load_image(const SgdTail& t, int p, int P, int G, int NP, int D, int A, unsigned char* sm,
+                                              unsigned int tag, int tid, int nt, bool w1_only) {
+    const TcImg I = tc_img(D, A);
+    const int KX = tc_kx(D);
+    const unsigned long long* img = t.ll_ws + (int64_t)P * G * ll_part_words(NP) + (int64_t)p * ll_img_words(D, A);
+    bool ok = true;
+    ok = ll_load_matrix(img, sm, I.W1[0][0], I.W1[0][1], 64 * KX, 0, D, tag, tid, nt) && ok;
+    ok = ll_load_matrix(img, sm, I.W1[1][0], I.W1[1][1], 64 * KX, 0, D, tag, tid, nt) && ok;
+    if (w1_only) return ok;
+    ok = ll_load_matrix(img, sm, I.W2[0][0], I.W2[0][1], 64 * 64, 1, 0, tag, tid, nt) && ok;
+    ok = ll_load_matrix(img, sm, I.W2[1][0], I.W2[1][1], 64 * 64, 1, 0, tag, tid, nt) && ok;
+    ok = ll_load_matrix(img, sm, I.WoT[0][0], I.WoT[0][1], TC_NO * 64, 2, 2 * A, tag, tid, nt) && ok;
+    ok = ll_load_matrix(img, sm, I.WoT[1][0], I.WoT[1][1], TC_NO * 64, 2, 1, tag, tid, nt) && ok;
+    // fp32 block: b1c[128] b2c[128] bo[16] bvo[4]; real entries: all of b1c / b2c, bo[0 .. 2A), bvo[0]
+#pragma unroll 1
+    for (int k = tid; k < 128 + 128 + 16 + 4; k += nt) {
+        const bool real = k < 256 || (k < 272 ? (k - 256) < 2 * A : k == 272);
+        unsigned int v = 0u;
+        if (real) {
+            unsigned long long w = 0ull;
+            bool hit = false;
+#pragma unroll 1
+            for (unsigned int it = 0; it < LL_SPINS; ++it) {
+                w = ll_ld1(img + (I.b1c >> 1) + 2 * k);
+                if ((unsigned int)(w >> 32) == tag) { hit = true; break; }
+            }
+            ok = ok && hit;
+            v = (unsigned int)w;
+        }
+        *reinterpret_cast<unsigned int*>(sm + I.b1c + 4 * k) = v;
+    }
+    return ok;
+}
+
+// Requires sgd_slice_len(NP, G) <= blockDim.x (thread tid owns element bx * S + tid of the slice).
+__device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailStep& ts, int p, int P, int bx, int G, int NP, int step,
+                                                 int D, int A, float* smem, long long* dbg = nullptr) {
+#define TAIL_STAMP(i)                                                                                              \
+    do {                                                                                                           \
+        if (dbg && threadIdx.x == 0) {                                                                             \
+            if (blockIdx.x == 0 && blockIdx.y == 0) dbg[i] = clock64();                                            \
+            long long gt_;                                                                                         \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                \
+            dbg[64 + 8 * (blockIdx.y * gridDim.x + blockIdx.x) + ((i) - 37)] = gt_;   /* 40..43 -> slots 3..6 */     \
+        }                                                                                                          \
+    } while (0)
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int NPs = (NP + 3) & ~3, LLW = ll_part_words(NP);
+    const unsigned int tag = ts.epoch + (unsigned int)ts.round;
+    float2* scr = reinterpret_cast<float2*>(smem);      // [ngrp][npair]
+    float* red = smem + 4 * nt;                         // [64]: warp partials, flags
+    const int W = t.world > 1 ? t.world : 1;
+    bool ok = true;
+    const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S);
+    const int j_own = j0 + tid;
+    const bool own = tid < S && j_own < NP;
+    // optimizer state of this thread's element: independent of the reduce, the loads fly behind it
+    float m_pf = 0.f, v_pf = 0.f, th_pf = 0.f;
+    if (own) {
+        const int64_t k = (int64_t)p * NP + j_own;
+        m_pf = __ldcg(t.m + k); v_pf = __ldcg(t.v + k); th_pf = __ldcg(t.theta + k);
+    }
+    if (tid == 0) red[40] = 1.f;
+    TAIL_STAMP(40);
+
+    // ---- slice reduce over the G partials: group g adds partials g, g + ngrp, ...; 4 polled loads in flight -----------
+    const int npair = max(0, (j1 - j0) >> 1);
+    const int ngrp = npair > 0 ? max(1, min(min(8, G), nt / npair)) : 1;
+    {
+        const int g = npair > 0 ? tid / npair : ngrp, c = npair > 0 ? tid - g * npair : 0;
+        if (g < ngrp) {
+            const unsigned long long* src = t.ll_ws + (int64_t)p * G * LLW + j0 + 2 * c;
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+            for (int i0 = g; i0 < G; i0 += 4 * ngrp) {
+                unsigned long long a[4], b[4];
+                unsigned int pending = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a[k] = 0ull; b[k] = 0ull;
+                    if (i0 + k * ngrp < G) pending |= 1u << k;
+                }
+#pragma unroll 1
+                for (unsigned int it = 0; pending != 0u && it < LL_SPINS; ++it) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((pending >> k) & 1u) ll_ld2(src + (int64_t)(i0 + k * ngrp) * LLW, a[k], b[k]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (((pending >> k) & 1u) && (unsigned int)(a[k] >> 32) == tag && (unsigned int)(b[k] >> 32) == tag)
+                            pending &= ~(1u << k);
+                }
+                ok = ok && pending == 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {      // words of absent partials are zero
+                    acc.x += __uint_as_float((unsigned int)a[k]);
+                    acc.y += __uint_as_float((unsigned int)b[k]);
+                }
+            }
+            scr[g * npair + c] = acc;
+        }
+    }
+    __syncthreads();
+    float gval = 0.f;      // this thread's reduced gradient element (register-resident up to the Adam update)
+    {
+        float s = 0.f;
+        const bool act = tid < 2 * npair;
+        if (act) {
+            for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * npair + (tid >> 1)])[tid & 1];
+        }
+        const int64_t xstride = (int64_t)G * S;
+        float* slice_dst = t.grad + (int64_t)p * NP + j0;
+        if (W > 1) {
+            // push to every rank's exchange buffer (own copy included), two neighbouring elements as ONE 16-byte store
+            const unsigned int seq = ts.seq;
+            const unsigned long long want = (unsigned long long)(seq + 1u) << 32;
+            const int par = (int)(seq & 1u);
+            const int64_t xoff = (((int64_t)par * W + t.rank) * P + p) * xstride + j0;
+            const float s_nb = __shfl_down_sync(0xffffffffu, s, 1);      // whole warps: npair pairs never straddle a warp edge
+            if (act && j_own < NP && (tid & 1) == 0) {
+                const unsigned long long w0 = want | (unsigned long long)__float_as_uint(s);
+                if (j_own + 1 < NP) {
+                    const unsigned long long w1 = want | (unsigned long long)__float_as_uint(s_nb);
+#pragma unroll 1
+                    for (int w = 0; w < W; ++w)
+                        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(t.peer_x[w] + xoff + tid), "l"(w0), "l"(w1)
+                                     : "memory");
+                } else {
+#pragma unroll 1
+                    for (int w = 0; w < W; ++w) st_relaxed_sys_u64(t.peer_x[w] + xoff + tid, w0);
+                }
+            }
+            // wait for the world's words of this step, add them in rank order
+            if (own) {
+                const unsigned long long* xl = t.peer_x[t.rank] + ((int64_t)par * W * P + p) * xstride + j0 + tid;
+                const unsigned int want32 = seq + 1u;
+                unsigned long long wd[DDRL_MAX_RANKS];
+                unsigned int pending = (1u << W) - 1u;
+#pragma unroll 1
+                for (unsigned int it = 0; pending != 0u && it < 2000000u; ++it) {
+#pragma unroll
+                    for (int w = 0; w < DDRL_MAX_RANKS; ++w)
+                        if ((pending >> w) & 1u) wd[w] = ld_relaxed_sys_u64(xl + (int64_t)w * P * xstride);
+#pragma unroll
+                    for (int w = 0; w < DDRL_MAX_RANKS; ++w)
+                        if (((pending >> w) & 1u) && (unsigned int)(wd[w] >> 32) == want32) pending &= ~(1u << w);
+                }
+                ok = ok && pending == 0u;
+                float sw = 0.f;
+#pragma unroll
+                for (int w = 0; w < DDRL_MAX_RANKS; ++w)
+                    if (w < W) sw += __uint_as_float((unsigned int)wd[w]);      // rank order: identical bits on every rank
+                slice_dst[tid] = sw;
+                gval = sw;
+            }
+        } else if (own) {
+            slice_dst[tid] = s;
+            gval = s;
+        }
+    }
+    // loss statistics: CTA 0 of the policy, warp w sums stat w over the G partials (two 32-bit halves per float64)
+    if (bx == 0 && warp < DDRL_NSTAT && t.step_stats) {
+        double s = 0.0;
+        bool got = true;
+        for (int i = lane; i < G; i += 32) {
+            const unsigned long long* src = t.ll_ws + ((int64_t)p * G + i) * LLW + NPs + 2 * warp;
+            unsigned long long a = 0ull, b = 0ull;
+            bool hit = false;
+#pragma unroll 1
+            for (unsigned int it = 0; it < LL_SPINS; ++it) {
+                ll_ld2(src, a, b);
+                if ((unsigned int)(a >> 32) == tag && (unsigned int)(b >> 32) == tag) { hit = true; break; }
+            }
+            got = got && hit;
+            s += __longlong_as_double((long long)(((b & 0xffffffffull) << 32) | (a & 0xffffffffull)));
+        }
+        s = warp_sum(s);
+        ok = ok && got;
+        if (lane == 0) t.step_stats[((int64_t)step * P + p) * DDRL_NSTAT + warp] = s;
+    }
+    TAIL_STAMP(41);
+    // ---- ||g||^2 of the slice (fixed order) -> tagged words ("barrier B") -> global norm -------------------------------
+    float ss = warp_sum(gval * gval);
+    if (lane == 0) red[warp] = ss;
+    if (!ok) red[40] = 0.f;      // benign race: every writer stores the same value
+    __syncthreads();
+    constexpr int SQ_STRIDE = 16;
+    unsigned long long* sq64 = reinterpret_cast<unsigned long long*>(t.sq_ws) + (int64_t)p * G * SQ_STRIDE;
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += red[w];
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(sq64 + (int64_t)bx * SQ_STRIDE),
+                     "l"(((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(s)) : "memory");
+    }
+    if (warp == 0) {
+        float s = 0.f;
+        bool got = true;
+        for (int i = lane; i < G; i += 32) {
+            unsigned long long w64 = 0ull;
+            bool hit = false;
+#pragma unroll 1
+            for (unsigned int it = 0; it < 8000000u; ++it) {
+                w64 = ll_ld1(sq64 + (int64_t)i * SQ_STRIDE);
+                if ((unsigned int)(w64 >> 32) == tag) { hit = true; break; }
+            }
+            got = got && hit;
+            s += __uint_as_float((unsigned int)w64);
+        }
+        s = warp_sum(s);
+        got = __all_sync(0xffffffffu, got);
+        if (lane == 0) {
+            const float norm = sqrtf(s);
+            red[32] = t.grad_clip > 0.f ? t.grad_clip * fminf(1.f / norm, 1.f / t.grad_clip) : 1.f;
+            red[39] = got ? 1.f : 0.f;
+            if (bx == 0 && t.gnorm_out) t.gnorm_out[p] = norm;
+        }
+    }
+    __syncthreads();
+    ok = red[39] != 0.f && red[40] != 0.f;
+    TAIL_STAMP(42);
+    // ---- clip + TF1 Adam on the slice; publish the new weights as LL words in image order ------------------------------
+    if (own) {
+        const float scale = red[32];
+        const float alpha = t.lr * sqrtf(1.f - ts.b2p) / (1.f - ts.b1p);
+        const int64_t k = (int64_t)p * NP + j_own;
+        const float gj = gval * scale;
+        float mj = m_pf, vj = v_pf;
+        mj += (gj - mj) * (1.f - t.beta1);
+        vj += (gj * gj - vj) * (1.f - t.beta2);
+        const float tnew = th_pf - (mj * alpha) / (sqrtf(vj) + t.eps);
+        const TcImg L = tc_img(D, A);
+        const FcOffsets o = fc_offsets(D, A);
+        bool f16;
+        int p0, p1;
+        tc_img_pos(L, o, D, A, j_own, f16, p0, p1);
+        unsigned long long* limg = t.ll_ws + (int64_t)P * G * LLW + (int64_t)p * ll_img_words(D, A);
+        unsigned char* im = reinterpret_cast<unsigned char*>(t.fcnet_tc_img) + (int64_t)p * L.bytes;
+        if (f16) {
+            const float ws = tnew * 256.f;
+            const __half hi = __float2half_rn(ws);
+            const __half lo = __float2half_rn(ws - __half2float(hi));
+            ll_st1(limg + (p0 >> 1), (unsigned int)__half_as_ushort(hi) | ((unsigned int)__half_as_ushort(lo) << 16), tag);
+            if (t.fcnet_tc_img) {      // the global image serves the first step of the next launch and the inference forward
+                *reinterpret_cast<__half*>(im + p0) = hi;
+                *reinterpret_cast<__half*>(im + p1) = lo;
+            }
+        } else {
+            ll_st1(limg + (p0 >> 1), __float_as_uint(tnew), tag);
+            if (t.fcnet_tc_img) *reinterpret_cast<float*>(im + p0) = tnew;
+        }
+        t.m[k] = mj;
+        t.v[k] = vj;
+        t.theta[k] = tnew;
+    }
+    TAIL_STAMP(43);
+    // ---- last step of the launch: the done ticket advances the clocks ---------------------------------------------------
+    if (ts.last) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (bx == 0) {     // every CTA read beta_pow at kernel entry: safe to advance
+                t.beta_pow[p * 2] = ts.b1p * t.beta1;
+                t.beta_pow[p * 2 + 1] = ts.b2p * t.beta2;
+            }
+            const unsigned int total = gridDim.x * gridDim.y;
+            if (atomicAdd(t.barrier_ws + 4 * P, 1u) == total - 1) {   // last CTA of the grid: clocks
+                t.barrier_ws[4 * P + 1] = ts.epoch + (unsigned int)ts.nsteps;   // every CTA read it at kernel entry
+                if (t.step_ctr) *t.step_ctr += ts.nsteps;
+                if (t.seq) *t.seq = ts.seq + 1u;
+                t.barrier_ws[4 * P] = 0u;
+                __threadfence();
+            }
+        }
+    }
+    if (tid == 0 && !ok && t.status) atomicOr(t.status, 64);
+    return ok;
+#undef TAIL_STAMP
+}
+
 // Host-side validation shared by the launchers.
 inline int sgd_tail_check(const ddrl_sgd_tail* tail, int ctas_total, const char* who) {
     DDRL_REQUIRE(tail->theta && tail->m && tail->v && tail->beta_pow && tail->grad && tail->barrier_ws && tail->sq_ws,
@@ -361,6 +735,7 @@ inline int sgd_tail_check(const ddrl_sgd_tail* tail, int ctas_total, const char*
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     DDRL_REQUIRE(ctas_total <= sms, DDRL_E_BADARG, "%s: fused tail needs all %d CTAs co-resident (%d SMs)", who, ctas_total, sms);
     DDRL_REQUIRE(tail->nsteps >= 0, DDRL_E_BADARG, "%s: fused tail: nsteps must be >= 0", who);
+    DDRL_REQUIRE(!tail->ll_ws || tail->fcnet_tc_img, DDRL_E_BADARG, "%s: fused tail: ll_ws needs the tensor-core image", who);
     if (tail->world > 1) {
         DDRL_REQUIRE(tail->world <= DDRL_MAX_RANKS && tail->rank >= 0 && tail->rank < tail->world && tail->seq, DDRL_E_BADARG,
                      "%s: fused tail: bad world/rank/seq (world <= %d)", who, DDRL_MAX_RANKS);

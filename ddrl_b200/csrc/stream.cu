@@ -490,6 +490,42 @@ __global__ void leg_coupling_kernel(float* __restrict__ logits, const int32_t* _
     }
 }
 
+// LegCoupling backward: dlogits_pre = dout * coeff (in place on dout) and dcoupling[n][j] = sum over rows b with
+// node_id[b] == n of dout[b][j] * logits_pre[b][j], j < 2 (the trainable tf.Variable of the reference layer).
+// ONE block, fixed-order tree reduction over float64 per-thread sums: bit-reproducible (the op is tiny next to the MLP).
+__global__ void __launch_bounds__(1024, 1) leg_coupling_bwd_kernel(float* __restrict__ dout, const float* __restrict__ logits_pre,
+                                                                   const int32_t* __restrict__ node_id,
+                                                                   const float* __restrict__ coupling, int64_t B, int W,
+                                                                   float* __restrict__ dcoupling) {
+    __shared__ double red[32][8];
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        const int n = node_id[b] & 3;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float g = dout[b * W + j];
+            const double prod = (double)g * (double)logits_pre[b * W + j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[2 * q + j] += (q == n) ? prod : 0.0;
+            dout[b * W + j] = g * coupling[n * 2 + j];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        dcoupling[threadIdx.x] = (float)v;
+    }
+}
+
 }  // namespace ddrl
 
 using namespace ddrl;
@@ -679,9 +715,23 @@ extern "C" int ddrl_leg_coupling(float* logits, const int32_t* node_id, const fl
     return DDRL_OK;
 }
 
+extern "C" int ddrl_leg_coupling_backward(float* dout, const float* logits_pre, const int32_t* node_id, const float* coupling,
+                                          int64_t B, int W, float* dcoupling, void* stream) {
+    DDRL_REQUIRE(dout && logits_pre && node_id && coupling && dcoupling && B >= 0 && W >= 2, DDRL_E_BADARG,
+                 "leg_coupling_backward: null pointer or bad shape");
+    leg_coupling_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dout, logits_pre, node_id, coupling, B, W, dcoupling);
+    DDRL_CHECK_LAUNCH("leg_coupling_backward");
+    return DDRL_OK;
+}
+
 extern "C" int64_t ddrl_sgd_exchange_words(int NP, int ctas_per_policy) {
     if (NP < 1 || ctas_per_policy < 1) return DDRL_E_BADARG;
     return (int64_t)ctas_per_policy * sgd_slice_len(NP, ctas_per_policy);
+}
+
+extern "C" int64_t ddrl_sgd_ll_words(int P, int ctas_per_policy, int D, int A) {
+    if (P < 1 || ctas_per_policy < 1 || D < 1 || A < 1) return DDRL_E_BADARG;
+    return ll_total_words(P, ctas_per_policy, fc_offsets(D, A).NP, D, A);
 }
 
 // ---- peer-mapped memory (CUDA IPC) for the in-kernel gradient all-reduce ------------------------------------------------

@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     float* stg = reinterpret_cast<float*>(sm + S.H1[0][0]);   // [NPs] staging of the partial (H1 is free after the main loop)
     float* gp = cs > 1 ? stg : a.grad_part + ((int64_t)p * G + bx) * NPs;
     const bool has_tail = a.tail.theta != nullptr;
+    // LL tail (sgd_tail.cuh): partial gradients and updated weights travel between CTAs as self-validating words
+    const bool ll = !FWD && has_tail && a.tail.ll_ws != nullptr && cs == 1 && sgd_slice_len(o.NP, G) <= T2_NT;
+    const int LLW = ll_part_words(o.NP);
+    unsigned long long* llp = ll ? a.tail.ll_ws + ((int64_t)p * G + bx) * LLW : nullptr;
     const int nsteps = (has_tail && a.tail.nsteps > 1) ? a.tail.nsteps : 1;   // consecutive SGD steps of this launch
     const int step0 = a.step_ctr ? *a.step_ctr : 0;
     TailStep ts;
@@ -221,11 +225,18 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
-    if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
+    const unsigned int tag = ts.epoch + (unsigned int)s + 1u;      // LL tag of THIS step's partials / weights
+    if (s > 0 && ll) {   // rebuild the weight image from the LL words the slice owners published in the previous step's tail
+        if (!ll_load_image(a.tail, p, gridDim.y, G, o.NP, D, A, sm, tag - 1u, tid, T2_NT, false)) {
+            ok = false;
+            if (a.status) atomicOr(a.status, 64);
+        }
+        if (warp >= T2_MMA_WARP) umma::fence_async_smem();   // the epilogue warps fence in publish() before F1
+    } else if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
         if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
         __syncthreads();
     }
-    if (warp < T2_MMA_WARP) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
+    if (warp < T2_MMA_WARP && !(s > 0 && ll)) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
         const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
 #pragma unroll 2
         for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
@@ -251,8 +262,12 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     do {   // single exit towards the fused tail (one inlined copy of it)
     if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        for (int i = tid; i < NPs; i += T2_NT) gp[i] = 0.f;
-        if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
+        if (ll) {
+            for (int i = tid; i < (LLW >> 1); i += T2_NT) ll_st2(llp + 2 * i, 0u, 0u, tag);
+        } else {
+            for (int i = tid; i < NPs; i += T2_NT) gp[i] = 0.f;
+            if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
+        }
         break;
     }
 
@@ -283,7 +298,6 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         umma::fence_after_sync();
     };
     auto epi_sync = [&]() { asm volatile("bar.sync 4, %0;" ::"n"(TC_NT) : "memory"); };   // the 16 epilogue warps only
-    const uint32_t Xh = sbase + S.X[0], Xl = sbase + S.X[1];
 
     // ---- write-out pieces: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
     const float inv = a.hp.inv_global_mb;
@@ -292,6 +306,18 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     // gW2_b, gb2_b, gWh_b are final once B3(b) / B1 have completed, i.e. BEFORE the last B5: they are written while B5 runs.
     // (Not with clusters: the staging buffer of the partial lives in H1, which B5 still reads.)
     const bool early_out = cs == 1;
+    auto put1 = [&](int idx, float v) {
+        if (ll) ll_st1(llp + idx, __float_as_uint(v), tag);
+        else gp[idx] = v;
+    };
+    auto put4 = [&](int idx, float x0, float x1, float x2, float x3) {      // idx % 4 == 0
+        if (ll) {
+            ll_st2(llp + idx, __float_as_uint(x0), __float_as_uint(x1), tag);
+            ll_st2(llp + idx + 2, __float_as_uint(x2), __float_as_uint(x3), tag);
+        } else {
+            *reinterpret_cast<float4*>(gp + idx) = make_float4(x0, x1, x2, x3);
+        }
+    };
     auto write_w2_heads = [&](int b) {
         const float sgb = sgs[b];
         const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX), inv_gwh = inv_gw2;
@@ -301,15 +327,15 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8, r1);
             umma::tmem_ld_wait();
             if (mine) {
-                float4* dst = reinterpret_cast<float4*>(gp + (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq);
-                dst[0] = make_float4(__uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
-                                     __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
-                dst[1] = make_float4(__uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
-                                     __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
-                dst[2] = make_float4(__uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
-                                     __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
-                dst[3] = make_float4(__uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
-                                     __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
+                const int dst = (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq;      // W2 / Wv2 offsets are multiples of 4
+                put4(dst, __uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
+                     __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
+                put4(dst + 4, __uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
+                     __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
+                put4(dst + 8, __uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
+                     __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
+                put4(dst + 12, __uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
+                     __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
             }
         }
         if (cq == 2) {                                   // gb2_b: column of the constant-1 pad inside its 16-wide window
@@ -318,7 +344,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             const int jsel = (D - 8 * ch0) & 7;
             const float g = jsel == 0 ? v[0] : jsel == 1 ? v[1] : jsel == 2 ? v[2] : jsel == 3 ? v[3] : jsel == 4 ? v[4]
                           : jsel == 5 ? v[5] : jsel == 6 ? v[6] : v[7];
-            if (mine) gp[(b ? o.bv2 : o.b2) + m] = g * inv_gw1;
+            if (mine) put1((b ? o.bv2 : o.b2) + m, g * inv_gw1);
         }
         if (cq == 3) {                                   // gWh_b[k = m][o]
             float w[16], w2[16];
@@ -329,9 +355,9 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             if (mine) {
                 if (b == 0) {
 #pragma unroll
-                    for (int oo = 0; oo < A2; ++oo) gp[o.Wo + m * A2 + oo] = w[oo] * inv_gwh;
+                    for (int oo = 0; oo < A2; ++oo) put1(o.Wo + m * A2 + oo, w[oo] * inv_gwh);
                 } else {
-                    gp[o.Wvo + m] = w[0] * inv_gwh;
+                    put1(o.Wvo + m, w[0] * inv_gwh);
                 }
             }
         }
@@ -350,8 +376,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
                 for (int j = 0; j < 8; ++j) {
                     const int d = 8 * c8 + j;
                     const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
-                    if (d < D) gp[(b ? o.Wv1 : o.W1) + d * 64 + m] = g;
-                    else if (d == D) gp[(b ? o.bv1 : o.b1) + m] = g;
+                    if (d < D) put1((b ? o.Wv1 : o.W1) + d * 64 + m, g);
+                    else if (d == D) put1((b ? o.bv1 : o.b1) + m, g);
                 }
             }
         }
@@ -360,92 +386,96 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     if (warp >= T2_MMA_WARP) {
         // ================= MMA-issue warps: one hand-off barrier per batch; lane 0 of each warp issues ITS share of the batch
         // (shares never split an accumulator) and commits to the branch's mbarrier (expected arrivals = T2_NMMA) ==========
-        const int mw = warp - T2_MMA_WARP;
-        const uint32_t H1h[2] = {sbase + S.H1[0][0], sbase + S.H1[1][0]}, H1l[2] = {sbase + S.H1[0][1], sbase + S.H1[1][1]};
-        const uint32_t H2h[2] = {sbase + S.H2[0][0], sbase + S.H2[1][0]}, H2l[2] = {sbase + S.H2[0][1], sbase + S.H2[1][1]};
-        const uint32_t DLh[2] = {sbase + S.DL[0][0], sbase + S.DL[1][0]}, DLl[2] = {sbase + S.DL[0][1], sbase + S.DL[1][1]};
+        // warp-uniform issue (tc_gemm_u): every lane runs the same code on provably uniform values, an elected lane issues
+        const int mw = __shfl_sync(0xffffffffu, warp, 0) - T2_MMA_WARP;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t sbu = __shfl_sync(0xffffffffu, sbase, 0);
+        const uint32_t Xhu = sbu + S.X[0], Xlu = sbu + S.X[1];
+        const uint32_t H1h[2] = {sbu + S.H1[0][0], sbu + S.H1[1][0]}, H1l[2] = {sbu + S.H1[0][1], sbu + S.H1[1][1]};
+        const uint32_t H2h[2] = {sbu + S.H2[0][0], sbu + S.H2[1][0]}, H2l[2] = {sbu + S.H2[0][1], sbu + S.H2[1][1]};
+        const uint32_t DLh[2] = {sbu + S.DL[0][0], sbu + S.DL[1][0]}, DLl[2] = {sbu + S.DL[0][1], sbu + S.DL[1][1]};
 #pragma unroll 1
         for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
             const bool acc = !first;
             mma_turn();      // X split done.  F1: Dacc_b = X * W1b^T   (warp b)
-            if (lane == 0) {
+            {
                 if (mw < 2)
-                    tc_gemm(tmem + T2_DACC + 64 * mw, Xh, Xl, TC_ROWS, false, sbase + I.W1[mw][0], sbase + I.W1[mw][1], 64, false,
+                    tc_gemm_u(tm + T2_DACC + 64 * mw, Xhu, Xlu, TC_ROWS, false, sbu + I.W1[mw][0], sbu + I.W1[mw][1], 64, false,
                             128, 64, KX >> 4, false, 3);
-                umma::mma_commit(mbar);
-                umma::mma_commit(mbar + 1);
+                umma::mma_commit_elect(mbar);
+                umma::mma_commit_elect(mbar + 1);
             }
             __syncwarp();
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {   // F2: Dacc_b = H1_b * W2b   (warp b)
                 mma_turn();
-                if (lane == 0) {
+                {
                     if (mw == b)
-                        tc_gemm(tmem + T2_DACC + 64 * b, H1h[b], H1l[b], TC_ROWS, false, sbase + I.W2[b][0], sbase + I.W2[b][1], 64,
+                        tc_gemm_u(tm + T2_DACC + 64 * b, H1h[b], H1l[b], TC_ROWS, false, sbu + I.W2[b][0], sbu + I.W2[b][1], 64,
                                 true, 128, 64, 4, false, 3);
-                    umma::mma_commit(mbar + b);
+                    umma::mma_commit_elect(mbar + b);
                 }
                 __syncwarp();
             }
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {   // heads: Hout_b[128][16] = H2_b * WoT_b^T   (warp b)
                 mma_turn();
-                if (lane == 0) {
+                {
                     if (mw == b)
-                        tc_gemm(tmem + T2_HOUT + 16 * b, H2h[b], H2l[b], TC_ROWS, false, sbase + I.WoT[b][0], sbase + I.WoT[b][1],
+                        tc_gemm_u(tm + T2_HOUT + 16 * b, H2h[b], H2l[b], TC_ROWS, false, sbu + I.WoT[b][0], sbu + I.WoT[b][1],
                                 TC_NO, false, 128, TC_NO, 4, false, 3);
-                    umma::mma_commit(mbar + b);
+                    umma::mma_commit_elect(mbar + b);
                 }
                 __syncwarp();
             }
             if (FWD) continue;      // inference: nothing after the heads
             mma_turn();      // loss done.  dz2-pre: Dacc_b = DL_b * WoT_b (warp b, first);  gWh_b (+)= H2_b^T DL_b by product
-            if (lane == 0) {
+            {
                 const int b = mw & 1;
                 if (mw < 2) {
-                    tc_gemm(tmem + T2_DACC + 64 * b, DLh[b], DLl[b], TC_ROWS, false, sbase + I.WoT[b][0], sbase + I.WoT[b][1], TC_NO,
+                    tc_gemm_u(tm + T2_DACC + 64 * b, DLh[b], DLl[b], TC_ROWS, false, sbu + I.WoT[b][0], sbu + I.WoT[b][1], TC_NO,
                             true, 128, 64, 1, false, 3);
-                    tc_gemm_mask(tmem + T2_GWH + 16 * (2 * b), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64, 16, 8,
+                    tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64, 16, 8,
                                  acc, 1);
                 } else {
-                    tc_gemm_mask(tmem + T2_GWH + 16 * (2 * b + 1), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64,
+                    tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b + 1), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64,
                                  16, 8, acc, 6);
                 }
-                umma::mma_commit(mbar);
-                umma::mma_commit(mbar + 1);
+                umma::mma_commit_elect(mbar);
+                umma::mma_commit_elect(mbar + 1);
             }
             __syncwarp();
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {   // B4: Dacc_b = dZ2_b * W2b^T (warp 0);  gW2_b (+)= H1_b^T dZ2_b (warp 1 / 3);  gb2_b (warp 2)
                 mma_turn();
-                if (lane == 0) {
+                {
                     if (mw == 0)
-                        tc_gemm(tmem + T2_DACC + 64 * b, H2h[b], H2l[b], TC_ROWS, false, sbase + I.W2[b][0], sbase + I.W2[b][1], 64,
+                        tc_gemm_u(tm + T2_DACC + 64 * b, H2h[b], H2l[b], TC_ROWS, false, sbu + I.W2[b][0], sbu + I.W2[b][1], 64,
                                 false, 128, 64, 4, false, 3);
                     else if (mw == (b ? 3 : 1))
-                        tc_gemm(tmem + T2_GW2 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, H2h[b], H2l[b], TC_ROWS, true, 64, 64, 8, acc, 3);
+                        tc_gemm_u(tm + T2_GW2 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, H2h[b], H2l[b], TC_ROWS, true, 64, 64, 8, acc, 3);
                     else if (mw == 2)
-                        tc_gemm(tmem + T2_GB2 + 16 * b, H2h[b], H2l[b], TC_ROWS, true, Xh + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
+                        tc_gemm_u(tm + T2_GB2 + 16 * b, H2h[b], H2l[b], TC_ROWS, true, Xhu + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
                                 16, 8, acc, 2);
-                    umma::mma_commit(mbar + b);
+                    umma::mma_commit_elect(mbar + b);
                 }
                 __syncwarp();
             }
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {   // B5: gW1_b[c][d] (+)= dZ1_b^T X by product (column D of X = constant 1 -> bias gradient)
                 mma_turn();
-                if (lane == 0) {
+                {
                     if (gw1_split) {
                         if (mw == 0)
-                            tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8,
+                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b), H1h[b], H1l[b], TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8,
                                          acc, 1);
                         if (mw == 1)
-                            tc_gemm_mask(tmem + T2_GW1 + 32 * (2 * b + 1), H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX,
+                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b + 1), H1h[b], H1l[b], TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX,
                                          8, acc, 6);
                     } else if (mw == b) {
-                        tc_gemm(tmem + T2_GW1 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, Xh, Xl, TC_ROWS, true, 64, KX, 8, acc, 3);
+                        tc_gemm_u(tm + T2_GW1 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8, acc, 3);
                     }
-                    umma::mma_commit(mbar + b);
+                    umma::mma_commit_elect(mbar + b);
                 }
                 __syncwarp();
             }
@@ -637,9 +667,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             T2_STAMP(21 + 3 * b);
         }
         if (S.dl_in_w1 && row0 + TC_ROWS < cr1) {   // both B1 are complete (DL dead) and another tile follows: restore W1
-            const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+            if (ll && s > 0) {      // this step's weights exist as LL words only (the global image is not fenced between steps)
+                ok = ll_load_image(a.tail, p, gridDim.y, G, o.NP, D, A, sm, tag - 1u, tid, TC_NT, true) && ok;
+            } else {
+                const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
 #pragma unroll 1
-            for (int i = I.W1[0][0] / 16 + tid; i < I.W2[0][0] / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+                for (int i = I.W1[0][0] / 16 + tid; i < I.W2[0][0] / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+            }
         }
         // ---- dz1 epilogue -> B5: gW1_b[c][d] (+)= dZ1_b^T X   (column D of X is the constant 1 -> bias gradient) --------
 #pragma unroll 1
@@ -700,14 +734,20 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     T2_STAMP(32);
     const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][24]
     auto sum4 = [&](int w0, int i) { return (redd[w0 * 24 + i] + redd[(w0 + 1) * 24 + i]) + (redd[(w0 + 2) * 24 + i] + redd[(w0 + 3) * 24 + i]); };
-    if (tid < A2) gp[o.bo + tid] = (float)sum4(0, 8 + tid) * inv;
-    if (tid == A2) gp[o.bvo] = (float)sum4(4, 8) * inv;
-    if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) gp[o.NP + (tid - A2 - 1)] = 0.f;   // padding floats of the partial
-    if (tid < DDRL_NSTAT && a.stat_part) {
+    if (tid < A2) put1(o.bo + tid, (float)sum4(0, 8 + tid) * inv);
+    if (tid == A2) put1(o.bvo, (float)sum4(4, 8) * inv);
+    if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) put1(o.NP + (tid - A2 - 1), 0.f);   // padding floats of the partial
+    if (tid < DDRL_NSTAT && (ll || a.stat_part)) {
         // stat slots (ddrl_b200.h): 0 -surr, 1 KL, 2 vf, 3 entropy, 4 R, 5 R^2, 6 R-v, 7 (R-v)^2
         const int w0 = (tid == 0 || tid == 1 || tid == 3) ? 0 : 4;
         const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
-        a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sum4(w0, idx);
+        const double sv = sum4(w0, idx);
+        if (ll) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(sv);
+            ll_st2(llp + NPs + 2 * tid, (unsigned int)bits, (unsigned int)(bits >> 32), tag);
+        } else {
+            a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sv;
+        }
     }
     } while (0);
     if (cs > 1) {   // in-cluster reduction over distributed shared memory: CTA `crank` adds part `crank` of the cs staged partials
@@ -750,8 +790,15 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     if (has_tail) {   // fused grad-reduce + [peer all-reduce] + clip + Adam
         ts.round = s + 1;
         ts.last = s == nsteps - 1;
-        const bool tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                       reinterpret_cast<float*>(sm + S.H2[0][0]), a.dbg_clock, ncl);
+        bool tok;
+        if (ll) {
+            __syncthreads();      // every thread is past its last use of the shared memory the tail scratches
+            tok = sgd_step_tail_ll(a.tail, ts, p, gridDim.y, bx, G, o.NP, step, D, A, reinterpret_cast<float*>(sm + S.H2[0][0]),
+                                   a.dbg_clock);
+        } else {
+            tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
+                                reinterpret_cast<float*>(sm + S.H2[0][0]), a.dbg_clock, ncl);
+        }
         ok = ok && tok;
         ts.b1p *= a.tail.beta1;
         ts.b2p *= a.tail.beta2;

@@ -108,6 +108,41 @@ __device__ __forceinline__ void tc_gemm_mask(uint32_t d_tmem, uint32_t a_hi, uin
     }
 }
 
+// Warp-uniform variants: the WHOLE warp calls these with warp-uniform arguments (kernel parameters, constants,
+// __shfl_sync(.., 0) results); one elected lane issues each instruction.  ptxas then keeps descriptors and TMEM addresses in
+// uniform registers and emits bare UTCHMMA instructions instead of a per-instruction R2UR waterfall loop
+// (profiles/r02_umma_issue_bench.txt: 148 -> 100 cycles per dependent MMA, 39-50 with independent accumulators interleaved).
+__device__ __forceinline__ void tc_gemm_mask_u(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
+                                               uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate,
+                                               int pmask) {
+    const uint32_t idesc = umma::idesc_f16(M, N, a_mn, b_mn);
+    const uint64_t astep = a_mn ? 16u : (uint64_t)(2 * a_rows);
+    const uint64_t bstep = b_mn ? 16u : (uint64_t)(2 * b_rows);
+    const uint64_t ah = a_mn ? umma::desc_mnmajor(a_hi, a_rows) : umma::desc_kmajor(a_hi, a_rows);
+    const uint64_t al = a_mn ? umma::desc_mnmajor(a_lo, a_rows) : umma::desc_kmajor(a_lo, a_rows);
+    const uint64_t bh = b_mn ? umma::desc_mnmajor(b_hi, b_rows) : umma::desc_kmajor(b_hi, b_rows);
+    const uint64_t bl = b_mn ? umma::desc_mnmajor(b_lo, b_rows) : umma::desc_kmajor(b_lo, b_rows);
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) {
+        if (!((pmask >> pr) & 1)) continue;
+        uint64_t ad = pr == 2 ? al : ah;
+        uint64_t bd = pr == 1 ? bl : bh;
+#pragma unroll 4
+        for (int ks = 0; ks < nk; ++ks) {
+            umma::mma_f16_elect(d_tmem, ad, bd, idesc, acc);
+            acc = 1u;
+            ad += astep;
+            bd += bstep;
+        }
+    }
+}
+// nprod == 3: (hi,hi) (hi,lo) (lo,hi); nprod == 2: (hi,hi) (lo,hi)
+__device__ __forceinline__ void tc_gemm_u(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
+                                          uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate, int nprod) {
+    tc_gemm_mask_u(d_tmem, a_hi, a_lo, a_rows, a_mn, b_hi, b_lo, b_rows, b_mn, M, N, nk, accumulate, nprod == 3 ? 7 : 5);
+}
+
 // split 8 floats (times a power-of-two scale) into fp16 hi / lo 16-byte chunks; returns true on fp16 overflow
 __device__ __forceinline__ bool tc_split8(const float* v, float scale, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];

@@ -331,6 +331,18 @@ def leg_coupling_(logits, node_id, coupling):
     return logits
 
 
+def leg_coupling_backward_(dout, logits_pre, node_id, coupling):
+    """In place: dout [B,W] becomes the gradient w.r.t. the pre-coupling logits; returns dcoupling [4,2] (see
+    ddrl_leg_coupling_backward)."""
+    B, W = dout.shape
+    f32 = torch.float32
+    dc = torch.empty(4, 2, dtype=f32, device=dout.device)
+    _lib.check(_lib.load().ddrl_leg_coupling_backward(_p(dout, f32, "dout"), _p(logits_pre, f32, "logits_pre"),
+                                                      _p(node_id, torch.int32, "node_id"), _p(coupling, f32, "coupling"), B, W,
+                                                      _p(dc, f32, "dcoupling"), _stream()), "leg_coupling_backward")
+    return dc
+
+
 def filter_partial(x: torch.Tensor, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-rank half of the filter update: x [P,R,D] -> partials [P, nparts, D, 3] f64 {count, mean, M2}."""
     lib = _lib.load()
@@ -533,8 +545,16 @@ def graph_obs_build(obs_full: torch.Tensor, table: torch.Tensor, leg_zw: torch.T
     return (state, node_idx) if replicate else state
 
 
+def sgd_ll_words(P: int, ctas_per_policy: int, D: int, A: int) -> int:
+    """64-bit words of the LL workspace (``ddrl_sgd_tail.ll_ws``) of the ping-pong tcgen05 step."""
+    n = int(_lib.load().ddrl_sgd_ll_words(P, ctas_per_policy, D, A))
+    if n <= 0:
+        raise DDRLError("ddrl_sgd_ll_words failed")
+    return n
+
+
 def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, beta2, eps, grad_clip, gnorm_out=None, img=None,
-                  tc_img=None, step_stats=None, step_ctr=None, status=None) -> SgdTail:
+                  tc_img=None, step_stats=None, step_ctr=None, status=None, ll_ws=None) -> SgdTail:
     """Fused grad-reduce + [peer all-reduce] + clip + Adam tail of the SGD step (see ddrl_sgd_tail in ddrl_b200.h).
     The caller keeps the tensors alive; barrier_ws must be zero-initialised int32 [4*P + 4].  For world > 1 let
     ``peer.PeerExchange.fill`` add the rank / peer-buffer fields."""
@@ -548,6 +568,7 @@ def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, bet
     t.lr, t.beta1, t.beta2, t.eps, t.grad_clip = float(lr), float(beta1), float(beta2), float(eps), float(grad_clip)
     t.status = _p(status, torch.int32, "status")
     t.world, t.rank, t.nsteps = 1, 0, 1
+    t.ll_ws = _p(ll_ws, torch.int64, "ll_ws")
     return t
 
 

@@ -109,7 +109,7 @@ class FCNetLearner(_LearnerBase):
 
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
                  use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True,
-                 persistent: bool = True, tc_forward: bool = True):
+                 persistent: bool = True, tc_forward: bool = True, ll_tail: bool = True):
         """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
                  "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes."""
         super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
@@ -119,6 +119,9 @@ class FCNetLearner(_LearnerBase):
         self.fuse_tail = fuse_tail
         self.persistent = persistent      # one persistent launch per epoch where the kernel supports it
         self.tc_forward = tc_forward and mode == "tc"   # inference forward on the tensor cores as well
+        # ping-pong tcgen05 step: CTAs exchange partial gradients / updated weights as self-validating {payload, tag} words
+        # (one barrier-free tail per step, csrc/sgd_tail.cuh); False keeps the three-barrier tail for A/B runs
+        self.ll_tail = ll_tail and mode == "tc"
         self.D, self.A = D, A
         dev = self.device
         self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -202,7 +205,8 @@ class FCNetLearner(_LearnerBase):
             tail = K.make_sgd_tail(self.theta, self.m, self.v, self.beta_pow, self.grad, b["tail_bar"], b["tail_sq"], c.lr,
                                    c.beta1, c.beta2, c.adam_eps, c.grad_clip, self.gnorm,
                                    img=self.img if self.mode == "fp32" else None, tc_img=self.tc_img,
-                                   step_stats=b["step_stats"], step_ctr=self.step_ctr, status=self.tc_status)
+                                   step_stats=b["step_stats"], step_ctr=self.step_ctr, status=self.tc_status,
+                                   ll_ws=b.get("tail_ll"))
             tail.nsteps = nsteps
             if self.world > 1:
                 self._peer_exchange(G).fill(tail)
@@ -337,6 +341,9 @@ class FCNetLearner(_LearnerBase):
             b["step_stats"] = torch.zeros(steps, P, K.NSTAT, dtype=torch.float64, device=self.device)
             b["tail_bar"] = torch.zeros(4 * P + 4, dtype=torch.int32, device=self.device)
             b["tail_sq"] = torch.zeros(P, G, 32, dtype=torch.float32, device=self.device)   # one 128-byte line per {sum, tag} word
+            # LL workspace: same lifetime as tail_bar (its tags are the step count kept there)
+            b["tail_ll"] = (torch.zeros(K.sgd_ll_words(P, G, self.D, self.A), dtype=torch.int64, device=self.device)
+                            if self.ll_tail and K.tc_pingpong_eligible(self.D, self.A) else None)
             self._graph = None
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()

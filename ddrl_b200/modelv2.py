@@ -324,18 +324,41 @@ class FullyConnectedNetwork_GNN_GlorotUniformInitializer(_DDRLModel):
         return action, state
 
 
+class _LegCouplingFn(torch.autograd.Function):
+    """logits_pre [B,2A], node_idx [B], coupling [4,2] -> logits_pre * pad(coupling, ones)[node_idx]; backward returns the
+    gradient w.r.t. the pre-coupling logits AND the trainable table (ddrl_leg_coupling / ddrl_leg_coupling_backward)."""
+
+    @staticmethod
+    def forward(ctx, logits_pre, node_idx, coupling):
+        ctx.save_for_backward(logits_pre, node_idx, coupling)
+        return K.leg_coupling_(logits_pre.detach().clone().contiguous(), node_idx, coupling.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, dout):
+        logits_pre, node_idx, coupling = ctx.saved_tensors
+        d = dout.contiguous().float().clone()
+        dc = K.leg_coupling_backward_(d, logits_pre.detach().contiguous(), node_idx, coupling.detach().contiguous())
+        return d, None, dc
+
+
 class LegCoupling:
-    """logits * pad(coupling[4,2], ones)[node_id]  (models/coupling_net_glorot_uniform_init.py:11-30)."""
+    """logits * pad(coupling[4,2], ones)[node_id]  (models/coupling_net_glorot_uniform_init.py:11-30).  `coupling` is a
+    trainable variable like the reference's `tf.Variable(..., name='leg_coupling')` (:20-21)."""
     INIT = ((1.0, 1.0), (-1.0, -1.0), (-1.0, -1.0), (1.0, 1.0))
 
     def __init__(self, device):
-        self.coupling = torch.tensor(self.INIT, dtype=torch.float32, device=device)
+        c = torch.tensor(self.INIT, dtype=torch.float32, device=device)
+        self.coupling = torch.nn.Parameter(c) if _HAVE_RAY else c.requires_grad_(True)
+
+    def __call__(self, logits_pre, node_idx):
+        return _LegCouplingFn.apply(logits_pre, node_idx, self.coupling)
 
 
 class FullyConnectedNetwork_Coupling_GlorotUniformInitializer(FullyConnectedNetwork_GlorotUniformInitializer):
     """FCNet over Tuple(node_idx[1], obs[D]) with the LegCoupling multiply on the logits
-    (models/coupling_net_glorot_uniform_init.py:32-170).  The coupling table is applied by the
-    ``ddrl_leg_coupling`` kernel; it is kept at its initial value (its gradient path is a 'next' item)."""
+    (models/coupling_net_glorot_uniform_init.py:32-170).  The coupling table is applied by the ``ddrl_leg_coupling`` kernel
+    and TRAINED like the reference's registered `leg_coupling` variable (:20-21,160-161): ``ddrl_leg_coupling_backward``
+    returns its gradient (segment sum of dlogits * logits_pre by node id) next to the gradient of the MLP output."""
 
     def __init__(self, obs_space, action_space, num_outputs, model_config, name):
         orig = getattr(obs_space, "original_space", obs_space)
@@ -354,11 +377,9 @@ class FullyConnectedNetwork_Coupling_GlorotUniformInitializer(FullyConnectedNetw
         obs = torch.as_tensor(obs, dtype=torch.float32, device=dev).contiguous()
         node_idx = torch.as_tensor(node_idx, device=dev).reshape(-1).to(torch.int32).contiguous()
         logits, self._value_out = _FCNetFn.apply(self.kernel_parameters(), obs, self.A)
-        if logits.requires_grad:
-            # keep autograd intact: the multiply by a per-row constant is expressed on the graph
-            coeff = torch.cat([self.leg_coupling.coupling, torch.ones(4, self.A, device=dev)], dim=1)[node_idx.long()]
-            return logits * coeff, state
-        return K.leg_coupling_(logits.contiguous(), node_idx, self.leg_coupling.coupling), state
+        if torch.is_grad_enabled() and (logits.requires_grad or self.leg_coupling.coupling.requires_grad):
+            return self.leg_coupling(logits, node_idx), state
+        return K.leg_coupling_(logits.detach().contiguous(), node_idx, self.leg_coupling.coupling.detach()), state
 
 
 def register_all():

@@ -214,7 +214,14 @@ typedef struct {
     uint32_t* seq;
     unsigned long long* peer_x[DDRL_MAX_RANKS];
     int32_t nsteps;           /* consecutive SGD steps per launch (0 or 1 = one); > 1 only ddrl_ppo_train_step_tc (ping-pong) */
+    unsigned long long* ll_ws; /* NULL, or ddrl_sgd_ll_words(...) zero-initialised 64-bit words: the ping-pong kernel then hands partial
+                                * gradients and updated weights between CTAs as self-validating {payload, step tag} words instead of
+                                * barrier-protected arrays (one barrier-free tail per step; csrc/sgd_tail.cuh).  Must share the lifetime
+                                * of barrier_ws (the tags are the step count kept there). */
 } ddrl_sgd_tail;
+
+/* 64-bit words of ddrl_sgd_tail.ll_ws for P policies of an FCNet (D, A) stepped by ctas_per_policy CTAs each. */
+int64_t ddrl_sgd_ll_words(int P, int ctas_per_policy, int D, int A);
 
 /* 64-bit words per (rank, policy) in the exchange buffer: ctas_per_policy slices of ((NP + G - 1) / G rounded up to 4) */
 int64_t ddrl_sgd_exchange_words(int NP, int ctas_per_policy);
@@ -343,6 +350,13 @@ int ddrl_dg_sample(const float* logits, const float* eps, int64_t R, int A, floa
  *   logits[b][j] *= (j < 2 ? coupling[node_id[b]][j] : 1)      in place; coupling [4][2]. */
 int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupling, int64_t B,
                       int W, void* stream);
+/* Backward of the layer (the table is a TRAINABLE tf.Variable registered with the model,
+ * models/coupling_net_glorot_uniform_init.py:20-21,160-161):
+ *   dcoupling[n][j] = sum_{b: node_id[b] == n} dout[b][j] * logits_pre[b][j]   (j < 2; [4][2], overwritten)
+ *   dout[b][j]     *= coupling[node_id[b]][j]                                   (in place -> gradient w.r.t. logits_pre)
+ * Fixed-order reduction (one block, float64 partial sums): bit-reproducible. */
+int ddrl_leg_coupling_backward(float* dout, const float* logits_pre, const int32_t* node_id,
+                               const float* coupling, int64_t B, int W, float* dcoupling, void* stream);
 
 /* Tensor-core variant of ddrl_ppo_train_step (PPO path only): every GEMM of the fused forward + loss + backward
  * runs on tcgen05 (kind::f16, FP32 accumulation in TMEM) with FP32 operands split into fp16 (hi, lo) pairs and

@@ -282,14 +282,18 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile", "tc-classic", "tc-llmt"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
 def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
     """filter -> forward/sample -> GAE -> standardise -> 2 epochs x 4 minibatches of clip+Adam -> KL update.
     "-3k" = the three-kernel SGD step (train, grad_reduce, clip_adam) instead of the fused tail; "-1step" = one launch
-    per optimizer step instead of one persistent launch per epoch."""
+    per optimizer step instead of one persistent launch per epoch.  "tc" (32 CTAs per policy) runs the barrier-free LL tail
+    (csrc/sgd_tail.cuh); "-classic" = the same with the three-barrier tail; "-llmt" = LL tail with two 128-row tiles per CTA
+    (24 CTAs per policy x 136 rows: the W1 part of the image is restored from the LL words between the tiles)."""
     fuse = not mode.endswith("-3k")
+    classic = mode.endswith("-classic")
+    llmt = mode.endswith("-llmt")
     persistent = not mode.endswith("-1step")      # "tc": one persistent launch per epoch where the kernel allows it
     cluster = mode.endswith("-cluster")           # thread-block clusters pre-reduce the partial gradients over DSMEM
     multitile = mode.endswith("-multitile")       # 2 CTAs per policy x 256 rows: two 128-row tiles per CTA, persistent launch
@@ -297,9 +301,9 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
     O = _oracle()
-    T, C = (16, 128) if multitile else (16, 32)
+    T, C = (16, 128) if multitile else (16, 408) if llmt else (16, 32)
     R = T * C
-    MBS = 512 if multitile else 128
+    MBS = 512 if multitile else 3264 if llmt else 128
     cfgd = dict(num_sgd_iter=2, sgd_minibatch_size=MBS)
     cfg_o = O.PPOConfig(**cfgd)
     cfg = PPOConfig(**cfgd)
@@ -317,7 +321,8 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     shuffle = np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32) if use_shuffle else None
 
     L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse,
-                     persistent=persistent, ctas_per_policy=8 if cluster else 2 if multitile else None)
+                     persistent=persistent, ctas_per_policy=8 if cluster else 2 if multitile else 24 if llmt else None,
+                     ll_tail=not classic)
     if cluster:
         from ddrl_b200 import kernels as K
         K.tc_set_cluster(-1)

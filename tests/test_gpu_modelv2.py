@@ -107,6 +107,46 @@ def test_coupling_modelv2():
     assert torch.allclose(out2.detach(), out, rtol=0, atol=1e-7)
 
 
+def test_coupling_table_is_trainable():
+    """The reference registers `leg_coupling` as a trainable tf.Variable (models/coupling_net_glorot_uniform_init.py:20-21,
+    160-161): gradients w.r.t. the table (non-initial values) and w.r.t. the MLP weights against the oracle's autograd."""
+    from ddrl_b200 import spaces
+    from ddrl_b200.catalog import ModelCatalog
+    import ddrl_b200.modelv2  # noqa: F401
+    O = _O()
+    obs_space = spaces.Tuple([spaces.MultiDiscrete([4]), spaces.Box(-np.inf, np.inf, (19,), np.float64)])
+    model = ModelCatalog.get_model_v2(obs_space, spaces.Box(-1.0, 1.0, (2,)), 4, dict(MODEL_CONFIG, custom_model="cup"),
+                                      name="policy_legs")
+    g = torch.Generator().manual_seed(3)
+    table = torch.tensor([[0.7, -1.3], [-0.4, 0.9], [1.6, -0.2], [-1.1, 0.5]])
+    with torch.no_grad():
+        model.leg_coupling.coupling.copy_(table.cuda())
+    assert model.leg_coupling.coupling.requires_grad
+    assert any(v is model.leg_coupling.coupling for v in model.trainable_variables())
+    B = 777                                     # ragged against the 1024-thread reduction
+    idx = torch.randint(0, 4, (B, 1), generator=g)
+    x = torch.randn(B, 19, generator=g)
+    w_out = torch.randn(B, 4, generator=g)
+    w_val = torch.randn(B, generator=g)
+    out, _ = model({"obs": (idx.cuda(), x.cuda())}, [], None)
+    loss = (out * w_out.cuda()).sum() + (model.value_function() * w_val.cuda()).sum()
+    model.theta.grad = None
+    model.leg_coupling.coupling.grad = None
+    loss.backward()
+    th = model.theta.detach().cpu().double().requires_grad_(True)
+    tb = table.double().requires_grad_(True)
+    lg, vr = O.fcnet_forward(th, x.double(), 4)
+    ref = O.leg_coupling(lg, idx, tb)
+    ((ref * w_out.double()).sum() + (vr * w_val.double()).sum()).backward()
+    assert scaled_err(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    assert scaled_err(model.leg_coupling.coupling.grad.cpu().numpy(), tb.grad.numpy()) < TOL
+    assert scaled_err(model.theta.grad.cpu().numpy(), th.grad.numpy()) < 2e-5
+    # one plain SGD step moves the table (it was frozen at its initial value before round 2)
+    with torch.no_grad():
+        model.leg_coupling.coupling -= 1e-3 * model.leg_coupling.coupling.grad
+    assert not torch.equal(model.leg_coupling.coupling.detach().cpu(), table)
+
+
 def test_unsupported_model_configs_fail_loudly():
     from ddrl_b200 import spaces
     from ddrl_b200._lib import DDRLError
