@@ -353,28 +353,27 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
 }
 
 // =====================================================================================================================
-// "LL" tail (ping-pong tcgen05 kernel, ddrl_sgd_tail.ll_ws != NULL): the same arithmetic as sgd_step_tail, but every
-// cross-CTA hand-off inside a step travels as self-validating 64-bit words {payload, step tag} (NCCL-"LL" style) instead
-// of plain data behind a release / acquire barrier:
+// "LL" tail (ping-pong tcgen05 kernel, ddrl_sgd_tail.ll_ws != NULL): the same arithmetic as sgd_step_tail, but the partial
+// gradients reach the slice owners as self-validating 64-bit words {fp32 payload, step tag} (NCCL-"LL" style) instead of
+// plain data behind a release / acquire barrier:
 //
-//   write-out   each CTA stores its partial gradient (and its 8 float64 loss statistics as 16 half words) as LL words
-//   reduce      the owner of slice bx reads the G partial slices — polling only words whose tag is not this step's yet —
-//               and adds them in a fixed order (no barrier A, no store drain before an arrival)
-//   [world > 1] peer exchange, unchanged (it already was an LL exchange)
-//   norm        tagged ||g_slice||^2 words, unchanged ("barrier B")
-//   Adam        on the slice; the new weights are PUBLISHED as LL words in tensor-core image order
-//               {fp16 hi | fp16 lo << 16, tag} (biases: {fp32, tag}), index = image byte offset / 2
-//   next step   every CTA rebuilds its shared-memory weight image from those words (ll_load_image: no barrier C, no
-//               second pass over a global image behind it)
+//   write-out   each CTA stores its partial gradient (and its 8 float64 loss statistics as 16 half words) as LL words, then
+//               ONE tagged "done" word — relaxed stores, no fence, no drain
+//   reduce      the owner of slice bx polls the G done words (one warp), pulls the G slices into shared memory with TMA bulk
+//               copies (cp.async.bulk + mbarrier complete_tx: one L2 round trip, no registers) and adds them in a fixed order,
+//               checking every word's tag (a word that is not this step's yet -> the copy is repeated)
+//   [world > 1] peer exchange, norm exchange ("barrier B"), clip + Adam, barrier-C arrival: as in sgd_step_tail
 //
-// Buffers are single (not double-buffered): a CTA writes the partial of step s+1 only after it has read every owner's
-// weights of step s, and an owner publishes those only after it has read every partial of step s.  Tags are the global
-// step count (ts.epoch + round >= 1); the workspace starts zeroed.  All sums keep a fixed order: bit-reproducible.
+// It removes barrier A (store drain + atomic + poll, ~2 us) and turns the slice reduce into one bulk round trip.  The buffer
+// is single: a CTA writes the partial of step s+1 only after it passed barrier C of step s, which every owner reaches
+// after it has consumed the partials of step s.  Tags are the global step count (ts.epoch + round >= 1); the workspace
+// starts zeroed.  All sums keep a fixed order: bit-reproducible.
 __host__ __device__ inline int ll_part_words(int NP) { return ((NP + 3) & ~3) + 2 * DDRL_NSTAT; }
-__host__ __device__ inline int64_t ll_img_words(int D, int A) { return tc_img(D, A).bytes / 2; }
-__host__ __device__ inline int64_t ll_total_words(int P, int G, int NP, int D, int A) {
-    return (int64_t)P * G * ll_part_words(NP) + (int64_t)P * ll_img_words(D, A);
+constexpr int LL_FLAG_STRIDE = 16;      // one done word per 128-byte line
+__host__ __device__ inline int64_t ll_total_words(int P, int G, int NP) {
+    return (int64_t)P * G * ll_part_words(NP) + (int64_t)P * G * LL_FLAG_STRIDE;
 }
+constexpr int LL_STAGE_BYTES = 88 * 1024;      // shared-memory staging of the slice copies (dead activation buffers)
 
 __device__ __forceinline__ void ll_st1(unsigned long long* p, unsigned int payload, unsigned int tag) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | payload) : "memory");
@@ -393,97 +392,33 @@ __device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long* p
 }
 constexpr unsigned int LL_SPINS = 4000000u;
 
-// One matrix of the image: nel fp16 elements at byte offsets hi_off / lo_off (chunked layout, element offset e).
-// kind 0: W1 [64][KX] chunked along d (element real iff d < D); 1: W2 (all real); 2: WoT (real iff row o < nreal).
-// Real elements are taken from the LL words (waiting for this step's tag), padding is written as zero.
-__device__ __forceinline__ bool ll_load_matrix(const unsigned long long* __restrict__ img, unsigned char* sm, int hi_off, int lo_off,
-                                               int nel, int kind, int lim, unsigned int tag, int tid, int nt) {
-    bool ok = true;
-    const int npair = nel >> 1;
-    const unsigned long long* src = img + (hi_off >> 1);
-#pragma unroll 1
-    for (int b0 = tid; b0 < npair; b0 += 4 * nt) {
-        unsigned long long w0[4], w1[4];
-        unsigned int need = 0u;      // bit 2k: first element of pair k is real, bit 2k+1: second
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int pr = b0 + k * nt, e = 2 * pr;
-            w0[k] = 0ull; w1[k] = 0ull;
-            if (pr < npair) {
-                bool r0, r1;
-                if (kind == 0)      { const int d = ((e >> 9) << 3) + (e & 7); r0 = d < lim; r1 = d + 1 < lim; }
-                else if (kind == 1) { r0 = r1 = true; }
-                else                { r0 = r1 = ((e >> 3) & (TC_NO - 1)) < lim; }
-                need |= (r0 ? 1u : 0u) << (2 * k) | (r1 ? 1u : 0u) << (2 * k + 1);
-            }
-        }
-        unsigned int pending = need;
-#pragma unroll 1
-        for (unsigned int it = 0; pending != 0u && it < LL_SPINS; ++it) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((pending >> (2 * k)) & 3u) ll_ld2(src + 2 * (b0 + k * nt), w0[k], w1[k]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (((pending >> (2 * k)) & 1u) && (unsigned int)(w0[k] >> 32) == tag) pending &= ~(1u << (2 * k));
-                if (((pending >> (2 * k + 1)) & 1u) && (unsigned int)(w1[k] >> 32) == tag) pending &= ~(1u << (2 * k + 1));
-            }
-        }
-        ok = ok && pending == 0u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int pr = b0 + k * nt;
-            if (pr < npair) {
-                const unsigned int a = ((need >> (2 * k)) & 1u) ? (unsigned int)w0[k] : 0u;
-                const unsigned int b = ((need >> (2 * k + 1)) & 1u) ? (unsigned int)w1[k] : 0u;
-                *reinterpret_cast<unsigned int*>(sm + hi_off + 4 * pr) = (a & 0xffffu) | (b << 16);
-                *reinterpret_cast<unsigned int*>(sm + lo_off + 4 * pr) = (a >> 16) | (b & 0xffff0000u);
-            }
-        }
-    }
-    return ok;
+// TMA bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned int smem_dst, const void* gsrc, unsigned int bytes, unsigned int mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
 }
-
-// Rebuild the shared-memory weight image of policy p from the LL words of step `tag` (all nt calling threads take part;
-// the caller publishes the writes to the async proxy).  w1_only: just the W1 matrices (multi-tile CTAs restore them
-// after the loss-gradient operand has used their space).
-__device__ __forceinline__ bool ll_load_image(const SgdTail& t, int p, int P, int G, int NP, int D, int A, unsigned char* sm,
-                                              unsigned int tag, int tid, int nt, bool w1_only) {
-    const TcImg I = tc_img(D, A);
-    const int KX = tc_kx(D);
-    const unsigned long long* img = t.ll_ws + (int64_t)P * G * ll_part_words(NP) + (int64_t)p * ll_img_words(D, A);
-    bool ok = true;
-    ok = ll_load_matrix(img, sm, I.W1[0][0], I.W1[0][1], 64 * KX, 0, D, tag, tid, nt) && ok;
-    ok = ll_load_matrix(img, sm, I.W1[1][0], I.W1[1][1], 64 * KX, 0, D, tag, tid, nt) && ok;
-    if (w1_only) return ok;
-    ok = ll_load_matrix(img, sm, I.W2[0][0], I.W2[0][1], 64 * 64, 1, 0, tag, tid, nt) && ok;
-    ok = ll_load_matrix(img, sm, I.W2[1][0], I.W2[1][1], 64 * 64, 1, 0, tag, tid, nt) && ok;
-    ok = ll_load_matrix(img, sm, I.WoT[0][0], I.WoT[0][1], TC_NO * 64, 2, 2 * A, tag, tid, nt) && ok;
-    ok = ll_load_matrix(img, sm, I.WoT[1][0], I.WoT[1][1], TC_NO * 64, 2, 1, tag, tid, nt) && ok;
-    // fp32 block: b1c[128] b2c[128] bo[16] bvo[4]; real entries: all of b1c / b2c, bo[0 .. 2A), bvo[0]
+__device__ __forceinline__ void mbar_expect_tx(unsigned int mbar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_parity(unsigned int mbar, unsigned int parity) {
 #pragma unroll 1
-    for (int k = tid; k < 128 + 128 + 16 + 4; k += nt) {
-        const bool real = k < 256 || (k < 272 ? (k - 256) < 2 * A : k == 272);
-        unsigned int v = 0u;
-        if (real) {
-            unsigned long long w = 0ull;
-            bool hit = false;
-#pragma unroll 1
-            for (unsigned int it = 0; it < LL_SPINS; ++it) {
-                w = ll_ld1(img + (I.b1c >> 1) + 2 * k);
-                if ((unsigned int)(w >> 32) == tag) { hit = true; break; }
-            }
-            ok = ok && hit;
-            v = (unsigned int)w;
-        }
-        *reinterpret_cast<unsigned int*>(sm + I.b1c + 4 * k) = v;
+    for (unsigned int i = 0; i < 20000000u; ++i) {
+        unsigned int ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return true;
     }
-    return ok;
+    return false;
 }
 
 // Requires sgd_slice_len(NP, G) <= blockDim.x (thread tid owns element bx * S + tid of the slice).
+//   smem   16 * blockDim.x + 256 bytes of scratch (16-byte aligned), disjoint from `stage`
+//   stage  LL_STAGE_BYTES of shared memory (16-byte aligned) for the slice copies
+//   mbar   shared::cta address of an mbarrier initialised with count 1; *mbar_phase = its current parity (kept by the caller)
 __device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailStep& ts, int p, int P, int bx, int G, int NP, int step,
-                                                 int D, int A, float* smem, long long* dbg = nullptr) {
+                                                 int D, int A, float* smem, unsigned char* stage, unsigned int mbar,
+                                                 unsigned int& mbar_phase, long long* dbg = nullptr) {
 #define TAIL_STAMP(i)                                                                                              \
     do {                                                                                                           \
         if (dbg && threadIdx.x == 0) {                                                                             \
@@ -496,67 +431,77 @@ __device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailSte
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int NPs = (NP + 3) & ~3, LLW = ll_part_words(NP);
     const unsigned int tag = ts.epoch + (unsigned int)ts.round;
-    float2* scr = reinterpret_cast<float2*>(smem);      // [ngrp][npair]
     float* red = smem + 4 * nt;                         // [64]: warp partials, flags
     const int W = t.world > 1 ? t.world : 1;
     bool ok = true;
-    const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S);
+    const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S), len = max(0, j1 - j0);
     const int j_own = j0 + tid;
     const bool own = tid < S && j_own < NP;
+    unsigned long long* flags = t.ll_ws + (int64_t)P * G * LLW + (int64_t)p * G * LL_FLAG_STRIDE;
+    // caller: __syncthreads() after the write-out -> every LL store of this CTA has been issued
+    if (tid == 0) {
+        ll_st1(flags + (int64_t)bx * LL_FLAG_STRIDE, 0u, tag);
+        red[40] = 1.f;
+        red[41] = 0.f;
+    }
     // optimizer state of this thread's element: independent of the reduce, the loads fly behind it
     float m_pf = 0.f, v_pf = 0.f, th_pf = 0.f;
     if (own) {
         const int64_t k = (int64_t)p * NP + j_own;
         m_pf = __ldcg(t.m + k); v_pf = __ldcg(t.v + k); th_pf = __ldcg(t.theta + k);
     }
-    if (tid == 0) red[40] = 1.f;
+    // ---- wait for the G done words (warp 0), then pull the slices: chunks of `pc` partials per bulk round ---------------
+    const unsigned int slice_bytes = (unsigned int)len * 8u;
+    const int pc = slice_bytes > 0 ? min(G, (int)(LL_STAGE_BYTES / slice_bytes)) : G;      // partials per staging round
+    if (warp == 0) {
+        bool got = true;
+        for (int i = lane; i < G; i += 32) {
+            bool hit = false;
+#pragma unroll 1
+            for (unsigned int it = 0; it < 8000000u; ++it) {
+                if ((unsigned int)(ll_ld1(flags + (int64_t)i * LL_FLAG_STRIDE) >> 32) == tag) { hit = true; break; }
+            }
+            got = got && hit;
+        }
+        got = __all_sync(0xffffffffu, got);
+        if (lane == 0 && !got) red[40] = 0.f;
+    }
     TAIL_STAMP(40);
-
-    // ---- slice reduce over the G partials: group g adds partials g, g + ngrp, ...; 4 polled loads in flight -----------
-    const int npair = max(0, (j1 - j0) >> 1);
-    const int ngrp = npair > 0 ? max(1, min(min(8, G), nt / npair)) : 1;
-    {
-        const int g = npair > 0 ? tid / npair : ngrp, c = npair > 0 ? tid - g * npair : 0;
-        if (g < ngrp) {
-            const unsigned long long* src = t.ll_ws + (int64_t)p * G * LLW + j0 + 2 * c;
-            float2 acc = make_float2(0.f, 0.f);
+    float gsum = 0.f;
+    const unsigned long long* stg = reinterpret_cast<const unsigned long long*>(stage);
+    const unsigned int stage_s = (unsigned int)__cvta_generic_to_shared(stage);
 #pragma unroll 1
-            for (int i0 = g; i0 < G; i0 += 4 * ngrp) {
-                unsigned long long a[4], b[4];
-                unsigned int pending = 0u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    a[k] = 0ull; b[k] = 0ull;
-                    if (i0 + k * ngrp < G) pending |= 1u << k;
-                }
+    for (int c0 = 0; c0 < G && len > 0; c0 += pc) {
+        const int nc = min(pc, G - c0);
 #pragma unroll 1
-                for (unsigned int it = 0; pending != 0u && it < LL_SPINS; ++it) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if ((pending >> k) & 1u) ll_ld2(src + (int64_t)(i0 + k * ngrp) * LLW, a[k], b[k]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (((pending >> k) & 1u) && (unsigned int)(a[k] >> 32) == tag && (unsigned int)(b[k] >> 32) == tag)
-                            pending &= ~(1u << k);
-                }
-                ok = ok && pending == 0u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {      // words of absent partials are zero
-                    acc.x += __uint_as_float((unsigned int)a[k]);
-                    acc.y += __uint_as_float((unsigned int)b[k]);
+        for (int attempt = 0; attempt < 64; ++attempt) {
+            __syncthreads();      // done words seen (first round) / previous use of the staging buffer over
+            if (warp == 0) {
+                if (lane == 0) mbar_expect_tx(mbar, (unsigned int)nc * slice_bytes);
+                __syncwarp();
+                for (int i = lane; i < nc; i += 32)
+                    bulk_g2s(stage_s + (unsigned int)i * slice_bytes, t.ll_ws + ((int64_t)p * G + c0 + i) * LLW + j0, slice_bytes, mbar);
+            }
+            if (!mbar_wait_parity(mbar, mbar_phase)) ok = false;
+            mbar_phase ^= 1u;
+            float part = 0.f;
+            bool bad = false;
+            if (tid < len) {
+#pragma unroll 4
+                for (int i = 0; i < nc; ++i) {
+                    const unsigned long long w = stg[(int64_t)i * len + tid];
+                    bad = bad || (unsigned int)(w >> 32) != tag;
+                    part += __uint_as_float((unsigned int)w);
                 }
             }
-            scr[g * npair + c] = acc;
+            if (!__syncthreads_or(bad ? 1 : 0)) { gsum += part; break; }      // all words were this step's: partial order fixed
+            if (attempt == 63) ok = false;
         }
     }
-    __syncthreads();
     float gval = 0.f;      // this thread's reduced gradient element (register-resident up to the Adam update)
     {
-        float s = 0.f;
-        const bool act = tid < 2 * npair;
-        if (act) {
-            for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * npair + (tid >> 1)])[tid & 1];
-        }
+        const float s = gsum;
+        const bool act = tid < len;
         const int64_t xstride = (int64_t)G * S;
         float* slice_dst = t.grad + (int64_t)p * NP + j0;
         if (W > 1) {
@@ -565,7 +510,7 @@ __device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailSte
             const unsigned long long want = (unsigned long long)(seq + 1u) << 32;
             const int par = (int)(seq & 1u);
             const int64_t xoff = (((int64_t)par * W + t.rank) * P + p) * xstride + j0;
-            const float s_nb = __shfl_down_sync(0xffffffffu, s, 1);      // whole warps: npair pairs never straddle a warp edge
+            const float s_nb = __shfl_down_sync(0xffffffffu, s, 1);      // len is even: pairs never straddle a warp edge
             if (act && j_own < NP && (tid & 1) == 0) {
                 const unsigned long long w0 = want | (unsigned long long)__float_as_uint(s);
                 if (j_own + 1 < NP) {
@@ -667,7 +612,7 @@ __device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailSte
     __syncthreads();
     ok = red[39] != 0.f && red[40] != 0.f;
     TAIL_STAMP(42);
-    // ---- clip + TF1 Adam on the slice; publish the new weights as LL words in image order ------------------------------
+    // ---- clip + TF1 Adam on the slice; the tensor-core image first (it is what barrier C publishes) ----------------------
     if (own) {
         const float scale = red[32];
         const float alpha = t.lr * sqrtf(1.f - ts.b2p) / (1.f - ts.b1p);
@@ -682,37 +627,38 @@ __device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailSte
         bool f16;
         int p0, p1;
         tc_img_pos(L, o, D, A, j_own, f16, p0, p1);
-        unsigned long long* limg = t.ll_ws + (int64_t)P * G * LLW + (int64_t)p * ll_img_words(D, A);
         unsigned char* im = reinterpret_cast<unsigned char*>(t.fcnet_tc_img) + (int64_t)p * L.bytes;
         if (f16) {
             const float ws = tnew * 256.f;
             const __half hi = __float2half_rn(ws);
-            const __half lo = __float2half_rn(ws - __half2float(hi));
-            ll_st1(limg + (p0 >> 1), (unsigned int)__half_as_ushort(hi) | ((unsigned int)__half_as_ushort(lo) << 16), tag);
-            if (t.fcnet_tc_img) {      // the global image serves the first step of the next launch and the inference forward
-                *reinterpret_cast<__half*>(im + p0) = hi;
-                *reinterpret_cast<__half*>(im + p1) = lo;
-            }
+            *reinterpret_cast<__half*>(im + p0) = hi;
+            *reinterpret_cast<__half*>(im + p1) = __float2half_rn(ws - __half2float(hi));
         } else {
-            ll_st1(limg + (p0 >> 1), __float_as_uint(tnew), tag);
-            if (t.fcnet_tc_img) *reinterpret_cast<float*>(im + p0) = tnew;
+            *reinterpret_cast<float*>(im + p0) = tnew;
         }
         t.m[k] = mj;
         t.v[k] = vj;
         t.theta[k] = tnew;
     }
+    // ---- end of step: barrier-C arrival (more steps follow in this launch) or the done ticket (last step) -----------------
+    __syncthreads();
     TAIL_STAMP(43);
-    // ---- last step of the launch: the done ticket advances the clocks ---------------------------------------------------
-    if (ts.last) {
-        __syncthreads();
-        if (tid == 0) {
+    if (tid == 0) {
+        if (!ts.last) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(t.barrier_ws + 4 * p + 2) : "memory");   // Adam slice visible
+        } else {
             __threadfence();
             if (bx == 0) {     // every CTA read beta_pow at kernel entry: safe to advance
                 t.beta_pow[p * 2] = ts.b1p * t.beta1;
                 t.beta_pow[p * 2 + 1] = ts.b2p * t.beta2;
             }
             const unsigned int total = gridDim.x * gridDim.y;
-            if (atomicAdd(t.barrier_ws + 4 * P, 1u) == total - 1) {   // last CTA of the grid: clocks
+            if (atomicAdd(t.barrier_ws + 4 * P, 1u) == total - 1) {   // last CTA of the grid: clocks, re-arm
+                for (int q = 0; q < P; ++q) {
+                    t.barrier_ws[4 * q] = 0u;
+                    t.barrier_ws[4 * q + 1] = 0u;
+                    t.barrier_ws[4 * q + 2] = 0u;
+                }
                 t.barrier_ws[4 * P + 1] = ts.epoch + (unsigned int)ts.nsteps;   // every CTA read it at kernel entry
                 if (t.step_ctr) *t.step_ctr += ts.nsteps;
                 if (t.seq) *t.seq = ts.seq + 1u;
@@ -720,8 +666,8 @@ __device__ __forceinline__ bool sgd_step_tail_ll(const SgdTail& t, const TailSte
                 __threadfence();
             }
         }
+        if (!ok && t.status) atomicOr(t.status, 64);
     }
-    if (tid == 0 && !ok && t.status) atomicOr(t.status, 64);
     return ok;
 #undef TAIL_STAMP
 }

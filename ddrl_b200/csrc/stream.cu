@@ -731,7 +731,7 @@ extern "C" int64_t ddrl_sgd_exchange_words(int NP, int ctas_per_policy) {
 
 extern "C" int64_t ddrl_sgd_ll_words(int P, int ctas_per_policy, int D, int A) {
     if (P < 1 || ctas_per_policy < 1 || D < 1 || A < 1) return DDRL_E_BADARG;
-    return ll_total_words(P, ctas_per_policy, fc_offsets(D, A).NP, D, A);
+    return ll_total_words(P, ctas_per_policy, fc_offsets(D, A).NP);
 }
 
 // ---- peer-mapped memory (CUDA IPC) for the in-kernel gradient all-reduce ------------------------------------------------

@@ -124,8 +124,10 @@ __device__ __forceinline__ long long t2_gtime() {
 
 // FWD = true: forward-only (inference) mode — the same F1 / tanh / F2 / tanh / heads pipeline over ALL rows of each policy
 // (a.MB = a.R), filter normalisation in the X split, DiagGaussian sample + logp in place of the loss, nothing after it.
-template <int A, bool FWD>
-__global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrainArgs a) {
+// LL = true: the barrier-free "LL" tail (sgd_tail.cuh); its own instantiation so that the classic kernel keeps its register
+// allocation (the kernel sits at the 96-register limit of 640 threads: the merged variant spilled and lost 3 us per step).
+template <int A, bool FWD, bool LL>
+__global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_constant__ TcTrainArgs a) {
     constexpr int A2 = 2 * A;
     T2_STAMP(0);
     extern __shared__ __align__(1024) unsigned char sm[];
@@ -142,13 +144,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 
     // ---- once per launch: TMEM, mbarriers, launch-wide state -------------------------------------------------------------
     if (warp == 0) umma::tmem_alloc(tslot, T2_TMEM_COLS);
-    if (tid == 0) { umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::fence_mbar_init(); }   // every MMA warp commits
+    if (tid == 0) {      // every MMA warp commits; [4] (byte 32): TMA bulk copies of the LL tail
+        umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::mbar_init(mbar + 4, 1); umma::fence_mbar_init();
+    }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = *tslot;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     uint32_t ph0 = 0, ph1 = 0;
+    unsigned int ll_phase = 0;
     bool ok = true;
     int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 8 = dl, 16 = dz2, 32 = dz1
     const float klc = a.kl_coeff[p];
@@ -158,15 +163,15 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     // Thread-block clusters (launch attribute; cluster = cs consecutive CTAs of one policy): the per-CTA partial gradient
     // goes to shared memory, the cluster adds its cs partials over distributed shared memory (CTA r owns 1/cs of the
     // vector) and only ONE partial per cluster reaches L2 — the 148 x 45 KB write / drain / re-read per step was ~9 us.
-    const int cs = (int)umma::cluster_nctarank(), crank = (int)umma::cluster_ctarank();
+    const int cs = LL ? 1 : (int)umma::cluster_nctarank(), crank = LL ? 0 : (int)umma::cluster_ctarank();
     const int ncl = G / cs, cid = bx / cs;                 // clusters per policy, this CTA's cluster
     float* stg = reinterpret_cast<float*>(sm + S.H1[0][0]);   // [NPs] staging of the partial (H1 is free after the main loop)
     float* gp = cs > 1 ? stg : a.grad_part + ((int64_t)p * G + bx) * NPs;
     const bool has_tail = a.tail.theta != nullptr;
     // LL tail (sgd_tail.cuh): partial gradients and updated weights travel between CTAs as self-validating words
-    const bool ll = !FWD && has_tail && a.tail.ll_ws != nullptr && cs == 1 && sgd_slice_len(o.NP, G) <= T2_NT;
+    constexpr bool ll = LL;      // the launcher picks the instantiation: fused tail, ll_ws given, no clusters, slice <= CTA
     const int LLW = ll_part_words(o.NP);
-    unsigned long long* llp = ll ? a.tail.ll_ws + ((int64_t)p * G + bx) * LLW : nullptr;
+    unsigned long long* llp = a.tail.ll_ws + ((int64_t)p * G + bx) * LLW;      // used only if LL
     const int nsteps = (has_tail && a.tail.nsteps > 1) ? a.tail.nsteps : 1;   // consecutive SGD steps of this launch
     const int step0 = a.step_ctr ? *a.step_ctr : 0;
     TailStep ts;
@@ -226,17 +231,11 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
     const unsigned int tag = ts.epoch + (unsigned int)s + 1u;      // LL tag of THIS step's partials / weights
-    if (s > 0 && ll) {   // rebuild the weight image from the LL words the slice owners published in the previous step's tail
-        if (!ll_load_image(a.tail, p, gridDim.y, G, o.NP, D, A, sm, tag - 1u, tid, T2_NT, false)) {
-            ok = false;
-            if (a.status) atomicOr(a.status, 64);
-        }
-        if (warp >= T2_MMA_WARP) umma::fence_async_smem();   // the epilogue warps fence in publish() before F1
-    } else if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
+    if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
         if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
         __syncthreads();
     }
-    if (warp < T2_MMA_WARP && !(s > 0 && ll)) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
+    if (warp < T2_MMA_WARP) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
         const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
 #pragma unroll 2
         for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
@@ -262,7 +261,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     do {   // single exit towards the fused tail (one inlined copy of it)
     if (cr1 <= cr0) {   // no rows: zero partial, no tensor work (still takes part in the fused tail)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        if (ll) {
+        if (FWD) break;      // inference: a CTA without rows has nothing to write (there is no partial-gradient buffer)
+        if constexpr (LL) {
             for (int i = tid; i < (LLW >> 1); i += T2_NT) ll_st2(llp + 2 * i, 0u, 0u, tag);
         } else {
             for (int i = tid; i < NPs; i += T2_NT) gp[i] = 0.f;
@@ -307,11 +307,11 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
     // (Not with clusters: the staging buffer of the partial lives in H1, which B5 still reads.)
     const bool early_out = cs == 1;
     auto put1 = [&](int idx, float v) {
-        if (ll) ll_st1(llp + idx, __float_as_uint(v), tag);
+        if constexpr (LL) ll_st1(llp + idx, __float_as_uint(v), tag);
         else gp[idx] = v;
     };
     auto put4 = [&](int idx, float x0, float x1, float x2, float x3) {      // idx % 4 == 0
-        if (ll) {
+        if constexpr (LL) {
             ll_st2(llp + idx, __float_as_uint(x0), __float_as_uint(x1), tag);
             ll_st2(llp + idx + 2, __float_as_uint(x2), __float_as_uint(x3), tag);
         } else {
@@ -667,13 +667,9 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
             T2_STAMP(21 + 3 * b);
         }
         if (S.dl_in_w1 && row0 + TC_ROWS < cr1) {   // both B1 are complete (DL dead) and another tile follows: restore W1
-            if (ll && s > 0) {      // this step's weights exist as LL words only (the global image is not fenced between steps)
-                ok = ll_load_image(a.tail, p, gridDim.y, G, o.NP, D, A, sm, tag - 1u, tid, TC_NT, true) && ok;
-            } else {
-                const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+            const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
 #pragma unroll 1
-                for (int i = I.W1[0][0] / 16 + tid; i < I.W2[0][0] / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
-            }
+            for (int i = I.W1[0][0] / 16 + tid; i < I.W2[0][0] / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
         }
         // ---- dz1 epilogue -> B5: gW1_b[c][d] (+)= dZ1_b^T X   (column D of X is the constant 1 -> bias gradient) --------
 #pragma unroll 1
@@ -742,7 +738,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         const int w0 = (tid == 0 || tid == 1 || tid == 3) ? 0 : 4;
         const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
         const double sv = sum4(w0, idx);
-        if (ll) {
+        if constexpr (LL) {
             const unsigned long long bits = (unsigned long long)__double_as_longlong(sv);
             ll_st2(llp + NPs + 2 * tid, (unsigned int)bits, (unsigned int)(bits >> 32), tag);
         } else {
@@ -750,7 +746,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         }
     }
     } while (0);
-    if (cs > 1) {   // in-cluster reduction over distributed shared memory: CTA `crank` adds part `crank` of the cs staged partials
+    if (!LL && cs > 1) {   // in-cluster reduction over distributed shared memory: CTA `crank` adds part `crank` of the cs staged partials
         __syncthreads();
         umma::cluster_sync_all();
         const int n4 = NPs >> 2, pl4 = (n4 + cs - 1) / cs;          // float4s in the vector / per part
@@ -791,10 +787,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
         ts.round = s + 1;
         ts.last = s == nsteps - 1;
         bool tok;
-        if (ll) {
+        if constexpr (LL) {
             __syncthreads();      // every thread is past its last use of the shared memory the tail scratches
-            tok = sgd_step_tail_ll(a.tail, ts, p, gridDim.y, bx, G, o.NP, step, D, A, reinterpret_cast<float*>(sm + S.H2[0][0]),
-                                   a.dbg_clock);
+            tok = sgd_step_tail_ll(a.tail, ts, p, gridDim.y, bx, G, o.NP, step, D, A, reinterpret_cast<float*>(sm + S.X[0]),
+                                   sm + S.H1[0][0], sbase + S.bar + 32, ll_phase, a.dbg_clock);
         } else {
             tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
                                 reinterpret_cast<float*>(sm + S.H2[0][0]), a.dbg_clock, ncl);
@@ -819,10 +815,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const TcTrain
 static int g_tc2_cluster = 0;    // 0 = off (default: measured slower), -1 = automatic (largest of 16, 8, 4, 2 that
                                  // divides G and is co-resident), else the forced size
 
-template <int A, bool FWD>
+template <int A, bool FWD, bool LL>
 static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st, int* used_cluster) {
     static bool attr = false;
-    auto kern = fcnet_train_tc2_kernel<A, FWD>;
+    auto kern = fcnet_train_tc2_kernel<A, FWD, LL>;
     if (!attr) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
@@ -860,7 +856,7 @@ static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStr
         cache_P = P; cache_G = G; cache_cs = best; cache_req = g_tc2_cluster;
     }
     // without the fused tail the caller reduces G per-CTA partials itself (ddrl_grad_reduce): no cluster pre-reduction
-    const int cs_use = a.tail.theta ? cache_cs : 1;
+    const int cs_use = (a.tail.theta && !LL) ? cache_cs : 1;
     at[0].val.clusterDim.x = cs_use;
     if (used_cluster) *used_cluster = cs_use;
     if (cudaLaunchKernelEx(&cfg, kern, a) != cudaSuccess) {
@@ -874,11 +870,22 @@ static int g_tc2_last_cluster = 0;
 
 int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
     const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
+    // LL tail: fused tail with an LL workspace, no thread-block clusters requested, one slice element per thread
+    const bool ll = a.tail.theta && a.tail.ll_ws && g_tc2_cluster == 0 && sgd_slice_len(fc_offsets(a.D, a.A).NP, G) <= T2_NT;
+    if (ll) {
+        switch (a.A) {
+            case 1: return launch_tc2_t<1, false, true>(a, P, G, smem, st, &g_tc2_last_cluster);
+            case 2: return launch_tc2_t<2, false, true>(a, P, G, smem, st, &g_tc2_last_cluster);
+            case 4: return launch_tc2_t<4, false, true>(a, P, G, smem, st, &g_tc2_last_cluster);
+            case 8: return launch_tc2_t<8, false, true>(a, P, G, smem, st, &g_tc2_last_cluster);
+            default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4,8}"); return DDRL_E_UNSUPPORTED_SHAPE;
+        }
+    }
     switch (a.A) {
-        case 1: return launch_tc2_t<1, false>(a, P, G, smem, st, &g_tc2_last_cluster);
-        case 2: return launch_tc2_t<2, false>(a, P, G, smem, st, &g_tc2_last_cluster);
-        case 4: return launch_tc2_t<4, false>(a, P, G, smem, st, &g_tc2_last_cluster);
-        case 8: return launch_tc2_t<8, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 1: return launch_tc2_t<1, false, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 2: return launch_tc2_t<2, false, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 4: return launch_tc2_t<4, false, false>(a, P, G, smem, st, &g_tc2_last_cluster);
+        case 8: return launch_tc2_t<8, false, false>(a, P, G, smem, st, &g_tc2_last_cluster);
         default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4,8}"); return DDRL_E_UNSUPPORTED_SHAPE;
     }
 }
@@ -887,10 +894,10 @@ int launch_tc2_forward(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
     const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
     int dummy = 0;
     switch (a.A) {
-        case 1: return launch_tc2_t<1, true>(a, P, G, smem, st, &dummy);
-        case 2: return launch_tc2_t<2, true>(a, P, G, smem, st, &dummy);
-        case 4: return launch_tc2_t<4, true>(a, P, G, smem, st, &dummy);
-        case 8: return launch_tc2_t<8, true>(a, P, G, smem, st, &dummy);
+        case 1: return launch_tc2_t<1, true, false>(a, P, G, smem, st, &dummy);
+        case 2: return launch_tc2_t<2, true, false>(a, P, G, smem, st, &dummy);
+        case 4: return launch_tc2_t<4, true, false>(a, P, G, smem, st, &dummy);
+        case 8: return launch_tc2_t<8, true, false>(a, P, G, smem, st, &dummy);
         default: set_error("fcnet_forward_tc: A must be 1, 2, 4 or 8"); return DDRL_E_UNSUPPORTED_SHAPE;
     }
 }

@@ -282,18 +282,18 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile", "tc-classic", "tc-llmt"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile", "tc-ll", "tc-llmt"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
 def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
     """filter -> forward/sample -> GAE -> standardise -> 2 epochs x 4 minibatches of clip+Adam -> KL update.
     "-3k" = the three-kernel SGD step (train, grad_reduce, clip_adam) instead of the fused tail; "-1step" = one launch
-    per optimizer step instead of one persistent launch per epoch.  "tc" (32 CTAs per policy) runs the barrier-free LL tail
-    (csrc/sgd_tail.cuh); "-classic" = the same with the three-barrier tail; "-llmt" = LL tail with two 128-row tiles per CTA
-    (24 CTAs per policy x 136 rows: the W1 part of the image is restored from the LL words between the tiles)."""
+    per optimizer step instead of one persistent launch per epoch.  "-ll" = the opt-in LL tail (partial gradients as
+    self-validating words pulled by TMA bulk copies, csrc/sgd_tail.cuh) at 32 CTAs per policy; "-llmt" = the same with two
+    128-row tiles per CTA (24 CTAs per policy x 136 rows)."""
     fuse = not mode.endswith("-3k")
-    classic = mode.endswith("-classic")
     llmt = mode.endswith("-llmt")
+    ll = mode.endswith("-ll") or llmt
     persistent = not mode.endswith("-1step")      # "tc": one persistent launch per epoch where the kernel allows it
     cluster = mode.endswith("-cluster")           # thread-block clusters pre-reduce the partial gradients over DSMEM
     multitile = mode.endswith("-multitile")       # 2 CTAs per policy x 256 rows: two 128-row tiles per CTA, persistent launch
@@ -322,7 +322,7 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
 
     L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse,
                      persistent=persistent, ctas_per_policy=8 if cluster else 2 if multitile else 24 if llmt else None,
-                     ll_tail=not classic)
+                     ll_tail=ll)
     if cluster:
         from ddrl_b200 import kernels as K
         K.tc_set_cluster(-1)
@@ -394,7 +394,9 @@ def test_packed_weight_image_path_equals_flat_path():
 
 
 @pytest.mark.parametrize("arch", ["FullyDecentral", "Local", "TwoSides", "Centralized", "SingleDiagonal", "FullyDecentral_TVel"])
-@pytest.mark.parametrize("R", [1, 100, 128, 700, 20011])      # 20011: several 128-row tiles per CTA, ragged last tile
+@pytest.mark.parametrize("R", [1, 100, 128, 700, 6528, 20011])      # 20011: several 128-row tiles per CTA, ragged last tile;
+# 6528: the rows-per-CTA rounding leaves the last CTA of a policy WITHOUT rows (it wrote through a null partial-gradient
+# pointer before round 2)
 def test_tensor_core_inference_forward_matches_oracle(arch, R):
     """ddrl_fcnet_forward_tc: filter normalise -> logits / value -> DiagGaussian sample + logp, on checkpoint weights with
     the checkpoint's filter; 1e-5 of the tensor's scale vs the float64 oracle; obs_out identical to the FP32 kernel's."""
