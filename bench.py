@@ -214,7 +214,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def time_graphnet(envs, epochs, steps, warmup, two_launch=False):
+def time_graphnet(envs, epochs, steps, warmup, step_kind="tc"):
     """BASELINE.json configs[3] — shared GraphNet policy over the 4-leg graph, `envs` envs x 4 agents, T=32, one weight set,
     minibatch = rows/32; -> (ms per learner iteration, config dict)."""
     import torch
@@ -229,7 +229,7 @@ def time_graphnet(envs, epochs, steps, warmup, two_launch=False):
     cfg = PPOConfig(num_sgd_iter=E, sgd_minibatch_size=R // nb)
     g = torch.Generator().manual_seed(7)
     th = _FlatParams(graphnet_shapes(2 * A)).init_host(g, small=("actor/linear_out", "critic/linear_out")).reshape(1, -1)
-    L = GraphNetLearner(A, cfg, dev, theta=th, two_launch_step=two_launch)
+    L = GraphNetLearner(A, cfg, dev, theta=th, step=step_kind)
     state = torch.randn(T, C, 4, 23, generator=g).to(dev)
     idx = torch.arange(4, dtype=torch.int32).repeat(T * N).reshape(T, C).to(dev)
     adj = torch.from_numpy(QuantrupedDecentralizedSharedGraphEnv.create_adj()).float().expand(T, C, 4, 4).contiguous().to(dev)
@@ -252,14 +252,14 @@ def time_graphnet(envs, epochs, steps, warmup, two_launch=False):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return ms, {"workload": "Shared GraphNet policy over the 4-leg graph (BASELINE.json configs[3])", "envs": N, "fragment_T": T,
-                "rows": R, "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_step": getattr(L, "step_kind", "two-launch" if two_launch else "three-kernel")}
+                "rows": R, "num_sgd_iter": E, "minibatches_per_epoch": nb, "sgd_step": L.step_kind}
 
 
 def run_graphnet(args):
     """Supplementary line (not the headline): BASELINE.json configs[3]."""
     import torch
     torch.cuda.set_device(0)
-    ms, cfgd = time_graphnet(args.envs, args.gn_epochs, args.steps, args.warmup, args.gn_two_launch)
+    ms, cfgd = time_graphnet(args.envs, args.gn_epochs, args.steps, args.warmup, args.gn_step)
     print(json.dumps({"metric": METRIC, "value": cfgd["rows"] / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                       "config": dict(cfgd, note="supplementary")}))
@@ -362,7 +362,8 @@ def main():
                     help="tcgen05 schedule: 0 auto, 1 branch-sequential, 2 ping-pong (A/B timing)")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per policy of the SGD-step kernel (0 = the learner's choice)")
     ap.add_argument("--sets", type=int, default=3, help="rotating rollout sets (aggregate > L2)")
-    ap.add_argument("--gn-two-launch", action="store_true", help="graphnet workload: ddrl_graphnet_train_step (A/B; measured slower than the three-kernel step)")
+    ap.add_argument("--gn-step", default="tc", choices=["tc", "three-kernel", "two-launch"],
+                    help="graphnet workload: SGD-step kernel (tc = persistent tensor-core step, default)")
     ap.add_argument("--workload", default="fcnet", choices=["fcnet", "graphnet"])
     ap.add_argument("--arch", default="FullyDecentral",
                     help="supplementary: any published architecture (Centralized, FullyDecentral, Local, SingleNeighbor, "

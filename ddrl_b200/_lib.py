@@ -75,6 +75,8 @@ PROTOTYPES = {
     "ddrl_graphnet_set_variant": (C.c_int, [C.c_int]),
     "ddrl_graphnet_train_ws_bytes": (C.c_int64, [C.c_int64]),
     "ddrl_graphnet_train_stat_parts": (C.c_int, [C.c_int64]),
+    "ddrl_graphnet_train_step_tc": (C.c_int, [c_f32p, c_i32p] + [c_f32p] * 8 + [C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, c_f32p,
+                                                C.POINTER(PPOHyper), C.c_int, c_f32p, c_f64p, c_i32p, C.POINTER(SgdTail), c_stream]),
     "ddrl_graphnet_train_step": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                            C.c_int64, C.c_int, c_f32p, C.POINTER(PPOHyper), C.c_int, C.c_void_p, c_f32p, c_f64p,
                                            c_stream]),

@@ -416,6 +416,31 @@ def graphnet_train_step(theta, node_idx, state, adj, actions, old_logits, old_lo
     return ws
 
 
+def graphnet_train_step_tc(theta, node_idx, state, adj, actions, old_logits, old_logp, vf_preds, adv, vtarg, A: int, MB: int,
+                           mb_perm, step_ctr, kl_coeff, hyper: PPOHyper, ctas_per_net: int, grad_part, stat_part, status=None,
+                           tail: Optional[SgdTail] = None):
+    """Persistent tensor-core GraphNet SGD step(s) over ALL R rows of the (shuffled) train batch: theta [NP], node_idx [R] i32,
+    state [R,4,23], adj [R,4,4], actions [R,A], old_logits [R,2A], old_logp / vf_preds / adv / vtarg [R]; step k of the launch
+    trains minibatch mb_perm[step_ctr + k] (see ddrl_graphnet_train_step_tc).  grad_part [ctas_per_net, NPs] f32, stat_part
+    [2 * ctas_per_net, 8] f64 zero-initialised."""
+    R = state.shape[0]
+    f32 = torch.float32
+    if tuple(state.shape[1:]) != (GN_NODES, GN_FEATS + GN_ENC_IN) or tuple(adj.shape[1:]) != (GN_NODES, GN_NODES):
+        raise DDRLError(f"graphnet: state {tuple(state.shape)} / adj {tuple(adj.shape)} must be [R,4,23] / [R,4,4]")
+    if theta.numel() != graphnet_num_params(2 * A):
+        raise DDRLError(f"graphnet: theta has {theta.numel()} params, expected {graphnet_num_params(2 * A)}")
+    if tuple(grad_part.shape) != (ctas_per_net, part_stride(theta.numel())) or stat_part.numel() != 2 * ctas_per_net * NSTAT:
+        raise DDRLError(f"graphnet_train_step_tc: grad_part must be [{ctas_per_net}, {part_stride(theta.numel())}] f32, stat_part "
+                        f"[{2 * ctas_per_net}, {NSTAT}] f64")
+    _lib.check(_lib.load().ddrl_graphnet_train_step_tc(
+        _p(theta, f32, "theta"), _p(node_idx, torch.int32, "node_idx"), _p(state, f32, "state"), _p(adj, f32, "adj"),
+        _p(actions, f32, "actions"), _p(old_logits, f32, "old_logits"), _p(old_logp, f32, "old_logp"),
+        _p(vf_preds, f32, "vf_preds"), _p(adv, f32, "adv"), _p(vtarg, f32, "vtarg"), R, A, int(MB),
+        _p(mb_perm, torch.int32, "mb_perm"), _p(step_ctr, torch.int32, "step_ctr"), _p(kl_coeff, f32, "kl_coeff"),
+        C.byref(hyper), int(ctas_per_net), _p(grad_part, f32, "grad_part"), _p(stat_part, torch.float64, "stat_part"),
+        _p(status, torch.int32, "status"), C.byref(tail) if tail is not None else None, _stream()), "graphnet_train_step_tc")
+
+
 def dg_sample(logits: torch.Tensor, eps: torch.Tensor):
     """logits [R,2A], eps [R,A] -> action [R,A], logp [R]  (DiagGaussian sample, unclipped)."""
     R, A = eps.shape

@@ -476,15 +476,22 @@ class GraphNetLearner(_LearnerBase):
     quantruped_GraphDecentralizedController_environments.py:219-233), so there is no filter stage here."""
 
     def __init__(self, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
-                 ctas: Optional[int] = None, two_launch_step: bool = False):
-        """two_launch_step: run every SGD step as `ddrl_graphnet_train_step` (warp-per-row forward + loss + backward to
-        the layer inputs, then the weight gradients) instead of forward + ppo_loss_grad + row-per-CTA backward.  Opt-in:
-        written after round 1's GPU budget was spent, not yet timed or parity-run on a GPU."""
+                 ctas: Optional[int] = None, two_launch_step: bool = False, step: Optional[str] = None):
+        """step: "tc" (default) = ONE persistent launch per epoch, `ddrl_graphnet_train_step_tc`: FMA/MUFU hyper-encoder,
+        tcgen05 MPNN / head / weight-gradient GEMMs, fused gradient reduce + in-kernel NVLink all-reduce + clip + Adam;
+        "three-kernel" = forward + ppo_loss_grad + row-per-CTA backward + reduce + Adam (FP32, 1e-5 path, A/B reference);
+        "two-launch" (or two_launch_step=True) = `ddrl_graphnet_train_step` (measured slower than three-kernel)."""
         super().__init__(1, K.graphnet_num_params(2 * A), cfg, device, theta)
         self.A = A
-        self.two_launch_step = two_launch_step
+        self.step_kind = step or ("two-launch" if two_launch_step else os.environ.get("DDRL_GN_STEP", "tc"))
+        if self.step_kind not in ("tc", "three-kernel", "two-launch"):
+            raise DDRLError(f"GraphNetLearner: unknown step kind {self.step_kind!r}")
+        self.two_launch_step = self.step_kind == "two-launch"
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.ctas = ctas or max(1, self.sms // 2)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._tc = None
+        self._peers = None
 
     def forward(self, node_idx, state, adj):
         return K.graphnet_forward(self.theta.reshape(-1), node_idx, state, adj, self.A)
@@ -541,11 +548,15 @@ class GraphNetLearner(_LearnerBase):
         if shuffle is not None:
             sl = shuffle.long()
             cols = {k: v[sl].contiguous() for k, v in cols.items()}
-        MB = min(cfg.sgd_minibatch_size // self.world if self.world > 1 else cfg.sgd_minibatch_size, R)
+        MB = min(local_minibatch(cfg.sgd_minibatch_size, self.world), R)
+        if MB < 1:
+            raise DDRLError("sgd_minibatch_size smaller than the number of ranks")
         E, nb = perms.shape
         if nb != max(1, R // MB):
             raise DDRLError(f"perms has {nb} minibatches per epoch, expected {max(1, R // MB)}")
         hyper = self._hyper(MB * self.world)
+        if self.step_kind == "tc":
+            return self._sgd_phase_tc(cols, perms, R, MB, E, nb, hyper)
         G = min(self.ctas, MB)
         LG = max(1, min(64, (MB + 255) // 256))
         dlogits = torch.empty(MB, 2 * A, dtype=f32, device=dev)
@@ -584,6 +595,58 @@ class GraphNetLearner(_LearnerBase):
         stats = finalize_stats(last.cpu().numpy(), self.kl_coeff_host, cfg, MB * self.world)
         self._update_kl(stats)
         return stats
+
+
+def _graphnet_sgd_phase_tc(self, cols, perms, R: int, MB: int, E: int, nb: int, hyper) -> List[Dict[str, float]]:
+    """E persistent launches of `ddrl_graphnet_train_step_tc` (nb optimizer steps each, fused tail) + stats + KL update."""
+    cfg, dev, A = self.cfg, self.device, self.A
+    steps = E * nb
+    Gn = max(1, min(self.ctas, self.sms // 2))
+    key = (steps, Gn)
+    if self._tc is None or self._tc["key"] != key:
+        self._tc = {"key": key,
+                    "mb_perm": torch.empty(steps, dtype=torch.int32, device=dev),
+                    "grad_part": torch.empty(Gn, K.part_stride(self.NP), dtype=torch.float32, device=dev),
+                    "stat_part": torch.zeros(2 * Gn, K.NSTAT, dtype=torch.float64, device=dev),
+                    "step_stats": torch.zeros(steps, 1, K.NSTAT, dtype=torch.float64, device=dev),
+                    "tail_bar": torch.zeros(8, dtype=torch.int32, device=dev),
+                    "tail_sq": torch.zeros(1, 2 * Gn, 32, dtype=torch.float32, device=dev)}
+    w = self._tc
+    w["mb_perm"].copy_(perms.reshape(steps))
+    self.step_ctr.zero_()
+    self.status.zero_()
+    tail = K.make_sgd_tail(self.theta, self.m, self.v, self.beta_pow, self.grad, w["tail_bar"], w["tail_sq"], cfg.lr, cfg.beta1,
+                           cfg.beta2, cfg.adam_eps, cfg.grad_clip, self.gnorm, step_stats=w["step_stats"], step_ctr=self.step_ctr,
+                           status=self.status)
+    tail.nsteps = nb
+    if self.world > 1:
+        pkey = (1, self.NP, 2 * Gn)
+        if self._peers is None or self._peers.key != pkey:
+            from .peer import PeerExchange
+            if self._peers is not None:
+                self._peers.close()
+            self._peers = PeerExchange(self.dist, self.world, self.rank, 1, self.NP, 2 * Gn, dev)
+        self._peers.fill(tail)
+    th = self.theta.reshape(-1)
+    for _ in range(E):
+        K.graphnet_train_step_tc(th, cols["idx"], cols["st"], cols["adj"], cols["act"], cols["logits"], cols["logp"], cols["value"],
+                                 cols["adv"], cols["vtarg"], A, MB, w["mb_perm"], self.step_ctr, self.kl_coeff, hyper, Gn,
+                                 w["grad_part"], w["stat_part"], self.status, tail)
+    last = w["step_stats"][steps - nb:].clone()
+    if self.world > 1:
+        self.dist.all_reduce(last)
+    stats = finalize_stats(last.cpu().numpy(), self.kl_coeff_host, cfg, MB * self.world)
+    code = int(self.status.item())
+    if code:
+        what = [n for bit, n in ((1, "MMA completion timed out"), (8, "dl overflow"), (16, "dy overflow"),
+                                 (64, "fused-tail barrier / peer wait timed out")) if code & bit]
+        raise DDRLError("GraphNet SGD step failed (" + ", ".join(what) + ")" +
+                        (" — fp16 split range exceeded: use step='three-kernel' for this workload" if code & 24 else ""))
+    self._update_kl(stats)
+    return stats
+
+
+GraphNetLearner._sgd_phase_tc = _graphnet_sgd_phase_tc
 
 
 def _lib_backward(th, idx, st, adj, dlogits, dvalue, B, A, G, gpart):

@@ -317,6 +317,27 @@ int ddrl_graphnet_train_step(const float* theta, const int32_t* node_idx, const 
                              const float* kl_coeff, const ddrl_ppo_hyper* hyper, int ctas, void* ws,
                              float* grad_part, double* stat_part, void* stream);
 
+/* GraphNet SGD steps on tensor cores (csrc/graphnet_tc.cu): ONE persistent kernel per launch runs, for every optimizer step,
+ * forward + PPOLoss + backward of the actor / critic wrapper and (with `tail`) the fused gradient reduce + [NVLink all-reduce]
+ * + clip + TF1 Adam.  The hyper-network leg encoder (1216 tanh per (row, node) pair; not a contraction) runs on the FMA + MUFU
+ * pipes with thread-owned columns; the MPNN (msg_transform / node_update), the linear head, their transposes and the
+ * K = rows weight-gradient GEMMs run on tcgen05 with fp16 hi/lo split operands (3 products, FP32 accumulation in TMEM).
+ *   batch arrays as ddrl_graphnet_train_step but for ALL R rows; step k of the launch trains rows
+ *   [mb * MB, mb * MB + MB) with mb = mb_perm[*step_ctr + k] (mb_perm NULL: mb = step);
+ *   grid = 2 x ctas_per_net CTAs (all co-resident: 2 * ctas_per_net <= #SMs);
+ *   grad_part [ctas_per_net][NPs] (row i: actor half from actor CTA i, critic half from critic CTA i; reduce with
+ *   ddrl_grad_reduce(P = 1, G = ctas_per_net) when tail == NULL); stat_part [2 * ctas_per_net][DDRL_NSTAT] float64,
+ *   ZERO-INITIALISED by the caller (rows >= ctas_per_net are never written);
+ *   tail: ddrl_sgd_tail for P = 1, NP = ddrl_graphnet_num_params(2A), 2 * ctas_per_net CTAs (sq_ws / exchange buffers sized
+ *   for that CTA count), fcnet_img / fcnet_tc_img / ll_ws NULL; tail->nsteps consecutive steps per launch;
+ *   status: device int or NULL (1 MMA wait timed out, 8 / 16 fp16 range of the loss gradients exceeded, 64 tail wait). */
+int ddrl_graphnet_train_step_tc(const float* theta, const int32_t* node_idx, const float* state, const float* adj,
+                                const float* actions, const float* old_logits, const float* old_logp,
+                                const float* vf_preds, const float* adv, const float* vtarg, int64_t R, int A, int MB,
+                                const int32_t* mb_perm, const int32_t* step_ctr, const float* kl_coeff,
+                                const ddrl_ppo_hyper* hyper, int ctas_per_net, float* grad_part, double* stat_part,
+                                int* status, const ddrl_sgd_tail* tail, void* stream);
+
 /* GCN layer (models/gcn.py:7-37, graph_ops.adj_norm models/graph_ops.py:13-21):
  *   y = act((D^-1 A) X W + b), X [B][4][F], A [B][4][4], W [F][U], b [U] or NULL, act: 0 none 1 tanh */
 int ddrl_gcn_forward(const float* x, const float* adj, const float* W, const float* b, int64_t B,

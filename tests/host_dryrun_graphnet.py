@@ -15,6 +15,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle.ddrl_oracle as O  # noqa: E402
 
+os.environ["DDRL_GN_STEP"] = "three-kernel"      # the orchestration checked here is the kernel-per-stage path (mocked below)
+
 _dev = torch.device
 torch.device = lambda *a, **k: _dev("cpu")
 torch.cuda.is_available = lambda: True
