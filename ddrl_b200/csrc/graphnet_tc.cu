@@ -103,6 +103,27 @@ __device__ __forceinline__ float gnt_rexp(float pre_scaled) {
     return r;
 }
 
+// Packed FP32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: one issue slot for two FP32 operations — the encoder is issue bound).
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ float2 f2b(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 gnt_rexp2(float2 pre_scaled) {      // r = 1 / (2^pre' + 1), both halves
+    float2 t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(pre_scaled.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(pre_scaled.y));
+    t = __fadd2_rn(t, f2b(1.f));
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(t.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(t.y));
+    return r;
+}
+// pre' of a column pair: b + e . W   (e broadcast to both halves)
+__device__ __forceinline__ float2 gnt_pre2(const float4& e, const float2 (&W)[4], float2 b) {
+    float2 q = __ffma2_rn(f2b(e.x), W[0], b);
+    q = __ffma2_rn(f2b(e.y), W[1], q);
+    q = __ffma2_rn(f2b(e.z), W[2], q);
+    return __ffma2_rn(f2b(e.w), W[3], q);
+}
+
 __device__ __forceinline__ float gnt_tanh(float x) {      // same as graphnet.cu: ex2 + rcp, absolute error <= 2.4e-7
     float t, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.885390081777927f));
@@ -176,6 +197,23 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
         umma::fence_after_sync();
     };
 
+    // pull the batch rows [r0, r0 + n) (state, adjacency, node index, loss inputs) into L2 ahead of their tile: the batch is
+    // larger than L2, so the staging loads of a tile would otherwise pay the full HBM latency on the critical path
+    auto prefetch_rows = [&](int64_t r0, int n) {
+        if (n <= 0) return;
+        const char* base = reinterpret_cast<const char*>(a.state + r0 * GT_N * GT_S);
+        const int lines = (n * GT_N * GT_S * 4 + 127) >> 7;
+        for (int i = tid; i < lines; i += GT_NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 128 * i));
+        const char* ab = reinterpret_cast<const char*>(a.adj + r0 * GT_N * GT_N);
+        for (int i = tid; i < ((n * GT_N * GT_N * 4 + 127) >> 7); i += GT_NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(ab + 128 * i));
+        if (tid < 8) {
+            const void* ptrs[8] = {a.node_idx + r0, a.old_logp + r0, a.vf_preds + r0, a.adv + r0, a.vtarg + r0, a.actions + r0 * a.A,
+                                   a.old_logits + r0 * 2 * a.A, a.old_logits + r0 * 2 * a.A + 32};
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptrs[tid]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ptrs[tid]) + 128));
+        }
+    };
+
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
         if (s > 0) {      // every CTA must have written its Adam slice of the previous step
@@ -193,6 +231,11 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
             for (int e = 0; e < GT_E; ++e) We[k][e] = v ? kTanhIn * __ldcg(th + o.We + e * GT_F * GT_H + f * GT_H + eh) : 0.f;
             be[k] = v ? kTanhIn * __ldcg(th + o.be + f * GT_H + eh) : 0.f;
         }
+        // packed column pairs of this lane: (k0, k1), (k2, k3) and k4 duplicated (its two halves serve the two pairs of an iteration)
+        float2 W01[GT_E], W23[GT_E], W4[GT_E];
+#pragma unroll
+        for (int e = 0; e < GT_E; ++e) { W01[e] = f2(We[0][e], We[1][e]); W23[e] = f2(We[2][e], We[3][e]); W4[e] = f2b(We[4][e]); }
+        const float2 b01 = f2(be[0], be[1]), b23 = f2(be[2], be[3]), b4 = f2b(be[4]);
         for (int i = tid; i < 2 * GT_H * GT_H; i += GT_NT) {
             const int mtx = i >> 12, j = i & 4095, r = j >> 6, c = j & 63;      // W[r = in][c = out], chunked along c
             const float w = __ldcg(th + (mtx ? o.Wm : o.Wu) + j) * TC_SW;
@@ -219,13 +262,10 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
         const int rpc = (((a.MB + Gn - 1) / Gn) + 7) & ~7;
         const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
 
-        float gWe[GT_KC][GT_E], gbe[GT_KC];
+        // gradient accumulators of the packed columns: [e] = dW_e row e, [4] = db_e; g4: halves = the two pairs of an iteration
+        float2 g01[GT_E + 1], g23[GT_E + 1], g4[GT_E + 1];
 #pragma unroll
-        for (int k = 0; k < GT_KC; ++k) {
-            gbe[k] = 0.f;
-#pragma unroll
-            for (int e = 0; e < GT_E; ++e) gWe[k][e] = 0.f;
-        }
+        for (int e = 0; e <= GT_E; ++e) { g01[e] = f2b(0.f); g23[e] = f2b(0.f); g4[e] = f2b(0.f); }
         double st[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) st[i] = 0.0;
@@ -238,6 +278,7 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
 #pragma unroll 1
         for (int64_t row0 = cr0; row0 < cr1; row0 += GT_ROWS) {
             const int nrows = (int)min((int64_t)GT_ROWS, cr1 - row0);
+            prefetch_rows(row0 + GT_ROWS, (int)min((int64_t)GT_ROWS, cr1 - row0 - GT_ROWS));      // next tile -> L2
             // ---- pairs of this tile ---------------------------------------------------------------------------------------
             if (tid < GT_ROWS) {
                 int need = 0, snd = 0, idx = 0;
@@ -276,17 +317,24 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
             }
             __syncthreads();
             const int npairs = reinterpret_cast<const int*>(sred)[0];
-            for (int i = tid; i < npairs * GT_S; i += GT_NT) {      // stage e [4] and leg [19 + zero pad] of every pair
-                const int pr = i / GT_S, j = i - pr * GT_S;
-                const int code = pinfo[pr];
-                const float v = a.state[((row0 + (code & 255)) * GT_N + (code >> 8)) * GT_S + j];
-                if (j < GT_F) sLeg[pr * GT_LEG + (j / GT_KC) * 8 + (j % GT_KC)] = v;
-                else sE[pr * GT_E + (j - GT_F)] = v;
+            // stage e [4] and leg [19] of every pair: asynchronous 4-byte copies, all in flight at once (32 slots per pair: slot
+            // t < 23 copies float t of the node's state vector)
+            for (int i = tid; i < npairs * 32; i += GT_NT) {
+                const int pr = i >> 5, j = i & 31;
+                if (j < GT_S) {
+                    const int code = pinfo[pr];
+                    const float* src = a.state + ((row0 + (code & 255)) * GT_N + (code >> 8)) * GT_S + j;
+                    float* dst = j < GT_F ? sLeg + pr * GT_LEG + (j / GT_KC) * 8 + (j % GT_KC) : sE + pr * GT_E + (j - GT_F);
+                    tc_cp4(dst, src);
+                } else if (j == GT_S) {
+                    sLeg[pr * GT_LEG + 3 * 8 + 4] = 0.f;      // f = 19 does not exist
+                }
             }
-            for (int i = tid; i < npairs; i += GT_NT) sLeg[i * GT_LEG + 3 * 8 + 4] = 0.f;      // f = 19 does not exist
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();
 
-            // ---- encoder forward: x of every pair -> XQ (two pairs per iteration: 10 independent tanh chains per lane) -----
+            // ---- encoder forward: x of every pair -> XQ (two pairs per iteration, packed FP32 pairs) ------------------------
 #pragma unroll 1
             for (int i = pset; i < npairs; i += 4) {
                 const int i2 = min(i + 2, npairs - 1);
@@ -294,19 +342,21 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
                 const float4 eb = *reinterpret_cast<const float4*>(sE + i2 * GT_E);
                 const float4 la = *reinterpret_cast<const float4*>(sLeg + i * GT_LEG + 8 * fq);
                 const float4 lb = *reinterpret_cast<const float4*>(sLeg + i2 * GT_LEG + 8 * fq);
-                const float la4 = sLeg[i * GT_LEG + 8 * fq + 4], lb4 = sLeg[i2 * GT_LEG + 8 * fq + 4];
-                const float lga[GT_KC] = {la.x, la.y, la.z, la.w, la4}, lgb[GT_KC] = {lb.x, lb.y, lb.z, lb.w, lb4};
-                float pa = 0.f, pb = 0.f;
-#pragma unroll
-                for (int k = 0; k < GT_KC; ++k) {
-                    float qa = be[k], qb = be[k];
-                    qa = fmaf(ea.x, We[k][0], qa); qb = fmaf(eb.x, We[k][0], qb);
-                    qa = fmaf(ea.y, We[k][1], qa); qb = fmaf(eb.y, We[k][1], qb);
-                    qa = fmaf(ea.z, We[k][2], qa); qb = fmaf(eb.z, We[k][2], qb);
-                    qa = fmaf(ea.w, We[k][3], qa); qb = fmaf(eb.w, We[k][3], qb);
-                    pa = fmaf(lga[k], fmaf(-2.f, gnt_rexp(qa), 1.f), pa);
-                    pb = fmaf(lgb[k], fmaf(-2.f, gnt_rexp(qb), 1.f), pb);
-                }
+                const float2 l4 = f2(sLeg[i * GT_LEG + 8 * fq + 4], sLeg[i2 * GT_LEG + 8 * fq + 4]);
+                const float2 ra01 = gnt_rexp2(gnt_pre2(ea, W01, b01)), ra23 = gnt_rexp2(gnt_pre2(ea, W23, b23));
+                const float2 rb01 = gnt_rexp2(gnt_pre2(eb, W01, b01)), rb23 = gnt_rexp2(gnt_pre2(eb, W23, b23));
+                float2 q4 = __ffma2_rn(f2(ea.x, eb.x), W4[0], b4);
+                q4 = __ffma2_rn(f2(ea.y, eb.y), W4[1], q4);
+                q4 = __ffma2_rn(f2(ea.z, eb.z), W4[2], q4);
+                q4 = __ffma2_rn(f2(ea.w, eb.w), W4[3], q4);
+                const float2 r4 = gnt_rexp2(q4);
+                const float2 m2 = f2b(-2.f), one = f2b(1.f);
+                float2 sa = __fmul2_rn(f2(la.x, la.y), __ffma2_rn(m2, ra01, one));
+                sa = __ffma2_rn(f2(la.z, la.w), __ffma2_rn(m2, ra23, one), sa);
+                float2 sb = __fmul2_rn(f2(lb.x, lb.y), __ffma2_rn(m2, rb01, one));
+                sb = __ffma2_rn(f2(lb.z, lb.w), __ffma2_rn(m2, rb23, one), sb);
+                const float2 s4 = __fmul2_rn(l4, __ffma2_rn(m2, r4, one));
+                float pa = (sa.x + sa.y) + s4.x, pb = (sb.x + sb.y) + s4.y;
                 pa += __shfl_xor_sync(0xffffffffu, pa, 8);
                 pb += __shfl_xor_sync(0xffffffffu, pb, 8);
                 pa += __shfl_xor_sync(0xffffffffu, pa, 16);
@@ -466,14 +516,20 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
             hand_off();
             // ---- dXc = dYpre W_upd^T, dXmean = dYpre W_msg^T;  gW_upd (+)= Xc^T dYpre, gW_msg (+)= Xmean^T dYpre -----------
             if (warp == 0) {
-                tc_gemm_u(tm_u + GC_DXC, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS, false, sb_u + S.Wu[0], sb_u + S.Wu[1], GT_H, false,
-                          64, 64, 4, false, 3);
-                tc_gemm_u(tm_u + GC_DXM, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS, false, sb_u + S.Wm[0], sb_u + S.Wm[1], GT_H, false,
-                          64, 64, 4, false, 3);
-                tc_gemm_u(tm_u + GC_GWU, sb_u + S.Xc[0], sb_u + S.Xc[1], GT_ROWS, true, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS, true,
-                          64, 64, 4, !first, 3);
-                tc_gemm_u(tm_u + GC_GWM, sb_u + S.Xm[0], sb_u + S.Xm[1], GT_ROWS, true, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS, true,
-                          64, 64, 4, !first, 3);
+                // four independent accumulators: issue product by product round robin, so consecutive MMAs never wait for each
+                // other's accumulate (a dependent chain runs at ~100 cycles per MMA, independent ones at ~45)
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                    const int pm = 1 << pr;
+                    tc_gemm_mask_u(tm_u + GC_DXC, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS, false, sb_u + S.Wu[0], sb_u + S.Wu[1], GT_H,
+                                   false, 64, 64, 4, pr > 0, pm);
+                    tc_gemm_mask_u(tm_u + GC_DXM, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS, false, sb_u + S.Wm[0], sb_u + S.Wm[1], GT_H,
+                                   false, 64, 64, 4, pr > 0, pm);
+                    tc_gemm_mask_u(tm_u + GC_GWU, sb_u + S.Xc[0], sb_u + S.Xc[1], GT_ROWS, true, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS,
+                                   true, 64, 64, 4, pr > 0 || !first, pm);
+                    tc_gemm_mask_u(tm_u + GC_GWM, sb_u + S.Xm[0], sb_u + S.Xm[1], GT_ROWS, true, sb_u + S.Y[0], sb_u + S.Y[1], GT_ROWS,
+                                   true, 64, 64, 4, pr > 0 || !first, pm);
+                }
                 umma::mma_commit_elect(mbar);
             }
             mma_wait();
@@ -513,24 +569,38 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
                 const float4 eb = *reinterpret_cast<const float4*>(sE + i2 * GT_E);
                 const float4 la = *reinterpret_cast<const float4*>(sLeg + i * GT_LEG + 8 * fq);
                 const float4 lb = *reinterpret_cast<const float4*>(sLeg + i2 * GT_LEG + 8 * fq);
-                const float la4 = sLeg[i * GT_LEG + 8 * fq + 4], lb4 = sLeg[i2 * GT_LEG + 8 * fq + 4];
+                const float2 l4 = f2(sLeg[i * GT_LEG + 8 * fq + 4], sLeg[i2 * GT_LEG + 8 * fq + 4]);
                 const float da = 4.f * XQ[i * GT_XS + eh], db = (i + 2 < npairs) ? 4.f * XQ[i2 * GT_XS + eh] : 0.f;
-                const float lga[GT_KC] = {la.x, la.y, la.z, la.w, la4}, lgb[GT_KC] = {lb.x, lb.y, lb.z, lb.w, lb4};
-#pragma unroll
-                for (int k = 0; k < GT_KC; ++k) {
-                    float qa = be[k], qb = be[k];
-                    qa = fmaf(ea.x, We[k][0], qa); qb = fmaf(eb.x, We[k][0], qb);
-                    qa = fmaf(ea.y, We[k][1], qa); qb = fmaf(eb.y, We[k][1], qb);
-                    qa = fmaf(ea.z, We[k][2], qa); qb = fmaf(eb.z, We[k][2], qb);
-                    qa = fmaf(ea.w, We[k][3], qa); qb = fmaf(eb.w, We[k][3], qb);
-                    const float ra = gnt_rexp(qa), rb = gnt_rexp(qb);
-                    const float wa = (da * lga[k]) * (ra * (1.f - ra)), wb = (db * lgb[k]) * (rb * (1.f - rb));   // dx_pre leg (1 - w^2)
-                    gbe[k] += wa + wb;
-                    gWe[k][0] = fmaf(ea.x, wa, fmaf(eb.x, wb, gWe[k][0]));
-                    gWe[k][1] = fmaf(ea.y, wa, fmaf(eb.y, wb, gWe[k][1]));
-                    gWe[k][2] = fmaf(ea.z, wa, fmaf(eb.z, wb, gWe[k][2]));
-                    gWe[k][3] = fmaf(ea.w, wa, fmaf(eb.w, wb, gWe[k][3]));
-                }
+                // dw = dx_pre leg (1 - w^2) = (4 dx_pre leg) (r - r^2)
+                float2 r = gnt_rexp2(gnt_pre2(ea, W01, b01));
+                float2 dw = __fmul2_rn(__fmul2_rn(f2b(da), f2(la.x, la.y)), __ffma2_rn(f2(-r.x, -r.y), r, r));
+                g01[4] = __fadd2_rn(g01[4], dw);
+                g01[0] = __ffma2_rn(f2b(ea.x), dw, g01[0]); g01[1] = __ffma2_rn(f2b(ea.y), dw, g01[1]);
+                g01[2] = __ffma2_rn(f2b(ea.z), dw, g01[2]); g01[3] = __ffma2_rn(f2b(ea.w), dw, g01[3]);
+                r = gnt_rexp2(gnt_pre2(eb, W01, b01));
+                dw = __fmul2_rn(__fmul2_rn(f2b(db), f2(lb.x, lb.y)), __ffma2_rn(f2(-r.x, -r.y), r, r));
+                g01[4] = __fadd2_rn(g01[4], dw);
+                g01[0] = __ffma2_rn(f2b(eb.x), dw, g01[0]); g01[1] = __ffma2_rn(f2b(eb.y), dw, g01[1]);
+                g01[2] = __ffma2_rn(f2b(eb.z), dw, g01[2]); g01[3] = __ffma2_rn(f2b(eb.w), dw, g01[3]);
+                r = gnt_rexp2(gnt_pre2(ea, W23, b23));
+                dw = __fmul2_rn(__fmul2_rn(f2b(da), f2(la.z, la.w)), __ffma2_rn(f2(-r.x, -r.y), r, r));
+                g23[4] = __fadd2_rn(g23[4], dw);
+                g23[0] = __ffma2_rn(f2b(ea.x), dw, g23[0]); g23[1] = __ffma2_rn(f2b(ea.y), dw, g23[1]);
+                g23[2] = __ffma2_rn(f2b(ea.z), dw, g23[2]); g23[3] = __ffma2_rn(f2b(ea.w), dw, g23[3]);
+                r = gnt_rexp2(gnt_pre2(eb, W23, b23));
+                dw = __fmul2_rn(__fmul2_rn(f2b(db), f2(lb.z, lb.w)), __ffma2_rn(f2(-r.x, -r.y), r, r));
+                g23[4] = __fadd2_rn(g23[4], dw);
+                g23[0] = __ffma2_rn(f2b(eb.x), dw, g23[0]); g23[1] = __ffma2_rn(f2b(eb.y), dw, g23[1]);
+                g23[2] = __ffma2_rn(f2b(eb.z), dw, g23[2]); g23[3] = __ffma2_rn(f2b(eb.w), dw, g23[3]);
+                float2 q4 = __ffma2_rn(f2(ea.x, eb.x), W4[0], b4);
+                q4 = __ffma2_rn(f2(ea.y, eb.y), W4[1], q4);
+                q4 = __ffma2_rn(f2(ea.z, eb.z), W4[2], q4);
+                q4 = __ffma2_rn(f2(ea.w, eb.w), W4[3], q4);
+                r = gnt_rexp2(q4);
+                dw = __fmul2_rn(__fmul2_rn(f2(da, db), l4), __ffma2_rn(f2(-r.x, -r.y), r, r));
+                g4[4] = __fadd2_rn(g4[4], dw);
+                g4[0] = __ffma2_rn(f2(ea.x, eb.x), dw, g4[0]); g4[1] = __ffma2_rn(f2(ea.y, eb.y), dw, g4[1]);
+                g4[2] = __ffma2_rn(f2(ea.z, eb.z), dw, g4[2]); g4[3] = __ffma2_rn(f2(ea.w, eb.w), dw, g4[3]);
             }
             first = false;
             __syncthreads();
@@ -540,6 +610,12 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
         const bool any = cr1 > cr0;
         {   // encoder gradients: add the two pair sets (fixed order), thread-owned columns -> flat order
             float* scr = XQ;      // [8 hgrp][32 lanes][25]
+            float gWe[GT_KC][GT_E], gbe[GT_KC];      // unpack: column k, row e
+#pragma unroll
+            for (int e = 0; e < GT_E; ++e) {
+                gWe[0][e] = g01[e].x; gWe[1][e] = g01[e].y; gWe[2][e] = g23[e].x; gWe[3][e] = g23[e].y; gWe[4][e] = g4[e].x + g4[e].y;
+            }
+            gbe[0] = g01[4].x; gbe[1] = g01[4].y; gbe[2] = g23[4].x; gbe[3] = g23[4].y; gbe[4] = g4[4].x + g4[4].y;
             if (pset == 1) {
                 float* d = scr + (hgrp * 32 + lane) * 25;
 #pragma unroll
@@ -618,6 +694,12 @@ __global__ void __launch_bounds__(GT_NT, 1) graphnet_train_tc_kernel(const __gri
                 const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
                 if (act_slot == (net == 0)) a.stat_part[(int64_t)bx * DDRL_NSTAT + tid] = sum4(idx);
             }
+        }
+        if (s + 1 < nsteps) {      // the next step's first tile does not depend on the weights: pull it into L2 behind the tail
+            const int mbn = a.mb_perm ? a.mb_perm[step + 1] : step + 1;
+            const int64_t n0 = (int64_t)mbn * a.MB, n1 = min(n0 + a.MB, a.R);
+            const int64_t c0n = min(n0 + (int64_t)bx * rpc, n1), c1n = min(c0n + rpc, n1);
+            prefetch_rows(c0n, (int)min((int64_t)GT_ROWS, c1n - c0n));
         }
         if (has_tail) {
             ts.round = s + 1;
