@@ -37,6 +37,7 @@ umma_selftest_kernel(const float* __restrict__ A, int ra, int ca, const float* _
     }
     const uint32_t ncols = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     if (warp == 0) umma::tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); }
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();

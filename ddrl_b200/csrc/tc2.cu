@@ -252,9 +252,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     double st[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) st[i] = 0.0;
-    float gbh[A2];   // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0]
+    // head bias gradients: policy threads sum_r dl[r][o]; value threads use gbh[0].  Wide heads (A = 8) keep the sums per
+    // warp in shared memory instead (16 more live registers made that instantiation spill)
+    constexpr bool GBH_SMEM = A > 4;
+    float gbh[GBH_SMEM ? 1 : A2];
 #pragma unroll
-    for (int i = 0; i < A2; ++i) gbh[i] = 0.f;
+    for (int i = 0; i < (GBH_SMEM ? 1 : A2); ++i) gbh[i] = 0.f;
+    if (GBH_SMEM && warp < 8 && lane < 16) reinterpret_cast<double*>(sm + S.red)[warp * 24 + 8 + lane] = 0.0;   // read behind later barriers
     const int64_t mb1 = min(mb0 + a.MB, a.R);
     const int rpc = (((a.MB + G - 1) / G) + 7) & ~7;
     const int64_t cr0 = min(mb0 + (int64_t)bx * rpc, mb1), cr1 = min(cr0 + rpc, mb1);
@@ -608,14 +612,24 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                     ppo_row_policy(lg, A, pa + row * A, po + row * A2, ps[row], ps[2 * TC_ROWS + row], klc,
                                    a.hp.clip_param, a.hp.entropy_coeff, 1.f, dl, s);
 #pragma unroll
-                    for (int oo = 0; oo < A2; ++oo) gbh[oo] += dl[oo];
+                    for (int oo = 0; oo < (GBH_SMEM ? 0 : A2); ++oo) gbh[oo] += dl[oo];
                     st[0] += s[0]; st[1] += s[1]; st[2] += s[3];
                 } else {
                     const float val = fmaf(out[0], 1.f / (TC_SH * TC_SW), sbvo[0]);
                     dl[0] = ppo_row_value(val, ps[TC_ROWS + row], ps[3 * TC_ROWS + row], a.hp.vf_clip_param,
                                           a.hp.vf_loss_coeff, 1.f, s);
-                    gbh[0] += dl[0];
+                    if (!GBH_SMEM) gbh[0] += dl[0];
                     st[0] += s[2]; st[1] += s[4]; st[2] += s[5]; st[3] += s[6]; st[4] += s[7];
+                }
+            }
+            if constexpr (GBH_SMEM) {      // dl is zero for rows beyond nrows: whole-warp sums, one writer per warp
+                double* redg = reinterpret_cast<double*>(sm + S.red);
+#pragma unroll
+                for (int oo = 0; oo < A2; ++oo) {
+                    if (b == 0 || oo == 0) {
+                        const float sx = warp_sum(dl[oo]);
+                        if (lane == 0) redg[warp * 24 + 8 + oo] += (double)sx;
+                    }
                 }
             }
             if (first) {   // per-branch gradient scale of this CTA: power of two with max|dl| * scale ~ TC_GTARGET
@@ -705,8 +719,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][24]
 #pragma unroll
         for (int i = 0; i < A2; ++i) {
-            const float sx = warp_sum(gbh[i]);
-            if (lane == 0) redd[warp * 24 + 8 + i] = (double)sx;
+            if constexpr (!GBH_SMEM) {
+                const float sx = warp_sum(gbh[i]);
+                if (lane == 0) redd[warp * 24 + 8 + i] = (double)sx;
+            }
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
