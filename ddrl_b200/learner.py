@@ -275,10 +275,12 @@ class FCNetLearner(_LearnerBase):
                 K.gather_rows(b[nme], shuffle, b[nme + "_s"])
 
     def _prepare_cached(self, b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc):
-        """Single GPU: the ~20 short launches of the preparation phase are captured once per set of input buffers and
-        replayed (the kernels only see pointers; graphs are keyed by the input addresses, at most 8 are kept)."""
+        """The ~20 short launches of the preparation phase are captured once per set of input buffers and replayed (the
+        kernels only see pointers; graphs are keyed by the input addresses, at most 8 are kept).  At world > 1 the capture
+        includes the three NCCL collectives of the phase (filter partials, advantage moments); every rank captures and
+        replays in the same iteration, so the collectives stay matched."""
         args = (b, obs_flat, boot_obs, rewards, dones, eps_flat, shuffle, cols_per_env, update_filter, T, Cc)
-        if not self.use_graph or self.world > 1 or self._prep_graphs is None or not self._prep_warm:
+        if not self.use_graph or self._prep_graphs is None or not self._prep_warm:
             self._prep_warm = True           # first call runs eagerly (one-time function attributes, lazy allocations)
             return self._prepare(*args)
         if b.get("filt_ws") is None:
@@ -294,6 +296,8 @@ class FCNetLearner(_LearnerBase):
                 return self._prepare(*args)
             try:
                 torch.cuda.synchronize()
+                if self.world > 1:
+                    self.dist.barrier()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._prepare(*args)
