@@ -490,6 +490,28 @@ __global__ void leg_coupling_kernel(float* __restrict__ logits, const int32_t* _
     }
 }
 
+// Optional FCNet layouts (vf_share_layers / free_log_std, models/fcnet_glorot_uniform_init.py:30-36,85-113) on the two-branch
+// kernels: the kernels' parameter vector is an index-select of the model's variables (tied value-branch copies, constant
+// zeros), and the model gradient is the fixed-order sum of the (at most two) kernel-layout gradients of each variable.
+__global__ void param_expand_kernel(const float* __restrict__ theta_model, const int32_t* __restrict__ map, int NPm, int NPk,
+                                    float* __restrict__ theta_kernel) {
+    const int p = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NPk; i += gridDim.x * blockDim.x) {
+        const int j = map[i];
+        theta_kernel[(int64_t)p * NPk + i] = (j >= 0 && j < NPm) ? theta_model[(int64_t)p * NPm + j] : 0.f;
+    }
+}
+__global__ void grad_tie_kernel(const float* __restrict__ grad_kernel, const int32_t* __restrict__ inv, int NPm, int NPk,
+                                float* __restrict__ grad_model) {
+    const int p = blockIdx.y;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < NPm; j += gridDim.x * blockDim.x) {
+        const int i0 = inv[2 * j], i1 = inv[2 * j + 1];
+        float g = i0 >= 0 ? grad_kernel[(int64_t)p * NPk + i0] : 0.f;
+        if (i1 >= 0) g += grad_kernel[(int64_t)p * NPk + i1];
+        grad_model[(int64_t)p * NPm + j] = g;
+    }
+}
+
 // LegCoupling backward: dlogits_pre = dout * coeff (in place on dout) and dcoupling[n][j] = sum over rows b with
 // node_id[b] == n of dout[b][j] * logits_pre[b][j], j < 2 (the trainable tf.Variable of the reference layer).
 // ONE block, fixed-order tree reduction over float64 per-thread sums: bit-reproducible (the op is tiny next to the MLP).
@@ -712,6 +734,21 @@ extern "C" int ddrl_leg_coupling(float* logits, const int32_t* node_id, const fl
     const int nb = (int)std::min<int64_t>(1024, (B * W + 255) / 256);
     leg_coupling_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(logits, node_id, coupling, B, W);
     DDRL_CHECK_LAUNCH("leg_coupling");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_param_expand(const float* theta_model, const int32_t* map, int P, int NPm, int NPk, float* theta_kernel,
+                                 void* stream) {
+    DDRL_REQUIRE(theta_model && map && theta_kernel && P >= 1 && NPm >= 1 && NPk >= 1, DDRL_E_BADARG, "param_expand: bad arguments");
+    param_expand_kernel<<<dim3((NPk + 255) / 256, P), 256, 0, (cudaStream_t)stream>>>(theta_model, map, NPm, NPk, theta_kernel);
+    DDRL_CHECK_LAUNCH("param_expand");
+    return DDRL_OK;
+}
+
+extern "C" int ddrl_grad_tie(const float* grad_kernel, const int32_t* inv, int P, int NPm, int NPk, float* grad_model, void* stream) {
+    DDRL_REQUIRE(grad_kernel && inv && grad_model && P >= 1 && NPm >= 1 && NPk >= 1, DDRL_E_BADARG, "grad_tie: bad arguments");
+    grad_tie_kernel<<<dim3((NPm + 255) / 256, P), 256, 0, (cudaStream_t)stream>>>(grad_kernel, inv, NPm, NPk, grad_model);
+    DDRL_CHECK_LAUNCH("grad_tie");
     return DDRL_OK;
 }
 

@@ -331,6 +331,24 @@ def leg_coupling_(logits, node_id, coupling):
     return logits
 
 
+def param_expand(theta_model, layout_map, theta_kernel):
+    """theta_kernel [P,NPk] = index-select of theta_model [P,NPm] through layout_map [NPk] i32 (>= NPm: constant zero)."""
+    P, NPm = theta_model.shape
+    NPk = theta_kernel.shape[1]
+    _lib.check(_lib.load().ddrl_param_expand(_p(theta_model, torch.float32, "theta_model"), _p(layout_map, torch.int32, "map"), P,
+                                             NPm, NPk, _p(theta_kernel, torch.float32, "theta_kernel"), _stream()), "param_expand")
+    return theta_kernel
+
+
+def grad_tie(grad_kernel, inverse_map, grad_model):
+    """grad_model [P,NPm] = sum over the (<= 2) kernel-layout copies of every model variable (inverse_map [NPm,2] i32)."""
+    P, NPk = grad_kernel.shape
+    NPm = grad_model.shape[1]
+    _lib.check(_lib.load().ddrl_grad_tie(_p(grad_kernel, torch.float32, "grad_kernel"), _p(inverse_map, torch.int32, "inv"), P,
+                                         NPm, NPk, _p(grad_model, torch.float32, "grad_model"), _stream()), "grad_tie")
+    return grad_model
+
+
 def leg_coupling_backward_(dout, logits_pre, node_id, coupling):
     """In place: dout [B,W] becomes the gradient w.r.t. the pre-coupling logits; returns dcoupling [4,2] (see
     ddrl_leg_coupling_backward)."""

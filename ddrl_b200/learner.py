@@ -110,10 +110,40 @@ class FCNetLearner(_LearnerBase):
 
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
                  use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True,
-                 persistent: bool = True, tc_forward: bool = True, ll_tail: bool = False):
+                 persistent: bool = True, tc_forward: bool = True, ll_tail: bool = False, vf_share_layers: bool = False,
+                 free_log_std: bool = False):
         """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
-                 "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes."""
+                 "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes.
+        vf_share_layers / free_log_std: the reference model's optional layouts (models/fcnet_glorot_uniform_init.py:30-36,
+        85-113).  `theta` is then [P, NPm] in the MODEL's variable order (`modelv2.fcnet_variant_shapes`); the kernels run on
+        its index-select (`self.theta`, tied value branch / constant zero columns), the gradients of tied copies are added
+        (`ddrl_grad_tie`) and clip + Adam act on the model variables (`self.theta_model`) — the kernel-per-stage step, since
+        the fused tail owns kernel-layout slices."""
+        self.variant = bool(vf_share_layers or free_log_std)
+        theta_model = None
+        if self.variant:
+            from .modelv2 import fcnet_layout_map, fcnet_variant_shapes
+            lmap = fcnet_layout_map(D, 2 * A, vf_share_layers, free_log_std)
+            NPm = int(sum(int(np.prod(shp)) for _, shp in fcnet_variant_shapes(D, 2 * A, vf_share_layers, free_log_std)))
+            if theta is None or tuple(theta.shape) != (P, NPm):
+                raise DDRLError(f"optional FCNet layout: theta must be [P={P}, {NPm}] in the model's variable order")
+            theta_model, theta = theta, None
+            fuse_tail, persistent = False, False
         super().__init__(P, K.fcnet_num_params(D, A), cfg, device, theta)
+        if self.variant:
+            dev_ = self.device
+            self.NPm = NPm
+            self.theta_model = theta_model.to(dev_, torch.float32).contiguous().clone()
+            self.m = torch.zeros_like(self.theta_model)
+            self.v = torch.zeros_like(self.theta_model)
+            self.grad_model = torch.zeros_like(self.theta_model)
+            self.layout_map = lmap.to(torch.int32).to(dev_)
+            inv = torch.full((NPm, 2), -1, dtype=torch.int32)
+            for i, j in enumerate(lmap.tolist()):
+                if j < NPm:
+                    inv[j, 0 if inv[j, 0] < 0 else 1] = i
+            self.inverse_map = inv.to(dev_)
+            K.param_expand(self.theta_model, self.layout_map, self.theta)
         if mode not in ("tc", "fp32"):
             raise DDRLError(f"mode must be 'tc' or 'fp32', got {mode!r}")
         self.mode = mode
@@ -226,6 +256,19 @@ class FCNetLearner(_LearnerBase):
         if tail is not None:
             return
         K.grad_reduce(b["grad_part"], b["stat_part"], self.P, G, self.NP, self.grad, b["step_stats"], self.step_ctr)
+        if self.variant:
+            # optional layouts: tie the gradients of the copies, clip + Adam on the MODEL's variables, re-expand, re-pack
+            c = self.cfg
+            K.grad_tie(self.grad, self.inverse_map, self.grad_model)
+            if self.world > 1:
+                self.dist.all_reduce(self.grad_model)
+            K.clip_adam(self.theta_model, self.m, self.v, self.beta_pow, self.grad_model, c.lr, c.beta1, c.beta2, c.adam_eps,
+                        c.grad_clip, self.sync_ws, self.gnorm, self.step_ctr, None, 0, 0)
+            K.param_expand(self.theta_model, self.layout_map, self.theta)
+            K.fcnet_pack(self.theta, self.D, self.A, self.img)
+            if self.tc_img is not None:
+                K.fcnet_tc_pack(self.theta, self.D, self.A, self.tc_img)
+            return
         if self.world > 1:
             self.dist.all_reduce(self.grad)
         self._adam()

@@ -379,6 +379,14 @@ int ddrl_leg_coupling(float* logits, const int32_t* node_id, const float* coupli
 int ddrl_leg_coupling_backward(float* dout, const float* logits_pre, const int32_t* node_id,
                                const float* coupling, int64_t B, int W, float* dcoupling, void* stream);
 
+/* Optional FCNet layouts (`vf_share_layers`, `free_log_std`; models/fcnet_glorot_uniform_init.py:30-36,85-113) on the two-branch
+ * kernels.  The kernels' parameter vector [NPk] is an index-select of the model's variables [NPm]:
+ *   ddrl_param_expand: theta_kernel[p][i] = map[i] in [0, NPm) ? theta_model[p][map[i]] : 0      (map [NPk] int32)
+ *   ddrl_grad_tie:     grad_model[p][j] = sum of grad_kernel[p][inv[j][k]], k = 0, 1 (inv [NPm][2] int32, -1 = none; fixed
+ *                      order) — the gradients of tied copies add up, gradients of constant entries are dropped. */
+int ddrl_param_expand(const float* theta_model, const int32_t* map, int P, int NPm, int NPk, float* theta_kernel, void* stream);
+int ddrl_grad_tie(const float* grad_kernel, const int32_t* inv, int P, int NPm, int NPk, float* grad_model, void* stream);
+
 /* Tensor-core variant of ddrl_ppo_train_step (PPO path only): every GEMM of the fused forward + loss + backward
  * runs on tcgen05 (kind::f16, FP32 accumulation in TMEM) with FP32 operands split into fp16 (hi, lo) pairs and
  * three products per GEMM, which keeps the 1e-5 parity bar.  Same batch arrays, minibatch selection, outputs

@@ -460,3 +460,55 @@ def test_graph_replayed_iterations_are_bit_identical_to_eager_ones():
     for x, y in zip(out[0][:5], out[1][:5]):
         assert torch.equal(x, y)
     assert out[0][5] == out[1][5]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("vf_share,free_std", [(True, False), (False, True), (True, True)])
+def test_learner_trains_the_optional_layouts_like_the_oracle(vf_share, free_std, mode):
+    """`vf_share_layers` / `free_log_std` (models/fcnet_glorot_uniform_init.py:30-36,85-113) in the fused learner: the
+    kernels run on the index-select of the model's variables, tied gradients are added, clip + Adam act on the model
+    variables.  2 epochs x 4 minibatches on postprocessed columns against the oracle's float64 trajectory of the SAME layout."""
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import FCNetLearner
+    O = _oracle()
+    P, D, A, R, E, NB = 2, 19, 2, 512, 2, 4
+    cfgd = dict(num_sgd_iter=E, sgd_minibatch_size=R // NB, entropy_coeff=0.01)
+    cfg, cfg_o = PPOConfig(**cfgd), O.PPOConfig(**cfgd)
+    g = torch.Generator().manual_seed(17)
+    th0 = torch.stack([O.fcnet_init(D, 2 * A, g, vf_share_layers=vf_share, free_log_std=free_std) for _ in range(P)])
+    th0 = th0 + 0.05 * torch.randn(th0.shape, generator=g)          # non-zero biases / log_std, larger heads
+    rng = np.random.default_rng(5)
+    obs = rng.standard_normal((P, R, D)).astype(np.float32)
+    old_logits = (0.3 * rng.standard_normal((P, R, 2 * A))).astype(np.float32)
+    actions = (old_logits[..., :A] + np.exp(old_logits[..., A:]) * rng.standard_normal((P, R, A))).astype(np.float32)
+    old_logp = np.stack([O.dg_logp(torch.from_numpy(old_logits[p]), torch.from_numpy(actions[p])).numpy() for p in range(P)]).astype(np.float32)
+    vf_preds = rng.standard_normal((P, R)).astype(np.float32)
+    adv = rng.standard_normal((P, R)).astype(np.float32)
+    vtarg = (vf_preds + 2.0 * rng.standard_normal((P, R))).astype(np.float32)
+    perms = np.stack([np.stack([rng.permutation(NB) for _ in range(E)]) for _ in range(P)]).astype(np.int32)
+    L = FCNetLearner(P, D, A, cfg, "cuda", theta=th0.float(), mode=mode, vf_share_layers=vf_share, free_log_std=free_std)
+    stats = L.learn_on_batch(_dev(obs, "cuda"), _dev(actions, "cuda"), _dev(old_logits, "cuda"), _dev(old_logp, "cuda"),
+                             _dev(vf_preds, "cuda"), _dev(adv, "cuda"), _dev(vtarg, "cuda"), _dev(perms, "cuda"), standardize=False)
+    torch.cuda.synchronize()
+    fwd = lambda th, x: O.fcnet_forward(th, x, 2 * A, vf_share_layers=vf_share, free_log_std=free_std)
+    for p in range(P):
+        def run(dtype):
+            batch = {"obs": torch.from_numpy(obs[p]).to(dtype), "actions": torch.from_numpy(actions[p]).to(dtype),
+                     "old_logits": torch.from_numpy(old_logits[p]).to(dtype), "old_logp": torch.from_numpy(old_logp[p]).to(dtype),
+                     "vf_preds": torch.from_numpy(vf_preds[p]).to(dtype), "advantages": torch.from_numpy(adv[p]).to(dtype),
+                     "value_targets": torch.from_numpy(vtarg[p]).to(dtype)}
+            t = th0[p].float().to(dtype)
+            return O.sgd_loop(t, O.AdamState.zeros(t.numel(), dtype, cfg_o), fwd, batch, perms[p], cfg_o.kl_coeff, cfg_o)
+        th64, s64 = run(torch.float64)
+        th32, _ = run(torch.float32)
+        base = th0[p].float().numpy().astype(np.float64)
+        upd_o = th64.numpy() - base
+        err_dev = scaled_err(L.theta_model[p].cpu().numpy().astype(np.float64) - base, upd_o)
+        err_twin = scaled_err(th32.numpy().astype(np.float64) - base, upd_o)
+        assert err_dev < 10.0 * err_twin + 1e-5, (err_dev, err_twin)
+        assert scaled_err(L.theta_model[p].cpu().numpy(), th64.numpy()) < 2e-3
+        # the kernel-layout vector is the index-select of the trained variables (tied copies identical)
+        sel = torch.cat([L.theta_model[p], L.theta_model.new_zeros(1)])[L.layout_map.long().clamp(max=L.NPm)]
+        assert torch.equal(L.theta[p], sel)
+        for k in ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var"):
+            assert abs(stats[p][k] - s64[k]) < 1e-4 * max(1.0, abs(s64[k])), (k, stats[p][k], s64[k])
