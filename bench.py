@@ -307,13 +307,15 @@ def time_fcnet(arch, envs, nb, mode, steps, warmup, sets=2):
     L.step_ctr.zero_()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nl = E if pers else min(E * nb, 64)
+    nl = 2 if pers else min(E * nb, 64)
     e0.record()
     for _ in range(nl):
-        L._sgd_step(b, MB, G, hyper, src, nsteps=nb if pers else 1)
+        if pers:
+            L.step_ctr.zero_()
+        L._sgd_step(b, MB, G, hyper, src, nsteps=E * nb if pers else 1)
     e1.record()
     torch.cuda.synchronize()
-    us_step = 1e3 * e0.elapsed_time(e1) / (nl * (nb if pers else 1))
+    us_step = 1e3 * e0.elapsed_time(e1) / (nl * (E * nb if pers else 1))
     del L, rs
     return {"arch": arch, "policies": P, "agents_per_env": Ag, "obs_dim": D, "act_dim": A, "envs": envs, "rows_per_policy": R,
             "minibatches_per_epoch": nb, "sgd_minibatch_size": R // nb, "mode": mode, "value": T * envs * Ag / (ms * 1e-3),
@@ -515,7 +517,7 @@ def main():
     G_ = L._sgd_setup(R)[2]
     fused = L.fuse_tail and G_ * P <= L.sms     # train kernel carries reduce + [peer all-reduce] + clip + Adam
     per_sgd = 1 if fused else 3
-    sgd_launches = E if L._persistent_steps(G_) else steps_per_iter * per_sgd    # persistent: one launch per epoch
+    sgd_launches = 1 if L._persistent_steps(G_) else steps_per_iter * per_sgd    # persistent: ONE launch for all E * nb steps
     launches_per_iter = 1 + 2 + 2 + 2 + 1 + 7 + sgd_launches   # pack, filter x2, fwd x2, gae x2, standardise, 7 gathers, sgd
     ms_e2e = timed(step_e2e, max(4, args.warmup), max(3, args.steps // 2))   # warm-up covers both staging slots (graph capture)
     e2e_steps = max(3, args.steps // 2)
@@ -525,26 +527,28 @@ def main():
     e2e_value = agent_steps * e2e_steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel: the SGD-step kernel exactly as the product path launches it (fused forward +
-    # PPO loss + backward + gradient reduce + [peer all-reduce] + clip + Adam; persistent: one launch = one epoch of
-    # `nb` steps), each launch bracketed by CUDA events on the launching (= torch current) stream -------------------------
+    # PPO loss + backward + gradient reduce + [peer all-reduce] + clip + Adam; persistent: one launch = the E * nb steps of
+    # an iteration), each launch bracketed by CUDA events on the launching (= torch current) stream -------------------------
     b = L._bufs
     src = {n_: b[n_ + "_s"] for n_ in ("obs", "act", "logits", "logp", "value", "adv", "vtarg")}
     MB, nbb, G = L._sgd_setup(R)
     hyper = L._hyper(MB * world)
     persistent = L._persistent_steps(G)
-    steps_per_launch = nb if persistent else 1
-    n_launch = E if persistent else 40
+    steps_per_launch = E * nb if persistent else 1      # as the product path launches it: all steps of an iteration
+    n_launch = 5 if persistent else 40
     evs = []
     L.step_ctr.zero_()
     barrier()
     for i in range(n_launch):
         a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if persistent:
+            L.step_ctr.zero_()      # every launch runs steps 0 .. E * nb - 1 of the minibatch schedule
         a.record()
         L._sgd_step(b, MB, G, hyper, src, nsteps=steps_per_launch)
         c.record()
         evs.append((a, c))
     torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(c) for a, c in evs[2:]]))
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in evs[1 if persistent else 2:]]))
     flops_launch = train_flops_per_row(D, A) * MB * P * steps_per_launch
     achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12
     peaks = {}

@@ -159,17 +159,20 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
         }
         __syncthreads();
         const int nf = 4 * min(cpp, ncol4 - c0);
-        for (int f = tid; f < nf; f += nt) {
+        for (int fb = 0; fb < nf; fb += nt) {      // every thread runs the same trip count: the shuffle below is warp-wide
+            const int f = fb + tid;
+            const bool act = f < nf;
             const int col = f >> 2, e = f & 3;
             float s = 0.f;
-            for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * cpp + col])[e];
+            if (act)
+                for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * cpp + col])[e];
             const int jj = 4 * c0 + f;           // offset inside the slice
             if (W > 1) {
                 // push to every rank's exchange buffer (own copy included).  Two neighbouring elements travel as ONE 16-byte
                 // store {value, flag, value, flag} issued by the even lane (NCCL-LL line: each 8-byte half is self-validating,
                 // so the store need not be atomic as a whole) — half the NVLink packets of one store per element.
-                const float s_nb = __shfl_down_sync(__activemask(), s, 1);      // nf is a multiple of 4: lane pairs stay together
-                if (j0 + jj < NP && (f & 1) == 0) {
+                const float s_nb = __shfl_down_sync(0xffffffffu, s, 1);      // nf is a multiple of 4: lane pairs stay together
+                if (act && j0 + jj < NP && (f & 1) == 0) {
                     const unsigned long long w0 = want | (unsigned long long)__float_as_uint(s);
                     if (j0 + jj + 1 < NP) {
                         const unsigned long long w1 = want | (unsigned long long)__float_as_uint(s_nb);
@@ -182,7 +185,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
                         for (int w = 0; w < W; ++w) st_relaxed_sys_u64(t.peer_x[w] + xoff + jj, w0);
                     }
                 }
-            } else if (j0 + jj < NP) {
+            } else if (act && j0 + jj < NP) {
                 slice_dst[jj] = s;
                 gval = s;
             }

@@ -82,6 +82,7 @@ class _LearnerBase:
         self.gnorm = torch.zeros(P, dtype=f32, device=self.device)
         self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.sync_ws = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.sync_token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.dist, self.world, self.rank = _dist_world()
 
     def _hyper(self, global_mb: int) -> PPOHyper:
@@ -398,13 +399,17 @@ class FCNetLearner(_LearnerBase):
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()
         hyper = self._hyper(MB * self.world)
+        if self.world > 1:
+            # the persistent kernels exchange gradients over peer memory with BOUNDED spins: line the ranks' streams up first
+            # (one tiny collective; learn_on_batch(standardize=False) has no other collective ahead of the launch)
+            self.dist.all_reduce(self.sync_token)
         if self.world > 1 and self.fuse_tail and G * P <= self.sms:
             self._peer_exchange(G)      # allocate / map the peer buffers outside any graph capture
         ran = False
         if self._persistent_steps(G):
-            # one persistent launch per epoch: nb consecutive optimizer steps inside the kernel (no graph needed)
-            for _ in range(E):
-                self._sgd_step(b, MB, G, hyper, src, nsteps=nb)
+            # ONE persistent launch for the whole SGD phase: all E * nb optimizer steps run inside the kernel (the minibatch
+            # order of every epoch is in mb_perm; no graph needed)
+            self._sgd_step(b, MB, G, hyper, src, nsteps=steps)
             ran = True
         elif self.use_graph:
             key = (T, Cc, steps, G, MB, src_key)
@@ -645,7 +650,7 @@ class GraphNetLearner(_LearnerBase):
 
 
 def _graphnet_sgd_phase_tc(self, cols, perms, R: int, MB: int, E: int, nb: int, hyper) -> List[Dict[str, float]]:
-    """E persistent launches of `ddrl_graphnet_train_step_tc` (nb optimizer steps each, fused tail) + stats + KL update."""
+    """ONE persistent launch of `ddrl_graphnet_train_step_tc` (all E * nb optimizer steps, fused tail) + stats + KL update."""
     cfg, dev, A = self.cfg, self.device, self.A
     steps = E * nb
     Gn = max(1, min(self.ctas, self.sms // 2))
@@ -662,10 +667,12 @@ def _graphnet_sgd_phase_tc(self, cols, perms, R: int, MB: int, E: int, nb: int, 
     w["mb_perm"].copy_(perms.reshape(steps))
     self.step_ctr.zero_()
     self.status.zero_()
+    if self.world > 1:
+        self.dist.all_reduce(self.sync_token)      # line the ranks' streams up ahead of the bounded peer spins
     tail = K.make_sgd_tail(self.theta, self.m, self.v, self.beta_pow, self.grad, w["tail_bar"], w["tail_sq"], cfg.lr, cfg.beta1,
                            cfg.beta2, cfg.adam_eps, cfg.grad_clip, self.gnorm, step_stats=w["step_stats"], step_ctr=self.step_ctr,
                            status=self.status)
-    tail.nsteps = nb
+    tail.nsteps = steps
     if self.world > 1:
         pkey = (1, self.NP, 2 * Gn)
         if self._peers is None or self._peers.key != pkey:
@@ -675,10 +682,9 @@ def _graphnet_sgd_phase_tc(self, cols, perms, R: int, MB: int, E: int, nb: int, 
             self._peers = PeerExchange(self.dist, self.world, self.rank, 1, self.NP, 2 * Gn, dev)
         self._peers.fill(tail)
     th = self.theta.reshape(-1)
-    for _ in range(E):
-        K.graphnet_train_step_tc(th, cols["idx"], cols["st"], cols["adj"], cols["act"], cols["logits"], cols["logp"], cols["value"],
-                                 cols["adv"], cols["vtarg"], A, MB, w["mb_perm"], self.step_ctr, self.kl_coeff, hyper, Gn,
-                                 w["grad_part"], w["stat_part"], self.status, tail)
+    K.graphnet_train_step_tc(th, cols["idx"], cols["st"], cols["adj"], cols["act"], cols["logits"], cols["logp"], cols["value"],
+                             cols["adv"], cols["vtarg"], A, MB, w["mb_perm"], self.step_ctr, self.kl_coeff, hyper, Gn,
+                             w["grad_part"], w["stat_part"], self.status, tail)      # all E * nb steps in ONE launch
     last = w["step_stats"][steps - nb:].clone()
     if self.world > 1:
         self.dist.all_reduce(last)
