@@ -29,7 +29,7 @@ import torch
 from . import kernels as K
 from ._lib import DDRLError, PPOHyper
 from .config import PPOConfig
-from .sharding import gather_parts_rank_order, local_minibatch
+from .sharding import gather_stats_rank_order, local_minibatch
 
 STAT_NAMES = ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "vf_explained_var")
 
@@ -162,6 +162,9 @@ class FCNetLearner(_LearnerBase):
         self.filt_M = torch.zeros(P, D, dtype=torch.float64, device=dev)
         self.filt_S = torch.zeros(P, D, dtype=torch.float64, device=dev)
         self.norm = torch.zeros(P, 2, D, dtype=torch.float64, device=dev)
+        self._filt_tmp = {"n": torch.zeros(P, dtype=torch.int64, device=dev), "M": torch.zeros(P, D, dtype=torch.float64, device=dev),
+                          "S": torch.zeros(P, D, dtype=torch.float64, device=dev),
+                          "norm": torch.zeros(P, 2, D, dtype=torch.float64, device=dev)}      # per-rank merge at world > 1
         self.use_graph = use_graph
         self.ctas_per_policy = ctas_per_policy
         # packed shared-memory image of the weights (kept in step by clip_adam); rebuilt at every iteration start so
@@ -290,7 +293,14 @@ class FCNetLearner(_LearnerBase):
         # (i) filter + forward + sample ------------------------------------------------------------------
         if update_filter:
             if self.world > 1:
-                allp = gather_parts_rank_order(K.filter_partial(obs_flat), self.dist, self.world)
+                # this rank's partials -> ONE {count, mean, M2} per (policy, feature) (Chan merge into a zero state), the
+                # ranks' triples gathered in rank order, then folded into the running state: identical bits on every rank
+                t = self._filt_tmp
+                for k in ("n", "M", "S"):
+                    t[k].zero_()
+                K.filter_merge(K.filter_partial(obs_flat), R, t["n"], t["M"], t["S"], t["norm"])
+                one = torch.stack([t["n"].double().unsqueeze(1).expand(P, D), t["M"], t["S"]], dim=-1).reshape(P, 1, D, 3)
+                allp = gather_stats_rank_order(one, self.dist, self.world)
                 K.filter_merge(allp, R * self.world, self.filt_n, self.filt_M, self.filt_S, self.norm)
             else:
                 K.filter_update(obs_flat, self.filt_n, self.filt_M, self.filt_S, self.norm, b["filt_ws"])

@@ -34,6 +34,18 @@ def gather_parts_rank_order(parts: torch.Tensor, dist, world: int) -> torch.Tens
     return torch.cat(bufs, dim=1).contiguous()
 
 
+def gather_stats_rank_order(stat: torch.Tensor, dist, world: int) -> torch.Tensor:
+    """stat [P, 1, D, 3] — ONE {count, mean, M2} triple per (policy, feature): this rank's partials already merged —
+    -> [P, world, D, 3] in RANK ORDER (one all_gather_into_tensor; the final merge then folds `world` entries instead of
+    world x nparts, which was 0.4 ms of serial Chan merges per iteration at 8 ranks)."""
+    if world == 1:
+        return stat
+    P = stat.shape[0]
+    out = torch.empty((world * P,) + tuple(stat.shape[1:]), dtype=stat.dtype, device=stat.device)      # ranks concatenated on dim 0
+    dist.all_gather_into_tensor(out, stat.contiguous())
+    return out.view(world, P, *stat.shape[2:]).permute(1, 0, 2, 3).contiguous()
+
+
 def allreduce_sum_(t: torch.Tensor, dist, world: int) -> torch.Tensor:
     if world > 1:
         dist.all_reduce(t)

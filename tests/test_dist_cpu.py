@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle.ddrl_oracle as O
-from ddrl_b200.sharding import allreduce_sum_, gather_parts_rank_order, local_minibatch, shard_envs
+from ddrl_b200.sharding import allreduce_sum_, gather_parts_rank_order, gather_stats_rank_order, local_minibatch, shard_envs
 
 
 def _free_port():
@@ -63,7 +63,9 @@ def _worker(rank, world, port, out):
     rows_global = pr["T"] * pr["N"]
     assert local_minibatch(rows_global, world) == pr["T"] * (hi - lo)
     g = allreduce_sum_(_grad_sum(pr, slice(lo, hi), 1.0 / rows_global), dist, world)
-    allp = gather_parts_rank_order(_parts(pr["x"][:, lo:hi].reshape(-1, pr["D"])), dist, world)
+    mine = _parts(pr["x"][:, lo:hi].reshape(-1, pr["D"]))
+    allp = gather_stats_rank_order(mine, dist, world)          # the product path: one merged triple per rank
+    assert torch.equal(allp, gather_parts_rank_order(mine, dist, world))
     a = pr["adv"][:, lo:hi].reshape(-1)
     mom = allreduce_sum_(torch.stack([torch.tensor(float(a.numel()), dtype=torch.float64), a.sum(), (a * a).sum()]), dist, world)
     if rank == 0:
