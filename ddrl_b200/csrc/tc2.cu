@@ -36,49 +36,52 @@ constexpr int T2_NMMA = 4;                   // MMA-issue warps: one thread issu
 constexpr int T2_NT = TC_NT + 32 * T2_NMMA;  // 16 epilogue warps + the MMA-issue warps
 constexpr int T2_MMA_WARP = TC_NT / 32;      // first MMA warp (16); these warps never touch an accumulator
 
-__device__ __forceinline__ void t2_split2(float x0, float x1, uint32_t& h, uint32_t& l) {
-    const __half2 hh = __floats2half2_rn(x0, x1);
+// Epilogue math in packed FP32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: one issue slot for two FP32 operations).
+// tanh(x) = 1 - 2 r, r = 1 / (2^(2 log2(e) x) + 1): MUFU ex2 + rcp, absolute error <= 2.4e-7 over the whole range (tanhf:
+// 1.2e-7; 2^y overflows to +inf -> r = 0 -> 1, underflows to 0 -> r = 1 -> -1, so no |x| / copysign is needed).  The
+// cancellation near 0 costs RELATIVE accuracy only, and the activations are cut to ~22 bits (fp16 hi + lo, 2.4e-7 absolute)
+// right afterwards, so the odd-polynomial branch of tanhf buys nothing here.
+constexpr float kT2TanhIn = 2.885390081777927f;      // 2 log2(e)
+__device__ __forceinline__ float2 t2_tanh2(float2 y) {      // y = 2 log2(e) x
+    float2 t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(y.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(y.y));
+    t = __fadd2_rn(t, make_float2(1.f, 1.f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(t.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(t.y));
+    return __ffma2_rn(make_float2(-2.f, -2.f), r, make_float2(1.f, 1.f));
+}
+// (x0, x1) (already scaled, inside the fp16 range) -> fp16 hi pair / lo pair
+__device__ __forceinline__ void t2_split2v(float2 x, uint32_t& h, uint32_t& l) {
+    const __half2 hh = __floats2half2_rn(x.x, x.y);
     const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    const float2 d = __fadd2_rn(x, make_float2(-hf.x, -hf.y));
+    const __half2 ll = __floats2half2_rn(d.x, d.y);
     h = *reinterpret_cast<const uint32_t*>(&hh);
     l = *reinterpret_cast<const uint32_t*>(&ll);
-}
-// 8 floats (times a power-of-two scale) -> fp16 hi / lo chunks, no range check (caller knows |v * scale| < 65504)
-__device__ __forceinline__ void t2_split8(const float* v, float scale, uint4& hi, uint4& lo) {
-    t2_split2(v[0] * scale, v[1] * scale, hi.x, lo.x);
-    t2_split2(v[2] * scale, v[3] * scale, hi.y, lo.y);
-    t2_split2(v[4] * scale, v[5] * scale, hi.z, lo.z);
-    t2_split2(v[6] * scale, v[7] * scale, hi.w, lo.w);
-}
-
-// tanh = sign(x) * (1 - 2 / (exp(2|x|) + 1)) with MUFU ex2 + rcp: absolute error <= 2.4e-7 over the whole range (tanhf:
-// 1.2e-7).  The cancellation near 0 costs RELATIVE accuracy only, and the activations are cut to ~22 bits (fp16 hi + lo,
-// 2.4e-7 absolute) right afterwards, so the odd-polynomial branch of tanhf buys nothing here.
-__device__ __forceinline__ float t2_tanh(float x) {
-    float t, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.885390081777927f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.f));
-    return copysignf(fmaf(-2.f, r, 1.f), x);
 }
 
 // Forward epilogue of this thread's 16 columns: act = tanh(acc * inv_in + bias) -> fp16 hi/lo (x TC_SH), chunked [128][64].
 __device__ __noinline__ void t2_epi_tanh(uint32_t taddr, const float* bias, float inv_in, unsigned char* dhi, unsigned char* dlo,
                                          int row, int cq) {
+    const float2 k2 = make_float2(inv_in * kT2TanhIn, inv_in * kT2TanhIn), c2 = make_float2(kT2TanhIn, kT2TanhIn),
+                 sh = make_float2(TC_SH, TC_SH);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         float v[8];
         umma::tmem_ld8(taddr + 8 * c, v);
         const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
-        v[0] = t2_tanh(fmaf(v[0], inv_in, b0.x)); v[1] = t2_tanh(fmaf(v[1], inv_in, b0.y));
-        v[2] = t2_tanh(fmaf(v[2], inv_in, b0.z)); v[3] = t2_tanh(fmaf(v[3], inv_in, b0.w));
-        v[4] = t2_tanh(fmaf(v[4], inv_in, b1.x)); v[5] = t2_tanh(fmaf(v[5], inv_in, b1.y));
-        v[6] = t2_tanh(fmaf(v[6], inv_in, b1.z)); v[7] = t2_tanh(fmaf(v[7], inv_in, b1.w));
-        uint4 hi, lo;
-        t2_split8(v, TC_SH, hi, lo);          // |tanh| <= 1: always inside the fp16 range
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 y = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), k2, __fmul2_rn(bb[j], c2));
+            t2_split2v(__fmul2_rn(t2_tanh2(y), sh), h[j], l[j]);          // |tanh| <= 1: always inside the fp16 range
+        }
         const int off = ((2 * cq + c) * TC_ROWS + row) * 16;
-        *reinterpret_cast<uint4*>(dhi + off) = hi;
-        *reinterpret_cast<uint4*>(dlo + off) = lo;
+        *reinterpret_cast<uint4*>(dhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(dlo + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -87,21 +90,27 @@ __device__ __noinline__ void t2_epi_tanh(uint32_t taddr, const float* bias, floa
 __device__ __noinline__ bool t2_epi_grad(uint32_t taddr, float inv_in, float out_scale, unsigned char* bhi, unsigned char* blo,
                                          int row, int cq) {
     float mx = 0.f;
+    const float2 ki = make_float2(inv_in, inv_in), ks = make_float2(1.f / TC_SH, 1.f / TC_SH), os = make_float2(out_scale, out_scale),
+                 one = make_float2(1.f, 1.f);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-        float v[8], h[8];
+        float v[8];
         umma::tmem_ld8(taddr + 8 * c, v);
         const int off = ((2 * cq + c) * TC_ROWS + row) * 16;
-        tc_join8(*reinterpret_cast<const uint4*>(bhi + off), *reinterpret_cast<const uint4*>(blo + off), 1.f / TC_SH, h);
+        const uint4 qh = *reinterpret_cast<const uint4*>(bhi + off), ql = *reinterpret_cast<const uint4*>(blo + off);
+        const __half2* hp = reinterpret_cast<const __half2*>(&qh);
+        const __half2* lp = reinterpret_cast<const __half2*>(&ql);
+        uint32_t h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v[j] = v[j] * inv_in * (1.f - h[j] * h[j]);
-            mx = fmaxf(mx, fabsf(v[j]));
+        for (int j = 0; j < 4; ++j) {
+            const float2 act = __fmul2_rn(__fadd2_rn(__half22float2(hp[j]), __half22float2(lp[j])), ks);
+            const float2 om = __ffma2_rn(make_float2(-act.x, -act.y), act, one);                    // 1 - h^2
+            const float2 g = __fmul2_rn(__fmul2_rn(make_float2(v[2 * j], v[2 * j + 1]), ki), om);
+            mx = fmaxf(mx, fmaxf(fabsf(g.x), fabsf(g.y)));
+            t2_split2v(__fmul2_rn(g, os), h[j], l[j]);      // an overflow of the fp16 range is reported through the return value
         }
-        uint4 hi, lo;
-        t2_split8(v, out_scale, hi, lo);
-        *reinterpret_cast<uint4*>(bhi + off) = hi;
-        *reinterpret_cast<uint4*>(blo + off) = lo;
+        *reinterpret_cast<uint4*>(bhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(blo + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
     return !(mx * out_scale <= 60000.f);
 }
