@@ -97,6 +97,8 @@ PROTOTYPES = {
     "ddrl_tc_set_variant": (C.c_int, [C.c_int]),
     "ddrl_mpnn2_forward": (C.c_int, [c_f32p] * 5 + [C.c_int64, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
     "ddrl_gat1_forward": (C.c_int, [c_f32p] * 5 + [C.c_int64, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
+    "ddrl_mpnn2_backward": (C.c_int, [c_f32p] * 6 + [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_stream]),
+    "ddrl_gat1_backward": (C.c_int, [c_f32p] * 6 + [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_stream]),
     "ddrl_symm_norm": (C.c_int, [c_f32p, C.c_int64, C.c_int, c_f32p, c_stream]),
     "ddrl_segment_softmax": (C.c_int, [c_f32p, c_i32p, C.c_int64, C.c_int, C.c_int64, c_f32p, c_i32p, c_f32p, c_stream]),
     "ddrl_tc_pingpong_eligible": (C.c_int, [C.c_int, C.c_int]),

@@ -286,6 +286,43 @@ def mpnn2_forward(x, adj, W_msg, W_upd, b=None, act: str = "tanh"):
     return y
 
 
+def _graph_layer_backward(fn_name, x, adj, W0, W1, b, dy, NPw: int, act: str, ctas: Optional[int], need_dx: bool):
+    B, n, F = x.shape
+    U = dy.shape[2]
+    f32 = torch.float32
+    G = ctas or int(max(1, min(B, 148 * 2)))
+    gp = torch.empty(G, part_stride(NPw), dtype=f32, device=x.device)
+    dx = torch.empty(B, n, F, dtype=f32, device=x.device) if need_dx else None
+    fn = getattr(_lib.load(), fn_name)
+    _lib.check(fn(_p(x, f32, "x"), _p(adj, f32, "adj"), _p(W0, f32, "W0"), _p(W1, f32, "W1"), _p(b, f32, "b"), _p(dy, f32, "dy"),
+                  B, F, U, _ACT[act], G, _p(dx, f32, "dx"), _p(gp, f32, "grad_part"), _stream()), fn_name)
+    g = torch.empty(1, NPw, dtype=f32, device=x.device)
+    grad_reduce(gp, None, 1, G, NPw, g)
+    return dx, g.reshape(-1)
+
+
+def mpnn2_backward(x, adj, W_msg, W_upd, b, dy, act: str = "tanh", ctas: Optional[int] = None, need_dx: bool = True):
+    """Backward of MPNN2: dy [B,4,U] -> (dx [B,4,F] or None, dW_msg [2F,U], dW_upd [F+U,U], db [U])."""
+    B, n, F = x.shape
+    U = W_upd.shape[1]
+    if n != 4 or tuple(W_msg.shape) != (2 * F, U) or tuple(W_upd.shape) != (F + U, U) or tuple(dy.shape) != (B, n, U):
+        raise DDRLError("mpnn2_backward: bad shapes")
+    dx, g = _graph_layer_backward("ddrl_mpnn2_backward", x, adj, W_msg, W_upd, b, dy, 2 * F * U + (F + U) * U + U, act, ctas, need_dx)
+    o1, o2 = 2 * F * U, 2 * F * U + (F + U) * U
+    return dx, g[:o1].reshape(2 * F, U), g[o1:o2].reshape(F + U, U), g[o2:]
+
+
+def gat1_backward(x, adj, W_pre, w_att, b, dy, act: str = "tanh", ctas: Optional[int] = None, need_dx: bool = True):
+    """Backward of GAT1: dy [B,4,U] -> (dx [B,4,F] or None, dW_pre [F,U], dw_att [2U], db [U])."""
+    B, n, F = x.shape
+    U = W_pre.shape[1]
+    w_att = w_att.reshape(-1).contiguous()
+    if n != 4 or W_pre.shape[0] != F or w_att.numel() != 2 * U or tuple(dy.shape) != (B, n, U):
+        raise DDRLError("gat1_backward: bad shapes")
+    dx, g = _graph_layer_backward("ddrl_gat1_backward", x, adj, W_pre, w_att, b, dy, F * U + 3 * U, act, ctas, need_dx)
+    return dx, g[:F * U].reshape(F, U), g[F * U:F * U + 2 * U], g[F * U + 2 * U:]
+
+
 def gat1_forward(x, adj, W_pre, w_att, b=None, act: str = "tanh"):
     """GAT1 (models/gcn.py:153-206): x [B,4,F], adj [B,4,4], W_pre [F,U], w_att [2U] (or [2U,1]) -> [B,4,U]."""
     B, n, F = x.shape

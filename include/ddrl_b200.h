@@ -343,7 +343,7 @@ int ddrl_graphnet_train_step_tc(const float* theta, const int32_t* node_idx, con
 int ddrl_gcn_forward(const float* x, const float* adj, const float* W, const float* b, int64_t B,
                      int F, int U, int act, float* y, void* stream);
 
-/* Graph-layer variants the reference carries but does not wire into a model, forward only,
+/* Graph-layer variants the reference carries but does not wire into a model,
  * 4-node graphs: X [B][4][F], A [B][4][4] (adj[s][r] != 0 => edge s -> r), F, U <= 64, act: 0 none, 1 tanh.
  *   MPNN2 (models/gcn.py:96-150):  e = [x_s, x_r] W_msg (W_msg [2F][U]);  m_r = mean of incoming e (0 if none);
  *                                   y = act([x, m] W_upd + b)  (W_upd [F+U][U], b [U] or NULL)
@@ -357,6 +357,14 @@ int ddrl_mpnn2_forward(const float* x, const float* adj, const float* W_msg, con
                        int64_t B, int F, int U, int act, float* y, void* stream);
 int ddrl_gat1_forward(const float* x, const float* adj, const float* W_pre, const float* w_att, const float* b,
                       int64_t B, int F, int U, int act, float* y, void* stream);
+/* Backward of the two layers (tf.gradients through models/gcn.py:96-206): dy [B][4][U] -> dx [B][4][F] (or NULL) and per-CTA
+ * partial weight gradients grad_part [ctas][NPs], NPs = (NP + 3) & ~3, flat order MPNN2 [W_msg (2F x U) | W_upd ((F + U) x U) |
+ * b (U)], GAT1 [W_pre (F x U) | w_att (2U) | b (U)] (the b entries are written even when b == NULL); reduce with
+ * ddrl_grad_reduce(P = 1, G = ctas).  Fixed order, no atomics. */
+int ddrl_mpnn2_backward(const float* x, const float* adj, const float* W_msg, const float* W_upd, const float* b,
+                        const float* dy, int64_t B, int F, int U, int act, int ctas, float* dx, float* grad_part, void* stream);
+int ddrl_gat1_backward(const float* x, const float* adj, const float* W_pre, const float* w_att, const float* b,
+                       const float* dy, int64_t B, int F, int U, int act, int ctas, float* dx, float* grad_part, void* stream);
 int ddrl_symm_norm(const float* adj, int64_t B, int N, float* out, void* stream);
 int ddrl_segment_softmax(const float* data, const int32_t* segment_ids, int64_t E, int C, int64_t num_segments,
                          float* sums_ws, int* bad_id, float* out, void* stream);

@@ -231,3 +231,55 @@ def test_symm_norm_and_segment_softmax():
     from ddrl_b200._lib import DDRLError
     with pytest.raises(DDRLError):
         K.segment_softmax(_dev(data), _dev(seg), S - 5)
+
+
+@pytest.mark.parametrize("F,U,bias,act,ctas", [(19, 64, True, "tanh", None), (64, 64, False, None, 7), (23, 32, True, "tanh", 300)])
+def test_mpnn2_backward_matches_autograd(F, U, bias, act, ctas):
+    """Backward of MPNN2: gradients w.r.t. the inputs, W_msg, W_upd and the bias against the oracle's
+    float64 autograd through `mpnn2_layer` (random graphs incl. isolated receivers); more CTAs than samples allowed."""
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(3 * F + U)
+    B = 257
+    x = rng.standard_normal((B, 4, F)).astype(np.float32)
+    adj = _rand_adj(rng, B)
+    Wm = (rng.standard_normal((2 * F, U)) * 0.2).astype(np.float32)
+    Wu = (rng.standard_normal((F + U, U)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(U).astype(np.float32)
+    dy = rng.standard_normal((B, 4, U)).astype(np.float32)
+    dx, gWm, gWu, gb = K.mpnn2_backward(_dev(x), _dev(adj), _dev(Wm), _dev(Wu), _dev(b) if bias else None, _dev(dy), act, ctas)
+    d = lambda a: torch.from_numpy(a).double().requires_grad_(True)
+    tx, tWm, tWu, tb = d(x), d(Wm), d(Wu), d(b)
+    ref = O.mpnn2_layer(tx, torch.from_numpy(adj).double(), tWm, tWu, tb if bias else None, act)
+    (ref * torch.from_numpy(dy).double()).sum().backward()
+    assert scaled_err(dx.cpu().numpy(), tx.grad.numpy()) < 1e-5
+    assert scaled_err(gWm.cpu().numpy(), tWm.grad.numpy()) < 1e-5
+    assert scaled_err(gWu.cpu().numpy(), tWu.grad.numpy()) < 1e-5
+    if bias:
+        assert scaled_err(gb.cpu().numpy(), tb.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("F,U,bias,act,ctas", [(23, 64, False, "tanh", None), (64, 48, True, None, 5), (19, 64, True, "tanh", 200)])
+def test_gat1_backward_matches_autograd(F, U, bias, act, ctas):
+    """Backward of GAT1 (self loops, leaky-relu attention logits, softmax over the senders of each receiver): gradients
+    w.r.t. the inputs, W_pre, w_att and the bias against the oracle's float64 autograd through `gat1_layer`."""
+    from ddrl_b200 import kernels as K
+    O = _O()
+    rng = np.random.default_rng(F * U + 1)
+    B = 130
+    x = rng.standard_normal((B, 4, F)).astype(np.float32)
+    adj = _rand_adj(rng, B, selfloops=True)
+    Wp = (rng.standard_normal((F, U)) * 0.2).astype(np.float32)
+    wa = (rng.standard_normal((2 * U, 1)) * 0.3).astype(np.float32)
+    b = rng.standard_normal(U).astype(np.float32)
+    dy = rng.standard_normal((B, 4, U)).astype(np.float32)
+    dx, gWp, gwa, gb = K.gat1_backward(_dev(x), _dev(adj), _dev(Wp), _dev(wa), _dev(b) if bias else None, _dev(dy), act, ctas)
+    d = lambda a: torch.from_numpy(a).double().requires_grad_(True)
+    tx, tWp, twa, tb = d(x), d(Wp), d(wa), d(b)
+    ref = O.gat1_layer(tx, torch.from_numpy(adj).double(), tWp, twa, tb if bias else None, act)
+    (ref * torch.from_numpy(dy).double()).sum().backward()
+    assert scaled_err(dx.cpu().numpy(), tx.grad.numpy()) < 1e-5
+    assert scaled_err(gWp.cpu().numpy(), tWp.grad.numpy()) < 1e-5
+    assert scaled_err(gwa.cpu().numpy(), twa.grad.numpy().reshape(-1)) < 1e-5
+    if bias:
+        assert scaled_err(gb.cpu().numpy(), tb.grad.numpy()) < 1e-5
