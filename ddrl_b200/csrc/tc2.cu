@@ -240,16 +240,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
     const unsigned int tag = ts.epoch + (unsigned int)s + 1u;      // LL tag of THIS step's partials / weights
-    if (s > 0) {   // the weights of the previous step: every CTA of this policy must have written its Adam slice
-        if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
-        __syncthreads();
-    }
-    if (warp < T2_MMA_WARP) {   // epilogue warps only: they wait for their cp.async groups and publish them to the async proxy
-        const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
-#pragma unroll 2
-        for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
-        asm volatile("cp.async.commit_group;\n" ::);
-    }
+    // (the weights of this step are fetched inside the tile loop, AFTER the first tile's x has been split: the split does not
+    // depend on them and runs while the other CTAs of the policy still finish their Adam slices)
     T2_STAMP(35);
     T2_GSTAMP(0);
     const int step = step0 + s;
@@ -528,6 +520,17 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 *reinterpret_cast<uint4*>(sm + S.X[0] + (c8 * TC_ROWS + r) * 16) = hi;
                 *reinterpret_cast<uint4*>(sm + S.X[1] + (c8 * TC_ROWS + r) * 16) = lo;
             }
+        }
+        if (first) {   // this step's weight image (epilogue warps only: they wait for their cp.async groups and publish them)
+            if (s > 0) {   // every CTA of this policy must have written its Adam slice of the previous step
+                if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
+                epi_sync();
+            }
+            const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+#pragma unroll 2
+            for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         publish();
         T2_STAMP(3);
