@@ -63,27 +63,44 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
-    def start(self):
+    def start(self, wait_first=10.0):
+        """Spawn `nvidia-smi -lms 100` and wait for its FIRST sample: NVML initialisation takes 50-500 ms and stalls CUDA
+        calls of the process meanwhile — started right in front of the warm-up it used to land inside the timed region of
+        short runs (10-60 ms hiccups in 3 of 9 five-step runs).  Sampling itself goes on through the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t_end = time.time() + wait_first
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, begin):
+        """Host time stamps of the timed region (set right after / before the synchronising barriers)."""
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        rows = self.rows
+        if self.t0 is not None and self.t1 is not None:      # samples taken while the timed region ran (+ one period)
+            inside = [r for r in rows if self.t0 <= r[0] <= self.t1 + 0.1]
+            rows = inside or rows
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for _, r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -492,16 +509,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, warmup, steps):
+    def timed(fn, warmup, steps, sampler=None):
         for i in range(warmup):
             fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.mark(True)
         e0.record()
         for i in range(steps):
             fn(warmup + i)
         e1.record()
         barrier()
+        if sampler is not None:
+            sampler.mark(False)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -510,7 +531,7 @@ def main():
     clocks = ClockSampler(local)
     n0 = K.launch_count()
     clocks.start()
-    ms_total = timed(step_resident, args.warmup, args.steps)
+    ms_total = timed(step_resident, args.warmup, args.steps, clocks)
     clk = clocks.stop()
     # kernels per iteration: API launches outside the captured graph + graph replays x nodes
     steps_per_iter = E * nb

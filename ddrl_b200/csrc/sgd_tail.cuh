@@ -42,13 +42,18 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
 // one thread, after a __syncthreads(): arrive (gpu-scope RELEASE: cumulative over the CTA's writes ordered before it by
 // the barrier — no separate __threadfence) and spin (tight acquire loads, no sleep) until `target` CTAs have arrived;
 // false on timeout
-__device__ __noinline__ static bool grid_group_barrier(unsigned int* ctr, unsigned int target) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+__device__ __noinline__ static bool grid_group_barrier(unsigned int* ctr, unsigned int target, bool arrive = true) {
+    if (arrive) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 #pragma unroll 1
     for (unsigned int i = 0; i < 8000000u; ++i) {
         if (ld_acquire_u32(ctr) >= target) return true;
     }
     return false;
+}
+
+// barrier-A arrival on its own (one thread, after the __syncthreads() behind the CTA's last partial-gradient store)
+__device__ __forceinline__ void sgd_tail_arrive_a(const ddrl_sgd_tail& t, int p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(t.barrier_ws + 4 * p) : "memory");
 }
 
 __host__ __device__ inline int sgd_slice_len(int NP, int G) { return (((NP + G - 1) / G) + 3) & ~3; }
@@ -89,9 +94,13 @@ __device__ __forceinline__ bool sgd_wait_weights(const SgdTail& t, int p, int G,
 
 __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& ts, const float* __restrict__ grad_part,
                                               const double* __restrict__ stat_part, int p, int P, int bx, int G, int NP,
-                                              int step, int D, int A, float* smem, long long* dbg = nullptr, int npart = 0) {
+                                              int step, int D, int A, float* smem, long long* dbg = nullptr, int npart = 0,
+                                              bool arrived = false) {
     // npart: number of gradient partials per policy at grad_part[p][0..npart) (default: one per CTA = G; a kernel that
     // pre-reduces inside thread-block clusters passes the number of clusters)
+    // arrived: the caller has already made thread 0 arrive on barrier A (sgd_tail_arrive_a, right behind the __syncthreads()
+    // that completed the partial) — so that loads the caller issues in between (the next step's input prefetch) are not
+    // ahead of the release and do not lengthen its drain
     if (npart <= 0) npart = G;
 #define TAIL_STAMP(i)                                                                                              \
     do {                                                                                                           \
@@ -120,7 +129,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     __syncthreads();
     if (tid == 0) {
         red[40] = 1.f;
-        red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)(G * ts.round)) ? 1.f : 0.f;
+        red[39] = grid_group_barrier(t.barrier_ws + 4 * p, (unsigned)(G * ts.round), !arrived) ? 1.f : 0.f;
     }
     __syncthreads();
     ok = ok && red[39] != 0.f;
@@ -192,12 +201,6 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
         }
         if (!pf) __syncthreads();
     }
-    if (bx == 0 && warp < DDRL_NSTAT && stat_part && t.step_stats) {   // warp w sums stat w (lanes stride over the partials)
-        double s = 0.0;
-        for (int i = lane; i < G; i += 32) s += __ldcg(stat_part + ((int64_t)p * G + i) * DDRL_NSTAT + warp);
-        s = warp_sum(s);
-        if (lane == 0) t.step_stats[((int64_t)step * P + p) * DDRL_NSTAT + warp] = s;
-    }
     // ---- data parallel: wait for the world's words of this step, add them in rank order -------------------------------
     if (W > 1) {
         const unsigned long long* xl = t.peer_x[t.rank] + ((int64_t)par * W * P + p) * xstride + j0;   // + w * P * xstride
@@ -254,6 +257,17 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
         for (int w = 0; w < nw; ++w) s += red[w];
         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(sq64 + (int64_t)bx * SQ_STRIDE),
                      "l"(((unsigned long long)btag << 32) | (unsigned long long)__float_as_uint(s)) : "memory");
+    }
+    // loss statistics of the step (CTA 0 of the policy; warps 1.. sum one stat each over the G partials, which barrier A made
+    // visible).  Done HERE, behind this CTA's norm word: every CTA of the policy waits for the slowest publisher, and with the
+    // sums ahead of the publication CTA 0 was that one by ~1 us per step (per-CTA globaltimer stamps).
+    if (bx == 0 && warp >= 1 && stat_part && t.step_stats) {
+        for (int w = warp - 1; w < DDRL_NSTAT; w += nw - 1) {
+            double s = 0.0;
+            for (int i = lane; i < G; i += 32) s += __ldcg(stat_part + ((int64_t)p * G + i) * DDRL_NSTAT + w);
+            s = warp_sum(s);
+            if (lane == 0) t.step_stats[((int64_t)step * P + p) * DDRL_NSTAT + w] = s;
+        }
     }
     if (warp == 0) {
         float s = 0.f;

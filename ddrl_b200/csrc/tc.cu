@@ -704,6 +704,7 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
     DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS - 1 && (A == 1 || A == 2 || A == 4 || A == 8), DDRL_E_UNSUPPORTED_SHAPE,
                  "ppo_train_step_tc: unsupported D=%d A=%d (A in {1,2,4,8}, D <= 63)", D, A);
     TcTrainArgs a;
+    DDRL_REQUIRE((reinterpret_cast<uintptr_t>(tc_img_p) & 15) == 0, DDRL_E_BADARG, "ppo_train_step_tc: the weight image must be 16-byte aligned (TMA bulk copies)");
     a.img = (const unsigned char*)tc_img_p; a.obs = obs; a.actions = actions; a.old_logits = old_logits;
     a.old_logp = old_logp; a.vf_preds = vf_preds; a.adv = adv; a.vtarg = vtarg; a.R = R; a.D = D; a.A = A; a.MB = MB;
     a.mb_perm = mb_perm; a.perm_stride = perm_stride; a.step_ctr = step_ctr; a.kl_coeff = kl_coeff; a.hp = *hyper;
@@ -752,6 +753,7 @@ extern "C" int ddrl_fcnet_forward_tc(const void* tc_img_p, const float* obs, con
     DDRL_REQUIRE(R <= 0x7fffffff, DDRL_E_UNSUPPORTED_SHAPE, "fcnet_forward_tc: R must fit 31 bits");
     if (R == 0) return DDRL_OK;
     TcTrainArgs a = {};
+    DDRL_REQUIRE((reinterpret_cast<uintptr_t>(tc_img_p) & 15) == 0, DDRL_E_BADARG, "fcnet_forward_tc: the weight image must be 16-byte aligned (TMA bulk copies)");
     a.img = (const unsigned char*)tc_img_p; a.obs = obs; a.R = R; a.D = D; a.A = A; a.MB = (int)R;
     a.hp = ddrl_ppo_hyper{0.f, 0.f, 0.f, 0.f, 1.f};
     a.status = status; a.dbg_clock = nullptr; a.tail = SgdTail{};

@@ -115,6 +115,21 @@ __device__ __noinline__ bool t2_epi_grad(uint32_t taddr, float inv_in, float out
     return !(mx * out_scale <= 60000.f);
 }
 
+// Shared-memory stores through an explicit shared::cta address.  The staging base is passed through an empty asm statement
+// ("laundered") so that ptxas keeps it in ONE register: left visible, the base is re-derived from D at every store of the
+// write-out (the kernel sits at its 96-register cap) — ~20 integer instructions per stored element, which made the
+// write-out issue bound (1.5 us for two TMEM loads and 16 stores per thread).
+__device__ __forceinline__ uint32_t t2_launder(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ void t2_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void t2_sts4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 t2_lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
 #define T2_STAMP(i)                                                                        \
     do {                                                                                   \
         if (a.dbg_clock && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg_clock[i] = clock64(); \
@@ -135,16 +150,31 @@ __device__ __forceinline__ long long t2_gtime() {
 // (a.MB = a.R), filter normalisation in the X split, DiagGaussian sample + logp in place of the loss, nothing after it.
 // LL = true: the barrier-free "LL" tail (sgd_tail.cuh); its own instantiation so that the classic kernel keeps its register
 // allocation (the kernel sits at the 96-register limit of 640 threads: the merged variant spilled and lost 3 us per step).
-template <int A, bool FWD, bool LL>
+// DT > 0: the observation width as a compile-time constant (the launcher instantiates the ten (D, A) pairs of the published
+// architectures, policies.ARCHITECTURES; DT = 0 reads a.D).  Every shared-memory offset, image offset and flat-parameter offset
+// is a function of (D, A): with D in a register ptxas — at the kernel's 96-register cap — re-derived them from D at nearly
+// every use (~20 integer instructions per staged element in the x split and the write-out); as constants they cost nothing.
+template <int A, bool FWD, bool LL, int DT>
 __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_constant__ TcTrainArgs a) {
     constexpr int A2 = 2 * A;
     T2_STAMP(0);
     extern __shared__ __align__(1024) unsigned char sm[];
     const int p = blockIdx.y, G = gridDim.x, bx = blockIdx.x;
-    const int D = a.D, KX = tc_kx(D);
+    const int D = DT > 0 ? DT : a.D, KX = tc_kx(D);
     const TcImg I = tc_img(D, A);
     const Tc2Smem S = tc2_smem(D, A);
     const FcOffsets o = fc_offsets(D, A);
+    // [branch b][hi | lo h] buffers are equally spaced: offsets by arithmetic, not by indexing the layout structs with a
+    // run-time b (that put the structs into local memory: an LDL in front of every epilogue call and every MMA batch)
+    constexpr int BUFB = TC_ROWS * 64 * 2, DLB = TC_ROWS * TC_NO * 2, W2B = 64 * 64 * 2, WOB = TC_NO * 64 * 2;
+    const int W1B = 64 * KX * 2, sH1_0 = S.H1[0][0], sH2_0 = S.H2[0][0], sDL_0 = S.DL[0][0], iW1_0 = I.W1[0][0],
+              iW2_0 = I.W2[0][0], iWoT_0 = I.WoT[0][0];
+    auto sH1 = [&](int b, int h) { return sH1_0 + (2 * b + h) * BUFB; };
+    auto sH2 = [&](int b, int h) { return sH2_0 + (2 * b + h) * BUFB; };
+    auto sDL = [&](int b, int h) { return sDL_0 + (2 * b + h) * DLB; };
+    auto iW1 = [&](int b, int h) { return iW1_0 + (2 * b + h) * W1B; };
+    auto iW2 = [&](int b, int h) { return iW2_0 + (2 * b + h) * W2B; };
+    auto iWoT = [&](int b, int h) { return iWoT_0 + (2 * b + h) * WOB; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S.bar);          // [2]: one per branch
     uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + S.bar + 16);
@@ -153,8 +183,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 
     // ---- once per launch: TMEM, mbarriers, launch-wide state -------------------------------------------------------------
     if (warp == 0) umma::tmem_alloc(tslot, T2_TMEM_COLS);
-    if (tid == 0) {      // every MMA warp commits; [4] (byte 32): TMA bulk copies of the LL tail
-        umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::mbar_init(mbar + 4, 1); umma::fence_mbar_init();
+    if (tid == 0) {      // every MMA warp commits; [4] (byte 32): TMA bulk copies of the LL tail; [5] (byte 40): weight image
+        umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::mbar_init(mbar + 4, 1); umma::mbar_init(mbar + 5, 1); umma::fence_mbar_init();
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -162,7 +192,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     const uint32_t tmem = *tslot;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     uint32_t ph0 = 0, ph1 = 0;
-    unsigned int ll_phase = 0;
+    unsigned int ll_phase = 0, img_phase = 0;      // parities of the TMA mbarriers: [4] LL tail, [5] weight image
     bool ok = true;
     int ovf = 0;   // bit mask of fp16 overflows: 2 = x, 8 = dl, 16 = dz2, 32 = dz1
     const float klc = a.kl_coeff[p];
@@ -174,8 +204,29 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     // vector) and only ONE partial per cluster reaches L2 — the 148 x 45 KB write / drain / re-read per step was ~9 us.
     const int cs = LL ? 1 : (int)umma::cluster_nctarank(), crank = LL ? 0 : (int)umma::cluster_ctarank();
     const int ncl = G / cs, cid = bx / cs;                 // clusters per policy, this CTA's cluster
-    float* stg = reinterpret_cast<float*>(sm + S.H1[0][0]);   // [NPs] staging of the partial (H1 is free after the main loop)
-    float* gp = cs > 1 ? stg : a.grad_part + ((int64_t)p * G + bx) * NPs;
+    float* stg = reinterpret_cast<float*>(sm + sH1(0, 0));   // [NPs] staging of the partial (H1 is free after the main loop)
+    // Without clusters the partial is staged as well — in H2 (64 KB >= NPs floats; both dZ2 are dead once the last B3 has
+    // completed, so gW2 / gb2 / gWh can go there while B5 still runs) — and leaves the SM as ONE coalesced copy of full
+    // 128-byte lines.  Written straight from the TMEM read-out (lane = matrix row) the partial reached L2 as ~3000 16-byte
+    // partial-sector requests per CTA, and the drain of those requests — not their bytes — set the length of the write-out,
+    // of barrier A behind it and of the slice reduce that re-reads them.
+    float* gpart = a.grad_part + ((int64_t)p * G + bx) * NPs;      // this CTA's partial in global memory
+    float* gp = LL ? gpart : (cs > 1 ? stg : reinterpret_cast<float*>(sm + sH2(0, 0)));
+    const bool stage_copy = !FWD && !LL && cs == 1;
+    bool staged = false;                                           // this step's partial sits in shared memory (CTA-uniform)
+    // staged partial -> global memory, float4 range [i0, i1), full 128-byte lines; `nthr` threads (t0 = 0 .. nthr-1) take part
+    auto copy_out = [&](int i0, int i1, int t0, int nthr) {
+        const int w2a = o.W2 >> 2, v2a = o.Wv2 >> 2;      // the two swizzled 64 x 64 blocks: 1024 float4 each
+        const uint32_t s4 = t2_launder(umma::smem_u32(gp));
+        float4* g4 = reinterpret_cast<float4*>(gpart);
+#pragma unroll 2
+        for (int i = i0 + t0; i < i1; i += nthr) {
+            const unsigned int r0 = (unsigned int)(i - w2a), r1 = (unsigned int)(i - v2a);
+            const int sw = r0 < 1024u ? (int)((r0 >> 4) & 7u) : r1 < 1024u ? (int)((r1 >> 4) & 7u) : 0;
+            g4[i] = t2_lds4(s4 + 16u * (uint32_t)(i ^ sw));      // block starts are multiples of 16 float4: the XOR stays inside the row
+        }
+    };
+
     const bool has_tail = a.tail.theta != nullptr;
     // LL tail (sgd_tail.cuh): partial gradients and updated weights travel between CTAs as self-validating words
     constexpr bool ll = LL;      // the launcher picks the instantiation: fused tail, ll_ws given, no clusters, slice <= CTA
@@ -200,39 +251,38 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     const float* sbo = reinterpret_cast<const float*>(sm + I.bo);
     const float* sbvo = reinterpret_cast<const float*>(sm + I.bvo);
 
-    auto prefetch_x = [&](int64_t r0, int n) {
+    // contiguous run of `cnt` floats global -> shared: 16-byte cp.async when both ends and the length allow it (every full
+    // tile of the shuffled batch does: a quarter of the LDGSTS instructions and of their address arithmetic)
+    auto cp_run = [&](float* dst, const float* src, int cnt) {
+        if ((((uint32_t)reinterpret_cast<uintptr_t>(src) | umma::smem_u32(dst) | ((uint32_t)cnt << 2)) & 15u) == 0u) {
 #pragma unroll 1
-        for (int i = tid; i < n * D; i += TC_NT) tc_cp4(xraw + i, obs_p + r0 * D + i);
+            for (int i = tid; i < (cnt >> 2); i += TC_NT)
+                tc_cp16(reinterpret_cast<unsigned char*>(dst + 4 * i), reinterpret_cast<const unsigned char*>(src + 4 * i));
+        } else {
+#pragma unroll 1
+            for (int i = tid; i < cnt; i += TC_NT) tc_cp4(dst + i, src + i);
+        }
     };
+    auto prefetch_x = [&](int64_t r0, int n) { cp_run(xraw, obs_p + r0 * D, n * D); };
     auto prefetch_loss = [&](int64_t r0, int n) {
         const int64_t g0 = (int64_t)p * a.R + r0;
         float* pa = pf;
         float* po = reinterpret_cast<float*>(sm + S.po);
         float* ps = pa + TC_ROWS * A + (S.po_in_w1 ? 0 : TC_ROWS * A2);
         const float* first_in = FWD ? a.eps : a.actions;      // inference: the only per-row input besides x is the noise
-        if (first_in) {
-#pragma unroll 1
-            for (int i = tid; i < n * A; i += TC_NT) tc_cp4(pa + i, first_in + g0 * A + i);
-        }
+        if (first_in) cp_run(pa, first_in + g0 * A, n * A);
         if (FWD) return;
-        if (!S.po_in_w1) {
-#pragma unroll 1
-            for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
-        }
-#pragma unroll 1
-        for (int i = tid; i < n; i += TC_NT) {
-            tc_cp4(ps + i, a.old_logp + g0 + i);
-            tc_cp4(ps + TC_ROWS + i, a.vf_preds + g0 + i);
-            tc_cp4(ps + 2 * TC_ROWS + i, a.adv + g0 + i);
-            tc_cp4(ps + 3 * TC_ROWS + i, a.vtarg + g0 + i);
-        }
+        if (!S.po_in_w1) cp_run(po, a.old_logits + g0 * A2, n * A2);
+        cp_run(ps, a.old_logp + g0, n);
+        cp_run(ps + TC_ROWS, a.vf_preds + g0, n);
+        cp_run(ps + 2 * TC_ROWS, a.adv + g0, n);
+        cp_run(ps + 3 * TC_ROWS, a.vtarg + g0, n);
     };
 
     auto prefetch_po = [&](int64_t r0, int n) {   // old logits into the W1 region: only once F1 has consumed W1 (po_in_w1)
         const int64_t g0 = (int64_t)p * a.R + r0;
         float* po = reinterpret_cast<float*>(sm + S.po);
-#pragma unroll 1
-        for (int i = tid; i < n * A2; i += TC_NT) tc_cp4(po + i, a.old_logits + g0 * A2 + i);
+        cp_run(po, a.old_logits + g0 * A2, n * A2);
         asm volatile("cp.async.commit_group;\n" ::);
     };
     bool prefetched = false;   // the first tile's inputs of this step were already requested behind the previous step's tail
@@ -249,6 +299,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     const int64_t mb0 = (int64_t)mb * a.MB;
     if (mb0 >= 0) T2_STAMP(36);
     bool first = true;
+    staged = false;
     // loss warps: 0-3 policy part (s0 = -surr, s1 = KL, s2 = entropy), 4-7 value part (s0 = vf, s1..4 = R, R^2, R-v, (R-v)^2)
     double st[5];
 #pragma unroll
@@ -270,11 +321,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         if constexpr (LL) {
             for (int i = tid; i < (LLW >> 1); i += T2_NT) ll_st2(llp + 2 * i, 0u, 0u, tag);
         } else {
-            for (int i = tid; i < NPs; i += T2_NT) gp[i] = 0.f;
+            float* z = stage_copy ? gpart : gp;      // (already coalesced: straight to global memory)
+            for (int i = tid; i < NPs; i += T2_NT) z[i] = 0.f;
             if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
         }
         break;
     }
+    staged = stage_copy;
 
     // ---- this step's first tile: inputs ---------------------------------------------------------------------------------
     if (warp < T2_MMA_WARP && !prefetched) {
@@ -311,16 +364,17 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     // gW2_b, gb2_b, gWh_b are final once B3(b) / B1 have completed, i.e. BEFORE the last B5: they are written while B5 runs.
     // (Not with clusters: the staging buffer of the partial lives in H1, which B5 still reads.)
     const bool early_out = cs == 1;
+    uint32_t gps = 0;      // shared::cta address of the staged partial (laundered right before each write-out piece)
     auto put1 = [&](int idx, float v) {
         if constexpr (LL) ll_st1(llp + idx, __float_as_uint(v), tag);
-        else gp[idx] = v;
+        else t2_sts(gps + 4u * (uint32_t)idx, v);
     };
     auto put4 = [&](int idx, float x0, float x1, float x2, float x3) {      // idx % 4 == 0
         if constexpr (LL) {
             ll_st2(llp + idx, __float_as_uint(x0), __float_as_uint(x1), tag);
             ll_st2(llp + idx + 2, __float_as_uint(x2), __float_as_uint(x3), tag);
         } else {
-            *reinterpret_cast<float4*>(gp + idx) = make_float4(x0, x1, x2, x3);
+            t2_sts4(gps + 4u * (uint32_t)idx, x0, x1, x2, x3);
         }
     };
     auto write_w2_heads = [&](int b) {
@@ -332,14 +386,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             umma::tmem_ld8_nowait(tmem + tlane + T2_GW2 + 64 * b + 16 * cq + 8, r1);
             umma::tmem_ld_wait();
             if (mine) {
-                const int dst = (b ? o.Wv2 : o.W2) + m * 64 + 16 * cq;      // W2 / Wv2 offsets are multiples of 4
-                put4(dst, __uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
+                // staged copy: the 16 float4 of row m are XOR-swizzled by (m & 7) so that the 16 lanes (16 rows, 256 bytes
+                // apart) hit different banks; the copy-out undoes it
+                const int rowb = (b ? o.Wv2 : o.W2) + m * 64, c4 = 4 * cq, sw = stage_copy ? (m & 7) : 0;
+                put4(rowb + 4 * ((c4 + 0) ^ sw), __uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
                      __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
-                put4(dst + 4, __uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
+                put4(rowb + 4 * ((c4 + 1) ^ sw), __uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
                      __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
-                put4(dst + 8, __uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
+                put4(rowb + 4 * ((c4 + 2) ^ sw), __uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
                      __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
-                put4(dst + 12, __uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
+                put4(rowb + 4 * ((c4 + 3) ^ sw), __uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
                      __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
             }
         }
@@ -377,12 +433,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             umma::tmem_ld8_nowait(gw1_split ? base0 + 32 : base0, r3);      // second product half (split) or the same again
             umma::tmem_ld_wait();
             if (mine) {
+                // flat order: gW1[d][m] at W1 + 64 d + m, and the bias gradient (column D: the constant-1 input) is row D
+                // of the same block (b1 == W1 + 64 D, fc_offsets) -> one base index, immediate offsets, one predicate each
+                const int i0 = (b ? o.Wv1 : o.W1) + 512 * c8 + m, jmax = D - 8 * c8;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int d = 8 * c8 + j;
                     const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
-                    if (d < D) put1((b ? o.Wv1 : o.W1) + d * 64 + m, g);
-                    else if (d == D) put1((b ? o.bv1 : o.b1) + m, g);
+                    if (j <= jmax) put1(i0 + 64 * j, g);
                 }
             }
         }
@@ -396,16 +453,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const uint32_t sbu = __shfl_sync(0xffffffffu, sbase, 0);
         const uint32_t Xhu = sbu + S.X[0], Xlu = sbu + S.X[1];
-        const uint32_t H1h[2] = {sbu + S.H1[0][0], sbu + S.H1[1][0]}, H1l[2] = {sbu + S.H1[0][1], sbu + S.H1[1][1]};
-        const uint32_t H2h[2] = {sbu + S.H2[0][0], sbu + S.H2[1][0]}, H2l[2] = {sbu + S.H2[0][1], sbu + S.H2[1][1]};
-        const uint32_t DLh[2] = {sbu + S.DL[0][0], sbu + S.DL[1][0]}, DLl[2] = {sbu + S.DL[0][1], sbu + S.DL[1][1]};
 #pragma unroll 1
         for (int64_t row0 = cr0; row0 < cr1; row0 += TC_ROWS) {
             const bool acc = !first;
             mma_turn();      // X split done.  F1: Dacc_b = X * W1b^T   (warp b)
             {
                 if (mw < 2)
-                    tc_gemm_u(tm + T2_DACC + 64 * mw, Xhu, Xlu, TC_ROWS, false, sbu + I.W1[mw][0], sbu + I.W1[mw][1], 64, false,
+                    tc_gemm_u(tm + T2_DACC + 64 * mw, Xhu, Xlu, TC_ROWS, false, sbu + iW1(mw, 0), sbu + iW1(mw, 1), 64, false,
                             128, 64, KX >> 4, false, 3);
                 umma::mma_commit_elect(mbar);
                 umma::mma_commit_elect(mbar + 1);
@@ -416,7 +470,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 mma_turn();
                 {
                     if (mw == b)
-                        tc_gemm_u(tm + T2_DACC + 64 * b, H1h[b], H1l[b], TC_ROWS, false, sbu + I.W2[b][0], sbu + I.W2[b][1], 64,
+                        tc_gemm_u(tm + T2_DACC + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, false, sbu + iW2(b, 0), sbu + iW2(b, 1), 64,
                                 true, 128, 64, 4, false, 3);
                     umma::mma_commit_elect(mbar + b);
                 }
@@ -427,7 +481,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 mma_turn();
                 {
                     if (mw == b)
-                        tc_gemm_u(tm + T2_HOUT + 16 * b, H2h[b], H2l[b], TC_ROWS, false, sbu + I.WoT[b][0], sbu + I.WoT[b][1],
+                        tc_gemm_u(tm + T2_HOUT + 16 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, false, sbu + iWoT(b, 0), sbu + iWoT(b, 1),
                                 TC_NO, false, 128, TC_NO, 4, false, 3);
                     umma::mma_commit_elect(mbar + b);
                 }
@@ -438,12 +492,12 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             {
                 const int b = mw & 1;
                 if (mw < 2) {
-                    tc_gemm_u(tm + T2_DACC + 64 * b, DLh[b], DLl[b], TC_ROWS, false, sbu + I.WoT[b][0], sbu + I.WoT[b][1], TC_NO,
+                    tc_gemm_u(tm + T2_DACC + 64 * b, (sbu + sDL(b, 0)), (sbu + sDL(b, 1)), TC_ROWS, false, sbu + iWoT(b, 0), sbu + iWoT(b, 1), TC_NO,
                             true, 128, 64, 1, false, 3);
-                    tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64, 16, 8,
+                    tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b), (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, (sbu + sDL(b, 0)), (sbu + sDL(b, 1)), TC_ROWS, true, 64, 16, 8,
                                  acc, 1);
                 } else {
-                    tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b + 1), H2h[b], H2l[b], TC_ROWS, true, DLh[b], DLl[b], TC_ROWS, true, 64,
+                    tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b + 1), (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, (sbu + sDL(b, 0)), (sbu + sDL(b, 1)), TC_ROWS, true, 64,
                                  16, 8, acc, 6);
                 }
                 umma::mma_commit_elect(mbar);
@@ -455,12 +509,12 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 mma_turn();
                 {
                     if (mw == 0)
-                        tc_gemm_u(tm + T2_DACC + 64 * b, H2h[b], H2l[b], TC_ROWS, false, sbu + I.W2[b][0], sbu + I.W2[b][1], 64,
+                        tc_gemm_u(tm + T2_DACC + 64 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, false, sbu + iW2(b, 0), sbu + iW2(b, 1), 64,
                                 false, 128, 64, 4, false, 3);
                     else if (mw == (b ? 3 : 1))
-                        tc_gemm_u(tm + T2_GW2 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, H2h[b], H2l[b], TC_ROWS, true, 64, 64, 8, acc, 3);
+                        tc_gemm_u(tm + T2_GW2 + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, 64, 64, 8, acc, 3);
                     else if (mw == 2)
-                        tc_gemm_u(tm + T2_GB2 + 16 * b, H2h[b], H2l[b], TC_ROWS, true, Xhu + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
+                        tc_gemm_u(tm + T2_GB2 + 16 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, Xhu + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
                                 16, 8, acc, 2);
                     umma::mma_commit_elect(mbar + b);
                 }
@@ -472,13 +526,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 {
                     if (gw1_split) {
                         if (mw == 0)
-                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b), H1h[b], H1l[b], TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8,
+                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b), (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8,
                                          acc, 1);
                         if (mw == 1)
-                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b + 1), H1h[b], H1l[b], TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX,
+                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b + 1), (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX,
                                          8, acc, 6);
                     } else if (mw == b) {
-                        tc_gemm_u(tm + T2_GW1 + 64 * b, H1h[b], H1l[b], TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8, acc, 3);
+                        tc_gemm_u(tm + T2_GW1 + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8, acc, 3);
                     }
                     umma::mma_commit_elect(mbar + b);
                 }
@@ -521,16 +575,27 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 *reinterpret_cast<uint4*>(sm + S.X[1] + (c8 * TC_ROWS + r) * 16) = lo;
             }
         }
-        if (first) {   // this step's weight image (epilogue warps only: they wait for their cp.async groups and publish them)
-            if (s > 0) {   // every CTA of this policy must have written its Adam slice of the previous step
-                if (tid == 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
-                epi_sync();
-            }
-            const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
-#pragma unroll 2
-            for (int i = tid; i < I.bytes / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
-            asm volatile("cp.async.commit_group;\n" ::);
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (first) {   // this step's weight image: ONE thread waits for the Adam slices and hands the 57-66 KB to the TMA (four
+                       // cp.async.bulk copies completing on an mbarrier); nobody else issues a load or computes an address
+            const uint32_t imb = sbase + S.bar + 40;
+            if (warp == 0) {
+                if (lane == 0) {
+                    // every CTA of this policy must have written its Adam slice of the previous step
+                    if (s > 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
+                    asm volatile("fence.proxy.async;" ::: "memory");      // acquired generic-proxy writes -> async-proxy (TMA) reads
+                    const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
+                    const uint32_t part = (uint32_t)(((I.bytes >> 2) + 15) & ~15);
+                    mbar_expect_tx(imb, (uint32_t)I.bytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t off = (uint32_t)k * part;
+                        if (off < (uint32_t)I.bytes) bulk_g2s(sbase + off, img_p + off, min(part, (uint32_t)I.bytes - off), imb);
+                    }
+                }
+                __syncwarp();      // lanes 1-31 must not spin on the mbarrier while lane 0 is still polling (divergent try_wait
+            }                      // loops delay the other path by 0.5-2 us)
+            if (!mbar_wait_parity(imb, img_phase)) ok = false;
+            img_phase ^= 1u;
         }
         publish();
         T2_STAMP(3);
@@ -541,7 +606,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             wait_b(b);
             T2_STAMP(4 + 3 * b);
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b1c + b * 64 + 16 * cq, 1.f / (TC_SX * TC_SW),
-                        sm + S.H1[b][0], sm + S.H1[b][1], row, cq);
+                        sm + sH1(b, 0), sm + sH1(b, 1), row, cq);
             T2_STAMP(5 + 3 * b);
             publish();
             T2_STAMP(6 + 3 * b);
@@ -553,7 +618,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             wait_b(b);
             T2_STAMP(10 + 3 * b);
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b2c + b * 64 + 16 * cq, 1.f / (TC_SH * TC_SW),
-                        sm + S.H2[b][0], sm + S.H2[b][1], row, cq);
+                        sm + sH2(b, 0), sm + sH2(b, 1), row, cq);
             T2_STAMP(11 + 3 * b);
             if (!FWD && S.po_in_w1 && b == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // old logits landed (barrier follows)
             publish();
@@ -667,8 +732,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             for (int c = 0; c < 2; ++c) {
                 uint4 hi, lo;
                 ovf |= tc_split8(&dl[8 * c], sg_l, hi, lo) ? 8 : 0;
-                *reinterpret_cast<uint4*>(sm + S.DL[b][0] + (c * TC_ROWS + row) * 16) = hi;
-                *reinterpret_cast<uint4*>(sm + S.DL[b][1] + (c * TC_ROWS + row) * 16) = lo;
+                *reinterpret_cast<uint4*>(sm + sDL(b, 0) + (c * TC_ROWS + row) * 16) = hi;
+                *reinterpret_cast<uint4*>(sm + sDL(b, 1) + (c * TC_ROWS + row) * 16) = lo;
             }
         }
         T2_STAMP(17);
@@ -686,8 +751,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             const float sg = b ? sg1 : sg0;
             wait_b(b);      // B1 has consumed H2_b; dz2 = pre * (1 - h2^2) overwrites it
             T2_STAMP(19 + 3 * b);
-            ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H2[b][0],
-                               sm + S.H2[b][1], row, cq) ? 16 : 0;
+            ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + sH2(b, 0),
+                               sm + sH2(b, 1), row, cq) ? 16 : 0;
             T2_STAMP(20 + 3 * b);
             publish();
             T2_STAMP(21 + 3 * b);
@@ -695,7 +760,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         if (S.dl_in_w1 && row0 + TC_ROWS < cr1) {   // both B1 are complete (DL dead) and another tile follows: restore W1
             const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
 #pragma unroll 1
-            for (int i = I.W1[0][0] / 16 + tid; i < I.W2[0][0] / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
+            for (int i = iW1(0, 0) / 16 + tid; i < iW2(0, 0) / 16; i += TC_NT) tc_cp16(sm + 16 * i, img_p + 16 * i);
         }
         // ---- dz1 epilogue -> B5: gW1_b[c][d] (+)= dZ1_b^T X   (column D of X is the constant 1 -> bias gradient) --------
 #pragma unroll 1
@@ -708,8 +773,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 asm volatile("cp.async.commit_group;\n" ::);
             }
             T2_STAMP(25 + 3 * b);
-            ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + S.H1[b][0],
-                               sm + S.H1[b][1], row, cq) ? 32 : 0;
+            ovf |= t2_epi_grad(tmem + tlane + T2_DACC + 64 * b + 16 * cq, 1.f / (sg * TC_SW), sg, sm + sH1(b, 0),
+                               sm + sH1(b, 1), row, cq) ? 32 : 0;
             T2_STAMP(26 + 3 * b);
             publish();
             T2_STAMP(27 + 3 * b);
@@ -719,16 +784,12 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     if (!FWD) {
     if (early_out) {   // B5 of the last tile is in flight: gW2 / gb2 / gWh (complete since B3 / B1) leave meanwhile
         umma::fence_after_sync();
+        if constexpr (!LL) gps = t2_launder(umma::smem_u32(gp));
         write_w2_heads(0);
         write_w2_heads(1);
     }
-    wait_b(0);
-    wait_b(1);
-    T2_STAMP(31);
-    T2_GSTAMP(1);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    if (cq < 2) {   // loss warps: head-bias gradients and loss statistics -> per-warp sums (read after the write-out barrier)
-        double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][24]
+    if (cq < 2) {   // loss warps (also behind B5): head-bias gradients and loss statistics -> per-warp sums, read after the
+        double* redd = reinterpret_cast<double*>(sm + S.red);          // write-out barrier  [8 warps][24]
 #pragma unroll
         for (int i = 0; i < A2; ++i) {
             if constexpr (!GBH_SMEM) {
@@ -742,6 +803,15 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             if (lane == 0) redd[warp * 24 + i] = sx;
         }
     }
+    if (early_out && staged) {   // [W2, bo) of the flat vector (gW2, gb2 of both branches, gWo: ~3/4 of it) is staged: it leaves
+        epi_sync();              // for global memory while B5 is still running
+        copy_out(o.W2 >> 2, o.bo >> 2, tid, TC_NT);
+    }
+    wait_b(0);
+    wait_b(1);
+    T2_STAMP(31);
+    T2_GSTAMP(1);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }   // training only
     }   // epilogue warps
     if (FWD) break;      // inference: no partial gradient, no statistics, no tail
@@ -749,6 +819,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     // ---- late write-out: what B5 produced (gW1, b1); everything else left while B5 was running (or leaves now: clusters) ----
     __syncthreads();
     T2_STAMP(45);
+    if constexpr (!LL) gps = t2_launder(umma::smem_u32(gp));
     if (warp < T2_MMA_WARP) {
         if (!early_out) { write_w2_heads(0); write_w2_heads(1); }
         write_w1(0);
@@ -774,6 +845,12 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         }
     }
     } while (0);
+    if (staged) {   // the rest of the staged partial (gW1 / gb1 of both branches, head biases, gWvo) leaves (all 20 warps copy)
+        __syncthreads();
+        copy_out(0, o.W2 >> 2, tid, T2_NT);
+        copy_out(o.bo >> 2, NPs >> 2, tid, T2_NT);
+        __syncthreads();      // the next step's observations are streamed into H2[1] below
+    }
     if (!LL && cs > 1) {   // in-cluster reduction over distributed shared memory: CTA `crank` adds part `crank` of the cs staged partials
         __syncthreads();
         umma::cluster_sync_all();
@@ -799,6 +876,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     T2_STAMP(33);
     T2_GSTAMP(2);
     prefetched = false;
+    // barrier-A arrival BEFORE the prefetch below is issued: the release then drains the partial's stores only (the copy-out
+    // path ends in a __syncthreads(), so every store of the CTA is ordered before this thread's arrival)
+    const bool arrive_early = !LL && staged && has_tail;
+    if (arrive_early && tid == 0) sgd_tail_arrive_a(a.tail, p);
     if (s + 1 < nsteps && warp < T2_MMA_WARP) {   // the next step's inputs do not depend on the weights: request them now,
         const int mbn = a.mb_perm ? a.mb_perm[(int64_t)p * a.perm_stride + step + 1] : step + 1;   // they land behind the tail
         const int64_t n0 = (int64_t)mbn * a.MB, n1 = min(n0 + a.MB, a.R);
@@ -818,10 +899,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         if constexpr (LL) {
             __syncthreads();      // every thread is past its last use of the shared memory the tail scratches
             tok = sgd_step_tail_ll(a.tail, ts, p, gridDim.y, bx, G, o.NP, step, D, A, reinterpret_cast<float*>(sm + S.X[0]),
-                                   sm + S.H1[0][0], sbase + S.bar + 32, ll_phase, a.dbg_clock);
+                                   sm + sH1(0, 0), sbase + S.bar + 32, ll_phase, a.dbg_clock);
         } else {
             tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                reinterpret_cast<float*>(sm + S.H2[0][0]), a.dbg_clock, ncl);
+                                reinterpret_cast<float*>(sm + sH2(0, 0)), a.dbg_clock, ncl, arrive_early);
         }
         ok = ok && tok;
         ts.b1p *= a.tail.beta1;
@@ -843,10 +924,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 static int g_tc2_cluster = 0;    // 0 = off (default: measured slower), -1 = automatic (largest of 16, 8, 4, 2 that
                                  // divides G and is co-resident), else the forced size
 
-template <int A, bool FWD, bool LL>
+template <int A, bool FWD, bool LL, int DT = 0>
 static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st, int* used_cluster) {
     static bool attr = false;
-    auto kern = fcnet_train_tc2_kernel<A, FWD, LL>;
+    auto kern = fcnet_train_tc2_kernel<A, FWD, LL, DT>;
     if (!attr) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
@@ -909,6 +990,12 @@ int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
             default: set_error("ppo_train_step_tc: ping-pong kernel supports A in {1,2,4,8}"); return DDRL_E_UNSUPPORTED_SHAPE;
         }
     }
+    // the published architectures (policies.ARCHITECTURES: obs width with / without the target velocity, action width)
+#define T2_PUBLISHED(DD, AA) \
+    if (a.D == DD && a.A == AA) return launch_tc2_t<AA, false, false, DD>(a, P, G, smem, st, &g_tc2_last_cluster);
+    T2_PUBLISHED(19, 2) T2_PUBLISHED(20, 2) T2_PUBLISHED(27, 2) T2_PUBLISHED(28, 2) T2_PUBLISHED(35, 2) T2_PUBLISHED(36, 2)
+    T2_PUBLISHED(27, 4) T2_PUBLISHED(28, 4) T2_PUBLISHED(43, 8) T2_PUBLISHED(44, 8)
+#undef T2_PUBLISHED
     switch (a.A) {
         case 1: return launch_tc2_t<1, false, false>(a, P, G, smem, st, &g_tc2_last_cluster);
         case 2: return launch_tc2_t<2, false, false>(a, P, G, smem, st, &g_tc2_last_cluster);
