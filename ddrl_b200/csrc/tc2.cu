@@ -66,6 +66,7 @@ __device__ __noinline__ void t2_epi_tanh(uint32_t taddr, const float* bias, floa
                                          int row, int cq) {
     const float2 k2 = make_float2(inv_in * kT2TanhIn, inv_in * kT2TanhIn), c2 = make_float2(kT2TanhIn, kT2TanhIn),
                  sh = make_float2(TC_SH, TC_SH);
+    // (two x8 TMEM loads, not one x16: measured 0.55 us per step FASTER — the second half's load overlaps the first half's math)
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         float v[8];
@@ -346,16 +347,54 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     // epilogue warps -> MMA warp hand-off: generic smem writes -> async proxy, TMEM reads retired, then a barrier that the
     // MMA warp joins (it issues right behind it).  The MMA warp is a warp of its own ON PURPOSE: when the issuing lane
     // shared a warp with lanes spinning in mbarrier.try_wait, the suspended warp delayed every issue by 0.5-2 us.
+    // Two named barriers (3 and 5) alternate from hand-off to hand-off.  The epilogue warps only ARRIVE (bar.arrive: they do
+    // not wait for their slowest sibling, they go straight on to the other branch's mbarrier); the MMA warps bar.sync and issue.
+    // A warp can run at most one hand-off ahead of the slowest one: the mbarrier it waits for next belongs to MMAs that are
+    // issued only after the previous hand-off has completed — so hand-off k + 2 (same barrier id) never starts before k is over.
+    // publish_sync (everybody waits) is kept where the epilogue warps do need each other: behind the x split / weight image and
+    // behind the loss (the branch gradient scales sgs[] are read by all warps afterwards).
+    unsigned int hand = 0;      // parity of the next hand-off (both roles toggle it in lockstep)
     auto publish = [&]() {
         umma::fence_async_smem();
         umma::fence_before_sync();
-        asm volatile("bar.sync 3, %0;" ::"n"(T2_NT) : "memory");
+        if (hand) asm volatile("bar.arrive 5, %0;" ::"n"(T2_NT) : "memory");
+        else      asm volatile("bar.arrive 3, %0;" ::"n"(T2_NT) : "memory");
+        hand ^= 1u;
+    };
+    auto publish_sync = [&]() {
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        if (hand) asm volatile("bar.sync 5, %0;" ::"n"(T2_NT) : "memory");
+        else      asm volatile("bar.sync 3, %0;" ::"n"(T2_NT) : "memory");
+        hand ^= 1u;
     };
     auto mma_turn = [&]() {    // MMA warp: wait for the epilogue warps' hand-off
-        asm volatile("bar.sync 3, %0;" ::"n"(T2_NT) : "memory");
+        if (hand) asm volatile("bar.sync 5, %0;" ::"n"(T2_NT) : "memory");
+        else      asm volatile("bar.sync 3, %0;" ::"n"(T2_NT) : "memory");
+        hand ^= 1u;
         umma::fence_after_sync();
     };
     auto epi_sync = [&]() { asm volatile("bar.sync 4, %0;" ::"n"(TC_NT) : "memory"); };   // the 16 epilogue warps only
+    // head outputs of branch b: the three product accumulators added up (whole warps: .sync.aligned loads)
+    auto load_heads = [&](int b, float (&out)[16]) {
+        umma::tmem_ld16(tmem + tlane + T2_HOUT + 16 * b, out);
+        if constexpr (A2 <= 8) {
+            uint32_t e0[8], e1[8];
+            umma::tmem_ld8_nowait(tmem + tlane + T2_DACC + 64 * b, e0);
+            umma::tmem_ld8_nowait(tmem + tlane + T2_DACC + 64 * b + 16, e1);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[i] += __uint_as_float(e0[i]) + __uint_as_float(e1[i]);
+        } else {
+            float e[16];
+            umma::tmem_ld16(tmem + tlane + T2_DACC + 64 * b, e);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) out[i] += e[i];
+            umma::tmem_ld16(tmem + tlane + T2_DACC + 64 * b + 16, e);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) out[i] += e[i];
+        }
+    };
 
     // ---- write-out pieces: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
     const float inv = a.hp.inv_global_mb;
@@ -477,12 +516,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 __syncwarp();
             }
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {   // heads: Hout_b[128][16] = H2_b * WoT_b^T   (warp b)
+            for (int b = 0; b < 2; ++b) {   // heads: Hout_b[128][16] = H2_b * WoT_b^T, one product per warp 0-2
                 mma_turn();
                 {
-                    if (mw == b)
-                        tc_gemm_u(tm + T2_HOUT + 16 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, false, sbu + iWoT(b, 0), sbu + iWoT(b, 1),
-                                TC_NO, false, 128, TC_NO, 4, false, 3);
+                    // three independent accumulators (chains of 4 MMAs instead of one of 12; a dependent MMA costs ~100 cycles
+                    // and nothing hides the second head): hi*hi -> Hout_b, hi*lo and lo*hi -> the first 32 columns of Dacc_b,
+                    // which the tanh2(b) epilogue has just consumed and dz2-pre rewrites only after the loss; the readers add them
+                    if (mw < 3)
+                        tc_gemm_mask_u(mw == 0 ? tm + T2_HOUT + 16 * b : tm + T2_DACC + 64 * b + 16 * (mw - 1), (sbu + sH2(b, 0)),
+                                       (sbu + sH2(b, 1)), TC_ROWS, false, sbu + iWoT(b, 0), sbu + iWoT(b, 1), TC_NO, false, 128, TC_NO,
+                                       4, false, 1 << mw);
                     umma::mma_commit_elect(mbar + b);
                 }
                 __syncwarp();
@@ -597,7 +640,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             if (!mbar_wait_parity(imb, img_phase)) ok = false;
             img_phase ^= 1u;
         }
-        publish();
+        publish_sync();
         T2_STAMP(3);
         // ---- F1 (both branches): Dacc_b = X * W1b^T --------------------------------------------------------------
         // ---- tanh epilogue 1 -> F2: Dacc_b = H1_b * W2b -------------------------------------------------------------
@@ -630,7 +673,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         T2_STAMP(16);
         if (FWD) {      // inference epilogue: logits, value, DiagGaussian sample + logp (RLlib tf_action_dist.DiagGaussian)
             float out[16];
-            if (cq < 2) umma::tmem_ld16(tmem + tlane + T2_HOUT + 16 * cq, out);    // .sync.aligned: whole warps
+            if (cq < 2) load_heads(cq, out);
             if (cq < 2 && row < nrows) {
                 const int64_t gr = (int64_t)p * a.R + row0 + row;
                 if (cq == 0) {
@@ -672,7 +715,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         if (cq < 2) {
             const int b = cq;
             float out[16], dl[16];
-            umma::tmem_ld16(tmem + tlane + T2_HOUT + 16 * b, out);
+            load_heads(b, out);
             double s[DDRL_NSTAT];
 #pragma unroll
             for (int i = 0; i < DDRL_NSTAT; ++i) s[i] = 0.0;
@@ -737,11 +780,29 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             }
         }
         T2_STAMP(17);
-        publish();
+        publish_sync();
         T2_STAMP(18);
+        const bool nxt_none = row0 + TC_ROWS >= cr1;
         {   // both branches consumed the staged loss inputs: fetch the next tile's
             const int64_t nxt = row0 + TC_ROWS;
             if (nxt < cr1) prefetch_loss(nxt, (int)min((int64_t)TC_ROWS, cr1 - nxt));
+        }
+        if (nxt_none && cq < 2) {   // last tile: the loss warps add up the head-bias gradients and the loss statistics (per-warp
+            // sums, read after the write-out barrier) while they would otherwise wait for B1 — 5 float64 warp reductions that
+            // used to sit between the last epilogue and the write-out
+            double* redd = reinterpret_cast<double*>(sm + S.red);          // [8 warps][24]
+#pragma unroll
+            for (int i = 0; i < A2; ++i) {
+                if constexpr (!GBH_SMEM) {
+                    const float sx = warp_sum(gbh[i]);
+                    if (lane == 0) redd[warp * 24 + 8 + i] = (double)sx;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const double sx = warp_sum(st[i]);
+                if (lane == 0) redd[warp * 24 + i] = sx;
+            }
         }
         const float sg0 = sgs[0], sg1 = sgs[1];
         // ---- B1: gWh_b[k][o] (+)= H2_b^T DL_b ;  dz2-pre: Dacc_b = DL_b * WoT_b (B MN-major) ---------------------------
@@ -787,21 +848,6 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         if constexpr (!LL) gps = t2_launder(umma::smem_u32(gp));
         write_w2_heads(0);
         write_w2_heads(1);
-    }
-    if (cq < 2) {   // loss warps (also behind B5): head-bias gradients and loss statistics -> per-warp sums, read after the
-        double* redd = reinterpret_cast<double*>(sm + S.red);          // write-out barrier  [8 warps][24]
-#pragma unroll
-        for (int i = 0; i < A2; ++i) {
-            if constexpr (!GBH_SMEM) {
-                const float sx = warp_sum(gbh[i]);
-                if (lane == 0) redd[warp * 24 + 8 + i] = (double)sx;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const double sx = warp_sum(st[i]);
-            if (lane == 0) redd[warp * 24 + i] = sx;
-        }
     }
     if (early_out && staged) {   // [W2, bo) of the flat vector (gW2, gb2 of both branches, gWo: ~3/4 of it) is staged: it leaves
         epi_sync();              // for global memory while B5 is still running
