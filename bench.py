@@ -434,6 +434,8 @@ def main():
 
     if args.tc_variant:
         K.tc_set_variant(args.tc_variant)
+    if os.environ.get("DDRL_TC_CLUSTER"):      # A/B switch: thread-block cluster size of the ping-pong kernel (default off)
+        K.tc_set_cluster(int(os.environ["DDRL_TC_CLUSTER"]))
     from ddrl_b200.modelv2 import fcnet_init_flat      # the product's own GlorotUniformScaled initialiser
     gen = torch.Generator().manual_seed(1234)
     theta0 = torch.stack([fcnet_init_flat(D, 2 * A, gen) for _ in range(P)])
