@@ -131,9 +131,14 @@ __device__ __forceinline__ float4 t2_lds4(uint32_t a) {
     return v;
 }
 
+// (DBG is a template flag of the kernel: the ~50 stamp sites cost ~500 instructions, and the step is sensitive to its code size —
+// the kernel is ~8 000 instructions executed once per step against a 32 KB instruction cache.  Only the bench shape has a DBG
+// instantiation, tests/phase_clock.py.)
 #define T2_STAMP(i)                                                                        \
     do {                                                                                   \
-        if (a.dbg_clock && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg_clock[i] = clock64(); \
+        if constexpr (DBG) {                                                               \
+            if (a.dbg_clock && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg_clock[i] = clock64(); \
+        }                                                                                  \
     } while (0)
 
 // every CTA: globaltimer stamps (comparable across SMs) at a few points of the step -> dbg_clock[64 + 8 * cta + k]
@@ -144,7 +149,9 @@ __device__ __forceinline__ long long t2_gtime() {
 }
 #define T2_GSTAMP(k)                                                                                     \
     do {                                                                                                 \
-        if (a.dbg_clock && threadIdx.x == 0) a.dbg_clock[64 + 8 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = t2_gtime(); \
+        if constexpr (DBG) {                                                                             \
+            if (a.dbg_clock && threadIdx.x == 0) a.dbg_clock[64 + 8 * (blockIdx.y * gridDim.x + blockIdx.x) + (k)] = t2_gtime(); \
+        }                                                                                                \
     } while (0)
 
 // FWD = true: forward-only (inference) mode — the same F1 / tanh / F2 / tanh / heads pipeline over ALL rows of each policy
@@ -155,7 +162,7 @@ __device__ __forceinline__ long long t2_gtime() {
 // architectures, policies.ARCHITECTURES; DT = 0 reads a.D).  Every shared-memory offset, image offset and flat-parameter offset
 // is a function of (D, A): with D in a register ptxas — at the kernel's 96-register cap — re-derived them from D at nearly
 // every use (~20 integer instructions per staged element in the x split and the write-out); as constants they cost nothing.
-template <int A, bool FWD, bool LL, int DT>
+template <int A, bool FWD, bool LL, int DT, bool DBG>
 __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_constant__ TcTrainArgs a) {
     constexpr int A2 = 2 * A;
     T2_STAMP(0);
@@ -216,15 +223,20 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     const bool stage_copy = !FWD && !LL && cs == 1;
     bool staged = false;                                           // this step's partial sits in shared memory (CTA-uniform)
     // staged partial -> global memory, float4 range [i0, i1), full 128-byte lines; `nthr` threads (t0 = 0 .. nthr-1) take part
+    // The staged vector is ROTATED: flat index o.W2 sits at the start of the staging buffers (rot() below), so that the blocks
+    // which are complete first (gW2 / gb2 of the policy branch) land in the part of the buffers that is dead first.
     auto copy_out = [&](int i0, int i1, int t0, int nthr) {
-        const int w2a = o.W2 >> 2, v2a = o.Wv2 >> 2;      // the two swizzled 64 x 64 blocks: 1024 float4 each
-        const uint32_t s4 = t2_launder(umma::smem_u32(gp));
+        const int w2a = o.W2 >> 2, v2a = o.Wv2 >> 2, n4 = NPs >> 2;      // the two swizzled 64 x 64 blocks: 1024 float4 each
+        const uint32_t s4 = t2_launder(umma::smem_u32(gp)), s5 = t2_launder(sbase);      // the two staged halves (see `half1`)
         float4* g4 = reinterpret_cast<float4*>(gpart);
 #pragma unroll 2
         for (int i = i0 + t0; i < i1; i += nthr) {
             const unsigned int r0 = (unsigned int)(i - w2a), r1 = (unsigned int)(i - v2a);
             const int sw = r0 < 1024u ? (int)((r0 >> 4) & 7u) : r1 < 1024u ? (int)((r1 >> 4) & 7u) : 0;
-            g4[i] = t2_lds4(s4 + 16u * (uint32_t)(i ^ sw));      // block starts are multiples of 16 float4: the XOR stays inside the row
+            const int si = i >= w2a ? i - w2a : i + (n4 - w2a);
+            const uint32_t so = 16u * (uint32_t)(si ^ sw);      // block starts are multiples of 16 float4: the XOR stays inside the row
+            const float4 u = t2_lds4(s4 + so), w = t2_lds4(s5 + so);
+            g4[i] = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
         }
     };
 
@@ -398,8 +410,15 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 
     // ---- write-out pieces: TMEM accumulators (M = 64: row m lives in lane 32*(m/16) + m%16) -> flat partial, x 1/minibatch ----
     const float inv = a.hp.inv_global_mb;
-    const int m = 16 * q + lane;            // valid for lane < 16
-    const bool mine = lane < 16;
+    // LL tail: M = 64 accumulators (lanes 0-15 of every quadrant hold rows 16 q ..).  Otherwise the weight-gradient
+    // accumulators are M = 128 with the hi | lo halves of the A operand stacked (tc_gemm_stack_u): lane = row, rows 64-127
+    // (quadrants 2, 3) carry the lo-half products of parameter row m = row - 64.  The two halves are staged in TWO
+    // flat-indexed buffers — half 0 where the partial has always been staged, half 1 at the start of shared memory (the
+    // weight image: dead once the last tile's B4 has completed, reloaded by the next step, and always longer than the
+    // flat vector) — and added by the copy-out, so no thread waits for another one's store.
+    const int m = LL ? 16 * q + lane : (32 * q + lane) & 63;
+    const bool mine = LL ? lane < 16 : true;
+    const bool half1 = !LL && q >= 2;
     // gW2_b, gb2_b, gWh_b are final once B3(b) / B1 have completed, i.e. BEFORE the last B5: they are written while B5 runs.
     // (Not with clusters: the staging buffer of the partial lives in H1, which B5 still reads.)
     const bool early_out = cs == 1;
@@ -467,9 +486,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 #pragma unroll 1
         for (int c8 = cq; c8 < (KX >> 3); c8 += 4) {   // gW1_b[c = m][d]: 8 input features at a time
             uint32_t r2[8], r3[8];
-            const uint32_t base0 = tmem + tlane + T2_GW1 + (gw1_split ? 32 * (2 * b) : 64 * b) + 8 * c8;
+            const uint32_t base0 = tmem + tlane + T2_GW1 + 64 * b + 8 * c8;
             umma::tmem_ld8_nowait(base0, r2);
-            umma::tmem_ld8_nowait(gw1_split ? base0 + 32 : base0, r3);      // second product half (split) or the same again
+            // second column block: the other products (LL: accumulator [2b + 1]; stacked: the X lo columns) or the same again
+            umma::tmem_ld8_nowait(gw1_split ? base0 + (LL ? 32 : KX) : base0, r3);
             umma::tmem_ld_wait();
             if (mine) {
                 // flat order: gW1[d][m] at W1 + 64 d + m, and the bias gradient (column D: the constant-1 input) is row D
@@ -480,6 +500,118 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                     const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
                     if (j <= jmax) put1(i0 + 64 * j, g);
                 }
+            }
+        }
+    };
+
+    // ---- stacked accumulators (everything but the LL tail): the write-out belongs to the FOUR MMA-ISSUE WARPS --------------
+    // They are idle between two hand-offs, and warp 16 + k may read TMEM lanes 32 k .. 32 k + 31 = accumulator rows of ALL
+    // columns.  Each block of the partial is staged as soon as its accumulator is complete, in the gaps of the issue schedule:
+    //   slot 1 (behind the B4(1) issue, once B4(0) has completed)   gW2_0, gb2_0
+    //   slot 2 (behind the B5(0) issue, once B4(1) has completed)   gW2_1, gb2_1, gWh_0, gWh_1   -> bar.arrive 6
+    //   slot 3 (behind the B5(1) issue)                             gW1_0 / gb1_0 (B5(0) done), gW1_1 / gb1_1 (B5(1) done)
+    // so that the 16 epilogue warps go from their last epilogue straight to the copy-out of the early 3/4 of the vector
+    // (bar.sync 6) and only gW1_1 — 1/16 of the accumulator data — is read after the last MMA has completed.  Before, the
+    // epilogue warps did all of it behind their last epilogue: 3.0 us from the last hand-off to the barrier-A arrival.
+    // (Copy-out by the MMA warps themselves, inside the slots, was measured too: the slots overran and delayed B5(1).)
+    const int rotn = NPs - o.W2;      // rotated staging index of flat index 0
+    auto rot = [&](int idx) { return idx >= o.W2 ? idx - o.W2 : idx + rotn; };
+    auto stage_w2 = [&](int b) {      // gW2_b: the 64 columns of this quadrant's 32 rows; gb2_b
+        const float sgb = sgs[b];
+        const float inv_gw2 = inv / (TC_SH * sgb), inv_gw1 = inv / (sgb * TC_SX);
+        const int rowb = rot(b ? o.Wv2 : o.W2) + m * 64, sw = stage_copy ? (m & 7) : 0;
+        const uint32_t t0 = tmem + tlane + T2_GW2 + 64 * b;
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; ++c16) {
+            uint32_t r0[8], r1[8];
+            umma::tmem_ld8_nowait(t0 + 16 * c16, r0);
+            umma::tmem_ld8_nowait(t0 + 16 * c16 + 8, r1);
+            umma::tmem_ld_wait();
+            const int c4 = 4 * c16;
+            put4(rowb + 4 * ((c4 + 0) ^ sw), __uint_as_float(r0[0]) * inv_gw2, __uint_as_float(r0[1]) * inv_gw2,
+                 __uint_as_float(r0[2]) * inv_gw2, __uint_as_float(r0[3]) * inv_gw2);
+            put4(rowb + 4 * ((c4 + 1) ^ sw), __uint_as_float(r0[4]) * inv_gw2, __uint_as_float(r0[5]) * inv_gw2,
+                 __uint_as_float(r0[6]) * inv_gw2, __uint_as_float(r0[7]) * inv_gw2);
+            put4(rowb + 4 * ((c4 + 2) ^ sw), __uint_as_float(r1[0]) * inv_gw2, __uint_as_float(r1[1]) * inv_gw2,
+                 __uint_as_float(r1[2]) * inv_gw2, __uint_as_float(r1[3]) * inv_gw2);
+            put4(rowb + 4 * ((c4 + 3) ^ sw), __uint_as_float(r1[4]) * inv_gw2, __uint_as_float(r1[5]) * inv_gw2,
+                 __uint_as_float(r1[6]) * inv_gw2, __uint_as_float(r1[7]) * inv_gw2);
+        }
+        float v[8];      // gb2_b: column of the constant-1 pad inside its 16-wide window
+        umma::tmem_ld8(tmem + tlane + T2_GB2 + 16 * b + (((D - 8 * ch0) >> 3) << 3), v);
+        const int jsel = (D - 8 * ch0) & 7;
+        const float g = jsel == 0 ? v[0] : jsel == 1 ? v[1] : jsel == 2 ? v[2] : jsel == 3 ? v[3] : jsel == 4 ? v[4]
+                      : jsel == 5 ? v[5] : jsel == 6 ? v[6] : v[7];
+        put1(rot(b ? o.bv2 : o.b2) + m, g * inv_gw1);
+    };
+    auto stage_heads = [&](int b) {   // gWh_b[k = m][o]: the DL hi and DL lo column blocks added
+        const float inv_gwh = inv / (TC_SH * sgs[b]);
+        float w[16], w2[16];
+        umma::tmem_ld16(tmem + tlane + T2_GWH + 32 * b, w);
+        umma::tmem_ld16(tmem + tlane + T2_GWH + 32 * b + 16, w2);
+        if (b == 0) {
+#pragma unroll
+            for (int oo = 0; oo < A2; ++oo) put1(rot(o.Wo) + m * A2 + oo, (w[oo] + w2[oo]) * inv_gwh);
+        } else {
+            put1(rot(o.Wvo) + m, (w[0] + w2[0]) * inv_gwh);
+        }
+    };
+    auto stage_w1 = [&](int b) {      // gW1_b[c = m][d] and gb1_b (column D of X: the constant 1): 8 input features at a time
+        const float inv_gw1 = inv / (sgs[b] * TC_SX);
+#pragma unroll 1
+        for (int c8 = 0; c8 < (KX >> 3); ++c8) {
+            uint32_t r2[8], r3[8];
+            const uint32_t base0 = tmem + tlane + T2_GW1 + 64 * b + 8 * c8;
+            umma::tmem_ld8_nowait(base0, r2);
+            umma::tmem_ld8_nowait(gw1_split ? base0 + KX : base0, r3);      // the X lo column block (2 KX <= 64) or the same again
+            umma::tmem_ld_wait();
+            // flat order: gW1[d][m] at W1 + 64 d + m, bias gradient = row D of the same block (b1 == W1 + 64 D, fc_offsets)
+            const int i0 = rot(b ? o.Wv1 : o.W1) + 512 * c8 + m, jmax = D - 8 * c8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = (__uint_as_float(r2[j]) + (gw1_split ? __uint_as_float(r3[j]) : 0.f)) * inv_gw1;
+                if (j <= jmax) put1(i0 + 64 * j, g);
+            }
+        }
+    };
+    // MMA warps: commit to branch b's mbarrier / wait for the phase committed last (ph0 / ph1 are theirs to keep: they never
+    // call wait_b)
+    auto commit_b = [&](int b) {
+        umma::mma_commit_elect(mbar + b);
+        if (b) ph1 ^= 1u; else ph0 ^= 1u;
+    };
+    auto mma_wait = [&](int b) {
+        ok = umma::mbar_wait(mbar + b, (b ? ph1 : ph0) ^ 1u) && ok;
+        umma::fence_after_sync();
+    };
+
+    // head bias gradients and loss statistics of this CTA: the four per-warp sums of each loss half (redd[], written by the
+    // loss warps of the last tile) -> partial / stat partial.  Threads of warp 0 (half-0 staging); the caller guarantees a
+    // barrier between the loss warps' stores and this.
+    auto bias_stats = [&](int tid) {      // tid: lane of the ONE warp that runs this (a warp of TMEM quadrant 0: half-0 staging)
+        if constexpr (!LL) gps = t2_launder(umma::smem_u32(gp));
+        const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][24]
+        auto sum4 = [&](int w0, int i) { return (redd[w0 * 24 + i] + redd[(w0 + 1) * 24 + i]) + (redd[(w0 + 2) * 24 + i] + redd[(w0 + 3) * 24 + i]); };
+        auto rl = [&](int idx) { return LL ? idx : rot(idx); };
+        if (tid < A2) put1(rl(o.bo) + tid, (float)sum4(0, 8 + tid) * inv);
+        if (tid == A2) put1(rl(o.bvo), (float)sum4(4, 8) * inv);
+        if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) put1(rl(o.NP) + (tid - A2 - 1), 0.f);   // padding floats of the partial
+        if constexpr (!LL) {      // these entries have no lo-half rows: zero in the half-1 staging
+            const uint32_t z = t2_launder(sbase);
+            if (tid < A2) t2_sts(z + 4u * (uint32_t)(rot(o.bo) + tid), 0.f);
+            if (tid == A2) t2_sts(z + 4u * (uint32_t)rot(o.bvo), 0.f);
+            if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) t2_sts(z + 4u * (uint32_t)(rot(o.NP) + (tid - A2 - 1)), 0.f);
+        }
+        if (tid < DDRL_NSTAT && (ll || a.stat_part)) {
+            // stat slots (ddrl_b200.h): 0 -surr, 1 KL, 2 vf, 3 entropy, 4 R, 5 R^2, 6 R-v, 7 (R-v)^2
+            const int w0 = (tid == 0 || tid == 1 || tid == 3) ? 0 : 4;
+            const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
+            const double sv = sum4(w0, idx);
+            if constexpr (LL) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(sv);
+                ll_st2(llp + NPs + 2 * tid, (unsigned int)bits, (unsigned int)(bits >> 32), tag);
+            } else {
+                a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sv;
             }
         }
     };
@@ -500,8 +632,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                 if (mw < 2)
                     tc_gemm_u(tm + T2_DACC + 64 * mw, Xhu, Xlu, TC_ROWS, false, sbu + iW1(mw, 0), sbu + iW1(mw, 1), 64, false,
                             128, 64, KX >> 4, false, 3);
-                umma::mma_commit_elect(mbar);
-                umma::mma_commit_elect(mbar + 1);
+                commit_b(0);
+                commit_b(1);
             }
             __syncwarp();
 #pragma unroll 1
@@ -511,7 +643,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                     if (mw == b)
                         tc_gemm_u(tm + T2_DACC + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, false, sbu + iW2(b, 0), sbu + iW2(b, 1), 64,
                                 true, 128, 64, 4, false, 3);
-                    umma::mma_commit_elect(mbar + b);
+                    commit_b(b);
                 }
                 __syncwarp();
             }
@@ -526,13 +658,13 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                         tc_gemm_mask_u(mw == 0 ? tm + T2_HOUT + 16 * b : tm + T2_DACC + 64 * b + 16 * (mw - 1), (sbu + sH2(b, 0)),
                                        (sbu + sH2(b, 1)), TC_ROWS, false, sbu + iWoT(b, 0), sbu + iWoT(b, 1), TC_NO, false, 128, TC_NO,
                                        4, false, 1 << mw);
-                    umma::mma_commit_elect(mbar + b);
+                    commit_b(b);
                 }
                 __syncwarp();
             }
             if (FWD) continue;      // inference: nothing after the heads
-            mma_turn();      // loss done.  dz2-pre: Dacc_b = DL_b * WoT_b (warp b, first);  gWh_b (+)= H2_b^T DL_b by product
-            {
+            mma_turn();      // loss done.  dz2-pre: Dacc_b = DL_b * WoT_b (warp b);  gWh_b (+)= H2_b^T DL_b
+            if constexpr (LL) {      // (M = 64, split by product into two accumulators)
                 const int b = mw & 1;
                 if (mw < 2) {
                     tc_gemm_u(tm + T2_DACC + 64 * b, (sbu + sDL(b, 0)), (sbu + sDL(b, 1)), TC_ROWS, false, sbu + iWoT(b, 0), sbu + iWoT(b, 1), TC_NO,
@@ -543,8 +675,16 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                     tc_gemm_mask_u(tm + T2_GWH + 16 * (2 * b + 1), (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, (sbu + sDL(b, 0)), (sbu + sDL(b, 1)), TC_ROWS, true, 64,
                                  16, 8, acc, 6);
                 }
-                umma::mma_commit_elect(mbar);
-                umma::mma_commit_elect(mbar + 1);
+                commit_b(0);
+                commit_b(1);
+            } else {                 // stacked (tc_gemm_stack_u): [H2_b hi | lo]^T [DL_b hi | lo], 8 MMAs per branch (warps 2, 3)
+                if (mw < 2)
+                    tc_gemm_u(tm + T2_DACC + 64 * mw, (sbu + sDL(mw, 0)), (sbu + sDL(mw, 1)), TC_ROWS, false, sbu + iWoT(mw, 0), sbu + iWoT(mw, 1), TC_NO,
+                            true, 128, 64, 1, false, 3);
+                else
+                    tc_gemm_stack_u(tm + T2_GWH + 32 * (mw - 2), sbu + sH2(mw - 2, 0), TC_ROWS, sbu + sDL(mw - 2, 0), 0u, TC_ROWS, 2 * TC_NO, 8, acc, 1);
+                commit_b(0);
+                commit_b(1);
             }
             __syncwarp();
 #pragma unroll 1
@@ -554,34 +694,76 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                     if (mw == 0)
                         tc_gemm_u(tm + T2_DACC + 64 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, false, sbu + iW2(b, 0), sbu + iW2(b, 1), 64,
                                 false, 128, 64, 4, false, 3);
-                    else if (mw == (b ? 3 : 1))
-                        tc_gemm_u(tm + T2_GW2 + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, 64, 64, 8, acc, 3);
-                    else if (mw == 2)
-                        tc_gemm_u(tm + T2_GB2 + 16 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, Xhu + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
-                                16, 8, acc, 2);
-                    umma::mma_commit_elect(mbar + b);
+                    else if (mw == (b ? 3 : 1)) {
+                        if constexpr (LL)
+                            tc_gemm_u(tm + T2_GW2 + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, 64, 64, 8, acc, 3);
+                        else      // [H1_b hi | lo]^T dZ2_b hi, then ... dZ2_b lo: 16 dependent MMAs instead of 24
+                            tc_gemm_stack_u(tm + T2_GW2 + 64 * b, sbu + sH1(b, 0), TC_ROWS, sbu + sH2(b, 0), sbu + sH2(b, 1), TC_ROWS, 64, 8, acc, 2);
+                    } else if (mw == 2) {
+                        if constexpr (LL)
+                            tc_gemm_u(tm + T2_GB2 + 16 * b, (sbu + sH2(b, 0)), (sbu + sH2(b, 1)), TC_ROWS, true, Xhu + ch0 * TC_ROWS * 16, 0, TC_ROWS, true, 64,
+                                    16, 8, acc, 2);
+                        else
+                            tc_gemm_stack_u(tm + T2_GB2 + 16 * b, sbu + sH2(b, 0), TC_ROWS, Xhu + ch0 * TC_ROWS * 16, 0u, TC_ROWS, 16, 8, acc, 1);
+                    }
+                    commit_b(b);
                 }
                 __syncwarp();
+            }
+            const bool wout = !LL && early_out && row0 + TC_ROWS >= cr1;      // last tile: stage the partial between the issues
+            if constexpr (!LL) gps = t2_launder(half1 ? sbu : umma::smem_u32(gp));
+            if (wout) {   // slot 1
+                mma_wait(0);
+                stage_w2(0);
+                umma::fence_before_sync();      // TMEM reads retired before the next hand-off barrier
             }
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {   // B5: gW1_b[c][d] (+)= dZ1_b^T X by product (column D of X = constant 1 -> bias gradient)
                 mma_turn();
                 {
-                    if (gw1_split) {
-                        if (mw == 0)
-                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b), (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8,
-                                         acc, 1);
-                        if (mw == 1)
-                            tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b + 1), (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX,
-                                         8, acc, 6);
-                    } else if (mw == b) {
-                        tc_gemm_u(tm + T2_GW1 + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8, acc, 3);
+                    if constexpr (LL) {
+                        if (gw1_split) {
+                            if (mw == 0)
+                                tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b), (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8,
+                                             acc, 1);
+                            if (mw == 1)
+                                tc_gemm_mask_u(tm + T2_GW1 + 32 * (2 * b + 1), (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX,
+                                             8, acc, 6);
+                        } else if (mw == b) {
+                            tc_gemm_u(tm + T2_GW1 + 64 * b, (sbu + sH1(b, 0)), (sbu + sH1(b, 1)), TC_ROWS, true, Xhu, Xlu, TC_ROWS, true, 64, KX, 8, acc, 3);
+                        }
+                    } else if (mw == b) {      // [dZ1_b hi | lo]^T [X hi | lo]: 8 MMAs (2 KX <= 64 columns), else hi and lo in turn: 16
+                        if (gw1_split) tc_gemm_stack_u(tm + T2_GW1 + 64 * b, sbu + sH1(b, 0), TC_ROWS, Xhu, 0u, TC_ROWS, 2 * KX, 8, acc, 1);
+                        else           tc_gemm_stack_u(tm + T2_GW1 + 64 * b, sbu + sH1(b, 0), TC_ROWS, Xhu, Xlu, TC_ROWS, KX, 8, acc, 2);
                     }
-                    umma::mma_commit_elect(mbar + b);
+                    commit_b(b);
                 }
                 __syncwarp();
+                if (wout && b == 0) {   // slot 2
+                    mma_wait(1);
+                    stage_w2(1);
+                    stage_heads(0);
+                    stage_heads(1);
+                    umma::fence_before_sync();
+                    asm volatile("bar.arrive 6, %0;" ::"n"(T2_NT) : "memory");
+                }
             }
             first = false;
+        }
+        if constexpr (!FWD && !LL) {   // slot 3 (clusters: everything — their staging buffer, H1, is read by B5)
+            // head-bias gradients and loss statistics: first MMA warp, while B5(1) runs (cold code executed once per step: ~0.6 us
+            // when it sat on the epilogue warps' path to the barrier-A arrival)
+            if (early_out && staged && mw == 0) bias_stats(lane);
+            gps = t2_launder(half1 ? sbu : umma::smem_u32(gp));
+            mma_wait(0);
+            if (!early_out) {
+                mma_wait(1);
+                stage_w2(0); stage_w2(1); stage_heads(0); stage_heads(1);
+            }
+            stage_w1(0);
+            mma_wait(1);
+            stage_w1(1);
+            umma::fence_before_sync();
         }
     } else {
     // ================= epilogue warps ==========================================================================================
@@ -843,16 +1025,19 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         first = false;
     }
     if (!FWD) {
-    if (early_out) {   // B5 of the last tile is in flight: gW2 / gb2 / gWh (complete since B3 / B1) leave meanwhile
+    if constexpr (LL) {   // B5 of the last tile is in flight: gW2 / gb2 / gWh (complete since B3 / B1) leave meanwhile
         umma::fence_after_sync();
-        if constexpr (!LL) gps = t2_launder(umma::smem_u32(gp));
         write_w2_heads(0);
         write_w2_heads(1);
-    }
-    if (early_out && staged) {   // [W2, bo) of the flat vector (gW2, gb2 of both branches, gWo: ~3/4 of it) is staged: it leaves
-        epi_sync();              // for global memory while B5 is still running
+    } else if (early_out && staged) {
+        // [W2, bo) of the flat vector (gW2, gb2 of both branches, gWo: ~3/4 of it) has been staged by the MMA warps (slots 1, 2)
+        // and leaves for global memory while B5(1) is still running; redd[] (per-warp loss sums, written before every warp's
+        // last hand-offs) is visible to warp 0 behind this barrier as well
+        asm volatile("bar.sync 6, %0;" ::"n"(T2_NT) : "memory");
+        T2_STAMP(46);
         copy_out(o.W2 >> 2, o.bo >> 2, tid, TC_NT);
     }
+    T2_STAMP(47);
     wait_b(0);
     wait_b(1);
     T2_STAMP(31);
@@ -863,42 +1048,36 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     if (FWD) break;      // inference: no partial gradient, no statistics, no tail
 
     // ---- late write-out: what B5 produced (gW1, b1); everything else left while B5 was running (or leaves now: clusters) ----
-    __syncthreads();
+    __syncthreads();      // (stacked accumulators: the MMA warps arrive here once they have staged gW1 / gb1 — slot 3)
     T2_STAMP(45);
-    if constexpr (!LL) gps = t2_launder(umma::smem_u32(gp));
-    if (warp < T2_MMA_WARP) {
-        if (!early_out) { write_w2_heads(0); write_w2_heads(1); }
-        write_w1(0);
-        write_w1(1);
-    }
-    // head bias gradients and stats: add the four per-warp sums of each loss half (written before the write-out barrier)
-    T2_STAMP(32);
-    const double* redd = reinterpret_cast<const double*>(sm + S.red);          // [8 warps][24]
-    auto sum4 = [&](int w0, int i) { return (redd[w0 * 24 + i] + redd[(w0 + 1) * 24 + i]) + (redd[(w0 + 2) * 24 + i] + redd[(w0 + 3) * 24 + i]); };
-    if (tid < A2) put1(o.bo + tid, (float)sum4(0, 8 + tid) * inv);
-    if (tid == A2) put1(o.bvo, (float)sum4(4, 8) * inv);
-    if (tid > A2 && o.NP + (tid - A2 - 1) < NPs) put1(o.NP + (tid - A2 - 1), 0.f);   // padding floats of the partial
-    if (tid < DDRL_NSTAT && (ll || a.stat_part)) {
-        // stat slots (ddrl_b200.h): 0 -surr, 1 KL, 2 vf, 3 entropy, 4 R, 5 R^2, 6 R-v, 7 (R-v)^2
-        const int w0 = (tid == 0 || tid == 1 || tid == 3) ? 0 : 4;
-        const int idx = tid == 0 ? 0 : tid == 1 ? 1 : tid == 3 ? 2 : tid == 2 ? 0 : tid - 3;
-        const double sv = sum4(w0, idx);
-        if constexpr (LL) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(sv);
-            ll_st2(llp + NPs + 2 * tid, (unsigned int)bits, (unsigned int)(bits >> 32), tag);
-        } else {
-            a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = sv;
+    if constexpr (LL) {
+        if (warp < T2_MMA_WARP) {
+            write_w1(0);
+            write_w1(1);
         }
+        if (warp == 0) bias_stats(lane);
+    } else if (!(early_out && staged)) {
+        if (warp == 0) bias_stats(lane);
     }
+    T2_STAMP(32);
     } while (0);
     if (staged) {   // the rest of the staged partial (gW1 / gb1 of both branches, head biases, gWvo) leaves (all 20 warps copy)
-        __syncthreads();
         copy_out(0, o.W2 >> 2, tid, T2_NT);
         copy_out(o.bo >> 2, NPs >> 2, tid, T2_NT);
+        T2_STAMP(48);
         __syncthreads();      // the next step's observations are streamed into H2[1] below
     }
     if (!LL && cs > 1) {   // in-cluster reduction over distributed shared memory: CTA `crank` adds part `crank` of the cs staged partials
         __syncthreads();
+        if (cr1 > cr0) {   // the lo-half rows of the stacked weight-gradient accumulators were staged at the start of shared memory
+            float4* h0 = reinterpret_cast<float4*>(stg);
+            const float4* h1 = reinterpret_cast<const float4*>(sm);
+            for (int i = tid; i < (NPs >> 2); i += T2_NT) {
+                const float4 u = h0[i], w = h1[i];
+                h0[i] = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+            }
+            __syncthreads();
+        }
         umma::cluster_sync_all();
         const int n4 = NPs >> 2, pl4 = (n4 + cs - 1) / cs;          // float4s in the vector / per part
         float4* dstp = reinterpret_cast<float4*>(a.grad_part + ((int64_t)p * G + cid) * NPs);
@@ -916,7 +1095,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
             }
-            dstp[i] = acc;
+            dstp[i < n4 - (o.W2 >> 2) ? i + (o.W2 >> 2) : i - (n4 - (o.W2 >> 2))] = acc;      // staging (rotated) -> flat index
         }
     }
     T2_STAMP(33);
@@ -945,10 +1124,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         if constexpr (LL) {
             __syncthreads();      // every thread is past its last use of the shared memory the tail scratches
             tok = sgd_step_tail_ll(a.tail, ts, p, gridDim.y, bx, G, o.NP, step, D, A, reinterpret_cast<float*>(sm + S.X[0]),
-                                   sm + sH1(0, 0), sbase + S.bar + 32, ll_phase, a.dbg_clock);
+                                   sm + sH1(0, 0), sbase + S.bar + 32, ll_phase, DBG ? a.dbg_clock : nullptr);
         } else {
             tok = sgd_step_tail(a.tail, ts, a.grad_part, a.stat_part, p, gridDim.y, bx, G, o.NP, step, D, A,
-                                reinterpret_cast<float*>(sm + sH2(0, 0)), a.dbg_clock, ncl, arrive_early);
+                                reinterpret_cast<float*>(sm + sH2(0, 0)), DBG ? a.dbg_clock : nullptr, ncl, arrive_early);
         }
         ok = ok && tok;
         ts.b1p *= a.tail.beta1;
@@ -970,10 +1149,10 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
 static int g_tc2_cluster = 0;    // 0 = off (default: measured slower), -1 = automatic (largest of 16, 8, 4, 2 that
                                  // divides G and is co-resident), else the forced size
 
-template <int A, bool FWD, bool LL, int DT = 0>
+template <int A, bool FWD, bool LL, int DT = 0, bool DBG = false>
 static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStream_t st, int* used_cluster) {
     static bool attr = false;
-    auto kern = fcnet_train_tc2_kernel<A, FWD, LL, DT>;
+    auto kern = fcnet_train_tc2_kernel<A, FWD, LL, DT, DBG>;
     if (!attr) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             set_error("ppo_train_step_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1037,6 +1216,7 @@ int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
         }
     }
     // the published architectures (policies.ARCHITECTURES: obs width with / without the target velocity, action width)
+    if (a.dbg_clock && a.D == 19 && a.A == 2) return launch_tc2_t<2, false, false, 19, true>(a, P, G, smem, st, &g_tc2_last_cluster);
 #define T2_PUBLISHED(DD, AA) \
     if (a.D == DD && a.A == AA) return launch_tc2_t<AA, false, false, DD>(a, P, G, smem, st, &g_tc2_last_cluster);
     T2_PUBLISHED(19, 2) T2_PUBLISHED(20, 2) T2_PUBLISHED(27, 2) T2_PUBLISHED(28, 2) T2_PUBLISHED(35, 2) T2_PUBLISHED(36, 2)

@@ -108,6 +108,12 @@ __device__ __forceinline__ void tc_gemm_mask(uint32_t d_tmem, uint32_t a_hi, uin
     }
 }
 
+#ifndef TC_MMA_UNROLL_N
+#define TC_MMA_UNROLL_N 1
+#endif
+constexpr int TC_MMA_UNROLL = TC_MMA_UNROLL_N;   // K-step unrolling of the warp-uniform issue loops: 1 — a dependent MMA takes ~100
+                                                 // cycles anyway, and 26 KB less code measured 0.5 us per step faster (i-cache)
+
 // Warp-uniform variants: the WHOLE warp calls these with warp-uniform arguments (kernel parameters, constants,
 // __shfl_sync(.., 0) results); one elected lane issues each instruction.  ptxas then keeps descriptors and TMEM addresses in
 // uniform registers and emits bare UTCHMMA instructions instead of a per-instruction R2UR waterfall loop
@@ -128,7 +134,7 @@ __device__ __forceinline__ void tc_gemm_mask_u(uint32_t d_tmem, uint32_t a_hi, u
         if (!((pmask >> pr) & 1)) continue;
         uint64_t ad = pr == 2 ? al : ah;
         uint64_t bd = pr == 1 ? bl : bh;
-#pragma unroll 4
+#pragma unroll TC_MMA_UNROLL
         for (int ks = 0; ks < nk; ++ks) {
             umma::mma_f16_elect(d_tmem, ad, bd, idesc, acc);
             acc = 1u;
@@ -141,6 +147,36 @@ __device__ __forceinline__ void tc_gemm_mask_u(uint32_t d_tmem, uint32_t a_hi, u
 __device__ __forceinline__ void tc_gemm_u(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, bool a_mn, uint32_t b_hi,
                                           uint32_t b_lo, int b_rows, bool b_mn, int M, int N, int nk, bool accumulate, int nprod) {
     tc_gemm_mask_u(d_tmem, a_hi, a_lo, a_rows, a_mn, b_hi, b_lo, b_rows, b_mn, M, N, nk, accumulate, nprod == 3 ? 7 : 5);
+}
+
+// Weight-gradient GEMM with the hi | lo halves of the A operand STACKED along M (warp-uniform issue, see above):
+//     D[128][N] (+)= [A_hi | A_lo]^T * B        (A, B MN-major views of chunked buffers: the reduction runs over rows)
+// The lo buffer of every activation follows its hi buffer in shared memory, i.e. it continues the hi buffer's chunk sequence,
+// so ONE M = 128 instruction over the 16 chunks computes A_hi^T B (accumulator rows 0-63) and A_lo^T B (rows 64-127): the
+// M = 64 weight-gradient GEMMs left half of the tensor core's M idle, and their three products were three dependent MMAs per
+// 16 rows of K — a dependent MMA costs ~100 cycles whatever its shape (profiles/r02_umma_issue_bench.txt), so the chain
+// length, not the math, set the time of the backward stages.  B is either the hi | lo pair itself as ONE operand of 2 x cols
+// columns (ngroups == 1, b1 unused: all four products from nk MMAs; the reader adds the two column blocks) or hi and lo one
+// after the other into the same columns (ngroups == 2: 2 nk MMAs).  The reader adds accumulator rows m and m + 64.  The
+// fourth product lo * lo (~2^-22 relative) comes for free and only moves the result closer to the FP32 product.
+__device__ __forceinline__ void tc_gemm_stack_u(uint32_t d_tmem, uint32_t a_hi, int a_rows, uint32_t b0, uint32_t b1, int b_rows,
+                                                int N, int nk, bool accumulate, int ngroups) {
+    const uint32_t idesc = umma::idesc_f16(128, N, true, true);
+    const uint64_t ad0 = umma::desc_mnmajor(a_hi, a_rows);
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        if (g >= ngroups) continue;
+        uint64_t ad = ad0;
+        uint64_t bd = umma::desc_mnmajor(g ? b1 : b0, b_rows);
+#pragma unroll TC_MMA_UNROLL
+        for (int ks = 0; ks < nk; ++ks) {
+            umma::mma_f16_elect(d_tmem, ad, bd, idesc, acc);
+            acc = 1u;
+            ad += 16u;
+            bd += 16u;
+        }
+    }
 }
 
 // split 8 floats (times a power-of-two scale) into fp16 hi / lo 16-byte chunks; returns true on fp16 overflow

@@ -15,8 +15,10 @@ NAMES = {0: "entry", 1: "setup done", 2: "inputs landed", 3: "x split+publish", 
          21: "publish", 22: "B1(1) ready", 23: "dz2(1)", 24: "publish", 25: "B3(0) ready", 26: "dz1(0)", 27: "publish",
          28: "B3(1) ready", 29: "dz1(1)", 30: "publish", 31: "B5 done", 32: "write-out", 33: "stats+dealloc", 34: "tail end", 35: "image issued", 36: "step/perm read", 37: "prefetch fn setup",
          38: "tmem alloc", 39: "inputs issued", 40: "tail: barrier A", 41: "tail: slice reduce", 42: "tail: sq + barrier B",
-         43: "tail: norm + Adam", 44: "tail: ticket", 45: "write-out entry barrier"}
-ORDER = [0, 35, 36, 37, 38, 39] + list(range(1, 32)) + [45, 32, 33, 40, 41, 42, 43, 44, 34]
+         43: "tail: norm + Adam", 44: "tail: ticket", 45: "write-out entry barrier",
+         46: "early TMEM->smem", 47: "early copy-out", 48: "late copy-out", 49: "early copy-out (loop)",
+         50: "copy it0", 51: "copy it1", 52: "copy it2", 53: "copy it3", 54: "copy it4"}
+ORDER = [0, 35, 36, 37, 38, 39] + list(range(1, 31)) + [46, 50, 51, 52, 53, 54, 49, 47, 31, 45, 32, 48, 33, 40, 41, 42, 43, 44, 34]
 
 
 def main():
@@ -63,6 +65,11 @@ def main():
     for k in range(8):
         col = (g[:, k] - base) / 1e3
         print(f"  {names[k]:10s} {col.min():7.2f} {np.median(col):7.2f} {col.max():7.2f}   argmax CTA {int(col.argmax())}")
+    # mean durations between consecutive stamps over all CTAs and the captured iterations (globaltimer ticks are coarse —
+    # 32 ns to 1 us depending on the part — so medians are quantised; means over 128 CTAs x 3 captures are not)
+    allg = np.stack([a[64:64 + 8 * nc].reshape(nc, 8).astype(np.float64) for a in acc])
+    dm = np.diff(allg, axis=2).mean(axis=(0, 1)) / 1e3
+    print("mean phase durations (us): " + "  ".join(f"{names[k + 1]} {dm[k]:.3f}" for k in range(7)) + f"  | step {dm.sum():.3f}")
     d = (g[:, 1] - g[:, 0]) / 1e3
     print("main loop duration per CTA: min %.2f med %.2f max %.2f; slowest CTAs %s" % (d.min(), np.median(d), d.max(), np.argsort(-d)[:8].tolist()))
     d2 = (g[:, 2] - g[:, 1]) / 1e3
