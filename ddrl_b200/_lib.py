@@ -31,7 +31,7 @@ class SgdTail(C.Structure):
                 ("step_stats", C.c_void_p), ("step_ctr", C.c_void_p), ("barrier_ws", C.c_void_p), ("sq_ws", C.c_void_p),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_clip", C.c_float),
                 ("status", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32), ("seq", C.c_void_p),
-                ("peer_x", C.c_void_p * MAX_RANKS), ("nsteps", C.c_int32), ("ll_ws", C.c_void_p)]
+                ("peer_x", C.c_void_p * MAX_RANKS), ("nsteps", C.c_int32), ("ll_ws", C.c_void_p), ("grad_acc", C.c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/ddrl_b200.h one to one (tests check every symbol).

@@ -686,6 +686,7 @@ extern "C" int ddrl_ppo_train_step(const float* theta, const float* img, const f
         if (rc != DDRL_OK) return rc;
         DDRL_REQUIRE(tail->nsteps <= 1, DDRL_E_UNSUPPORTED_SHAPE, "ppo_train_step: nsteps > 1 is not supported by the FP32 kernel");
         a.tail = *tail;
+        a.tail.grad_acc = nullptr;      // (accumulation vector: ping-pong tcgen05 kernel only; this kernel writes per-CTA partials)
     }
     const FcSmem L = fc_smem(D, A, false, true);
     const size_t smem = (size_t)L.total * sizeof(float);

@@ -752,6 +752,7 @@ extern "C" int ddrl_graphnet_train_step_tc(const float* theta, const int32_t* no
         DDRL_REQUIRE(!tail->fcnet_img && !tail->fcnet_tc_img && !tail->ll_ws, DDRL_E_BADARG,
                      "graphnet_train_step_tc: the tail must not carry FCNet weight images / an LL workspace");
         a.tail = *tail;
+        a.tail.grad_acc = nullptr;      // (accumulation vector: FCNet ping-pong kernel only; this kernel writes per-CTA partials)
     }
     const size_t smem = (size_t)gnt_smem().total;
     static bool attr = false;

@@ -138,7 +138,11 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     // ---- slice reduce over the G partials --------------------------------------------------------------------------
     const int S = sgd_slice_len(NP, G), j0 = bx * S, j1 = min(NPs, j0 + S);
     const int ncol4 = max(0, (j1 - j0) >> 2);
-    const int ngrp = ncol4 >= nt ? 1 : max(1, min(min(8, npart), nt / max(ncol4, 1)));
+    // t.grad_acc: the partials of the policy were ADDED into one vector at L2 (red.global.add, ping-pong kernel): the slice is
+    // read once (and zeroed for the next step) instead of being summed over npart partials
+    const bool use_acc = t.grad_acc != nullptr;
+    float* acc_p = use_acc ? t.grad_acc + (int64_t)p * NPs + j0 : nullptr;
+    const int ngrp = (use_acc || ncol4 >= nt) ? 1 : max(1, min(min(8, npart), nt / max(ncol4, 1)));
     const int cpp = nt / ngrp;                  // float4 columns per pass
     const unsigned int seq = ts.seq;
     const unsigned long long want = (unsigned long long)(seq + 1u) << 32;     // flag half of the LL words of this step
@@ -151,7 +155,7 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
     float gval = 0.f;
     for (int c0 = 0; c0 < ncol4; c0 += cpp) {
         const int g = tid / cpp, c = c0 + (tid - g * cpp);
-        if (g < ngrp && c < ncol4) {
+        if (!use_acc && g < ngrp && c < ncol4) {
             const float4* src = reinterpret_cast<const float4*>(grad_part + (int64_t)p * G * NPs + j0) + c;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             const int64_t pstride = (int64_t)ngrp * (NPs >> 2);
@@ -166,16 +170,22 @@ __device__ __forceinline__ bool sgd_step_tail(const SgdTail& t, const TailStep& 
             }
             scr[g * cpp + (c - c0)] = acc;
         }
-        __syncthreads();
+        if (!use_acc) __syncthreads();
         const int nf = 4 * min(cpp, ncol4 - c0);
         for (int fb = 0; fb < nf; fb += nt) {      // every thread runs the same trip count: the shuffle below is warp-wide
             const int f = fb + tid;
             const bool act = f < nf;
             const int col = f >> 2, e = f & 3;
             float s = 0.f;
-            if (act)
-                for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * cpp + col])[e];
             const int jj = 4 * c0 + f;           // offset inside the slice
+            if (act) {
+                if (use_acc) {
+                    s = __ldcg(acc_p + jj);
+                    acc_p[jj] = 0.f;             // re-armed for the next step (ordered before this CTA's barrier-C arrival / ticket)
+                } else {
+                    for (int gg = 0; gg < ngrp; ++gg) s += reinterpret_cast<const float*>(&scr[gg * cpp + col])[e];
+                }
+            }
             if (W > 1) {
                 // push to every rank's exchange buffer (own copy included).  Two neighbouring elements travel as ONE 16-byte
                 // store {value, flag, value, flag} issued by the even lane (NCCL-LL line: each 8-byte half is self-validating,

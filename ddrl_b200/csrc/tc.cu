@@ -732,6 +732,7 @@ extern "C" int ddrl_ppo_train_step_tc(const void* tc_img_p, const float* obs, co
         DDRL_CHECK_LAUNCH("ppo_train_step_tc");
         return DDRL_OK;
     }
+    a.tail.grad_acc = nullptr;      // the branch-sequential kernel writes per-CTA partials
     switch (A) {
         case 1: rc = launch_tc<1>(a, P, ctas_per_policy, smem, (cudaStream_t)stream); break;
         case 2: rc = launch_tc<2>(a, P, ctas_per_policy, smem, (cudaStream_t)stream); break;

@@ -222,21 +222,32 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     float* gp = LL ? gpart : (cs > 1 ? stg : reinterpret_cast<float*>(sm + sH2(0, 0)));
     const bool stage_copy = !FWD && !LL && cs == 1;
     bool staged = false;                                           // this step's partial sits in shared memory (CTA-uniform)
+    const bool acc_mode = stage_copy && a.tail.theta != nullptr && a.tail.grad_acc != nullptr;
     // staged partial -> global memory, float4 range [i0, i1), full 128-byte lines; `nthr` threads (t0 = 0 .. nthr-1) take part
     // The staged vector is ROTATED: flat index o.W2 sits at the start of the staging buffers (rot() below), so that the blocks
     // which are complete first (gW2 / gb2 of the policy branch) land in the part of the buffers that is dead first.
     auto copy_out = [&](int i0, int i1, int t0, int nthr) {
         const int w2a = o.W2 >> 2, v2a = o.Wv2 >> 2, n4 = NPs >> 2;      // the two swizzled 64 x 64 blocks: 1024 float4 each
         const uint32_t s4 = t2_launder(umma::smem_u32(gp)), s5 = t2_launder(sbase);      // the two staged halves (see `half1`)
-        float4* g4 = reinterpret_cast<float4*>(gpart);
+        // a.tail.grad_acc: ADD into the policy's one accumulation vector at L2 (sgd_tail.cuh) instead of storing this CTA's own
+        // partial.  Every CTA starts at a different place of the range so that the G CTAs of a policy do not walk the same
+        // addresses (= the same L2 slices' atomic units) in lockstep.
+        float4* g4 = reinterpret_cast<float4*>(acc_mode ? a.tail.grad_acc + (int64_t)p * NPs : gpart);
+        const int span = i1 - i0, shift = acc_mode ? (int)(((int64_t)span * bx) / G) : 0;
 #pragma unroll 2
-        for (int i = i0 + t0; i < i1; i += nthr) {
+        for (int k = t0; k < span; k += nthr) {
+            int i = i0 + k + shift;
+            if (i >= i1) i -= span;
             const unsigned int r0 = (unsigned int)(i - w2a), r1 = (unsigned int)(i - v2a);
             const int sw = r0 < 1024u ? (int)((r0 >> 4) & 7u) : r1 < 1024u ? (int)((r1 >> 4) & 7u) : 0;
             const int si = i >= w2a ? i - w2a : i + (n4 - w2a);
             const uint32_t so = 16u * (uint32_t)(si ^ sw);      // block starts are multiples of 16 float4: the XOR stays inside the row
             const float4 u = t2_lds4(s4 + so), w = t2_lds4(s5 + so);
-            g4[i] = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+            if (acc_mode)
+                asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g4 + i), "f"(u.x + w.x), "f"(u.y + w.y),
+                             "f"(u.z + w.z), "f"(u.w + w.w) : "memory");
+            else
+                g4[i] = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
         }
     };
 
@@ -335,7 +346,8 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             for (int i = tid; i < (LLW >> 1); i += T2_NT) ll_st2(llp + 2 * i, 0u, 0u, tag);
         } else {
             float* z = stage_copy ? gpart : gp;      // (already coalesced: straight to global memory)
-            for (int i = tid; i < NPs; i += T2_NT) z[i] = 0.f;
+            if (!acc_mode)                           // (accumulation vector: nothing to add)
+                for (int i = tid; i < NPs; i += T2_NT) z[i] = 0.f;
             if (tid < DDRL_NSTAT && a.stat_part) a.stat_part[((int64_t)p * G + bx) * DDRL_NSTAT + tid] = 0.0;
         }
         break;
@@ -1202,7 +1214,9 @@ static int launch_tc2_t(const TcTrainArgs& a, int P, int G, size_t smem, cudaStr
 
 static int g_tc2_last_cluster = 0;
 
-int launch_tc2(const TcTrainArgs& a, int P, int G, cudaStream_t st) {
+int launch_tc2(const TcTrainArgs& a_in, int P, int G, cudaStream_t st) {
+    TcTrainArgs a = a_in;
+    if (g_tc2_cluster != 0 || a.tail.ll_ws) a.tail.grad_acc = nullptr;   // the accumulation vector is the plain staged path's
     const size_t smem = (size_t)tc2_smem(a.D, a.A).total;
     // LL tail: fused tail with an LL workspace, no thread-block clusters requested, one slice element per thread
     const bool ll = a.tail.theta && a.tail.ll_ws && g_tc2_cluster == 0 && sgd_slice_len(fc_offsets(a.D, a.A).NP, G) <= T2_NT;

@@ -634,7 +634,7 @@ def sgd_ll_words(P: int, ctas_per_policy: int, D: int, A: int) -> int:
 
 
 def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, beta2, eps, grad_clip, gnorm_out=None, img=None,
-                  tc_img=None, step_stats=None, step_ctr=None, status=None, ll_ws=None) -> SgdTail:
+                  tc_img=None, step_stats=None, step_ctr=None, status=None, ll_ws=None, grad_acc=None) -> SgdTail:
     """Fused grad-reduce + [peer all-reduce] + clip + Adam tail of the SGD step (see ddrl_sgd_tail in ddrl_b200.h).
     The caller keeps the tensors alive; barrier_ws must be zero-initialised int32 [4*P + 4].  For world > 1 let
     ``peer.PeerExchange.fill`` add the rank / peer-buffer fields."""
@@ -649,6 +649,7 @@ def make_sgd_tail(theta, m, v, beta_pow, grad, barrier_ws, sq_ws, lr, beta1, bet
     t.status = _p(status, torch.int32, "status")
     t.world, t.rank, t.nsteps = 1, 0, 1
     t.ll_ws = _p(ll_ws, torch.int64, "ll_ws")
+    t.grad_acc = _p(grad_acc, f32, "grad_acc")
     return t
 
 

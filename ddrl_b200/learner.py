@@ -112,7 +112,7 @@ class FCNetLearner(_LearnerBase):
     def __init__(self, P: int, D: int, A: int, cfg: PPOConfig, device="cuda", theta: Optional[torch.Tensor] = None,
                  use_graph: bool = True, ctas_per_policy: Optional[int] = None, mode: str = "tc", fuse_tail: bool = True,
                  persistent: bool = True, tc_forward: bool = True, ll_tail: bool = False, vf_share_layers: bool = False,
-                 free_log_std: bool = False):
+                 free_log_std: bool = False, atomic_reduce: bool = True):
         """mode: "tc"   = tensor-core (tcgen05) SGD step, fp16 hi/lo operand split (gradients within 5e-5 of scale);
                  "fp32" = FP32-FMA SGD step (1e-5 parity).  Inference / GAE / Adam are FP32 in both modes.
         vf_share_layers / free_log_std: the reference model's optional layouts (models/fcnet_glorot_uniform_init.py:30-36,
@@ -156,6 +156,12 @@ class FCNetLearner(_LearnerBase):
         # 30.3 us per step against 29.4 us for the three-barrier tail (the 8-byte words double the early write-out), so
         # it is OFF by default; DDRL_LL_TAIL=1 switches it on for A/B timing
         self.ll_tail = (ll_tail or os.environ.get("DDRL_LL_TAIL", "0") == "1") and mode == "tc"
+        # the CTAs of a policy ADD their partial gradients into one vector at L2 (red.global.add.v4.f32) instead of writing G
+        # partials that every slice owner reads back: 1.4 us per step faster on the bench workload, but the order of the float
+        # additions is no longer fixed (last-bit differences from run to run; the ranks of one run still end bit-identical).
+        # atomic_reduce=False / DDRL_FIXED_ORDER=1 keeps the fixed-order, bit-reproducible reduction
+        self.atomic_reduce = (atomic_reduce and os.environ.get("DDRL_FIXED_ORDER", "0") != "1" and mode == "tc"
+                              and not self.ll_tail)
         self.D, self.A = D, A
         dev = self.device
         self.filt_n = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -243,7 +249,7 @@ class FCNetLearner(_LearnerBase):
                                    c.beta1, c.beta2, c.adam_eps, c.grad_clip, self.gnorm,
                                    img=self.img if self.mode == "fp32" else None, tc_img=self.tc_img,
                                    step_stats=b["step_stats"], step_ctr=self.step_ctr, status=self.tc_status,
-                                   ll_ws=b.get("tail_ll"))
+                                   ll_ws=b.get("tail_ll"), grad_acc=b.get("tail_acc"))
             tail.nsteps = nsteps
             if self.world > 1:
                 self._peer_exchange(G).fill(tail)
@@ -405,6 +411,8 @@ class FCNetLearner(_LearnerBase):
             # LL workspace: same lifetime as tail_bar (its tags are the step count kept there)
             b["tail_ll"] = (torch.zeros(K.sgd_ll_words(P, G, self.D, self.A), dtype=torch.int64, device=self.device)
                             if self.ll_tail and K.tc_pingpong_eligible(self.D, self.A) else None)
+            b["tail_acc"] = (torch.zeros(P, K.part_stride(self.NP), dtype=torch.float32, device=self.device)
+                             if self.atomic_reduce and K.tc_pingpong_eligible(self.D, self.A) else None)
             self._graph = None
         b["mb_perm"].copy_(perms.reshape(P, steps))
         self.step_ctr.zero_()

@@ -218,6 +218,12 @@ typedef struct {
                                 * gradients and updated weights between CTAs as self-validating {payload, step tag} words instead of
                                 * barrier-protected arrays (one barrier-free tail per step; csrc/sgd_tail.cuh).  Must share the lifetime
                                 * of barrier_ws (the tags are the step count kept there). */
+    float* grad_acc;           /* NULL, or [P][NP rounded up to 4] ZERO-initialised floats: the ping-pong kernel then ADDS its per-CTA
+                                * partial gradients into this one vector per policy (red.global.add.v4.f32 at L2) instead of writing
+                                * ctas_per_policy partials that every slice owner re-reads — per step 45 KB instead of 1.4 MB read back per
+                                * policy; the slice owner reads its slice once and zeroes it again.  The order of the float additions is
+                                * then NOT fixed: results vary from run to run in the last bits (ranks of one run still end bit-identical,
+                                * the exchange adds in rank order).  NULL keeps the fixed-order reduction (bit-reproducible). */
 } ddrl_sgd_tail;
 
 /* 64-bit words of ddrl_sgd_tail.ll_ws for P policies of an FCNet (D, A) stepped by ctas_per_policy CTAs each. */

@@ -282,7 +282,8 @@ def _oracle_iteration(b_np, theta0, cfg, O, dtype, perms, shuffle, T, C, dones, 
     return pols, out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile", "tc-ll", "tc-llmt"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "tc-fixed", "fp32-3k", "tc-3k", "tc-1step", "tc-cluster", "tc-multitile",
+                                  "tc-multitile-fixed", "tc-ll", "tc-llmt"])
 @pytest.mark.parametrize("arch,use_graph,use_shuffle", [("FullyDecentral", True, True), ("TwoSides", False, False),
                                                         ("Centralized", True, False)])
 def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mode):
@@ -290,7 +291,11 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
     "-3k" = the three-kernel SGD step (train, grad_reduce, clip_adam) instead of the fused tail; "-1step" = one launch
     per optimizer step instead of one persistent launch per epoch.  "-ll" = the opt-in LL tail (partial gradients as
     self-validating words pulled by TMA bulk copies, csrc/sgd_tail.cuh) at 32 CTAs per policy; "-llmt" = the same with two
-    128-row tiles per CTA (24 CTAs per policy x 136 rows)."""
+    128-row tiles per CTA (24 CTAs per policy x 136 rows).  "-fixed" = the fixed-order reduction of the per-CTA partial
+    gradients (atomic_reduce=False) instead of the default accumulation vector at L2 (red.global.add)."""
+    fixed = mode.endswith("-fixed")
+    if fixed:
+        mode = mode[:-len("-fixed")]
     fuse = not mode.endswith("-3k")
     llmt = mode.endswith("-llmt")
     ll = mode.endswith("-ll") or llmt
@@ -322,7 +327,7 @@ def test_full_learner_iteration_matches_oracle(arch, use_graph, use_shuffle, mod
 
     L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), use_graph=use_graph, mode=mode, fuse_tail=fuse,
                      persistent=persistent, ctas_per_policy=8 if cluster else 2 if multitile else 24 if llmt else None,
-                     ll_tail=ll)
+                     ll_tail=ll, atomic_reduce=not fixed)
     if cluster:
         from ddrl_b200 import kernels as K
         K.tc_set_cluster(-1)
@@ -430,9 +435,12 @@ def test_tensor_core_inference_forward_matches_oracle(arch, R):
     assert torch.equal(vb, out["value"])
 
 
-def test_graph_replayed_iterations_are_bit_identical_to_eager_ones():
+@pytest.mark.parametrize("atomic", [False, True])
+def test_graph_replayed_iterations_are_bit_identical_to_eager_ones(atomic):
     """use_graph=True replays the preparation phase (filter, inference, GAE, shuffle) from a CUDA graph keyed by the input
-    buffers; three consecutive iterations must leave exactly the state the eager learner reaches."""
+    buffers; three consecutive iterations must leave exactly the state the eager learner reaches — bit for bit with the
+    fixed-order reduction of the partial gradients (atomic_reduce=False); with the default accumulation vector at L2
+    (red.global.add: the order of the float additions is not fixed) to round-off."""
     from ddrl_b200.config import PPOConfig
     from ddrl_b200.learner import FCNetLearner
     arch, T, C = "FullyDecentral", 16, 32
@@ -451,12 +459,19 @@ def test_graph_replayed_iterations_are_bit_identical_to_eager_ones():
     out = []
     for graph in (True, False):
         L = FCNetLearner(P, D, A, PPOConfig(num_sgd_iter=2, sgd_minibatch_size=128), "cuda", theta=torch.from_numpy(theta0),
-                         use_graph=graph)
+                         use_graph=graph, atomic_reduce=atomic)
         stats = [L.learn_on_rollout(raw, boot, rewards, dones, eps, perms, shuffle) for _ in range(3)]
         torch.cuda.synchronize()
         if graph:
             assert L._prep_graphs is not None and len(L._prep_graphs) == 1, getattr(L, "graph_error", None)
         out.append((L.theta.clone(), L.m.clone(), L.v.clone(), L.filt_M.clone(), L.filt_n.clone(), stats))
+    if atomic:
+        assert torch.equal(out[0][3], out[1][3]) and torch.equal(out[0][4], out[1][4])      # filter state: no atomics involved
+        # 24 Adam steps apart, element by element: Adam turns last-bit gradient differences into O(lr) differences only for
+        # elements whose gradient is at round-off level, so compare against the size of the update
+        upd = (out[1][0] - torch.from_numpy(theta0).cuda()).abs().max().item()
+        assert (out[0][0] - out[1][0]).abs().max().item() < 2e-2 * upd
+        return
     for x, y in zip(out[0][:5], out[1][:5]):
         assert torch.equal(x, y)
     assert out[0][5] == out[1][5]

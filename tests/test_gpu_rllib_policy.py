@@ -36,7 +36,8 @@ def test_learn_on_batch_is_the_sgd_phase_of_learn_on_rollout(mode):
     shuffle = np.stack([rng.permutation(R) for _ in range(P)]).astype(np.int32)
 
     def learner():
-        L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), mode=mode)
+        # (fixed-order reduction of the partial gradients: the two learners are compared bit for bit)
+        L = FCNetLearner(P, D, A, cfg, "cuda", theta=torch.from_numpy(theta0), mode=mode, atomic_reduce=False)
         L.filt_n.copy_(torch.tensor([f[0] for f in filt]))
         L.filt_M.copy_(torch.from_numpy(np.stack([f[1] for f in filt])))
         L.filt_S.copy_(torch.from_numpy(np.stack([f[2] for f in filt])))
