@@ -644,6 +644,9 @@ def main():
             "impl_detail": {"cuda_graph_prepare_phase": bool(L.use_graph and L._prep_graphs), "sgd_kernel": args.mode,
                             "kernels_per_sgd_step": per_sgd, "persistent_sgd_launch": bool(L._persistent_steps(G_)),
                             "ctas_per_policy": G_, "cluster_size": K.tc_last_cluster() if args.mode == "tc" else 0,
+                            "partial_gradient_reduce": ("L2 accumulation vector (red.global.add.v4.f32; float addition order not fixed)"
+                                                        if getattr(L, "atomic_reduce", False) and args.mode == "tc"
+                                                        else "fixed-order sum of per-CTA partials"),
                             "bytes_per_rollout_set": int(bytes_per_set)},
             "ranks_identical": ranks_identical,
             "clocks": clk,
