@@ -29,7 +29,9 @@ void count_launch(int n) { __atomic_add_fetch(&g_launches, (int64_t)n, __ATOMIC_
 // =================================================================================================
 constexpr int FT = 256;        // threads
 constexpr int FROWS = 128;     // rows staged in shared memory per sub-chunk
-constexpr int FMAXBLK = 64;    // partials per policy
+constexpr int FMAXBLK = 256;   // partials per policy (64 until round 2: 16 dependent sub-chunks per CTA made the kernel latency bound,
+                               // 75 us for 40 MB; the merge below is two-level so that its serial chain stays short)
+constexpr int FMG = 16;        // merge groups: group g folds a contiguous run of partials, then the groups are folded in order
 constexpr int FMAXCOL = DDRL_MAX_OBS / 8;  // columns per warp
 
 struct Stat { double n, mean, m2; };
@@ -91,19 +93,31 @@ __global__ void __launch_bounds__(FT) filter_partial_kernel(const T* __restrict_
     }
 }
 
-__global__ void filter_merge_kernel(const double* __restrict__ part, int nblk, int D, int64_t R, int64_t* n_io,
-                                    double* M, double* S, double* norm) {
-    const int p = blockIdx.x, d = threadIdx.x;
+__global__ void __launch_bounds__(FMG * 64) filter_merge_kernel(const double* __restrict__ part, int nblk, int D, int64_t R,
+                                                                  int64_t* n_io, double* M, double* S, double* norm) {
+    // thread (g, d): feature d, merge group g.  Fixed order: inside a group the partials in index order, then the groups in
+    // order, then the running state — bit-reproducible; every thread's loads are independent of its merge chain's results, so
+    // they are issued ahead (the one-level loop of round 1 waited for an L2 round trip per partial: 50 us for 64 partials).
+    __shared__ Stat grp[FMG][64];
+    const int p = blockIdx.x, d = threadIdx.x & 63, g = threadIdx.x >> 6;
     const int64_t n_old = n_io[p];
     const int64_t n_new = n_old + R;
-    __syncthreads();  // every thread has read the old count before thread 0 overwrites it
-    if (d == 0) n_io[p] = n_new;
-    if (d >= D) return;
+    const int L = (nblk + FMG - 1) / FMG, i0 = g * L, i1 = min(nblk, i0 + L);
     Stat b{0.0, 0.0, 0.0};
-    for (int i = 0; i < nblk; ++i) {
-        const double* o = part + (((int64_t)p * nblk + i) * D + d) * 3;
-        chan_merge(b, Stat{o[0], o[1], o[2]});
+    if (d < D) {
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+            const double* o = part + (((int64_t)p * nblk + i) * D + d) * 3;
+            const Stat c{__ldg(o), __ldg(o + 1), __ldg(o + 2)};
+            if (i == i0) b = c; else chan_merge(b, c);
+        }
     }
+    grp[g][d] = b;
+    __syncthreads();  // also: every thread has read the old count before thread 0 overwrites it
+    if (threadIdx.x == 0) n_io[p] = n_new;
+    if (g != 0 || d >= D) return;
+    for (int k = 1; k < FMG; ++k)
+        if (grp[k][d].n != 0.0) chan_merge(b, grp[k][d]);      // (an empty group must not even round-trip (n mean) / n)
     Stat a{(double)n_old, M[p * D + d], S[p * D + d]};
     chan_merge(a, b);
     M[p * D + d] = a.mean;
@@ -598,7 +612,7 @@ extern "C" int ddrl_filter_merge(const void* parts, int nparts, int P, int D, in
     DDRL_REQUIRE(parts && n && M && S && norm && P >= 1 && nparts >= 0 && R_total >= 0, DDRL_E_BADARG,
                  "filter_merge: null pointer or bad shape");
     DDRL_REQUIRE(D >= 1 && D <= DDRL_MAX_OBS, DDRL_E_UNSUPPORTED_SHAPE, "filter_merge: D=%d > %d", D, DDRL_MAX_OBS);
-    filter_merge_kernel<<<P, 64, 0, (cudaStream_t)stream>>>((const double*)parts, nparts, D, R_total, n, M, S, norm);
+    filter_merge_kernel<<<P, FMG * 64, 0, (cudaStream_t)stream>>>((const double*)parts, nparts, D, R_total, n, M, S, norm);
     DDRL_CHECK_LAUNCH("filter_merge");
     return DDRL_OK;
 }

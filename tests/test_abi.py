@@ -56,8 +56,8 @@ def test_pure_host_entry_points():
     assert lib.ddrl_fcnet_num_params(65, 2) == -2 and lib.ddrl_fcnet_num_params(19, 9) == -2   # DDRL_E_UNSUPPORTED_SHAPE
     assert lib.ddrl_graphnet_num_params(4) == 14532 + 14337
     assert lib.ddrl_graphnet_num_params(3) == -2
-    assert lib.ddrl_filter_num_partials(1) == 1 and lib.ddrl_filter_num_partials(131072) == 64
-    assert lib.ddrl_filter_ws_bytes(4, 131072, 19) == 4 * 64 * 19 * 3 * 8
+    assert lib.ddrl_filter_num_partials(1) == 1 and lib.ddrl_filter_num_partials(131072) == 256
+    assert lib.ddrl_filter_ws_bytes(4, 131072, 19) == 4 * 256 * 19 * 3 * 8
     assert lib.ddrl_gae_ws_bytes(4, 4096) == 4 * 16 * 2 * 8
     assert isinstance(lib.ddrl_launch_count(), int)
 
