@@ -305,6 +305,10 @@ def time_fcnet(arch, envs, nb, mode, steps, warmup, sets=2):
     def step(i):
         r = rs[i % sets]
         return L.learn_on_rollout(r["raw"], r["boot"], r["rewards"], r["dones"], r["eps"], r["perms"], r["shuffle"])
+    # the first call runs the preparation phase eagerly, every later call captures the CUDA graph of its rollout set on first
+    # sight: sets + 1 untimed calls leave no capture inside the timed region (with warmup = sets the third call — the first
+    # TIMED one — used to capture set 0: several ms in a 3-step measurement)
+    warmup = max(warmup, sets + 1)
     for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
