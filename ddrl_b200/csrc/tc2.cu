@@ -15,10 +15,17 @@
 //   * the two PPO-loss halves (policy part on warps 0-3, value part on warps 4-7) run concurrently.
 //   * H1/H2 of both branches live in shared memory (128 KB); DL, the observation staging and (A = 8) the old logits reuse
 //     space that is dead at the time (fcnet_tc_layout.cuh): D <= 46, every published architecture (tc2_eligible).
+//   * the weight-gradient GEMMs stack the hi | lo halves of their A operand along M (tc_gemm_stack_u: one M = 128 MMA gives
+//     A_hi^T B and A_lo^T B; dependent chains of 16 / 8 instead of 24 / 16 MMAs), and the four MMA-issue warps — idle between
+//     two hand-offs — read the finished accumulators out of TMEM and stage the partial gradient in shared memory in the gaps
+//     of their issue schedule; the epilogue warps copy it out (two staging halves added on the way) while the last MMAs run.
 //   * the launch runs a.tail.nsteps consecutive optimizer steps: per step the fused tail (sgd_tail.cuh) reduces the
-//     partial gradients over the CTAs of a policy, all-reduces them over NVLink peer memory (world > 1), clips and applies
-//     Adam; the CTAs of a policy meet at a barrier before they reload the updated weight image.  The next step's inputs are
-//     requested behind the tail; gW2 / gb2 / gWh leave for the partial while the last B5 is still running.
+//     partial gradients over the CTAs of a policy (by default they are ADDED into one vector per policy at L2 by the
+//     copy-out, ddrl_sgd_tail.grad_acc), all-reduces them over NVLink peer memory (world > 1), clips and applies Adam; the
+//     CTAs of a policy meet at a barrier before they reload the updated weight image.  The next step's inputs are requested
+//     behind the tail.
+//   * the step is sensitive to CODE SIZE (every warp walks ~4 000 instructions once per ~23 us step, far more than the
+//     32 KB instruction cache holds): issue loops are not unrolled, debug stamps sit behind the DBG template flag.
 //   * FWD = true: forward-only over all rows of each policy (filter normalise in the X split, DiagGaussian sample + logp in
 //     place of the loss) — ddrl_fcnet_forward_tc.
 #include <algorithm>
@@ -1043,8 +1050,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
         write_w2_heads(1);
     } else if (early_out && staged) {
         // [W2, bo) of the flat vector (gW2, gb2 of both branches, gWo: ~3/4 of it) has been staged by the MMA warps (slots 1, 2)
-        // and leaves for global memory while B5(1) is still running; redd[] (per-warp loss sums, written before every warp's
-        // last hand-offs) is visible to warp 0 behind this barrier as well
+        // and leaves for global memory while B5(1) is still running
         asm volatile("bar.sync 6, %0;" ::"n"(T2_NT) : "memory");
         T2_STAMP(46);
         copy_out(o.W2 >> 2, o.bo >> 2, tid, TC_NT);

@@ -1,5 +1,6 @@
 /* Plain-C consumer of include/ddrl_b200.h: compiled with gcc -std=c99 and linked against libddrl_b200.so by
  * tests/test_abi.py::test_plain_c_program_links_and_calls_the_library (no Python, no torch, no CUDA headers). */
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -18,5 +19,8 @@ int main(void) {
     int rc = ddrl_fcnet_forward(NULL, NULL, NULL, NULL, 0.0f, 1, 1, 19, 2, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
     printf("badarg %d %s\n", rc, ddrl_last_error());
     printf("sizes %d %d\n", (int)sizeof hp, (int)sizeof tail.peer_x / (int)sizeof tail.peer_x[0]);
+    /* layout of the fused-tail descriptor as a plain-C consumer sees it (the ctypes mirror in ddrl_b200/_lib.py must agree) */
+    printf("tail %d %d %d %d %d\n", (int)sizeof tail, (int)offsetof(ddrl_sgd_tail, lr), (int)offsetof(ddrl_sgd_tail, peer_x),
+           (int)offsetof(ddrl_sgd_tail, ll_ws), (int)offsetof(ddrl_sgd_tail, grad_acc));
     return 0;
 }

@@ -117,3 +117,7 @@ def test_plain_c_program_links_and_calls_the_library(tmp_path):
     assert lines[2] == "graphnet 28869"                  # actor 14 532 + critic 14 337
     assert lines[5].startswith("badarg -1 fcnet_forward:")
     assert lines[6] == "sizes 20 8"
+    # the ctypes mirror of ddrl_sgd_tail (ddrl_b200/_lib.py) has the layout the C compiler gives the header's struct
+    from ddrl_b200._lib import SgdTail
+    assert lines[7] == "tail %d %d %d %d %d" % (ctypes.sizeof(SgdTail), SgdTail.lr.offset, SgdTail.peer_x.offset,
+                                                 SgdTail.ll_ws.offset, SgdTail.grad_acc.offset)

@@ -230,3 +230,36 @@ def test_graphnet_learner_orchestration_with_oracle_mocked_kernels():
                          timeout=900, cwd=root)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
     assert out.stdout.split() == ["iteration", "ok", "learn_on_batch", "ok"]
+
+
+def test_finalize_stats_vectorised_equals_the_per_policy_loop():
+    """`learner.finalize_stats` works on all policies at once (the GPU idles while the host computes it between two
+    iterations); it must return exactly what the per-policy loop it replaced returned — float32 means like RLlib's
+    `_averaged`, same summation order."""
+    from ddrl_b200.config import PPOConfig
+    from ddrl_b200.learner import finalize_stats
+
+    def loop(sums, kl_coeff, cfg, rows):
+        n, out = float(rows), []
+        for p in range(sums.shape[1]):
+            s = sums[:, p, :]
+            pol, kl, vf, ent = s[:, 0] / n, s[:, 1] / n, s[:, 2] / n, s[:, 3] / n
+            total = pol + kl_coeff[p] * kl + cfg.vf_loss_coeff * vf - cfg.entropy_coeff * ent
+            yvar = s[:, 5] / n - (s[:, 4] / n) ** 2
+            dvar = s[:, 7] / n - (s[:, 6] / n) ** 2
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ev = np.maximum(-1.0, 1.0 - dvar / yvar)
+            m = lambda a: float(np.mean(a.astype(np.float32)))      # noqa: E731
+            out.append({"total_loss": m(total), "policy_loss": m(pol), "vf_loss": m(vf), "kl": m(kl), "entropy": m(ent),
+                        "vf_explained_var": m(ev), "cur_kl_coeff": float(np.float32(kl_coeff[p])),
+                        "cur_lr": float(np.float32(cfg.lr)), "entropy_coeff": float(cfg.entropy_coeff)})
+        return out
+
+    rng = np.random.default_rng(5)
+    cfg = PPOConfig(entropy_coeff=0.01)
+    for _ in range(40):
+        nb, P = int(rng.integers(1, 130)), int(rng.integers(1, 7))
+        sums = rng.standard_normal((nb, P, 8)) * 100.0 + 500.0
+        sums[..., 5] = np.abs(sums[..., 5]) * 50.0
+        kl = rng.random(P) + 0.1
+        assert finalize_stats(sums, kl, cfg, 4096.0) == loop(sums, kl, cfg, 4096.0)
