@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
     // ---- once per launch: TMEM, mbarriers, launch-wide state -------------------------------------------------------------
     if (warp == 0) umma::tmem_alloc(tslot, T2_TMEM_COLS);
     if (tid == 0) {      // every MMA warp commits; [4] (byte 32): TMA bulk copies of the LL tail; [5] (byte 40): weight image
-        umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::mbar_init(mbar + 4, 1); umma::mbar_init(mbar + 5, 1); umma::fence_mbar_init();
+        umma::mbar_init(mbar, T2_NMMA); umma::mbar_init(mbar + 1, T2_NMMA); umma::mbar_init(mbar + 4, 1); umma::mbar_init(mbar + 5, 1); umma::mbar_init(mbar + 6, 1); umma::fence_mbar_init();
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -828,13 +828,15 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
                     if (s > 0 && !sgd_wait_weights(a.tail, p, G, s)) { ok = false; if (a.status) atomicOr(a.status, 64); }
                     asm volatile("fence.proxy.async;" ::: "memory");      // acquired generic-proxy writes -> async-proxy (TMA) reads
                     const unsigned char* img_p = a.img + (int64_t)p * I.bytes;
-                    const uint32_t part = (uint32_t)(((I.bytes >> 2) + 15) & ~15);
-                    mbar_expect_tx(imb, (uint32_t)I.bytes);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t off = (uint32_t)k * part;
-                        if (off < (uint32_t)I.bytes) bulk_g2s(sbase + off, img_p + off, min(part, (uint32_t)I.bytes - off), imb);
-                    }
+                    // part A (mbarrier [5]): W1 of both branches and the fp32 block (biases) — all that F1 and the first tanh
+                    // epilogue need; part B ([6]): W2 and WoT, needed from F2 on, land behind F1 and that epilogue
+                    const uint32_t a0 = (uint32_t)iW2_0, f0 = (uint32_t)I.b1c, nb = f0 - a0, hb = ((nb >> 1) + 15u) & ~15u;
+                    mbar_expect_tx(imb, a0 + ((uint32_t)I.bytes - f0));
+                    bulk_g2s(sbase, img_p, a0, imb);
+                    bulk_g2s(sbase + f0, img_p + f0, (uint32_t)I.bytes - f0, imb);
+                    mbar_expect_tx(imb + 8u, nb);
+                    bulk_g2s(sbase + a0, img_p + a0, hb, imb + 8u);
+                    bulk_g2s(sbase + a0 + hb, img_p + a0 + hb, nb - hb, imb + 8u);
                 }
                 __syncwarp();      // lanes 1-31 must not spin on the mbarrier while lane 0 is still polling (divergent try_wait
             }                      // loops delay the other path by 0.5-2 us)
@@ -852,6 +854,7 @@ __global__ void __launch_bounds__(T2_NT, 1) fcnet_train_tc2_kernel(const __grid_
             t2_epi_tanh(tmem + tlane + T2_DACC + 64 * b + 16 * cq, b1c + b * 64 + 16 * cq, 1.f / (TC_SX * TC_SW),
                         sm + sH1(b, 0), sm + sH1(b, 1), row, cq);
             T2_STAMP(5 + 3 * b);
+            if (first && b == 0 && !mbar_wait_parity(sbase + S.bar + 48, img_phase ^ 1u)) ok = false;   // W2 / WoT landed (part B)
             publish();
             T2_STAMP(6 + 3 * b);
         }
